@@ -165,7 +165,8 @@ int cuboid_process_batch_device(cuboid_handle* h, const void* depth_dev, int w, 
 int cuboid_batch_results(cuboid_handle* h, cuboid_frame_result* results, int n_frames);
 /* Parity taps on the most recent batch: copy one frame's intermediate array to the host.
  * what: 0 points(xyzw) 1 voxel key per point(int32) 2 voxels(xyzw) 3 inlier indices(int32)
- *       4 remaining points(xyzw) 5 cluster index list(int32) 6 cluster offsets(int32) */
+ *       4 remaining points(xyzw) 5 cluster index list(int32) 6 cluster offsets(int32) 7 points per voxel(int32)
+ * Only frames of the last resident chunk (the last max_batch frames of the batch) can be fetched. */
 int cuboid_batch_fetch(cuboid_handle* h, int frame, int what, void* out, int cap_bytes, int* n_items);
 
 /* ---- publish side (icp.cpp:179, 55-128) — host arithmetic, kept here so a node does one call -- */

@@ -661,8 +661,8 @@ void icp(const P4* src, int n_src, const P4* tgt, int n_tgt, const KdTree& tree,
     bool guess_is_identity = true;
     if (guess) {
         fin = *guess;
-        const M4 id = m4_identity();
-        guess_is_identity = std::memcmp(&id, guess, sizeof(M4)) == 0;
+        const M4 id = m4_identity(); /* Eigen `guess != Matrix4::Identity()`: coefficient-wise float compare */
+        for (int i = 0; i < 4; ++i) for (int j = 0; j < 4; ++j) if (guess->a[i][j] != id.a[i][j]) guess_is_identity = false;
     }
     if (!guess_is_identity) for (int i = 0; i < n_src; ++i) cur[i] = m4_apply(fin, src[i]);
     const double max_d2 = max_corr_dist * max_corr_dist;

@@ -1,0 +1,861 @@
+// cuboid_cuda.cu — handle, memory and the C ABI of libcuboid_cuda.so (see include/cuboid_cuda.h).
+//
+// Data layout in HBM (per chunk of B frames, everything frame-major with a fixed per-frame stride so
+// every kernel indexes [frame][item] without indirection; P = max points per frame, M = max remainder):
+//   depth   u16   [B][P]     input (or the caller's device pointer)        pts     f32x4 [B][P] survivors, xyzw
+//   keysA/B u64   [B][P]     (sortkey<<32 | point#) ping-pong              vox     f32x4 [B][P] centroids
+//   hist    u32   [B][256][P/2048]  radix digit histograms                  inl*    i32   [B][P] inlier lists
+//   remain  f32x4 [B][P]     non-plane points                              parent.. i32  [B][M] union-find
+//   cur     f32x4 [B][G][M]  ICP working source, corr i32 / cd f32 alike   res     cuboid_frame_result[n_frames]
+// Points are float4 (x,y,z,1) = pcl::PointXYZ's 16-byte layout, so every point access is one 128-bit
+// coalesced load/store.
+#include <cuda_runtime.h>
+
+#include <algorithm>
+#include <cmath>
+#include <cstdio>
+#include <cstdlib>
+#include <cstring>
+#include <random>
+#include <string>
+#include <vector>
+
+#include "cluster.cuh"
+#include "common.cuh"
+#include "cuboid_cuda.h"
+#include "icp.cuh"
+#include "preprocess.cuh"
+#include "ransac.cuh"
+#include "voxel.cuh"
+
+using namespace cuboid;
+
+struct cuboid_handle {
+    cuboid_params p;
+    int device = 0;
+    int P = 0, B = 0, M = 0, KC = 1024;
+    int tilesP = 0, tilesV = 0;
+    cudaStream_t stream = nullptr;
+    cudaEvent_t ev[6] = {};
+    // chunk buffers
+    uint16_t* d_depth = nullptr;
+    unsigned char* d_blob = nullptr; size_t blob_cap = 0;
+    int* d_n_in = nullptr;
+    float4* d_pts = nullptr;
+    unsigned long long *d_keysA = nullptr, *d_keysB = nullptr;
+    int* d_kpp = nullptr;
+    unsigned int* d_hist = nullptr;
+    float4* d_vox = nullptr;
+    int* d_vcount = nullptr;
+    int *d_shuffled = nullptr, *d_inl_pre = nullptr, *d_inl = nullptr;
+    float4* d_remain = nullptr;
+    int *d_parent = nullptr, *d_csize = nullptr, *d_crank = nullptr, *d_idx_sorted = nullptr, *d_offsets = nullptr, *d_roots = nullptr;
+    float4* d_cur = nullptr; int* d_corr = nullptr; float* d_cd = nullptr; IcpOut* d_icp_out = nullptr;
+    size_t icp_scratch_elems = 0; size_t icp_out_elems = 0;
+    FrameScratch* d_scr = nullptr;
+    unsigned long long *d_desc1 = nullptr, *d_desc2 = nullptr;
+    unsigned int* d_ticket = nullptr;
+    cuboid_frame_result* d_res = nullptr; int res_cap = 0;
+    int* d_rng = nullptr; int rng_len = 0;
+    int* d_triplets = nullptr; int triplets_cap = 0;
+    float4* d_tmpl[CUBOID_MAX_TEMPLATES] = {}; int tmpl_n[CUBOID_MAX_TEMPLATES] = {}; int tmpl_pad[CUBOID_MAX_TEMPLATES] = {};
+    float* d_guesses = nullptr; int n_guess = 1; int guess_mode = 0; bool have_guesses = false;
+    int* d_trace_corr = nullptr; float* d_trace_T = nullptr; float4* d_aligned = nullptr;
+    int smem_optin = 0; int icp_resident_pts = 0;
+    int last_chunk_base = 0, last_chunk_frames = 0, last_total_frames = 0;
+    int taps = 1;
+    int64_t launches = 0;
+    float stage_ms[5] = {0, 0, 0, 0, 0};
+    std::string last_error;
+};
+
+namespace {
+
+#define CK(h, call)                                                                                         \
+    do {                                                                                                    \
+        cudaError_t e_ = (call);                                                                            \
+        if (e_ != cudaSuccess) {                                                                            \
+            char buf_[512];                                                                                 \
+            snprintf(buf_, sizeof buf_, "%s:%d %s -> %s", __FILE__, __LINE__, #call, cudaGetErrorString(e_)); \
+            if (h) (h)->last_error = buf_;                                                                  \
+            return CUBOID_E_CUDA;                                                                           \
+        }                                                                                                   \
+    } while (0)
+#define CKS(h, expr)                    \
+    do {                                \
+        int s_ = (expr);                \
+        if (s_ != CUBOID_OK) return s_; \
+    } while (0)
+
+float limit_hi(double mx) { float f = (float)mx; if ((double)f > mx) f = nextafterf(f, -INFINITY); return f; }
+float limit_lo(double mn) { float f = (float)mn; if ((double)f < mn) f = nextafterf(f, INFINITY); return f; }
+float thr_up(double t) { float f = (float)t; if ((double)f < t) f = nextafterf(f, INFINITY); return f; }
+
+template <typename T>
+int dalloc(cuboid_handle* h, T** p, size_t n) {
+    CK(h, cudaMalloc(reinterpret_cast<void**>(p), n * sizeof(T)));
+    return CUBOID_OK;
+}
+
+int validate_params(const cuboid_params* p) {
+    if (!(p->leaf > 0.f) || p->sac_max_iter < 0 || p->n_guess < 1 || p->icp_max_iter < 1) return CUBOID_E_INVALID;
+    if (!(p->sac_prob > 0.0 && p->sac_prob < 1.0)) return CUBOID_E_INVALID;
+    // icp.cpp:175 leaves setMaxCorrespondenceDistance commented out; a distance gate that can actually reject is not built
+    if (!(p->icp_max_corr_dist * p->icp_max_corr_dist >= 3.0e38)) return CUBOID_E_UNSUPPORTED;
+    return CUBOID_OK;
+}
+
+int upload_rng(cuboid_handle* h) {
+    const int len = 3 * (h->p.sac_max_iter * 11 + 2064);
+    std::mt19937 mt(h->p.sac_seed);   // std::mt19937 == boost::mt19937
+    std::vector<int> tab(len);
+    for (int i = 0; i < len; ++i) tab[i] = (int)(mt() >> 1);   // boost::uniform_int<>(0, INT_MAX) over mt19937 (bucket size 2)
+    if (h->d_rng) cudaFree(h->d_rng);
+    h->d_rng = nullptr;
+    CKS(h, dalloc(h, &h->d_rng, (size_t)len));
+    CK(h, cudaMemcpy(h->d_rng, tab.data(), sizeof(int) * len, cudaMemcpyHostToDevice));
+    h->rng_len = len;
+    return CUBOID_OK;
+}
+
+int ensure_icp_scratch(cuboid_handle* h, int frames, int n_guess) {
+    const size_t need = (size_t)frames * n_guess * h->M;
+    if (need > h->icp_scratch_elems) {
+        if (h->d_cur) { cudaFree(h->d_cur); cudaFree(h->d_corr); cudaFree(h->d_cd); }
+        h->d_cur = nullptr; h->d_corr = nullptr; h->d_cd = nullptr; h->icp_scratch_elems = 0;
+        CKS(h, dalloc(h, &h->d_cur, need));
+        CKS(h, dalloc(h, &h->d_corr, need));
+        CKS(h, dalloc(h, &h->d_cd, need));
+        h->icp_scratch_elems = need;
+    }
+    const size_t need_out = (size_t)frames * CUBOID_MAX_CLUSTERS * n_guess;
+    if (need_out > h->icp_out_elems) {
+        if (h->d_icp_out) cudaFree(h->d_icp_out);
+        h->d_icp_out = nullptr; h->icp_out_elems = 0;
+        CKS(h, dalloc(h, &h->d_icp_out, need_out));
+        h->icp_out_elems = need_out;
+    }
+    return CUBOID_OK;
+}
+
+int ensure_results(cuboid_handle* h, int n) {
+    if (n <= h->res_cap) return CUBOID_OK;
+    if (h->d_res) cudaFree(h->d_res);
+    h->d_res = nullptr; h->res_cap = 0;
+    CKS(h, dalloc(h, &h->d_res, (size_t)n));
+    h->res_cap = n;
+    return CUBOID_OK;
+}
+
+struct ChunkIn {
+    const uint16_t* depth = nullptr;   // device, [nf][w*h]
+    int w = 0, hgt = 0;
+    const unsigned char* blob = nullptr; int point_step = 0, xoff = 0, yoff = 0, zoff = 0;   // device blob, frame stride P*point_step
+    int in_stride = 0;                 // inputs per frame
+};
+
+// stage bits: 1 preprocess+voxel, 2 plane, 4 cluster, 8 icp
+int run_chunk(cuboid_handle* h, const ChunkIn& in, int nf, cuboid_frame_result* d_res, int stages, int tmpl_slot,
+              bool skip_pre = false, bool skip_vox = false, bool skip_plane = false, bool skip_cluster = false,
+              const int* d_triplets = nullptr, int n_triplets = 0, const float* guesses_override = nullptr, int n_guess_override = 0,
+              int guess_mode_override = 0, int* trace_corr = nullptr, float* trace_T = nullptr, int cap_trace = 0,
+              float4* aligned = nullptr, bool force_cluster = false) {
+    cudaStream_t st = h->stream;
+    const cuboid_params& p = h->p;
+    CK(h, cudaEventRecord(h->ev[0], st));
+    if ((stages & 1) && !skip_pre) {
+        CK(h, cudaMemsetAsync(d_res, 0, sizeof(cuboid_frame_result) * nf, st));
+        k_init_scratch<<<(nf + 127) / 128, 128, 0, st>>>(h->d_scr, nf);
+        ++h->launches;
+        const int per = in.in_stride;
+        const int tiles = (per + PRE_TILE - 1) / PRE_TILE;
+        CK(h, cudaMemsetAsync(h->d_desc1, 0, sizeof(unsigned long long) * (size_t)nf * h->tilesP, st));
+        CK(h, cudaMemsetAsync(h->d_ticket, 0, sizeof(unsigned int) * 4, st));
+        PreArgs a{};
+        a.depth = in.depth; a.blob = in.blob; a.point_step = in.point_step; a.xoff = in.xoff; a.yoff = in.yoff; a.zoff = in.zoff;
+        a.n_in = in.blob ? h->d_n_in : nullptr;
+        a.w = in.w; a.h = in.hgt; a.P = per;
+        a.fx = p.fx; a.fy = p.fy; a.cx = p.cx; a.cy = p.cy; a.depth_scale = p.depth_scale;
+        a.z_lo = limit_lo(p.pass_z_min); a.z_hi = limit_hi(p.pass_z_max);
+        a.x_lo = limit_lo(p.pass_x_min); a.x_hi = limit_hi(p.pass_x_max);
+        a.pts = h->d_pts; a.res = d_res; a.scr = h->d_scr; a.desc = h->d_desc1; a.ticket = h->d_ticket;
+        a.tiles = tiles; a.n_frames = nf;
+        a.Pout = h->P;
+        if (tiles > h->tilesP) return CUBOID_E_CAPACITY;
+        if (in.blob) k_preprocess<1><<<nf * tiles, PRE_THREADS, 0, st>>>(a);
+        else k_preprocess<0><<<nf * tiles, PRE_THREADS, 0, st>>>(a);
+        ++h->launches;
+        CK(h, cudaGetLastError());
+    }
+    CK(h, cudaEventRecord(h->ev[1], st));
+    if ((stages & 1) && !skip_vox) {
+        VoxArgs v{};
+        v.pts = h->d_pts; v.keysA = h->d_keysA; v.keysB = h->d_keysB; v.kpp = h->taps ? h->d_kpp : nullptr; v.hist = h->d_hist;
+        v.vox = h->d_vox; v.vcount = h->taps ? h->d_vcount : nullptr; v.res = d_res; v.scr = h->d_scr; v.desc = h->d_desc2;
+        v.ticket = h->d_ticket + 1; v.P = h->P; v.tilesP = h->tilesP; v.tilesV = h->tilesV; v.n_frames = nf;
+        v.inv_leaf = 1.0f / p.leaf;
+        CK(h, cudaMemsetAsync(h->d_desc2, 0, sizeof(unsigned long long) * (size_t)nf * h->tilesV, st));
+        k_voxel_empty<<<(nf + 127) / 128, 128, 0, st>>>(v);
+        k_voxel_keys<<<dim3((h->P + 255) / 256, nf), 256, 0, st>>>(v);
+        h->launches += 2;
+        for (int pass = 0; pass < 4; ++pass) {
+            k_sort_hist<<<dim3(h->tilesP, nf), SORT_THREADS, 0, st>>>(v, pass);
+            k_sort_scan<<<nf, 256, 0, st>>>(v, pass);
+            k_sort_scatter<<<dim3(h->tilesP, nf), SORT_THREADS, 0, st>>>(v, pass);
+            h->launches += 3;
+        }
+        k_voxel_reduce<<<nf * h->tilesV, VR_THREADS, 0, st>>>(v);
+        ++h->launches;
+        CK(h, cudaGetLastError());
+    }
+    CK(h, cudaEventRecord(h->ev[2], st));
+    if ((stages & 2) && !skip_plane) {
+        SacArgs s{};
+        s.vox = h->d_vox; s.shuffled = h->d_shuffled; s.rng = h->d_rng; s.rng_len = h->rng_len;
+        s.triplets = d_triplets; s.n_triplets = n_triplets;
+        s.inl_pre = h->d_inl_pre; s.inl = h->d_inl; s.remain = h->d_remain; s.res = d_res; s.scr = h->d_scr; s.P = h->P;
+        s.thr_f = thr_up(p.sac_threshold); s.max_iter = p.sac_max_iter; s.log_prob = std::log(1.0 - p.sac_prob);
+        s.refine = p.sac_refine; s.negative = p.extract_negative;
+        s.use_z2 = p.use_pass_z2; s.z2_lo = limit_lo(p.pass_z2_min); s.z2_hi = limit_hi(p.pass_z2_max);
+        s.cap_remain = h->M;
+        k_sac_plane<<<nf, SAC_THREADS, sizeof(SacShared), st>>>(s);
+        ++h->launches;
+        CK(h, cudaGetLastError());
+    }
+    CK(h, cudaEventRecord(h->ev[3], st));
+    if ((stages & 4) && !skip_cluster) {
+        CluArgs c{};
+        c.remain = h->d_remain; c.parent = h->d_parent; c.csize = h->d_csize; c.crank = h->d_crank; c.idx_sorted = h->d_idx_sorted;
+        c.offsets = h->d_offsets; c.roots = h->d_roots; c.res = d_res; c.P = h->P; c.M = h->M; c.KC = h->KC;
+        c.r2 = (float)(p.cluster_tol * p.cluster_tol); c.min_size = p.cluster_min; c.max_size = p.cluster_max;
+        c.use_cluster = force_cluster ? 1 : p.use_cluster;
+        k_cluster<<<nf, CLU_THREADS, 0, st>>>(c);
+        ++h->launches;
+        CK(h, cudaGetLastError());
+    }
+    CK(h, cudaEventRecord(h->ev[4], st));
+    if (stages & 8) {
+        if (tmpl_slot < 0 || tmpl_slot >= CUBOID_MAX_TEMPLATES || !h->d_tmpl[tmpl_slot]) return CUBOID_E_NO_TEMPLATE;
+        const float* gs = guesses_override ? guesses_override : (h->have_guesses ? h->d_guesses : nullptr);
+        const int ng = guesses_override ? n_guess_override : (h->have_guesses ? h->n_guess : 1);
+        const int gm = guesses_override ? guess_mode_override : h->guess_mode;
+        CKS(h, ensure_icp_scratch(h, std::max(nf, 1), ng));
+        IcpArgs a{};
+        a.remain = h->d_remain; a.idx_sorted = h->d_idx_sorted; a.offsets = h->d_offsets;
+        a.tmpl = h->d_tmpl[tmpl_slot]; a.T = h->tmpl_n[tmpl_slot]; a.Tpad = h->tmpl_pad[tmpl_slot];
+        a.guesses = gs; a.n_guess = ng; a.guess_mode = gm;
+        a.cur = h->d_cur; a.corr = h->d_corr; a.cd = h->d_cd; a.out = h->d_icp_out; a.res = d_res;
+        a.P = h->P; a.M = h->M; a.KC = h->KC; a.max_iter = p.icp_max_iter;
+        a.rot_thr = 1.0 - p.icp_tf_eps; a.trans_thr = p.icp_tf_eps; a.rel_mse = p.icp_rel_mse; a.abs_thr = 1e-12;
+        a.tmpl_resident_pts = h->icp_resident_pts;
+        a.corr_trace = trace_corr; a.T_trace = trace_T; a.cap_trace = cap_trace; a.aligned_out = nullptr;
+        const size_t dyn = (size_t)std::min(a.Tpad, h->icp_resident_pts) * 16;
+        k_icp<<<dim3(ng, CUBOID_MAX_CLUSTERS, nf), ICP_THREADS, dyn, st>>>(a);
+        const int tot = nf * CUBOID_MAX_CLUSTERS;
+        k_icp_select<<<(tot + 127) / 128, 128, 0, st>>>(h->d_icp_out, d_res, nf, ng, p.icp_fitness_gate, h->d_cur, h->M, h->d_offsets,
+                                                     h->KC, aligned);
+        h->launches += 2;
+        CK(h, cudaGetLastError());
+    }
+    CK(h, cudaEventRecord(h->ev[5], st));
+    return CUBOID_OK;
+}
+
+int accumulate_stage_ms(cuboid_handle* h) {
+    for (int s = 0; s < 5; ++s) {
+        float ms = 0.f;
+        CK(h, cudaEventElapsedTime(&ms, h->ev[s], h->ev[s + 1]));
+        h->stage_ms[s] += ms;
+    }
+    return CUBOID_OK;
+}
+
+__global__ void k_set_counts(cuboid_frame_result* res, int n_points, int n_voxels, int n_remain, int n_clusters, int* offsets,
+                             int* idx_sorted, int identity_n) {
+    const int i = blockIdx.x * blockDim.x + threadIdx.x;
+    if (i == 0) {
+        if (n_points >= 0) res[0].n_points = n_points;
+        if (n_voxels >= 0) res[0].n_voxels = n_voxels;
+        if (n_remain >= 0) res[0].n_remain = n_remain;
+        if (n_clusters >= 0) { res[0].n_clusters = n_clusters; res[0].cluster[0].size = identity_n; offsets[0] = 0; offsets[1] = identity_n; }
+    }
+    if (idx_sorted && i < identity_n) idx_sorted[i] = i;
+}
+
+// ---- FP32 peak micro-benchmarks (roofline denominator for the ICP distance kernel) ----
+__global__ void k_peak_unfused(float* out, int iters, float a, float b) {
+    float x[8];
+#pragma unroll
+    for (int k = 0; k < 8; ++k) x[k] = (float)(threadIdx.x + k) * 1e-3f;
+    for (int i = 0; i < iters; ++i) {
+#pragma unroll
+        for (int k = 0; k < 8; ++k) { x[k] = x[k] * a; x[k] = x[k] + b; }
+    }
+    float s = 0.f;
+#pragma unroll
+    for (int k = 0; k < 8; ++k) s += x[k];
+    if (s == 123.456f) out[0] = s;
+}
+__global__ void k_peak_ffma(float* out, int iters, float a, float b) {
+    float x[8];
+#pragma unroll
+    for (int k = 0; k < 8; ++k) x[k] = (float)(threadIdx.x + k) * 1e-3f;
+    for (int i = 0; i < iters; ++i) {
+#pragma unroll
+        for (int k = 0; k < 8; ++k) { x[k] = __fmaf_rn(x[k], a, b); x[k] = __fmaf_rn(x[k], a, b); }
+    }
+    float s = 0.f;
+#pragma unroll
+    for (int k = 0; k < 8; ++k) s += x[k];
+    if (s == 123.456f) out[0] = s;
+}
+
+}  // namespace
+
+extern "C" {
+
+void cuboid_default_params(cuboid_params* p) {
+    std::memset(p, 0, sizeof(*p));
+    p->fx = 384.0898742675781f; p->fy = 384.0898742675781f; p->cx = 322.4656677246094f; p->cy = 240.64073181152344f;
+    p->depth_scale = 0.001f;
+    p->pass_z_min = 0.0; p->pass_z_max = 0.9; p->pass_x_min = -0.2; p->pass_x_max = 0.2;
+    p->pass_z2_min = 0.0; p->pass_z2_max = 0.75; p->use_pass_z2 = 0;
+    p->leaf = 0.005f;
+    p->sac_threshold = 0.015; p->sac_max_iter = 1000; p->sac_seed = 12345u; p->sac_prob = 0.99; p->sac_refine = 1;
+    p->extract_negative = 1;
+    p->cluster_tol = 0.02; p->cluster_min = 200; p->cluster_max = 25000; p->use_cluster = 1;
+    p->icp_max_iter = 5000; p->icp_tf_eps = 1e-9; p->icp_rel_mse = 0.0004; p->icp_fitness_gate = 0.0004;
+    p->icp_max_corr_dist = std::sqrt(1.7976931348623157e308);
+    p->n_guess = 1; p->guess_mode = 0;
+}
+
+int cuboid_create(cuboid_handle** out, const cuboid_params* p, int device, int max_points, int max_batch) {
+    if (!out || !p || max_points < 1 || max_batch < 1) return CUBOID_E_INVALID;
+    *out = nullptr;
+    const int vs = validate_params(p);
+    if (vs != CUBOID_OK) return vs;
+    int ndev = 0;
+    if (cudaGetDeviceCount(&ndev) != cudaSuccess || ndev <= 0 || device < 0 || device >= ndev) return CUBOID_E_NO_DEVICE;
+    if (cudaSetDevice(device) != cudaSuccess) return CUBOID_E_NO_DEVICE;
+    cuboid_handle* h = new cuboid_handle();
+    h->p = *p; h->device = device;
+    h->P = (max_points + 7) & ~7;
+    h->B = max_batch;
+    const char* envm = std::getenv("CUBOID_MAX_REMAIN");
+    h->M = std::min(h->P, envm ? std::max(1024, atoi(envm)) : 65536);
+    h->tilesP = (h->P + PRE_TILE - 1) / PRE_TILE;
+    h->tilesV = (h->P + VR_TILE - 1) / VR_TILE;
+    const char* envt = std::getenv("CUBOID_TAPS");
+    h->taps = envt ? atoi(envt) : 1;
+    auto fail = [&](int code) { cuboid_destroy(h); return code; };
+#define CA(expr) do { int s_ = (expr); if (s_ != CUBOID_OK) { std::string e = h->last_error; fprintf(stderr, "cuboid_create: %s\n", e.c_str()); return fail(s_); } } while (0)
+    if (cudaStreamCreateWithFlags(&h->stream, cudaStreamNonBlocking) != cudaSuccess) return fail(CUBOID_E_CUDA);
+    for (auto& e : h->ev) if (cudaEventCreate(&e) != cudaSuccess) return fail(CUBOID_E_CUDA);
+    const size_t BP = (size_t)h->B * h->P, BM = (size_t)h->B * h->M;
+    CA(dalloc(h, &h->d_depth, BP));
+    CA(dalloc(h, &h->d_n_in, (size_t)h->B));
+    CA(dalloc(h, &h->d_pts, BP));
+    CA(dalloc(h, &h->d_keysA, BP));
+    CA(dalloc(h, &h->d_keysB, BP));
+    CA(dalloc(h, &h->d_kpp, BP));
+    CA(dalloc(h, &h->d_hist, (size_t)h->B * 256 * h->tilesP));
+    CA(dalloc(h, &h->d_vox, BP));
+    CA(dalloc(h, &h->d_vcount, BP));
+    CA(dalloc(h, &h->d_shuffled, BP));
+    CA(dalloc(h, &h->d_inl_pre, BP));
+    CA(dalloc(h, &h->d_inl, BP));
+    CA(dalloc(h, &h->d_remain, BP));
+    CA(dalloc(h, &h->d_parent, BM));
+    CA(dalloc(h, &h->d_csize, BM));
+    CA(dalloc(h, &h->d_crank, BM));
+    CA(dalloc(h, &h->d_idx_sorted, BM));
+    CA(dalloc(h, &h->d_offsets, (size_t)h->B * (h->KC + 1)));
+    CA(dalloc(h, &h->d_roots, (size_t)h->B * h->KC));
+    CA(dalloc(h, &h->d_scr, (size_t)h->B));
+    CA(dalloc(h, &h->d_desc1, (size_t)h->B * h->tilesP));
+    CA(dalloc(h, &h->d_desc2, (size_t)h->B * h->tilesV));
+    CA(dalloc(h, &h->d_ticket, (size_t)4));
+    CA(ensure_results(h, h->B));
+    CA(upload_rng(h));
+    CA(ensure_icp_scratch(h, h->B, std::max(1, (int)p->n_guess)));
+    cudaDeviceGetAttribute(&h->smem_optin, cudaDevAttrMaxSharedMemoryPerBlockOptin, device);
+    h->icp_resident_pts = ((h->smem_optin - 6144) / 16 / ICP_CHUNK) * ICP_CHUNK;
+    if (cudaFuncSetAttribute(k_icp, cudaFuncAttributeMaxDynamicSharedMemorySize, h->icp_resident_pts * 16) != cudaSuccess) return fail(CUBOID_E_CUDA);
+    if (cudaFuncSetAttribute(k_sac_plane, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)sizeof(SacShared)) != cudaSuccess) return fail(CUBOID_E_CUDA);
+#undef CA
+    *out = h;
+    return CUBOID_OK;
+}
+
+int cuboid_destroy(cuboid_handle* h) {
+    if (!h) return CUBOID_E_INVALID;
+    cudaSetDevice(h->device);
+    if (h->stream) cudaStreamSynchronize(h->stream);
+    void* ptrs[] = {h->d_depth, h->d_blob, h->d_n_in, h->d_pts, h->d_keysA, h->d_keysB, h->d_kpp, h->d_hist, h->d_vox, h->d_vcount, h->d_shuffled,
+                    h->d_inl_pre, h->d_inl, h->d_remain, h->d_parent, h->d_csize, h->d_crank, h->d_idx_sorted, h->d_offsets, h->d_roots,
+                    h->d_cur, h->d_corr, h->d_cd, h->d_icp_out, h->d_scr, h->d_desc1, h->d_desc2, h->d_ticket, h->d_res, h->d_rng,
+                    h->d_triplets, h->d_guesses, h->d_trace_corr, h->d_trace_T, h->d_aligned};
+    for (void* q : ptrs) if (q) cudaFree(q);
+    for (auto& t : h->d_tmpl) if (t) cudaFree(t);
+    for (auto& e : h->ev) if (e) cudaEventDestroy(e);
+    if (h->stream) cudaStreamDestroy(h->stream);
+    delete h;
+    return CUBOID_OK;
+}
+
+int cuboid_set_params(cuboid_handle* h, const cuboid_params* p) {
+    if (!h || !p) return CUBOID_E_INVALID;
+    const int vs = validate_params(p);
+    if (vs != CUBOID_OK) return vs;
+    cudaSetDevice(h->device);
+    const bool rng_changed = p->sac_seed != h->p.sac_seed || p->sac_max_iter != h->p.sac_max_iter;
+    h->p = *p;
+    if (rng_changed) CKS(h, upload_rng(h));
+    return CUBOID_OK;
+}
+
+int cuboid_set_template(cuboid_handle* h, int slot, const float* xyz, int stride_bytes, int n) {
+    if (!h || slot < 0 || slot >= CUBOID_MAX_TEMPLATES || !xyz || n < 1 || stride_bytes < 12) return CUBOID_E_INVALID;
+    cudaSetDevice(h->device);
+    const int pad = ((n + ICP_CHUNK - 1) / ICP_CHUNK) * ICP_CHUNK;
+    std::vector<float4> host(pad);
+    const unsigned char* b = reinterpret_cast<const unsigned char*>(xyz);
+    for (int i = 0; i < n; ++i) {
+        float v[3];
+        std::memcpy(v, b + (size_t)i * stride_bytes, 12);
+        host[i] = make_float4(v[0], v[1], v[2], 1.0f);
+    }
+    // far sentinels: their distance is huge but finite, so they never win and never produce NaN
+    for (int i = n; i < pad; ++i) host[i] = make_float4(1.0e18f, 1.0e18f, 1.0e18f, 1.0f);
+    if (h->d_tmpl[slot]) { cudaFree(h->d_tmpl[slot]); h->d_tmpl[slot] = nullptr; }
+    CKS(h, dalloc(h, &h->d_tmpl[slot], (size_t)pad));
+    CK(h, cudaMemcpy(h->d_tmpl[slot], host.data(), sizeof(float4) * pad, cudaMemcpyHostToDevice));
+    h->tmpl_n[slot] = n; h->tmpl_pad[slot] = pad;
+    return CUBOID_OK;
+}
+
+int cuboid_set_guesses(cuboid_handle* h, const float* guesses, int n_guess, int guess_mode) {
+    if (!h || n_guess < 1 || (guess_mode != 0 && guess_mode != 1)) return CUBOID_E_INVALID;
+    cudaSetDevice(h->device);
+    if (h->d_guesses) { cudaFree(h->d_guesses); h->d_guesses = nullptr; }
+    h->have_guesses = false; h->n_guess = 1; h->guess_mode = 0;
+    if (!guesses) return CUBOID_OK;
+    const size_t per = guess_mode == 0 ? 16 : 9;
+    CKS(h, dalloc(h, &h->d_guesses, per * n_guess));
+    CK(h, cudaMemcpy(h->d_guesses, guesses, sizeof(float) * per * n_guess, cudaMemcpyHostToDevice));
+    h->have_guesses = true; h->n_guess = n_guess; h->guess_mode = guess_mode;
+    return CUBOID_OK;
+}
+
+int cuboid_unproject(cuboid_handle* h, const uint16_t* depth, int w, int hgt, float* xyzw_out, int cap, int* n_out) {
+    if (!h || !depth || !xyzw_out || w < 1 || hgt < 1) return CUBOID_E_INVALID;
+    const int n = w * hgt;
+    if (n > h->P || cap < n) return CUBOID_E_CAPACITY;
+    cudaSetDevice(h->device);
+    CK(h, cudaMemcpyAsync(h->d_depth, depth, sizeof(uint16_t) * n, cudaMemcpyHostToDevice, h->stream));
+    k_unproject_all<<<(n + 255) / 256, 256, 0, h->stream>>>(h->d_depth, w, n, h->p.fx, h->p.fy, h->p.cx, h->p.cy, h->p.depth_scale, h->d_pts);
+    ++h->launches;
+    CK(h, cudaMemcpyAsync(xyzw_out, h->d_pts, sizeof(float4) * n, cudaMemcpyDeviceToHost, h->stream));
+    CK(h, cudaStreamSynchronize(h->stream));
+    if (n_out) *n_out = n;
+    return CUBOID_OK;
+}
+
+static int upload_blob(cuboid_handle* h, const void* pts, int point_step, int n) {
+    const size_t bytes = (size_t)n * point_step;
+    if (bytes > h->blob_cap) {
+        if (h->d_blob) cudaFree(h->d_blob);
+        h->d_blob = nullptr; h->blob_cap = 0;
+        const size_t cap = std::max(bytes, (size_t)h->P * 16);
+        CK(h, cudaMalloc(reinterpret_cast<void**>(&h->d_blob), cap));
+        h->blob_cap = cap;
+    }
+    CK(h, cudaMemcpyAsync(h->d_blob, pts, bytes, cudaMemcpyHostToDevice, h->stream));
+    CK(h, cudaMemcpyAsync(h->d_n_in, &n, sizeof(int), cudaMemcpyHostToDevice, h->stream));
+    return CUBOID_OK;
+}
+
+int cuboid_preprocess(cuboid_handle* h, const void* pts, int point_step, int xoff, int yoff, int zoff, int n, float* vox_xyzw_out,
+                      int cap, int* n_vox, int32_t* key_per_point_out, int* n_pass) {
+    if (!h || (!pts && n > 0) || n < 0 || point_step < 12 || (point_step & 3) || (xoff & 3) || (yoff & 3) || (zoff & 3)) return CUBOID_E_INVALID;
+    if (n > h->P) return CUBOID_E_CAPACITY;
+    cudaSetDevice(h->device);
+    const int saved_taps = h->taps;
+    h->taps = 1;
+    CKS(h, upload_blob(h, pts, point_step, n));
+    ChunkIn in;
+    in.blob = h->d_blob; in.point_step = point_step; in.xoff = xoff; in.yoff = yoff; in.zoff = zoff; in.in_stride = h->P;
+    const int st = run_chunk(h, in, 1, h->d_res, 1, 0);
+    h->taps = saved_taps;
+    if (st != CUBOID_OK) return st;
+    cuboid_frame_result r;
+    CK(h, cudaMemcpyAsync(&r, h->d_res, sizeof r, cudaMemcpyDeviceToHost, h->stream));
+    CK(h, cudaStreamSynchronize(h->stream));
+    h->last_chunk_base = 0; h->last_chunk_frames = 1; h->last_total_frames = 1;
+    if (n_vox) *n_vox = r.n_voxels;
+    if (n_pass) *n_pass = r.n_points;
+    if (vox_xyzw_out) {
+        if (cap < r.n_voxels) return CUBOID_E_CAPACITY;
+        CK(h, cudaMemcpy(vox_xyzw_out, h->d_vox, sizeof(float4) * r.n_voxels, cudaMemcpyDeviceToHost));
+    }
+    if (key_per_point_out) CK(h, cudaMemcpy(key_per_point_out, h->d_kpp, sizeof(int) * r.n_points, cudaMemcpyDeviceToHost));
+    return CUBOID_OK;
+}
+
+int cuboid_segment_plane(cuboid_handle* h, const float* xyzw, int n, const int32_t* triplets, int n_triplets, float coeff_out[4],
+                         int32_t* inlier_idx_out, int* n_inl, int32_t* inlier_pre_out, int* n_inl_pre, float* remain_xyzw_out,
+                         int* n_remain, int* iters_run, int* plane_found) {
+    if (!h || (!xyzw && n > 0) || n < 0) return CUBOID_E_INVALID;
+    if (n > h->P) return CUBOID_E_CAPACITY;
+    cudaSetDevice(h->device);
+    CK(h, cudaMemsetAsync(h->d_res, 0, sizeof(cuboid_frame_result), h->stream));
+    if (n) CK(h, cudaMemcpyAsync(h->d_vox, xyzw, sizeof(float4) * n, cudaMemcpyHostToDevice, h->stream));
+    k_set_counts<<<1, 32, 0, h->stream>>>(h->d_res, -1, n, -1, -1, nullptr, nullptr, 0);
+    ++h->launches;
+    const int* dtrip = nullptr;
+    if (triplets && n_triplets > 0) {
+        if (n_triplets > h->triplets_cap) {
+            if (h->d_triplets) cudaFree(h->d_triplets);
+            h->d_triplets = nullptr; h->triplets_cap = 0;
+            CKS(h, dalloc(h, &h->d_triplets, (size_t)3 * n_triplets));
+            h->triplets_cap = n_triplets;
+        }
+        CK(h, cudaMemcpyAsync(h->d_triplets, triplets, sizeof(int) * 3 * n_triplets, cudaMemcpyHostToDevice, h->stream));
+        dtrip = h->d_triplets;
+    }
+    ChunkIn in;
+    CKS(h, run_chunk(h, in, 1, h->d_res, 2, 0, true, true, false, true, dtrip, n_triplets));
+    cuboid_frame_result r;
+    CK(h, cudaMemcpyAsync(&r, h->d_res, sizeof r, cudaMemcpyDeviceToHost, h->stream));
+    CK(h, cudaStreamSynchronize(h->stream));
+    h->last_chunk_base = 0; h->last_chunk_frames = 1; h->last_total_frames = 1;
+    if (coeff_out) std::memcpy(coeff_out, r.plane_coeff, 16);
+    if (n_inl) *n_inl = r.n_inliers;
+    if (n_inl_pre) *n_inl_pre = r.n_inliers_pre;
+    if (n_remain) *n_remain = r.n_remain;
+    if (iters_run) *iters_run = r.sac_iterations;
+    if (plane_found) *plane_found = r.plane_found;
+    if (inlier_idx_out && r.n_inliers) CK(h, cudaMemcpy(inlier_idx_out, h->d_inl, sizeof(int) * r.n_inliers, cudaMemcpyDeviceToHost));
+    if (inlier_pre_out && r.n_inliers_pre) CK(h, cudaMemcpy(inlier_pre_out, h->d_inl_pre, sizeof(int) * r.n_inliers_pre, cudaMemcpyDeviceToHost));
+    if (remain_xyzw_out && r.n_remain) CK(h, cudaMemcpy(remain_xyzw_out, h->d_remain, sizeof(float4) * r.n_remain, cudaMemcpyDeviceToHost));
+    return CUBOID_OK;
+}
+
+int cuboid_cluster(cuboid_handle* h, const float* xyzw, int n, int32_t* idx_sorted_out, int32_t* offsets_out, int cap_clusters,
+                   int* n_clusters) {
+    if (!h || (!xyzw && n > 0) || n < 0 || !n_clusters) return CUBOID_E_INVALID;
+    if (n > h->M) return CUBOID_E_CAPACITY;
+    cudaSetDevice(h->device);
+    CK(h, cudaMemsetAsync(h->d_res, 0, sizeof(cuboid_frame_result), h->stream));
+    if (n) CK(h, cudaMemcpyAsync(h->d_remain, xyzw, sizeof(float4) * n, cudaMemcpyHostToDevice, h->stream));
+    k_set_counts<<<1, 32, 0, h->stream>>>(h->d_res, -1, -1, n, -1, nullptr, nullptr, 0);
+    ++h->launches;
+    ChunkIn in;
+    CKS(h, run_chunk(h, in, 1, h->d_res, 4, 0, true, true, true, false, nullptr, 0, nullptr, 0, 0, nullptr, nullptr, 0, nullptr, true));
+    cuboid_frame_result r;
+    CK(h, cudaMemcpyAsync(&r, h->d_res, sizeof r, cudaMemcpyDeviceToHost, h->stream));
+    CK(h, cudaStreamSynchronize(h->stream));
+    h->last_chunk_base = 0; h->last_chunk_frames = 1; h->last_total_frames = 1;
+    *n_clusters = r.n_clusters;
+    if (r.n_clusters > cap_clusters) return CUBOID_E_CAPACITY;
+    if (offsets_out) CK(h, cudaMemcpy(offsets_out, h->d_offsets, sizeof(int) * (r.n_clusters + 1), cudaMemcpyDeviceToHost));
+    if (idx_sorted_out && r.n_clusters > 0) {
+        int total = 0;
+        CK(h, cudaMemcpy(&total, h->d_offsets + r.n_clusters, sizeof(int), cudaMemcpyDeviceToHost));
+        CK(h, cudaMemcpy(idx_sorted_out, h->d_idx_sorted, sizeof(int) * total, cudaMemcpyDeviceToHost));
+    }
+    return CUBOID_OK;
+}
+
+int cuboid_icp(cuboid_handle* h, const float* src_xyzw, int n_src, int tmpl_slot, const float* guesses_4x4, int n_guess,
+               float best_T_out[16], double* fitness_out, int* converged, int* iters, int* state, int* best_guess,
+               float* aligned_xyzw_out, int32_t* corr_trace, float* T_trace, int cap_trace_iters, uint64_t* corr_hash) {
+    if (!h || (!src_xyzw && n_src > 0) || n_src < 0 || n_guess < 1) return CUBOID_E_INVALID;
+    if (n_src > h->M) return CUBOID_E_CAPACITY;
+    if (tmpl_slot < 0 || tmpl_slot >= CUBOID_MAX_TEMPLATES || !h->d_tmpl[tmpl_slot]) return CUBOID_E_NO_TEMPLATE;
+    cudaSetDevice(h->device);
+    CK(h, cudaMemsetAsync(h->d_res, 0, sizeof(cuboid_frame_result), h->stream));
+    if (n_src) CK(h, cudaMemcpyAsync(h->d_remain, src_xyzw, sizeof(float4) * n_src, cudaMemcpyHostToDevice, h->stream));
+    k_set_counts<<<(std::max(n_src, 1) + 255) / 256, 256, 0, h->stream>>>(h->d_res, -1, -1, n_src, n_src > 0 ? 1 : 0, h->d_offsets, h->d_idx_sorted, n_src);
+    ++h->launches;
+    float* dg = nullptr;
+    if (guesses_4x4) {
+        CK(h, cudaMalloc(reinterpret_cast<void**>(&dg), sizeof(float) * 16 * n_guess));
+        CK(h, cudaMemcpyAsync(dg, guesses_4x4, sizeof(float) * 16 * n_guess, cudaMemcpyHostToDevice, h->stream));
+    } else {
+        n_guess = 1;
+    }
+    int* dct = nullptr; float* dtt = nullptr; float4* dal = nullptr;
+    if (corr_trace && cap_trace_iters > 0 && n_src > 0) {
+        CK(h, cudaMalloc(reinterpret_cast<void**>(&dct), sizeof(int) * (size_t)cap_trace_iters * n_src));
+        CK(h, cudaMemsetAsync(dct, 0xff, sizeof(int) * (size_t)cap_trace_iters * n_src, h->stream));
+        CK(h, cudaMalloc(reinterpret_cast<void**>(&dtt), sizeof(float) * 16 * cap_trace_iters));
+        CK(h, cudaMemsetAsync(dtt, 0, sizeof(float) * 16 * cap_trace_iters, h->stream));
+    }
+    if (aligned_xyzw_out && n_src > 0) CK(h, cudaMalloc(reinterpret_cast<void**>(&dal), sizeof(float4) * n_src));
+    ChunkIn in;
+    // with no guesses the kernel must still see "no guess table": pass override only when present
+    const int st = run_chunk(h, in, 1, h->d_res, 8, tmpl_slot, true, true, true, true, nullptr, 0, dg, n_guess, 0, dct, dtt, cap_trace_iters, dal);
+    int rc = st;
+    cuboid_frame_result r;
+    std::memset(&r, 0, sizeof r);
+    if (rc == CUBOID_OK) {
+        if (cudaMemcpyAsync(&r, h->d_res, sizeof r, cudaMemcpyDeviceToHost, h->stream) != cudaSuccess) rc = CUBOID_E_CUDA;
+        if (cudaStreamSynchronize(h->stream) != cudaSuccess) { rc = CUBOID_E_CUDA; h->last_error = cudaGetErrorString(cudaGetLastError()); }
+    }
+    if (rc == CUBOID_OK) {
+        const cuboid_cluster_result& c = r.cluster[0];
+        if (best_T_out) std::memcpy(best_T_out, c.T, 64);
+        if (n_src == 0 && best_T_out) { for (int k = 0; k < 16; ++k) best_T_out[k] = (k % 5 == 0) ? 1.f : 0.f; }
+        if (fitness_out) *fitness_out = n_src > 0 ? c.fitness : 1.7976931348623157e308;
+        if (converged) *converged = c.converged;
+        if (iters) *iters = c.iterations;
+        if (state) *state = c.state;
+        if (best_guess) *best_guess = c.best_guess;
+        if (corr_hash) *corr_hash = c.corr_hash;
+        if (dct) {
+            cudaMemcpy(corr_trace, dct, sizeof(int) * (size_t)cap_trace_iters * n_src, cudaMemcpyDeviceToHost);
+            if (T_trace) cudaMemcpy(T_trace, dtt, sizeof(float) * 16 * cap_trace_iters, cudaMemcpyDeviceToHost);
+        }
+        if (dal) cudaMemcpy(aligned_xyzw_out, dal, sizeof(float4) * n_src, cudaMemcpyDeviceToHost);
+    }
+    if (dg) cudaFree(dg);
+    if (dct) cudaFree(dct);
+    if (dtt) cudaFree(dtt);
+    if (dal) cudaFree(dal);
+    h->last_chunk_base = 0; h->last_chunk_frames = 1; h->last_total_frames = 1;
+    return rc;
+}
+
+int cuboid_process_cloud(cuboid_handle* h, const void* pts, int point_step, int xoff, int yoff, int zoff, int n, int tmpl_slot,
+                         cuboid_frame_result* result) {
+    if (!h || (!pts && n > 0) || n < 0 || !result || point_step < 12 || (point_step & 3) || (xoff & 3) || (yoff & 3) || (zoff & 3)) return CUBOID_E_INVALID;
+    if (n > h->P) return CUBOID_E_CAPACITY;
+    cudaSetDevice(h->device);
+    CKS(h, upload_blob(h, pts, point_step, n));
+    ChunkIn in;
+    in.blob = h->d_blob; in.point_step = point_step; in.xoff = xoff; in.yoff = yoff; in.zoff = zoff; in.in_stride = h->P;
+    const bool have_t = tmpl_slot >= 0 && tmpl_slot < CUBOID_MAX_TEMPLATES && h->d_tmpl[tmpl_slot];
+    CKS(h, run_chunk(h, in, 1, h->d_res, have_t ? 15 : 7, tmpl_slot));
+    CK(h, cudaMemcpyAsync(result, h->d_res, sizeof(cuboid_frame_result), cudaMemcpyDeviceToHost, h->stream));
+    CK(h, cudaStreamSynchronize(h->stream));
+    h->last_chunk_base = 0; h->last_chunk_frames = 1; h->last_total_frames = 1;
+    return CUBOID_OK;
+}
+
+static int process_frames(cuboid_handle* h, const uint16_t* depth, bool on_device, int w, int hgt, int n_frames, int tmpl_slot, int stages) {
+    if (!h || !depth || w < 1 || hgt < 1 || n_frames < 1) return CUBOID_E_INVALID;
+    const int per = w * hgt;
+    if (per > h->P) return CUBOID_E_CAPACITY;
+    if ((stages & 8) && (tmpl_slot < 0 || tmpl_slot >= CUBOID_MAX_TEMPLATES || !h->d_tmpl[tmpl_slot])) return CUBOID_E_NO_TEMPLATE;
+    cudaSetDevice(h->device);
+    CKS(h, ensure_results(h, n_frames));
+    for (float& m : h->stage_ms) m = 0.f;
+    for (int base = 0; base < n_frames; base += h->B) {
+        const int nf = std::min(h->B, n_frames - base);
+        ChunkIn in;
+        in.w = w; in.hgt = hgt; in.in_stride = per;
+        if (on_device) {
+            in.depth = depth + (size_t)base * per;
+        } else {
+            CK(h, cudaMemcpyAsync(h->d_depth, depth + (size_t)base * per, sizeof(uint16_t) * (size_t)nf * per, cudaMemcpyHostToDevice, h->stream));
+            in.depth = h->d_depth;
+        }
+        CKS(h, run_chunk(h, in, nf, h->d_res + base, stages, tmpl_slot));
+        if (base + nf < n_frames || true) {
+            CK(h, cudaStreamSynchronize(h->stream));   // chunk buffers are reused by the next chunk's events/timers
+            CKS(h, accumulate_stage_ms(h));
+        }
+        h->last_chunk_base = base; h->last_chunk_frames = nf;
+    }
+    h->last_total_frames = n_frames;
+    return CUBOID_OK;
+}
+
+int cuboid_process_batch(cuboid_handle* h, const uint16_t* depth, int w, int hgt, int n_frames, int tmpl_slot, cuboid_frame_result* results) {
+    if (!results) return CUBOID_E_INVALID;
+    const bool have_t = h && tmpl_slot >= 0 && tmpl_slot < CUBOID_MAX_TEMPLATES && h->d_tmpl[tmpl_slot];
+    CKS(h, process_frames(h, depth, false, w, hgt, n_frames, tmpl_slot, have_t ? 15 : 7));
+    CK(h, cudaMemcpyAsync(results, h->d_res, sizeof(cuboid_frame_result) * n_frames, cudaMemcpyDeviceToHost, h->stream));
+    CK(h, cudaStreamSynchronize(h->stream));
+    return CUBOID_OK;
+}
+
+int cuboid_process_batch_device(cuboid_handle* h, const void* depth_dev, int w, int hgt, int n_frames, int tmpl_slot, int stages) {
+    if (stages <= 0 || stages > 15) return CUBOID_E_INVALID;
+    int full = 0;
+    if (stages & 8) full = 15; else if (stages & 4) full = 7; else if (stages & 2) full = 3; else full = 1;
+    return process_frames(h, static_cast<const uint16_t*>(depth_dev), true, w, hgt, n_frames, tmpl_slot, full);
+}
+
+int cuboid_batch_results(cuboid_handle* h, cuboid_frame_result* results, int n_frames) {
+    if (!h || !results || n_frames < 1 || n_frames > h->last_total_frames) return CUBOID_E_INVALID;
+    cudaSetDevice(h->device);
+    CK(h, cudaMemcpyAsync(results, h->d_res, sizeof(cuboid_frame_result) * n_frames, cudaMemcpyDeviceToHost, h->stream));
+    CK(h, cudaStreamSynchronize(h->stream));
+    return CUBOID_OK;
+}
+
+int cuboid_batch_fetch(cuboid_handle* h, int frame, int what, void* out, int cap_bytes, int* n_items) {
+    if (!h || !out || !n_items) return CUBOID_E_INVALID;
+    const int local = frame - h->last_chunk_base;
+    if (local < 0 || local >= h->last_chunk_frames) return CUBOID_E_INVALID;   // only the last chunk is still resident
+    cudaSetDevice(h->device);
+    cuboid_frame_result r;
+    CK(h, cudaMemcpy(&r, h->d_res + frame, sizeof r, cudaMemcpyDeviceToHost));
+    const void* src = nullptr; size_t bytes = 0; int n = 0;
+    switch (what) {
+        case 0: n = r.n_points; src = h->d_pts + (size_t)local * h->P; bytes = sizeof(float4) * (size_t)n; break;
+        case 1: n = r.n_points; src = h->d_kpp + (size_t)local * h->P; bytes = sizeof(int) * (size_t)n; if (!h->taps) return CUBOID_E_UNSUPPORTED; break;
+        case 2: n = r.n_voxels; src = h->d_vox + (size_t)local * h->P; bytes = sizeof(float4) * (size_t)n; break;
+        case 3: n = r.n_inliers; src = h->d_inl + (size_t)local * h->P; bytes = sizeof(int) * (size_t)n; break;
+        case 4: n = r.n_remain; src = h->d_remain + (size_t)local * h->P; bytes = sizeof(float4) * (size_t)n; break;
+        case 5: {
+            n = 0;
+            if (r.n_clusters > 0) CK(h, cudaMemcpy(&n, h->d_offsets + (size_t)local * (h->KC + 1) + r.n_clusters, sizeof(int), cudaMemcpyDeviceToHost));
+            src = h->d_idx_sorted + (size_t)local * h->M; bytes = sizeof(int) * (size_t)n; break;
+        }
+        case 6: n = r.n_clusters + 1; src = h->d_offsets + (size_t)local * (h->KC + 1); bytes = sizeof(int) * (size_t)n; break;
+        case 7: n = r.n_voxels; src = h->d_vcount + (size_t)local * h->P; bytes = sizeof(int) * (size_t)n; if (!h->taps) return CUBOID_E_UNSUPPORTED; break;
+        default: return CUBOID_E_INVALID;
+    }
+    *n_items = n;
+    if ((size_t)cap_bytes < bytes) return CUBOID_E_CAPACITY;
+    if (bytes) CK(h, cudaMemcpy(out, src, bytes, cudaMemcpyDeviceToHost));
+    return CUBOID_OK;
+}
+
+// getFinalTransformation().cast<double>().inverse() (icp.cpp:179) + tf::Matrix3x3::getRotation (icp.cpp:55-88)
+void cuboid_pose_from_transform(const float T[16], double H[16], double pose7[7]) {
+    double m[16], inv[16];
+    for (int i = 0; i < 16; ++i) m[i] = (double)T[i];
+    // general 4x4 inverse by cofactors, as Eigen's fixed-size inverse does
+    const double s0 = m[0] * m[5] - m[4] * m[1], s1 = m[0] * m[6] - m[4] * m[2], s2 = m[0] * m[7] - m[4] * m[3];
+    const double s3 = m[1] * m[6] - m[5] * m[2], s4 = m[1] * m[7] - m[5] * m[3], s5 = m[2] * m[7] - m[6] * m[3];
+    const double c5 = m[10] * m[15] - m[14] * m[11], c4 = m[9] * m[15] - m[13] * m[11], c3 = m[9] * m[14] - m[13] * m[10];
+    const double c2 = m[8] * m[15] - m[12] * m[11], c1 = m[8] * m[14] - m[12] * m[10], c0 = m[8] * m[13] - m[12] * m[9];
+    const double det = s0 * c5 - s1 * c4 + s2 * c3 + s3 * c2 - s4 * c1 + s5 * c0;
+    const double id = 1.0 / det;
+    inv[0] = (m[5] * c5 - m[6] * c4 + m[7] * c3) * id;
+    inv[1] = (-m[1] * c5 + m[2] * c4 - m[3] * c3) * id;
+    inv[2] = (m[13] * s5 - m[14] * s4 + m[15] * s3) * id;
+    inv[3] = (-m[9] * s5 + m[10] * s4 - m[11] * s3) * id;
+    inv[4] = (-m[4] * c5 + m[6] * c2 - m[7] * c1) * id;
+    inv[5] = (m[0] * c5 - m[2] * c2 + m[3] * c1) * id;
+    inv[6] = (-m[12] * s5 + m[14] * s2 - m[15] * s1) * id;
+    inv[7] = (m[8] * s5 - m[10] * s2 + m[11] * s1) * id;
+    inv[8] = (m[4] * c4 - m[5] * c2 + m[7] * c0) * id;
+    inv[9] = (-m[0] * c4 + m[1] * c2 - m[3] * c0) * id;
+    inv[10] = (m[12] * s4 - m[13] * s2 + m[15] * s0) * id;
+    inv[11] = (-m[8] * s4 + m[9] * s2 - m[11] * s0) * id;
+    inv[12] = (-m[4] * c3 + m[5] * c1 - m[6] * c0) * id;
+    inv[13] = (m[0] * c3 - m[1] * c1 + m[2] * c0) * id;
+    inv[14] = (-m[12] * s3 + m[13] * s1 - m[14] * s0) * id;
+    inv[15] = (m[8] * s3 - m[9] * s1 + m[10] * s0) * id;
+    for (int i = 0; i < 16; ++i) H[i] = inv[i];
+    auto R = [&](int r, int c) { return H[4 * r + c]; };
+    const double trace = R(0, 0) + R(1, 1) + R(2, 2);
+    double q[4];
+    if (trace > 0.0) {
+        double s = std::sqrt(trace + 1.0);
+        q[3] = s * 0.5; s = 0.5 / s;
+        q[0] = (R(2, 1) - R(1, 2)) * s; q[1] = (R(0, 2) - R(2, 0)) * s; q[2] = (R(1, 0) - R(0, 1)) * s;
+    } else {
+        const int i = R(0, 0) < R(1, 1) ? (R(1, 1) < R(2, 2) ? 2 : 1) : (R(0, 0) < R(2, 2) ? 2 : 0);
+        const int j = (i + 1) % 3, k = (i + 2) % 3;
+        double s = std::sqrt(R(i, i) - R(j, j) - R(k, k) + 1.0);
+        q[i] = s * 0.5; s = 0.5 / s;
+        q[3] = (R(k, j) - R(j, k)) * s; q[j] = (R(j, i) + R(i, j)) * s; q[k] = (R(k, i) + R(i, k)) * s;
+    }
+    pose7[0] = H[3]; pose7[1] = H[7]; pose7[2] = H[11];
+    pose7[3] = q[0]; pose7[4] = q[1]; pose7[5] = q[2]; pose7[6] = q[3];
+}
+
+// publish_bounding_box (icp.cpp:94-128): the 8 (+-l/2, +-w/2, +-h/2) corners through H.cast<float>()
+void cuboid_bbox_corners(const double H[16], double l, double w, double hgt, float out[32]) {
+    float Hf[16];
+    for (int i = 0; i < 16; ++i) Hf[i] = (float)H[i];
+    int k = 0;
+    for (int sx = -1; sx <= 1; sx += 2) for (int sy = -1; sy <= 1; sy += 2) for (int sz = -1; sz <= 1; sz += 2) {
+        const float x = (float)(sx * l / 2), y = (float)(sy * w / 2), z = (float)(sz * hgt / 2);
+        out[4 * k + 0] = ((Hf[0] * x + Hf[1] * y) + Hf[2] * z) + Hf[3];
+        out[4 * k + 1] = ((Hf[4] * x + Hf[5] * y) + Hf[6] * z) + Hf[7];
+        out[4 * k + 2] = ((Hf[8] * x + Hf[9] * y) + Hf[10] * z) + Hf[11];
+        out[4 * k + 3] = 1.0f;
+        ++k;
+    }
+}
+
+uint64_t cuboid_pack_fitness_key(double fitness, int32_t guess_id) {
+    // Non-negative doubles order like their bit patterns. The key is that pattern with its low 16 bits replaced
+    // by the guess id, so one unsigned MIN all-reduce orders by fitness first and by guess id among fitness
+    // values that agree to 2^-36 relative.
+    uint64_t b;
+    if (!(fitness >= 0.0)) fitness = 1.7976931348623157e308;
+    std::memcpy(&b, &fitness, 8);
+    return (b & ~0xffffull) | (uint64_t)(uint16_t)guess_id;
+}
+void cuboid_unpack_fitness_key(uint64_t key, double* fitness, int32_t* guess_id) {
+    const uint64_t b = key & ~0xffffull;
+    if (fitness) std::memcpy(fitness, &b, 8);
+    if (guess_id) *guess_id = (int32_t)(key & 0xffff);
+}
+
+const char* cuboid_strerror(int s) {
+    switch (s) {
+        case CUBOID_OK: return "ok";
+        case CUBOID_E_INVALID: return "invalid argument";
+        case CUBOID_E_NO_DEVICE: return "no usable CUDA device (libcuboid_cuda has no CPU fallback)";
+        case CUBOID_E_CUDA: return "CUDA runtime error";
+        case CUBOID_E_CAPACITY: return "buffer or internal capacity too small";
+        case CUBOID_E_NO_TEMPLATE: return "template slot is empty";
+        case CUBOID_E_UNSUPPORTED: return "unsupported parameter";
+        default: return "unknown status";
+    }
+}
+const char* cuboid_last_error(cuboid_handle* h) { return h ? h->last_error.c_str() : ""; }
+int cuboid_abi_version(void) { return CUBOID_ABI_VERSION; }
+int cuboid_params_size(void) { return (int)sizeof(cuboid_params); }
+int cuboid_frame_result_size(void) { return (int)sizeof(cuboid_frame_result); }
+int64_t cuboid_launch_count(cuboid_handle* h) { return h ? h->launches : 0; }
+int cuboid_stage_ms(cuboid_handle* h, float ms_out[5]) {
+    if (!h || !ms_out) return CUBOID_E_INVALID;
+    for (int i = 0; i < 5; ++i) ms_out[i] = h->stage_ms[i];
+    return CUBOID_OK;
+}
+
+int cuboid_measure_fp32_peak(cuboid_handle* h, double* unfused_tflops, double* ffma_tflops) {
+    if (!h) return CUBOID_E_INVALID;
+    cudaSetDevice(h->device);
+    int sms = 0;
+    cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, h->device);
+    float* d = nullptr;
+    CK(h, cudaMalloc(reinterpret_cast<void**>(&d), 64));
+    const int iters = 4096, blocks = sms * 8, threads = 256;
+    cudaEvent_t a, b;
+    cudaEventCreate(&a); cudaEventCreate(&b);
+    double res[2] = {0, 0};
+    for (int which = 0; which < 2; ++which) {
+        float best = 1e30f;
+        for (int rep = 0; rep < 5; ++rep) {
+            cudaEventRecord(a, h->stream);
+            if (which == 0) k_peak_unfused<<<blocks, threads, 0, h->stream>>>(d, iters, 1.0000001f, 1e-7f);
+            else k_peak_ffma<<<blocks, threads, 0, h->stream>>>(d, iters, 1.0000001f, 1e-7f);
+            cudaEventRecord(b, h->stream);
+            cudaEventSynchronize(b);
+            float ms = 0.f;
+            cudaEventElapsedTime(&ms, a, b);
+            if (rep > 0 && ms < best) best = ms;
+        }
+        h->launches += 5;
+        const double lane_ops = (double)blocks * threads * iters * 16.0;   // 16 instructions per iteration per thread
+        res[which] = lane_ops * (which == 0 ? 1.0 : 2.0) / (best * 1e-3) * 1e-12;
+    }
+    cudaEventDestroy(a); cudaEventDestroy(b);
+    cudaFree(d);
+    if (unfused_tflops) *unfused_tflops = res[0];
+    if (ffma_tflops) *ffma_tflops = res[1];
+    return CUBOID_OK;
+}
+
+}  // extern "C"

@@ -1,0 +1,545 @@
+// icp.cuh — stage 4: pcl::IterativeClosestPoint<PointXYZ,PointXYZ>::align + getFitnessScore
+// (icp.cpp:170-182, opd.cpp:220-235). One persistent CTA per (frame, cluster, guess):
+// the whole ICP loop — nearest neighbours, Umeyama, 3x3 Jacobi SVD, incremental transform,
+// DefaultConvergenceCriteria — runs on the device, no host round trip.
+//
+//   nearest neighbour   brute force over the template, which is staged ONCE in shared memory by TMA bulk
+//                       copies; d2 = ((dx*dx)+dy*dy)+dz*dz un-fused FP32; each thread keeps R source points in
+//                       registers so one broadcast LDS.128 feeds R*8 FP32 ops; running minimum per 64-point
+//                       template chunk with FMNMX, chunk id kept on strict '<', the exact index is recovered
+//                       by re-scanning the winning chunk (ties -> lowest template index, the canonical choice)
+//   Umeyama             canonical 256-lane strided partial sums + xor-butterfly + 8 warp partials left to right
+//                       (identical in oracle/cuboid_oracle.cpp: canon_reduce), Eigen JacobiSVD restated
+//   convergence         max iterations | transform epsilon | |dMSE| < 1e-12 | rel dMSE < icp_fitness_score
+//
+// Roofline: FP32 pipe (un-fused): 8*S*T ops per iteration per hypothesis (+ S*T FMNMX on the ALU pipe); HBM ~ 0.
+#pragma once
+#include "common.cuh"
+#include "ransac.cuh"   // TMA bulk-copy helpers
+
+namespace cuboid {
+
+struct IcpOut {
+    float T[16];
+    double fitness;
+    int converged, iters, state, pad;
+    unsigned long long corr_hash;
+};
+
+struct IcpArgs {
+    const float4* remain;    // [F][P]
+    const int* idx_sorted;   // [F][M]
+    const int* offsets;      // [F][KC+1]
+    const float4* tmpl;      // [Tpad] padded to a multiple of 64 with far sentinels
+    int T, Tpad;
+    const float* guesses;    // n_guess * (16 | 9) or NULL
+    int n_guess, guess_mode;
+    float4* cur;             // [F][G][M]
+    int* corr;               // [F][G][M]
+    float* cd;               // [F][G][M]
+    IcpOut* out;             // [F][MAXC][G]
+    cuboid_frame_result* res;
+    int P, M, KC;
+    int max_iter;
+    double rot_thr, trans_thr, rel_mse, abs_thr;
+    int tmpl_resident_pts;   // template points that fit the dynamic shared memory window (multiple of 64)
+    int* corr_trace; float* T_trace; int cap_trace;   // debug taps for problem (0,0,0)
+    float4* aligned_out;                               // optional: transformCloud(src, final) of problem (0,0,best)
+};
+
+constexpr int ICP_THREADS = 256;
+constexpr int ICP_CHUNK = 64;
+
+struct M3f { float a[3][3]; };
+struct Rotf { float c, s; };
+
+__device__ __forceinline__ void rot_rows(M3f& m, int p, int q, Rotf j) {
+    if (j.c == 1.f && j.s == 0.f) return;
+#pragma unroll
+    for (int i = 0; i < 3; ++i) {
+        const float xi = m.a[p][i], yi = m.a[q][i];
+        m.a[p][i] = j.c * xi + j.s * yi;
+        m.a[q][i] = -j.s * xi + j.c * yi;
+    }
+}
+__device__ __forceinline__ void rot_cols(M3f& m, int p, int q, Rotf j) {
+    const Rotf t{j.c, -j.s};
+    if (t.c == 1.f && t.s == 0.f) return;
+#pragma unroll
+    for (int i = 0; i < 3; ++i) {
+        const float xi = m.a[i][p], yi = m.a[i][q];
+        m.a[i][p] = t.c * xi + t.s * yi;
+        m.a[i][q] = -t.s * xi + t.c * yi;
+    }
+}
+__device__ __forceinline__ Rotf make_jacobi(float x, float y, float z) {
+    const float deno = 2.0f * fabsf(y);
+    if (deno < 1.17549435e-38f) return Rotf{1.f, 0.f};
+    const float tau = (x - z) / deno;
+    const float w = sqrtf(tau * tau + 1.0f);
+    float t;
+    if (tau > 0.f) t = 1.0f / (tau + w); else t = 1.0f / (tau - w);
+    const float sign_t = t > 0.f ? 1.0f : -1.0f;
+    const float n = 1.0f / sqrtf(t * t + 1.0f);
+    Rotf r;
+    r.s = -sign_t * (y / fabsf(y)) * fabsf(t) * n;
+    r.c = n;
+    return r;
+}
+__device__ __forceinline__ void jacobi_2x2(const M3f& w, int p, int q, Rotf* jl, Rotf* jr) {
+    float m00 = w.a[p][p], m01 = w.a[p][q], m10 = w.a[q][p], m11 = w.a[q][q];
+    Rotf rot1;
+    const float t = m00 + m11;
+    const float d = m10 - m01;
+    if (fabsf(d) < 1.17549435e-38f) { rot1.s = 0.f; rot1.c = 1.f; }
+    else {
+        const float u = t / d;
+        const float tmp = sqrtf(1.0f + u * u);
+        rot1.s = 1.0f / tmp;
+        rot1.c = u / tmp;
+    }
+    if (!(rot1.c == 1.f && rot1.s == 0.f)) {
+        const float x0 = m00, x1 = m01, y0 = m10, y1 = m11;
+        m00 = rot1.c * x0 + rot1.s * y0; m01 = rot1.c * x1 + rot1.s * y1;
+        m10 = -rot1.s * x0 + rot1.c * y0; m11 = -rot1.s * x1 + rot1.c * y1;
+    }
+    *jr = make_jacobi(m00, m01, m11);
+    const Rotf jt{jr->c, -jr->s};
+    jl->c = rot1.c * jt.c - rot1.s * jt.s;
+    jl->s = rot1.c * jt.s + rot1.s * jt.c;
+}
+__device__ __forceinline__ float det3(const M3f& m) {
+    const float h0 = m.a[0][0] * (m.a[1][1] * m.a[2][2] - m.a[1][2] * m.a[2][1]);
+    const float h1 = m.a[0][1] * (m.a[1][0] * m.a[2][2] - m.a[1][2] * m.a[2][0]);
+    const float h2 = m.a[0][2] * (m.a[1][0] * m.a[2][1] - m.a[1][1] * m.a[2][0]);
+    return h0 - h1 + h2;
+}
+// Eigen::JacobiSVD<Matrix3f>(sigma, ComputeFullU | ComputeFullV)
+__device__ void jacobi_svd3(const M3f& in, M3f& U, M3f& V) {
+    const float precision = 2.0f * 1.1920928955078125e-07f;
+    const float consider_zero = 1.17549435e-38f;
+    float scale = 0.f;
+#pragma unroll
+    for (int i = 0; i < 3; ++i)
+#pragma unroll
+        for (int j = 0; j < 3; ++j) scale = fmaxf(scale, fabsf(in.a[i][j]));
+    if (scale == 0.f) scale = 1.f;
+    M3f W;
+#pragma unroll
+    for (int i = 0; i < 3; ++i)
+#pragma unroll
+        for (int j = 0; j < 3; ++j) { W.a[i][j] = in.a[i][j] / scale; U.a[i][j] = (i == j) ? 1.f : 0.f; V.a[i][j] = (i == j) ? 1.f : 0.f; }
+    float max_diag = fmaxf(fabsf(W.a[0][0]), fmaxf(fabsf(W.a[1][1]), fabsf(W.a[2][2])));
+    bool finished = false;
+    int guard = 0;
+    while (!finished && guard++ < 1000) {
+        finished = true;
+#pragma unroll
+        for (int p = 1; p < 3; ++p) {
+#pragma unroll
+            for (int q = 0; q < 2; ++q) {
+                if (q >= p) continue;
+                const float thr = fmaxf(consider_zero, precision * max_diag);
+                if (fabsf(W.a[p][q]) > thr || fabsf(W.a[q][p]) > thr) {
+                    finished = false;
+                    Rotf jl, jr;
+                    jacobi_2x2(W, p, q, &jl, &jr);
+                    rot_rows(W, p, q, jl);
+                    rot_cols(U, p, q, Rotf{jl.c, -jl.s});
+                    rot_cols(W, p, q, jr);
+                    rot_cols(V, p, q, jr);
+                    max_diag = fmaxf(max_diag, fmaxf(fabsf(W.a[p][p]), fabsf(W.a[q][q])));
+                }
+            }
+        }
+    }
+    float sv[3];
+#pragma unroll
+    for (int i = 0; i < 3; ++i) {
+        const float d = W.a[i][i];
+        sv[i] = fabsf(d);
+        if (d < 0.f) { U.a[0][i] = -U.a[0][i]; U.a[1][i] = -U.a[1][i]; U.a[2][i] = -U.a[2][i]; }
+    }
+#pragma unroll
+    for (int i = 0; i < 3; ++i) sv[i] = sv[i] * scale;
+#pragma unroll
+    for (int i = 0; i < 3; ++i) {
+        int pos = i;
+        for (int k = i + 1; k < 3; ++k) if (sv[k] > sv[pos]) pos = k;
+        if (sv[pos] == 0.f) break;
+        if (pos != i) {
+            float t = sv[i]; sv[i] = sv[pos]; sv[pos] = t;
+            for (int r = 0; r < 3; ++r) {
+                t = U.a[r][i]; U.a[r][i] = U.a[r][pos]; U.a[r][pos] = t;
+                t = V.a[r][i]; V.a[r][i] = V.a[r][pos]; V.a[r][pos] = t;
+            }
+        }
+    }
+}
+
+// tr * (x,y,z,1) = ((m0*x + m1*y) + m2*z) + m3   (Eigen 4x4 * 4x1)
+__device__ __forceinline__ float4 xform(const float* m, const float4 p) {
+    float4 o;
+    o.x = ((m[0] * p.x + m[1] * p.y) + m[2] * p.z) + m[3];
+    o.y = ((m[4] * p.x + m[5] * p.y) + m[6] * p.z) + m[7];
+    o.z = ((m[8] * p.x + m[9] * p.y) + m[10] * p.z) + m[11];
+    o.w = 1.0f;
+    return o;
+}
+
+// canonical block reduction of NQ quantities held one-per-lane by the first 256 threads (lane partials are
+// already the sequential strided sums). Result for quantity q lands in s_out[q]. Contains two __syncthreads.
+template <typename Tq, int NQ>
+__device__ __forceinline__ void canon_block_reduce(Tq (&v)[NQ], Tq* s_part /* [NQ][8] */, Tq* s_out) {
+    const int lane = threadIdx.x & 31, wid = threadIdx.x >> 5;
+#pragma unroll
+    for (int q = 0; q < NQ; ++q) {
+        Tq x = v[q];
+#pragma unroll
+        for (int o = 16; o >= 1; o >>= 1) x = x + __shfl_xor_sync(FULL_MASK, x, o);
+        if (lane == 0 && wid < 8) s_part[q * 8 + wid] = x;
+    }
+    __syncthreads();
+    if (threadIdx.x < NQ) {
+        const Tq* p = s_part + threadIdx.x * 8;
+        Tq s = p[0];
+#pragma unroll
+        for (int g = 1; g < 8; ++g) s = s + p[g];
+        s_out[threadIdx.x] = s;
+    }
+    __syncthreads();
+}
+
+// nearest neighbour of R source points (registers) against template points [0, n_t) in shared memory.
+// best/bchunk persist across template windows; chunk ids are global (chunk_base + local).
+template <int R>
+__device__ __forceinline__ void nn_window(const float4* __restrict__ s_t, int n_t, int chunk_base, const float (&sx)[R],
+                                          const float (&sy)[R], const float (&sz)[R], float (&best)[R], int (&bchunk)[R]) {
+    for (int c0 = 0; c0 < n_t; c0 += ICP_CHUNK) {
+        float m[R];
+#pragma unroll
+        for (int r = 0; r < R; ++r) m[r] = __int_as_float(0x7f800000);
+#pragma unroll 8
+        for (int jj = 0; jj < ICP_CHUNK; ++jj) {
+            const float4 t = s_t[c0 + jj];
+#pragma unroll
+            for (int r = 0; r < R; ++r) {
+                const float dx = sx[r] - t.x, dy = sy[r] - t.y, dz = sz[r] - t.z;
+                const float d = ((dx * dx) + dy * dy) + dz * dz;
+                m[r] = fminf(m[r], d);
+            }
+        }
+        const int cid = chunk_base + c0 / ICP_CHUNK;
+#pragma unroll
+        for (int r = 0; r < R; ++r)
+            if (m[r] < best[r]) { best[r] = m[r]; bchunk[r] = cid; }
+    }
+}
+
+struct IcpShared {
+    unsigned long long bar;
+    float part_f[16 * 8];
+    double part_d[8];
+    float red_f[16];
+    double red_d[2];
+    float Tm[16];       // this iteration's transformation_
+    float fin[16];      // final_transformation_
+    float guess[16];
+    int done, converged, state, iters;
+    double prev_mse;
+};
+
+// one full NN pass over source points cur[0..S): writes corr[] / cd[]
+__device__ void icp_nn_pass(const IcpArgs& a, const float4* s_tmpl, bool resident, const float4* cur, int S, int* corr, float* cd,
+                            float4* s_window) {
+    const int NT = ICP_THREADS;
+    for (int g0 = 0; g0 < S; g0 += NT * 4) {
+        // R = 4 rounds of NT points; inactive slots replicate a valid point and are not stored
+        float sx[4], sy[4], sz[4], best[4];
+        int bch[4];
+#pragma unroll
+        for (int r = 0; r < 4; ++r) {
+            const int i = g0 + r * NT + threadIdx.x;
+            const float4 p = cur[i < S ? i : (S - 1)];
+            sx[r] = p.x; sy[r] = p.y; sz[r] = p.z;
+            best[r] = __int_as_float(0x7f800000);
+            bch[r] = 0;
+        }
+        const int rounds = min(4, (S - g0 + NT - 1) / NT);
+        if (resident) {
+            if (rounds > 2) nn_window<4>(s_tmpl, a.Tpad, 0, sx, sy, sz, best, bch);
+            else if (rounds == 2) {
+                float sx2[2] = {sx[0], sx[1]}, sy2[2] = {sy[0], sy[1]}, sz2[2] = {sz[0], sz[1]}, b2[2] = {best[0], best[1]};
+                int c2[2] = {0, 0};
+                nn_window<2>(s_tmpl, a.Tpad, 0, sx2, sy2, sz2, b2, c2);
+                best[0] = b2[0]; best[1] = b2[1]; bch[0] = c2[0]; bch[1] = c2[1];
+            } else {
+                float sx1[1] = {sx[0]}, sy1[1] = {sy[0]}, sz1[1] = {sz[0]}, b1[1] = {best[0]};
+                int c1[1] = {0};
+                nn_window<1>(s_tmpl, a.Tpad, 0, sx1, sy1, sz1, b1, c1);
+                best[0] = b1[0]; bch[0] = c1[0];
+            }
+        } else {
+            // template larger than shared memory: stream it through the window (block-uniform loop)
+            for (int w0 = 0; w0 < a.Tpad; w0 += a.tmpl_resident_pts) {
+                const int wn = min(a.tmpl_resident_pts, a.Tpad - w0);
+                __syncthreads();
+                for (int j = threadIdx.x; j < wn; j += NT) s_window[j] = a.tmpl[w0 + j];
+                __syncthreads();
+                nn_window<4>(s_window, wn, w0 / ICP_CHUNK, sx, sy, sz, best, bch);
+            }
+        }
+        // recover the exact index: first j in the winning chunk whose distance equals the minimum
+#pragma unroll
+        for (int r = 0; r < 4; ++r) {
+            const int i = g0 + r * NT + threadIdx.x;
+            if (r >= rounds || i >= S) continue;
+            const float4* ch = (resident ? s_tmpl : a.tmpl) + (size_t)bch[r] * ICP_CHUNK;
+            int jbest = 0;
+            for (int jj = ICP_CHUNK - 1; jj >= 0; --jj) {
+                const float4 t = ch[jj];
+                const float dx = sx[r] - t.x, dy = sy[r] - t.y, dz = sz[r] - t.z;
+                const float d = ((dx * dx) + dy * dy) + dz * dz;
+                if (d == best[r]) jbest = jj;
+            }
+            corr[i] = bch[r] * ICP_CHUNK + jbest;
+            cd[i] = best[r];
+        }
+    }
+}
+
+__global__ void __launch_bounds__(ICP_THREADS, 1) k_icp(const IcpArgs a) {
+    extern __shared__ __align__(128) unsigned char smem_raw[];
+    float4* s_tmpl = reinterpret_cast<float4*>(smem_raw);
+    __shared__ IcpShared S_;
+    IcpShared& sh = S_;
+
+    const int g = blockIdx.x, c = blockIdx.y, f = blockIdx.z;
+    const cuboid_frame_result& R = a.res[f];
+    const int ncl = min(R.n_clusters, CUBOID_MAX_CLUSTERS);
+    if (c >= ncl) return;
+    const int* offsets = a.offsets + (size_t)f * (a.KC + 1);
+    const int o0 = offsets[c], S = offsets[c + 1] - o0;
+    const int* idx = a.idx_sorted + (size_t)f * a.M + o0;
+    const float4* src = a.remain + (size_t)f * a.P;
+    const size_t pbase = ((size_t)f * a.n_guess + g) * a.M + o0;
+    float4* cur = a.cur + pbase;
+    int* corr = a.corr + pbase;
+    float* cd = a.cd + pbase;
+    IcpOut& out = a.out[((size_t)f * CUBOID_MAX_CLUSTERS + c) * a.n_guess + g];
+    const bool resident = a.Tpad <= a.tmpl_resident_pts;
+    const bool trace = a.corr_trace && f == 0 && c == 0 && g == 0;
+
+    // ---- stage the template once (TMA bulk copies, 32 KB each) ----
+    if (threadIdx.x == 0) {
+        mbar_init(&sh.bar, 1);
+        asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
+    }
+    __syncthreads();
+    if (resident) {
+        if (threadIdx.x == 0) {
+            const unsigned int total = (unsigned int)a.Tpad * 16u;
+            mbar_expect_tx(&sh.bar, total);
+            for (unsigned int off = 0; off < total; off += 32768u) {
+                const unsigned int n = min(32768u, total - off);
+                tma_bulk_g2s(reinterpret_cast<unsigned char*>(s_tmpl) + off, reinterpret_cast<const unsigned char*>(a.tmpl) + off, n, &sh.bar);
+            }
+        }
+    }
+
+    // ---- guess: final = guess; src_t = (guess == I) ? src : guess * src ----
+    if (threadIdx.x < 16) {
+        float v = (threadIdx.x % 5 == 0) ? 1.f : 0.f;
+        if (a.guesses && a.guess_mode == 0) v = a.guesses[(size_t)g * 16 + threadIdx.x];
+        sh.guess[threadIdx.x] = v;
+    }
+    __syncthreads();
+    if (a.guesses && a.guess_mode == 1) {
+        // rotation about the cluster centroid: G = T(c) R T(-c), centroid by the canonical reduction
+        float v3[3] = {0.f, 0.f, 0.f};
+        for (int i = threadIdx.x; i < S; i += ICP_THREADS) {
+            const float4 p = src[idx[i]];
+            v3[0] = v3[0] + p.x; v3[1] = v3[1] + p.y; v3[2] = v3[2] + p.z;
+        }
+        canon_block_reduce<float, 3>(v3, sh.part_f, sh.red_f);
+        if (threadIdx.x == 0) {
+            const float cn = (float)S;
+            const float cx = sh.red_f[0] / cn, cy = sh.red_f[1] / cn, cz = sh.red_f[2] / cn;
+            const float* Rm = a.guesses + (size_t)g * 9;
+            const float cc[3] = {cx, cy, cz};
+            for (int i = 0; i < 3; ++i) {
+                for (int j = 0; j < 3; ++j) sh.guess[4 * i + j] = Rm[3 * i + j];
+                sh.guess[4 * i + 3] = cc[i] - ((Rm[3 * i] * cx + Rm[3 * i + 1] * cy) + Rm[3 * i + 2] * cz);
+            }
+        }
+        __syncthreads();
+    }
+    bool guess_identity = true;
+#pragma unroll
+    for (int k = 0; k < 16; ++k) guess_identity = guess_identity && (sh.guess[k] == ((k % 5 == 0) ? 1.f : 0.f));
+    for (int i = threadIdx.x; i < S; i += ICP_THREADS) {
+        const float4 p = src[idx[i]];
+        cur[i] = guess_identity ? make_float4(p.x, p.y, p.z, 1.0f) : xform(sh.guess, p);
+    }
+    if (threadIdx.x < 16) sh.fin[threadIdx.x] = sh.guess[threadIdx.x];
+    if (threadIdx.x == 0) { sh.done = 0; sh.converged = 0; sh.state = CUBOID_ICP_NOT_CONVERGED; sh.iters = 0; sh.prev_mse = 1.7976931348623157e308; }
+    if (resident) mbar_wait(&sh.bar, 0);
+    __syncthreads();
+
+    unsigned long long chash = 0;
+    const float one_over_n = 1.0f / (float)S;
+    int it = 0;
+    if (S < 3) {   // "Not enough correspondences found" -> converged_ = false, no iteration
+        if (threadIdx.x == 0) { sh.done = 1; sh.state = CUBOID_ICP_NO_CORRESPONDENCES; }
+        __syncthreads();
+    }
+    while (!sh.done) {
+        // 1. correspondences
+        icp_nn_pass(a, s_tmpl, resident, cur, S, corr, cd, s_tmpl);
+        __syncthreads();
+        // 2. means + MSE (first 256 threads are the 256 canonical lanes)
+        float q6[6] = {0.f, 0.f, 0.f, 0.f, 0.f, 0.f};
+        double qd[1] = {0.0};
+        for (int i = threadIdx.x; i < S; i += ICP_THREADS) {
+            const float4 p = cur[i];
+            const int j = corr[i];
+            const float4 t = resident ? s_tmpl[j] : a.tmpl[j];
+            q6[0] = q6[0] + p.x; q6[1] = q6[1] + p.y; q6[2] = q6[2] + p.z;
+            q6[3] = q6[3] + t.x; q6[4] = q6[4] + t.y; q6[5] = q6[5] + t.z;
+            qd[0] = qd[0] + (double)cd[i];
+            chash += splitmix64((((unsigned long long)it * (unsigned long long)S + (unsigned long long)i) << 32) | (unsigned int)j);
+            if (trace && it < a.cap_trace) a.corr_trace[(size_t)it * S + i] = j;
+        }
+        canon_block_reduce<float, 6>(q6, sh.part_f, sh.red_f);
+        canon_block_reduce<double, 1>(qd, sh.part_d, sh.red_d);
+        float sm[3], dm[3];
+#pragma unroll
+        for (int k = 0; k < 3; ++k) { sm[k] = sh.red_f[k] * one_over_n; dm[k] = sh.red_f[3 + k] * one_over_n; }
+        const double mse_sum = sh.red_d[0];
+        __syncthreads();
+        // 3. sigma = one_over_n * dst_demean * src_demean^T
+        float q9[9];
+#pragma unroll
+        for (int k = 0; k < 9; ++k) q9[k] = 0.f;
+        for (int i = threadIdx.x; i < S; i += ICP_THREADS) {
+            const float4 p = cur[i];
+            const float4 t = resident ? s_tmpl[corr[i]] : a.tmpl[corr[i]];
+            const float sd[3] = {p.x - sm[0], p.y - sm[1], p.z - sm[2]};
+            const float dd[3] = {t.x - dm[0], t.y - dm[1], t.z - dm[2]};
+#pragma unroll
+            for (int r = 0; r < 3; ++r)
+#pragma unroll
+                for (int cc = 0; cc < 3; ++cc) q9[3 * r + cc] = q9[3 * r + cc] + dd[r] * sd[cc];
+        }
+        canon_block_reduce<float, 9>(q9, sh.part_f, sh.red_f);
+        // 4. thread 0: SVD, R, t, final, convergence
+        if (threadIdx.x == 0) {
+            M3f sigma, U, V;
+#pragma unroll
+            for (int r = 0; r < 3; ++r)
+#pragma unroll
+                for (int cc = 0; cc < 3; ++cc) sigma.a[r][cc] = one_over_n * sh.red_f[3 * r + cc];
+            jacobi_svd3(sigma, U, V);
+            float Sg[3] = {1.f, 1.f, 1.f};
+            if (det3(U) * det3(V) < 0.f) Sg[2] = -1.f;
+            float Tm[16];
+#pragma unroll
+            for (int i = 0; i < 3; ++i) {
+#pragma unroll
+                for (int j = 0; j < 3; ++j)
+                    Tm[4 * i + j] = ((U.a[i][0] * Sg[0]) * V.a[j][0] + (U.a[i][1] * Sg[1]) * V.a[j][1]) + (U.a[i][2] * Sg[2]) * V.a[j][2];
+            }
+#pragma unroll
+            for (int i = 0; i < 3; ++i) Tm[4 * i + 3] = dm[i] - ((Tm[4 * i] * sm[0] + Tm[4 * i + 1] * sm[1]) + Tm[4 * i + 2] * sm[2]);
+            Tm[12] = 0.f; Tm[13] = 0.f; Tm[14] = 0.f; Tm[15] = 1.f;
+            float nf[16];
+#pragma unroll
+            for (int i = 0; i < 4; ++i)
+#pragma unroll
+                for (int j = 0; j < 4; ++j)
+                    nf[4 * i + j] = ((Tm[4 * i] * sh.fin[j] + Tm[4 * i + 1] * sh.fin[4 + j]) + Tm[4 * i + 2] * sh.fin[8 + j]) + Tm[4 * i + 3] * sh.fin[12 + j];
+#pragma unroll
+            for (int k = 0; k < 16; ++k) { sh.fin[k] = nf[k]; sh.Tm[k] = Tm[k]; }
+            if (trace && it < a.cap_trace) for (int k = 0; k < 16; ++k) a.T_trace[(size_t)it * 16 + k] = Tm[k];
+            const int itn = it + 1;
+            sh.iters = itn;
+            // DefaultConvergenceCriteria::hasConverged
+            int done = 0;
+            if (itn >= a.max_iter) { done = 1; sh.converged = 1; sh.state = CUBOID_ICP_ITERATIONS; }
+            if (!done) {
+                const double cos_angle = 0.5 * (double)(Tm[0] + Tm[5] + Tm[10] - 1.0f);
+                const double tsq = (double)(Tm[3] * Tm[3] + Tm[7] * Tm[7] + Tm[11] * Tm[11]);
+                if (cos_angle >= a.rot_thr && tsq <= a.trans_thr) { done = 1; sh.converged = 1; sh.state = CUBOID_ICP_TRANSFORM; }
+            }
+            if (!done) {
+                const double mse = mse_sum / (double)S;
+                if (fabs(mse - sh.prev_mse) < a.abs_thr) { done = 1; sh.converged = 1; sh.state = CUBOID_ICP_ABS_MSE; }
+                else if (fabs(mse - sh.prev_mse) / sh.prev_mse < a.rel_mse) { done = 1; sh.converged = 1; sh.state = CUBOID_ICP_REL_MSE; }
+                else sh.prev_mse = mse;
+            }
+            sh.done = done;
+        }
+        __syncthreads();
+        // 5. transformCloud(input_transformed, input_transformed, transformation_): incremental, in place
+        for (int i = threadIdx.x; i < S; i += ICP_THREADS) cur[i] = xform(sh.Tm, cur[i]);
+        ++it;
+        __syncthreads();
+    }
+
+    // ---- output = transformCloud(src, final); getFitnessScore(): one more NN pass ----
+    for (int i = threadIdx.x; i < S; i += ICP_THREADS) cur[i] = xform(sh.fin, src[idx[i]]);
+    __syncthreads();
+    double fitness = 1.7976931348623157e308;
+    if (S > 0) {
+        icp_nn_pass(a, s_tmpl, resident, cur, S, corr, cd, s_tmpl);
+        __syncthreads();
+        double qd[1] = {0.0};
+        for (int i = threadIdx.x; i < S; i += ICP_THREADS) qd[0] = qd[0] + (double)cd[i];
+        canon_block_reduce<double, 1>(qd, sh.part_d, sh.red_d);
+        fitness = sh.red_d[0] / (double)S;
+    }
+    // reduce the correspondence hash
+    chash = warp_sum_u64(chash);
+    __shared__ unsigned long long s_hh[8];
+    if ((threadIdx.x & 31) == 0) s_hh[threadIdx.x >> 5] = chash;
+    __syncthreads();
+    if (threadIdx.x == 0) {
+        unsigned long long t = 0;
+        for (int k = 0; k < 8; ++k) t += s_hh[k];
+        for (int k = 0; k < 16; ++k) out.T[k] = sh.fin[k];
+        out.fitness = fitness;
+        out.converged = sh.converged;
+        out.iters = sh.iters;
+        out.state = sh.state;
+        out.corr_hash = t;
+    }
+}
+
+// best guess per (frame, cluster): lowest fitness, ties -> lowest guess id; fills cuboid_cluster_result
+__global__ void k_icp_select(const IcpOut* out, cuboid_frame_result* res, int n_frames, int n_guess, double gate,
+                             const float4* cur, int M, const int* offsets, int KC, float4* aligned_out) {
+    const int t = blockIdx.x * blockDim.x + threadIdx.x;
+    const int f = t / CUBOID_MAX_CLUSTERS, c = t % CUBOID_MAX_CLUSTERS;
+    if (f >= n_frames) return;
+    cuboid_frame_result& R = res[f];
+    if (c >= min(R.n_clusters, CUBOID_MAX_CLUSTERS)) return;
+    const IcpOut* o = out + ((size_t)f * CUBOID_MAX_CLUSTERS + c) * n_guess;
+    int bg = 0;
+    for (int g = 1; g < n_guess; ++g) if (o[g].fitness < o[bg].fitness) bg = g;
+    cuboid_cluster_result& C = R.cluster[c];
+    C.converged = o[bg].converged;
+    C.iterations = o[bg].iters;
+    C.best_guess = bg;
+    C.state = o[bg].state;
+    C.fitness = o[bg].fitness;
+    C.accepted = (o[bg].converged && o[bg].fitness < gate) ? 1 : 0;
+    for (int k = 0; k < 16; ++k) C.T[k] = o[bg].T[k];
+    C.corr_hash = o[bg].corr_hash;
+    if (aligned_out && f == 0 && c == 0) {   // single-problem API: hand back the aligned cloud of the winner
+        const int o0 = offsets[0], S = offsets[1] - o0;
+        const float4* src = cur + ((size_t)f * n_guess + bg) * M + o0;
+        for (int i = 0; i < S; ++i) aligned_out[i] = src[i];
+    }
+}
+
+}  // namespace cuboid

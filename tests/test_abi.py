@@ -1,0 +1,85 @@
+"""CPU-side checks of the C-ABI library: it loads, exports every symbol include/cuboid_cuda.h declares, the
+struct layouts match the ctypes mirrors, host-only entry points agree with the oracle, and compute entry points
+fail loudly (no fallback) when there is no CUDA device."""
+import ctypes as C
+import os
+import re
+
+import numpy as np
+import pytest
+
+from perception_b200 import api
+from perception_b200.params import CuboidParams, FrameResult, default_params
+
+ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+
+
+def _header_symbols():
+    txt = open(os.path.join(ROOT, "include", "cuboid_cuda.h")).read()
+    txt = re.sub(r"/\*.*?\*/", "", txt, flags=re.S)
+    return sorted(set(re.findall(r"\b(cuboid_[a-z0-9_]+)\s*\(", txt)))
+
+
+def test_library_exports_every_declared_symbol():
+    lib = api.load()
+    declared = _header_symbols()
+    assert len(declared) >= 25
+    for name in declared:
+        assert hasattr(lib, name), "libcuboid_cuda.so does not export " + name
+    assert sorted(api.ABI_SYMBOLS) == declared
+
+
+def test_struct_layouts_and_defaults():
+    lib = api.load()
+    assert lib.cuboid_abi_version() == 1
+    assert lib.cuboid_params_size() == C.sizeof(CuboidParams) == 176
+    assert lib.cuboid_frame_result_size() == C.sizeof(FrameResult)
+    p = CuboidParams()
+    lib.cuboid_default_params(C.byref(p))
+    q = default_params("cuboid")
+    for name, _ in CuboidParams._fields_:
+        assert getattr(p, name) == getattr(q, name), name
+    # the launch-file values the reference nodes read (cuboid_detection/launch/*.launch, gps.cpp:56,64,88; icp.cpp:173-176)
+    assert (p.leaf, p.sac_threshold, p.sac_max_iter, p.icp_max_iter) == (np.float32(0.005), 0.015, 1000, 5000)
+    assert (p.pass_z_max, p.pass_x_min, p.pass_x_max, p.icp_rel_mse, p.icp_fitness_gate) == (0.9, -0.2, 0.2, 0.0004, 0.0004)
+    o = default_params("object")
+    assert (o.leaf, o.sac_threshold, o.use_pass_z2) == (np.float32(0.001), 0.01, 1)
+
+
+def test_strerror_and_no_device_is_loud():
+    import torch
+    lib = api.load()
+    assert b"no CPU fallback" in lib.cuboid_strerror(api.E_NO_DEVICE)
+    if torch.cuda.is_available():
+        pytest.skip("a GPU is present; the no-device path is checked on the CPU box")
+    with pytest.raises(api.CuboidError) as e:
+        api.CuboidCuda(default_params())
+    assert e.value.status == api.E_NO_DEVICE
+
+
+def test_pose_and_bbox_match_oracle():
+    from oracle import pyoracle as O
+    rng = np.random.default_rng(0)
+    for _ in range(20):
+        A = rng.normal(size=(3, 3))
+        Q, _r = np.linalg.qr(A)
+        if np.linalg.det(Q) < 0:
+            Q[:, 0] = -Q[:, 0]
+        T = np.eye(4, dtype=np.float32)
+        T[:3, :3] = Q
+        T[:3, 3] = rng.uniform(-1, 1, 3)
+        H, pose = api.pose_from_transform(T)
+        Ho, poseo = O.pose_from_transform(T)
+        assert np.allclose(H, Ho, atol=1e-12) and np.allclose(H, np.linalg.inv(T.astype(np.float64)), atol=1e-12)
+        assert np.allclose(pose, poseo, atol=1e-12)
+        assert np.array_equal(api.bbox_corners(H, 0.2, 0.1, 0.03), O.bbox_corners(H, 0.2, 0.1, 0.03))
+
+
+def test_fitness_key_orders_by_fitness_then_guess():
+    k = api.pack_fitness_key
+    assert k(1e-6, 5) < k(2e-6, 0)
+    assert k(1e-6, 3) < k(1e-6, 4)
+    f, g = api.unpack_fitness_key(k(7.38e-6, 17))
+    assert g == 17 and abs(f - 7.38e-6) / 7.38e-6 < 1e-10
+    assert k(float("nan"), 0) > k(1e300, 65535)
+    assert k(1e-6, 0) < 2 ** 63   # fits a signed int64 all-reduce

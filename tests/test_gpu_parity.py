@@ -1,0 +1,298 @@
+"""GPU parity: libcuboid_cuda (through the C ABI) against the CPU oracle on identical seeded inputs.
+
+Bars (BASELINE.json north_star): voxel keys, RANSAC inlier index sets and ICP correspondences bit-exact;
+final ICP pose within 1e-4 rad / 1e-5 m, fitness within 1e-6 (they are in fact bit-equal here because the
+CUDA path reproduces the oracle's canonical operation order)."""
+import ctypes as C
+
+import numpy as np
+import pytest
+
+from oracle import pyoracle as O
+from perception_b200 import api, synth
+from perception_b200.params import default_params
+
+from conftest import bits
+
+pytestmark = pytest.mark.gpu
+
+ROT_TOL, TRANS_TOL, FIT_TOL = 1e-4, 1e-5, 1e-6
+
+
+@pytest.fixture(scope="module")
+def cc(params, tmpl30, tmpl100):
+    h = api.CuboidCuda(params, device=0, max_points=640 * 480, max_batch=8)
+    h.set_template(0, tmpl30)
+    h.set_template(1, tmpl100)
+    yield h
+    h.close()
+
+
+def _pose_close(Tg, To):
+    Tg, To = np.asarray(Tg, np.float64).reshape(4, 4), np.asarray(To, np.float64).reshape(4, 4)
+    D = Tg[:3, :3] @ To[:3, :3].T
+    ang = np.linalg.norm([D[2, 1] - D[1, 2], D[0, 2] - D[2, 0], D[1, 0] - D[0, 1]]) / 2
+    return ang < ROT_TOL and np.abs(Tg[:3, 3] - To[:3, 3]).max() < TRANS_TOL
+
+
+def _same_frame(r, ref, check_icp=True):
+    for k in ("status", "n_points", "n_voxels", "plane_found", "n_inliers_pre", "n_inliers", "sac_iterations", "sac_draws",
+              "n_remain", "n_clusters", "points_hash", "voxel_key_hash", "voxel_hash", "inlier_hash", "remain_hash",
+              "cluster_hash"):
+        assert getattr(r, k) == getattr(ref, k), (k, getattr(r, k), getattr(ref, k))
+    assert list(r.min_b) == list(ref.min_b) and list(r.div_b) == list(ref.div_b)
+    assert np.array_equal(bits(list(r.plane_coeff)), bits(list(ref.plane_coeff)))
+    if not check_icp:
+        return
+    for c in range(min(r.n_clusters, 16)):
+        a, b = r.cluster[c], ref.cluster[c]
+        assert (a.size, a.converged, a.iterations, a.state, a.best_guess, a.accepted) == \
+               (b.size, b.converged, b.iterations, b.state, b.best_guess, b.accepted)
+        assert a.corr_hash == b.corr_hash                       # every iteration's correspondences, bit-exact
+        assert _pose_close(list(a.T), list(b.T)) and abs(a.fitness - b.fitness) < FIT_TOL
+        assert np.array_equal(bits(list(a.T)), bits(list(b.T))) and a.fitness == b.fitness
+
+
+def test_unproject_bit_exact(cc, frame0, stage_data):
+    g = cc.unproject(frame0)
+    assert np.array_equal(bits(g), bits(stage_data["all"]))
+
+
+def test_preprocess_voxel_keys_and_centroids_bit_exact(cc, stage_data, params):
+    g = cc.preprocess(stage_data["all"])
+    vg = stage_data["vg"]
+    assert g["n_pass"] == len(stage_data["passed"])
+    assert np.array_equal(g["key_per_point"], vg["key_per_point"])     # the bit-exact voxel key
+    assert np.array_equal(bits(g["vox"]), bits(vg["vox"]))
+    # PointCloud2-style blob: 32-byte records, z/x/y shuffled, NaN + inf rows (PassThrough must drop them)
+    n = 20000
+    blob = np.zeros((n + 3, 8), np.float32)
+    src = stage_data["all"][40000:40000 + n]
+    blob[:n, 5], blob[:n, 1], blob[:n, 2] = src[:, 0], src[:, 1], src[:, 2]
+    blob[n] = np.nan
+    blob[n + 1, 5], blob[n + 1, 1], blob[n + 1, 2] = 0.1, np.inf, 0.5
+    blob[n + 2, 5], blob[n + 2, 1], blob[n + 2, 2] = 0.2, 0.0, 0.5   # 0.2f > 0.2 -> dropped
+    g = cc.preprocess(blob.view(np.uint8).reshape(-1), point_step=32, xoff=20, yoff=4, zoff=8, n=n + 3)
+    pz, _ = O.passthrough(src, 2, params.pass_z_min, params.pass_z_max)
+    px, _ = O.passthrough(pz, 0, params.pass_x_min, params.pass_x_max)
+    ov = O.voxel_grid(px, params.leaf)
+    assert g["n_pass"] == len(px) and np.array_equal(g["key_per_point"], ov["key_per_point"])
+    assert np.array_equal(bits(g["vox"]), bits(ov["vox"]))
+
+
+def test_segment_plane_inlier_sets_bit_exact(cc, stage_data):
+    vox, sac = stage_data["vg"]["vox"], stage_data["sac"]
+    g = cc.segment_plane(vox)
+    assert g["found"] and g["iters"] == sac["iters"]
+    assert np.array_equal(g["inliers_pre"], sac["inliers_pre"])
+    assert np.array_equal(bits(g["coeff"]), bits(sac["coeff"]))
+    assert np.array_equal(g["inliers"], sac["inliers"])
+    assert np.array_equal(bits(g["remain"]), bits(stage_data["remain"]))
+    # same seeded sample triplets handed in explicitly (north_star: "given the same seeded sample triplets")
+    g2 = cc.segment_plane(vox, triplets=sac["triplets"])
+    assert np.array_equal(g2["inliers"], sac["inliers"]) and np.array_equal(bits(g2["coeff"]), bits(sac["coeff"]))
+    # a different explicit list: long enough that the adaptive stop decides, not the list end
+    rng = np.random.default_rng(11)
+    trips = np.stack([rng.choice(len(vox), 3, replace=False) for _ in range(64)]).astype(np.int32)
+    o = O.sac_plane(vox, triplets=trips)
+    g3 = cc.segment_plane(vox, triplets=trips)
+    assert g3["iters"] == o["iters"] and np.array_equal(g3["inliers"], o["inliers"]) and np.array_equal(bits(g3["coeff"]), bits(o["coeff"]))
+
+
+def test_segment_plane_edge_cases(cc):
+    g = cc.segment_plane(np.zeros((0, 4), np.float32))
+    assert not g["found"] and len(g["inliers"]) == 0 and len(g["remain"]) == 0
+    two = np.array([[0, 0, 0.5, 1], [0.1, 0, 0.5, 1]], np.float32)
+    g = cc.segment_plane(two)
+    assert not g["found"] and np.array_equal(bits(g["remain"]), bits(two))   # ExtractIndices(negative) of nothing keeps all
+    # collinear cloud: every sample fails isSampleGood -> no model, like the oracle
+    line = np.ones((50, 4), np.float32)
+    line[:, 0] = np.arange(50) * 0.01
+    line[:, 1] = 0.0
+    line[:, 2] = 0.5
+    o = O.sac_plane(line)
+    g = cc.segment_plane(line)
+    assert g["found"] == o["found"] and np.array_equal(g["inliers"], o["inliers"])
+    # rough cloud: many RANSAC iterations, several scoring rounds
+    rng = np.random.default_rng(2)
+    pts = np.ones((4000, 4), np.float32)
+    pts[:, :3] = rng.uniform(-0.2, 0.2, (4000, 3)).astype(np.float32)
+    pts[:1200, 2] = (0.3 + 0.002 * rng.standard_normal(1200)).astype(np.float32)
+    o = O.sac_plane(pts)
+    g = cc.segment_plane(pts)
+    assert o["iters"] > 8 and g["iters"] == o["iters"]
+    assert np.array_equal(g["inliers"], o["inliers"]) and np.array_equal(bits(g["coeff"]), bits(o["coeff"]))
+
+
+def test_cluster_sets_equal(cc, stage_data):
+    idx, off = cc.cluster(stage_data["remain"])
+    assert np.array_equal(off, stage_data["coff"]) and np.array_equal(idx, stage_data["cidx"])
+    rng = np.random.default_rng(3)
+    blobs = [rng.uniform(0, 0.03, (n, 3)) + [0.07 * k, 0, 0] for k, n in enumerate([300, 400, 400, 150, 650])]
+    pts = np.ones((sum(len(b) for b in blobs), 4), np.float32)
+    pts[:, :3] = np.vstack(blobs)
+    pts = pts[rng.permutation(len(pts))]
+    oi, oo = O.cluster(pts, 0.02, 200, 25000)
+    gi, go = cc.cluster(pts)
+    assert list(go) == list(oo) and len(oo) == 5 and np.array_equal(gi, oi)   # 150-point blob filtered; 400/400 tie by smallest member
+    gi, go = cc.cluster(pts[:0])
+    assert list(go) == [0]
+
+
+def test_icp_per_iteration_correspondences_bit_exact(cc, stage_data, tmpl30):
+    src = stage_data["remain"][stage_data["cidx"]]
+    o = O.icp(src, tmpl30, trace_iters=128)
+    g = cc.icp(src, 0, trace_iters=128)
+    assert g["iters"] == o["iters"] and g["state"] == o["state"] and g["converged"] == o["converged"]
+    n = o["iters"]
+    assert np.array_equal(g["corr_trace"][:n], o["corr_trace"][:n])          # every iteration, every point
+    assert np.array_equal(bits(g["T_trace"][:n]), bits(o["T_trace"][:n]))
+    assert g["corr_hash"] == o["corr_hash"]
+    assert _pose_close(g["T"], o["T"]) and abs(g["fitness"] - o["fitness"]) < FIT_TOL
+    assert np.array_equal(bits(g["T"]), bits(o["T"])) and np.array_equal(bits(g["aligned"]), bits(o["aligned"]))
+
+
+def test_icp_guesses_and_streamed_template(cc, stage_data, tmpl30):
+    src = stage_data["remain"][stage_data["cidx"]]
+    c = src[:, :3].mean(0)
+    gs = []
+    for k in range(4):
+        a = k * np.pi / 2
+        G = np.eye(4, dtype=np.float32)
+        G[:3, :3] = [[np.cos(a), -np.sin(a), 0], [np.sin(a), np.cos(a), 0], [0, 0, 1]]
+        G[:3, 3] = c - G[:3, :3] @ c
+        gs.append(G)
+    gs[0] = np.eye(4, dtype=np.float32)
+    outs = [O.icp(src, tmpl30, guess=G) for G in gs]
+    best = int(np.argmin([o["fitness"] for o in outs]))
+    g = cc.icp(src, 0, guesses=np.stack(gs))
+    assert g["best_guess"] == best and g["corr_hash"] == outs[best]["corr_hash"]
+    assert np.array_equal(bits(g["T"]), bits(outs[best]["T"])) and g["fitness"] == outs[best]["fitness"]
+    # a template larger than shared memory (21 400-point class) streams through the window: same answers
+    rng = np.random.default_rng(4)
+    big = np.ones((21400, 4), np.float32)
+    big[:, :3] = rng.uniform(-0.1, 0.1, (21400, 3)).astype(np.float32)
+    big[:7250] = tmpl30
+    cc.set_template(2, big)
+    o = O.icp(src, big, max_iter=6)
+    p = default_params("cuboid")
+    p.icp_max_iter = 6
+    cc.set_params(p)
+    try:
+        g = cc.icp(src, 2)
+    finally:
+        cc.set_params(default_params("cuboid"))
+    assert g["corr_hash"] == o["corr_hash"] and np.array_equal(bits(g["T"]), bits(o["T"])) and g["fitness"] == o["fitness"]
+
+
+def test_icp_edge_cases(cc, tmpl30):
+    o = O.icp(tmpl30[:2], tmpl30)
+    g = cc.icp(tmpl30[:2], 0)
+    assert (g["converged"], g["iters"], g["state"]) == (o["converged"], o["iters"], o["state"]) == (0, 0, 5)
+    assert np.array_equal(g["T"], np.eye(4, dtype=np.float32)) and g["fitness"] == o["fitness"]
+    for n in (3, 255, 256, 257, 1024, 1025):
+        src = tmpl30[5:5 + n].copy()
+        src[:, :3] += np.float32(0.0007)
+        o = O.icp(src, tmpl30)
+        g = cc.icp(src, 0)
+        assert g["corr_hash"] == o["corr_hash"] and g["iters"] == o["iters"], n
+        assert np.array_equal(bits(g["T"]), bits(o["T"])) and g["fitness"] == o["fitness"], n
+    with pytest.raises(api.CuboidError) as e:
+        cc.icp(tmpl30[:10], 5)
+    assert e.value.status == api.E_NO_TEMPLATE
+
+
+def test_process_batch_matches_oracle_frame_by_frame(cc, tmpl30, params):
+    seeds = [0, 1, 2, 3, 4]
+    depth = synth.depth_batch("bench", seeds)
+    res = cc.process_batch(depth)
+    for i, s in enumerate(seeds):
+        _same_frame(res[i], O.process_frame(params, depth[i], tmpl30))
+    # intermediate arrays of one frame, fetched through the parity taps
+    f = 3
+    ref_pts = O.unproject(depth[f], params.fx, params.fy, params.cx, params.cy, params.depth_scale)
+    pz, _ = O.passthrough(ref_pts, 2, params.pass_z_min, params.pass_z_max)
+    px, _ = O.passthrough(pz, 0, params.pass_x_min, params.pass_x_max)
+    vg = O.voxel_grid(px, params.leaf)
+    assert np.array_equal(bits(cc.fetch(f, "points")), bits(px))
+    assert np.array_equal(cc.fetch(f, "voxel_keys"), vg["key_per_point"])
+    assert np.array_equal(bits(cc.fetch(f, "voxels")), bits(vg["vox"]))
+    assert np.array_equal(cc.fetch(f, "voxel_counts"), vg["voxel_count"])
+    sac = O.sac_plane(vg["vox"])
+    assert np.array_equal(cc.fetch(f, "inliers"), sac["inliers"])
+
+
+def test_process_cloud_entry_matches_depth_entry(cc, frame0, stage_data, tmpl30, params):
+    r = cc.process_cloud(stage_data["all"])
+    ref = O.process_cloud(params, stage_data["all"], 16, 0, 4, 8, len(stage_data["all"]), tmpl30)
+    _same_frame(r, ref)
+    _same_frame(r, O.process_frame(params, frame0, tmpl30))
+
+
+def test_batch_edge_frames(cc, tmpl30, params):
+    """empty / degenerate frames inside a batch: all-invalid depth, everything beyond pass limits, plane only."""
+    depth = np.zeros((4, 480, 640), np.uint16)
+    depth[1] = 2000                                   # z = 2 m: PassThrough z drops everything
+    depth[2] = synth.depth_frame("plane_only", 5)     # no object: nothing to cluster
+    depth[3] = synth.depth_frame("cuboid1", 9)
+    res = cc.process_batch(depth)
+    for i in range(4):
+        _same_frame(res[i], O.process_frame(params, depth[i], tmpl30))
+    assert res[1].n_points == 0 and res[1].n_voxels == 0 and res[1].plane_found == 0
+    assert res[0].n_voxels == 1                       # all-zero depth collapses into the origin voxel
+    assert res[2].n_clusters == 0 and res[3].n_clusters == 1
+
+
+def test_multi_guess_rotations_about_centroid(tmpl30, params):
+    depth = synth.depth_batch("bench", [21, 22])
+    rots = []
+    for k in range(4):
+        a = k * np.pi / 2
+        rots.append(np.array([[np.cos(a), -np.sin(a), 0], [np.sin(a), np.cos(a), 0], [0, 0, 1]], np.float32))
+    rots[0] = np.eye(3, dtype=np.float32)
+    rots = np.stack(rots)
+    p = default_params("cuboid")
+    p.n_guess, p.guess_mode = 4, 1
+    with api.CuboidCuda(p, max_points=640 * 480, max_batch=2) as h:
+        h.set_template(0, tmpl30)
+        h.set_guesses(rots, mode=1)
+        res = h.process_batch(depth)
+    for i in range(2):
+        _same_frame(res[i], O.process_frame(p, depth[i], tmpl30, guesses=rots))
+
+
+def test_multi_object_frame_and_second_template(tmpl100):
+    p = default_params("multi8")
+    depth = synth.depth_batch("multi8", [0])
+    with api.CuboidCuda(p, max_points=640 * 480, max_batch=1) as h:
+        h.set_template(0, tmpl100)
+        res = h.process_batch(depth)
+    ref = O.process_frame(p, depth[0], tmpl100)
+    assert ref.n_clusters >= 4
+    _same_frame(res[0], ref)
+
+
+def test_object_detection_variant_small_leaf(tmpl30):
+    """object_detection.launch: leaf 0.001 (inv_leaf = 999.99994f), threshold 0.01, extra PassThrough z [0, 0.75]."""
+    p = default_params("object")
+    p.icp_max_iter = 8
+    depth = synth.depth_batch("cuboid1", [3])
+    with api.CuboidCuda(p, max_points=640 * 480, max_batch=1) as h:
+        h.set_template(0, tmpl30)
+        res = h.process_batch(depth)
+    _same_frame(res[0], O.process_frame(p, depth[0], tmpl30))
+
+
+def test_full_size_batch_properties(cc, tmpl30, params):
+    """BASELINE-sized work: a 64-frame batch in 8-frame chunks must equal the same frames run one by one
+    (determinism, chunk independence) and a sample must equal the oracle."""
+    seeds = list(range(100, 164))
+    depth = synth.depth_batch("bench", seeds)
+    res = cc.process_batch(depth)
+    again = cc.process_batch(depth[::-1].copy())
+    for i in range(64):
+        a, b = res[i], again[63 - i]
+        assert bytes(a) == bytes(b)
+    for i in (0, 31, 63):
+        _same_frame(res[i], O.process_frame(params, depth[i], tmpl30))
+    assert all(r.n_clusters == 1 and r.cluster[0].converged for r in res)

@@ -1,0 +1,313 @@
+#!/usr/bin/env python
+"""bench.py — VGA frames/s of the cuboid_detection hot path (plane segmentation + clustering + cuboid ICP).
+
+Contract (driver): python bench.py --gpus N --steps K --warmup W  [--impl reference]
+  * one "step" = one pass of the whole hot path over this rank's batch of synthetic VGA depth frames
+    (stage 1a unprojection, PassThrough x2, VoxelGrid, RANSAC plane + ExtractIndices, Euclidean clustering,
+    ICP of every cluster against the make_cuboid.py template) through libcuboid_cuda's C ABI;
+  * `value`  : whole-job frames/s with the depth frames already resident in HBM, device time from CUDA events
+    recorded on the library's own stream (max over ranks);
+  * `e2e`    : the same metric through cuboid_process_batch with PINNED HOST depth buffers: host->device copy of
+    every frame and device->host copy of every frame's result inside the timed region;
+  * `roofline`: the dominant kernel (k_icp, FP32-pipe bound: un-fused FMUL/FADD) — algorithmic
+    flops from the per-frame results (8*S*T per nearest-neighbour pass) over its CUDA-event time, against the
+    un-fused FP32 peak measured in the same run; `roofline_hbm` is the same for the HBM-bound preprocess kernel
+    against MEASURED_PEAKS.json;
+  * `cpu_baseline`: the CPU oracle (restatement of the PCL path, 1 thread like the reference node) on a bounded
+    sample of the same frames;
+  * --impl reference: that CPU restatement on all host cores (the real PCL/ROS reference cannot be built
+    offline: DESIGN.md), same metric/config, rank 0 only.
+"""
+import argparse
+import json
+import os
+import subprocess
+import sys
+import threading
+import time
+
+ROOT = os.path.dirname(os.path.abspath(__file__))
+sys.path.insert(0, ROOT)
+
+import numpy as np  # noqa: E402
+
+METRIC = "VGA frames/s (plane seg + cuboid ICP)"
+W, H = 640, 480
+T_TEMPLATE = (0.2, 0.1, 0.03, 0.002)   # template_cuboid_L200_W100_H30_3faces.pcd, the launch default
+
+
+def _measured_peaks():
+    try:
+        return json.load(open(os.path.join(ROOT, "MEASURED_PEAKS.json"))), "measured"
+    except Exception:
+        return {"hbm_gbs": 6650.0}, "fallback"
+
+
+class ClockSampler:
+    """nvidia-smi clocks / throttle reasons DURING the timed region (B200_PROFILING.md recipe)."""
+    Q = ("index,clocks.sm,clocks.max.sm,power.draw,clocks_event_reasons.active,clocks_event_reasons.hw_slowdown,"
+         "clocks_event_reasons.hw_thermal_slowdown,clocks_event_reasons.sw_thermal_slowdown,clocks_event_reasons.sw_power_cap")
+
+    def __init__(self, gpu_index):
+        self.gpu, self.rows, self.proc = gpu_index, [], None
+
+    def start(self):
+        try:
+            self.proc = subprocess.Popen(["nvidia-smi", "-i", str(self.gpu), "--query-gpu=" + self.Q, "--format=csv,noheader,nounits",
+                                          "-lms", "200"], stdout=subprocess.PIPE, stderr=subprocess.DEVNULL, text=True)
+            self.thr = threading.Thread(target=self._read, daemon=True)
+            self.thr.start()
+        except Exception:
+            self.proc = None
+
+    def _read(self):
+        for line in self.proc.stdout:
+            self.rows.append([c.strip() for c in line.split(",")])
+
+    def stop(self):
+        if not self.proc:
+            return {"sm_mhz": None, "sm_max_mhz": None, "reasons": ["nvidia-smi unavailable"]}
+        self.proc.terminate()
+        try:
+            self.proc.wait(timeout=5)
+        except Exception:
+            self.proc.kill()
+        sm, mx, reasons = [], [], set()
+        names = ["hw_slowdown", "hw_thermal_slowdown", "sw_thermal_slowdown", "sw_power_cap"]
+        for r in self.rows:
+            try:
+                sm.append(float(r[1])); mx.append(float(r[2]))
+                for k, nm in enumerate(names):
+                    if r[5 + k].lower().startswith("active"):
+                        reasons.add(nm)
+            except Exception:
+                pass
+        return {"sm_mhz": float(np.median(sm)) if sm else None, "sm_max_mhz": max(mx) if mx else None,
+                "reasons": sorted(reasons), "samples": len(sm)}
+
+
+def make_frames(n, seed0, kind="bench"):
+    from perception_b200 import synth
+    return synth.depth_batch(kind, range(seed0, seed0 + n))
+
+
+def template():
+    from perception_b200 import pcd
+    return pcd.template_points(*T_TEMPLATE)
+
+
+def icp_flops(results, n_tmpl):
+    """Algorithmic FP32 ops of the ICP kernel: 8*S*T per nearest-neighbour pass; iterations + 1 fitness pass."""
+    ops = 0
+    for r in results:
+        for c in range(min(r.n_clusters, 16)):
+            cl = r.cluster[c]
+            ops += 8.0 * cl.size * n_tmpl * (cl.iterations + 1)
+    return ops
+
+
+def run_reference(args, rank, world):
+    """--impl reference: the CPU restatement of the PCL path on all host cores (oracle port; PCL itself is unbuildable here)."""
+    if rank != 0:
+        return
+    from concurrent.futures import ThreadPoolExecutor
+    from oracle import pyoracle as O
+    from perception_b200.params import default_params
+    cores = os.cpu_count() or 1
+    p = O.params_from(default_params("cuboid"))
+    tm = template()
+    per_step = max(cores, 2 * cores if args.frames >= 2 * cores else cores)
+    frames = make_frames(per_step, 0)
+
+    def one(i):
+        return O.process_frame(p, frames[i], tm)
+
+    def step():
+        with ThreadPoolExecutor(max_workers=cores) as ex:   # ctypes releases the GIL: frames run in parallel
+            return list(ex.map(one, range(per_step)))
+
+    for _ in range(args.warmup):
+        step()
+    t0 = time.perf_counter()
+    for _ in range(args.steps):
+        step()
+    dt = time.perf_counter() - t0
+    fps = per_step * args.steps / dt
+    line = {
+        "impl": "reference", "metric": METRIC, "value": fps, "unit": "frames/s", "n_gpus": args.gpus, "steps": args.steps,
+        "warmup": args.warmup, "ms_per_step": 1e3 * dt / args.steps, "higher_is_better": True, "scaling": "weak",
+        "vs_baseline": None, "dtype": "f32", "data": "synthetic",
+        "config": workload_config(args, args.frames),
+        "cpu_baseline": {"value": fps, "unit": "frames/s", "cores": cores, "kind": "port",
+                         "sample": "%d frames per step of the bench workload, frames parallel over %d host threads" % (per_step, cores)},
+        "e2e": {"value": fps, "unit": "frames/s", "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
+        "note": "CPU restatement of the PCL path (oracle/), not a PCL binary: PCL/ROS cannot be built offline",
+    }
+    print(json.dumps(line), flush=True)
+
+
+def workload_config(args, frames_per_gpu):
+    return {"workload": "batch of %d synthetic 640x480 D435 depth frames per GPU (table + one 200x100x30 mm cuboid), full hot path: "
+                        "unproject + passthrough + voxel(5 mm) + RANSAC plane + extract + Euclidean clustering + ICP vs "
+                        "template_cuboid_L200_W100_H30_3faces (7250 pts), 1 initial-pose hypothesis" % frames_per_gpu,
+            "frames_per_gpu": frames_per_gpu, "image": [W, H], "template_points": 7250, "leaf": 0.005, "n_guess": 1,
+            "l2": "inputs (%.0f MB of depth per GPU per step) are larger than the 126 MB L2" % (frames_per_gpu * W * H * 2 / 1e6),
+            "parallelism": "frames sharded per GPU, no data-path collective"}
+
+
+def main():
+    ap = argparse.ArgumentParser()
+    ap.add_argument("--gpus", type=int, default=1)
+    ap.add_argument("--steps", type=int, default=3)
+    ap.add_argument("--warmup", type=int, default=3)
+    ap.add_argument("--impl", default="b200")
+    ap.add_argument("--frames", type=int, default=1024, help="frames per GPU per step")
+    ap.add_argument("--chunk", type=int, default=256, help="frames resident per chunk (max_batch)")
+    ap.add_argument("--cpu-sample", type=int, default=64, help="frames of the CPU baseline sample")
+    ap.add_argument("--no-cpu", action="store_true")
+    args = ap.parse_args()
+
+    rank = int(os.environ.get("RANK", "0"))
+    local_rank = int(os.environ.get("LOCAL_RANK", "0"))
+    world = int(os.environ.get("WORLD_SIZE", "1"))
+
+    if args.impl == "reference":
+        run_reference(args, rank, world)
+        return
+
+    import torch
+    import torch.distributed as dist
+    from perception_b200 import api
+    from perception_b200.params import FrameResult, default_params
+    import ctypes as C
+
+    if not torch.cuda.is_available():
+        raise SystemExit("bench.py needs a CUDA device: libcuboid_cuda has no CPU fallback")
+    torch.cuda.set_device(local_rank)
+    if world > 1:
+        os.environ.setdefault("MASTER_ADDR", "127.0.0.1")
+        dist.init_process_group("nccl", device_id=torch.device("cuda", local_rank))
+
+    F = args.frames
+    p = default_params("cuboid")
+    tm = template()
+    t_gen = time.perf_counter()
+    frames = make_frames(F, rank * F)                         # uint16 [F,480,640], unique seeds per rank
+    t_gen = time.perf_counter() - t_gen
+    host = torch.empty((F, H, W), dtype=torch.uint16, pin_memory=True)
+    host.numpy()[...] = frames
+    dev = host.to("cuda", non_blocking=False)                 # resident input for the kernel-only number
+
+    cc = api.CuboidCuda(p, device=local_rank, max_points=W * H, max_batch=min(args.chunk, F))
+    cc.set_template(0, tm)
+    peak_unfused, peak_ffma = cc.measure_fp32_peak()
+
+    def barrier():
+        torch.cuda.synchronize()
+        if world > 1:
+            dist.barrier()
+        torch.cuda.synchronize()
+
+    # ---- device-resident: value + rooflines ----
+    for _ in range(args.warmup):
+        cc.process_batch_device(dev.data_ptr(), W, H, F)
+    barrier()
+    sampler = ClockSampler(local_rank)
+    sampler.start()
+    l0 = cc.launch_count()
+    stage = {k: 0.0 for k in ("preprocess", "voxel", "plane", "cluster", "icp")}
+    wall0 = time.perf_counter()
+    for _ in range(args.steps):
+        cc.process_batch_device(dev.data_ptr(), W, H, F)
+        for k, v in cc.stage_ms().items():
+            stage[k] += v
+    barrier()
+    wall = time.perf_counter() - wall0
+    launches = cc.launch_count() - l0
+    clocks = sampler.stop()
+    dev_ms = sum(stage.values())                               # CUDA events on the library's stream, summed over chunks
+    res = cc.batch_results(F)
+
+    # ---- end to end: pinned host depth in, host results out ----
+    for _ in range(min(args.warmup, 1)):
+        cc.process_batch(host)
+    barrier()
+    e0 = time.perf_counter()
+    for _ in range(args.steps):
+        res_e2e = cc.process_batch(host)
+    barrier()
+    e2e_s = time.perf_counter() - e0
+
+    # max over ranks (device time), sum of frames
+    t_dev, t_e2e, t_wall = dev_ms / 1e3, e2e_s, wall
+    if world > 1:
+        t = torch.tensor([t_dev, t_e2e, t_wall], dtype=torch.float64, device="cuda")
+        dist.all_reduce(t, op=dist.ReduceOp.MAX)
+        t_dev, t_e2e, t_wall = [float(x) for x in t.cpu()]
+        cnt = torch.tensor([F], dtype=torch.int64, device="cuda")
+        dist.all_reduce(cnt)
+        total_frames = int(cnt.item())
+    else:
+        total_frames = F
+
+    if rank == 0:
+        peaks, peak_src = _measured_peaks()
+        n_chunks = (F + cc.max_batch - 1) // cc.max_batch
+        ops = icp_flops(res, len(tm))
+        icp_s = stage["icp"] / 1e3 / args.steps
+        achieved = ops / icp_s / 1e12 if icp_s > 0 else 0.0
+        n_pts = sum(r.n_points for r in res)
+        pre_bytes = 2.0 * F * W * H + 16.0 * n_pts
+        pre_s = stage["preprocess"] / 1e3 / args.steps
+        pre_gbs = pre_bytes / pre_s / 1e9 if pre_s > 0 else 0.0
+        n_vox = sum(r.n_voxels for r in res)
+        vox_bytes = 16.0 * n_pts + 16.0 * n_vox
+        vox_s = stage["voxel"] / 1e3 / args.steps
+        line = {
+            "metric": METRIC, "value": total_frames * args.steps / t_dev, "unit": "frames/s", "n_gpus": world, "steps": args.steps,
+            "warmup": args.warmup, "ms_per_step": 1e3 * t_dev / args.steps, "higher_is_better": True, "scaling": "weak",
+            "vs_baseline": None, "dtype": "f32", "data": "synthetic",
+            "config": workload_config(args, F),
+            "clocks": clocks,
+            "e2e": {"value": total_frames * args.steps / t_e2e, "unit": "frames/s", "h2d_bytes_per_step": F * W * H * 2,
+                    "d2h_bytes_per_step": F * C.sizeof(FrameResult)},
+            "gpu_launches": int(launches),
+            "roofline": {"kernel": "k_icp", "bound": "fp32", "achieved": achieved, "peak": peak_unfused, "unit": "TFLOP/s",
+                         "frac": achieved / peak_unfused if peak_unfused else None, "traffic": None,
+                         "peak_source": "un-fused FMUL+FADD micro-benchmark in this run (bit-exactness forbids FFMA); FFMA peak %.1f" % peak_ffma,
+                         "launches_per_step": n_chunks, "ms_per_launch": 1e3 * icp_s / n_chunks,
+                         "algorithmic_flops_per_step": ops},
+            "roofline_hbm": {"kernel": "k_preprocess", "bound": "hbm", "achieved": pre_gbs, "peak": peaks.get("hbm_gbs"), "unit": "GB/s",
+                             "frac": pre_gbs / peaks.get("hbm_gbs") if peaks.get("hbm_gbs") else None, "traffic": None,
+                             "peak_source": peak_src, "ms_per_launch": 1e3 * pre_s / n_chunks, "algorithmic_bytes_per_step": pre_bytes},
+            "stages_ms_per_step": {k: v / args.steps for k, v in stage.items()},
+            "voxel_stage": {"achieved_gbs": vox_bytes / vox_s / 1e9 if vox_s > 0 else 0.0, "algorithmic_bytes_per_step": vox_bytes},
+            "wall_ms_per_step": 1e3 * t_wall / args.steps,
+            "frame_stats": {"mean_points": n_pts / F, "mean_voxels": n_vox / F, "mean_remain": sum(r.n_remain for r in res) / F,
+                            "mean_icp_iterations": float(np.mean([r.cluster[0].iterations for r in res if r.n_clusters > 0] or [0])),
+                            "accepted": int(sum(r.cluster[0].accepted for r in res if r.n_clusters > 0)),
+                            "e2e_equals_device": bool(all(bytes(a) == bytes(b) for a, b in zip(res, res_e2e)))},
+            "input_generation_s": t_gen,
+        }
+        if world == 1 and not args.no_cpu:
+            from oracle import pyoracle as O
+            op = O.params_from(p)
+            ns = min(args.cpu_sample, F)
+            O.process_frame(op, frames[0], tm)
+            c0 = time.perf_counter()
+            cpu_res = [O.process_frame(op, frames[i], tm) for i in range(ns)]
+            cdt = time.perf_counter() - c0
+            same = all(cpu_res[i].cluster[0].corr_hash == res[i].cluster[0].corr_hash and cpu_res[i].inlier_hash == res[i].inlier_hash
+                       for i in range(ns))
+            line["cpu_baseline"] = {"value": ns / cdt, "unit": "frames/s", "cores": 1, "kind": "port",
+                                    "sample": "first %d frames of the same batch, single thread (the reference node is one ros::spin thread)" % ns,
+                                    "gpu_matches_oracle_on_sample": bool(same)}
+        print(json.dumps(line), flush=True)
+    cc.close()
+    if world > 1:
+        dist.barrier()
+        dist.destroy_process_group()
+
+
+if __name__ == "__main__":
+    main()

@@ -70,18 +70,18 @@ def make_scene(kind="cuboid1", seed=0):
         b.yaw = rng.uniform(0.0, 2.0 * math.pi)
     elif kind == "multi8":
         sc.n_boxes = 8
-        # 4 x 2 lattice of cells 0.30 x 0.19 m centred on the optical-axis foot; box diagonal < cell - 4 cm
+        # 2 rows (world X) x 4 columns (world Y), long side along X: >= 9 cm between neighbours
         k = 0
         for ix in range(2):
             for iy in range(4):
                 b = sc.box[k]
-                if k % 2 == 0:
+                if (ix + iy) % 2 == 0:
                     b.L, b.W, b.H = 0.2, 0.1, 0.03
                 else:
                     b.L, b.W, b.H = 0.2, 0.075, 0.1
-                b.px = ax - 0.08 + (ix - 0.5) * 0.30 + rng.uniform(-0.005, 0.005)
-                b.py = (iy - 1.5) * 0.19 + rng.uniform(-0.005, 0.005)
-                b.yaw = rng.uniform(-0.25, 0.25) + (math.pi / 2 if True else 0.0)
+                b.px = 0.27 + 0.30 * ix + rng.uniform(-0.005, 0.005)
+                b.py = (iy - 1.5) * 0.2 + rng.uniform(-0.005, 0.005)
+                b.yaw = rng.uniform(-0.08, 0.08)
                 k += 1
     elif kind == "plane_only":
         sc.n_boxes = 0

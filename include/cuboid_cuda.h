@@ -189,6 +189,13 @@ int cuboid_frame_result_size(void);
 int64_t cuboid_launch_count(cuboid_handle* h);
 /* last batch: device time in ms of stage s (0 preprocess,1 voxel,2 plane,3 cluster,4 icp), CUDA events */
 int cuboid_stage_ms(cuboid_handle* h, float ms_out[5]);
+/* options: CUBOID_OPT_ICP_CULL (default 1; 0 = plain brute force over every template chunk, same results),
+ *          CUBOID_OPT_TAPS (default 1; 0 = do not keep the per-point voxel key / per-voxel count arrays) */
+enum { CUBOID_OPT_ICP_CULL = 1, CUBOID_OPT_TAPS = 2 };
+int cuboid_set_option(cuboid_handle* h, int option, int value);
+/* last batch: out[0] = source-template pairs the ICP kernel actually evaluated, out[1] = pairs of the
+ * brute-force equivalent (S*T per nearest-neighbour pass). Roofline accounting for the culled kernel. */
+int cuboid_icp_work(cuboid_handle* h, uint64_t out[2]);
 /* un-fused FP32 (FMUL+FADD) and FFMA throughput micro-benchmark, lane-ops/s -> TFLOP/s */
 int cuboid_measure_fp32_peak(cuboid_handle* h, double* unfused_tflops, double* ffma_tflops);
 

@@ -34,8 +34,9 @@ ABI_SYMBOLS = [
     "cuboid_batch_results", "cuboid_batch_fetch", "cuboid_pose_from_transform", "cuboid_bbox_corners",
     "cuboid_pack_fitness_key", "cuboid_unpack_fitness_key", "cuboid_strerror", "cuboid_last_error",
     "cuboid_abi_version", "cuboid_params_size", "cuboid_frame_result_size", "cuboid_launch_count",
-    "cuboid_stage_ms", "cuboid_measure_fp32_peak",
+    "cuboid_stage_ms", "cuboid_measure_fp32_peak", "cuboid_set_option", "cuboid_icp_work",
 ]
+OPT_ICP_CULL, OPT_TAPS = 1, 2
 
 
 class CuboidError(RuntimeError):
@@ -90,6 +91,8 @@ def load():
     L.cuboid_launch_count.restype = C.c_int64
     L.cuboid_stage_ms.argtypes = [vp, vp]
     L.cuboid_measure_fp32_peak.argtypes = [vp, C.POINTER(C.c_double), C.POINTER(C.c_double)]
+    L.cuboid_set_option.argtypes = [vp, i32, i32]
+    L.cuboid_icp_work.argtypes = [vp, vp]
     if L.cuboid_params_size() != C.sizeof(CuboidParams) or L.cuboid_frame_result_size() != C.sizeof(FrameResult):
         raise ImportError("struct layout mismatch between params.py and include/cuboid_cuda.h")
     _lib = L
@@ -303,6 +306,15 @@ class CuboidCuda:
         ms = np.zeros(5, np.float32)
         self._ck(self.lib.cuboid_stage_ms(self._h, _ptr(ms)), "cuboid_stage_ms")
         return dict(zip(["preprocess", "voxel", "plane", "cluster", "icp"], [float(x) for x in ms]))
+
+    def set_option(self, option, value):
+        self._ck(self.lib.cuboid_set_option(self._h, int(option), int(value)), "cuboid_set_option")
+
+    def icp_work(self):
+        """(pairs evaluated, brute-force-equivalent pairs) of the last batch."""
+        w = np.zeros(2, np.uint64)
+        self._ck(self.lib.cuboid_icp_work(self._h, _ptr(w)), "cuboid_icp_work")
+        return int(w[0]), int(w[1])
 
     def measure_fp32_peak(self):
         a, b = C.c_double(0), C.c_double(0)

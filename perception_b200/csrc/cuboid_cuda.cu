@@ -59,9 +59,12 @@ struct cuboid_handle {
     int* d_rng = nullptr; int rng_len = 0;
     int* d_triplets = nullptr; int triplets_cap = 0;
     float4* d_tmpl[CUBOID_MAX_TEMPLATES] = {}; int tmpl_n[CUBOID_MAX_TEMPLATES] = {}; int tmpl_pad[CUBOID_MAX_TEMPLATES] = {};
+    float4* d_boxes[CUBOID_MAX_TEMPLATES] = {}; int tmpl_nchunk[CUBOID_MAX_TEMPLATES] = {}; int tmpl_nsuper[CUBOID_MAX_TEMPLATES] = {};
+    unsigned long long* d_work = nullptr; unsigned long long work_total[2] = {0, 0};
+    int icp_cull = 1;
     float* d_guesses = nullptr; int n_guess = 1; int guess_mode = 0; bool have_guesses = false;
     int* d_trace_corr = nullptr; float* d_trace_T = nullptr; float4* d_aligned = nullptr;
-    int smem_optin = 0; int icp_resident_pts = 0;
+    int smem_optin = 0; int icp_smem_budget = 0;
     int last_chunk_base = 0, last_chunk_frames = 0, last_total_frames = 0;
     int taps = 1;
     int64_t launches = 0;
@@ -243,13 +246,18 @@ int run_chunk(cuboid_handle* h, const ChunkIn& in, int nf, cuboid_frame_result* 
         IcpArgs a{};
         a.remain = h->d_remain; a.idx_sorted = h->d_idx_sorted; a.offsets = h->d_offsets;
         a.tmpl = h->d_tmpl[tmpl_slot]; a.T = h->tmpl_n[tmpl_slot]; a.Tpad = h->tmpl_pad[tmpl_slot];
+        a.boxes = h->d_boxes[tmpl_slot]; a.nchunk = h->tmpl_nchunk[tmpl_slot]; a.nsuper = h->tmpl_nsuper[tmpl_slot];
         a.guesses = gs; a.n_guess = ng; a.guess_mode = gm;
         a.cur = h->d_cur; a.corr = h->d_corr; a.cd = h->d_cd; a.out = h->d_icp_out; a.res = d_res;
         a.P = h->P; a.M = h->M; a.KC = h->KC; a.max_iter = p.icp_max_iter;
         a.rot_thr = 1.0 - p.icp_tf_eps; a.trans_thr = p.icp_tf_eps; a.rel_mse = p.icp_rel_mse; a.abs_thr = 1e-12;
-        a.tmpl_resident_pts = h->icp_resident_pts;
-        a.corr_trace = trace_corr; a.T_trace = trace_T; a.cap_trace = cap_trace; a.aligned_out = nullptr;
-        const size_t dyn = (size_t)std::min(a.Tpad, h->icp_resident_pts) * 16;
+        const size_t box_bytes = (size_t)(2 * a.nchunk + 2 * a.nsuper) * 16;
+        if (box_bytes > (size_t)h->icp_smem_budget) return CUBOID_E_CAPACITY;
+        a.resident = (box_bytes + (size_t)a.Tpad * 16 <= (size_t)h->icp_smem_budget) ? 1 : 0;
+        a.cull = h->icp_cull;
+        a.work = h->d_work;
+        a.corr_trace = trace_corr; a.T_trace = trace_T; a.cap_trace = cap_trace;
+        const size_t dyn = box_bytes + (a.resident ? (size_t)a.Tpad * 16 : 0);
         k_icp<<<dim3(ng, CUBOID_MAX_CLUSTERS, nf), ICP_THREADS, dyn, st>>>(a);
         const int tot = nf * CUBOID_MAX_CLUSTERS;
         k_icp_select<<<(tot + 127) / 128, 128, 0, st>>>(h->d_icp_out, d_res, nf, ng, p.icp_fitness_gate, h->d_cur, h->M, h->d_offsets,
@@ -379,8 +387,11 @@ int cuboid_create(cuboid_handle** out, const cuboid_params* p, int device, int m
     CA(upload_rng(h));
     CA(ensure_icp_scratch(h, h->B, std::max(1, (int)p->n_guess)));
     cudaDeviceGetAttribute(&h->smem_optin, cudaDevAttrMaxSharedMemoryPerBlockOptin, device);
-    h->icp_resident_pts = ((h->smem_optin - 6144) / 16 / ICP_CHUNK) * ICP_CHUNK;
-    if (cudaFuncSetAttribute(k_icp, cudaFuncAttributeMaxDynamicSharedMemorySize, h->icp_resident_pts * 16) != cudaSuccess) return fail(CUBOID_E_CUDA);
+    h->icp_smem_budget = h->smem_optin - 4096;   // static shared memory of k_icp stays well below 4 KB
+    if (cudaFuncSetAttribute(k_icp, cudaFuncAttributeMaxDynamicSharedMemorySize, h->icp_smem_budget) != cudaSuccess) return fail(CUBOID_E_CUDA);
+    CA(dalloc(h, &h->d_work, (size_t)2));
+    if (cudaMemset(h->d_work, 0, 16) != cudaSuccess) return fail(CUBOID_E_CUDA);
+    { const char* ec = std::getenv("CUBOID_ICP_CULL"); if (ec) h->icp_cull = atoi(ec) ? 1 : 0; }
     if (cudaFuncSetAttribute(k_sac_plane, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)sizeof(SacShared)) != cudaSuccess) return fail(CUBOID_E_CUDA);
 #undef CA
     *out = h;
@@ -394,9 +405,10 @@ int cuboid_destroy(cuboid_handle* h) {
     void* ptrs[] = {h->d_depth, h->d_blob, h->d_n_in, h->d_pts, h->d_keysA, h->d_keysB, h->d_kpp, h->d_hist, h->d_vox, h->d_vcount, h->d_shuffled,
                     h->d_inl_pre, h->d_inl, h->d_remain, h->d_parent, h->d_csize, h->d_crank, h->d_idx_sorted, h->d_offsets, h->d_roots,
                     h->d_cur, h->d_corr, h->d_cd, h->d_icp_out, h->d_scr, h->d_desc1, h->d_desc2, h->d_ticket, h->d_res, h->d_rng,
-                    h->d_triplets, h->d_guesses, h->d_trace_corr, h->d_trace_T, h->d_aligned};
+                    h->d_triplets, h->d_guesses, h->d_trace_corr, h->d_trace_T, h->d_aligned, h->d_work};
     for (void* q : ptrs) if (q) cudaFree(q);
     for (auto& t : h->d_tmpl) if (t) cudaFree(t);
+    for (auto& t : h->d_boxes) if (t) cudaFree(t);
     for (auto& e : h->ev) if (e) cudaEventDestroy(e);
     if (h->stream) cudaStreamDestroy(h->stream);
     delete h;
@@ -414,23 +426,81 @@ int cuboid_set_params(cuboid_handle* h, const cuboid_params* p) {
     return CUBOID_OK;
 }
 
+namespace {
+struct KdItem { float x, y, z; int orig; };
+// Re-orders items so that every run of 64 is spatially compact: split the chunk count in half along the widest
+// axis (median by nth_element, ties by original index so the order is deterministic), recurse.
+void kd_order(KdItem* a, int n) {
+    if (n <= ICP_CHUNK) return;
+    float mn[3] = {a[0].x, a[0].y, a[0].z}, mx[3] = {a[0].x, a[0].y, a[0].z};
+    for (int i = 1; i < n; ++i) {
+        mn[0] = std::min(mn[0], a[i].x); mx[0] = std::max(mx[0], a[i].x);
+        mn[1] = std::min(mn[1], a[i].y); mx[1] = std::max(mx[1], a[i].y);
+        mn[2] = std::min(mn[2], a[i].z); mx[2] = std::max(mx[2], a[i].z);
+    }
+    int ax = 0;
+    for (int d = 1; d < 3; ++d) if (mx[d] - mn[d] > mx[ax] - mn[ax]) ax = d;
+    const int nch = (n + ICP_CHUNK - 1) / ICP_CHUNK;
+    const int k = ICP_CHUNK * ((nch + 1) / 2);
+    auto key = [ax](const KdItem& p) { return ax == 0 ? p.x : (ax == 1 ? p.y : p.z); };
+    std::nth_element(a, a + k, a + n, [&](const KdItem& p, const KdItem& q) {
+        const float kp = key(p), kq = key(q);
+        return kp < kq || (kp == kq && p.orig < q.orig);
+    });
+    kd_order(a, k);
+    kd_order(a + k, n - k);
+}
+}  // namespace
+
 int cuboid_set_template(cuboid_handle* h, int slot, const float* xyz, int stride_bytes, int n) {
     if (!h || slot < 0 || slot >= CUBOID_MAX_TEMPLATES || !xyz || n < 1 || stride_bytes < 12) return CUBOID_E_INVALID;
     cudaSetDevice(h->device);
-    const int pad = ((n + ICP_CHUNK - 1) / ICP_CHUNK) * ICP_CHUNK;
-    std::vector<float4> host(pad);
+    const int nchunk = (n + ICP_CHUNK - 1) / ICP_CHUNK;
+    const int nsuper = (nchunk + ICP_SUPER - 1) / ICP_SUPER;
+    const int pad = nchunk * ICP_CHUNK;
+    std::vector<KdItem> items(n);
     const unsigned char* b = reinterpret_cast<const unsigned char*>(xyz);
     for (int i = 0; i < n; ++i) {
         float v[3];
         std::memcpy(v, b + (size_t)i * stride_bytes, 12);
-        host[i] = make_float4(v[0], v[1], v[2], 1.0f);
+        items[i] = KdItem{v[0], v[1], v[2], i};
+    }
+    kd_order(items.data(), n);
+    std::vector<float4> host(pad), boxes(2 * (size_t)nchunk + 2 * (size_t)nsuper);
+    for (int i = 0; i < n; ++i) {
+        float w;
+        std::memcpy(&w, &items[i].orig, 4);   // .w carries the ORIGINAL template index (ties resolve to the lowest one)
+        host[i] = make_float4(items[i].x, items[i].y, items[i].z, w);
     }
     // far sentinels: their distance is huge but finite, so they never win and never produce NaN
-    for (int i = n; i < pad; ++i) host[i] = make_float4(1.0e18f, 1.0e18f, 1.0e18f, 1.0f);
+    const int big = 0x7fffffff;
+    float wbig;
+    std::memcpy(&wbig, &big, 4);
+    for (int i = n; i < pad; ++i) host[i] = make_float4(1.0e18f, 1.0e18f, 1.0e18f, wbig);
+    const float inf = INFINITY;
+    for (int c = 0; c < nchunk; ++c) {
+        float4 lo = make_float4(inf, inf, inf, 0.f), hi = make_float4(-inf, -inf, -inf, 0.f);
+        for (int j = c * ICP_CHUNK; j < std::min(n, (c + 1) * ICP_CHUNK); ++j) {
+            lo.x = std::min(lo.x, host[j].x); lo.y = std::min(lo.y, host[j].y); lo.z = std::min(lo.z, host[j].z);
+            hi.x = std::max(hi.x, host[j].x); hi.y = std::max(hi.y, host[j].y); hi.z = std::max(hi.z, host[j].z);
+        }
+        boxes[2 * c] = lo; boxes[2 * c + 1] = hi;
+    }
+    for (int sc = 0; sc < nsuper; ++sc) {
+        float4 lo = make_float4(inf, inf, inf, 0.f), hi = make_float4(-inf, -inf, -inf, 0.f);
+        for (int c = sc * ICP_SUPER; c < std::min(nchunk, (sc + 1) * ICP_SUPER); ++c) {
+            lo.x = std::min(lo.x, boxes[2 * c].x); lo.y = std::min(lo.y, boxes[2 * c].y); lo.z = std::min(lo.z, boxes[2 * c].z);
+            hi.x = std::max(hi.x, boxes[2 * c + 1].x); hi.y = std::max(hi.y, boxes[2 * c + 1].y); hi.z = std::max(hi.z, boxes[2 * c + 1].z);
+        }
+        boxes[2 * (size_t)nchunk + 2 * sc] = lo; boxes[2 * (size_t)nchunk + 2 * sc + 1] = hi;
+    }
     if (h->d_tmpl[slot]) { cudaFree(h->d_tmpl[slot]); h->d_tmpl[slot] = nullptr; }
+    if (h->d_boxes[slot]) { cudaFree(h->d_boxes[slot]); h->d_boxes[slot] = nullptr; }
     CKS(h, dalloc(h, &h->d_tmpl[slot], (size_t)pad));
+    CKS(h, dalloc(h, &h->d_boxes[slot], boxes.size()));
     CK(h, cudaMemcpy(h->d_tmpl[slot], host.data(), sizeof(float4) * pad, cudaMemcpyHostToDevice));
-    h->tmpl_n[slot] = n; h->tmpl_pad[slot] = pad;
+    CK(h, cudaMemcpy(h->d_boxes[slot], boxes.data(), sizeof(float4) * boxes.size(), cudaMemcpyHostToDevice));
+    h->tmpl_n[slot] = n; h->tmpl_pad[slot] = pad; h->tmpl_nchunk[slot] = nchunk; h->tmpl_nsuper[slot] = nsuper;
     return CUBOID_OK;
 }
 
@@ -651,6 +721,7 @@ static int process_frames(cuboid_handle* h, const uint16_t* depth, bool on_devic
     cudaSetDevice(h->device);
     CKS(h, ensure_results(h, n_frames));
     for (float& m : h->stage_ms) m = 0.f;
+    CK(h, cudaMemsetAsync(h->d_work, 0, 16, h->stream));
     for (int base = 0; base < n_frames; base += h->B) {
         const int nf = std::min(h->B, n_frames - base);
         ChunkIn in;
@@ -669,6 +740,7 @@ static int process_frames(cuboid_handle* h, const uint16_t* depth, bool on_devic
         h->last_chunk_base = base; h->last_chunk_frames = nf;
     }
     h->last_total_frames = n_frames;
+    CK(h, cudaMemcpy(h->work_total, h->d_work, 16, cudaMemcpyDeviceToHost));
     return CUBOID_OK;
 }
 
@@ -821,6 +893,20 @@ int64_t cuboid_launch_count(cuboid_handle* h) { return h ? h->launches : 0; }
 int cuboid_stage_ms(cuboid_handle* h, float ms_out[5]) {
     if (!h || !ms_out) return CUBOID_E_INVALID;
     for (int i = 0; i < 5; ++i) ms_out[i] = h->stage_ms[i];
+    return CUBOID_OK;
+}
+
+int cuboid_set_option(cuboid_handle* h, int option, int value) {
+    if (!h) return CUBOID_E_INVALID;
+    switch (option) {
+        case CUBOID_OPT_ICP_CULL: h->icp_cull = value ? 1 : 0; return CUBOID_OK;
+        case CUBOID_OPT_TAPS: h->taps = value ? 1 : 0; return CUBOID_OK;
+        default: return CUBOID_E_INVALID;
+    }
+}
+int cuboid_icp_work(cuboid_handle* h, uint64_t out[2]) {
+    if (!h || !out) return CUBOID_E_INVALID;
+    out[0] = h->work_total[0]; out[1] = h->work_total[1];
     return CUBOID_OK;
 }
 

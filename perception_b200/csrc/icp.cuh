@@ -3,16 +3,22 @@
 // the whole ICP loop — nearest neighbours, Umeyama, 3x3 Jacobi SVD, incremental transform,
 // DefaultConvergenceCriteria — runs on the device, no host round trip.
 //
-//   nearest neighbour   brute force over the template, which is staged ONCE in shared memory by TMA bulk
-//                       copies; d2 = ((dx*dx)+dy*dy)+dz*dz un-fused FP32; each thread keeps R source points in
-//                       registers so one broadcast LDS.128 feeds R*8 FP32 ops; running minimum per 64-point
-//                       template chunk with FMNMX, chunk id kept on strict '<', the exact index is recovered
-//                       by re-scanning the winning chunk (ties -> lowest template index, the canonical choice)
+//   nearest neighbour   brute-force tiles with exact culling. The template is re-ordered once on the host into
+//                       spatially compact 64-point chunks (kd split), each carrying its AABB; it is staged ONCE in
+//                       shared memory by TMA bulk copies. A warp task = 64 consecutive source points (2 per lane
+//                       in registers). Per chunk the warp first evaluates the AABB lower bound with the same
+//                       un-fused rounding sequence as the distance itself and skips the chunk only if the bound
+//                       is strictly above every point's running minimum; surviving chunks are scanned brute
+//                       force: one broadcast LDS.128 feeds 2*8 FP32 ops, d2 = ((dx*dx)+dy*dy)+dz*dz, running
+//                       minimum with FMNMX. The winner is recovered by re-scanning the minimal chunk(s) for the
+//                       LOWEST ORIGINAL template index at that distance, i.e. exactly what a brute-force scan in
+//                       template order with strict '<' returns (the canonical tie rule).
 //   Umeyama             canonical 256-lane strided partial sums + xor-butterfly + 8 warp partials left to right
 //                       (identical in oracle/cuboid_oracle.cpp: canon_reduce), Eigen JacobiSVD restated
 //   convergence         max iterations | transform epsilon | |dMSE| < 1e-12 | rel dMSE < icp_fitness_score
 //
-// Roofline: FP32 pipe (un-fused): 8*S*T ops per iteration per hypothesis (+ S*T FMNMX on the ALU pipe); HBM ~ 0.
+// Roofline: FP32 pipe (un-fused). Brute force is 8*S*T ops per pass; the culled kernel reports both the
+// pairs it actually evaluated and the brute-force equivalent (IcpArgs::work).
 #pragma once
 #include "common.cuh"
 #include "ransac.cuh"   // TMA bulk-copy helpers
@@ -30,25 +36,31 @@ struct IcpArgs {
     const float4* remain;    // [F][P]
     const int* idx_sorted;   // [F][M]
     const int* offsets;      // [F][KC+1]
-    const float4* tmpl;      // [Tpad] padded to a multiple of 64 with far sentinels
-    int T, Tpad;
+    const float4* tmpl;      // [Tpad] kd-ordered 64-point chunks, .w = original template index (bits); far sentinels pad the tail
+    const float4* boxes;     // [2*nchunk + 2*nsuper] AABB (lo, hi) of every chunk, then of every 8 consecutive chunks
+    int T, Tpad, nchunk, nsuper;
     const float* guesses;    // n_guess * (16 | 9) or NULL
     int n_guess, guess_mode;
     float4* cur;             // [F][G][M]
-    int* corr;               // [F][G][M]
+    int* corr;               // [F][G][M]  correspondences as positions in the kd-ordered template
     float* cd;               // [F][G][M]
     IcpOut* out;             // [F][MAXC][G]
     cuboid_frame_result* res;
     int P, M, KC;
     int max_iter;
     double rot_thr, trans_thr, rel_mse, abs_thr;
-    int tmpl_resident_pts;   // template points that fit the dynamic shared memory window (multiple of 64)
+    int resident;            // 1: the whole template sits in shared memory; 0: chunks are read through L1/L2
+    int cull;                // 1: skip chunks whose AABB lower bound exceeds the running minimum (exact)
+    unsigned long long* work;   // [2] += (chunk evaluations * 64 points * 64 pairs, brute-force pairs) or NULL
     int* corr_trace; float* T_trace; int cap_trace;   // debug taps for problem (0,0,0)
-    float4* aligned_out;                               // optional: transformCloud(src, final) of problem (0,0,best)
 };
 
-constexpr int ICP_THREADS = 256;
-constexpr int ICP_CHUNK = 64;
+constexpr int ICP_THREADS = 512;
+constexpr int ICP_LANES = 256;     // threads that own the 256 canonical reduction lanes
+constexpr int ICP_CHUNK = 64;      // template points per chunk
+constexpr int ICP_SUPER = 8;       // chunks per super box
+constexpr int ICP_R = 2;           // source points per lane in a nearest-neighbour task (64 points per warp task)
+
 
 struct M3f { float a[3][3]; };
 struct Rotf { float c, s; };
@@ -210,31 +222,6 @@ __device__ __forceinline__ void canon_block_reduce(Tq (&v)[NQ], Tq* s_part /* [N
     __syncthreads();
 }
 
-// nearest neighbour of R source points (registers) against template points [0, n_t) in shared memory.
-// best/bchunk persist across template windows; chunk ids are global (chunk_base + local).
-template <int R>
-__device__ __forceinline__ void nn_window(const float4* __restrict__ s_t, int n_t, int chunk_base, const float (&sx)[R],
-                                          const float (&sy)[R], const float (&sz)[R], float (&best)[R], int (&bchunk)[R]) {
-    for (int c0 = 0; c0 < n_t; c0 += ICP_CHUNK) {
-        float m[R];
-#pragma unroll
-        for (int r = 0; r < R; ++r) m[r] = __int_as_float(0x7f800000);
-#pragma unroll 8
-        for (int jj = 0; jj < ICP_CHUNK; ++jj) {
-            const float4 t = s_t[c0 + jj];
-#pragma unroll
-            for (int r = 0; r < R; ++r) {
-                const float dx = sx[r] - t.x, dy = sy[r] - t.y, dz = sz[r] - t.z;
-                const float d = ((dx * dx) + dy * dy) + dz * dz;
-                m[r] = fminf(m[r], d);
-            }
-        }
-        const int cid = chunk_base + c0 / ICP_CHUNK;
-#pragma unroll
-        for (int r = 0; r < R; ++r)
-            if (m[r] < best[r]) { best[r] = m[r]; bchunk[r] = cid; }
-    }
-}
 
 struct IcpShared {
     unsigned long long bar;
@@ -246,78 +233,120 @@ struct IcpShared {
     float fin[16];      // final_transformation_
     float guess[16];
     int done, converged, state, iters;
+    int task;           // dynamic task counter of the nearest-neighbour pass
     double prev_mse;
 };
 
-// one full NN pass over source points cur[0..S): writes corr[] / cd[]
-__device__ void icp_nn_pass(const IcpArgs& a, const float4* s_tmpl, bool resident, const float4* cur, int S, int* corr, float* cd,
-                            float4* s_window) {
-    const int NT = ICP_THREADS;
-    for (int g0 = 0; g0 < S; g0 += NT * 4) {
-        // R = 4 rounds of NT points; inactive slots replicate a valid point and are not stored
-        float sx[4], sy[4], sz[4], best[4];
-        int bch[4];
+__device__ __forceinline__ float dist2(float sx, float sy, float sz, const float4 t) {
+    const float dx = sx - t.x, dy = sy - t.y, dz = sz - t.z;
+    return ((dx * dx) + dy * dy) + dz * dz;   // FLANN L2_Simple order, un-fused
+}
+// Lower bound of dist2(s, t) over every t inside the box [lo, hi], evaluated with the same rounding sequence:
+// float subtraction, squaring and addition are monotone, so lb <= dist2(s,t) holds bit-for-bit.
+__device__ __forceinline__ float box_lb(float sx, float sy, float sz, const float4 lo, const float4 hi) {
+    const float dx = fmaxf(fmaxf(lo.x - sx, sx - hi.x), 0.f);
+    const float dy = fmaxf(fmaxf(lo.y - sy, sy - hi.y), 0.f);
+    const float dz = fmaxf(fmaxf(lo.z - sz, sz - hi.z), 0.f);
+    return ((dx * dx) + dy * dy) + dz * dz;
+}
+
+// One nearest-neighbour pass over cur[0..S): writes corr[] (kd-ordered template position) and cd[].
+// On entry corr[] holds a valid template position per point (the previous pass's answer, or 0): its distance
+// seeds the running minimum so the culling is tight from the first chunk.
+//
+// Exactness: a chunk is skipped only when lb > best (strict) for all 64 points of the warp task, so no chunk
+// holding a minimiser or a tie is ever skipped; ties between chunks are recorded and resolved to the LOWEST
+// ORIGINAL template index — the answer of a brute-force scan in original order with strict '<'.
+template <bool RESIDENT>
+__device__ __forceinline__ void icp_nn_pass(const IcpArgs& a, IcpShared& sh, const float4* s_tmpl, const float4* s_box, const float4* cur,
+                                            int S, int* corr, float* cd, unsigned long long& evaluated) {
+    const int lane = threadIdx.x & 31;
+    const float4* tp = RESIDENT ? s_tmpl : a.tmpl;
+    const int ntask = (S + 32 * ICP_R - 1) / (32 * ICP_R);
+    const float4* s_sbox = s_box + 2 * a.nchunk;
+    const bool cull = a.cull != 0;
+    while (true) {
+        int task = 0;
+        if (lane == 0) task = atomicAdd(&sh.task, 1);
+        task = __shfl_sync(FULL_MASK, task, 0);
+        if (task >= ntask) break;
+        float sx[ICP_R], sy[ICP_R], sz[ICP_R], best[ICP_R];
+        int bch[ICP_R], t1[ICP_R], t2[ICP_R], nt[ICP_R];
 #pragma unroll
-        for (int r = 0; r < 4; ++r) {
-            const int i = g0 + r * NT + threadIdx.x;
-            const float4 p = cur[i < S ? i : (S - 1)];
+        for (int r = 0; r < ICP_R; ++r) {
+            const int i = task * 32 * ICP_R + r * 32 + lane;
+            const int ii = i < S ? i : S - 1;
+            const float4 p = cur[ii];
             sx[r] = p.x; sy[r] = p.y; sz[r] = p.z;
-            best[r] = __int_as_float(0x7f800000);
-            bch[r] = 0;
+            const int seed = corr[ii];
+            best[r] = dist2(sx[r], sy[r], sz[r], tp[seed]);
+            bch[r] = seed / ICP_CHUNK; t1[r] = 0; t2[r] = 0; nt[r] = 0;
         }
-        const int rounds = min(4, (S - g0 + NT - 1) / NT);
-        if (resident) {
-            if (rounds > 2) nn_window<4>(s_tmpl, a.Tpad, 0, sx, sy, sz, best, bch);
-            else if (rounds == 2) {
-                float sx2[2] = {sx[0], sx[1]}, sy2[2] = {sy[0], sy[1]}, sz2[2] = {sz[0], sz[1]}, b2[2] = {best[0], best[1]};
-                int c2[2] = {0, 0};
-                nn_window<2>(s_tmpl, a.Tpad, 0, sx2, sy2, sz2, b2, c2);
-                best[0] = b2[0]; best[1] = b2[1]; bch[0] = c2[0]; bch[1] = c2[1];
-            } else {
-                float sx1[1] = {sx[0]}, sy1[1] = {sy[0]}, sz1[1] = {sz[0]}, b1[1] = {best[0]};
-                int c1[1] = {0};
-                nn_window<1>(s_tmpl, a.Tpad, 0, sx1, sy1, sz1, b1, c1);
-                best[0] = b1[0]; bch[0] = c1[0];
-            }
-        } else {
-            // template larger than shared memory: stream it through the window (block-uniform loop)
-            for (int w0 = 0; w0 < a.Tpad; w0 += a.tmpl_resident_pts) {
-                const int wn = min(a.tmpl_resident_pts, a.Tpad - w0);
-                __syncthreads();
-                for (int j = threadIdx.x; j < wn; j += NT) s_window[j] = a.tmpl[w0 + j];
-                __syncthreads();
-                nn_window<4>(s_window, wn, w0 / ICP_CHUNK, sx, sy, sz, best, bch);
-            }
-        }
-        // recover the exact index: first j in the winning chunk whose distance equals the minimum
+        for (int sc = 0; sc < a.nsuper; ++sc) {
+            if (cull) {
+                const float4 lo = s_sbox[2 * sc], hi = s_sbox[2 * sc + 1];
+                bool skip = true;
 #pragma unroll
-        for (int r = 0; r < 4; ++r) {
-            const int i = g0 + r * NT + threadIdx.x;
-            if (r >= rounds || i >= S) continue;
-            const float4* ch = (resident ? s_tmpl : a.tmpl) + (size_t)bch[r] * ICP_CHUNK;
-            int jbest = 0;
-            for (int jj = ICP_CHUNK - 1; jj >= 0; --jj) {
-                const float4 t = ch[jj];
-                const float dx = sx[r] - t.x, dy = sy[r] - t.y, dz = sz[r] - t.z;
-                const float d = ((dx * dx) + dy * dy) + dz * dz;
-                if (d == best[r]) jbest = jj;
+                for (int r = 0; r < ICP_R; ++r) skip = skip && (box_lb(sx[r], sy[r], sz[r], lo, hi) > best[r]);
+                if (__all_sync(FULL_MASK, skip)) continue;
             }
-            corr[i] = bch[r] * ICP_CHUNK + jbest;
+            const int c_end = min(a.nchunk, (sc + 1) * ICP_SUPER);
+            for (int c = sc * ICP_SUPER; c < c_end; ++c) {
+                if (cull) {
+                    const float4 lo = s_box[2 * c], hi = s_box[2 * c + 1];
+                    bool skip = true;
+#pragma unroll
+                    for (int r = 0; r < ICP_R; ++r) skip = skip && (box_lb(sx[r], sy[r], sz[r], lo, hi) > best[r]);
+                    if (__all_sync(FULL_MASK, skip)) continue;
+                }
+                float m[ICP_R];
+#pragma unroll
+                for (int r = 0; r < ICP_R; ++r) m[r] = __int_as_float(0x7f800000);
+                const float4* ch = tp + (size_t)c * ICP_CHUNK;
+#pragma unroll 16
+                for (int jj = 0; jj < ICP_CHUNK; ++jj) {
+                    const float4 t = ch[jj];
+#pragma unroll
+                    for (int r = 0; r < ICP_R; ++r) m[r] = fminf(m[r], dist2(sx[r], sy[r], sz[r], t));
+                }
+                ++evaluated;
+#pragma unroll
+                for (int r = 0; r < ICP_R; ++r) {
+                    if (m[r] < best[r]) { best[r] = m[r]; bch[r] = c; nt[r] = 0; }
+                    else if (m[r] == best[r] && c != bch[r]) {
+                        if (nt[r] == 0) t1[r] = c; else if (nt[r] == 1) t2[r] = c;
+                        ++nt[r];
+                    }
+                }
+            }
+        }
+        // recover the winner: lowest ORIGINAL index among all template points at distance == best
+#pragma unroll
+        for (int r = 0; r < ICP_R; ++r) {
+            const int i = task * 32 * ICP_R + r * 32 + lane;
+            if (i >= S) continue;
+            int win_orig = 0x7fffffff, win_pos = 0;
+            const int ncand = nt[r] > 2 ? a.nchunk : 1 + nt[r];
+            for (int k = 0; k < ncand; ++k) {
+                const int c = nt[r] > 2 ? k : (k == 0 ? bch[r] : (k == 1 ? t1[r] : t2[r]));
+                const float4* ch = tp + (size_t)c * ICP_CHUNK;
+                for (int jj = 0; jj < ICP_CHUNK; ++jj) {
+                    const float4 t = ch[jj];
+                    if (dist2(sx[r], sy[r], sz[r], t) == best[r]) {
+                        const int o = __float_as_int(t.w);
+                        if (o < win_orig) { win_orig = o; win_pos = c * ICP_CHUNK + jj; }
+                    }
+                }
+            }
+            corr[i] = win_pos;
             cd[i] = best[r];
         }
     }
 }
 
-__global__ void __launch_bounds__(ICP_THREADS, 1) k_icp(const IcpArgs a) {
-    extern __shared__ __align__(128) unsigned char smem_raw[];
-    float4* s_tmpl = reinterpret_cast<float4*>(smem_raw);
-    __shared__ IcpShared S_;
-    IcpShared& sh = S_;
-
+template <bool RESIDENT>
+__device__ __forceinline__ void icp_body(const IcpArgs& a, IcpShared& sh, float4* s_tmpl, float4* s_box) {
     const int g = blockIdx.x, c = blockIdx.y, f = blockIdx.z;
-    const cuboid_frame_result& R = a.res[f];
-    const int ncl = min(R.n_clusters, CUBOID_MAX_CLUSTERS);
-    if (c >= ncl) return;
     const int* offsets = a.offsets + (size_t)f * (a.KC + 1);
     const int o0 = offsets[c], S = offsets[c + 1] - o0;
     const int* idx = a.idx_sorted + (size_t)f * a.M + o0;
@@ -327,24 +356,24 @@ __global__ void __launch_bounds__(ICP_THREADS, 1) k_icp(const IcpArgs a) {
     int* corr = a.corr + pbase;
     float* cd = a.cd + pbase;
     IcpOut& out = a.out[((size_t)f * CUBOID_MAX_CLUSTERS + c) * a.n_guess + g];
-    const bool resident = a.Tpad <= a.tmpl_resident_pts;
     const bool trace = a.corr_trace && f == 0 && c == 0 && g == 0;
+    const float4* tp = RESIDENT ? s_tmpl : a.tmpl;
+    const bool lane_thread = threadIdx.x < ICP_LANES;
 
-    // ---- stage the template once (TMA bulk copies, 32 KB each) ----
+    // ---- stage the template (resident case) and the boxes with TMA bulk copies ----
     if (threadIdx.x == 0) {
         mbar_init(&sh.bar, 1);
         asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
     }
     __syncthreads();
-    if (resident) {
-        if (threadIdx.x == 0) {
-            const unsigned int total = (unsigned int)a.Tpad * 16u;
-            mbar_expect_tx(&sh.bar, total);
-            for (unsigned int off = 0; off < total; off += 32768u) {
-                const unsigned int n = min(32768u, total - off);
-                tma_bulk_g2s(reinterpret_cast<unsigned char*>(s_tmpl) + off, reinterpret_cast<const unsigned char*>(a.tmpl) + off, n, &sh.bar);
-            }
-        }
+    if (threadIdx.x == 0) {
+        const unsigned int tb = RESIDENT ? (unsigned int)a.Tpad * 16u : 0u;
+        const unsigned int bb = (unsigned int)(2 * a.nchunk + 2 * a.nsuper) * 16u;
+        mbar_expect_tx(&sh.bar, tb + bb);
+        for (unsigned int off = 0; off < tb; off += 32768u)
+            tma_bulk_g2s(reinterpret_cast<unsigned char*>(s_tmpl) + off, reinterpret_cast<const unsigned char*>(a.tmpl) + off, min(32768u, tb - off), &sh.bar);
+        for (unsigned int off = 0; off < bb; off += 32768u)
+            tma_bulk_g2s(reinterpret_cast<unsigned char*>(s_box) + off, reinterpret_cast<const unsigned char*>(a.boxes) + off, min(32768u, bb - off), &sh.bar);
     }
 
     // ---- guess: final = guess; src_t = (guess == I) ? src : guess * src ----
@@ -357,10 +386,11 @@ __global__ void __launch_bounds__(ICP_THREADS, 1) k_icp(const IcpArgs a) {
     if (a.guesses && a.guess_mode == 1) {
         // rotation about the cluster centroid: G = T(c) R T(-c), centroid by the canonical reduction
         float v3[3] = {0.f, 0.f, 0.f};
-        for (int i = threadIdx.x; i < S; i += ICP_THREADS) {
-            const float4 p = src[idx[i]];
-            v3[0] = v3[0] + p.x; v3[1] = v3[1] + p.y; v3[2] = v3[2] + p.z;
-        }
+        if (lane_thread)
+            for (int i = threadIdx.x; i < S; i += ICP_LANES) {
+                const float4 p = src[idx[i]];
+                v3[0] = v3[0] + p.x; v3[1] = v3[1] + p.y; v3[2] = v3[2] + p.z;
+            }
         canon_block_reduce<float, 3>(v3, sh.part_f, sh.red_f);
         if (threadIdx.x == 0) {
             const float cn = (float)S;
@@ -380,36 +410,43 @@ __global__ void __launch_bounds__(ICP_THREADS, 1) k_icp(const IcpArgs a) {
     for (int i = threadIdx.x; i < S; i += ICP_THREADS) {
         const float4 p = src[idx[i]];
         cur[i] = guess_identity ? make_float4(p.x, p.y, p.z, 1.0f) : xform(sh.guess, p);
+        corr[i] = 0;   // seed of the first nearest-neighbour pass: any valid template position
     }
     if (threadIdx.x < 16) sh.fin[threadIdx.x] = sh.guess[threadIdx.x];
-    if (threadIdx.x == 0) { sh.done = 0; sh.converged = 0; sh.state = CUBOID_ICP_NOT_CONVERGED; sh.iters = 0; sh.prev_mse = 1.7976931348623157e308; }
-    if (resident) mbar_wait(&sh.bar, 0);
+    if (threadIdx.x == 0) {
+        sh.done = 0; sh.converged = 0; sh.state = CUBOID_ICP_NOT_CONVERGED; sh.iters = 0; sh.prev_mse = 1.7976931348623157e308;
+        sh.task = 0;
+    }
+    mbar_wait(&sh.bar, 0);
     __syncthreads();
 
-    unsigned long long chash = 0;
+    unsigned long long chash = 0, evaluated = 0;
     const float one_over_n = 1.0f / (float)S;
-    int it = 0;
+    int it = 0, passes = 0;
     if (S < 3) {   // "Not enough correspondences found" -> converged_ = false, no iteration
         if (threadIdx.x == 0) { sh.done = 1; sh.state = CUBOID_ICP_NO_CORRESPONDENCES; }
         __syncthreads();
     }
     while (!sh.done) {
         // 1. correspondences
-        icp_nn_pass(a, s_tmpl, resident, cur, S, corr, cd, s_tmpl);
+        icp_nn_pass<RESIDENT>(a, sh, s_tmpl, s_box, cur, S, corr, cd, evaluated);
+        ++passes;
         __syncthreads();
-        // 2. means + MSE (first 256 threads are the 256 canonical lanes)
+        if (threadIdx.x == 0) sh.task = 0;
+        // 2. means + MSE: the first 256 threads are the 256 canonical lanes
         float q6[6] = {0.f, 0.f, 0.f, 0.f, 0.f, 0.f};
         double qd[1] = {0.0};
-        for (int i = threadIdx.x; i < S; i += ICP_THREADS) {
-            const float4 p = cur[i];
-            const int j = corr[i];
-            const float4 t = resident ? s_tmpl[j] : a.tmpl[j];
-            q6[0] = q6[0] + p.x; q6[1] = q6[1] + p.y; q6[2] = q6[2] + p.z;
-            q6[3] = q6[3] + t.x; q6[4] = q6[4] + t.y; q6[5] = q6[5] + t.z;
-            qd[0] = qd[0] + (double)cd[i];
-            chash += splitmix64((((unsigned long long)it * (unsigned long long)S + (unsigned long long)i) << 32) | (unsigned int)j);
-            if (trace && it < a.cap_trace) a.corr_trace[(size_t)it * S + i] = j;
-        }
+        if (lane_thread)
+            for (int i = threadIdx.x; i < S; i += ICP_LANES) {
+                const float4 p = cur[i];
+                const float4 t = tp[corr[i]];
+                q6[0] = q6[0] + p.x; q6[1] = q6[1] + p.y; q6[2] = q6[2] + p.z;
+                q6[3] = q6[3] + t.x; q6[4] = q6[4] + t.y; q6[5] = q6[5] + t.z;
+                qd[0] = qd[0] + (double)cd[i];
+                const int j = __float_as_int(t.w);   // original template index
+                chash += splitmix64((((unsigned long long)it * (unsigned long long)S + (unsigned long long)i) << 32) | (unsigned int)j);
+                if (trace && it < a.cap_trace) a.corr_trace[(size_t)it * S + i] = j;
+            }
         canon_block_reduce<float, 6>(q6, sh.part_f, sh.red_f);
         canon_block_reduce<double, 1>(qd, sh.part_d, sh.red_d);
         float sm[3], dm[3];
@@ -421,16 +458,17 @@ __global__ void __launch_bounds__(ICP_THREADS, 1) k_icp(const IcpArgs a) {
         float q9[9];
 #pragma unroll
         for (int k = 0; k < 9; ++k) q9[k] = 0.f;
-        for (int i = threadIdx.x; i < S; i += ICP_THREADS) {
-            const float4 p = cur[i];
-            const float4 t = resident ? s_tmpl[corr[i]] : a.tmpl[corr[i]];
-            const float sd[3] = {p.x - sm[0], p.y - sm[1], p.z - sm[2]};
-            const float dd[3] = {t.x - dm[0], t.y - dm[1], t.z - dm[2]};
+        if (lane_thread)
+            for (int i = threadIdx.x; i < S; i += ICP_LANES) {
+                const float4 p = cur[i];
+                const float4 t = tp[corr[i]];
+                const float sd[3] = {p.x - sm[0], p.y - sm[1], p.z - sm[2]};
+                const float dd[3] = {t.x - dm[0], t.y - dm[1], t.z - dm[2]};
 #pragma unroll
-            for (int r = 0; r < 3; ++r)
+                for (int r = 0; r < 3; ++r)
 #pragma unroll
-                for (int cc = 0; cc < 3; ++cc) q9[3 * r + cc] = q9[3 * r + cc] + dd[r] * sd[cc];
-        }
+                    for (int cc = 0; cc < 3; ++cc) q9[3 * r + cc] = q9[3 * r + cc] + dd[r] * sd[cc];
+            }
         canon_block_reduce<float, 9>(q9, sh.part_f, sh.red_f);
         // 4. thread 0: SVD, R, t, final, convergence
         if (threadIdx.x == 0) {
@@ -486,33 +524,52 @@ __global__ void __launch_bounds__(ICP_THREADS, 1) k_icp(const IcpArgs a) {
         __syncthreads();
     }
 
-    // ---- output = transformCloud(src, final); getFitnessScore(): one more NN pass ----
+    // ---- output = transformCloud(src, final); getFitnessScore(): one more nearest-neighbour pass ----
     for (int i = threadIdx.x; i < S; i += ICP_THREADS) cur[i] = xform(sh.fin, src[idx[i]]);
     __syncthreads();
     double fitness = 1.7976931348623157e308;
     if (S > 0) {
-        icp_nn_pass(a, s_tmpl, resident, cur, S, corr, cd, s_tmpl);
+        icp_nn_pass<RESIDENT>(a, sh, s_tmpl, s_box, cur, S, corr, cd, evaluated);
+        ++passes;
         __syncthreads();
         double qd[1] = {0.0};
-        for (int i = threadIdx.x; i < S; i += ICP_THREADS) qd[0] = qd[0] + (double)cd[i];
+        if (lane_thread)
+            for (int i = threadIdx.x; i < S; i += ICP_LANES) qd[0] = qd[0] + (double)cd[i];
         canon_block_reduce<double, 1>(qd, sh.part_d, sh.red_d);
         fitness = sh.red_d[0] / (double)S;
     }
-    // reduce the correspondence hash
+    // reduce the correspondence hash and the work counters
     chash = warp_sum_u64(chash);
-    __shared__ unsigned long long s_hh[8];
-    if ((threadIdx.x & 31) == 0) s_hh[threadIdx.x >> 5] = chash;
+    evaluated = warp_sum_u64(evaluated);   // every lane of a warp counted the same chunk evaluations
+    __shared__ unsigned long long s_hh[16], s_ev[16];
+    if ((threadIdx.x & 31) == 0) { s_hh[threadIdx.x >> 5] = chash; s_ev[threadIdx.x >> 5] = evaluated / 32; }
     __syncthreads();
     if (threadIdx.x == 0) {
-        unsigned long long t = 0;
-        for (int k = 0; k < 8; ++k) t += s_hh[k];
+        unsigned long long t = 0, ev = 0;
+        for (int k = 0; k < ICP_THREADS / 32; ++k) { t += s_hh[k]; ev += s_ev[k]; }
         for (int k = 0; k < 16; ++k) out.T[k] = sh.fin[k];
         out.fitness = fitness;
         out.converged = sh.converged;
         out.iters = sh.iters;
         out.state = sh.state;
         out.corr_hash = t;
+        if (a.work) {
+            atomicAdd(&a.work[0], ev * (unsigned long long)(32 * ICP_R * ICP_CHUNK));
+            atomicAdd(&a.work[1], (unsigned long long)passes * (unsigned long long)S * (unsigned long long)a.T);
+        }
     }
+}
+
+__global__ void __launch_bounds__(ICP_THREADS, 1) k_icp(const IcpArgs a) {
+    extern __shared__ __align__(128) unsigned char smem_raw[];
+    __shared__ IcpShared sh;
+    const cuboid_frame_result& R = a.res[blockIdx.z];
+    if ((int)blockIdx.y >= min(R.n_clusters, CUBOID_MAX_CLUSTERS)) return;
+    // dynamic shared memory: [boxes (2*nchunk + 2*nsuper float4)] [template (Tpad float4, resident case only)]
+    float4* s_box = reinterpret_cast<float4*>(smem_raw);
+    float4* s_tmpl = s_box + (2 * a.nchunk + 2 * a.nsuper);
+    if (a.resident) icp_body<true>(a, sh, s_tmpl, s_box);
+    else icp_body<false>(a, sh, s_tmpl, s_box);
 }
 
 // best guess per (frame, cluster): lowest fitness, ties -> lowest guess id; fills cuboid_cluster_result

@@ -185,6 +185,56 @@ def test_icp_guesses_and_streamed_template(cc, stage_data, tmpl30):
     assert g["corr_hash"] == o["corr_hash"] and np.array_equal(bits(g["T"]), bits(o["T"])) and g["fitness"] == o["fitness"]
 
 
+def test_icp_exact_ties_resolve_to_lowest_template_index(cc):
+    """Dyadic lattice template + sources at exact cell/face/edge centres: 8-, 4- and 2-way exact float ties that
+    straddle the kd-ordered chunks. The culled kernel must return the lowest ORIGINAL template index, like a
+    brute-force scan in template order with strict '<' (and like the oracle's exact KD-tree)."""
+    g = np.arange(16, dtype=np.float32) / np.float32(256.0)
+    X, Y, Z = np.meshgrid(g, g, g, indexing="ij")
+    tm = np.ones((4096, 4), np.float32)
+    tm[:, 0], tm[:, 1], tm[:, 2] = X.ravel(), Y.ravel(), Z.ravel()
+    rng = np.random.default_rng(8)
+    tm = tm[rng.permutation(4096)]                       # original order unrelated to space
+    cells = rng.integers(0, 15, (900, 3)).astype(np.float32) / np.float32(256.0)
+    h = np.float32(1.0 / 512.0)
+    src = np.ones((900, 4), np.float32)
+    src[:, :3] = cells
+    src[:300, :3] += h                                   # cell centres: 8-way ties
+    src[300:600, 0] += h; src[300:600, 1] += h           # face centres: 4-way ties
+    src[600:, 2] += h                                    # edge midpoints: 2-way ties
+    d = src[:, None, :3] - tm[None, :, :3]
+    d2 = (d[..., 0] * d[..., 0] + d[..., 1] * d[..., 1]).astype(np.float32) + d[..., 2] * d[..., 2]
+    assert ((d2 == d2.min(axis=1, keepdims=True)).sum(axis=1)[:300] == 8).all()
+    cc.set_template(3, tm)
+    p = default_params("cuboid")
+    p.icp_max_iter = 2
+    cc.set_params(p)
+    try:
+        o = O.icp(src, tm, max_iter=2, trace_iters=2)
+        for cull in (1, 0):
+            cc.set_option(api.OPT_ICP_CULL, cull)
+            gq = cc.icp(src, 3, trace_iters=2)
+            assert np.array_equal(gq["corr_trace"][0], d2.argmin(axis=1))      # numpy argmin = first = lowest index
+            assert np.array_equal(gq["corr_trace"], o["corr_trace"]) and gq["corr_hash"] == o["corr_hash"]
+            assert np.array_equal(bits(gq["T"]), bits(o["T"])) and gq["fitness"] == o["fitness"]
+    finally:
+        cc.set_option(api.OPT_ICP_CULL, 1)
+        cc.set_params(default_params("cuboid"))
+
+
+def test_icp_culling_is_exact_and_saves_work(cc, tmpl30, params):
+    depth = synth.depth_batch("bench", [41, 42, 43])
+    cc.set_option(api.OPT_ICP_CULL, 0)
+    brute = cc.process_batch(depth)
+    w0 = cc.icp_work()
+    cc.set_option(api.OPT_ICP_CULL, 1)
+    culled = cc.process_batch(depth)
+    w1 = cc.icp_work()
+    for a, b in zip(brute, culled):
+        assert bytes(a) == bytes(b)
+    assert w0[1] == w1[1] and w0[0] >= w0[1] and w1[0] < 0.5 * w0[0]
+
+
 def test_icp_edge_cases(cc, tmpl30):
     o = O.icp(tmpl30[:2], tmpl30)
     g = cc.icp(tmpl30[:2], 0)

@@ -27,7 +27,7 @@ struct CluArgs {
     int min_size, max_size, use_cluster;
 };
 
-constexpr int CLU_THREADS = 256;
+constexpr int CLU_THREADS = 1024;
 
 __device__ __forceinline__ int uf_find(int* parent, int x) {
     volatile int* p = parent;
@@ -52,9 +52,9 @@ __device__ __forceinline__ void uf_unite(int* parent, int a, int b) {
 
 __global__ void __launch_bounds__(CLU_THREADS) k_cluster(const CluArgs a) {
     __shared__ float4 s_tile[CLU_THREADS];
-    __shared__ int s_w[9];
+    __shared__ int s_w[CLU_THREADS / 32 + 1];
     __shared__ int s_cur[1024];
-    __shared__ unsigned long long s_h[8];
+    __shared__ unsigned long long s_h[CLU_THREADS / 32];
     const int f = blockIdx.x;
     cuboid_frame_result& R = a.res[f];
     const int n = R.n_remain;
@@ -75,7 +75,7 @@ __global__ void __launch_bounds__(CLU_THREADS) k_cluster(const CluArgs a) {
         __syncthreads();
         if (threadIdx.x == 0) {
             unsigned long long t = 0;
-            for (int k = 0; k < 8; ++k) t += s_h[k];
+            for (int k = 0; k < CLU_THREADS / 32; ++k) t += s_h[k];
             const int ncl = n > 0 ? 1 : 0;
             offsets[0] = 0; offsets[1] = n;
             R.n_clusters = ncl;
@@ -126,7 +126,7 @@ __global__ void __launch_bounds__(CLU_THREADS) k_cluster(const CluArgs a) {
         bool keep = false;
         if (i < n && parent[i] == i) { const int s = csize[i]; keep = s >= a.min_size && s <= a.max_size; }
         int total;
-        const int pos = K + block_excl_scan256(keep ? 1 : 0, s_w, &total);
+        const int pos = K + block_excl_scan<CLU_THREADS>(keep ? 1 : 0, s_w, &total);
         if (keep && pos < a.KC) roots[pos] = i;
         K += total;
         __syncthreads();

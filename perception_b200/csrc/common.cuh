@@ -93,6 +93,24 @@ __device__ __forceinline__ int block_excl_scan256(int v, int* s_w, int* total) {
     *total = s_w[8];
     return s_w[w] + inc - v;
 }
+// same for NT threads (NT/32 warps, up to 32); s_w must hold NT/32 + 1 ints
+template <int NT>
+__device__ __forceinline__ int block_excl_scan(int v, int* s_w, int* total) {
+    constexpr int NW = NT / 32;
+    const int lane = threadIdx.x & 31, w = threadIdx.x >> 5;
+    const int inc = warp_incl_scan(v, lane);
+    if (lane == 31) s_w[w] = inc;
+    __syncthreads();
+    if (w == 0) {
+        const int t = lane < NW ? s_w[lane] : 0;
+        const int ti = warp_incl_scan(t, lane);
+        if (lane < NW) s_w[lane] = ti - t;
+        if (lane == 31) s_w[NW] = ti;
+    }
+    __syncthreads();
+    *total = s_w[NW];
+    return s_w[w] + inc - v;
+}
 __device__ __forceinline__ unsigned long long warp_sum_u64(unsigned long long v) {
 #pragma unroll
     for (int o = 16; o >= 1; o >>= 1) v += __shfl_xor_sync(FULL_MASK, v, o);

@@ -58,7 +58,7 @@ struct cuboid_handle {
     cuboid_frame_result* d_res = nullptr; int res_cap = 0;
     int* d_rng = nullptr; int rng_len = 0;
     int* d_triplets = nullptr; int triplets_cap = 0;
-    float4* d_tmpl[CUBOID_MAX_TEMPLATES] = {}; int tmpl_n[CUBOID_MAX_TEMPLATES] = {}; int tmpl_pad[CUBOID_MAX_TEMPLATES] = {};
+    float* d_tmpl[CUBOID_MAX_TEMPLATES] = {}; int* d_tmpl_orig[CUBOID_MAX_TEMPLATES] = {}; int tmpl_n[CUBOID_MAX_TEMPLATES] = {}; int tmpl_pad[CUBOID_MAX_TEMPLATES] = {};
     float4* d_boxes[CUBOID_MAX_TEMPLATES] = {}; int tmpl_nchunk[CUBOID_MAX_TEMPLATES] = {}; int tmpl_nsuper[CUBOID_MAX_TEMPLATES] = {};
     unsigned long long* d_work = nullptr; unsigned long long work_total[2] = {0, 0};
     int icp_cull = 1;
@@ -245,7 +245,7 @@ int run_chunk(cuboid_handle* h, const ChunkIn& in, int nf, cuboid_frame_result* 
         CKS(h, ensure_icp_scratch(h, std::max(nf, 1), ng));
         IcpArgs a{};
         a.remain = h->d_remain; a.idx_sorted = h->d_idx_sorted; a.offsets = h->d_offsets;
-        a.tmpl = h->d_tmpl[tmpl_slot]; a.T = h->tmpl_n[tmpl_slot]; a.Tpad = h->tmpl_pad[tmpl_slot];
+        a.tmpl = h->d_tmpl[tmpl_slot]; a.tmpl_orig = h->d_tmpl_orig[tmpl_slot]; a.T = h->tmpl_n[tmpl_slot]; a.Tpad = h->tmpl_pad[tmpl_slot];
         a.boxes = h->d_boxes[tmpl_slot]; a.nchunk = h->tmpl_nchunk[tmpl_slot]; a.nsuper = h->tmpl_nsuper[tmpl_slot];
         a.guesses = gs; a.n_guess = ng; a.guess_mode = gm;
         a.cur = h->d_cur; a.corr = h->d_corr; a.cd = h->d_cd; a.out = h->d_icp_out; a.res = d_res;
@@ -253,11 +253,11 @@ int run_chunk(cuboid_handle* h, const ChunkIn& in, int nf, cuboid_frame_result* 
         a.rot_thr = 1.0 - p.icp_tf_eps; a.trans_thr = p.icp_tf_eps; a.rel_mse = p.icp_rel_mse; a.abs_thr = 1e-12;
         const size_t box_bytes = (size_t)(2 * a.nchunk + 2 * a.nsuper) * 16;
         if (box_bytes > (size_t)h->icp_smem_budget) return CUBOID_E_CAPACITY;
-        a.resident = (box_bytes + (size_t)a.Tpad * 16 <= (size_t)h->icp_smem_budget) ? 1 : 0;
+        a.resident = (box_bytes + (size_t)a.Tpad * 12 <= (size_t)h->icp_smem_budget) ? 1 : 0;
         a.cull = h->icp_cull;
         a.work = h->d_work;
         a.corr_trace = trace_corr; a.T_trace = trace_T; a.cap_trace = cap_trace;
-        const size_t dyn = box_bytes + (a.resident ? (size_t)a.Tpad * 16 : 0);
+        const size_t dyn = box_bytes + (a.resident ? (size_t)a.Tpad * 12 : 0);
         k_icp<<<dim3(ng, CUBOID_MAX_CLUSTERS, nf), ICP_THREADS, dyn, st>>>(a);
         const int tot = nf * CUBOID_MAX_CLUSTERS;
         k_icp_select<<<(tot + 127) / 128, 128, 0, st>>>(h->d_icp_out, d_res, nf, ng, p.icp_fitness_gate, h->d_cur, h->M, h->d_offsets,
@@ -409,6 +409,7 @@ int cuboid_destroy(cuboid_handle* h) {
     for (void* q : ptrs) if (q) cudaFree(q);
     for (auto& t : h->d_tmpl) if (t) cudaFree(t);
     for (auto& t : h->d_boxes) if (t) cudaFree(t);
+    for (auto& t : h->d_tmpl_orig) if (t) cudaFree(t);
     for (auto& e : h->ev) if (e) cudaEventDestroy(e);
     if (h->stream) cudaStreamDestroy(h->stream);
     delete h;
@@ -466,23 +467,21 @@ int cuboid_set_template(cuboid_handle* h, int slot, const float* xyz, int stride
         items[i] = KdItem{v[0], v[1], v[2], i};
     }
     kd_order(items.data(), n);
-    std::vector<float4> host(pad), boxes(2 * (size_t)nchunk + 2 * (size_t)nsuper);
+    // SoA per chunk: x[64] y[64] z[64]; far sentinels (huge but finite distance: never win, never NaN) pad the tail
+    std::vector<float> host((size_t)pad * 3, 1.0e18f);
+    std::vector<int> orig(pad, 0x7fffffff);
+    std::vector<float4> boxes(2 * (size_t)nchunk + 2 * (size_t)nsuper);
     for (int i = 0; i < n; ++i) {
-        float w;
-        std::memcpy(&w, &items[i].orig, 4);   // .w carries the ORIGINAL template index (ties resolve to the lowest one)
-        host[i] = make_float4(items[i].x, items[i].y, items[i].z, w);
+        float* ch = host.data() + (size_t)(i / ICP_CHUNK) * ICP_CHUNK_FLOATS + (i % ICP_CHUNK);
+        ch[0] = items[i].x; ch[64] = items[i].y; ch[128] = items[i].z;
+        orig[i] = items[i].orig;   // ties resolve to the lowest ORIGINAL template index
     }
-    // far sentinels: their distance is huge but finite, so they never win and never produce NaN
-    const int big = 0x7fffffff;
-    float wbig;
-    std::memcpy(&wbig, &big, 4);
-    for (int i = n; i < pad; ++i) host[i] = make_float4(1.0e18f, 1.0e18f, 1.0e18f, wbig);
     const float inf = INFINITY;
     for (int c = 0; c < nchunk; ++c) {
         float4 lo = make_float4(inf, inf, inf, 0.f), hi = make_float4(-inf, -inf, -inf, 0.f);
         for (int j = c * ICP_CHUNK; j < std::min(n, (c + 1) * ICP_CHUNK); ++j) {
-            lo.x = std::min(lo.x, host[j].x); lo.y = std::min(lo.y, host[j].y); lo.z = std::min(lo.z, host[j].z);
-            hi.x = std::max(hi.x, host[j].x); hi.y = std::max(hi.y, host[j].y); hi.z = std::max(hi.z, host[j].z);
+            lo.x = std::min(lo.x, items[j].x); lo.y = std::min(lo.y, items[j].y); lo.z = std::min(lo.z, items[j].z);
+            hi.x = std::max(hi.x, items[j].x); hi.y = std::max(hi.y, items[j].y); hi.z = std::max(hi.z, items[j].z);
         }
         boxes[2 * c] = lo; boxes[2 * c + 1] = hi;
     }
@@ -495,10 +494,13 @@ int cuboid_set_template(cuboid_handle* h, int slot, const float* xyz, int stride
         boxes[2 * (size_t)nchunk + 2 * sc] = lo; boxes[2 * (size_t)nchunk + 2 * sc + 1] = hi;
     }
     if (h->d_tmpl[slot]) { cudaFree(h->d_tmpl[slot]); h->d_tmpl[slot] = nullptr; }
+    if (h->d_tmpl_orig[slot]) { cudaFree(h->d_tmpl_orig[slot]); h->d_tmpl_orig[slot] = nullptr; }
     if (h->d_boxes[slot]) { cudaFree(h->d_boxes[slot]); h->d_boxes[slot] = nullptr; }
-    CKS(h, dalloc(h, &h->d_tmpl[slot], (size_t)pad));
+    CKS(h, dalloc(h, &h->d_tmpl[slot], host.size()));
+    CKS(h, dalloc(h, &h->d_tmpl_orig[slot], orig.size()));
     CKS(h, dalloc(h, &h->d_boxes[slot], boxes.size()));
-    CK(h, cudaMemcpy(h->d_tmpl[slot], host.data(), sizeof(float4) * pad, cudaMemcpyHostToDevice));
+    CK(h, cudaMemcpy(h->d_tmpl[slot], host.data(), sizeof(float) * host.size(), cudaMemcpyHostToDevice));
+    CK(h, cudaMemcpy(h->d_tmpl_orig[slot], orig.data(), sizeof(int) * orig.size(), cudaMemcpyHostToDevice));
     CK(h, cudaMemcpy(h->d_boxes[slot], boxes.data(), sizeof(float4) * boxes.size(), cudaMemcpyHostToDevice));
     h->tmpl_n[slot] = n; h->tmpl_pad[slot] = pad; h->tmpl_nchunk[slot] = nchunk; h->tmpl_nsuper[slot] = nsuper;
     return CUBOID_OK;

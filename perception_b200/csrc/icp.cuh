@@ -36,7 +36,8 @@ struct IcpArgs {
     const float4* remain;    // [F][P]
     const int* idx_sorted;   // [F][M]
     const int* offsets;      // [F][KC+1]
-    const float4* tmpl;      // [Tpad] kd-ordered 64-point chunks, .w = original template index (bits); far sentinels pad the tail
+    const float* tmpl;       // [nchunk][3][64] kd-ordered 64-point chunks, SoA per chunk (x[64] y[64] z[64]); far sentinels pad the tail
+    const int* tmpl_orig;    // [Tpad] original template index of every kd-ordered position (sentinels: INT_MAX)
     const float4* boxes;     // [2*nchunk + 2*nsuper] AABB (lo, hi) of every chunk, then of every 8 consecutive chunks
     int T, Tpad, nchunk, nsuper;
     const float* guesses;    // n_guess * (16 | 9) or NULL
@@ -55,8 +56,8 @@ struct IcpArgs {
     int* corr_trace; float* T_trace; int cap_trace;   // debug taps for problem (0,0,0)
 };
 
-constexpr int ICP_THREADS = 512;
-constexpr int ICP_LANES = 256;     // threads that own the 256 canonical reduction lanes
+constexpr int ICP_THREADS = 256;   // = the 256 canonical reduction lanes; two CTAs (two ICP problems) share an SM
+constexpr int ICP_LANES = 256;
 constexpr int ICP_CHUNK = 64;      // template points per chunk
 constexpr int ICP_SUPER = 8;       // chunks per super box
 constexpr int ICP_R = 2;           // source points per lane in a nearest-neighbour task (64 points per warp task)
@@ -237,9 +238,14 @@ struct IcpShared {
     double prev_mse;
 };
 
-__device__ __forceinline__ float dist2(float sx, float sy, float sz, const float4 t) {
-    const float dx = sx - t.x, dy = sy - t.y, dz = sz - t.z;
+__device__ __forceinline__ float dist2(float sx, float sy, float sz, float tx, float ty, float tz) {
+    const float dx = sx - tx, dy = sy - ty, dz = sz - tz;
     return ((dx * dx) + dy * dy) + dz * dz;   // FLANN L2_Simple order, un-fused
+}
+constexpr int ICP_CHUNK_FLOATS = 3 * 64;   // one SoA chunk
+__device__ __forceinline__ float3 tmpl_point(const float* soa, int pos) {
+    const float* ch = soa + (size_t)(pos >> 6) * ICP_CHUNK_FLOATS + (pos & 63);
+    return make_float3(ch[0], ch[64], ch[128]);
 }
 // Lower bound of dist2(s, t) over every t inside the box [lo, hi], evaluated with the same rounding sequence:
 // float subtraction, squaring and addition are monotone, so lb <= dist2(s,t) holds bit-for-bit.
@@ -258,10 +264,10 @@ __device__ __forceinline__ float box_lb(float sx, float sy, float sz, const floa
 // holding a minimiser or a tie is ever skipped; ties between chunks are recorded and resolved to the LOWEST
 // ORIGINAL template index — the answer of a brute-force scan in original order with strict '<'.
 template <bool RESIDENT>
-__device__ __forceinline__ void icp_nn_pass(const IcpArgs& a, IcpShared& sh, const float4* s_tmpl, const float4* s_box, const float4* cur,
+__device__ __forceinline__ void icp_nn_pass(const IcpArgs& a, IcpShared& sh, const float* s_tmpl, const float4* s_box, const float4* cur,
                                             int S, int* corr, float* cd, unsigned long long& evaluated) {
     const int lane = threadIdx.x & 31;
-    const float4* tp = RESIDENT ? s_tmpl : a.tmpl;
+    const float* tp = RESIDENT ? s_tmpl : a.tmpl;
     const int ntask = (S + 32 * ICP_R - 1) / (32 * ICP_R);
     const float4* s_sbox = s_box + 2 * a.nchunk;
     const bool cull = a.cull != 0;
@@ -279,7 +285,8 @@ __device__ __forceinline__ void icp_nn_pass(const IcpArgs& a, IcpShared& sh, con
             const float4 p = cur[ii];
             sx[r] = p.x; sy[r] = p.y; sz[r] = p.z;
             const int seed = corr[ii];
-            best[r] = dist2(sx[r], sy[r], sz[r], tp[seed]);
+            const float3 t = tmpl_point(tp, seed);
+            best[r] = dist2(sx[r], sy[r], sz[r], t.x, t.y, t.z);
             bch[r] = seed / ICP_CHUNK; t1[r] = 0; t2[r] = 0; nt[r] = 0;
         }
         for (int sc = 0; sc < a.nsuper; ++sc) {
@@ -302,12 +309,19 @@ __device__ __forceinline__ void icp_nn_pass(const IcpArgs& a, IcpShared& sh, con
                 float m[ICP_R];
 #pragma unroll
                 for (int r = 0; r < ICP_R; ++r) m[r] = __int_as_float(0x7f800000);
-                const float4* ch = tp + (size_t)c * ICP_CHUNK;
-#pragma unroll 16
-                for (int jj = 0; jj < ICP_CHUNK; ++jj) {
-                    const float4 t = ch[jj];
+                const float* ch = tp + (size_t)c * ICP_CHUNK_FLOATS;
+#pragma unroll 4
+                for (int jj = 0; jj < ICP_CHUNK; jj += 4) {   // three broadcast LDS.128 feed 4 template points
+                    const float4 X = *reinterpret_cast<const float4*>(ch + jj);
+                    const float4 Y = *reinterpret_cast<const float4*>(ch + 64 + jj);
+                    const float4 Z = *reinterpret_cast<const float4*>(ch + 128 + jj);
 #pragma unroll
-                    for (int r = 0; r < ICP_R; ++r) m[r] = fminf(m[r], dist2(sx[r], sy[r], sz[r], t));
+                    for (int r = 0; r < ICP_R; ++r) {
+                        m[r] = fminf(m[r], dist2(sx[r], sy[r], sz[r], X.x, Y.x, Z.x));
+                        m[r] = fminf(m[r], dist2(sx[r], sy[r], sz[r], X.y, Y.y, Z.y));
+                        m[r] = fminf(m[r], dist2(sx[r], sy[r], sz[r], X.z, Y.z, Z.z));
+                        m[r] = fminf(m[r], dist2(sx[r], sy[r], sz[r], X.w, Y.w, Z.w));
+                    }
                 }
                 ++evaluated;
 #pragma unroll
@@ -320,7 +334,8 @@ __device__ __forceinline__ void icp_nn_pass(const IcpArgs& a, IcpShared& sh, con
                 }
             }
         }
-        // recover the winner: lowest ORIGINAL index among all template points at distance == best
+        // recover the winner: lowest ORIGINAL index among all template points at distance == best.
+        // Lanes walk their (different) chunks in a lane-rotated order, so the scalar LDS are bank-conflict free.
 #pragma unroll
         for (int r = 0; r < ICP_R; ++r) {
             const int i = task * 32 * ICP_R + r * 32 + lane;
@@ -329,12 +344,13 @@ __device__ __forceinline__ void icp_nn_pass(const IcpArgs& a, IcpShared& sh, con
             const int ncand = nt[r] > 2 ? a.nchunk : 1 + nt[r];
             for (int k = 0; k < ncand; ++k) {
                 const int c = nt[r] > 2 ? k : (k == 0 ? bch[r] : (k == 1 ? t1[r] : t2[r]));
-                const float4* ch = tp + (size_t)c * ICP_CHUNK;
-                for (int jj = 0; jj < ICP_CHUNK; ++jj) {
-                    const float4 t = ch[jj];
-                    if (dist2(sx[r], sy[r], sz[r], t) == best[r]) {
-                        const int o = __float_as_int(t.w);
-                        if (o < win_orig) { win_orig = o; win_pos = c * ICP_CHUNK + jj; }
+                const float* ch = tp + (size_t)c * ICP_CHUNK_FLOATS;
+                for (int q = 0; q < ICP_CHUNK; ++q) {
+                    const int jj = (q + lane) & 63;
+                    if (dist2(sx[r], sy[r], sz[r], ch[jj], ch[64 + jj], ch[128 + jj]) == best[r]) {
+                        const int pos = c * ICP_CHUNK + jj;
+                        const int o = a.tmpl_orig[pos];
+                        if (o < win_orig) { win_orig = o; win_pos = pos; }
                     }
                 }
             }
@@ -345,7 +361,7 @@ __device__ __forceinline__ void icp_nn_pass(const IcpArgs& a, IcpShared& sh, con
 }
 
 template <bool RESIDENT>
-__device__ __forceinline__ void icp_body(const IcpArgs& a, IcpShared& sh, float4* s_tmpl, float4* s_box) {
+__device__ __forceinline__ void icp_body(const IcpArgs& a, IcpShared& sh, float* s_tmpl, float4* s_box) {
     const int g = blockIdx.x, c = blockIdx.y, f = blockIdx.z;
     const int* offsets = a.offsets + (size_t)f * (a.KC + 1);
     const int o0 = offsets[c], S = offsets[c + 1] - o0;
@@ -357,7 +373,7 @@ __device__ __forceinline__ void icp_body(const IcpArgs& a, IcpShared& sh, float4
     float* cd = a.cd + pbase;
     IcpOut& out = a.out[((size_t)f * CUBOID_MAX_CLUSTERS + c) * a.n_guess + g];
     const bool trace = a.corr_trace && f == 0 && c == 0 && g == 0;
-    const float4* tp = RESIDENT ? s_tmpl : a.tmpl;
+    const float* tp = RESIDENT ? s_tmpl : a.tmpl;
     const bool lane_thread = threadIdx.x < ICP_LANES;
 
     // ---- stage the template (resident case) and the boxes with TMA bulk copies ----
@@ -367,7 +383,7 @@ __device__ __forceinline__ void icp_body(const IcpArgs& a, IcpShared& sh, float4
     }
     __syncthreads();
     if (threadIdx.x == 0) {
-        const unsigned int tb = RESIDENT ? (unsigned int)a.Tpad * 16u : 0u;
+        const unsigned int tb = RESIDENT ? (unsigned int)a.Tpad * 12u : 0u;
         const unsigned int bb = (unsigned int)(2 * a.nchunk + 2 * a.nsuper) * 16u;
         mbar_expect_tx(&sh.bar, tb + bb);
         for (unsigned int off = 0; off < tb; off += 32768u)
@@ -439,11 +455,12 @@ __device__ __forceinline__ void icp_body(const IcpArgs& a, IcpShared& sh, float4
         if (lane_thread)
             for (int i = threadIdx.x; i < S; i += ICP_LANES) {
                 const float4 p = cur[i];
-                const float4 t = tp[corr[i]];
+                const int pos = corr[i];
+                const float3 t = tmpl_point(tp, pos);
                 q6[0] = q6[0] + p.x; q6[1] = q6[1] + p.y; q6[2] = q6[2] + p.z;
                 q6[3] = q6[3] + t.x; q6[4] = q6[4] + t.y; q6[5] = q6[5] + t.z;
                 qd[0] = qd[0] + (double)cd[i];
-                const int j = __float_as_int(t.w);   // original template index
+                const int j = a.tmpl_orig[pos];      // original template index
                 chash += splitmix64((((unsigned long long)it * (unsigned long long)S + (unsigned long long)i) << 32) | (unsigned int)j);
                 if (trace && it < a.cap_trace) a.corr_trace[(size_t)it * S + i] = j;
             }
@@ -461,7 +478,7 @@ __device__ __forceinline__ void icp_body(const IcpArgs& a, IcpShared& sh, float4
         if (lane_thread)
             for (int i = threadIdx.x; i < S; i += ICP_LANES) {
                 const float4 p = cur[i];
-                const float4 t = tp[corr[i]];
+                const float3 t = tmpl_point(tp, corr[i]);
                 const float sd[3] = {p.x - sm[0], p.y - sm[1], p.z - sm[2]};
                 const float dd[3] = {t.x - dm[0], t.y - dm[1], t.z - dm[2]};
 #pragma unroll
@@ -541,7 +558,7 @@ __device__ __forceinline__ void icp_body(const IcpArgs& a, IcpShared& sh, float4
     // reduce the correspondence hash and the work counters
     chash = warp_sum_u64(chash);
     evaluated = warp_sum_u64(evaluated);   // every lane of a warp counted the same chunk evaluations
-    __shared__ unsigned long long s_hh[16], s_ev[16];
+    __shared__ unsigned long long s_hh[ICP_THREADS / 32], s_ev[ICP_THREADS / 32];
     if ((threadIdx.x & 31) == 0) { s_hh[threadIdx.x >> 5] = chash; s_ev[threadIdx.x >> 5] = evaluated / 32; }
     __syncthreads();
     if (threadIdx.x == 0) {
@@ -560,14 +577,14 @@ __device__ __forceinline__ void icp_body(const IcpArgs& a, IcpShared& sh, float4
     }
 }
 
-__global__ void __launch_bounds__(ICP_THREADS, 1) k_icp(const IcpArgs a) {
+__global__ void __launch_bounds__(ICP_THREADS, 2) k_icp(const IcpArgs a) {
     extern __shared__ __align__(128) unsigned char smem_raw[];
     __shared__ IcpShared sh;
     const cuboid_frame_result& R = a.res[blockIdx.z];
     if ((int)blockIdx.y >= min(R.n_clusters, CUBOID_MAX_CLUSTERS)) return;
-    // dynamic shared memory: [boxes (2*nchunk + 2*nsuper float4)] [template (Tpad float4, resident case only)]
+    // dynamic shared memory: [boxes (2*nchunk + 2*nsuper float4)] [template SoA chunks (Tpad*3 floats, resident case only)]
     float4* s_box = reinterpret_cast<float4*>(smem_raw);
-    float4* s_tmpl = s_box + (2 * a.nchunk + 2 * a.nsuper);
+    float* s_tmpl = reinterpret_cast<float*>(s_box + (2 * a.nchunk + 2 * a.nsuper));
     if (a.resident) icp_body<true>(a, sh, s_tmpl, s_box);
     else icp_body<false>(a, sh, s_tmpl, s_box);
 }

@@ -163,11 +163,21 @@ constexpr int VR_THREADS = 256;
 constexpr int VR_ITEMS = 4;
 constexpr int VR_TILE = VR_THREADS * VR_ITEMS;  // 1024
 
+// Segment heads -> voxel ordinal (decoupled look-back over the frame's tiles) and the sequential float centroid.
+// The tile's keys and (gathered) points are staged in shared memory with fully parallel loads first; the
+// serial per-voxel sums then run out of shared memory. A voxel that runs past the tile (e.g. the origin voxel
+// that collects every zero-depth pixel) is finished by warp 0 with lane-parallel loads and an in-order
+// shuffle accumulation, so the float sum order stays exactly "ascending point index".
 __global__ void __launch_bounds__(VR_THREADS) k_voxel_reduce(const VoxArgs a) {
     __shared__ int s_w[9];
     __shared__ int s_tile, s_base;
     __shared__ unsigned long long s_h[8];
-    if (threadIdx.x == 0) s_tile = (int)atomicAdd(a.ticket, 1u);
+    __shared__ unsigned int s_key[VR_TILE];
+    __shared__ float s_x[VR_TILE], s_y[VR_TILE], s_z[VR_TILE];
+    __shared__ float s_open[3];
+    __shared__ int s_open_cnt, s_open_pos, s_open_flag;
+    __shared__ unsigned int s_open_key;
+    if (threadIdx.x == 0) { s_tile = (int)atomicAdd(a.ticket, 1u); s_open_flag = 0; }
     __syncthreads();
     const int lin = s_tile;
     const int f = lin / a.tilesV, t = lin - f * a.tilesV;
@@ -178,15 +188,27 @@ __global__ void __launch_bounds__(VR_THREADS) k_voxel_reduce(const VoxArgs a) {
     const int npass = (a.scr[f].sort_bits + 7) / 8;
     const unsigned long long* keys = ((npass & 1) ? a.keysB : a.keysA) + (size_t)f * a.P;
     const float4* pts = a.pts + (size_t)f * a.P;
-    const int first = t * VR_TILE + threadIdx.x * VR_ITEMS;
-    unsigned int kk[VR_ITEMS + 1];
-    kk[0] = (first > 0 && first - 1 < N) ? (unsigned int)(keys[first - 1] >> 32) : 0u;
+    const int base = t * VR_TILE;
+    const int n_here = min(VR_TILE, N - base);
 #pragma unroll
-    for (int k = 0; k < VR_ITEMS; ++k) kk[k + 1] = (first + k < N) ? (unsigned int)(keys[first + k] >> 32) : 0u;
+    for (int k = 0; k < VR_ITEMS; ++k) {
+        const int l = k * VR_THREADS + threadIdx.x;
+        if (l < n_here) {
+            const unsigned long long r = keys[base + l];
+            const float4 p = pts[(unsigned int)r];
+            s_key[l] = (unsigned int)(r >> 32);
+            s_x[l] = p.x; s_y[l] = p.y; s_z[l] = p.z;
+        }
+    }
+    const unsigned int prev_key = base > 0 ? (unsigned int)(keys[base - 1] >> 32) : 0u;
+    __syncthreads();
+    const int first = threadIdx.x * VR_ITEMS;
     unsigned int heads = 0;
 #pragma unroll
-    for (int k = 0; k < VR_ITEMS; ++k)
-        if (first + k < N && (first + k == 0 || kk[k + 1] != kk[k])) heads |= 1u << k;
+    for (int k = 0; k < VR_ITEMS; ++k) {
+        const int lp = first + k;
+        if (lp < n_here && (base + lp == 0 || s_key[lp] != (lp > 0 ? s_key[lp - 1] : prev_key))) heads |= 1u << k;
+    }
     int total;
     int pos = block_excl_scan256(__popc(heads), s_w, &total);
     if (threadIdx.x == 0) s_base = lookback_exclusive(a.desc + (size_t)f * a.tilesV, t, total);
@@ -197,24 +219,58 @@ __global__ void __launch_bounds__(VR_THREADS) k_voxel_reduce(const VoxArgs a) {
 #pragma unroll
     for (int k = 0; k < VR_ITEMS; ++k) {
         if (!(heads & (1u << k))) continue;
-        const unsigned int mykey = kk[k + 1];
-        int q = first + k;
-        const float4 p0 = pts[(unsigned int)keys[q]];
-        float sx = p0.x, sy = p0.y, sz = p0.z;   // centroid starts as the first point, then += in sorted order
-        ++q;
-        while (q < N) {
-            const unsigned long long r = keys[q];
-            if ((unsigned int)(r >> 32) != mykey) break;
-            const float4 p = pts[(unsigned int)r];
-            sx += p.x; sy += p.y; sz += p.z;
-            ++q;
+        const int lp = first + k;
+        const unsigned int mykey = s_key[lp];
+        float sx = s_x[lp], sy = s_y[lp], sz = s_z[lp];   // centroid starts as the first point, then += in sorted order
+        int q = lp + 1;
+        while (q < n_here && s_key[q] == mykey) { sx += s_x[q]; sy += s_y[q]; sz += s_z[q]; ++q; }
+        if (q == n_here && base + n_here < N) {   // may continue in the next tile(s): at most one such voxel per tile
+            s_open[0] = sx; s_open[1] = sy; s_open[2] = sz;
+            s_open_cnt = q - lp; s_open_pos = pos; s_open_key = mykey; s_open_flag = 1;
+        } else {
+            const float cnt = (float)(q - lp);
+            const float cx = sx / cnt, cy = sy / cnt, cz = sz / cnt;
+            vox[pos] = make_float4(cx, cy, cz, 1.0f);
+            if (a.vcount) a.vcount[(size_t)f * a.P + pos] = q - lp;
+            h += hash_point((unsigned int)pos, cx, cy, cz);
         }
-        const float cnt = (float)(q - (first + k));
-        const float cx = sx / cnt, cy = sy / cnt, cz = sz / cnt;
-        vox[pos] = make_float4(cx, cy, cz, 1.0f);
-        if (a.vcount) a.vcount[(size_t)f * a.P + pos] = q - (first + k);
-        h += hash_point((unsigned int)pos, cx, cy, cz);
         ++pos;
+    }
+    __syncthreads();
+    if (s_open_flag && threadIdx.x < 32) {
+        const int lane = threadIdx.x;
+        const unsigned int mykey = s_open_key;
+        float sx = s_open[0], sy = s_open[1], sz = s_open[2];
+        int cnt = s_open_cnt;
+        int q = base + n_here;
+        while (q < N) {
+            const int i = q + lane;
+            unsigned int kk = ~mykey;
+            float px = 0.f, py = 0.f, pz = 0.f;
+            if (i < N) {
+                const unsigned long long r = keys[i];
+                kk = (unsigned int)(r >> 32);
+                if (kk == mykey) { const float4 p = pts[(unsigned int)r]; px = p.x; py = p.y; pz = p.z; }
+            }
+            const unsigned int miss = __ballot_sync(FULL_MASK, kk != mykey);
+            const int nmatch = miss ? (__ffs(miss) - 1) : 32;
+            for (int j = 0; j < nmatch; ++j) {
+                sx += __shfl_sync(FULL_MASK, px, j);
+                sy += __shfl_sync(FULL_MASK, py, j);
+                sz += __shfl_sync(FULL_MASK, pz, j);
+            }
+            cnt += nmatch;
+            if (nmatch < 32) break;
+            q += 32;
+        }
+        if (lane == 0) {
+            const float c = (float)cnt;
+            const float cx = sx / c, cy = sy / c, cz = sz / c;
+            const int vp = s_open_pos;
+            vox[vp] = make_float4(cx, cy, cz, 1.0f);
+            if (a.vcount) a.vcount[(size_t)f * a.P + vp] = cnt;
+            h += hash_point((unsigned int)vp, cx, cy, cz);
+        }
     }
     h = warp_sum_u64(h);
     if ((threadIdx.x & 31) == 0) s_h[threadIdx.x >> 5] = h;

@@ -59,7 +59,7 @@ struct cuboid_handle {
     int* d_rng = nullptr; int rng_len = 0;
     int* d_triplets = nullptr; int triplets_cap = 0;
     float* d_tmpl[CUBOID_MAX_TEMPLATES] = {}; int* d_tmpl_orig[CUBOID_MAX_TEMPLATES] = {}; int tmpl_n[CUBOID_MAX_TEMPLATES] = {}; int tmpl_pad[CUBOID_MAX_TEMPLATES] = {};
-    float4* d_boxes[CUBOID_MAX_TEMPLATES] = {}; int tmpl_nchunk[CUBOID_MAX_TEMPLATES] = {}; int tmpl_nsuper[CUBOID_MAX_TEMPLATES] = {};
+    float4* d_boxes[CUBOID_MAX_TEMPLATES] = {}; int tmpl_nleaf[CUBOID_MAX_TEMPLATES] = {}; int tmpl_nnodes[CUBOID_MAX_TEMPLATES] = {};
     unsigned long long* d_work = nullptr; unsigned long long work_total[2] = {0, 0};
     int icp_cull = 1;
     float* d_guesses = nullptr; int n_guess = 1; int guess_mode = 0; bool have_guesses = false;
@@ -246,12 +246,12 @@ int run_chunk(cuboid_handle* h, const ChunkIn& in, int nf, cuboid_frame_result* 
         IcpArgs a{};
         a.remain = h->d_remain; a.idx_sorted = h->d_idx_sorted; a.offsets = h->d_offsets;
         a.tmpl = h->d_tmpl[tmpl_slot]; a.tmpl_orig = h->d_tmpl_orig[tmpl_slot]; a.T = h->tmpl_n[tmpl_slot]; a.Tpad = h->tmpl_pad[tmpl_slot];
-        a.boxes = h->d_boxes[tmpl_slot]; a.nchunk = h->tmpl_nchunk[tmpl_slot]; a.nsuper = h->tmpl_nsuper[tmpl_slot];
+        a.nodes = h->d_boxes[tmpl_slot]; a.nleaf = h->tmpl_nleaf[tmpl_slot]; a.nnodes = h->tmpl_nnodes[tmpl_slot];
         a.guesses = gs; a.n_guess = ng; a.guess_mode = gm;
         a.cur = h->d_cur; a.corr = h->d_corr; a.cd = h->d_cd; a.out = h->d_icp_out; a.res = d_res;
         a.P = h->P; a.M = h->M; a.KC = h->KC; a.max_iter = p.icp_max_iter;
         a.rot_thr = 1.0 - p.icp_tf_eps; a.trans_thr = p.icp_tf_eps; a.rel_mse = p.icp_rel_mse; a.abs_thr = 1e-12;
-        const size_t box_bytes = (size_t)(2 * a.nchunk + 2 * a.nsuper) * 16;
+        const size_t box_bytes = (size_t)(2 * a.nnodes) * 16;
         if (box_bytes > (size_t)h->icp_smem_budget) return CUBOID_E_CAPACITY;
         a.resident = (box_bytes + (size_t)a.Tpad * 12 <= (size_t)h->icp_smem_budget) ? 1 : 0;
         a.cull = h->icp_cull;
@@ -429,36 +429,45 @@ int cuboid_set_params(cuboid_handle* h, const cuboid_params* p) {
 
 namespace {
 struct KdItem { float x, y, z; int orig; };
-// Re-orders items so that every run of 64 is spatially compact: split the chunk count in half along the widest
-// axis (median by nth_element, ties by original index so the order is deterministic), recurse.
-void kd_order(KdItem* a, int n) {
-    if (n <= ICP_CHUNK) return;
-    float mn[3] = {a[0].x, a[0].y, a[0].z}, mx[3] = {a[0].x, a[0].y, a[0].z};
-    for (int i = 1; i < n; ++i) {
+struct BvhNode { float lo[3]; int skip; float hi[3]; int leaf; };
+// Orders items so that every run of ICP_LEAF is spatially compact (split the leaf count in half along the widest
+// axis; median by nth_element, ties by original index so the order is deterministic) and emits the BVH nodes in
+// depth-first order with skip links (index of the first node after the subtree) for stackless traversal.
+void bvh_build(KdItem* a, int first, int n, std::vector<BvhNode>& nodes) {
+    const size_t me = nodes.size();
+    nodes.push_back(BvhNode());
+    float mn[3] = {a[first].x, a[first].y, a[first].z}, mx[3] = {a[first].x, a[first].y, a[first].z};
+    for (int i = first + 1; i < first + n; ++i) {
         mn[0] = std::min(mn[0], a[i].x); mx[0] = std::max(mx[0], a[i].x);
         mn[1] = std::min(mn[1], a[i].y); mx[1] = std::max(mx[1], a[i].y);
         mn[2] = std::min(mn[2], a[i].z); mx[2] = std::max(mx[2], a[i].z);
     }
-    int ax = 0;
-    for (int d = 1; d < 3; ++d) if (mx[d] - mn[d] > mx[ax] - mn[ax]) ax = d;
-    const int nch = (n + ICP_CHUNK - 1) / ICP_CHUNK;
-    const int k = ICP_CHUNK * ((nch + 1) / 2);
-    auto key = [ax](const KdItem& p) { return ax == 0 ? p.x : (ax == 1 ? p.y : p.z); };
-    std::nth_element(a, a + k, a + n, [&](const KdItem& p, const KdItem& q) {
-        const float kp = key(p), kq = key(q);
-        return kp < kq || (kp == kq && p.orig < q.orig);
-    });
-    kd_order(a, k);
-    kd_order(a + k, n - k);
+    for (int d = 0; d < 3; ++d) { nodes[me].lo[d] = mn[d]; nodes[me].hi[d] = mx[d]; }
+    if (n <= ICP_LEAF) {
+        nodes[me].leaf = first / ICP_LEAF;
+    } else {
+        nodes[me].leaf = -1;
+        int ax = 0;
+        for (int d = 1; d < 3; ++d) if (mx[d] - mn[d] > mx[ax] - mn[ax]) ax = d;
+        const int nl = (n + ICP_LEAF - 1) / ICP_LEAF;
+        const int k = ICP_LEAF * ((nl + 1) / 2);
+        auto key = [ax](const KdItem& p) { return ax == 0 ? p.x : (ax == 1 ? p.y : p.z); };
+        std::nth_element(a + first, a + first + k, a + first + n, [&](const KdItem& p, const KdItem& q) {
+            const float kp = key(p), kq = key(q);
+            return kp < kq || (kp == kq && p.orig < q.orig);
+        });
+        bvh_build(a, first, k, nodes);
+        bvh_build(a, first + k, n - k, nodes);
+    }
+    nodes[me].skip = (int)nodes.size();
 }
 }  // namespace
 
 int cuboid_set_template(cuboid_handle* h, int slot, const float* xyz, int stride_bytes, int n) {
     if (!h || slot < 0 || slot >= CUBOID_MAX_TEMPLATES || !xyz || n < 1 || stride_bytes < 12) return CUBOID_E_INVALID;
     cudaSetDevice(h->device);
-    const int nchunk = (n + ICP_CHUNK - 1) / ICP_CHUNK;
-    const int nsuper = (nchunk + ICP_SUPER - 1) / ICP_SUPER;
-    const int pad = nchunk * ICP_CHUNK;
+    const int nleaf = (n + ICP_LEAF - 1) / ICP_LEAF;
+    const int pad = nleaf * ICP_LEAF;
     std::vector<KdItem> items(n);
     const unsigned char* b = reinterpret_cast<const unsigned char*>(xyz);
     for (int i = 0; i < n; ++i) {
@@ -466,43 +475,28 @@ int cuboid_set_template(cuboid_handle* h, int slot, const float* xyz, int stride
         std::memcpy(v, b + (size_t)i * stride_bytes, 12);
         items[i] = KdItem{v[0], v[1], v[2], i};
     }
-    kd_order(items.data(), n);
-    // SoA per chunk: x[64] y[64] z[64]; far sentinels (huge but finite distance: never win, never NaN) pad the tail
+    std::vector<BvhNode> nodes;
+    nodes.reserve(2 * (size_t)nleaf);
+    bvh_build(items.data(), 0, n, nodes);
+    static_assert(sizeof(BvhNode) == 32, "BVH node = two float4");
+    // SoA per leaf: x[32] y[32] z[32]; far sentinels (huge but finite distance: never win, never NaN) pad the tail
     std::vector<float> host((size_t)pad * 3, 1.0e18f);
     std::vector<int> orig(pad, 0x7fffffff);
-    std::vector<float4> boxes(2 * (size_t)nchunk + 2 * (size_t)nsuper);
     for (int i = 0; i < n; ++i) {
-        float* ch = host.data() + (size_t)(i / ICP_CHUNK) * ICP_CHUNK_FLOATS + (i % ICP_CHUNK);
-        ch[0] = items[i].x; ch[64] = items[i].y; ch[128] = items[i].z;
+        float* lf = host.data() + (size_t)(i / ICP_LEAF) * ICP_LEAF_FLOATS + (i % ICP_LEAF);
+        lf[0] = items[i].x; lf[ICP_LEAF] = items[i].y; lf[2 * ICP_LEAF] = items[i].z;
         orig[i] = items[i].orig;   // ties resolve to the lowest ORIGINAL template index
-    }
-    const float inf = INFINITY;
-    for (int c = 0; c < nchunk; ++c) {
-        float4 lo = make_float4(inf, inf, inf, 0.f), hi = make_float4(-inf, -inf, -inf, 0.f);
-        for (int j = c * ICP_CHUNK; j < std::min(n, (c + 1) * ICP_CHUNK); ++j) {
-            lo.x = std::min(lo.x, items[j].x); lo.y = std::min(lo.y, items[j].y); lo.z = std::min(lo.z, items[j].z);
-            hi.x = std::max(hi.x, items[j].x); hi.y = std::max(hi.y, items[j].y); hi.z = std::max(hi.z, items[j].z);
-        }
-        boxes[2 * c] = lo; boxes[2 * c + 1] = hi;
-    }
-    for (int sc = 0; sc < nsuper; ++sc) {
-        float4 lo = make_float4(inf, inf, inf, 0.f), hi = make_float4(-inf, -inf, -inf, 0.f);
-        for (int c = sc * ICP_SUPER; c < std::min(nchunk, (sc + 1) * ICP_SUPER); ++c) {
-            lo.x = std::min(lo.x, boxes[2 * c].x); lo.y = std::min(lo.y, boxes[2 * c].y); lo.z = std::min(lo.z, boxes[2 * c].z);
-            hi.x = std::max(hi.x, boxes[2 * c + 1].x); hi.y = std::max(hi.y, boxes[2 * c + 1].y); hi.z = std::max(hi.z, boxes[2 * c + 1].z);
-        }
-        boxes[2 * (size_t)nchunk + 2 * sc] = lo; boxes[2 * (size_t)nchunk + 2 * sc + 1] = hi;
     }
     if (h->d_tmpl[slot]) { cudaFree(h->d_tmpl[slot]); h->d_tmpl[slot] = nullptr; }
     if (h->d_tmpl_orig[slot]) { cudaFree(h->d_tmpl_orig[slot]); h->d_tmpl_orig[slot] = nullptr; }
     if (h->d_boxes[slot]) { cudaFree(h->d_boxes[slot]); h->d_boxes[slot] = nullptr; }
     CKS(h, dalloc(h, &h->d_tmpl[slot], host.size()));
     CKS(h, dalloc(h, &h->d_tmpl_orig[slot], orig.size()));
-    CKS(h, dalloc(h, &h->d_boxes[slot], boxes.size()));
+    CKS(h, dalloc(h, &h->d_boxes[slot], 2 * nodes.size()));
     CK(h, cudaMemcpy(h->d_tmpl[slot], host.data(), sizeof(float) * host.size(), cudaMemcpyHostToDevice));
     CK(h, cudaMemcpy(h->d_tmpl_orig[slot], orig.data(), sizeof(int) * orig.size(), cudaMemcpyHostToDevice));
-    CK(h, cudaMemcpy(h->d_boxes[slot], boxes.data(), sizeof(float4) * boxes.size(), cudaMemcpyHostToDevice));
-    h->tmpl_n[slot] = n; h->tmpl_pad[slot] = pad; h->tmpl_nchunk[slot] = nchunk; h->tmpl_nsuper[slot] = nsuper;
+    CK(h, cudaMemcpy(h->d_boxes[slot], nodes.data(), sizeof(BvhNode) * nodes.size(), cudaMemcpyHostToDevice));
+    h->tmpl_n[slot] = n; h->tmpl_pad[slot] = pad; h->tmpl_nleaf[slot] = nleaf; h->tmpl_nnodes[slot] = (int)nodes.size();
     return CUBOID_OK;
 }
 

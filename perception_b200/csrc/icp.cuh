@@ -3,16 +3,17 @@
 // the whole ICP loop — nearest neighbours, Umeyama, 3x3 Jacobi SVD, incremental transform,
 // DefaultConvergenceCriteria — runs on the device, no host round trip.
 //
-//   nearest neighbour   brute-force tiles with exact culling. The template is re-ordered once on the host into
-//                       spatially compact 64-point chunks (kd split), each carrying its AABB; it is staged ONCE in
-//                       shared memory by TMA bulk copies. A warp task = 64 consecutive source points (2 per lane
-//                       in registers). Per chunk the warp first evaluates the AABB lower bound with the same
-//                       un-fused rounding sequence as the distance itself and skips the chunk only if the bound
-//                       is strictly above every point's running minimum; surviving chunks are scanned brute
-//                       force: one broadcast LDS.128 feeds 2*8 FP32 ops, d2 = ((dx*dx)+dy*dy)+dz*dz, running
-//                       minimum with FMNMX. The winner is recovered by re-scanning the minimal chunk(s) for the
-//                       LOWEST ORIGINAL template index at that distance, i.e. exactly what a brute-force scan in
-//                       template order with strict '<' returns (the canonical tie rule).
+//   nearest neighbour   exact search over a bounding-volume hierarchy of the template. The template is re-ordered
+//                       once on the host (kd split) into spatially compact 32-point leaves stored SoA, with the
+//                       tree nodes (AABB + skip link, depth-first order) beside them; both are staged ONCE in
+//                       shared memory by TMA bulk copies. Each lane owns one source point and walks the tree
+//                       stacklessly: a node is skipped only if the AABB lower bound — evaluated with the same
+//                       un-fused rounding sequence as the distance itself, hence a true bit-level bound — is
+//                       strictly above the lane's running minimum, which is seeded with the distance to the
+//                       previous iteration's correspondent. Leaves are scanned brute force,
+//                       d2 = ((dx*dx)+dy*dy)+dz*dz; ties resolve to the LOWEST ORIGINAL template index, i.e.
+//                       exactly what a brute-force scan in template order with strict '<' returns (the canonical
+//                       tie rule). With culling off the same code visits every leaf (plain brute force).
 //   Umeyama             canonical 256-lane strided partial sums + xor-butterfly + 8 warp partials left to right
 //                       (identical in oracle/cuboid_oracle.cpp: canon_reduce), Eigen JacobiSVD restated
 //   convergence         max iterations | transform epsilon | |dMSE| < 1e-12 | rel dMSE < icp_fitness_score
@@ -36,10 +37,10 @@ struct IcpArgs {
     const float4* remain;    // [F][P]
     const int* idx_sorted;   // [F][M]
     const int* offsets;      // [F][KC+1]
-    const float* tmpl;       // [nchunk][3][64] kd-ordered 64-point chunks, SoA per chunk (x[64] y[64] z[64]); far sentinels pad the tail
+    const float* tmpl;       // [nleaf][3][32] kd-ordered 32-point leaves, SoA per leaf (x[32] y[32] z[32]); far sentinels pad the tail
     const int* tmpl_orig;    // [Tpad] original template index of every kd-ordered position (sentinels: INT_MAX)
-    const float4* boxes;     // [2*nchunk + 2*nsuper] AABB (lo, hi) of every chunk, then of every 8 consecutive chunks
-    int T, Tpad, nchunk, nsuper;
+    const float4* nodes;     // [2*nnodes] depth-first BVH: (lo.xyz, skip link) (hi.xyz, leaf id or -1)
+    int T, Tpad, nleaf, nnodes;
     const float* guesses;    // n_guess * (16 | 9) or NULL
     int n_guess, guess_mode;
     float4* cur;             // [F][G][M]
@@ -51,16 +52,14 @@ struct IcpArgs {
     int max_iter;
     double rot_thr, trans_thr, rel_mse, abs_thr;
     int resident;            // 1: the whole template sits in shared memory; 0: chunks are read through L1/L2
-    int cull;                // 1: skip chunks whose AABB lower bound exceeds the running minimum (exact)
-    unsigned long long* work;   // [2] += (chunk evaluations * 64 points * 64 pairs, brute-force pairs) or NULL
+    int cull;                // 1: skip subtrees whose AABB lower bound exceeds the running minimum (exact)
+    unsigned long long* work;   // [2] += (source-template pairs evaluated, brute-force pairs S*T per pass) or NULL
     int* corr_trace; float* T_trace; int cap_trace;   // debug taps for problem (0,0,0)
 };
 
 constexpr int ICP_THREADS = 256;   // = the 256 canonical reduction lanes; two CTAs (two ICP problems) share an SM
 constexpr int ICP_LANES = 256;
-constexpr int ICP_CHUNK = 64;      // template points per chunk
-constexpr int ICP_SUPER = 8;       // chunks per super box
-constexpr int ICP_R = 2;           // source points per lane in a nearest-neighbour task (64 points per warp task)
+constexpr int ICP_LEAF = 32;       // template points per BVH leaf
 
 
 struct M3f { float a[3][3]; };
@@ -242,10 +241,10 @@ __device__ __forceinline__ float dist2(float sx, float sy, float sz, float tx, f
     const float dx = sx - tx, dy = sy - ty, dz = sz - tz;
     return ((dx * dx) + dy * dy) + dz * dz;   // FLANN L2_Simple order, un-fused
 }
-constexpr int ICP_CHUNK_FLOATS = 3 * 64;   // one SoA chunk
+constexpr int ICP_LEAF_FLOATS = 3 * ICP_LEAF;   // one SoA leaf
 __device__ __forceinline__ float3 tmpl_point(const float* soa, int pos) {
-    const float* ch = soa + (size_t)(pos >> 6) * ICP_CHUNK_FLOATS + (pos & 63);
-    return make_float3(ch[0], ch[64], ch[128]);
+    const float* lf = soa + (size_t)(pos / ICP_LEAF) * ICP_LEAF_FLOATS + (pos % ICP_LEAF);
+    return make_float3(lf[0], lf[ICP_LEAF], lf[2 * ICP_LEAF]);
 }
 // Lower bound of dist2(s, t) over every t inside the box [lo, hi], evaluated with the same rounding sequence:
 // float subtraction, squaring and addition are monotone, so lb <= dist2(s,t) holds bit-for-bit.
@@ -258,110 +257,79 @@ __device__ __forceinline__ float box_lb(float sx, float sy, float sz, const floa
 
 // One nearest-neighbour pass over cur[0..S): writes corr[] (kd-ordered template position) and cd[].
 // On entry corr[] holds a valid template position per point (the previous pass's answer, or 0): its distance
-// seeds the running minimum so the culling is tight from the first chunk.
+// seeds the running minimum so the culling is tight from the first node.
 //
-// Exactness: a chunk is skipped only when lb > best (strict) for all 64 points of the warp task, so no chunk
-// holding a minimiser or a tie is ever skipped; ties between chunks are recorded and resolved to the LOWEST
-// ORIGINAL template index — the answer of a brute-force scan in original order with strict '<'.
+// Exactness: a subtree is skipped only when lb > best (strict), so no subtree holding a minimiser or a tie is
+// ever skipped; among equal distances the LOWEST ORIGINAL template index wins — the answer of a brute-force
+// scan in original order with strict '<'.
 template <bool RESIDENT>
-__device__ __forceinline__ void icp_nn_pass(const IcpArgs& a, IcpShared& sh, const float* s_tmpl, const float4* s_box, const float4* cur,
+__device__ __forceinline__ void icp_nn_pass(const IcpArgs& a, IcpShared& sh, const float* s_tmpl, const float4* s_nodes, const float4* cur,
                                             int S, int* corr, float* cd, unsigned long long& evaluated) {
     const int lane = threadIdx.x & 31;
     const float* tp = RESIDENT ? s_tmpl : a.tmpl;
-    const int ntask = (S + 32 * ICP_R - 1) / (32 * ICP_R);
-    const float4* s_sbox = s_box + 2 * a.nchunk;
+    const int ntask = (S + 31) / 32;
     const bool cull = a.cull != 0;
+    const int nnodes = a.nnodes;
     while (true) {
         int task = 0;
         if (lane == 0) task = atomicAdd(&sh.task, 1);
         task = __shfl_sync(FULL_MASK, task, 0);
         if (task >= ntask) break;
-        float sx[ICP_R], sy[ICP_R], sz[ICP_R], best[ICP_R];
-        int bch[ICP_R], t1[ICP_R], t2[ICP_R], nt[ICP_R];
-#pragma unroll
-        for (int r = 0; r < ICP_R; ++r) {
-            const int i = task * 32 * ICP_R + r * 32 + lane;
-            const int ii = i < S ? i : S - 1;
-            const float4 p = cur[ii];
-            sx[r] = p.x; sy[r] = p.y; sz[r] = p.z;
-            const int seed = corr[ii];
-            const float3 t = tmpl_point(tp, seed);
-            best[r] = dist2(sx[r], sy[r], sz[r], t.x, t.y, t.z);
-            bch[r] = seed / ICP_CHUNK; t1[r] = 0; t2[r] = 0; nt[r] = 0;
+        const int i = task * 32 + lane;
+        const int ii = i < S ? i : S - 1;
+        const float4 p = cur[ii];
+        const float sx = p.x, sy = p.y, sz = p.z;
+        int wpos = corr[ii];
+        int worig = a.tmpl_orig[wpos];
+        float best;
+        {
+            const float3 t = tmpl_point(tp, wpos);
+            best = dist2(sx, sy, sz, t.x, t.y, t.z);
         }
-        for (int sc = 0; sc < a.nsuper; ++sc) {
-            if (cull) {
-                const float4 lo = s_sbox[2 * sc], hi = s_sbox[2 * sc + 1];
-                bool skip = true;
-#pragma unroll
-                for (int r = 0; r < ICP_R; ++r) skip = skip && (box_lb(sx[r], sy[r], sz[r], lo, hi) > best[r]);
-                if (__all_sync(FULL_MASK, skip)) continue;
+        int node = 0;
+        unsigned int nleaf_eval = 0;
+        while (true) {
+            int leaf = -1;
+            while (node < nnodes) {   // walk to the next leaf that survives the bound
+                const float4 lo = s_nodes[2 * node], hi = s_nodes[2 * node + 1];
+                if (cull && box_lb(sx, sy, sz, lo, hi) > best) { node = __float_as_int(lo.w); continue; }
+                leaf = __float_as_int(hi.w);
+                ++node;
+                if (leaf >= 0) break;
             }
-            const int c_end = min(a.nchunk, (sc + 1) * ICP_SUPER);
-            for (int c = sc * ICP_SUPER; c < c_end; ++c) {
-                if (cull) {
-                    const float4 lo = s_box[2 * c], hi = s_box[2 * c + 1];
-                    bool skip = true;
+            if (leaf < 0) break;
+            ++nleaf_eval;
+            const float* lf = tp + (size_t)leaf * ICP_LEAF_FLOATS;
+            const int pbase = leaf * ICP_LEAF;
+#pragma unroll 2
+            for (int jj = 0; jj < ICP_LEAF; jj += 4) {
+                const float4 X = *reinterpret_cast<const float4*>(lf + jj);
+                const float4 Y = *reinterpret_cast<const float4*>(lf + ICP_LEAF + jj);
+                const float4 Z = *reinterpret_cast<const float4*>(lf + 2 * ICP_LEAF + jj);
+                const float d0 = dist2(sx, sy, sz, X.x, Y.x, Z.x);
+                const float d1 = dist2(sx, sy, sz, X.y, Y.y, Z.y);
+                const float d2 = dist2(sx, sy, sz, X.z, Y.z, Z.z);
+                const float d3 = dist2(sx, sy, sz, X.w, Y.w, Z.w);
+                if (fminf(fminf(d0, d1), fminf(d2, d3)) <= best) {   // rare once the seed is good
+                    const float dd[4] = {d0, d1, d2, d3};
 #pragma unroll
-                    for (int r = 0; r < ICP_R; ++r) skip = skip && (box_lb(sx[r], sy[r], sz[r], lo, hi) > best[r]);
-                    if (__all_sync(FULL_MASK, skip)) continue;
-                }
-                float m[ICP_R];
-#pragma unroll
-                for (int r = 0; r < ICP_R; ++r) m[r] = __int_as_float(0x7f800000);
-                const float* ch = tp + (size_t)c * ICP_CHUNK_FLOATS;
-#pragma unroll 4
-                for (int jj = 0; jj < ICP_CHUNK; jj += 4) {   // three broadcast LDS.128 feed 4 template points
-                    const float4 X = *reinterpret_cast<const float4*>(ch + jj);
-                    const float4 Y = *reinterpret_cast<const float4*>(ch + 64 + jj);
-                    const float4 Z = *reinterpret_cast<const float4*>(ch + 128 + jj);
-#pragma unroll
-                    for (int r = 0; r < ICP_R; ++r) {
-                        m[r] = fminf(m[r], dist2(sx[r], sy[r], sz[r], X.x, Y.x, Z.x));
-                        m[r] = fminf(m[r], dist2(sx[r], sy[r], sz[r], X.y, Y.y, Z.y));
-                        m[r] = fminf(m[r], dist2(sx[r], sy[r], sz[r], X.z, Y.z, Z.z));
-                        m[r] = fminf(m[r], dist2(sx[r], sy[r], sz[r], X.w, Y.w, Z.w));
-                    }
-                }
-                ++evaluated;
-#pragma unroll
-                for (int r = 0; r < ICP_R; ++r) {
-                    if (m[r] < best[r]) { best[r] = m[r]; bch[r] = c; nt[r] = 0; }
-                    else if (m[r] == best[r] && c != bch[r]) {
-                        if (nt[r] == 0) t1[r] = c; else if (nt[r] == 1) t2[r] = c;
-                        ++nt[r];
+                    for (int k = 0; k < 4; ++k) {
+                        if (dd[k] <= best) {
+                            const int pos = pbase + jj + k;
+                            const int o = a.tmpl_orig[pos];
+                            if (dd[k] < best || o < worig) { best = dd[k]; worig = o; wpos = pos; }
+                        }
                     }
                 }
             }
         }
-        // recover the winner: lowest ORIGINAL index among all template points at distance == best.
-        // Lanes walk their (different) chunks in a lane-rotated order, so the scalar LDS are bank-conflict free.
-#pragma unroll
-        for (int r = 0; r < ICP_R; ++r) {
-            const int i = task * 32 * ICP_R + r * 32 + lane;
-            if (i >= S) continue;
-            int win_orig = 0x7fffffff, win_pos = 0;
-            const int ncand = nt[r] > 2 ? a.nchunk : 1 + nt[r];
-            for (int k = 0; k < ncand; ++k) {
-                const int c = nt[r] > 2 ? k : (k == 0 ? bch[r] : (k == 1 ? t1[r] : t2[r]));
-                const float* ch = tp + (size_t)c * ICP_CHUNK_FLOATS;
-                for (int q = 0; q < ICP_CHUNK; ++q) {
-                    const int jj = (q + lane) & 63;
-                    if (dist2(sx[r], sy[r], sz[r], ch[jj], ch[64 + jj], ch[128 + jj]) == best[r]) {
-                        const int pos = c * ICP_CHUNK + jj;
-                        const int o = a.tmpl_orig[pos];
-                        if (o < win_orig) { win_orig = o; win_pos = pos; }
-                    }
-                }
-            }
-            corr[i] = win_pos;
-            cd[i] = best[r];
-        }
+        evaluated += (unsigned long long)nleaf_eval * ICP_LEAF;
+        if (i < S) { corr[i] = wpos; cd[i] = best; }
     }
 }
 
 template <bool RESIDENT>
-__device__ __forceinline__ void icp_body(const IcpArgs& a, IcpShared& sh, float* s_tmpl, float4* s_box) {
+__device__ __forceinline__ void icp_body(const IcpArgs& a, IcpShared& sh, float* s_tmpl, float4* s_nodes) {
     const int g = blockIdx.x, c = blockIdx.y, f = blockIdx.z;
     const int* offsets = a.offsets + (size_t)f * (a.KC + 1);
     const int o0 = offsets[c], S = offsets[c + 1] - o0;
@@ -384,12 +352,12 @@ __device__ __forceinline__ void icp_body(const IcpArgs& a, IcpShared& sh, float*
     __syncthreads();
     if (threadIdx.x == 0) {
         const unsigned int tb = RESIDENT ? (unsigned int)a.Tpad * 12u : 0u;
-        const unsigned int bb = (unsigned int)(2 * a.nchunk + 2 * a.nsuper) * 16u;
+        const unsigned int bb = (unsigned int)(2 * a.nnodes) * 16u;
         mbar_expect_tx(&sh.bar, tb + bb);
         for (unsigned int off = 0; off < tb; off += 32768u)
             tma_bulk_g2s(reinterpret_cast<unsigned char*>(s_tmpl) + off, reinterpret_cast<const unsigned char*>(a.tmpl) + off, min(32768u, tb - off), &sh.bar);
         for (unsigned int off = 0; off < bb; off += 32768u)
-            tma_bulk_g2s(reinterpret_cast<unsigned char*>(s_box) + off, reinterpret_cast<const unsigned char*>(a.boxes) + off, min(32768u, bb - off), &sh.bar);
+            tma_bulk_g2s(reinterpret_cast<unsigned char*>(s_nodes) + off, reinterpret_cast<const unsigned char*>(a.nodes) + off, min(32768u, bb - off), &sh.bar);
     }
 
     // ---- guess: final = guess; src_t = (guess == I) ? src : guess * src ----
@@ -445,7 +413,7 @@ __device__ __forceinline__ void icp_body(const IcpArgs& a, IcpShared& sh, float*
     }
     while (!sh.done) {
         // 1. correspondences
-        icp_nn_pass<RESIDENT>(a, sh, s_tmpl, s_box, cur, S, corr, cd, evaluated);
+        icp_nn_pass<RESIDENT>(a, sh, s_tmpl, s_nodes, cur, S, corr, cd, evaluated);
         ++passes;
         __syncthreads();
         if (threadIdx.x == 0) sh.task = 0;
@@ -546,7 +514,7 @@ __device__ __forceinline__ void icp_body(const IcpArgs& a, IcpShared& sh, float*
     __syncthreads();
     double fitness = 1.7976931348623157e308;
     if (S > 0) {
-        icp_nn_pass<RESIDENT>(a, sh, s_tmpl, s_box, cur, S, corr, cd, evaluated);
+        icp_nn_pass<RESIDENT>(a, sh, s_tmpl, s_nodes, cur, S, corr, cd, evaluated);
         ++passes;
         __syncthreads();
         double qd[1] = {0.0};
@@ -557,9 +525,9 @@ __device__ __forceinline__ void icp_body(const IcpArgs& a, IcpShared& sh, float*
     }
     // reduce the correspondence hash and the work counters
     chash = warp_sum_u64(chash);
-    evaluated = warp_sum_u64(evaluated);   // every lane of a warp counted the same chunk evaluations
+    evaluated = warp_sum_u64(evaluated);   // pairs evaluated by the 32 lanes
     __shared__ unsigned long long s_hh[ICP_THREADS / 32], s_ev[ICP_THREADS / 32];
-    if ((threadIdx.x & 31) == 0) { s_hh[threadIdx.x >> 5] = chash; s_ev[threadIdx.x >> 5] = evaluated / 32; }
+    if ((threadIdx.x & 31) == 0) { s_hh[threadIdx.x >> 5] = chash; s_ev[threadIdx.x >> 5] = evaluated; }
     __syncthreads();
     if (threadIdx.x == 0) {
         unsigned long long t = 0, ev = 0;
@@ -571,7 +539,7 @@ __device__ __forceinline__ void icp_body(const IcpArgs& a, IcpShared& sh, float*
         out.state = sh.state;
         out.corr_hash = t;
         if (a.work) {
-            atomicAdd(&a.work[0], ev * (unsigned long long)(32 * ICP_R * ICP_CHUNK));
+            atomicAdd(&a.work[0], ev);
             atomicAdd(&a.work[1], (unsigned long long)passes * (unsigned long long)S * (unsigned long long)a.T);
         }
     }
@@ -582,11 +550,11 @@ __global__ void __launch_bounds__(ICP_THREADS, 2) k_icp(const IcpArgs a) {
     __shared__ IcpShared sh;
     const cuboid_frame_result& R = a.res[blockIdx.z];
     if ((int)blockIdx.y >= min(R.n_clusters, CUBOID_MAX_CLUSTERS)) return;
-    // dynamic shared memory: [boxes (2*nchunk + 2*nsuper float4)] [template SoA chunks (Tpad*3 floats, resident case only)]
-    float4* s_box = reinterpret_cast<float4*>(smem_raw);
-    float* s_tmpl = reinterpret_cast<float*>(s_box + (2 * a.nchunk + 2 * a.nsuper));
-    if (a.resident) icp_body<true>(a, sh, s_tmpl, s_box);
-    else icp_body<false>(a, sh, s_tmpl, s_box);
+    // dynamic shared memory: [BVH nodes (2*nnodes float4)] [template SoA leaves (Tpad*3 floats, resident case only)]
+    float4* s_nodes = reinterpret_cast<float4*>(smem_raw);
+    float* s_tmpl = reinterpret_cast<float*>(s_nodes + 2 * a.nnodes);
+    if (a.resident) icp_body<true>(a, sh, s_tmpl, s_nodes);
+    else icp_body<false>(a, sh, s_tmpl, s_nodes);
 }
 
 // best guess per (frame, cluster): lowest fitness, ties -> lowest guess id; fills cuboid_cluster_result

@@ -50,7 +50,7 @@ struct cuboid_handle {
     int *d_shuffled = nullptr, *d_inl_pre = nullptr, *d_inl = nullptr;
     float4* d_remain = nullptr;
     int *d_parent = nullptr, *d_csize = nullptr, *d_crank = nullptr, *d_idx_sorted = nullptr, *d_offsets = nullptr, *d_roots = nullptr;
-    float4* d_cur = nullptr; int* d_corr = nullptr; float* d_cd = nullptr; IcpOut* d_icp_out = nullptr;
+    float4* d_cur = nullptr; int* d_corr = nullptr; float* d_cd = nullptr; int* d_order = nullptr; IcpOut* d_icp_out = nullptr;
     size_t icp_scratch_elems = 0; size_t icp_out_elems = 0;
     FrameScratch* d_scr = nullptr;
     unsigned long long *d_desc1 = nullptr, *d_desc2 = nullptr;
@@ -124,11 +124,12 @@ int upload_rng(cuboid_handle* h) {
 int ensure_icp_scratch(cuboid_handle* h, int frames, int n_guess) {
     const size_t need = (size_t)frames * n_guess * h->M;
     if (need > h->icp_scratch_elems) {
-        if (h->d_cur) { cudaFree(h->d_cur); cudaFree(h->d_corr); cudaFree(h->d_cd); }
-        h->d_cur = nullptr; h->d_corr = nullptr; h->d_cd = nullptr; h->icp_scratch_elems = 0;
+        if (h->d_cur) { cudaFree(h->d_cur); cudaFree(h->d_corr); cudaFree(h->d_cd); cudaFree(h->d_order); }
+        h->d_cur = nullptr; h->d_corr = nullptr; h->d_cd = nullptr; h->d_order = nullptr; h->icp_scratch_elems = 0;
         CKS(h, dalloc(h, &h->d_cur, need));
         CKS(h, dalloc(h, &h->d_corr, need));
         CKS(h, dalloc(h, &h->d_cd, need));
+        CKS(h, dalloc(h, &h->d_order, need));
         h->icp_scratch_elems = need;
     }
     const size_t need_out = (size_t)frames * CUBOID_MAX_CLUSTERS * n_guess;
@@ -248,7 +249,7 @@ int run_chunk(cuboid_handle* h, const ChunkIn& in, int nf, cuboid_frame_result* 
         a.tmpl = h->d_tmpl[tmpl_slot]; a.tmpl_orig = h->d_tmpl_orig[tmpl_slot]; a.T = h->tmpl_n[tmpl_slot]; a.Tpad = h->tmpl_pad[tmpl_slot];
         a.nodes = h->d_boxes[tmpl_slot]; a.nleaf = h->tmpl_nleaf[tmpl_slot]; a.nnodes = h->tmpl_nnodes[tmpl_slot];
         a.guesses = gs; a.n_guess = ng; a.guess_mode = gm;
-        a.cur = h->d_cur; a.corr = h->d_corr; a.cd = h->d_cd; a.out = h->d_icp_out; a.res = d_res;
+        a.cur = h->d_cur; a.corr = h->d_corr; a.cd = h->d_cd; a.order = h->d_order; a.out = h->d_icp_out; a.res = d_res;
         a.P = h->P; a.M = h->M; a.KC = h->KC; a.max_iter = p.icp_max_iter;
         a.rot_thr = 1.0 - p.icp_tf_eps; a.trans_thr = p.icp_tf_eps; a.rel_mse = p.icp_rel_mse; a.abs_thr = 1e-12;
         const size_t box_bytes = (size_t)(2 * a.nnodes) * 16;
@@ -404,7 +405,7 @@ int cuboid_destroy(cuboid_handle* h) {
     if (h->stream) cudaStreamSynchronize(h->stream);
     void* ptrs[] = {h->d_depth, h->d_blob, h->d_n_in, h->d_pts, h->d_keysA, h->d_keysB, h->d_kpp, h->d_hist, h->d_vox, h->d_vcount, h->d_shuffled,
                     h->d_inl_pre, h->d_inl, h->d_remain, h->d_parent, h->d_csize, h->d_crank, h->d_idx_sorted, h->d_offsets, h->d_roots,
-                    h->d_cur, h->d_corr, h->d_cd, h->d_icp_out, h->d_scr, h->d_desc1, h->d_desc2, h->d_ticket, h->d_res, h->d_rng,
+                    h->d_cur, h->d_corr, h->d_cd, h->d_order, h->d_icp_out, h->d_scr, h->d_desc1, h->d_desc2, h->d_ticket, h->d_res, h->d_rng,
                     h->d_triplets, h->d_guesses, h->d_trace_corr, h->d_trace_T, h->d_aligned, h->d_work};
     for (void* q : ptrs) if (q) cudaFree(q);
     for (auto& t : h->d_tmpl) if (t) cudaFree(t);

@@ -46,6 +46,7 @@ struct IcpArgs {
     float4* cur;             // [F][G][M]
     int* corr;               // [F][G][M]  correspondences as positions in the kd-ordered template
     float* cd;               // [F][G][M]
+    int* order;              // [F][G][M]  Morton order of the source points (nearest-neighbour visiting order only)
     IcpOut* out;             // [F][MAXC][G]
     cuboid_frame_result* res;
     int P, M, KC;
@@ -264,7 +265,7 @@ __device__ __forceinline__ float box_lb(float sx, float sy, float sz, const floa
 // scan in original order with strict '<'.
 template <bool RESIDENT>
 __device__ __forceinline__ void icp_nn_pass(const IcpArgs& a, IcpShared& sh, const float* s_tmpl, const float4* s_nodes, const float4* cur,
-                                            int S, int* corr, float* cd, unsigned long long& evaluated) {
+                                            int S, const int* order, int* corr, float* cd, unsigned long long& evaluated) {
     const int lane = threadIdx.x & 31;
     const float* tp = RESIDENT ? s_tmpl : a.tmpl;
     const int ntask = (S + 31) / 32;
@@ -275,11 +276,12 @@ __device__ __forceinline__ void icp_nn_pass(const IcpArgs& a, IcpShared& sh, con
         if (lane == 0) task = atomicAdd(&sh.task, 1);
         task = __shfl_sync(FULL_MASK, task, 0);
         if (task >= ntask) break;
-        const int i = task * 32 + lane;
-        const int ii = i < S ? i : S - 1;
-        const float4 p = cur[ii];
+        const int k = task * 32 + lane;
+        const bool valid = k < S;
+        const int i = order[valid ? k : S - 1];   // 32 lanes = 32 spatial neighbours: coherent tree walks, broadcast loads
+        const float4 p = cur[i];
         const float sx = p.x, sy = p.y, sz = p.z;
-        int wpos = corr[ii];
+        int wpos = corr[i];
         int worig = a.tmpl_orig[wpos];
         float best;
         {
@@ -289,43 +291,120 @@ __device__ __forceinline__ void icp_nn_pass(const IcpArgs& a, IcpShared& sh, con
         int node = 0;
         unsigned int nleaf_eval = 0;
         while (true) {
+            // phase 1: every lane walks to its next surviving leaf
             int leaf = -1;
-            while (node < nnodes) {   // walk to the next leaf that survives the bound
+            while (node < nnodes) {
                 const float4 lo = s_nodes[2 * node], hi = s_nodes[2 * node + 1];
                 if (cull && box_lb(sx, sy, sz, lo, hi) > best) { node = __float_as_int(lo.w); continue; }
                 leaf = __float_as_int(hi.w);
                 ++node;
                 if (leaf >= 0) break;
             }
-            if (leaf < 0) break;
-            ++nleaf_eval;
-            const float* lf = tp + (size_t)leaf * ICP_LEAF_FLOATS;
-            const int pbase = leaf * ICP_LEAF;
+            // reconverge, so the leaf scans of all lanes issue together
+            if (!__any_sync(FULL_MASK, leaf >= 0)) break;
+            if (leaf >= 0) {
+                ++nleaf_eval;
+                const float* lf = tp + (size_t)leaf * ICP_LEAF_FLOATS;
+                const int pbase = leaf * ICP_LEAF;
 #pragma unroll 2
-            for (int jj = 0; jj < ICP_LEAF; jj += 4) {
-                const float4 X = *reinterpret_cast<const float4*>(lf + jj);
-                const float4 Y = *reinterpret_cast<const float4*>(lf + ICP_LEAF + jj);
-                const float4 Z = *reinterpret_cast<const float4*>(lf + 2 * ICP_LEAF + jj);
-                const float d0 = dist2(sx, sy, sz, X.x, Y.x, Z.x);
-                const float d1 = dist2(sx, sy, sz, X.y, Y.y, Z.y);
-                const float d2 = dist2(sx, sy, sz, X.z, Y.z, Z.z);
-                const float d3 = dist2(sx, sy, sz, X.w, Y.w, Z.w);
-                if (fminf(fminf(d0, d1), fminf(d2, d3)) <= best) {   // rare once the seed is good
-                    const float dd[4] = {d0, d1, d2, d3};
+                for (int jj = 0; jj < ICP_LEAF; jj += 4) {
+                    const float4 X = *reinterpret_cast<const float4*>(lf + jj);
+                    const float4 Y = *reinterpret_cast<const float4*>(lf + ICP_LEAF + jj);
+                    const float4 Z = *reinterpret_cast<const float4*>(lf + 2 * ICP_LEAF + jj);
+                    const float d0 = dist2(sx, sy, sz, X.x, Y.x, Z.x);
+                    const float d1 = dist2(sx, sy, sz, X.y, Y.y, Z.y);
+                    const float d2 = dist2(sx, sy, sz, X.z, Y.z, Z.z);
+                    const float d3 = dist2(sx, sy, sz, X.w, Y.w, Z.w);
+                    if (fminf(fminf(d0, d1), fminf(d2, d3)) <= best) {   // rare once the seed is good
+                        const float dd[4] = {d0, d1, d2, d3};
 #pragma unroll
-                    for (int k = 0; k < 4; ++k) {
-                        if (dd[k] <= best) {
-                            const int pos = pbase + jj + k;
-                            const int o = a.tmpl_orig[pos];
-                            if (dd[k] < best || o < worig) { best = dd[k]; worig = o; wpos = pos; }
+                        for (int q = 0; q < 4; ++q) {
+                            if (dd[q] <= best) {
+                                const int pos = pbase + jj + q;
+                                const int o = a.tmpl_orig[pos];
+                                if (dd[q] < best || o < worig) { best = dd[q]; worig = o; wpos = pos; }
+                            }
                         }
                     }
                 }
             }
+            __syncwarp();
         }
         evaluated += (unsigned long long)nleaf_eval * ICP_LEAF;
-        if (i < S) { corr[i] = wpos; cd[i] = best; }
+        if (valid) { corr[i] = wpos; cd[i] = best; }
     }
+}
+
+// Morton order of the source points (visiting order of the nearest-neighbour pass only; results do not depend
+// on it). Sorted in the dynamic shared memory window BEFORE the template is staged there. S > cap: identity.
+__device__ __forceinline__ unsigned int morton_spread10(unsigned int v) {
+    v = (v | (v << 16)) & 0x030000FFu;
+    v = (v | (v << 8)) & 0x0300F00Fu;
+    v = (v | (v << 4)) & 0x030C30C3u;
+    v = (v | (v << 2)) & 0x09249249u;
+    return v;
+}
+__device__ void icp_morton_order(const float4* src, const int* idx, int S, int* order, unsigned long long* s_keys, int cap, float* s_mm /*[6*8]*/) {
+    int n2 = 1;
+    while (n2 < S) n2 <<= 1;
+    if (S < 64 || n2 > cap) {
+        for (int i = threadIdx.x; i < S; i += ICP_THREADS) order[i] = i;
+        return;
+    }
+    float mn[3] = {3.402823466e38f, 3.402823466e38f, 3.402823466e38f}, mx[3] = {-3.402823466e38f, -3.402823466e38f, -3.402823466e38f};
+    for (int i = threadIdx.x; i < S; i += ICP_THREADS) {
+        const float4 p = src[idx[i]];
+        mn[0] = fminf(mn[0], p.x); mx[0] = fmaxf(mx[0], p.x);
+        mn[1] = fminf(mn[1], p.y); mx[1] = fmaxf(mx[1], p.y);
+        mn[2] = fminf(mn[2], p.z); mx[2] = fmaxf(mx[2], p.z);
+    }
+#pragma unroll
+    for (int o = 16; o >= 1; o >>= 1)
+#pragma unroll
+        for (int c = 0; c < 3; ++c) {
+            mn[c] = fminf(mn[c], __shfl_xor_sync(FULL_MASK, mn[c], o));
+            mx[c] = fmaxf(mx[c], __shfl_xor_sync(FULL_MASK, mx[c], o));
+        }
+    const int lane = threadIdx.x & 31, wid = threadIdx.x >> 5;
+    if (lane == 0)
+        for (int c = 0; c < 3; ++c) { s_mm[wid * 6 + c] = mn[c]; s_mm[wid * 6 + 3 + c] = mx[c]; }
+    __syncthreads();
+    float ext = 0.f;
+    for (int c = 0; c < 3; ++c) {
+        float lo = s_mm[c], hi = s_mm[3 + c];
+        for (int w = 1; w < ICP_THREADS / 32; ++w) { lo = fminf(lo, s_mm[w * 6 + c]); hi = fmaxf(hi, s_mm[w * 6 + 3 + c]); }
+        mn[c] = lo;
+        ext = fmaxf(ext, hi - lo);
+    }
+    const float scale = ext > 0.f ? 1023.0f / ext : 0.f;
+    for (int i = threadIdx.x; i < n2; i += ICP_THREADS) {
+        unsigned long long key = ~0ull;
+        if (i < S) {
+            const float4 p = src[idx[i]];
+            const unsigned int qx = min(1023u, (unsigned int)((p.x - mn[0]) * scale));
+            const unsigned int qy = min(1023u, (unsigned int)((p.y - mn[1]) * scale));
+            const unsigned int qz = min(1023u, (unsigned int)((p.z - mn[2]) * scale));
+            const unsigned int code = morton_spread10(qx) | (morton_spread10(qy) << 1) | (morton_spread10(qz) << 2);
+            key = ((unsigned long long)code << 32) | (unsigned int)i;
+        }
+        s_keys[i] = key;
+    }
+    __syncthreads();
+    for (int k = 2; k <= n2; k <<= 1) {
+        for (int j = k >> 1; j > 0; j >>= 1) {
+            for (int t = threadIdx.x; t < n2; t += ICP_THREADS) {
+                const int u = t ^ j;
+                if (u > t) {
+                    const unsigned long long x = s_keys[t], y = s_keys[u];
+                    const bool up = (t & k) == 0;
+                    if ((x > y) == up) { s_keys[t] = y; s_keys[u] = x; }
+                }
+            }
+            __syncthreads();
+        }
+    }
+    for (int i = threadIdx.x; i < S; i += ICP_THREADS) order[i] = (int)(unsigned int)s_keys[i];
+    __syncthreads();
 }
 
 template <bool RESIDENT>
@@ -339,15 +418,22 @@ __device__ __forceinline__ void icp_body(const IcpArgs& a, IcpShared& sh, float*
     float4* cur = a.cur + pbase;
     int* corr = a.corr + pbase;
     float* cd = a.cd + pbase;
+    int* order = a.order + pbase;
     IcpOut& out = a.out[((size_t)f * CUBOID_MAX_CLUSTERS + c) * a.n_guess + g];
     const bool trace = a.corr_trace && f == 0 && c == 0 && g == 0;
     const float* tp = RESIDENT ? s_tmpl : a.tmpl;
     const bool lane_thread = threadIdx.x < ICP_LANES;
 
-    // ---- stage the template (resident case) and the boxes with TMA bulk copies ----
+    // ---- Morton visiting order, sorted in the (still empty) dynamic shared memory window ----
+    {
+        const int window_bytes = 2 * a.nnodes * 16 + (RESIDENT ? a.Tpad * 12 : 0);
+        icp_morton_order(src, idx, S, order, reinterpret_cast<unsigned long long*>(s_nodes), window_bytes / 8, sh.part_f);
+    }
+    // ---- stage the template (resident case) and the BVH nodes with TMA bulk copies ----
     if (threadIdx.x == 0) {
         mbar_init(&sh.bar, 1);
         asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
+        fence_proxy_async();   // generic-proxy writes of the sort happen-before the async-proxy (TMA) writes
     }
     __syncthreads();
     if (threadIdx.x == 0) {
@@ -413,7 +499,7 @@ __device__ __forceinline__ void icp_body(const IcpArgs& a, IcpShared& sh, float*
     }
     while (!sh.done) {
         // 1. correspondences
-        icp_nn_pass<RESIDENT>(a, sh, s_tmpl, s_nodes, cur, S, corr, cd, evaluated);
+        icp_nn_pass<RESIDENT>(a, sh, s_tmpl, s_nodes, cur, S, order, corr, cd, evaluated);
         ++passes;
         __syncthreads();
         if (threadIdx.x == 0) sh.task = 0;
@@ -514,7 +600,7 @@ __device__ __forceinline__ void icp_body(const IcpArgs& a, IcpShared& sh, float*
     __syncthreads();
     double fitness = 1.7976931348623157e308;
     if (S > 0) {
-        icp_nn_pass<RESIDENT>(a, sh, s_tmpl, s_nodes, cur, S, corr, cd, evaluated);
+        icp_nn_pass<RESIDENT>(a, sh, s_tmpl, s_nodes, cur, S, order, corr, cd, evaluated);
         ++passes;
         __syncthreads();
         double qd[1] = {0.0};

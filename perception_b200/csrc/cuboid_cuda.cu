@@ -36,6 +36,8 @@ struct cuboid_handle {
     int P = 0, B = 0, M = 0, KC = 1024;
     int tilesP = 0, tilesV = 0;
     cudaStream_t stream = nullptr;
+    cudaStream_t copy_stream = nullptr;   // host->device depth copies of chunk k+1 overlap the kernels of chunk k
+    cudaEvent_t ev_copy[2] = {};
     cudaEvent_t ev[6] = {};
     // chunk buffers
     uint16_t* d_depth = nullptr;
@@ -360,8 +362,10 @@ int cuboid_create(cuboid_handle** out, const cuboid_params* p, int device, int m
 #define CA(expr) do { int s_ = (expr); if (s_ != CUBOID_OK) { std::string e = h->last_error; fprintf(stderr, "cuboid_create: %s\n", e.c_str()); return fail(s_); } } while (0)
     if (cudaStreamCreateWithFlags(&h->stream, cudaStreamNonBlocking) != cudaSuccess) return fail(CUBOID_E_CUDA);
     for (auto& e : h->ev) if (cudaEventCreate(&e) != cudaSuccess) return fail(CUBOID_E_CUDA);
+    if (cudaStreamCreateWithFlags(&h->copy_stream, cudaStreamNonBlocking) != cudaSuccess) return fail(CUBOID_E_CUDA);
+    for (auto& e : h->ev_copy) if (cudaEventCreateWithFlags(&e, cudaEventDisableTiming) != cudaSuccess) return fail(CUBOID_E_CUDA);
     const size_t BP = (size_t)h->B * h->P, BM = (size_t)h->B * h->M;
-    CA(dalloc(h, &h->d_depth, BP));
+    CA(dalloc(h, &h->d_depth, 2 * BP));   // double-buffered input chunks
     CA(dalloc(h, &h->d_n_in, (size_t)h->B));
     CA(dalloc(h, &h->d_pts, BP));
     CA(dalloc(h, &h->d_keysA, BP));
@@ -412,6 +416,8 @@ int cuboid_destroy(cuboid_handle* h) {
     for (auto& t : h->d_boxes) if (t) cudaFree(t);
     for (auto& t : h->d_tmpl_orig) if (t) cudaFree(t);
     for (auto& e : h->ev) if (e) cudaEventDestroy(e);
+    for (auto& e : h->ev_copy) if (e) cudaEventDestroy(e);
+    if (h->copy_stream) cudaStreamDestroy(h->copy_stream);
     if (h->stream) cudaStreamDestroy(h->stream);
     delete h;
     return CUBOID_OK;
@@ -719,21 +725,31 @@ static int process_frames(cuboid_handle* h, const uint16_t* depth, bool on_devic
     CKS(h, ensure_results(h, n_frames));
     for (float& m : h->stage_ms) m = 0.f;
     CK(h, cudaMemsetAsync(h->d_work, 0, 16, h->stream));
-    for (int base = 0; base < n_frames; base += h->B) {
+    const size_t buf_stride = (size_t)h->B * h->P;
+    auto issue_copy = [&](int base, int slot) -> int {
+        const int nf = std::min(h->B, n_frames - base);
+        CK(h, cudaMemcpyAsync(h->d_depth + slot * buf_stride, depth + (size_t)base * per, sizeof(uint16_t) * (size_t)nf * per,
+                              cudaMemcpyHostToDevice, h->copy_stream));
+        CK(h, cudaEventRecord(h->ev_copy[slot], h->copy_stream));
+        return CUBOID_OK;
+    };
+    if (!on_device) CKS(h, issue_copy(0, 0));
+    int k = 0;
+    for (int base = 0; base < n_frames; base += h->B, ++k) {
         const int nf = std::min(h->B, n_frames - base);
         ChunkIn in;
         in.w = w; in.hgt = hgt; in.in_stride = per;
         if (on_device) {
             in.depth = depth + (size_t)base * per;
         } else {
-            CK(h, cudaMemcpyAsync(h->d_depth, depth + (size_t)base * per, sizeof(uint16_t) * (size_t)nf * per, cudaMemcpyHostToDevice, h->stream));
-            in.depth = h->d_depth;
+            // the other buffer was last read by chunk k-1, which has been synchronised below: safe to refill now
+            if (base + h->B < n_frames) CKS(h, issue_copy(base + h->B, (k + 1) & 1));
+            CK(h, cudaStreamWaitEvent(h->stream, h->ev_copy[k & 1], 0));
+            in.depth = h->d_depth + (k & 1) * buf_stride;
         }
         CKS(h, run_chunk(h, in, nf, h->d_res + base, stages, tmpl_slot));
-        if (base + nf < n_frames || true) {
-            CK(h, cudaStreamSynchronize(h->stream));   // chunk buffers are reused by the next chunk's events/timers
-            CKS(h, accumulate_stage_ms(h));
-        }
+        CK(h, cudaStreamSynchronize(h->stream));   // chunk buffers and the stage events are reused by the next chunk
+        CKS(h, accumulate_stage_ms(h));
         h->last_chunk_base = base; h->last_chunk_frames = nf;
     }
     h->last_total_frames = n_frames;

@@ -162,7 +162,7 @@ def main():
     ap.add_argument("--warmup", type=int, default=3)
     ap.add_argument("--impl", default="b200")
     ap.add_argument("--frames", type=int, default=1024, help="frames per GPU per step")
-    ap.add_argument("--chunk", type=int, default=256, help="frames resident per chunk (max_batch)")
+    ap.add_argument("--chunk", type=int, default=1024, help="frames resident per chunk (max_batch)")
     ap.add_argument("--cpu-sample", type=int, default=64, help="frames of the CPU baseline sample")
     ap.add_argument("--no-cpu", action="store_true")
     args = ap.parse_args()

@@ -37,7 +37,8 @@ struct cuboid_handle {
     int tilesP = 0, tilesV = 0;
     cudaStream_t stream = nullptr;
     cudaStream_t copy_stream = nullptr;   // host->device depth copies of chunk k+1 overlap the kernels of chunk k
-    cudaEvent_t ev_copy[2] = {};
+    std::vector<cudaEvent_t> ev_pool;     // stage-boundary events of every sub-chunk (timing) + copy events
+    int sub_batch = 128;                  // frames per host->device copy / pre-ICP launch group inside a resident chunk
     cudaEvent_t ev[6] = {};
     // chunk buffers
     uint16_t* d_depth = nullptr;
@@ -165,26 +166,36 @@ int run_chunk(cuboid_handle* h, const ChunkIn& in, int nf, cuboid_frame_result* 
               bool skip_pre = false, bool skip_vox = false, bool skip_plane = false, bool skip_cluster = false,
               const int* d_triplets = nullptr, int n_triplets = 0, const float* guesses_override = nullptr, int n_guess_override = 0,
               int guess_mode_override = 0, int* trace_corr = nullptr, float* trace_T = nullptr, int cap_trace = 0,
-              float4* aligned = nullptr, bool force_cluster = false) {
+              float4* aligned = nullptr, bool force_cluster = false, int f0 = 0, cudaEvent_t* evs = nullptr) {
     cudaStream_t st = h->stream;
     const cuboid_params& p = h->p;
-    CK(h, cudaEventRecord(h->ev[0], st));
+    if (!evs) evs = h->ev;
+    // per-frame buffers of the sub-range starting at frame f0 of the resident chunk (d_res is already offset by the caller)
+    const size_t oP = (size_t)f0 * h->P, oM = (size_t)f0 * h->M;
+    float4* b_pts = h->d_pts + oP; unsigned long long* b_keysA = h->d_keysA + oP; unsigned long long* b_keysB = h->d_keysB + oP;
+    int* b_kpp = h->d_kpp + oP; unsigned int* b_hist = h->d_hist + (size_t)f0 * 256 * h->tilesP; float4* b_vox = h->d_vox + oP;
+    int* b_vcount = h->d_vcount + oP; int* b_shuffled = h->d_shuffled + oP; int* b_inl_pre = h->d_inl_pre + oP; int* b_inl = h->d_inl + oP;
+    float4* b_remain = h->d_remain + oP; int* b_parent = h->d_parent + oM; int* b_csize = h->d_csize + oM; int* b_crank = h->d_crank + oM;
+    int* b_idx_sorted = h->d_idx_sorted + oM; int* b_offsets = h->d_offsets + (size_t)f0 * (h->KC + 1); int* b_roots = h->d_roots + (size_t)f0 * h->KC;
+    FrameScratch* b_scr = h->d_scr + f0; unsigned long long* b_desc1 = h->d_desc1 + (size_t)f0 * h->tilesP;
+    unsigned long long* b_desc2 = h->d_desc2 + (size_t)f0 * h->tilesV;
+    CK(h, cudaEventRecord(evs[0], st));
     if ((stages & 1) && !skip_pre) {
         CK(h, cudaMemsetAsync(d_res, 0, sizeof(cuboid_frame_result) * nf, st));
-        k_init_scratch<<<(nf + 127) / 128, 128, 0, st>>>(h->d_scr, nf);
+        k_init_scratch<<<(nf + 127) / 128, 128, 0, st>>>(b_scr, nf);
         ++h->launches;
         const int per = in.in_stride;
         const int tiles = (per + PRE_TILE - 1) / PRE_TILE;
-        CK(h, cudaMemsetAsync(h->d_desc1, 0, sizeof(unsigned long long) * (size_t)nf * h->tilesP, st));
+        CK(h, cudaMemsetAsync(b_desc1, 0, sizeof(unsigned long long) * (size_t)nf * h->tilesP, st));
         CK(h, cudaMemsetAsync(h->d_ticket, 0, sizeof(unsigned int) * 4, st));
         PreArgs a{};
         a.depth = in.depth; a.blob = in.blob; a.point_step = in.point_step; a.xoff = in.xoff; a.yoff = in.yoff; a.zoff = in.zoff;
-        a.n_in = in.blob ? h->d_n_in : nullptr;
+        a.n_in = in.blob ? h->d_n_in + f0 : nullptr;
         a.w = in.w; a.h = in.hgt; a.P = per;
         a.fx = p.fx; a.fy = p.fy; a.cx = p.cx; a.cy = p.cy; a.depth_scale = p.depth_scale;
         a.z_lo = limit_lo(p.pass_z_min); a.z_hi = limit_hi(p.pass_z_max);
         a.x_lo = limit_lo(p.pass_x_min); a.x_hi = limit_hi(p.pass_x_max);
-        a.pts = h->d_pts; a.res = d_res; a.scr = h->d_scr; a.desc = h->d_desc1; a.ticket = h->d_ticket;
+        a.pts = b_pts; a.res = d_res; a.scr = b_scr; a.desc = b_desc1; a.ticket = h->d_ticket;
         a.tiles = tiles; a.n_frames = nf;
         a.Pout = h->P;
         if (tiles > h->tilesP) return CUBOID_E_CAPACITY;
@@ -193,14 +204,14 @@ int run_chunk(cuboid_handle* h, const ChunkIn& in, int nf, cuboid_frame_result* 
         ++h->launches;
         CK(h, cudaGetLastError());
     }
-    CK(h, cudaEventRecord(h->ev[1], st));
+    CK(h, cudaEventRecord(evs[1], st));
     if ((stages & 1) && !skip_vox) {
         VoxArgs v{};
-        v.pts = h->d_pts; v.keysA = h->d_keysA; v.keysB = h->d_keysB; v.kpp = h->taps ? h->d_kpp : nullptr; v.hist = h->d_hist;
-        v.vox = h->d_vox; v.vcount = h->taps ? h->d_vcount : nullptr; v.res = d_res; v.scr = h->d_scr; v.desc = h->d_desc2;
+        v.pts = b_pts; v.keysA = b_keysA; v.keysB = b_keysB; v.kpp = h->taps ? b_kpp : nullptr; v.hist = b_hist;
+        v.vox = b_vox; v.vcount = h->taps ? b_vcount : nullptr; v.res = d_res; v.scr = b_scr; v.desc = b_desc2;
         v.ticket = h->d_ticket + 1; v.P = h->P; v.tilesP = h->tilesP; v.tilesV = h->tilesV; v.n_frames = nf;
         v.inv_leaf = 1.0f / p.leaf;
-        CK(h, cudaMemsetAsync(h->d_desc2, 0, sizeof(unsigned long long) * (size_t)nf * h->tilesV, st));
+        CK(h, cudaMemsetAsync(b_desc2, 0, sizeof(unsigned long long) * (size_t)nf * h->tilesV, st));
         k_voxel_empty<<<(nf + 127) / 128, 128, 0, st>>>(v);
         k_voxel_keys<<<dim3((h->P + 255) / 256, nf), 256, 0, st>>>(v);
         h->launches += 2;
@@ -214,12 +225,12 @@ int run_chunk(cuboid_handle* h, const ChunkIn& in, int nf, cuboid_frame_result* 
         ++h->launches;
         CK(h, cudaGetLastError());
     }
-    CK(h, cudaEventRecord(h->ev[2], st));
+    CK(h, cudaEventRecord(evs[2], st));
     if ((stages & 2) && !skip_plane) {
         SacArgs s{};
-        s.vox = h->d_vox; s.shuffled = h->d_shuffled; s.rng = h->d_rng; s.rng_len = h->rng_len;
+        s.vox = b_vox; s.shuffled = b_shuffled; s.rng = h->d_rng; s.rng_len = h->rng_len;
         s.triplets = d_triplets; s.n_triplets = n_triplets;
-        s.inl_pre = h->d_inl_pre; s.inl = h->d_inl; s.remain = h->d_remain; s.res = d_res; s.scr = h->d_scr; s.P = h->P;
+        s.inl_pre = b_inl_pre; s.inl = b_inl; s.remain = b_remain; s.res = d_res; s.scr = b_scr; s.P = h->P;
         s.thr_f = thr_up(p.sac_threshold); s.max_iter = p.sac_max_iter; s.log_prob = std::log(1.0 - p.sac_prob);
         s.refine = p.sac_refine; s.negative = p.extract_negative;
         s.use_z2 = p.use_pass_z2; s.z2_lo = limit_lo(p.pass_z2_min); s.z2_hi = limit_hi(p.pass_z2_max);
@@ -228,18 +239,18 @@ int run_chunk(cuboid_handle* h, const ChunkIn& in, int nf, cuboid_frame_result* 
         ++h->launches;
         CK(h, cudaGetLastError());
     }
-    CK(h, cudaEventRecord(h->ev[3], st));
+    CK(h, cudaEventRecord(evs[3], st));
     if ((stages & 4) && !skip_cluster) {
         CluArgs c{};
-        c.remain = h->d_remain; c.parent = h->d_parent; c.csize = h->d_csize; c.crank = h->d_crank; c.idx_sorted = h->d_idx_sorted;
-        c.offsets = h->d_offsets; c.roots = h->d_roots; c.res = d_res; c.P = h->P; c.M = h->M; c.KC = h->KC;
+        c.remain = b_remain; c.parent = b_parent; c.csize = b_csize; c.crank = b_crank; c.idx_sorted = b_idx_sorted;
+        c.offsets = b_offsets; c.roots = b_roots; c.res = d_res; c.P = h->P; c.M = h->M; c.KC = h->KC;
         c.r2 = (float)(p.cluster_tol * p.cluster_tol); c.min_size = p.cluster_min; c.max_size = p.cluster_max;
         c.use_cluster = force_cluster ? 1 : p.use_cluster;
         k_cluster<<<nf, CLU_THREADS, 0, st>>>(c);
         ++h->launches;
         CK(h, cudaGetLastError());
     }
-    CK(h, cudaEventRecord(h->ev[4], st));
+    CK(h, cudaEventRecord(evs[4], st));
     if (stages & 8) {
         if (tmpl_slot < 0 || tmpl_slot >= CUBOID_MAX_TEMPLATES || !h->d_tmpl[tmpl_slot]) return CUBOID_E_NO_TEMPLATE;
         const float* gs = guesses_override ? guesses_override : (h->have_guesses ? h->d_guesses : nullptr);
@@ -268,7 +279,7 @@ int run_chunk(cuboid_handle* h, const ChunkIn& in, int nf, cuboid_frame_result* 
         h->launches += 2;
         CK(h, cudaGetLastError());
     }
-    CK(h, cudaEventRecord(h->ev[5], st));
+    CK(h, cudaEventRecord(evs[5], st));
     return CUBOID_OK;
 }
 
@@ -363,9 +374,9 @@ int cuboid_create(cuboid_handle** out, const cuboid_params* p, int device, int m
     if (cudaStreamCreateWithFlags(&h->stream, cudaStreamNonBlocking) != cudaSuccess) return fail(CUBOID_E_CUDA);
     for (auto& e : h->ev) if (cudaEventCreate(&e) != cudaSuccess) return fail(CUBOID_E_CUDA);
     if (cudaStreamCreateWithFlags(&h->copy_stream, cudaStreamNonBlocking) != cudaSuccess) return fail(CUBOID_E_CUDA);
-    for (auto& e : h->ev_copy) if (cudaEventCreateWithFlags(&e, cudaEventDisableTiming) != cudaSuccess) return fail(CUBOID_E_CUDA);
+    { const char* es = std::getenv("CUBOID_SUB_BATCH"); if (es) h->sub_batch = std::max(1, atoi(es)); }
     const size_t BP = (size_t)h->B * h->P, BM = (size_t)h->B * h->M;
-    CA(dalloc(h, &h->d_depth, 2 * BP));   // double-buffered input chunks
+    CA(dalloc(h, &h->d_depth, BP));
     CA(dalloc(h, &h->d_n_in, (size_t)h->B));
     CA(dalloc(h, &h->d_pts, BP));
     CA(dalloc(h, &h->d_keysA, BP));
@@ -416,7 +427,7 @@ int cuboid_destroy(cuboid_handle* h) {
     for (auto& t : h->d_boxes) if (t) cudaFree(t);
     for (auto& t : h->d_tmpl_orig) if (t) cudaFree(t);
     for (auto& e : h->ev) if (e) cudaEventDestroy(e);
-    for (auto& e : h->ev_copy) if (e) cudaEventDestroy(e);
+    for (auto& e : h->ev_pool) if (e) cudaEventDestroy(e);
     if (h->copy_stream) cudaStreamDestroy(h->copy_stream);
     if (h->stream) cudaStreamDestroy(h->stream);
     delete h;
@@ -725,31 +736,57 @@ static int process_frames(cuboid_handle* h, const uint16_t* depth, bool on_devic
     CKS(h, ensure_results(h, n_frames));
     for (float& m : h->stage_ms) m = 0.f;
     CK(h, cudaMemsetAsync(h->d_work, 0, 16, h->stream));
-    const size_t buf_stride = (size_t)h->B * h->P;
-    auto issue_copy = [&](int base, int slot) -> int {
+    // A resident chunk (<= B frames) is fed in sub-chunks: every sub-chunk's depth copy is queued on the copy stream up
+    // front, its pre-ICP kernels start as soon as that copy lands (so copies overlap kernels), and ICP runs once over the
+    // whole chunk so that its one-CTA-per-problem grid spans several waves (the slowest problem no longer sets the time).
+    const int SUB = std::min(h->sub_batch, h->B);
+    const int max_sub = (h->B + SUB - 1) / SUB;
+    const size_t need_ev = (size_t)max_sub * 6 + 2;
+    while (h->ev_pool.size() < need_ev) {
+        cudaEvent_t e;
+        CK(h, cudaEventCreate(&e));
+        h->ev_pool.push_back(e);
+    }
+    for (int base = 0; base < n_frames; base += h->B) {
         const int nf = std::min(h->B, n_frames - base);
-        CK(h, cudaMemcpyAsync(h->d_depth + slot * buf_stride, depth + (size_t)base * per, sizeof(uint16_t) * (size_t)nf * per,
-                              cudaMemcpyHostToDevice, h->copy_stream));
-        CK(h, cudaEventRecord(h->ev_copy[slot], h->copy_stream));
-        return CUBOID_OK;
-    };
-    if (!on_device) CKS(h, issue_copy(0, 0));
-    int k = 0;
-    for (int base = 0; base < n_frames; base += h->B, ++k) {
-        const int nf = std::min(h->B, n_frames - base);
-        ChunkIn in;
-        in.w = w; in.hgt = hgt; in.in_stride = per;
-        if (on_device) {
-            in.depth = depth + (size_t)base * per;
-        } else {
-            // the other buffer was last read by chunk k-1, which has been synchronised below: safe to refill now
-            if (base + h->B < n_frames) CKS(h, issue_copy(base + h->B, (k + 1) & 1));
-            CK(h, cudaStreamWaitEvent(h->stream, h->ev_copy[k & 1], 0));
-            in.depth = h->d_depth + (k & 1) * buf_stride;
+        const int nsub = (nf + SUB - 1) / SUB;
+        if (!on_device)
+            for (int sb = 0; sb < nsub; ++sb) {
+                const int f0 = sb * SUB, n = std::min(SUB, nf - f0);
+                CK(h, cudaMemcpyAsync(h->d_depth + (size_t)f0 * per, depth + (size_t)(base + f0) * per, sizeof(uint16_t) * (size_t)n * per,
+                                      cudaMemcpyHostToDevice, h->copy_stream));
+                CK(h, cudaEventRecord(h->ev_pool[(size_t)sb * 6 + 5], h->copy_stream));
+            }
+        for (int sb = 0; sb < nsub; ++sb) {
+            const int f0 = sb * SUB, n = std::min(SUB, nf - f0);
+            ChunkIn in;
+            in.w = w; in.hgt = hgt; in.in_stride = per;
+            if (on_device) in.depth = depth + (size_t)(base + f0) * per;
+            else {
+                CK(h, cudaStreamWaitEvent(h->stream, h->ev_pool[(size_t)sb * 6 + 5], 0));
+                in.depth = h->d_depth + (size_t)f0 * per;
+            }
+            CKS(h, run_chunk(h, in, n, h->d_res + base + f0, stages & 1, tmpl_slot, false, false, false, false, nullptr, 0, nullptr, 0, 0,
+                             nullptr, nullptr, 0, nullptr, false, f0, &h->ev_pool[(size_t)sb * 6]));
         }
-        CKS(h, run_chunk(h, in, nf, h->d_res + base, stages, tmpl_slot));
-        CK(h, cudaStreamSynchronize(h->stream));   // chunk buffers and the stage events are reused by the next chunk
-        CKS(h, accumulate_stage_ms(h));
+        // plane segmentation, clustering and ICP are one CTA per frame / per problem: launch them over the whole chunk
+        if (stages & 14) {
+            ChunkIn none;
+            CKS(h, run_chunk(h, none, nf, h->d_res + base, stages & 14, tmpl_slot, true, true, false, false));
+        }
+        CK(h, cudaStreamSynchronize(h->stream));   // chunk buffers and the events are reused by the next chunk
+        for (int sb = 0; sb < nsub; ++sb)
+            for (int sg = 0; sg < 2; ++sg) {
+                float ms = 0.f;
+                CK(h, cudaEventElapsedTime(&ms, h->ev_pool[(size_t)sb * 6 + sg], h->ev_pool[(size_t)sb * 6 + sg + 1]));
+                h->stage_ms[sg] += ms;
+            }
+        if (stages & 14)
+            for (int sg = 2; sg < 5; ++sg) {
+                float ms = 0.f;
+                CK(h, cudaEventElapsedTime(&ms, h->ev[sg], h->ev[sg + 1]));
+                h->stage_ms[sg] += ms;
+            }
         h->last_chunk_base = base; h->last_chunk_frames = nf;
     }
     h->last_total_frames = n_frames;

@@ -58,7 +58,7 @@ struct IcpArgs {
     int* corr_trace; float* T_trace; int cap_trace;   // debug taps for problem (0,0,0)
 };
 
-constexpr int ICP_THREADS = 256;   // = the 256 canonical reduction lanes; two CTAs (two ICP problems) share an SM
+constexpr int ICP_THREADS = 512;   // first 256 = the canonical reduction lanes; two CTAs (two ICP problems) share an SM
 constexpr int ICP_LANES = 256;
 constexpr int ICP_LEAF = 32;       // template points per BVH leaf
 

@@ -9,6 +9,7 @@
 //   cur     f32x4 [B][G][M]  ICP working source, corr i32 / cd f32 alike   res     cuboid_frame_result[n_frames]
 // Points are float4 (x,y,z,1) = pcl::PointXYZ's 16-byte layout, so every point access is one 128-bit
 // coalesced load/store.
+#include <cuda_fp16.h>
 #include <cuda_runtime.h>
 
 #include <algorithm>
@@ -62,7 +63,7 @@ struct cuboid_handle {
     int* d_rng = nullptr; int rng_len = 0;
     int* d_triplets = nullptr; int triplets_cap = 0;
     float* d_tmpl[CUBOID_MAX_TEMPLATES] = {}; int* d_tmpl_orig[CUBOID_MAX_TEMPLATES] = {}; int tmpl_n[CUBOID_MAX_TEMPLATES] = {}; int tmpl_pad[CUBOID_MAX_TEMPLATES] = {};
-    float4* d_boxes[CUBOID_MAX_TEMPLATES] = {}; int tmpl_nleaf[CUBOID_MAX_TEMPLATES] = {}; int tmpl_nnodes[CUBOID_MAX_TEMPLATES] = {};
+    uint4* d_boxes[CUBOID_MAX_TEMPLATES] = {}; int tmpl_nleaf[CUBOID_MAX_TEMPLATES] = {}; int tmpl_nnodes[CUBOID_MAX_TEMPLATES] = {};
     unsigned long long* d_work = nullptr; unsigned long long work_total[2] = {0, 0};
     int icp_cull = 1;
     float* d_guesses = nullptr; int n_guess = 1; int guess_mode = 0; bool have_guesses = false;
@@ -265,7 +266,7 @@ int run_chunk(cuboid_handle* h, const ChunkIn& in, int nf, cuboid_frame_result* 
         a.cur = h->d_cur; a.corr = h->d_corr; a.cd = h->d_cd; a.order = h->d_order; a.out = h->d_icp_out; a.res = d_res;
         a.P = h->P; a.M = h->M; a.KC = h->KC; a.max_iter = p.icp_max_iter;
         a.rot_thr = 1.0 - p.icp_tf_eps; a.trans_thr = p.icp_tf_eps; a.rel_mse = p.icp_rel_mse; a.abs_thr = 1e-12;
-        const size_t box_bytes = (size_t)(2 * a.nnodes) * 16;
+        const size_t box_bytes = (size_t)a.nnodes * 16;
         if (box_bytes > (size_t)h->icp_smem_budget) return CUBOID_E_CAPACITY;
         a.resident = (box_bytes + (size_t)a.Tpad * 12 <= (size_t)h->icp_smem_budget) ? 1 : 0;
         a.cull = h->icp_cull;
@@ -496,7 +497,20 @@ int cuboid_set_template(cuboid_handle* h, int slot, const float* xyz, int stride
     std::vector<BvhNode> nodes;
     nodes.reserve(2 * (size_t)nleaf);
     bvh_build(items.data(), 0, n, nodes);
-    static_assert(sizeof(BvhNode) == 32, "BVH node = two float4");
+    // pack to 16 B: fp16 box rounded outward (still contains the subtree, so the bound stays exact) + link
+    std::vector<uint4> packed(nodes.size());
+    for (size_t i = 0; i < nodes.size(); ++i) {
+        unsigned short hb[6];
+        for (int d = 0; d < 3; ++d) {
+            const __half lo = __float2half_rd(nodes[i].lo[d]), hi = __float2half_ru(nodes[i].hi[d]);
+            std::memcpy(&hb[d], &lo, 2);
+            std::memcpy(&hb[3 + d], &hi, 2);
+        }
+        packed[i].x = (unsigned int)hb[0] | ((unsigned int)hb[1] << 16);
+        packed[i].y = (unsigned int)hb[2] | ((unsigned int)hb[3] << 16);
+        packed[i].z = (unsigned int)hb[4] | ((unsigned int)hb[5] << 16);
+        packed[i].w = (unsigned int)(nodes[i].leaf >= 0 ? ~nodes[i].leaf : nodes[i].skip);
+    }
     // SoA per leaf: x[32] y[32] z[32]; far sentinels (huge but finite distance: never win, never NaN) pad the tail
     std::vector<float> host((size_t)pad * 3, 1.0e18f);
     std::vector<int> orig(pad, 0x7fffffff);
@@ -510,10 +524,10 @@ int cuboid_set_template(cuboid_handle* h, int slot, const float* xyz, int stride
     if (h->d_boxes[slot]) { cudaFree(h->d_boxes[slot]); h->d_boxes[slot] = nullptr; }
     CKS(h, dalloc(h, &h->d_tmpl[slot], host.size()));
     CKS(h, dalloc(h, &h->d_tmpl_orig[slot], orig.size()));
-    CKS(h, dalloc(h, &h->d_boxes[slot], 2 * nodes.size()));
+    CKS(h, dalloc(h, &h->d_boxes[slot], packed.size()));
     CK(h, cudaMemcpy(h->d_tmpl[slot], host.data(), sizeof(float) * host.size(), cudaMemcpyHostToDevice));
     CK(h, cudaMemcpy(h->d_tmpl_orig[slot], orig.data(), sizeof(int) * orig.size(), cudaMemcpyHostToDevice));
-    CK(h, cudaMemcpy(h->d_boxes[slot], nodes.data(), sizeof(BvhNode) * nodes.size(), cudaMemcpyHostToDevice));
+    CK(h, cudaMemcpy(h->d_boxes[slot], packed.data(), sizeof(uint4) * packed.size(), cudaMemcpyHostToDevice));
     h->tmpl_n[slot] = n; h->tmpl_pad[slot] = pad; h->tmpl_nleaf[slot] = nleaf; h->tmpl_nnodes[slot] = (int)nodes.size();
     return CUBOID_OK;
 }

@@ -21,6 +21,8 @@
 // Roofline: FP32 pipe (un-fused). Brute force is 8*S*T ops per pass; the culled kernel reports both the
 // pairs it actually evaluated and the brute-force equivalent (IcpArgs::work).
 #pragma once
+#include <cuda_fp16.h>
+
 #include "common.cuh"
 #include "ransac.cuh"   // TMA bulk-copy helpers
 
@@ -39,7 +41,8 @@ struct IcpArgs {
     const int* offsets;      // [F][KC+1]
     const float* tmpl;       // [nleaf][3][32] kd-ordered 32-point leaves, SoA per leaf (x[32] y[32] z[32]); far sentinels pad the tail
     const int* tmpl_orig;    // [Tpad] original template index of every kd-ordered position (sentinels: INT_MAX)
-    const float4* nodes;     // [2*nnodes] depth-first BVH: (lo.xyz, skip link) (hi.xyz, leaf id or -1)
+    const uint4* nodes;      // [nnodes] depth-first BVH, 16 B each: fp16 AABB rounded OUTWARD (lo down, hi up) + link
+                             //          (link >= 0: inner node, index of the first node after its subtree; link < 0: leaf ~link)
     int T, Tpad, nleaf, nnodes;
     const float* guesses;    // n_guess * (16 | 9) or NULL
     int n_guess, guess_mode;
@@ -60,7 +63,7 @@ struct IcpArgs {
 
 constexpr int ICP_THREADS = 512;   // first 256 = the canonical reduction lanes; two CTAs (two ICP problems) share an SM
 constexpr int ICP_LANES = 256;
-constexpr int ICP_LEAF = 32;       // template points per BVH leaf
+constexpr int ICP_LEAF = 16;       // template points per BVH leaf
 
 
 struct M3f { float a[3][3]; };
@@ -256,6 +259,15 @@ __device__ __forceinline__ float box_lb(float sx, float sy, float sz, const floa
     return ((dx * dx) + dy * dy) + dz * dz;
 }
 
+// fp16 box -> float lower bound. The box was widened outward when it was rounded to fp16, so it still contains every
+// point of the subtree and box_lb stays a true lower bound.
+__device__ __forceinline__ float node_lb(float sx, float sy, float sz, const uint4 nd) {
+    const float2 a = __half22float2(*reinterpret_cast<const __half2*>(&nd.x));
+    const float2 b = __half22float2(*reinterpret_cast<const __half2*>(&nd.y));
+    const float2 c = __half22float2(*reinterpret_cast<const __half2*>(&nd.z));
+    return box_lb(sx, sy, sz, make_float4(a.x, a.y, b.x, 0.f), make_float4(b.y, c.x, c.y, 0.f));
+}
+
 // One nearest-neighbour pass over cur[0..S): writes corr[] (kd-ordered template position) and cd[].
 // On entry corr[] holds a valid template position per point (the previous pass's answer, or 0): its distance
 // seeds the running minimum so the culling is tight from the first node.
@@ -264,7 +276,7 @@ __device__ __forceinline__ float box_lb(float sx, float sy, float sz, const floa
 // ever skipped; among equal distances the LOWEST ORIGINAL template index wins — the answer of a brute-force
 // scan in original order with strict '<'.
 template <bool RESIDENT>
-__device__ __forceinline__ void icp_nn_pass(const IcpArgs& a, IcpShared& sh, const float* s_tmpl, const float4* s_nodes, const float4* cur,
+__device__ __forceinline__ void icp_nn_pass(const IcpArgs& a, IcpShared& sh, const float* s_tmpl, const uint4* s_nodes, const float4* cur,
                                             int S, const int* order, int* corr, float* cd, unsigned long long& evaluated) {
     const int lane = threadIdx.x & 31;
     const float* tp = RESIDENT ? s_tmpl : a.tmpl;
@@ -294,11 +306,11 @@ __device__ __forceinline__ void icp_nn_pass(const IcpArgs& a, IcpShared& sh, con
             // phase 1: every lane walks to its next surviving leaf
             int leaf = -1;
             while (node < nnodes) {
-                const float4 lo = s_nodes[2 * node], hi = s_nodes[2 * node + 1];
-                if (cull && box_lb(sx, sy, sz, lo, hi) > best) { node = __float_as_int(lo.w); continue; }
-                leaf = __float_as_int(hi.w);
+                const uint4 nd = s_nodes[node];
+                const int link = (int)nd.w;
+                if (cull && node_lb(sx, sy, sz, nd) > best) { node = link >= 0 ? link : node + 1; continue; }
                 ++node;
-                if (leaf >= 0) break;
+                if (link < 0) { leaf = ~link; break; }
             }
             // reconverge, so the leaf scans of all lanes issue together
             if (!__any_sync(FULL_MASK, leaf >= 0)) break;
@@ -306,7 +318,7 @@ __device__ __forceinline__ void icp_nn_pass(const IcpArgs& a, IcpShared& sh, con
                 ++nleaf_eval;
                 const float* lf = tp + (size_t)leaf * ICP_LEAF_FLOATS;
                 const int pbase = leaf * ICP_LEAF;
-#pragma unroll 2
+#pragma unroll
                 for (int jj = 0; jj < ICP_LEAF; jj += 4) {
                     const float4 X = *reinterpret_cast<const float4*>(lf + jj);
                     const float4 Y = *reinterpret_cast<const float4*>(lf + ICP_LEAF + jj);
@@ -408,7 +420,7 @@ __device__ void icp_morton_order(const float4* src, const int* idx, int S, int* 
 }
 
 template <bool RESIDENT>
-__device__ __forceinline__ void icp_body(const IcpArgs& a, IcpShared& sh, float* s_tmpl, float4* s_nodes) {
+__device__ __forceinline__ void icp_body(const IcpArgs& a, IcpShared& sh, float* s_tmpl, uint4* s_nodes) {
     const int g = blockIdx.x, c = blockIdx.y, f = blockIdx.z;
     const int* offsets = a.offsets + (size_t)f * (a.KC + 1);
     const int o0 = offsets[c], S = offsets[c + 1] - o0;
@@ -426,7 +438,7 @@ __device__ __forceinline__ void icp_body(const IcpArgs& a, IcpShared& sh, float*
 
     // ---- Morton visiting order, sorted in the (still empty) dynamic shared memory window ----
     {
-        const int window_bytes = 2 * a.nnodes * 16 + (RESIDENT ? a.Tpad * 12 : 0);
+        const int window_bytes = a.nnodes * 16 + (RESIDENT ? a.Tpad * 12 : 0);
         icp_morton_order(src, idx, S, order, reinterpret_cast<unsigned long long*>(s_nodes), window_bytes / 8, sh.part_f);
     }
     // ---- stage the template (resident case) and the BVH nodes with TMA bulk copies ----
@@ -438,7 +450,7 @@ __device__ __forceinline__ void icp_body(const IcpArgs& a, IcpShared& sh, float*
     __syncthreads();
     if (threadIdx.x == 0) {
         const unsigned int tb = RESIDENT ? (unsigned int)a.Tpad * 12u : 0u;
-        const unsigned int bb = (unsigned int)(2 * a.nnodes) * 16u;
+        const unsigned int bb = (unsigned int)a.nnodes * 16u;
         mbar_expect_tx(&sh.bar, tb + bb);
         for (unsigned int off = 0; off < tb; off += 32768u)
             tma_bulk_g2s(reinterpret_cast<unsigned char*>(s_tmpl) + off, reinterpret_cast<const unsigned char*>(a.tmpl) + off, min(32768u, tb - off), &sh.bar);
@@ -636,9 +648,9 @@ __global__ void __launch_bounds__(ICP_THREADS, 2) k_icp(const IcpArgs a) {
     __shared__ IcpShared sh;
     const cuboid_frame_result& R = a.res[blockIdx.z];
     if ((int)blockIdx.y >= min(R.n_clusters, CUBOID_MAX_CLUSTERS)) return;
-    // dynamic shared memory: [BVH nodes (2*nnodes float4)] [template SoA leaves (Tpad*3 floats, resident case only)]
-    float4* s_nodes = reinterpret_cast<float4*>(smem_raw);
-    float* s_tmpl = reinterpret_cast<float*>(s_nodes + 2 * a.nnodes);
+    // dynamic shared memory: [BVH nodes (nnodes x 16 B)] [template SoA leaves (Tpad*3 floats, resident case only)]
+    uint4* s_nodes = reinterpret_cast<uint4*>(smem_raw);
+    float* s_tmpl = reinterpret_cast<float*>(s_nodes + a.nnodes);
     if (a.resident) icp_body<true>(a, sh, s_tmpl, s_nodes);
     else icp_body<false>(a, sh, s_tmpl, s_nodes);
 }

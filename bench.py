@@ -114,13 +114,17 @@ def run_reference(args, rank, world):
     from oracle import pyoracle as O
     from perception_b200.params import default_params
     cores = os.cpu_count() or 1
-    p = O.params_from(default_params("cuboid"))
-    tm = template()
+    wl = WORKLOADS[args.workload]
+    dp = default_params(wl["variant"])
+    dp.n_guess, dp.guess_mode = wl["n_guess"], (1 if wl["n_guess"] > 1 else 0)
+    p = O.params_from(dp)
+    tm = template() if wl["stages"] & 8 else None
+    rots = guess_rotations() if wl["n_guess"] > 1 else None
     per_step = max(cores, 2 * cores if args.frames >= 2 * cores else cores)
-    frames = make_frames(per_step, 0)
+    frames = make_frames(per_step, 0, wl["kind"])
 
     def one(i):
-        return O.process_frame(p, frames[i], tm)
+        return O.process_frame(p, frames[i], tm, guesses=rots)
 
     def step():
         with ThreadPoolExecutor(max_workers=cores) as ex:   # ctypes releases the GIL: frames run in parallel
@@ -146,12 +150,44 @@ def run_reference(args, rank, world):
     print(json.dumps(line), flush=True)
 
 
+# BASELINE.json configs: "full" is the headline workload (configs[1]'s batch with the metric's full path);
+# the others are secondary lines for profiles/ (python bench.py --workload seg|guess64|multi8|hd720).
+WORKLOADS = {
+    "full":    dict(kind="bench",  variant="cuboid", stages=15, n_guess=1,  w=640,  h=480,
+                    text="table + one 200x100x30 mm cuboid; full hot path: unproject + passthrough + voxel(5 mm) + RANSAC plane + extract + "
+                         "Euclidean clustering + ICP vs template_cuboid_L200_W100_H30_3faces (7250 pts), 1 initial-pose hypothesis"),
+    "seg":     dict(kind="plane_var", variant="cuboid", stages=3, n_guess=1, w=640, h=480,
+                    text="BASELINE configs[1]: ground-plane segmentation only (unproject + passthrough + voxel + RANSAC plane + extract)"),
+    "guess64": dict(kind="bench",  variant="cuboid", stages=15, n_guess=64, w=640,  h=480,
+                    text="BASELINE configs[2]: full path with 64 initial-pose hypotheses per cluster (8 yaw x 8 flips about the cluster centroid)"),
+    "multi8":  dict(kind="multi8", variant="multi8", stages=15, n_guess=1,  w=640,  h=480,
+                    text="BASELINE configs[3]: 8 cuboids per frame, pass_x +-0.4, one ICP per cluster"),
+    "hd720":   dict(kind="hd720",  variant="hd720",  stages=15, n_guess=1,  w=1280, h=720,
+                    text="BASELINE configs[4]: 1280x720, 2 mm leaf (~870k points, ~620k voxels per frame)"),
+}
+
+
+def guess_rotations():
+    """identity + 63 rotations: 8 yaw steps x (4 roll quarter-turns x 2 pitch half-turns), applied about the cluster centroid."""
+    def rx(a): return np.array([[1, 0, 0], [0, np.cos(a), -np.sin(a)], [0, np.sin(a), np.cos(a)]])
+    def ry(a): return np.array([[np.cos(a), 0, np.sin(a)], [0, 1, 0], [-np.sin(a), 0, np.cos(a)]])
+    def rz(a): return np.array([[np.cos(a), -np.sin(a), 0], [np.sin(a), np.cos(a), 0], [0, 0, 1]])
+    out = []
+    for r in range(4):
+        for pch in range(2):
+            for yw in range(8):
+                out.append(rz(yw * np.pi / 4) @ ry(pch * np.pi) @ rx(r * np.pi / 2))
+    out = np.asarray(out, dtype=np.float32)
+    out[0] = np.eye(3, dtype=np.float32)
+    return out
+
+
 def workload_config(args, frames_per_gpu):
-    return {"workload": "batch of %d synthetic 640x480 D435 depth frames per GPU (table + one 200x100x30 mm cuboid), full hot path: "
-                        "unproject + passthrough + voxel(5 mm) + RANSAC plane + extract + Euclidean clustering + ICP vs "
-                        "template_cuboid_L200_W100_H30_3faces (7250 pts), 1 initial-pose hypothesis" % frames_per_gpu,
-            "frames_per_gpu": frames_per_gpu, "image": [W, H], "template_points": 7250, "leaf": 0.005, "n_guess": 1,
-            "l2": "inputs (%.0f MB of depth per GPU per step) are larger than the 126 MB L2" % (frames_per_gpu * W * H * 2 / 1e6),
+    wl = WORKLOADS[args.workload]
+    return {"workload": "batch of %d synthetic %dx%d D435-shaped depth frames per GPU; %s" % (frames_per_gpu, wl["w"], wl["h"], wl["text"]),
+            "name": args.workload, "frames_per_gpu": frames_per_gpu, "image": [wl["w"], wl["h"]], "template_points": 7250,
+            "n_guess": wl["n_guess"],
+            "l2": "inputs (%.0f MB of depth per GPU per step) are larger than the 126 MB L2" % (frames_per_gpu * wl["w"] * wl["h"] * 2 / 1e6),
             "parallelism": "frames sharded per GPU, no data-path collective"}
 
 
@@ -165,7 +201,11 @@ def main():
     ap.add_argument("--chunk", type=int, default=1024, help="frames resident per chunk (max_batch)")
     ap.add_argument("--cpu-sample", type=int, default=64, help="frames of the CPU baseline sample")
     ap.add_argument("--no-cpu", action="store_true")
+    ap.add_argument("--workload", default="full", choices=sorted(WORKLOADS))
     args = ap.parse_args()
+    global W, H
+    wl = WORKLOADS[args.workload]
+    W, H = wl["w"], wl["h"]
 
     rank = int(os.environ.get("RANK", "0"))
     local_rank = int(os.environ.get("LOCAL_RANK", "0"))
@@ -189,10 +229,11 @@ def main():
         dist.init_process_group("nccl", device_id=torch.device("cuda", local_rank))
 
     F = args.frames
-    p = default_params("cuboid")
+    p = default_params(wl["variant"])
+    p.n_guess, p.guess_mode = wl["n_guess"], (1 if wl["n_guess"] > 1 else 0)
     tm = template()
     t_gen = time.perf_counter()
-    frames = make_frames(F, rank * F)                         # uint16 [F,480,640], unique seeds per rank
+    frames = make_frames(F, rank * F, wl["kind"])             # uint16 [F,h,w], unique seeds per rank
     t_gen = time.perf_counter() - t_gen
     host = torch.empty((F, H, W), dtype=torch.uint16, pin_memory=True)
     host.numpy()[...] = frames
@@ -200,6 +241,10 @@ def main():
 
     cc = api.CuboidCuda(p, device=local_rank, max_points=W * H, max_batch=min(args.chunk, F))
     cc.set_template(0, tm)
+    rots = guess_rotations() if wl["n_guess"] > 1 else None
+    if rots is not None:
+        cc.set_guesses(rots, mode=1)
+    stages = wl["stages"]
     peak_unfused, peak_ffma = cc.measure_fp32_peak()
 
     def barrier():
@@ -210,7 +255,7 @@ def main():
 
     # ---- device-resident: value + rooflines ----
     for _ in range(args.warmup):
-        cc.process_batch_device(dev.data_ptr(), W, H, F)
+        cc.process_batch_device(dev.data_ptr(), W, H, F, stages=stages)
     barrier()
     sampler = ClockSampler(local_rank)
     sampler.start()
@@ -218,7 +263,7 @@ def main():
     stage = {k: 0.0 for k in ("preprocess", "voxel", "plane", "cluster", "icp")}
     wall0 = time.perf_counter()
     for _ in range(args.steps):
-        cc.process_batch_device(dev.data_ptr(), W, H, F)
+        cc.process_batch_device(dev.data_ptr(), W, H, F, stages=stages)
         for k, v in cc.stage_ms().items():
             stage[k] += v
     barrier()
@@ -230,6 +275,7 @@ def main():
     work_eval, work_brute = cc.icp_work()                      # pairs evaluated / brute-force-equivalent pairs, last step
 
     # ---- end to end: pinned host depth in, host results out ----
+    cc.set_option(api.OPT_STAGES, stages)   # the host-buffer entry runs the same stage set
     for _ in range(min(args.warmup, 1)):
         cc.process_batch(host)
     barrier()
@@ -255,7 +301,8 @@ def main():
         peaks, peak_src = _measured_peaks()
         n_chunks = (F + cc.max_batch - 1) // cc.max_batch
         ops = icp_flops(res, len(tm))                      # brute-force equivalent: 8*S*T per nearest-neighbour pass
-        assert abs(ops - 8.0 * work_brute) <= 1e-6 * ops, (ops, work_brute)
+        if wl["n_guess"] > 1:
+            ops = 8.0 * work_brute                         # every hypothesis counts, not only the winner reported per cluster
         ops_exec = 8.0 * work_eval                         # what the culled kernel actually executed
         icp_s = stage["icp"] / 1e3 / args.steps
         achieved = ops_exec / icp_s / 1e12 if icp_s > 0 else 0.0
@@ -300,9 +347,10 @@ def main():
             from oracle import pyoracle as O
             op = O.params_from(p)
             ns = min(args.cpu_sample, F)
-            O.process_frame(op, frames[0], tm)
+            otm = tm if stages & 8 else None
+            O.process_frame(op, frames[0], otm, guesses=rots)
             c0 = time.perf_counter()
-            cpu_res = [O.process_frame(op, frames[i], tm) for i in range(ns)]
+            cpu_res = [O.process_frame(op, frames[i], otm, guesses=rots) for i in range(ns)]
             cdt = time.perf_counter() - c0
             same = all(cpu_res[i].cluster[0].corr_hash == res[i].cluster[0].corr_hash and cpu_res[i].inlier_hash == res[i].inlier_hash
                        for i in range(ns))

@@ -2,12 +2,14 @@
 //
 // A Euclidean cluster is a connected component of the graph {(i,j) : d2(i,j) < (float)(tol*tol)} with
 // d2 = ((dx*dx)+dy*dy)+dz*dz in float (FLANN L2_Simple, strict '<'), so the BFS order of the reference
-// does not matter. One CTA per frame: tiled brute-force pair test from shared memory + lock-free
-// union-find (larger root hooks under smaller root, so a component's root is its smallest member),
-// then the size filter, the canonical ordering (size descending, ties by smallest member) and a
-// stable scatter of the member indices (ascending inside each cluster).
+// does not matter. One CTA per frame: points are binned into a hashed uniform grid (cell = 1.001 * tol, so
+// two points closer than tol are always in the same or in adjacent cells), every point tests the candidates
+// of its 27 neighbour cells with the exact float distance, and edges feed a lock-free union-find (larger
+// root hooks under smaller root, so a component's root is its smallest member). Then the size filter, the
+// canonical ordering (size descending, ties by smallest member) and a stable scatter of the member indices
+// (ascending inside each cluster).
 //
-// Roofline: FP32/latency bound, ops = 8 * M^2/2 (d-bar = M/2 candidates per point examined); bytes = 20*M.
+// Roofline: latency bound; ops = 8 * M * d-bar with d-bar = candidates examined per point (27 cells); bytes = 20*M.
 #pragma once
 #include "common.cuh"
 
@@ -21,24 +23,28 @@ struct CluArgs {
     int* idx_sorted;        // [F][M]
     int* offsets;           // [F][KC+1]
     int* roots;             // [F][KC]
+    int* cell_start;        // [F][2*M+2] hashed grid: end of every bucket in cell_pts
+    float4* cell_pts;       // [F][M]     points grouped by bucket, .w = point index (bits)
     cuboid_frame_result* res;
     int P, M, KC;
     float r2;
+    float inv_cell;         // 1 / (1.001 * tol)
     int min_size, max_size, use_cluster;
 };
 
 constexpr int CLU_THREADS = 1024;
 
+__device__ __forceinline__ unsigned int cell_hash(int cx, int cy, int cz) {
+    return ((unsigned int)cx * 73856093u) ^ ((unsigned int)cy * 19349663u) ^ ((unsigned int)cz * 83492791u);
+}
+// find with full path compression: parent links only ever point to smaller indices (a root is hooked under a
+// smaller root), so there are no cycles and rewriting a node's parent to any ancestor is safe under races.
 __device__ __forceinline__ int uf_find(int* parent, int x) {
     volatile int* p = parent;
-    int px = p[x];
-    while (px != x) {
-        const int gp = p[px];
-        if (gp != px) p[x] = gp;   // path halving: only ever replaces a parent by an ancestor
-        x = px;
-        px = gp;
-    }
-    return x;
+    int r = x, q;
+    while ((q = p[r]) != r) r = q;
+    while ((q = p[x]) > r) { p[x] = r; x = q; }   // '>' not '!=': a racing thread may already have lifted x above r
+    return r;
 }
 __device__ __forceinline__ void uf_unite(int* parent, int a, int b) {
     while (true) {
@@ -50,16 +56,25 @@ __device__ __forceinline__ void uf_unite(int* parent, int a, int b) {
     }
 }
 
-__global__ void __launch_bounds__(CLU_THREADS) k_cluster(const CluArgs a) {
-    __shared__ float4 s_tile[CLU_THREADS];
+// MODE 0: n <= CLU_SMEM_ALL: union-find forest, bucket table and bucketed points all in shared memory
+// MODE 1: n <= CLU_SMEM_UF : forest in shared memory, grid in global memory
+// MODE 2: everything in global memory
+constexpr int CLU_SMEM_ALL = 4096;
+constexpr int CLU_SMEM_UF = 16384;
+template <int MODE>
+__device__ __forceinline__ void cluster_body(const CluArgs& a) {
     __shared__ int s_w[CLU_THREADS / 32 + 1];
     __shared__ int s_cur[1024];
+    __shared__ int s_off[CLU_THREADS / 32][32], s_beg[CLU_THREADS / 32][32];
     __shared__ unsigned long long s_h[CLU_THREADS / 32];
     const int f = blockIdx.x;
     cuboid_frame_result& R = a.res[f];
     const int n = R.n_remain;
     const float4* pts = a.remain + (size_t)f * a.P;
-    int* parent = a.parent + (size_t)f * a.M;
+    // union-find forest in shared memory when the frame's remainder fits (pointer chasing at smem latency), else in global.
+    // The two cases are separate instantiations so the compiler emits LDS/ATOMS, not generic accesses.
+    extern __shared__ __align__(16) int s_dyn[];
+    int* parent = MODE <= 1 ? s_dyn : a.parent + (size_t)f * a.M;
     int* csize = a.csize + (size_t)f * a.M;
     int* crank = a.crank + (size_t)f * a.M;
     int* idx_sorted = a.idx_sorted + (size_t)f * a.M;
@@ -88,27 +103,76 @@ __global__ void __launch_bounds__(CLU_THREADS) k_cluster(const CluArgs a) {
     for (int i = threadIdx.x; i < n; i += CLU_THREADS) { parent[i] = i; csize[i] = 0; crank[i] = -1; }
     __syncthreads();
 
-    // pair test: i-block ib against j-tiles jb >= ib
-    const int nb = (n + CLU_THREADS - 1) / CLU_THREADS;
-    for (int ib = 0; ib < nb; ++ib) {
-        const int i = ib * CLU_THREADS + threadIdx.x;
-        const bool iv = i < n;
-        const float4 pi = iv ? pts[i] : make_float4(0.f, 0.f, 0.f, 0.f);
-        for (int jb = ib; jb < nb; ++jb) {
-            const int jj = jb * CLU_THREADS + threadIdx.x;
+    // hashed uniform grid: table size = power of two >= 2n; points are counting-sorted by bucket so that the
+    // candidates of a cell are one contiguous run (independent, pipelined loads instead of a pointer chase)
+    // MODE 0 shared layout: parent[4096] | cpts float4[4096] | cend[hs+1 <= 4097]
+    float4* cpts = MODE == 0 ? reinterpret_cast<float4*>(s_dyn + CLU_SMEM_ALL) : a.cell_pts + (size_t)f * a.M;
+    int* cend = MODE == 0 ? s_dyn + CLU_SMEM_ALL + 4 * CLU_SMEM_ALL : a.cell_start + (size_t)f * (2 * a.M + 2);
+    int hs = 64;
+    while (hs < (MODE == 0 ? n : 2 * n)) hs <<= 1;
+    const unsigned int hmask = (unsigned int)hs - 1u;
+    for (int i = threadIdx.x; i <= hs; i += CLU_THREADS) cend[i] = 0;
+    __syncthreads();
+    const float inv_cell = a.inv_cell;
+    for (int i = threadIdx.x; i < n; i += CLU_THREADS) {
+        const float4 p = pts[i];
+        const int cx = (int)floorf(p.x * inv_cell), cy = (int)floorf(p.y * inv_cell), cz = (int)floorf(p.z * inv_cell);
+        atomicAdd(&cend[cell_hash(cx, cy, cz) & hmask], 1);
+    }
+    __syncthreads();
+    {   // exclusive scan of the hs bucket counts (running carry over 1024-wide slices): cend[b] = start of bucket b
+        int carry = 0;
+        for (int b0 = 0; b0 < hs; b0 += CLU_THREADS) {
+            const int b = b0 + threadIdx.x;
+            const int c = b < hs ? cend[b] : 0;
+            int total;
+            const int ex = carry + block_excl_scan<CLU_THREADS>(c, s_w, &total);
+            if (b < hs) cend[b] = ex;
+            carry += total;
             __syncthreads();
-            s_tile[threadIdx.x] = (jj < n) ? pts[jj] : make_float4(0.f, 0.f, 0.f, 0.f);
-            __syncthreads();
-            if (!iv) continue;
-            const int jn = min(CLU_THREADS, n - jb * CLU_THREADS);
-            const int j0 = (jb == ib) ? threadIdx.x + 1 : 0;
-            for (int j = j0; j < jn; ++j) {
-                const float4 pj = s_tile[j];
-                const float dx = pi.x - pj.x, dy = pi.y - pj.y, dz = pi.z - pj.z;
-                const float d2 = ((dx * dx) + dy * dy) + dz * dz;
-                if (d2 < a.r2) uf_unite(parent, i, jb * CLU_THREADS + j);
+        }
+    }
+    // scatter: the cursor of bucket b walks from its start to its end, so afterwards cend[b] = end of bucket b
+    // and bucket b occupies [b ? cend[b-1] : 0, cend[b])
+    for (int i = threadIdx.x; i < n; i += CLU_THREADS) {
+        const float4 p = pts[i];
+        const int cx = (int)floorf(p.x * inv_cell), cy = (int)floorf(p.y * inv_cell), cz = (int)floorf(p.z * inv_cell);
+        const int pos = atomicAdd(&cend[cell_hash(cx, cy, cz) & hmask], 1);
+        cpts[pos] = make_float4(p.x, p.y, p.z, __int_as_float(i));
+    }
+    __syncthreads();
+    // Pair test, one warp per query point: the (deduplicated) runs of its 27 neighbour buckets are flattened into
+    // one candidate sequence and the 32 lanes take consecutive candidates, so loads are contiguous and all lanes
+    // execute the same distance code. Edges feed the union-find; a pair already under one parent is skipped.
+    for (int i = wid; i < n; i += CLU_THREADS / 32) {
+        const float4 pi = pts[i];
+        const int cx = (int)floorf(pi.x * inv_cell), cy = (int)floorf(pi.y * inv_cell), cz = (int)floorf(pi.z * inv_cell);
+        int bstart = 0, blen = 0;
+        if (lane < 27) {
+            const unsigned int b = cell_hash(cx + (lane % 3) - 1, cy + ((lane / 3) % 3) - 1, cz + (lane / 9) - 1) & hmask;
+            const unsigned int same = __match_any_sync(0x07ffffffu, b);   // distinct neighbour cells can share a bucket
+            if (lane == __ffs(same) - 1) {
+                bstart = b ? cend[b - 1] : 0;
+                blen = cend[b] - bstart;
             }
         }
+        const int incl = warp_incl_scan(blen, lane);
+        const int total = __shfl_sync(FULL_MASK, incl, 31);
+        s_off[wid][lane] = incl - blen;     // exclusive offsets of the 32 (27 used) runs
+        s_beg[wid][lane] = bstart;
+        __syncwarp();
+        for (int t = lane; t < total; t += 32) {
+            int e = 0;                      // last run with offset <= t (runs of length 0 share offsets: take the last)
+#pragma unroll
+            for (int step = 16; step >= 1; step >>= 1)
+                if (e + step < 32 && s_off[wid][e + step] <= t) e += step;
+            const float4 pj = cpts[s_beg[wid][e] + (t - s_off[wid][e])];
+            const int j = __float_as_int(pj.w);
+            const float ddx = pi.x - pj.x, ddy = pi.y - pj.y, ddz = pi.z - pj.z;
+            const float d2 = ((ddx * ddx) + ddy * ddy) + ddz * ddz;
+            if (j < i && d2 < a.r2 && ((volatile int*)parent)[j] != ((volatile int*)parent)[i]) uf_unite(parent, i, j);
+        }
+        __syncwarp();
     }
     __syncthreads();
     for (int i = threadIdx.x; i < n; i += CLU_THREADS) {
@@ -116,7 +180,12 @@ __global__ void __launch_bounds__(CLU_THREADS) k_cluster(const CluArgs a) {
         parent[i] = r;
     }
     __syncthreads();
-    for (int i = threadIdx.x; i < n; i += CLU_THREADS) atomicAdd(&csize[parent[i]], 1);
+    for (int i0 = 0; i0 < n; i0 += CLU_THREADS) {   // warp-aggregated: one atomic per distinct root per warp
+        const int i = i0 + threadIdx.x;
+        const int r = i < n ? parent[i] : -1;
+        const unsigned int peers = __match_any_sync(FULL_MASK, r);
+        if (r >= 0 && lane == __ffs(peers) - 1) atomicAdd(&csize[r], __popc(peers));
+    }
     __syncthreads();
 
     // kept roots, ascending (ordered compaction)
@@ -175,5 +244,13 @@ __global__ void __launch_bounds__(CLU_THREADS) k_cluster(const CluArgs a) {
         }
     }
 }
+
+__global__ void __launch_bounds__(CLU_THREADS) k_cluster(const CluArgs a) {
+    const int n = a.res[blockIdx.x].n_remain;
+    if (n <= CLU_SMEM_ALL) cluster_body<0>(a);
+    else if (n <= CLU_SMEM_UF) cluster_body<1>(a);
+    else cluster_body<2>(a);
+}
+constexpr size_t CLU_DYN_SMEM = (size_t)CLU_SMEM_ALL * 4 + (size_t)CLU_SMEM_ALL * 16 + (size_t)(CLU_SMEM_ALL + 4) * 4;   // 98 320 B >= 16384*4
 
 }  // namespace cuboid

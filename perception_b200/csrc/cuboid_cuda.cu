@@ -53,7 +53,7 @@ struct cuboid_handle {
     int* d_vcount = nullptr;
     int *d_shuffled = nullptr, *d_inl_pre = nullptr, *d_inl = nullptr;
     float4* d_remain = nullptr;
-    int *d_parent = nullptr, *d_csize = nullptr, *d_crank = nullptr, *d_idx_sorted = nullptr, *d_offsets = nullptr, *d_roots = nullptr;
+    int *d_parent = nullptr, *d_csize = nullptr, *d_crank = nullptr, *d_idx_sorted = nullptr, *d_offsets = nullptr, *d_roots = nullptr, *d_cell_head = nullptr; float4* d_cell_pts = nullptr;
     float4* d_cur = nullptr; int* d_corr = nullptr; float* d_cd = nullptr; int* d_order = nullptr; IcpOut* d_icp_out = nullptr;
     size_t icp_scratch_elems = 0; size_t icp_out_elems = 0;
     FrameScratch* d_scr = nullptr;
@@ -66,6 +66,7 @@ struct cuboid_handle {
     uint4* d_boxes[CUBOID_MAX_TEMPLATES] = {}; int tmpl_nleaf[CUBOID_MAX_TEMPLATES] = {}; int tmpl_nnodes[CUBOID_MAX_TEMPLATES] = {};
     unsigned long long* d_work = nullptr; unsigned long long work_total[2] = {0, 0};
     int icp_cull = 1;
+    int stage_mask = 15;
     float* d_guesses = nullptr; int n_guess = 1; int guess_mode = 0; bool have_guesses = false;
     int* d_trace_corr = nullptr; float* d_trace_T = nullptr; float4* d_aligned = nullptr;
     int smem_optin = 0; int icp_smem_budget = 0;
@@ -244,10 +245,11 @@ int run_chunk(cuboid_handle* h, const ChunkIn& in, int nf, cuboid_frame_result* 
     if ((stages & 4) && !skip_cluster) {
         CluArgs c{};
         c.remain = b_remain; c.parent = b_parent; c.csize = b_csize; c.crank = b_crank; c.idx_sorted = b_idx_sorted;
-        c.offsets = b_offsets; c.roots = b_roots; c.res = d_res; c.P = h->P; c.M = h->M; c.KC = h->KC;
-        c.r2 = (float)(p.cluster_tol * p.cluster_tol); c.min_size = p.cluster_min; c.max_size = p.cluster_max;
+        c.offsets = b_offsets; c.roots = b_roots; c.cell_start = h->d_cell_head + (size_t)f0 * (2 * h->M + 2); c.cell_pts = h->d_cell_pts + oM; c.res = d_res; c.P = h->P; c.M = h->M; c.KC = h->KC;
+        c.r2 = (float)(p.cluster_tol * p.cluster_tol);
+        c.inv_cell = (float)(1.0 / (1.001 * (p.cluster_tol > 0 ? p.cluster_tol : 1.0))); c.min_size = p.cluster_min; c.max_size = p.cluster_max;
         c.use_cluster = force_cluster ? 1 : p.use_cluster;
-        k_cluster<<<nf, CLU_THREADS, 0, st>>>(c);
+        k_cluster<<<nf, CLU_THREADS, CLU_DYN_SMEM, st>>>(c);
         ++h->launches;
         CK(h, cudaGetLastError());
     }
@@ -396,6 +398,8 @@ int cuboid_create(cuboid_handle** out, const cuboid_params* p, int device, int m
     CA(dalloc(h, &h->d_idx_sorted, BM));
     CA(dalloc(h, &h->d_offsets, (size_t)h->B * (h->KC + 1)));
     CA(dalloc(h, &h->d_roots, (size_t)h->B * h->KC));
+    CA(dalloc(h, &h->d_cell_head, (size_t)h->B * (2 * h->M + 2)));
+    CA(dalloc(h, &h->d_cell_pts, BM));
     CA(dalloc(h, &h->d_scr, (size_t)h->B));
     CA(dalloc(h, &h->d_desc1, (size_t)h->B * h->tilesP));
     CA(dalloc(h, &h->d_desc2, (size_t)h->B * h->tilesV));
@@ -410,6 +414,7 @@ int cuboid_create(cuboid_handle** out, const cuboid_params* p, int device, int m
     if (cudaMemset(h->d_work, 0, 16) != cudaSuccess) return fail(CUBOID_E_CUDA);
     { const char* ec = std::getenv("CUBOID_ICP_CULL"); if (ec) h->icp_cull = atoi(ec) ? 1 : 0; }
     if (cudaFuncSetAttribute(k_sac_plane, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)sizeof(SacShared)) != cudaSuccess) return fail(CUBOID_E_CUDA);
+    if (cudaFuncSetAttribute(k_cluster, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)CLU_DYN_SMEM) != cudaSuccess) return fail(CUBOID_E_CUDA);
 #undef CA
     *out = h;
     return CUBOID_OK;
@@ -420,7 +425,7 @@ int cuboid_destroy(cuboid_handle* h) {
     cudaSetDevice(h->device);
     if (h->stream) cudaStreamSynchronize(h->stream);
     void* ptrs[] = {h->d_depth, h->d_blob, h->d_n_in, h->d_pts, h->d_keysA, h->d_keysB, h->d_kpp, h->d_hist, h->d_vox, h->d_vcount, h->d_shuffled,
-                    h->d_inl_pre, h->d_inl, h->d_remain, h->d_parent, h->d_csize, h->d_crank, h->d_idx_sorted, h->d_offsets, h->d_roots,
+                    h->d_inl_pre, h->d_inl, h->d_remain, h->d_parent, h->d_csize, h->d_crank, h->d_idx_sorted, h->d_offsets, h->d_roots, h->d_cell_head, h->d_cell_pts,
                     h->d_cur, h->d_corr, h->d_cd, h->d_order, h->d_icp_out, h->d_scr, h->d_desc1, h->d_desc2, h->d_ticket, h->d_res, h->d_rng,
                     h->d_triplets, h->d_guesses, h->d_trace_corr, h->d_trace_T, h->d_aligned, h->d_work};
     for (void* q : ptrs) if (q) cudaFree(q);
@@ -734,7 +739,7 @@ int cuboid_process_cloud(cuboid_handle* h, const void* pts, int point_step, int 
     ChunkIn in;
     in.blob = h->d_blob; in.point_step = point_step; in.xoff = xoff; in.yoff = yoff; in.zoff = zoff; in.in_stride = h->P;
     const bool have_t = tmpl_slot >= 0 && tmpl_slot < CUBOID_MAX_TEMPLATES && h->d_tmpl[tmpl_slot];
-    CKS(h, run_chunk(h, in, 1, h->d_res, have_t ? 15 : 7, tmpl_slot));
+    CKS(h, run_chunk(h, in, 1, h->d_res, (have_t ? 15 : 7) & h->stage_mask, tmpl_slot));
     CK(h, cudaMemcpyAsync(result, h->d_res, sizeof(cuboid_frame_result), cudaMemcpyDeviceToHost, h->stream));
     CK(h, cudaStreamSynchronize(h->stream));
     h->last_chunk_base = 0; h->last_chunk_frames = 1; h->last_total_frames = 1;
@@ -811,7 +816,7 @@ static int process_frames(cuboid_handle* h, const uint16_t* depth, bool on_devic
 int cuboid_process_batch(cuboid_handle* h, const uint16_t* depth, int w, int hgt, int n_frames, int tmpl_slot, cuboid_frame_result* results) {
     if (!results) return CUBOID_E_INVALID;
     const bool have_t = h && tmpl_slot >= 0 && tmpl_slot < CUBOID_MAX_TEMPLATES && h->d_tmpl[tmpl_slot];
-    CKS(h, process_frames(h, depth, false, w, hgt, n_frames, tmpl_slot, have_t ? 15 : 7));
+    CKS(h, process_frames(h, depth, false, w, hgt, n_frames, tmpl_slot, (have_t ? 15 : 7) & h->stage_mask));
     CK(h, cudaMemcpyAsync(results, h->d_res, sizeof(cuboid_frame_result) * n_frames, cudaMemcpyDeviceToHost, h->stream));
     CK(h, cudaStreamSynchronize(h->stream));
     return CUBOID_OK;
@@ -965,6 +970,10 @@ int cuboid_set_option(cuboid_handle* h, int option, int value) {
     switch (option) {
         case CUBOID_OPT_ICP_CULL: h->icp_cull = value ? 1 : 0; return CUBOID_OK;
         case CUBOID_OPT_TAPS: h->taps = value ? 1 : 0; return CUBOID_OK;
+        case CUBOID_OPT_STAGES:
+            if (value < 1 || value > 15) return CUBOID_E_INVALID;
+            h->stage_mask = (value & 8) ? 15 : (value & 4) ? 7 : (value & 2) ? 3 : 1;
+            return CUBOID_OK;
         default: return CUBOID_E_INVALID;
     }
 }

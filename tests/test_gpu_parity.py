@@ -333,6 +333,33 @@ def test_object_detection_variant_small_leaf(tmpl30):
     _same_frame(res[0], O.process_frame(p, depth[0], tmpl30))
 
 
+def test_hd720_small_leaf_stress_frame(tmpl30):
+    """BASELINE configs[4]: 1280x720, 2 mm leaf: ~870k points, ~620k voxels, 29-bit keys (4 radix passes)."""
+    p = default_params("hd720")
+    p.icp_max_iter = 12
+    depth = synth.depth_batch("hd720", [0])
+    with api.CuboidCuda(p, max_points=1280 * 720, max_batch=1) as h:
+        h.set_template(0, tmpl30)
+        res = h.process_batch(depth)
+    ref = O.process_frame(p, depth[0], tmpl30)
+    assert ref.n_points > 800000 and ref.n_voxels > 500000
+    _same_frame(res[0], ref)
+
+
+def test_stage_mask_segmentation_only(cc, params, tmpl30):
+    depth = synth.depth_batch("plane_var", [5, 6])
+    cc.set_option(api.OPT_STAGES, 3)
+    try:
+        res = cc.process_batch(depth)
+    finally:
+        cc.set_option(api.OPT_STAGES, 15)
+    for i in range(2):
+        ref = O.process_frame(params, depth[i], None)
+        for k in ("n_points", "n_voxels", "n_inliers", "n_remain", "voxel_key_hash", "voxel_hash", "inlier_hash", "remain_hash"):
+            assert getattr(res[i], k) == getattr(ref, k), k
+        assert res[i].n_clusters == 0
+
+
 def test_full_size_batch_properties(cc, tmpl30, params):
     """BASELINE-sized work: a 64-frame batch in 8-frame chunks must equal the same frames run one by one
     (determinism, chunk independence) and a sample must equal the oracle."""

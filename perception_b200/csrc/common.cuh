@@ -141,6 +141,38 @@ __device__ __forceinline__ int lookback_exclusive(unsigned long long* desc, int 
     return excl;
 }
 
+// Warp-parallel variant: called by all 32 lanes of ONE warp; each step inspects 32 predecessors at once, so a tile
+// that starts while none of its predecessors has an inclusive prefix yet needs tile/32 round trips instead of `tile`.
+__device__ __forceinline__ int lookback_exclusive_warp(unsigned long long* desc, int tile, int aggregate) {
+    volatile unsigned long long* d = desc;
+    const int lane = threadIdx.x & 31;
+    if (tile == 0) {
+        if (lane == 0) d[0] = (2ull << 62) | (unsigned int)aggregate;
+        return 0;
+    }
+    if (lane == 0) d[tile] = (1ull << 62) | (unsigned int)aggregate;
+    int excl = 0;
+    int j = tile - 1;
+    while (true) {
+        const int idx = j - lane;
+        const unsigned long long v = idx >= 0 ? d[idx] : (2ull << 62);   // virtual tile -1: inclusive prefix 0
+        const unsigned int st = (unsigned int)(v >> 62);
+        const unsigned int incl = __ballot_sync(FULL_MASK, st == 2);
+        const unsigned int notready = __ballot_sync(FULL_MASK, st == 0);
+        const int first = incl ? (__ffs(incl) - 1) : 31;
+        const unsigned int upto = first == 31 ? 0xffffffffu : ((2u << first) - 1u);
+        if (notready & upto) continue;   // somebody in the window has not published yet: look again
+        int val = lane <= first ? (int)(unsigned int)v : 0;
+#pragma unroll
+        for (int o = 16; o >= 1; o >>= 1) val += __shfl_xor_sync(FULL_MASK, val, o);
+        excl += val;
+        if (incl) break;
+        j -= 32;
+    }
+    if (lane == 0) d[tile] = (2ull << 62) | (unsigned int)(excl + aggregate);
+    return excl;
+}
+
 // VoxelGrid geometry of one frame, recomputed by whoever needs it from the encoded min/max
 // (pcl::VoxelGrid<PCLPointCloud2>::applyFilter: min_b_, div_b_, divb_mul_  — SURVEY.md A.2)
 struct VoxelGeom {

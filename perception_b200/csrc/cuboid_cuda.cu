@@ -45,6 +45,7 @@ struct cuboid_handle {
     uint16_t* d_depth = nullptr;
     unsigned char* d_blob = nullptr; size_t blob_cap = 0;
     int* d_n_in = nullptr;
+    float* d_xr = nullptr; float* d_yr = nullptr; int ray_w = 0, ray_h = 0; float ray_k[4] = {0, 0, 0, 0};   // unprojection tables
     float4* d_pts = nullptr;
     unsigned long long *d_keysA = nullptr, *d_keysB = nullptr;
     int* d_kpp = nullptr;
@@ -156,6 +157,24 @@ int ensure_results(cuboid_handle* h, int n) {
     return CUBOID_OK;
 }
 
+// ((float)u - cx) / fx and ((float)v - cy) / fy with IEEE float ops on the host: the same bits the kernel would compute
+int ensure_ray_tables(cuboid_handle* h, int w, int hgt) {
+    const cuboid_params& p = h->p;
+    if (h->d_xr && h->ray_w == w && h->ray_h == hgt && h->ray_k[0] == p.fx && h->ray_k[1] == p.fy && h->ray_k[2] == p.cx && h->ray_k[3] == p.cy)
+        return CUBOID_OK;
+    if (h->d_xr) { cudaFree(h->d_xr); cudaFree(h->d_yr); h->d_xr = nullptr; h->d_yr = nullptr; }
+    std::vector<float> xr(w), yr(hgt);
+    for (int u = 0; u < w; ++u) { volatile float t = (float)u - p.cx; xr[u] = t / p.fx; }
+    for (int v = 0; v < hgt; ++v) { volatile float t = (float)v - p.cy; yr[v] = t / p.fy; }
+    CKS(h, dalloc(h, &h->d_xr, (size_t)w));
+    CKS(h, dalloc(h, &h->d_yr, (size_t)hgt));
+    CK(h, cudaMemcpyAsync(h->d_xr, xr.data(), sizeof(float) * w, cudaMemcpyHostToDevice, h->stream));
+    CK(h, cudaMemcpyAsync(h->d_yr, yr.data(), sizeof(float) * hgt, cudaMemcpyHostToDevice, h->stream));
+    CK(h, cudaStreamSynchronize(h->stream));
+    h->ray_w = w; h->ray_h = hgt; h->ray_k[0] = p.fx; h->ray_k[1] = p.fy; h->ray_k[2] = p.cx; h->ray_k[3] = p.cy;
+    return CUBOID_OK;
+}
+
 struct ChunkIn {
     const uint16_t* depth = nullptr;   // device, [nf][w*h]
     int w = 0, hgt = 0;
@@ -188,22 +207,21 @@ int run_chunk(cuboid_handle* h, const ChunkIn& in, int nf, cuboid_frame_result* 
         ++h->launches;
         const int per = in.in_stride;
         const int tiles = (per + PRE_TILE - 1) / PRE_TILE;
-        CK(h, cudaMemsetAsync(b_desc1, 0, sizeof(unsigned long long) * (size_t)nf * h->tilesP, st));
-        CK(h, cudaMemsetAsync(h->d_ticket, 0, sizeof(unsigned int) * 4, st));
         PreArgs a{};
         a.depth = in.depth; a.blob = in.blob; a.point_step = in.point_step; a.xoff = in.xoff; a.yoff = in.yoff; a.zoff = in.zoff;
         a.n_in = in.blob ? h->d_n_in + f0 : nullptr;
         a.w = in.w; a.h = in.hgt; a.P = per;
         a.fx = p.fx; a.fy = p.fy; a.cx = p.cx; a.cy = p.cy; a.depth_scale = p.depth_scale;
+        if (!in.blob) { CKS(h, ensure_ray_tables(h, in.w, in.hgt)); a.xr = h->d_xr; a.yr = h->d_yr; }
         a.z_lo = limit_lo(p.pass_z_min); a.z_hi = limit_hi(p.pass_z_max);
         a.x_lo = limit_lo(p.pass_x_min); a.x_hi = limit_hi(p.pass_x_max);
-        a.pts = b_pts; a.res = d_res; a.scr = b_scr; a.desc = b_desc1; a.ticket = h->d_ticket;
+        a.pts = b_pts; a.res = d_res; a.scr = b_scr; a.tile_count = reinterpret_cast<int*>(b_desc1);
         a.tiles = tiles; a.n_frames = nf;
         a.Pout = h->P;
         if (tiles > h->tilesP) return CUBOID_E_CAPACITY;
-        if (in.blob) k_preprocess<1><<<nf * tiles, PRE_THREADS, 0, st>>>(a);
-        else k_preprocess<0><<<nf * tiles, PRE_THREADS, 0, st>>>(a);
-        ++h->launches;
+        if (in.blob) { k_pre_count<1><<<dim3(tiles, nf), PRE_THREADS, 0, st>>>(a); k_preprocess<1><<<dim3(tiles, nf), PRE_THREADS, 0, st>>>(a); }
+        else { k_pre_count<0><<<dim3(tiles, nf), PRE_THREADS, 0, st>>>(a); k_preprocess<0><<<dim3(tiles, nf), PRE_THREADS, 0, st>>>(a); }
+        h->launches += 2;
         CK(h, cudaGetLastError());
     }
     CK(h, cudaEventRecord(evs[1], st));
@@ -211,9 +229,10 @@ int run_chunk(cuboid_handle* h, const ChunkIn& in, int nf, cuboid_frame_result* 
         VoxArgs v{};
         v.pts = b_pts; v.keysA = b_keysA; v.keysB = b_keysB; v.kpp = h->taps ? b_kpp : nullptr; v.hist = b_hist;
         v.vox = b_vox; v.vcount = h->taps ? b_vcount : nullptr; v.res = d_res; v.scr = b_scr; v.desc = b_desc2;
-        v.ticket = h->d_ticket + 1; v.P = h->P; v.tilesP = h->tilesP; v.tilesV = h->tilesV; v.n_frames = nf;
+        v.ticket = h->d_ticket + h->B + f0; v.P = h->P; v.tilesP = h->tilesP; v.tilesV = h->tilesV; v.n_frames = nf;
         v.inv_leaf = 1.0f / p.leaf;
         CK(h, cudaMemsetAsync(b_desc2, 0, sizeof(unsigned long long) * (size_t)nf * h->tilesV, st));
+        CK(h, cudaMemsetAsync(h->d_ticket + h->B + f0, 0, sizeof(unsigned int) * nf, st));
         k_voxel_empty<<<(nf + 127) / 128, 128, 0, st>>>(v);
         k_voxel_keys<<<dim3((h->P + 255) / 256, nf), 256, 0, st>>>(v);
         h->launches += 2;
@@ -403,7 +422,7 @@ int cuboid_create(cuboid_handle** out, const cuboid_params* p, int device, int m
     CA(dalloc(h, &h->d_scr, (size_t)h->B));
     CA(dalloc(h, &h->d_desc1, (size_t)h->B * h->tilesP));
     CA(dalloc(h, &h->d_desc2, (size_t)h->B * h->tilesV));
-    CA(dalloc(h, &h->d_ticket, (size_t)4));
+    CA(dalloc(h, &h->d_ticket, 2 * (size_t)h->B));   // per-frame tile tickets of k_preprocess and k_voxel_reduce
     CA(ensure_results(h, h->B));
     CA(upload_rng(h));
     CA(ensure_icp_scratch(h, h->B, std::max(1, (int)p->n_guess)));
@@ -424,7 +443,7 @@ int cuboid_destroy(cuboid_handle* h) {
     if (!h) return CUBOID_E_INVALID;
     cudaSetDevice(h->device);
     if (h->stream) cudaStreamSynchronize(h->stream);
-    void* ptrs[] = {h->d_depth, h->d_blob, h->d_n_in, h->d_pts, h->d_keysA, h->d_keysB, h->d_kpp, h->d_hist, h->d_vox, h->d_vcount, h->d_shuffled,
+    void* ptrs[] = {h->d_depth, h->d_blob, h->d_n_in, h->d_xr, h->d_yr, h->d_pts, h->d_keysA, h->d_keysB, h->d_kpp, h->d_hist, h->d_vox, h->d_vcount, h->d_shuffled,
                     h->d_inl_pre, h->d_inl, h->d_remain, h->d_parent, h->d_csize, h->d_crank, h->d_idx_sorted, h->d_offsets, h->d_roots, h->d_cell_head, h->d_cell_pts,
                     h->d_cur, h->d_corr, h->d_cd, h->d_order, h->d_icp_out, h->d_scr, h->d_desc1, h->d_desc2, h->d_ticket, h->d_res, h->d_rng,
                     h->d_triplets, h->d_guesses, h->d_trace_corr, h->d_trace_T, h->d_aligned, h->d_work};

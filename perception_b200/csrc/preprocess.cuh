@@ -21,12 +21,13 @@ struct PreArgs {
     int P;                       // inputs per frame (input stride)
     int Pout;                    // output stride of pts (the handle's max_points)
     float fx, fy, cx, cy, depth_scale;
+    const float* xr;             // [w] ((float)u - cx) / fx, precomputed with the same float ops (SRC 0)
+    const float* yr;             // [h] ((float)v - cy) / fy
     float z_lo, z_hi, x_lo, x_hi; // float-exact equivalents of the double limits (see host: limit_lo/limit_hi)
     float4* pts;                 // [F][P]
     cuboid_frame_result* res;    // [F]
     FrameScratch* scr;           // [F]
-    unsigned long long* desc;    // [F][tiles] look-back descriptors (zeroed)
-    unsigned int* ticket;        // zeroed
+    int* tile_count;             // [F][tiles] survivors per tile (written by k_pre_count)
     int tiles;                   // tiles per frame
     int n_frames;
 };
@@ -44,24 +45,10 @@ __device__ __forceinline__ bool pass_keep(const PreArgs& a, float x, float y, fl
     return true;
 }
 
+// the 8 inputs of one thread -> points and keep mask (shared by the counting and the writing kernel)
 template <int SRC>
-__global__ void __launch_bounds__(PRE_THREADS) k_preprocess(const PreArgs a) {
-    __shared__ float4 s_pts[PRE_TILE];
-    __shared__ int s_w[9];
-    __shared__ int s_tile, s_base;
-    __shared__ unsigned long long s_hash[8];
-    __shared__ float s_mm[8][6];
-
-    if (threadIdx.x == 0) s_tile = (int)atomicAdd(a.ticket, 1u);
-    __syncthreads();
-    const int lin = s_tile;
-    const int f = lin / a.tiles, t = lin - f * a.tiles;
-    if (f >= a.n_frames) return;
-    const int n_in = (SRC == 1 && a.n_in) ? a.n_in[f] : a.P;
-    const int base = t * PRE_TILE;
-    const int first = base + threadIdx.x * PRE_ITEMS;
-
-    float px[PRE_ITEMS], py[PRE_ITEMS], pz[PRE_ITEMS];
+__device__ __forceinline__ unsigned int pre_points(const PreArgs& a, int f, int first, int n_in, float (&px)[PRE_ITEMS], float (&py)[PRE_ITEMS],
+                                                   float (&pz)[PRE_ITEMS]) {
     unsigned int keep = 0;
     if (SRC == 0) {
         const uint16_t* d = a.depth + (size_t)f * a.P;
@@ -75,15 +62,18 @@ __global__ void __launch_bounds__(PRE_THREADS) k_preprocess(const PreArgs a) {
             for (int k = 0; k < PRE_ITEMS; ++k) dv[k] = (first + k < n_in) ? d[first + k] : 0;
         }
         int v = first / a.w, u = first - v * a.w;
+        float yrv = a.yr[min(v, a.h - 1)];
 #pragma unroll
         for (int k = 0; k < PRE_ITEMS; ++k) {
-            // z = d*scale; x = z*((u-cx)/fx); y = z*((v-cy)/fy), all float, no contraction
+            // z = d*scale; x = z*((u-cx)/fx); y = z*((v-cy)/fy), all float, no contraction;
+            // the two quotients come from tables filled with exactly these float operations
             const float z = (float)dv[k] * a.depth_scale;
-            px[k] = z * (((float)u - a.cx) / a.fx);
-            py[k] = z * (((float)v - a.cy) / a.fy);
+            px[k] = z * a.xr[u];
+            py[k] = z * yrv;
             pz[k] = z;
-            if (first + k < n_in && pass_keep(a, px[k], py[k], pz[k])) keep |= 1u << k;
-            if (++u == a.w) { u = 0; ++v; }
+            // depth-derived points are always finite: only the range tests remain
+            if (first + k < n_in && !(z > a.z_hi || z < a.z_lo) && !(px[k] > a.x_hi || px[k] < a.x_lo)) keep |= 1u << k;
+            if (++u == a.w) { u = 0; ++v; yrv = a.yr[min(v, a.h - 1)]; }
         }
     } else {
         const unsigned char* b = a.blob + (size_t)f * a.P * a.point_step;
@@ -101,13 +91,57 @@ __global__ void __launch_bounds__(PRE_THREADS) k_preprocess(const PreArgs a) {
             }
         }
     }
+    return keep;
+}
+
+// pass 1: survivors per tile. A tile's output offset is then a plain sum over the preceding tile counts of its
+// frame (no decoupled look-back, no spinning): depth is read twice (2 B/pixel), which is cheap next to the 16 B/point writes.
+template <int SRC>
+__global__ void __launch_bounds__(PRE_THREADS) k_pre_count(const PreArgs a) {
+    const int f = blockIdx.y, t = blockIdx.x;
+    const int n_in = (SRC == 1 && a.n_in) ? a.n_in[f] : a.P;
+    const int first = t * PRE_TILE + threadIdx.x * PRE_ITEMS;
+    float px[PRE_ITEMS], py[PRE_ITEMS], pz[PRE_ITEMS];
+    const unsigned int keep = pre_points<SRC>(a, f, first, n_in, px, py, pz);
+    int c = __popc(keep);
+#pragma unroll
+    for (int o = 16; o >= 1; o >>= 1) c += __shfl_xor_sync(FULL_MASK, c, o);
+    __shared__ int s_c[8];
+    if ((threadIdx.x & 31) == 0) s_c[threadIdx.x >> 5] = c;
+    __syncthreads();
+    if (threadIdx.x == 0) {
+        int tot = 0;
+        for (int k = 0; k < 8; ++k) tot += s_c[k];
+        a.tile_count[(size_t)f * a.tiles + t] = tot;
+    }
+}
+
+template <int SRC>
+__global__ void __launch_bounds__(PRE_THREADS) k_preprocess(const PreArgs a) {
+    __shared__ float4 s_pts[PRE_TILE];
+    __shared__ int s_w[9];
+    __shared__ int s_base;
+    __shared__ unsigned long long s_hash[8];
+    __shared__ float s_mm[8][6];
+
+    const int f = blockIdx.y, t = blockIdx.x;
+    const int n_in = (SRC == 1 && a.n_in) ? a.n_in[f] : a.P;
+    const int first = t * PRE_TILE + threadIdx.x * PRE_ITEMS;
+    if (threadIdx.x < 32) {   // output offset of this tile = sum of the counts of the tiles before it
+        int b = 0;
+        for (int k = threadIdx.x; k < t; k += 32) b += a.tile_count[(size_t)f * a.tiles + k];
+#pragma unroll
+        for (int o = 16; o >= 1; o >>= 1) b += __shfl_xor_sync(FULL_MASK, b, o);
+        if (threadIdx.x == 0) s_base = b;
+    }
+    float px[PRE_ITEMS], py[PRE_ITEMS], pz[PRE_ITEMS];
+    const unsigned int keep = pre_points<SRC>(a, f, first, n_in, px, py, pz);
     const int cnt = __popc(keep);
     int total;
     int pos = block_excl_scan256(cnt, s_w, &total);
 #pragma unroll
     for (int k = 0; k < PRE_ITEMS; ++k)
         if (keep & (1u << k)) s_pts[pos++] = make_float4(px[k], py[k], pz[k], 1.0f);
-    if (threadIdx.x == 0) s_base = lookback_exclusive(a.desc + (size_t)f * a.tiles, t, total);
     __syncthreads();
     const int gbase = s_base;
 

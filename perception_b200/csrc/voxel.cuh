@@ -24,7 +24,7 @@ struct VoxArgs {
     cuboid_frame_result* res;
     FrameScratch* scr;
     unsigned long long* desc;     // [F][tilesV] look-back descriptors (zeroed)
-    unsigned int* ticket;         // zeroed
+    unsigned int* ticket;         // [F] zeroed
     int P, tilesP, tilesV, n_frames;
     float inv_leaf;
 };
@@ -177,11 +177,11 @@ __global__ void __launch_bounds__(VR_THREADS) k_voxel_reduce(const VoxArgs a) {
     __shared__ float s_open[3];
     __shared__ int s_open_cnt, s_open_pos, s_open_flag;
     __shared__ unsigned int s_open_key;
-    if (threadIdx.x == 0) { s_tile = (int)atomicAdd(a.ticket, 1u); s_open_flag = 0; }
-    __syncthreads();
-    const int lin = s_tile;
-    const int f = lin / a.tilesV, t = lin - f * a.tilesV;
+    const int f = blockIdx.x / a.tilesV;   // per-frame ticket, see k_preprocess
     if (f >= a.n_frames) return;
+    if (threadIdx.x == 0) { s_tile = (int)atomicAdd(a.ticket + f, 1u); s_open_flag = 0; }
+    __syncthreads();
+    const int t = s_tile;
     const int N = a.res[f].n_points;
     const int ntile = (N + VR_TILE - 1) / VR_TILE;
     if (t >= ntile) return;   // tiles past the data are never looked at by live tiles (they only look back)
@@ -211,7 +211,10 @@ __global__ void __launch_bounds__(VR_THREADS) k_voxel_reduce(const VoxArgs a) {
     }
     int total;
     int pos = block_excl_scan256(__popc(heads), s_w, &total);
-    if (threadIdx.x == 0) s_base = lookback_exclusive(a.desc + (size_t)f * a.tilesV, t, total);
+    if (threadIdx.x < 32) {
+        const int ex = lookback_exclusive_warp(a.desc + (size_t)f * a.tilesV, t, total);
+        if (threadIdx.x == 0) s_base = ex;
+    }
     __syncthreads();
     pos += s_base;
     float4* vox = a.vox + (size_t)f * a.P;

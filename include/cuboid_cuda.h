@@ -192,8 +192,10 @@ int cuboid_stage_ms(cuboid_handle* h, float ms_out[5]);
 /* options: CUBOID_OPT_ICP_CULL (default 1; 0 = plain brute force over every template chunk, same results),
  *          CUBOID_OPT_TAPS (default 1; 0 = do not keep the per-point voxel key / per-voxel count arrays),
  *          CUBOID_OPT_STAGES (default 15; stage bits cuboid_process_batch / cuboid_process_cloud run, as in
- *          cuboid_process_batch_device: e.g. 3 = ground-plane segmentation only) */
-enum { CUBOID_OPT_ICP_CULL = 1, CUBOID_OPT_TAPS = 2, CUBOID_OPT_STAGES = 3 };
+ *          cuboid_process_batch_device: e.g. 3 = ground-plane segmentation only),
+ *          CUBOID_OPT_FRONTEND (default 1: stages 1a+1b run as ONE kernel, one thread-block cluster per frame;
+ *          0 = the unfused kernels, kept as the byte-for-byte cross-check of the fused one) */
+enum { CUBOID_OPT_ICP_CULL = 1, CUBOID_OPT_TAPS = 2, CUBOID_OPT_STAGES = 3, CUBOID_OPT_FRONTEND = 4 };
 int cuboid_set_option(cuboid_handle* h, int option, int value);
 /* last batch: out[0] = source-template pairs the ICP kernel actually evaluated, out[1] = pairs of the
  * brute-force equivalent (S*T per nearest-neighbour pass). Roofline accounting for the culled kernel. */

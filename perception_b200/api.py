@@ -36,7 +36,7 @@ ABI_SYMBOLS = [
     "cuboid_abi_version", "cuboid_params_size", "cuboid_frame_result_size", "cuboid_launch_count",
     "cuboid_stage_ms", "cuboid_measure_fp32_peak", "cuboid_set_option", "cuboid_icp_work",
 ]
-OPT_ICP_CULL, OPT_TAPS, OPT_STAGES = 1, 2, 3
+OPT_ICP_CULL, OPT_TAPS, OPT_STAGES, OPT_FRONTEND = 1, 2, 3, 4
 
 
 class CuboidError(RuntimeError):

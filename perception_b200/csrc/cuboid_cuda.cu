@@ -24,6 +24,7 @@
 #include "cluster.cuh"
 #include "common.cuh"
 #include "cuboid_cuda.h"
+#include "frontend.cuh"
 #include "icp.cuh"
 #include "preprocess.cuh"
 #include "ransac.cuh"
@@ -73,6 +74,8 @@ struct cuboid_handle {
     int smem_optin = 0; int icp_smem_budget = 0;
     int last_chunk_base = 0, last_chunk_frames = 0, last_total_frames = 0;
     int taps = 1;
+    // fused front end (frontend.cuh): one thread-block cluster per frame, persistent over the chunk
+    int frontend = 1; int fe_cluster = 1; int fe_threads = 512; int fe_slots = 0; unsigned long long* d_fe_keys = nullptr;
     int64_t launches = 0;
     float stage_ms[5] = {0, 0, 0, 0, 0};
     std::string last_error;
@@ -98,6 +101,7 @@ namespace {
 
 float limit_hi(double mx) { float f = (float)mx; if ((double)f > mx) f = nextafterf(f, -INFINITY); return f; }
 float limit_lo(double mn) { float f = (float)mn; if ((double)f < mn) f = nextafterf(f, INFINITY); return f; }
+int fe_smem(int nt) { return nt == 512 ? fe_dyn_smem<512>() : fe_dyn_smem<1024>(); }
 float thr_up(double t) { float f = (float)t; if ((double)f < t) f = nextafterf(f, INFINITY); return f; }
 
 template <typename T>
@@ -201,7 +205,42 @@ int run_chunk(cuboid_handle* h, const ChunkIn& in, int nf, cuboid_frame_result* 
     FrameScratch* b_scr = h->d_scr + f0; unsigned long long* b_desc1 = h->d_desc1 + (size_t)f0 * h->tilesP;
     unsigned long long* b_desc2 = h->d_desc2 + (size_t)f0 * h->tilesV;
     CK(h, cudaEventRecord(evs[0], st));
-    if ((stages & 1) && !skip_pre) {
+    const bool fused = h->frontend && (stages & 1) && !skip_pre && !skip_vox;
+    if (fused) {
+        CK(h, cudaMemsetAsync(d_res, 0, sizeof(cuboid_frame_result) * nf, st));
+        FrontArgs fa{};
+        PreArgs& a = fa.pre;
+        a.depth = in.depth; a.blob = in.blob; a.point_step = in.point_step; a.xoff = in.xoff; a.yoff = in.yoff; a.zoff = in.zoff;
+        a.n_in = in.blob ? h->d_n_in + f0 : nullptr;
+        a.w = in.w; a.h = in.hgt; a.P = in.in_stride;
+        a.fx = p.fx; a.fy = p.fy; a.cx = p.cx; a.cy = p.cy; a.depth_scale = p.depth_scale;
+        if (!in.blob) { CKS(h, ensure_ray_tables(h, in.w, in.hgt)); a.xr = h->d_xr; a.yr = h->d_yr; }
+        a.z_lo = limit_lo(p.pass_z_min); a.z_hi = limit_hi(p.pass_z_max);
+        a.x_lo = limit_lo(p.pass_x_min); a.x_hi = limit_hi(p.pass_x_max);
+        a.pts = b_pts; a.res = d_res; a.scr = b_scr; a.n_frames = nf; a.Pout = h->P;
+        if (in.in_stride > h->P) return CUBOID_E_CAPACITY;
+        fa.keys = h->d_fe_keys; fa.kpp = h->taps ? b_kpp : nullptr; fa.vox = b_vox; fa.vcount = h->taps ? b_vcount : nullptr;
+        fa.inv_leaf = 1.0f / p.leaf; fa.P = h->P; fa.n_frames = nf;
+        cudaLaunchConfig_t cfg{};
+        cudaLaunchAttribute at[1];
+        at[0].id = cudaLaunchAttributeClusterDimension;
+        at[0].val.clusterDim.x = h->fe_cluster; at[0].val.clusterDim.y = 1; at[0].val.clusterDim.z = 1;
+        cfg.gridDim = dim3((unsigned int)(std::min(h->fe_slots, nf) * h->fe_cluster));
+        cfg.blockDim = dim3((unsigned int)h->fe_threads);
+        cfg.dynamicSmemBytes = (size_t)fe_smem(h->fe_threads);
+        cfg.stream = st;
+        cfg.attrs = at; cfg.numAttrs = 1;
+        if (h->fe_threads == 512) {
+            if (in.blob) CK(h, cudaLaunchKernelEx(&cfg, k_frontend<1, 512>, fa));
+            else CK(h, cudaLaunchKernelEx(&cfg, k_frontend<0, 512>, fa));
+        } else {
+            if (in.blob) CK(h, cudaLaunchKernelEx(&cfg, k_frontend<1, 1024>, fa));
+            else CK(h, cudaLaunchKernelEx(&cfg, k_frontend<0, 1024>, fa));
+        }
+        ++h->launches;
+        CK(h, cudaGetLastError());
+    }
+    if (!fused && (stages & 1) && !skip_pre) {
         CK(h, cudaMemsetAsync(d_res, 0, sizeof(cuboid_frame_result) * nf, st));
         k_init_scratch<<<(nf + 127) / 128, 128, 0, st>>>(b_scr, nf);
         ++h->launches;
@@ -225,7 +264,7 @@ int run_chunk(cuboid_handle* h, const ChunkIn& in, int nf, cuboid_frame_result* 
         CK(h, cudaGetLastError());
     }
     CK(h, cudaEventRecord(evs[1], st));
-    if ((stages & 1) && !skip_vox) {
+    if (!fused && (stages & 1) && !skip_vox) {
         VoxArgs v{};
         v.pts = b_pts; v.keysA = b_keysA; v.keysB = b_keysB; v.kpp = h->taps ? b_kpp : nullptr; v.hist = b_hist;
         v.vox = b_vox; v.vcount = h->taps ? b_vcount : nullptr; v.res = d_res; v.scr = b_scr; v.desc = b_desc2;
@@ -429,6 +468,34 @@ int cuboid_create(cuboid_handle** out, const cuboid_params* p, int device, int m
     cudaDeviceGetAttribute(&h->smem_optin, cudaDevAttrMaxSharedMemoryPerBlockOptin, device);
     h->icp_smem_budget = h->smem_optin - 4096;   // static shared memory of k_icp stays well below 4 KB
     if (cudaFuncSetAttribute(k_icp, cudaFuncAttributeMaxDynamicSharedMemorySize, h->icp_smem_budget) != cudaSuccess) return fail(CUBOID_E_CUDA);
+    {   // fused front end: cluster size and the number of clusters the device keeps resident
+        const char* ef = std::getenv("CUBOID_FRONTEND"); if (ef) h->frontend = atoi(ef) ? 1 : 0;
+        const char* ec = std::getenv("CUBOID_FE_CLUSTER"); if (ec) h->fe_cluster = std::max(1, std::min(16, atoi(ec)));
+        const char* et = std::getenv("CUBOID_FE_THREADS"); if (et) h->fe_threads = atoi(et) == 1024 ? 1024 : 512;
+        const void* fns[4] = {(const void*)k_frontend<0, 512>, (const void*)k_frontend<1, 512>, (const void*)k_frontend<0, 1024>, (const void*)k_frontend<1, 1024>};
+        for (int k = 0; k < 4; ++k) {
+            if (cudaFuncSetAttribute(fns[k], cudaFuncAttributeMaxDynamicSharedMemorySize, fe_smem(k < 2 ? 512 : 1024)) != cudaSuccess) return fail(CUBOID_E_CUDA);
+            if (h->fe_cluster > 8) cudaFuncSetAttribute(fns[k], cudaFuncAttributeNonPortableClusterSizeAllowed, 1);
+        }
+        int sms = 0;
+        cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, device);
+        for (; h->fe_cluster >= 1; h->fe_cluster >>= 1) {
+            cudaLaunchConfig_t cfg{};
+            cudaLaunchAttribute at[1];
+            at[0].id = cudaLaunchAttributeClusterDimension;
+            at[0].val.clusterDim.x = h->fe_cluster; at[0].val.clusterDim.y = 1; at[0].val.clusterDim.z = 1;
+            cfg.gridDim = dim3((unsigned int)((sms / h->fe_cluster) * h->fe_cluster)); cfg.blockDim = dim3((unsigned int)h->fe_threads);
+            cfg.dynamicSmemBytes = (size_t)fe_smem(h->fe_threads);
+            cfg.attrs = at; cfg.numAttrs = 1;
+            int ncl = 0;
+            if (cudaOccupancyMaxActiveClusters(&ncl, fns[h->fe_threads == 512 ? 0 : 2], &cfg) == cudaSuccess && ncl > 0) { h->fe_slots = ncl; break; }
+            cudaGetLastError();
+            if (h->fe_cluster == 1) break;
+        }
+        if (h->fe_slots < 1) { h->last_error = "k_frontend: no resident cluster configuration"; fprintf(stderr, "cuboid_create: %s\n", h->last_error.c_str()); return fail(CUBOID_E_CUDA); }
+        h->fe_slots = std::min(h->fe_slots, std::max(1, h->B));
+        CA(dalloc(h, &h->d_fe_keys, (size_t)h->fe_slots * 2 * h->P));
+    }
     CA(dalloc(h, &h->d_work, (size_t)2));
     if (cudaMemset(h->d_work, 0, 16) != cudaSuccess) return fail(CUBOID_E_CUDA);
     { const char* ec = std::getenv("CUBOID_ICP_CULL"); if (ec) h->icp_cull = atoi(ec) ? 1 : 0; }
@@ -446,7 +513,7 @@ int cuboid_destroy(cuboid_handle* h) {
     void* ptrs[] = {h->d_depth, h->d_blob, h->d_n_in, h->d_xr, h->d_yr, h->d_pts, h->d_keysA, h->d_keysB, h->d_kpp, h->d_hist, h->d_vox, h->d_vcount, h->d_shuffled,
                     h->d_inl_pre, h->d_inl, h->d_remain, h->d_parent, h->d_csize, h->d_crank, h->d_idx_sorted, h->d_offsets, h->d_roots, h->d_cell_head, h->d_cell_pts,
                     h->d_cur, h->d_corr, h->d_cd, h->d_order, h->d_icp_out, h->d_scr, h->d_desc1, h->d_desc2, h->d_ticket, h->d_res, h->d_rng,
-                    h->d_triplets, h->d_guesses, h->d_trace_corr, h->d_trace_T, h->d_aligned, h->d_work};
+                    h->d_triplets, h->d_guesses, h->d_trace_corr, h->d_trace_T, h->d_aligned, h->d_work, h->d_fe_keys};
     for (void* q : ptrs) if (q) cudaFree(q);
     for (auto& t : h->d_tmpl) if (t) cudaFree(t);
     for (auto& t : h->d_boxes) if (t) cudaFree(t);
@@ -777,7 +844,8 @@ static int process_frames(cuboid_handle* h, const uint16_t* depth, bool on_devic
     // A resident chunk (<= B frames) is fed in sub-chunks: every sub-chunk's depth copy is queued on the copy stream up
     // front, its pre-ICP kernels start as soon as that copy lands (so copies overlap kernels), and ICP runs once over the
     // whole chunk so that its one-CTA-per-problem grid spans several waves (the slowest problem no longer sets the time).
-    const int SUB = std::min(h->sub_batch, h->B);
+    // device-resident input needs no copy overlap: the fused front end then takes the whole chunk in one persistent launch
+    const int SUB = (on_device && h->frontend) ? h->B : std::min(h->sub_batch, h->B);
     const int max_sub = (h->B + SUB - 1) / SUB;
     const size_t need_ev = (size_t)max_sub * 6 + 2;
     while (h->ev_pool.size() < need_ev) {
@@ -989,6 +1057,7 @@ int cuboid_set_option(cuboid_handle* h, int option, int value) {
     switch (option) {
         case CUBOID_OPT_ICP_CULL: h->icp_cull = value ? 1 : 0; return CUBOID_OK;
         case CUBOID_OPT_TAPS: h->taps = value ? 1 : 0; return CUBOID_OK;
+        case CUBOID_OPT_FRONTEND: h->frontend = value ? 1 : 0; return CUBOID_OK;
         case CUBOID_OPT_STAGES:
             if (value < 1 || value > 15) return CUBOID_E_INVALID;
             h->stage_mask = (value & 8) ? 15 : (value & 4) ? 7 : (value & 2) ? 3 : 1;

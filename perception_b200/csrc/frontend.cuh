@@ -1,0 +1,480 @@
+// frontend.cuh — stages 1a + 1b of one frame in ONE kernel: depth -> cloud unprojection (or PointCloud2 blob read),
+// both PassThrough filters, ordered compaction, getMinMax3D, the VoxelGrid key, the stable radix sort and the
+// sequential float centroids (gps.cpp:53-73, opd.cpp:275-298).
+//
+// One thread-block CLUSTER owns one frame at a time (persistent grid, clusters stride over the frames of the chunk).
+// The CTAs of the cluster split the frame's pixels, then its sort records, then its sorted records into contiguous
+// ranges; what they must agree on (survivor counts, min/max, digit histograms, voxel counts) is exchanged through
+// distributed shared memory between cluster barriers. The radix ping-pong buffers belong to the cluster SLOT, not to
+// the frame, so the same few megabytes are rewritten frame after frame and stay resident in the 126 MB L2: the only
+// HBM traffic left is the algorithmic one (depth in, points out, centroids out).
+//
+// Results are bit-identical to the unfused kernels in preprocess.cuh / voxel.cuh (kept as the CUBOID_OPT_FRONTEND=0
+// path and compared byte for byte in tests/test_gpu_parity.py): same point order, same keys, same stable order inside
+// a voxel, same sequential float sums.
+//
+// Roofline: HBM. Algorithmic bytes per frame = 2*P + 16*N (a0+a1) + 16*N + 16*V (a2).
+#pragma once
+#include <cooperative_groups.h>
+
+#include "common.cuh"
+#include "preprocess.cuh"
+#include "voxel.cuh"
+
+namespace cuboid {
+namespace cg = cooperative_groups;
+
+struct FrontArgs {
+    PreArgs pre;                 // input description, limits, pts, res, scr (tile_count / tiles are unused here)
+    unsigned long long* keys;    // [n_slots][2][P] radix ping-pong of the frame a cluster slot is working on
+    int* kpp;                    // [F][P] voxel idx per point (parity tap) or NULL
+    float4* vox;                 // [F][P]
+    int* vcount;                 // [F][P] points per voxel (parity tap) or NULL
+    float inv_leaf;
+    int P;                       // per-frame stride of pts / vox / kpp / vcount / keys
+    int n_frames;
+};
+
+constexpr int FE_ITEMS = 8;      // inputs / sort records per thread and tile
+constexpr int FE_RITEMS = 4;     // sorted records per thread and reduce tile
+constexpr int FE_LONGRUN = 96;   // voxels with more points than this are summed by a whole warp (lane-parallel loads)
+constexpr int FE_MAXDEF = 64;    // >= 512*4/96 + 1 and >= 1024*4/96 + 1
+
+struct FeXchg {          // what a CTA publishes to its cluster peers
+    int count;           // survivors of its input slice
+    float mn[3], mx[3];  // their min / max
+    int heads;           // voxels that start inside its range of the sorted records
+};
+struct FeFrame {         // cluster-wide facts of the current frame, replicated per CTA by thread 0
+    int base, N;         // first output position of this CTA's survivors, survivors of the frame
+    int vbase, V;
+    VoxelGeom g;
+};
+
+// dynamic shared memory: the three phases reuse one arena
+//   A2      u16 tile-local input index of every survivor of the tile            NT*8*2  bytes
+//   B       per-warp digit counters [NT/32][256] u32                            NT*32   bytes
+//   C2      key,x,y,z of the staged sorted records + u16 head positions         NT*4*18 bytes
+template <int NT>
+constexpr int fe_dyn_smem() { return NT * FE_RITEMS * 18; }
+
+template <int NT, int NQ>
+__device__ __forceinline__ void fe_block_sum_u64(unsigned long long (&v)[NQ], unsigned long long* s_part /*[NQ][NT/32]*/) {
+    constexpr int NW = NT / 32;
+    const int lane = threadIdx.x & 31, wid = threadIdx.x >> 5;
+#pragma unroll
+    for (int q = 0; q < NQ; ++q) {
+        const unsigned long long x = warp_sum_u64(v[q]);
+        if (lane == 0) s_part[q * NW + wid] = x;
+    }
+    __syncthreads();
+    if (threadIdx.x < NQ) {
+        unsigned long long s = 0;
+        for (int w = 0; w < NW; ++w) s += s_part[threadIdx.x * NW + w];
+        s_part[threadIdx.x * NW] = s;
+    }
+    __syncthreads();
+#pragma unroll
+    for (int q = 0; q < NQ; ++q) v[q] = s_part[q * NW];
+    __syncthreads();
+}
+
+// one input -> point, with exactly the float operations of pre_points (preprocess.cuh)
+template <int SRC>
+__device__ __forceinline__ float4 fe_point_at(const PreArgs& a, int f, int i) {
+    if (SRC == 0) {
+        const int v = i / a.w, u = i - v * a.w;
+        const float z = (float)a.depth[(size_t)f * a.P + i] * a.depth_scale;
+        return make_float4(z * a.xr[u], z * a.yr[v], z, 1.0f);
+    } else {
+        const unsigned char* rec = a.blob + ((size_t)f * a.P + i) * a.point_step;
+        return make_float4(*reinterpret_cast<const float*>(rec + a.xoff), *reinterpret_cast<const float*>(rec + a.yoff),
+                           *reinterpret_cast<const float*>(rec + a.zoff), 1.0f);
+    }
+}
+
+// s += (a run of +-0 values), folded: the sum only changes when it is -0 and a +0 is added (IEEE round-to-nearest)
+__device__ __forceinline__ float fe_add_zeros(float s, bool any_plus_zero) {
+    return (__float_as_uint(s) == 0x80000000u && any_plus_zero) ? 0.0f : s;
+}
+
+template <int SRC, int NT>
+__global__ void __launch_bounds__(NT, 2048 / NT >= 2 ? (NT <= 512 ? 2 : 1) : 1) k_frontend(const FrontArgs a) {
+    constexpr int NW = NT / 32;
+    constexpr int TILE = NT * FE_ITEMS;
+    constexpr int RTILE = NT * FE_RITEMS;
+    extern __shared__ __align__(16) unsigned char fe_dyn[];
+    __shared__ FeXchg s_x;
+    __shared__ FeFrame s_f;
+    __shared__ unsigned int s_hist[256];
+    __shared__ unsigned int s_base[256];
+    __shared__ int s_w[NW + 1];
+    __shared__ float s_mm[NW][6];
+    __shared__ int s_wc[NW];
+    __shared__ unsigned long long s_h64[2 * NW];
+    __shared__ int s_ndef;                 // voxels of the current reduce tile deferred to the warp-cooperative routine
+    __shared__ int s_def_lp[FE_MAXDEF], s_def_pos[FE_MAXDEF];
+
+    cg::cluster_group cluster = cg::this_cluster();
+    const int C = (int)cluster.num_blocks(), r = (int)cluster.block_rank();
+    const int slot = blockIdx.x / C, nslots = gridDim.x / C;
+    const int tid = threadIdx.x, lane = tid & 31, wid = tid >> 5;
+    const PreArgs& p = a.pre;
+    unsigned long long* bufA = a.keys + (size_t)slot * 2 * a.P;
+    unsigned long long* bufB = bufA + a.P;
+
+    for (int f = slot; f < a.n_frames; f += nslots) {
+        const int n_in = (SRC == 1 && p.n_in) ? p.n_in[f] : p.P;
+        int slice = (n_in + C - 1) / C;
+        slice = (slice + 7) & ~7;
+        const int s0 = min(n_in, r * slice), s1 = min(n_in, r * slice + slice);
+
+        // ---- A1: survivors and min/max of this CTA's input slice ----
+        {
+            int cnt = 0;
+            float mn[3] = {3.402823466e38f, 3.402823466e38f, 3.402823466e38f};
+            float mx[3] = {-3.402823466e38f, -3.402823466e38f, -3.402823466e38f};
+            for (int first = s0 + tid * FE_ITEMS; first < s1; first += TILE) {
+                float px[FE_ITEMS], py[FE_ITEMS], pz[FE_ITEMS];
+                const unsigned int keep = pre_points<SRC>(p, f, first, s1, px, py, pz);
+                cnt += __popc(keep);
+#pragma unroll
+                for (int k = 0; k < FE_ITEMS; ++k)
+                    if (keep & (1u << k)) {
+                        mn[0] = fminf(mn[0], px[k]); mx[0] = fmaxf(mx[0], px[k]);
+                        mn[1] = fminf(mn[1], py[k]); mx[1] = fmaxf(mx[1], py[k]);
+                        mn[2] = fminf(mn[2], pz[k]); mx[2] = fmaxf(mx[2], pz[k]);
+                    }
+            }
+#pragma unroll
+            for (int o = 16; o >= 1; o >>= 1) {
+                cnt += __shfl_xor_sync(FULL_MASK, cnt, o);
+#pragma unroll
+                for (int c = 0; c < 3; ++c) {
+                    mn[c] = fminf(mn[c], __shfl_xor_sync(FULL_MASK, mn[c], o));
+                    mx[c] = fmaxf(mx[c], __shfl_xor_sync(FULL_MASK, mx[c], o));
+                }
+            }
+            if (lane == 0) {
+                s_wc[wid] = cnt;
+#pragma unroll
+                for (int c = 0; c < 3; ++c) { s_mm[wid][c] = mn[c]; s_mm[wid][3 + c] = mx[c]; }
+            }
+            __syncthreads();
+            if (tid == 0) {
+                int count = 0;
+                float xmn[3] = {3.402823466e38f, 3.402823466e38f, 3.402823466e38f};
+                float xmx[3] = {-3.402823466e38f, -3.402823466e38f, -3.402823466e38f};
+                for (int w = 0; w < NW; ++w) {
+                    count += s_wc[w];
+                    for (int c = 0; c < 3; ++c) { xmn[c] = fminf(xmn[c], s_mm[w][c]); xmx[c] = fmaxf(xmx[c], s_mm[w][3 + c]); }
+                }
+                s_x.count = count;
+                for (int c = 0; c < 3; ++c) { s_x.mn[c] = xmn[c]; s_x.mx[c] = xmx[c]; }
+            }
+        }
+        cluster.sync();
+        if (tid == 0) {
+            int base = 0, N = 0;
+            float mn[3] = {3.402823466e38f, 3.402823466e38f, 3.402823466e38f};
+            float mx[3] = {-3.402823466e38f, -3.402823466e38f, -3.402823466e38f};
+            for (int rr = 0; rr < C; ++rr) {
+                const FeXchg* q = cluster.map_shared_rank(&s_x, rr);
+                const int c = q->count;
+                if (rr < r) base += c;
+                N += c;
+                if (c > 0)
+                    for (int k = 0; k < 3; ++k) { mn[k] = fminf(mn[k], q->mn[k]); mx[k] = fmaxf(mx[k], q->mx[k]); }
+            }
+            FrameScratch sc;
+            sc.mm[0] = sc.mm[1] = sc.mm[2] = 0xffffffffu;
+            sc.mm[3] = sc.mm[4] = sc.mm[5] = 0u;
+            sc.sort_bits = 0; sc.overflow_mode = 0; sc.best_count = 0; sc.pad = 0;
+            VoxelGeom g;
+            g.inv = a.inv_leaf; g.sort_bits = 0; g.overflow_mode = 0; g.pcl_overflow = 0; g.mul1 = g.mul2 = 0;
+            for (int k = 0; k < 3; ++k) { g.min_b[k] = 0; g.div_b[k] = 0; }
+            if (N > 0) {
+                for (int k = 0; k < 3; ++k) { sc.mm[k] = enc_f32(mn[k]); sc.mm[3 + k] = enc_f32(mx[k]); }
+                g = voxel_geom(sc, a.inv_leaf);
+                sc.sort_bits = g.sort_bits; sc.overflow_mode = g.overflow_mode;
+            }
+            s_f.base = base; s_f.N = N; s_f.g = g;
+            if (r == 0) {
+                p.scr[f] = sc;
+                cuboid_frame_result& R = p.res[f];
+                R.n_points = N;
+                if (N > 0) {
+                    for (int k = 0; k < 3; ++k) { R.min_b[k] = g.min_b[k]; R.div_b[k] = g.div_b[k]; }
+                    if (g.pcl_overflow) atomicOr(&R.status, CUBOID_W_VOXEL_OVERFLOW);
+                } else {
+                    R.n_voxels = 0;
+                }
+            }
+        }
+        __syncthreads();
+        const int N = s_f.N;
+        if (N == 0) {          // cluster-uniform; the barrier keeps a fast CTA from overwriting s_x while a peer still reads it
+            cluster.sync();
+            continue;
+        }
+        const VoxelGeom g = s_f.g;
+
+        // ---- A2: ordered compaction of the slice. The divergent part only records WHICH inputs survive (u16 tile-local
+        //      index, in order); the per-point work then runs dense, one survivor per thread, with coalesced stores ----
+        {
+            unsigned short* s_sel = reinterpret_cast<unsigned short*>(fe_dyn);
+            float4* out = p.pts + (size_t)f * p.Pout;
+            int* kpp = a.kpp ? a.kpp + (size_t)f * a.P : nullptr;
+            int run = s_f.base;
+            unsigned long long hh[2] = {0ull, 0ull};
+            for (int t0 = s0; t0 < s1; t0 += TILE) {
+                const int first = t0 + tid * FE_ITEMS;
+                unsigned int keep = 0;
+                if (first < s1) {
+                    float px[FE_ITEMS], py[FE_ITEMS], pz[FE_ITEMS];
+                    keep = pre_points<SRC>(p, f, first, s1, px, py, pz);
+                }
+                int total;
+                int lp = block_excl_scan<NT>(__popc(keep), s_w, &total);
+#pragma unroll
+                for (int k = 0; k < FE_ITEMS; ++k)
+                    if (keep & (1u << k)) s_sel[lp++] = (unsigned short)(tid * FE_ITEMS + k);
+                __syncthreads();
+                for (int q = tid; q < total; q += NT) {
+                    const float4 pt = fe_point_at<SRC>(p, f, t0 + (int)s_sel[q]);
+                    const int pos = run + q;
+                    out[pos] = pt;
+                    const int idx = voxel_index(g, pt.x, pt.y, pt.z);
+                    const unsigned int sk = g.overflow_mode ? ((unsigned int)idx ^ 0x80000000u) : (unsigned int)idx;
+                    __stcg(bufA + pos, ((unsigned long long)sk << 32) | (unsigned int)pos);
+                    if (kpp) kpp[pos] = idx;
+                    hh[0] += hash_point((unsigned int)pos, pt.x, pt.y, pt.z);
+                    hh[1] += hash_index((unsigned int)pos, idx);
+                }
+                run += total;
+                __syncthreads();
+            }
+            fe_block_sum_u64<NT, 2>(hh, s_h64);
+            if (tid == 0) {
+                if (hh[0]) atomic_add_u64(&p.res[f].points_hash, hh[0]);
+                if (hh[1]) atomic_add_u64(&p.res[f].voxel_key_hash, hh[1]);
+            }
+        }
+        __threadfence();
+        cluster.sync();
+
+        // ---- B: stable LSD radix sort of the frame's N records, 8-bit digits, significant key bits only ----
+        const int npass = (g.sort_bits + 7) / 8;
+        int per = (N + C - 1) / C;
+        per = (per + 255) & ~255;       // whole warp runs (8 items x 32 lanes): tiles of a range stay warp-aligned
+        const int q0 = min(N, r * per), q1 = min(N, r * per + per);
+        unsigned int (*s_cnt)[256] = reinterpret_cast<unsigned int (*)[256]>(fe_dyn);
+        for (int pass = 0; pass < npass; ++pass) {
+            const unsigned long long* src = (pass & 1) ? bufB : bufA;
+            unsigned long long* dst = (pass & 1) ? bufA : bufB;
+            const int shift = 32 + pass * 8;
+            if (tid < 256) s_hist[tid] = 0;
+            __syncthreads();
+            for (int i = q0 + tid; i < q1; i += NT) atomicAdd(&s_hist[(unsigned int)(__ldcg(src + i) >> shift) & 255u], 1u);
+            __syncthreads();
+            cluster.sync();
+            {   // digit d = tid: records of digit d in front of this CTA's = all smaller digits + digit d of lower ranks
+                unsigned int tot = 0, before = 0;
+                if (tid < 256) {
+                    if (C == 1) tot = s_hist[tid];
+                    else
+                        for (int rr = 0; rr < C; ++rr) {
+                            const unsigned int v = cluster.map_shared_rank(s_hist, rr)[tid];
+                            tot += v;
+                            if (rr < r) before += v;
+                        }
+                }
+                int total;
+                const int ex = block_excl_scan<NT>((int)tot, s_w, &total);
+                if (tid < 256) s_base[tid] = (unsigned int)ex + before;
+                __syncthreads();
+            }
+            for (int t0 = q0; t0 < q1; t0 += TILE) {
+                for (int d = lane; d < 256; d += 32) s_cnt[wid][d] = 0;
+                __syncwarp();
+                // warp w owns the contiguous run [t0 + w*256, +256): (warp, item, lane) order == ascending input order
+                unsigned long long key[FE_ITEMS];
+                unsigned int rank[FE_ITEMS];
+#pragma unroll
+                for (int k = 0; k < FE_ITEMS; ++k) {
+                    const int i = t0 + wid * (32 * FE_ITEMS) + k * 32 + lane;
+                    key[k] = i < q1 ? __ldcg(src + i) : ~0ull;
+                }
+#pragma unroll
+                for (int k = 0; k < FE_ITEMS; ++k) {
+                    const int i = t0 + wid * (32 * FE_ITEMS) + k * 32 + lane;
+                    const bool valid = i < q1;
+                    const unsigned int d = valid ? ((unsigned int)(key[k] >> shift) & 255u) : 256u;
+                    const unsigned int peers = __match_any_sync(FULL_MASK, d);
+                    const int leader = __ffs(peers) - 1;
+                    unsigned int before = 0;
+                    if (valid && lane == leader) { before = s_cnt[wid][d]; s_cnt[wid][d] = before + __popc(peers); }
+                    before = __shfl_sync(FULL_MASK, before, leader);
+                    rank[k] = before + __popc(peers & ((1u << lane) - 1u));
+                    __syncwarp();
+                }
+                __syncthreads();
+                if (tid < 256) {
+                    unsigned int run = s_base[tid];
+#pragma unroll 8
+                    for (int ww = 0; ww < NW; ++ww) { const unsigned int c = s_cnt[ww][tid]; s_cnt[ww][tid] = run; run += c; }
+                    s_base[tid] = run;
+                }
+                __syncthreads();
+#pragma unroll
+                for (int k = 0; k < FE_ITEMS; ++k) {
+                    const int i = t0 + wid * (32 * FE_ITEMS) + k * 32 + lane;
+                    if (i < q1) {
+                        const unsigned int d = (unsigned int)(key[k] >> shift) & 255u;
+                        __stcg(dst + s_cnt[wid][d] + rank[k], key[k]);
+                    }
+                }
+                __syncthreads();
+            }
+            __threadfence();
+            cluster.sync();
+        }
+        const unsigned long long* keys = (npass & 1) ? bufB : bufA;
+
+        // ---- C1: voxels that start inside this CTA's range -> voxel ordinal base (nothing to exchange when C == 1) ----
+        if (C > 1) {
+            int heads = 0;
+            for (int i = q0 + tid; i < q1; i += NT) {
+                const unsigned int k = (unsigned int)(__ldcg(keys + i) >> 32);
+                heads += (i == 0 || k != (unsigned int)(__ldcg(keys + i - 1) >> 32)) ? 1 : 0;
+            }
+#pragma unroll
+            for (int o = 16; o >= 1; o >>= 1) heads += __shfl_xor_sync(FULL_MASK, heads, o);
+            if (lane == 0) s_wc[wid] = heads;
+            __syncthreads();
+            if (tid == 0) {
+                int t = 0;
+                for (int w = 0; w < NW; ++w) t += s_wc[w];
+                s_x.heads = t;
+            }
+            cluster.sync();
+        }
+        if (tid == 0) {
+            int vbase = 0;
+            for (int rr = 0; rr < r; ++rr) vbase += cluster.map_shared_rank(&s_x, rr)->heads;
+            s_f.vbase = vbase;
+            s_ndef = 0;
+        }
+        __syncthreads();
+
+        // ---- C2: sequential float centroid of every voxel that starts in this range. A tile of sorted records (key and
+        //      gathered point) is staged with parallel loads; heads are compacted; then ONE THREAD PER VOXEL sums its run
+        //      out of shared memory in sorted (= ascending point index) order and the centroid stores are coalesced ----
+        {
+            unsigned int* s_key = reinterpret_cast<unsigned int*>(fe_dyn);
+            float* s_px = reinterpret_cast<float*>(fe_dyn) + RTILE;
+            float* s_py = s_px + RTILE;
+            float* s_pz = s_py + RTILE;
+            unsigned short* s_head = reinterpret_cast<unsigned short*>(s_pz + RTILE);
+            const float4* pts = p.pts + (size_t)f * p.Pout;
+            float4* vox = a.vox + (size_t)f * a.P;
+            int* vcount = a.vcount ? a.vcount + (size_t)f * a.P : nullptr;
+            int vrun = s_f.vbase;
+            unsigned long long hv[1] = {0ull};
+            for (int t0 = q0; t0 < q1; t0 += RTILE) {
+                const int n_here = min(RTILE, q1 - t0);
+#pragma unroll
+                for (int k = 0; k < FE_RITEMS; ++k) {
+                    const int l = k * NT + tid;
+                    if (l < n_here) {
+                        const unsigned long long rec = __ldcg(keys + t0 + l);
+                        const float4 pt = __ldcg(pts + (unsigned int)rec);
+                        s_key[l] = (unsigned int)(rec >> 32);
+                        s_px[l] = pt.x; s_py[l] = pt.y; s_pz[l] = pt.z;
+                    }
+                }
+                const unsigned int prev_key = t0 > 0 ? (unsigned int)(__ldcg(keys + t0 - 1) >> 32) : 0u;
+                __syncthreads();
+                const int first = tid * FE_RITEMS;
+                unsigned int heads = 0;
+#pragma unroll
+                for (int k = 0; k < FE_RITEMS; ++k) {
+                    const int lp = first + k;
+                    if (lp < n_here && (t0 + lp == 0 || s_key[lp] != (lp > 0 ? s_key[lp - 1] : prev_key))) heads |= 1u << k;
+                }
+                int total;
+                int hp = block_excl_scan<NT>(__popc(heads), s_w, &total);
+#pragma unroll
+                for (int k = 0; k < FE_RITEMS; ++k)
+                    if (heads & (1u << k)) s_head[hp++] = (unsigned short)(first + k);
+                __syncthreads();
+                for (int v = tid; v < total; v += NT) {
+                    const int lp = s_head[v];
+                    const int end = (v + 1 < total) ? (int)s_head[v + 1] : n_here;
+                    const int pos = vrun + v;
+                    if ((v + 1 == total && t0 + n_here < N) || end - lp > FE_LONGRUN) {
+                        // may continue past the tile (only the last voxel can), or long (e.g. the origin voxel that collects
+                        // every zero-depth pixel): a whole warp takes it
+                        const int d = atomicAdd(&s_ndef, 1);
+                        s_def_lp[d] = lp; s_def_pos[d] = pos;
+                        continue;
+                    }
+                    float sx = s_px[lp], sy = s_py[lp], sz = s_pz[lp];   // centroid starts as the first point, then += in sorted order
+                    for (int q = lp + 1; q < end; ++q) { sx += s_px[q]; sy += s_py[q]; sz += s_pz[q]; }
+                    const float cnt = (float)(end - lp);
+                    const float cx = sx / cnt, cy = sy / cnt, cz = sz / cnt;
+                    vox[pos] = make_float4(cx, cy, cz, 1.0f);
+                    if (vcount) vcount[pos] = end - lp;
+                    hv[0] += hash_point((unsigned int)pos, cx, cy, cz);
+                }
+                vrun += total;
+                __syncthreads();
+                for (int d = wid; d < s_ndef; d += NW) {   // lane-parallel loads from the sorted records, in-order accumulation
+                    const int lp = s_def_lp[d];
+                    const unsigned int mykey = s_key[lp];
+                    float sx = s_px[lp], sy = s_py[lp], sz = s_pz[lp];
+                    int cnt = 1;
+                    int q = t0 + lp + 1;
+                    unsigned long long rec = (q + lane < N) ? __ldcg(keys + q + lane) : ~0ull;
+                    while (q < N) {
+                        const unsigned int kk = (q + lane < N) ? (unsigned int)(rec >> 32) : ~mykey;
+                        float ax = 0.f, ay = 0.f, az = 0.f;
+                        if (kk == mykey) { const float4 pt = __ldcg(pts + (unsigned int)rec); ax = pt.x; ay = pt.y; az = pt.z; }
+                        if (q + 32 + lane < N) rec = __ldcg(keys + q + 32 + lane);   // next step's records while this step is summed
+                        const unsigned int miss = __ballot_sync(FULL_MASK, kk != mykey);
+                        const int nmatch = miss ? (__ffs(miss) - 1) : 32;
+                        const unsigned int in = nmatch == 32 ? FULL_MASK : ((1u << nmatch) - 1u);
+                        // an axis whose nmatch values are all +-0 folds in O(1): no 32-deep dependent chain
+                        const unsigned int nzx = __ballot_sync(FULL_MASK, ax != 0.0f) & in, nzy = __ballot_sync(FULL_MASK, ay != 0.0f) & in,
+                                           nzz = __ballot_sync(FULL_MASK, az != 0.0f) & in;
+                        const unsigned int pzx = __ballot_sync(FULL_MASK, __float_as_uint(ax) == 0u) & in,
+                                           pzy = __ballot_sync(FULL_MASK, __float_as_uint(ay) == 0u) & in,
+                                           pzz = __ballot_sync(FULL_MASK, __float_as_uint(az) == 0u) & in;
+                        if (nzx) { for (int j = 0; j < nmatch; ++j) sx += __shfl_sync(FULL_MASK, ax, j); } else sx = fe_add_zeros(sx, pzx != 0u);
+                        if (nzy) { for (int j = 0; j < nmatch; ++j) sy += __shfl_sync(FULL_MASK, ay, j); } else sy = fe_add_zeros(sy, pzy != 0u);
+                        if (nzz) { for (int j = 0; j < nmatch; ++j) sz += __shfl_sync(FULL_MASK, az, j); } else sz = fe_add_zeros(sz, pzz != 0u);
+                        cnt += nmatch;
+                        if (nmatch < 32) break;
+                        q += 32;
+                    }
+                    if (lane == 0) {
+                        const float c = (float)cnt;
+                        const float cx = sx / c, cy = sy / c, cz = sz / c;
+                        const int vp = s_def_pos[d];
+                        vox[vp] = make_float4(cx, cy, cz, 1.0f);
+                        if (vcount) vcount[vp] = cnt;
+                        hv[0] += hash_point((unsigned int)vp, cx, cy, cz);
+                    }
+                }
+                __syncthreads();
+                if (tid == 0) s_ndef = 0;
+            }
+            if (tid == 0 && q1 == N && q0 < q1) p.res[f].n_voxels = vrun;   // the CTA that owns the tail knows the total
+            fe_block_sum_u64<NT, 1>(hv, s_h64);
+            if (tid == 0 && hv[0]) atomic_add_u64(&p.res[f].voxel_hash, hv[0]);
+        }
+    }
+    cluster.sync();   // no CTA may exit while a peer can still read its shared memory
+}
+
+}  // namespace cuboid

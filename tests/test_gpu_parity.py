@@ -373,3 +373,30 @@ def test_full_size_batch_properties(cc, tmpl30, params):
     for i in (0, 31, 63):
         _same_frame(res[i], O.process_frame(params, depth[i], tmpl30))
     assert all(r.n_clusters == 1 and r.cluster[0].converged for r in res)
+
+
+@pytest.mark.parametrize("cluster,threads", [(1, 512), (2, 512), (4, 512), (1, 1024), (4, 1024), (8, 1024)])
+def test_fused_frontend_equals_unfused_kernels(tmpl30, params, cluster, threads, monkeypatch):
+    """Stages 1a+1b as one cluster-per-frame kernel (frontend.cuh) against the unfused kernels: every result byte and
+    every fetched intermediate array equal, for each cluster size, on normal, empty and degenerate frames."""
+    depth = np.concatenate([synth.depth_batch("bench", [40, 41, 42, 43, 44]), np.zeros((3, 480, 640), np.uint16)])
+    depth[6] = 2000
+    depth[7] = synth.depth_frame("plane_only", 3)
+    monkeypatch.setenv("CUBOID_FE_CLUSTER", str(cluster))
+    monkeypatch.setenv("CUBOID_FE_THREADS", str(threads))
+    out = {}
+    for fused in (0, 1):
+        with api.CuboidCuda(params, max_points=640 * 480, max_batch=8) as h:
+            h.set_template(0, tmpl30)
+            h.set_option(api.OPT_FRONTEND, fused)
+            res = h.process_batch(depth)
+            out[fused] = ([bytes(r) for r in res],
+                          {w: [h.fetch(f, w) for f in (0, 4, 5, 7)] for w in ("points", "voxel_keys", "voxels", "voxel_counts")})
+    assert out[0][0] == out[1][0]
+    for w, arrs in out[0][1].items():
+        for x, y in zip(arrs, out[1][1][w]):
+            assert x.tobytes() == y.tobytes(), w
+    ref = O.process_frame(params, depth[2], tmpl30)
+    with api.CuboidCuda(params, max_points=640 * 480, max_batch=8) as h:
+        h.set_template(0, tmpl30)
+        _same_frame(h.process_batch(depth)[2], ref)

@@ -102,6 +102,11 @@ namespace {
 float limit_hi(double mx) { float f = (float)mx; if ((double)f > mx) f = nextafterf(f, -INFINITY); return f; }
 float limit_lo(double mn) { float f = (float)mn; if ((double)f < mn) f = nextafterf(f, INFINITY); return f; }
 int fe_smem(int nt) { return nt == 512 ? fe_dyn_smem<512>() : fe_dyn_smem<1024>(); }
+// ceil(2^32 / w) if __umulhi(i, magic) == i / w for every i < n (true when n * w <= 2^32), else 0 (plain division)
+unsigned int row_magic(int w, int n) {
+    if (w < 2 || (unsigned long long)n * (unsigned long long)w > (1ull << 32)) return 0u;
+    return (unsigned int)(((1ull << 32) + (unsigned long long)w - 1) / (unsigned long long)w);
+}
 float thr_up(double t) { float f = (float)t; if ((double)f < t) f = nextafterf(f, INFINITY); return f; }
 
 template <typename T>
@@ -212,7 +217,7 @@ int run_chunk(cuboid_handle* h, const ChunkIn& in, int nf, cuboid_frame_result* 
         PreArgs& a = fa.pre;
         a.depth = in.depth; a.blob = in.blob; a.point_step = in.point_step; a.xoff = in.xoff; a.yoff = in.yoff; a.zoff = in.zoff;
         a.n_in = in.blob ? h->d_n_in + f0 : nullptr;
-        a.w = in.w; a.h = in.hgt; a.P = in.in_stride;
+        a.w = in.w; a.h = in.hgt; a.P = in.in_stride; a.w_magic = row_magic(in.w, in.in_stride);
         a.fx = p.fx; a.fy = p.fy; a.cx = p.cx; a.cy = p.cy; a.depth_scale = p.depth_scale;
         if (!in.blob) { CKS(h, ensure_ray_tables(h, in.w, in.hgt)); a.xr = h->d_xr; a.yr = h->d_yr; }
         a.z_lo = limit_lo(p.pass_z_min); a.z_hi = limit_hi(p.pass_z_max);
@@ -249,7 +254,7 @@ int run_chunk(cuboid_handle* h, const ChunkIn& in, int nf, cuboid_frame_result* 
         PreArgs a{};
         a.depth = in.depth; a.blob = in.blob; a.point_step = in.point_step; a.xoff = in.xoff; a.yoff = in.yoff; a.zoff = in.zoff;
         a.n_in = in.blob ? h->d_n_in + f0 : nullptr;
-        a.w = in.w; a.h = in.hgt; a.P = per;
+        a.w = in.w; a.h = in.hgt; a.P = per; a.w_magic = row_magic(in.w, per);
         a.fx = p.fx; a.fy = p.fy; a.cx = p.cx; a.cy = p.cy; a.depth_scale = p.depth_scale;
         if (!in.blob) { CKS(h, ensure_ray_tables(h, in.w, in.hgt)); a.xr = h->d_xr; a.yr = h->d_yr; }
         a.z_lo = limit_lo(p.pass_z_min); a.z_hi = limit_hi(p.pass_z_max);

@@ -52,11 +52,13 @@ struct FeFrame {         // cluster-wide facts of the current frame, replicated 
 };
 
 // dynamic shared memory: the three phases reuse one arena
-//   A2      u16 tile-local input index of every survivor of the tile            NT*8*2  bytes
+//   A1/A2   u16 tile-local input index of every survivor of the tile            NT*8*2  bytes
+//           + the keep masks A1 found, so A2 does not unproject and filter again   FE_MASK_BYTES
 //   B       per-warp digit counters [NT/32][256] u32                            NT*32   bytes
 //   C2      key,x,y,z of the staged sorted records + u16 head positions         NT*4*18 bytes
+constexpr int FE_MASK_BYTES = 40960;   // keep masks of one input slice (1 byte per 8 inputs): a VGA frame on one CTA needs 38 400
 template <int NT>
-constexpr int fe_dyn_smem() { return NT * FE_RITEMS * 18; }
+constexpr int fe_dyn_smem() { return (NT * 16 + FE_MASK_BYTES) > (NT * FE_RITEMS * 18) ? (NT * 16 + FE_MASK_BYTES) : (NT * FE_RITEMS * 18); }
 
 template <int NT, int NQ>
 __device__ __forceinline__ void fe_block_sum_u64(unsigned long long (&v)[NQ], unsigned long long* s_part /*[NQ][NT/32]*/) {
@@ -83,7 +85,7 @@ __device__ __forceinline__ void fe_block_sum_u64(unsigned long long (&v)[NQ], un
 template <int SRC>
 __device__ __forceinline__ float4 fe_point_at(const PreArgs& a, int f, int i) {
     if (SRC == 0) {
-        const int v = i / a.w, u = i - v * a.w;
+        const int v = pre_row(a, i), u = i - v * a.w;
         const float z = (float)a.depth[(size_t)f * a.P + i] * a.depth_scale;
         return make_float4(z * a.xr[u], z * a.yr[v], z, 1.0f);
     } else {
@@ -98,6 +100,25 @@ __device__ __forceinline__ float fe_add_zeros(float s, bool any_plus_zero) {
     return (__float_as_uint(s) == 0x80000000u && any_plus_zero) ? 0.0f : s;
 }
 
+// One 32-record step of a voxel's run, called by a whole warp: lane j holds record j (match = it belongs to the voxel,
+// a = its point). Adds the leading matching records to the running sums IN ORDER and returns how many there were
+// (32 = the run may continue). An axis whose values are all +-0 folds without the 32-deep dependent chain.
+struct FeRun { float sx, sy, sz; int cnt; };
+__device__ __forceinline__ int fe_run_step(FeRun& r, bool match, float ax, float ay, float az) {
+    const unsigned int miss = __ballot_sync(FULL_MASK, !match);
+    const int nmatch = miss ? (__ffs(miss) - 1) : 32;
+    const unsigned int in = nmatch == 32 ? FULL_MASK : ((1u << nmatch) - 1u);
+    const unsigned int nzx = __ballot_sync(FULL_MASK, ax != 0.0f) & in, nzy = __ballot_sync(FULL_MASK, ay != 0.0f) & in,
+                       nzz = __ballot_sync(FULL_MASK, az != 0.0f) & in;
+    const unsigned int pzx = __ballot_sync(FULL_MASK, __float_as_uint(ax) == 0u) & in, pzy = __ballot_sync(FULL_MASK, __float_as_uint(ay) == 0u) & in,
+                       pzz = __ballot_sync(FULL_MASK, __float_as_uint(az) == 0u) & in;
+    if (nzx) { for (int j = 0; j < nmatch; ++j) r.sx += __shfl_sync(FULL_MASK, ax, j); } else r.sx = fe_add_zeros(r.sx, pzx != 0u);
+    if (nzy) { for (int j = 0; j < nmatch; ++j) r.sy += __shfl_sync(FULL_MASK, ay, j); } else r.sy = fe_add_zeros(r.sy, pzy != 0u);
+    if (nzz) { for (int j = 0; j < nmatch; ++j) r.sz += __shfl_sync(FULL_MASK, az, j); } else r.sz = fe_add_zeros(r.sz, pzz != 0u);
+    r.cnt += nmatch;
+    return nmatch;
+}
+
 template <int SRC, int NT>
 __global__ void __launch_bounds__(NT, 2048 / NT >= 2 ? (NT <= 512 ? 2 : 1) : 1) k_frontend(const FrontArgs a) {
     constexpr int NW = NT / 32;
@@ -108,6 +129,7 @@ __global__ void __launch_bounds__(NT, 2048 / NT >= 2 ? (NT <= 512 ? 2 : 1) : 1) 
     __shared__ FeFrame s_f;
     __shared__ unsigned int s_hist[256];
     __shared__ unsigned int s_base[256];
+    __shared__ unsigned int s_histA[4][256];   // C == 1: digit histograms of all passes, counted while the keys are generated
     __shared__ int s_w[NW + 1];
     __shared__ float s_mm[NW][6];
     __shared__ int s_wc[NW];
@@ -128,15 +150,19 @@ __global__ void __launch_bounds__(NT, 2048 / NT >= 2 ? (NT <= 512 ? 2 : 1) : 1) 
         int slice = (n_in + C - 1) / C;
         slice = (slice + 7) & ~7;
         const int s0 = min(n_in, r * slice), s1 = min(n_in, r * slice + slice);
+        unsigned char* s_mask = fe_dyn + NT * 16;
+        const bool use_mask = ((slice + TILE - 1) / TILE) * NT <= FE_MASK_BYTES;
 
         // ---- A1: survivors and min/max of this CTA's input slice ----
         {
             int cnt = 0;
             float mn[3] = {3.402823466e38f, 3.402823466e38f, 3.402823466e38f};
             float mx[3] = {-3.402823466e38f, -3.402823466e38f, -3.402823466e38f};
-            for (int first = s0 + tid * FE_ITEMS; first < s1; first += TILE) {
+            int it = 0;
+            for (int first = s0 + tid * FE_ITEMS; first < s1; first += TILE, ++it) {
                 float px[FE_ITEMS], py[FE_ITEMS], pz[FE_ITEMS];
                 const unsigned int keep = pre_points<SRC>(p, f, first, s1, px, py, pz);
+                if (use_mask) s_mask[it * NT + tid] = (unsigned char)keep;
                 cnt += __popc(keep);
 #pragma unroll
                 for (int k = 0; k < FE_ITEMS; ++k)
@@ -218,6 +244,11 @@ __global__ void __launch_bounds__(NT, 2048 / NT >= 2 ? (NT <= 512 ? 2 : 1) : 1) 
             continue;
         }
         const VoxelGeom g = s_f.g;
+        const int npass = (g.sort_bits + 7) / 8;
+        if (C == 1) {
+            for (int k = tid; k < 4 * 256; k += NT) (&s_histA[0][0])[k] = 0u;
+            __syncthreads();
+        }
 
         // ---- A2: ordered compaction of the slice. The divergent part only records WHICH inputs survive (u16 tile-local
         //      index, in order); the per-point work then runs dense, one survivor per thread, with coalesced stores ----
@@ -227,12 +258,16 @@ __global__ void __launch_bounds__(NT, 2048 / NT >= 2 ? (NT <= 512 ? 2 : 1) : 1) 
             int* kpp = a.kpp ? a.kpp + (size_t)f * a.P : nullptr;
             int run = s_f.base;
             unsigned long long hh[2] = {0ull, 0ull};
-            for (int t0 = s0; t0 < s1; t0 += TILE) {
+            int it = 0;
+            for (int t0 = s0; t0 < s1; t0 += TILE, ++it) {
                 const int first = t0 + tid * FE_ITEMS;
                 unsigned int keep = 0;
                 if (first < s1) {
-                    float px[FE_ITEMS], py[FE_ITEMS], pz[FE_ITEMS];
-                    keep = pre_points<SRC>(p, f, first, s1, px, py, pz);
+                    if (use_mask) keep = s_mask[it * NT + tid];
+                    else {
+                        float px[FE_ITEMS], py[FE_ITEMS], pz[FE_ITEMS];
+                        keep = pre_points<SRC>(p, f, first, s1, px, py, pz);
+                    }
                 }
                 int total;
                 int lp = block_excl_scan<NT>(__popc(keep), s_w, &total);
@@ -240,16 +275,31 @@ __global__ void __launch_bounds__(NT, 2048 / NT >= 2 ? (NT <= 512 ? 2 : 1) : 1) 
                 for (int k = 0; k < FE_ITEMS; ++k)
                     if (keep & (1u << k)) s_sel[lp++] = (unsigned short)(tid * FE_ITEMS + k);
                 __syncthreads();
-                for (int q = tid; q < total; q += NT) {
-                    const float4 pt = fe_point_at<SRC>(p, f, t0 + (int)s_sel[q]);
-                    const int pos = run + q;
-                    out[pos] = pt;
-                    const int idx = voxel_index(g, pt.x, pt.y, pt.z);
-                    const unsigned int sk = g.overflow_mode ? ((unsigned int)idx ^ 0x80000000u) : (unsigned int)idx;
-                    __stcg(bufA + pos, ((unsigned long long)sk << 32) | (unsigned int)pos);
-                    if (kpp) kpp[pos] = idx;
-                    hh[0] += hash_point((unsigned int)pos, pt.x, pt.y, pt.z);
-                    hh[1] += hash_index((unsigned int)pos, idx);
+                for (int qb = 0; qb < total; qb += NT) {   // uniform trip count: the warp votes below need every lane
+                    const int q = qb + tid;
+                    const bool valid = q < total;
+                    unsigned int sk = 0u;
+                    if (valid) {
+                        const float4 pt = fe_point_at<SRC>(p, f, t0 + (int)s_sel[q]);
+                        const int pos = run + q;
+                        out[pos] = pt;
+                        const int idx = voxel_index(g, pt.x, pt.y, pt.z);
+                        sk = g.overflow_mode ? ((unsigned int)idx ^ 0x80000000u) : (unsigned int)idx;
+                        __stcg(bufA + pos, ((unsigned long long)sk << 32) | (unsigned int)pos);
+                        if (kpp) kpp[pos] = idx;
+                        hh[0] += hash_point((unsigned int)pos, pt.x, pt.y, pt.z);
+                        hh[1] += hash_index((unsigned int)pos, idx);
+                    }
+                    if (C == 1) {   // one CTA owns the frame: every pass's digit histogram is order-independent, count it here
+#pragma unroll
+                        for (int ps = 0; ps < 4; ++ps) {
+                            if (ps < npass) {
+                                const unsigned int d = valid ? ((sk >> (8 * ps)) & 255u) : 256u;
+                                const unsigned int peers = __match_any_sync(FULL_MASK, d);
+                                if (valid && lane == __ffs(peers) - 1) atomicAdd(&s_histA[ps][d], (unsigned int)__popc(peers));
+                            }
+                        }
+                    }
                 }
                 run += total;
                 __syncthreads();
@@ -264,7 +314,6 @@ __global__ void __launch_bounds__(NT, 2048 / NT >= 2 ? (NT <= 512 ? 2 : 1) : 1) 
         cluster.sync();
 
         // ---- B: stable LSD radix sort of the frame's N records, 8-bit digits, significant key bits only ----
-        const int npass = (g.sort_bits + 7) / 8;
         int per = (N + C - 1) / C;
         per = (per + 255) & ~255;       // whole warp runs (8 items x 32 lanes): tiles of a range stay warp-aligned
         const int q0 = min(N, r * per), q1 = min(N, r * per + per);
@@ -273,15 +322,31 @@ __global__ void __launch_bounds__(NT, 2048 / NT >= 2 ? (NT <= 512 ? 2 : 1) : 1) 
             const unsigned long long* src = (pass & 1) ? bufB : bufA;
             unsigned long long* dst = (pass & 1) ? bufA : bufB;
             const int shift = 32 + pass * 8;
-            if (tid < 256) s_hist[tid] = 0;
-            __syncthreads();
-            for (int i = q0 + tid; i < q1; i += NT) atomicAdd(&s_hist[(unsigned int)(__ldcg(src + i) >> shift) & 255u], 1u);
-            __syncthreads();
-            cluster.sync();
+            if (C > 1) {   // digit histogram of this CTA's range: warp-private counters, equal digits of a warp aggregated by a vote
+                for (int d = lane; d < 256; d += 32) s_cnt[wid][d] = 0;
+                __syncwarp();
+                for (int i0 = q0 + wid * 32; i0 < q1; i0 += NT) {
+                    const int i = i0 + lane;
+                    const bool valid = i < q1;
+                    const unsigned int d = valid ? ((unsigned int)(__ldcg(src + i) >> shift) & 255u) : 256u;
+                    const unsigned int peers = __match_any_sync(FULL_MASK, d);
+                    if (valid && lane == __ffs(peers) - 1) s_cnt[wid][d] += (unsigned int)__popc(peers);
+                    __syncwarp();
+                }
+                __syncthreads();
+                if (tid < 256) {
+                    unsigned int t = 0;
+#pragma unroll 8
+                    for (int ww = 0; ww < NW; ++ww) t += s_cnt[ww][tid];
+                    s_hist[tid] = t;
+                }
+                __syncthreads();
+                cluster.sync();
+            }
             {   // digit d = tid: records of digit d in front of this CTA's = all smaller digits + digit d of lower ranks
                 unsigned int tot = 0, before = 0;
                 if (tid < 256) {
-                    if (C == 1) tot = s_hist[tid];
+                    if (C == 1) tot = s_histA[pass][tid];
                     else
                         for (int rr = 0; rr < C; ++rr) {
                             const unsigned int v = cluster.map_shared_rank(s_hist, rr)[tid];
@@ -429,40 +494,39 @@ __global__ void __launch_bounds__(NT, 2048 / NT >= 2 ? (NT <= 512 ? 2 : 1) : 1) 
                 }
                 vrun += total;
                 __syncthreads();
-                for (int d = wid; d < s_ndef; d += NW) {   // lane-parallel loads from the sorted records, in-order accumulation
+                for (int d = wid; d < s_ndef; d += NW) {   // a whole warp per deferred voxel: lane-parallel loads, in-order sums
                     const int lp = s_def_lp[d];
                     const unsigned int mykey = s_key[lp];
-                    float sx = s_px[lp], sy = s_py[lp], sz = s_pz[lp];
-                    int cnt = 1;
-                    int q = t0 + lp + 1;
-                    unsigned long long rec = (q + lane < N) ? __ldcg(keys + q + lane) : ~0ull;
-                    while (q < N) {
-                        const unsigned int kk = (q + lane < N) ? (unsigned int)(rec >> 32) : ~mykey;
-                        float ax = 0.f, ay = 0.f, az = 0.f;
-                        if (kk == mykey) { const float4 pt = __ldcg(pts + (unsigned int)rec); ax = pt.x; ay = pt.y; az = pt.z; }
-                        if (q + 32 + lane < N) rec = __ldcg(keys + q + 32 + lane);   // next step's records while this step is summed
-                        const unsigned int miss = __ballot_sync(FULL_MASK, kk != mykey);
-                        const int nmatch = miss ? (__ffs(miss) - 1) : 32;
-                        const unsigned int in = nmatch == 32 ? FULL_MASK : ((1u << nmatch) - 1u);
-                        // an axis whose nmatch values are all +-0 folds in O(1): no 32-deep dependent chain
-                        const unsigned int nzx = __ballot_sync(FULL_MASK, ax != 0.0f) & in, nzy = __ballot_sync(FULL_MASK, ay != 0.0f) & in,
-                                           nzz = __ballot_sync(FULL_MASK, az != 0.0f) & in;
-                        const unsigned int pzx = __ballot_sync(FULL_MASK, __float_as_uint(ax) == 0u) & in,
-                                           pzy = __ballot_sync(FULL_MASK, __float_as_uint(ay) == 0u) & in,
-                                           pzz = __ballot_sync(FULL_MASK, __float_as_uint(az) == 0u) & in;
-                        if (nzx) { for (int j = 0; j < nmatch; ++j) sx += __shfl_sync(FULL_MASK, ax, j); } else sx = fe_add_zeros(sx, pzx != 0u);
-                        if (nzy) { for (int j = 0; j < nmatch; ++j) sy += __shfl_sync(FULL_MASK, ay, j); } else sy = fe_add_zeros(sy, pzy != 0u);
-                        if (nzz) { for (int j = 0; j < nmatch; ++j) sz += __shfl_sync(FULL_MASK, az, j); } else sz = fe_add_zeros(sz, pzz != 0u);
-                        cnt += nmatch;
-                        if (nmatch < 32) break;
-                        q += 32;
+                    FeRun acc;
+                    acc.sx = s_px[lp]; acc.sy = s_py[lp]; acc.sz = s_pz[lp]; acc.cnt = 1;
+                    bool open = true;
+                    for (int l = lp + 1; open && l < n_here; l += 32) {   // the part of the run that is staged in shared memory
+                        const int i = l + lane;
+                        const bool m = i < n_here && s_key[i] == mykey;
+                        open = fe_run_step(acc, m, m ? s_px[i] : 0.f, m ? s_py[i] : 0.f, m ? s_pz[i] : 0.f) == min(32, n_here - l);
+                    }
+                    for (int q = t0 + n_here; open && q < N; q += 128) {    // the rest from the sorted records, 128 per round trip
+                        unsigned long long rec[4];
+                        bool m[4];
+                        float4 pt[4];
+#pragma unroll
+                        for (int j = 0; j < 4; ++j) {
+                            const int i = q + j * 32 + lane;
+                            rec[j] = i < N ? __ldcg(keys + i) : 0ull;
+                            m[j] = i < N && (unsigned int)(rec[j] >> 32) == mykey;
+                        }
+#pragma unroll
+                        for (int j = 0; j < 4; ++j) pt[j] = m[j] ? __ldcg(pts + (unsigned int)rec[j]) : make_float4(0.f, 0.f, 0.f, 0.f);
+#pragma unroll
+                        for (int j = 0; j < 4; ++j)
+                            if (open) open = fe_run_step(acc, m[j], pt[j].x, pt[j].y, pt[j].z) == 32;
                     }
                     if (lane == 0) {
-                        const float c = (float)cnt;
-                        const float cx = sx / c, cy = sy / c, cz = sz / c;
+                        const float c = (float)acc.cnt;
+                        const float cx = acc.sx / c, cy = acc.sy / c, cz = acc.sz / c;
                         const int vp = s_def_pos[d];
                         vox[vp] = make_float4(cx, cy, cz, 1.0f);
-                        if (vcount) vcount[vp] = cnt;
+                        if (vcount) vcount[vp] = acc.cnt;
                         hv[0] += hash_point((unsigned int)vp, cx, cy, cz);
                     }
                 }

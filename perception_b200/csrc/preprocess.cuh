@@ -18,6 +18,7 @@ struct PreArgs {
     int point_step, xoff, yoff, zoff;
     const int* n_in;             // per-frame input count (SRC 1) or NULL -> P
     int w, h;                    // image size (SRC 0)
+    unsigned int w_magic;        // ceil(2^32 / w) when i / w == __umulhi(i, w_magic) for every input index (P*w <= 2^32), else 0
     int P;                       // inputs per frame (input stride)
     int Pout;                    // output stride of pts (the handle's max_points)
     float fx, fy, cx, cy, depth_scale;
@@ -45,6 +46,11 @@ __device__ __forceinline__ bool pass_keep(const PreArgs& a, float x, float y, fl
     return true;
 }
 
+// image row of input i: an exact multiply-high instead of an integer division when the host proved it exact
+__device__ __forceinline__ int pre_row(const PreArgs& a, int i) {
+    return a.w_magic ? (int)__umulhi((unsigned int)i, a.w_magic) : i / a.w;
+}
+
 // the 8 inputs of one thread -> points and keep mask (shared by the counting and the writing kernel)
 template <int SRC>
 __device__ __forceinline__ unsigned int pre_points(const PreArgs& a, int f, int first, int n_in, float (&px)[PRE_ITEMS], float (&py)[PRE_ITEMS],
@@ -53,7 +59,8 @@ __device__ __forceinline__ unsigned int pre_points(const PreArgs& a, int f, int 
     if (SRC == 0) {
         const uint16_t* d = a.depth + (size_t)f * a.P;
         uint16_t dv[PRE_ITEMS];
-        if (first + PRE_ITEMS <= n_in && ((((size_t)f * a.P + first) & 7) == 0)) {
+        const bool full = first + PRE_ITEMS <= n_in;
+        if (full && ((((size_t)f * a.P + first) & 7) == 0)) {
             const uint4 raw = *reinterpret_cast<const uint4*>(d + first);
             dv[0] = raw.x & 0xffff; dv[1] = raw.x >> 16; dv[2] = raw.y & 0xffff; dv[3] = raw.y >> 16;
             dv[4] = raw.z & 0xffff; dv[5] = raw.z >> 16; dv[6] = raw.w & 0xffff; dv[7] = raw.w >> 16;
@@ -61,19 +68,31 @@ __device__ __forceinline__ unsigned int pre_points(const PreArgs& a, int f, int 
 #pragma unroll
             for (int k = 0; k < PRE_ITEMS; ++k) dv[k] = (first + k < n_in) ? d[first + k] : 0;
         }
-        int v = first / a.w, u = first - v * a.w;
-        float yrv = a.yr[min(v, a.h - 1)];
+        int v = pre_row(a, first), u = first - v * a.w;
+        // z = d*scale; x = z*((u-cx)/fx); y = z*((v-cy)/fy), all float, no contraction;
+        // the two quotients come from tables filled with exactly these float operations.
+        // depth-derived points are always finite: only the range tests remain
+        if (full && u + PRE_ITEMS <= a.w) {   // the usual case: 8 pixels of one image row, all inside the input
+            const float yrv = a.yr[v];
 #pragma unroll
-        for (int k = 0; k < PRE_ITEMS; ++k) {
-            // z = d*scale; x = z*((u-cx)/fx); y = z*((v-cy)/fy), all float, no contraction;
-            // the two quotients come from tables filled with exactly these float operations
-            const float z = (float)dv[k] * a.depth_scale;
-            px[k] = z * a.xr[u];
-            py[k] = z * yrv;
-            pz[k] = z;
-            // depth-derived points are always finite: only the range tests remain
-            if (first + k < n_in && !(z > a.z_hi || z < a.z_lo) && !(px[k] > a.x_hi || px[k] < a.x_lo)) keep |= 1u << k;
-            if (++u == a.w) { u = 0; ++v; yrv = a.yr[min(v, a.h - 1)]; }
+            for (int k = 0; k < PRE_ITEMS; ++k) {
+                const float z = (float)dv[k] * a.depth_scale;
+                px[k] = z * a.xr[u + k];
+                py[k] = z * yrv;
+                pz[k] = z;
+                if (!(z > a.z_hi || z < a.z_lo) && !(px[k] > a.x_hi || px[k] < a.x_lo)) keep |= 1u << k;
+            }
+        } else {
+            float yrv = a.yr[min(v, a.h - 1)];
+#pragma unroll
+            for (int k = 0; k < PRE_ITEMS; ++k) {
+                const float z = (float)dv[k] * a.depth_scale;
+                px[k] = z * a.xr[u];
+                py[k] = z * yrv;
+                pz[k] = z;
+                if (first + k < n_in && !(z > a.z_hi || z < a.z_lo) && !(px[k] > a.x_hi || px[k] < a.x_lo)) keep |= 1u << k;
+                if (++u == a.w) { u = 0; ++v; yrv = a.yr[min(v, a.h - 1)]; }
+            }
         }
     } else {
         const unsigned char* b = a.blob + (size_t)f * a.P * a.point_step;

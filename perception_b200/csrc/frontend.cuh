@@ -39,6 +39,7 @@ constexpr int FE_ITEMS = 8;      // inputs / sort records per thread and tile
 constexpr int FE_RITEMS = 4;     // sorted records per thread and reduce tile
 constexpr int FE_LONGRUN = 96;   // voxels with more points than this are summed by a whole warp (lane-parallel loads)
 constexpr int FE_MAXDEF = 64;    // >= 512*4/96 + 1 and >= 1024*4/96 + 1
+constexpr int FE_LOOK = 128;     // sorted records staged past a reduce tile so that the tile's last voxel can finish in shared memory
 
 struct FeXchg {          // what a CTA publishes to its cluster peers
     int count;           // survivors of its input slice
@@ -53,12 +54,16 @@ struct FeFrame {         // cluster-wide facts of the current frame, replicated 
 
 // dynamic shared memory: the three phases reuse one arena
 //   A1/A2   u16 tile-local input index of every survivor of the tile            NT*8*2  bytes
-//           + the keep masks A1 found, so A2 does not unproject and filter again   FE_MASK_BYTES
+//           + the tile's depth values (u16), + the keep masks A1 found, so A2       NT*8*2 + FE_MASK_BYTES
+//             does not unproject and filter again
 //   B       per-warp digit counters [NT/32][256] u32                            NT*32   bytes
-//   C2      key,x,y,z of the staged sorted records + u16 head positions         NT*4*18 bytes
+//   C2      key,x,y,z of the staged sorted records (+ look-ahead) + u16 heads   (NT*4+128)*16 + NT*4*2 bytes
 constexpr int FE_MASK_BYTES = 40960;   // keep masks of one input slice (1 byte per 8 inputs): a VGA frame on one CTA needs 38 400
 template <int NT>
-constexpr int fe_dyn_smem() { return (NT * 16 + FE_MASK_BYTES) > (NT * FE_RITEMS * 18) ? (NT * 16 + FE_MASK_BYTES) : (NT * FE_RITEMS * 18); }
+constexpr int fe_dyn_smem() {
+    return (NT * 32 + FE_MASK_BYTES) > ((NT * FE_RITEMS + FE_LOOK) * 16 + NT * FE_RITEMS * 2) ? (NT * 32 + FE_MASK_BYTES)
+                                                                                             : ((NT * FE_RITEMS + FE_LOOK) * 16 + NT * FE_RITEMS * 2);
+}
 
 template <int NT, int NQ>
 __device__ __forceinline__ void fe_block_sum_u64(unsigned long long (&v)[NQ], unsigned long long* s_part /*[NQ][NT/32]*/) {
@@ -95,9 +100,31 @@ __device__ __forceinline__ float4 fe_point_at(const PreArgs& a, int f, int i) {
     }
 }
 
+// the same from a depth value already staged in shared memory (SRC 0 only)
+__device__ __forceinline__ float4 fe_point_from_depth(const PreArgs& a, int i, unsigned short dv) {
+    const int v = pre_row(a, i), u = i - v * a.w;
+    const float z = (float)dv * a.depth_scale;
+    return make_float4(z * a.xr[u], z * a.yr[v], z, 1.0f);
+}
+
 // s += (a run of +-0 values), folded: the sum only changes when it is -0 and a +0 is added (IEEE round-to-nearest)
 __device__ __forceinline__ float fe_add_zeros(float s, bool any_plus_zero) {
     return (__float_as_uint(s) == 0x80000000u && any_plus_zero) ? 0.0f : s;
+}
+
+// lanes of the warp holding the same 8-bit digit (256 = "no record": never equal to a real digit's peers that matter).
+// Eight votes: MATCH.ANY costs ~2 cycles per DISTINCT value per SM (measured, tools/microbench/match_bench.cu), which
+// is several times more than this for the scattered digits of the later radix passes.
+__device__ __forceinline__ unsigned int fe_digit_peers(unsigned int d) {
+    unsigned int peers = __ballot_sync(FULL_MASK, d < 256u);
+    if (d >= 256u) peers = ~peers;
+#pragma unroll
+    for (int b = 0; b < 8; ++b) {
+        const unsigned int bit = (d >> b) & 1u;
+        const unsigned int bal = __ballot_sync(FULL_MASK, bit != 0u);
+        peers &= bit ? bal : ~bal;
+    }
+    return peers;
 }
 
 // One 32-record step of a voxel's run, called by a whole warp: lane j holds record j (match = it belongs to the voxel,
@@ -150,7 +177,7 @@ __global__ void __launch_bounds__(NT, 2048 / NT >= 2 ? (NT <= 512 ? 2 : 1) : 1) 
         int slice = (n_in + C - 1) / C;
         slice = (slice + 7) & ~7;
         const int s0 = min(n_in, r * slice), s1 = min(n_in, r * slice + slice);
-        unsigned char* s_mask = fe_dyn + NT * 16;
+        unsigned char* s_mask = fe_dyn + NT * 32;
         const bool use_mask = ((slice + TILE - 1) / TILE) * NT <= FE_MASK_BYTES;
 
         // ---- A1: survivors and min/max of this CTA's input slice ----
@@ -254,6 +281,7 @@ __global__ void __launch_bounds__(NT, 2048 / NT >= 2 ? (NT <= 512 ? 2 : 1) : 1) 
         //      index, in order); the per-point work then runs dense, one survivor per thread, with coalesced stores ----
         {
             unsigned short* s_sel = reinterpret_cast<unsigned short*>(fe_dyn);
+            unsigned short* s_dep = reinterpret_cast<unsigned short*>(fe_dyn + NT * 16);
             float4* out = p.pts + (size_t)f * p.Pout;
             int* kpp = a.kpp ? a.kpp + (size_t)f * a.P : nullptr;
             int run = s_f.base;
@@ -262,6 +290,13 @@ __global__ void __launch_bounds__(NT, 2048 / NT >= 2 ? (NT <= 512 ? 2 : 1) : 1) 
             for (int t0 = s0; t0 < s1; t0 += TILE, ++it) {
                 const int first = t0 + tid * FE_ITEMS;
                 unsigned int keep = 0;
+                if (SRC == 0 && first < s1) {   // the tile's depth values -> shared memory: the dense loop below gathers from there
+                    const uint16_t* dsrc = p.depth + (size_t)f * p.P;
+                    if (first + FE_ITEMS <= s1 && ((((size_t)f * p.P + first) & 7) == 0))
+                        *reinterpret_cast<uint4*>(s_dep + tid * FE_ITEMS) = *reinterpret_cast<const uint4*>(dsrc + first);
+                    else
+                        for (int k = 0; k < FE_ITEMS; ++k) s_dep[tid * FE_ITEMS + k] = (first + k < s1) ? dsrc[first + k] : (uint16_t)0;
+                }
                 if (first < s1) {
                     if (use_mask) keep = s_mask[it * NT + tid];
                     else {
@@ -280,7 +315,8 @@ __global__ void __launch_bounds__(NT, 2048 / NT >= 2 ? (NT <= 512 ? 2 : 1) : 1) 
                     const bool valid = q < total;
                     unsigned int sk = 0u;
                     if (valid) {
-                        const float4 pt = fe_point_at<SRC>(p, f, t0 + (int)s_sel[q]);
+                        const int sel = (int)s_sel[q];
+                        const float4 pt = SRC == 0 ? fe_point_from_depth(p, t0 + sel, s_dep[sel]) : fe_point_at<SRC>(p, f, t0 + sel);
                         const int pos = run + q;
                         out[pos] = pt;
                         const int idx = voxel_index(g, pt.x, pt.y, pt.z);
@@ -290,15 +326,10 @@ __global__ void __launch_bounds__(NT, 2048 / NT >= 2 ? (NT <= 512 ? 2 : 1) : 1) 
                         hh[0] += hash_point((unsigned int)pos, pt.x, pt.y, pt.z);
                         hh[1] += hash_index((unsigned int)pos, idx);
                     }
-                    if (C == 1) {   // one CTA owns the frame: every pass's digit histogram is order-independent, count it here
+                    if (C == 1 && valid) {   // one CTA owns the frame: every pass's digit histogram is order-independent, count it here
 #pragma unroll
-                        for (int ps = 0; ps < 4; ++ps) {
-                            if (ps < npass) {
-                                const unsigned int d = valid ? ((sk >> (8 * ps)) & 255u) : 256u;
-                                const unsigned int peers = __match_any_sync(FULL_MASK, d);
-                                if (valid && lane == __ffs(peers) - 1) atomicAdd(&s_histA[ps][d], (unsigned int)__popc(peers));
-                            }
-                        }
+                        for (int ps = 0; ps < 4; ++ps)
+                            if (ps < npass) atomicAdd(&s_histA[ps][(sk >> (8 * ps)) & 255u], 1u);
                     }
                 }
                 run += total;
@@ -322,23 +353,16 @@ __global__ void __launch_bounds__(NT, 2048 / NT >= 2 ? (NT <= 512 ? 2 : 1) : 1) 
             const unsigned long long* src = (pass & 1) ? bufB : bufA;
             unsigned long long* dst = (pass & 1) ? bufA : bufB;
             const int shift = 32 + pass * 8;
-            if (C > 1) {   // digit histogram of this CTA's range: warp-private counters, equal digits of a warp aggregated by a vote
-                for (int d = lane; d < 256; d += 32) s_cnt[wid][d] = 0;
-                __syncwarp();
-                for (int i0 = q0 + wid * 32; i0 < q1; i0 += NT) {
-                    const int i = i0 + lane;
-                    const bool valid = i < q1;
-                    const unsigned int d = valid ? ((unsigned int)(__ldcg(src + i) >> shift) & 255u) : 256u;
-                    const unsigned int peers = __match_any_sync(FULL_MASK, d);
-                    if (valid && lane == __ffs(peers) - 1) s_cnt[wid][d] += (unsigned int)__popc(peers);
-                    __syncwarp();
-                }
+            if (C > 1) {   // digit histogram of this CTA's range
+                if (tid < 256) s_hist[tid] = 0;
                 __syncthreads();
-                if (tid < 256) {
-                    unsigned int t = 0;
-#pragma unroll 8
-                    for (int ww = 0; ww < NW; ++ww) t += s_cnt[ww][tid];
-                    s_hist[tid] = t;
+                for (int i0 = q0 + tid; i0 < q1; i0 += 4 * NT) {
+                    unsigned long long k4[4];
+#pragma unroll
+                    for (int j = 0; j < 4; ++j) k4[j] = (i0 + j * NT < q1) ? __ldcg(src + i0 + j * NT) : 0ull;
+#pragma unroll
+                    for (int j = 0; j < 4; ++j)
+                        if (i0 + j * NT < q1) atomicAdd(&s_hist[(unsigned int)(k4[j] >> shift) & 255u], 1u);
                 }
                 __syncthreads();
                 cluster.sync();
@@ -375,7 +399,7 @@ __global__ void __launch_bounds__(NT, 2048 / NT >= 2 ? (NT <= 512 ? 2 : 1) : 1) 
                     const int i = t0 + wid * (32 * FE_ITEMS) + k * 32 + lane;
                     const bool valid = i < q1;
                     const unsigned int d = valid ? ((unsigned int)(key[k] >> shift) & 255u) : 256u;
-                    const unsigned int peers = __match_any_sync(FULL_MASK, d);
+                    const unsigned int peers = fe_digit_peers(d);
                     const int leader = __ffs(peers) - 1;
                     unsigned int before = 0;
                     if (valid && lane == leader) { before = s_cnt[wid][d]; s_cnt[wid][d] = before + __popc(peers); }
@@ -437,10 +461,11 @@ __global__ void __launch_bounds__(NT, 2048 / NT >= 2 ? (NT <= 512 ? 2 : 1) : 1) 
         //      out of shared memory in sorted (= ascending point index) order and the centroid stores are coalesced ----
         {
             unsigned int* s_key = reinterpret_cast<unsigned int*>(fe_dyn);
-            float* s_px = reinterpret_cast<float*>(fe_dyn) + RTILE;
-            float* s_py = s_px + RTILE;
-            float* s_pz = s_py + RTILE;
-            unsigned short* s_head = reinterpret_cast<unsigned short*>(s_pz + RTILE);
+            constexpr int RSTAGE = RTILE + FE_LOOK;
+            float* s_px = reinterpret_cast<float*>(fe_dyn) + RSTAGE;
+            float* s_py = s_px + RSTAGE;
+            float* s_pz = s_py + RSTAGE;
+            unsigned short* s_head = reinterpret_cast<unsigned short*>(s_pz + RSTAGE);
             const float4* pts = p.pts + (size_t)f * p.Pout;
             float4* vox = a.vox + (size_t)f * a.P;
             int* vcount = a.vcount ? a.vcount + (size_t)f * a.P : nullptr;
@@ -448,14 +473,22 @@ __global__ void __launch_bounds__(NT, 2048 / NT >= 2 ? (NT <= 512 ? 2 : 1) : 1) 
             unsigned long long hv[1] = {0ull};
             for (int t0 = q0; t0 < q1; t0 += RTILE) {
                 const int n_here = min(RTILE, q1 - t0);
+                const int n_stage = min(n_here + FE_LOOK, N - t0);   // look-ahead records: the tile's last voxel usually ends in them
+                {
+                    unsigned long long rec[FE_RITEMS + 1];
 #pragma unroll
-                for (int k = 0; k < FE_RITEMS; ++k) {
-                    const int l = k * NT + tid;
-                    if (l < n_here) {
-                        const unsigned long long rec = __ldcg(keys + t0 + l);
-                        const float4 pt = __ldcg(pts + (unsigned int)rec);
-                        s_key[l] = (unsigned int)(rec >> 32);
-                        s_px[l] = pt.x; s_py[l] = pt.y; s_pz[l] = pt.z;
+                    for (int k = 0; k <= FE_RITEMS; ++k) {
+                        const int l = k * NT + tid;
+                        rec[k] = (l < n_stage && (k < FE_RITEMS || tid < FE_LOOK)) ? __ldcg(keys + t0 + l) : 0ull;
+                    }
+#pragma unroll
+                    for (int k = 0; k <= FE_RITEMS; ++k) {
+                        const int l = k * NT + tid;
+                        if (l < n_stage && (k < FE_RITEMS || tid < FE_LOOK)) {
+                            const float4 pt = __ldcg(pts + (unsigned int)rec[k]);
+                            s_key[l] = (unsigned int)(rec[k] >> 32);
+                            s_px[l] = pt.x; s_py[l] = pt.y; s_pz[l] = pt.z;
+                        }
                     }
                 }
                 const unsigned int prev_key = t0 > 0 ? (unsigned int)(__ldcg(keys + t0 - 1) >> 32) : 0u;
@@ -475,9 +508,11 @@ __global__ void __launch_bounds__(NT, 2048 / NT >= 2 ? (NT <= 512 ? 2 : 1) : 1) 
                 __syncthreads();
                 for (int v = tid; v < total; v += NT) {
                     const int lp = s_head[v];
-                    const int end = (v + 1 < total) ? (int)s_head[v + 1] : n_here;
+                    int end = n_here;
+                    if (v + 1 < total) end = (int)s_head[v + 1];
+                    else { const unsigned int mk = s_key[lp]; while (end < n_stage && s_key[end] == mk) ++end; }
                     const int pos = vrun + v;
-                    if ((v + 1 == total && t0 + n_here < N) || end - lp > FE_LONGRUN) {
+                    if ((end == n_stage && t0 + n_stage < N) || end - lp > FE_LONGRUN) {
                         // may continue past the tile (only the last voxel can), or long (e.g. the origin voxel that collects
                         // every zero-depth pixel): a whole warp takes it
                         const int d = atomicAdd(&s_ndef, 1);
@@ -500,12 +535,12 @@ __global__ void __launch_bounds__(NT, 2048 / NT >= 2 ? (NT <= 512 ? 2 : 1) : 1) 
                     FeRun acc;
                     acc.sx = s_px[lp]; acc.sy = s_py[lp]; acc.sz = s_pz[lp]; acc.cnt = 1;
                     bool open = true;
-                    for (int l = lp + 1; open && l < n_here; l += 32) {   // the part of the run that is staged in shared memory
+                    for (int l = lp + 1; open && l < n_stage; l += 32) {   // the part of the run that is staged in shared memory
                         const int i = l + lane;
-                        const bool m = i < n_here && s_key[i] == mykey;
-                        open = fe_run_step(acc, m, m ? s_px[i] : 0.f, m ? s_py[i] : 0.f, m ? s_pz[i] : 0.f) == min(32, n_here - l);
+                        const bool m = i < n_stage && s_key[i] == mykey;
+                        open = fe_run_step(acc, m, m ? s_px[i] : 0.f, m ? s_py[i] : 0.f, m ? s_pz[i] : 0.f) == min(32, n_stage - l);
                     }
-                    for (int q = t0 + n_here; open && q < N; q += 128) {    // the rest from the sorted records, 128 per round trip
+                    for (int q = t0 + n_stage; open && q < N; q += 128) {    // the rest from the sorted records, 128 per round trip
                         unsigned long long rec[4];
                         bool m[4];
                         float4 pt[4];

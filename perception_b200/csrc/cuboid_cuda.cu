@@ -76,6 +76,8 @@ struct cuboid_handle {
     int taps = 1;
     // fused front end (frontend.cuh): one thread-block cluster per frame, persistent over the chunk
     int frontend = 1; int fe_cluster = 1; int fe_threads = 512; int fe_slots = 0; unsigned long long* d_fe_keys = nullptr;
+    // host-buffer batches: sub-chunks run end to end on a few streams, so copies, front end and ICP of different sub-chunks overlap
+    static constexpr int NPIPE = 4; cudaStream_t pipe[NPIPE] = {}; cudaEvent_t pipe_done[NPIPE] = {}; unsigned long long* d_pipe_keys[NPIPE] = {}; int pipeline = 1;
     int64_t launches = 0;
     float stage_ms[5] = {0, 0, 0, 0, 0};
     std::string last_error;
@@ -196,8 +198,9 @@ int run_chunk(cuboid_handle* h, const ChunkIn& in, int nf, cuboid_frame_result* 
               bool skip_pre = false, bool skip_vox = false, bool skip_plane = false, bool skip_cluster = false,
               const int* d_triplets = nullptr, int n_triplets = 0, const float* guesses_override = nullptr, int n_guess_override = 0,
               int guess_mode_override = 0, int* trace_corr = nullptr, float* trace_T = nullptr, int cap_trace = 0,
-              float4* aligned = nullptr, bool force_cluster = false, int f0 = 0, cudaEvent_t* evs = nullptr) {
-    cudaStream_t st = h->stream;
+              float4* aligned = nullptr, bool force_cluster = false, int f0 = 0, cudaEvent_t* evs = nullptr,
+              cudaStream_t st_override = nullptr, unsigned long long* fe_keys_override = nullptr) {
+    cudaStream_t st = st_override ? st_override : h->stream;
     const cuboid_params& p = h->p;
     if (!evs) evs = h->ev;
     // per-frame buffers of the sub-range starting at frame f0 of the resident chunk (d_res is already offset by the caller)
@@ -224,7 +227,7 @@ int run_chunk(cuboid_handle* h, const ChunkIn& in, int nf, cuboid_frame_result* 
         a.x_lo = limit_lo(p.pass_x_min); a.x_hi = limit_hi(p.pass_x_max);
         a.pts = b_pts; a.res = d_res; a.scr = b_scr; a.n_frames = nf; a.Pout = h->P;
         if (in.in_stride > h->P) return CUBOID_E_CAPACITY;
-        fa.keys = h->d_fe_keys; fa.kpp = h->taps ? b_kpp : nullptr; fa.vox = b_vox; fa.vcount = h->taps ? b_vcount : nullptr;
+        fa.keys = fe_keys_override ? fe_keys_override : h->d_fe_keys; fa.kpp = h->taps ? b_kpp : nullptr; fa.vox = b_vox; fa.vcount = h->taps ? b_vcount : nullptr;
         fa.inv_leaf = 1.0f / p.leaf; fa.P = h->P; fa.n_frames = nf;
         cudaLaunchConfig_t cfg{};
         cudaLaunchAttribute at[1];
@@ -322,13 +325,15 @@ int run_chunk(cuboid_handle* h, const ChunkIn& in, int nf, cuboid_frame_result* 
         const float* gs = guesses_override ? guesses_override : (h->have_guesses ? h->d_guesses : nullptr);
         const int ng = guesses_override ? n_guess_override : (h->have_guesses ? h->n_guess : 1);
         const int gm = guesses_override ? guess_mode_override : h->guess_mode;
-        CKS(h, ensure_icp_scratch(h, std::max(nf, 1), ng));
+        CKS(h, ensure_icp_scratch(h, std::max(f0 + nf, 1), ng));   // callers that run sub-chunks concurrently size it up front
         IcpArgs a{};
-        a.remain = h->d_remain; a.idx_sorted = h->d_idx_sorted; a.offsets = h->d_offsets;
+        a.remain = b_remain; a.idx_sorted = b_idx_sorted; a.offsets = b_offsets;
         a.tmpl = h->d_tmpl[tmpl_slot]; a.tmpl_orig = h->d_tmpl_orig[tmpl_slot]; a.T = h->tmpl_n[tmpl_slot]; a.Tpad = h->tmpl_pad[tmpl_slot];
         a.nodes = h->d_boxes[tmpl_slot]; a.nleaf = h->tmpl_nleaf[tmpl_slot]; a.nnodes = h->tmpl_nnodes[tmpl_slot];
         a.guesses = gs; a.n_guess = ng; a.guess_mode = gm;
-        a.cur = h->d_cur; a.corr = h->d_corr; a.cd = h->d_cd; a.order = h->d_order; a.out = h->d_icp_out; a.res = d_res;
+        const size_t oG = (size_t)f0 * ng * h->M;
+        IcpOut* b_out = h->d_icp_out + (size_t)f0 * CUBOID_MAX_CLUSTERS * ng;
+        a.cur = h->d_cur + oG; a.corr = h->d_corr + oG; a.cd = h->d_cd + oG; a.order = h->d_order + oG; a.out = b_out; a.res = d_res;
         a.P = h->P; a.M = h->M; a.KC = h->KC; a.max_iter = p.icp_max_iter;
         a.rot_thr = 1.0 - p.icp_tf_eps; a.trans_thr = p.icp_tf_eps; a.rel_mse = p.icp_rel_mse; a.abs_thr = 1e-12;
         const size_t box_bytes = (size_t)a.nnodes * 16;
@@ -340,7 +345,7 @@ int run_chunk(cuboid_handle* h, const ChunkIn& in, int nf, cuboid_frame_result* 
         const size_t dyn = box_bytes + (a.resident ? (size_t)a.Tpad * 12 : 0);
         k_icp<<<dim3(ng, CUBOID_MAX_CLUSTERS, nf), ICP_THREADS, dyn, st>>>(a);
         const int tot = nf * CUBOID_MAX_CLUSTERS;
-        k_icp_select<<<(tot + 127) / 128, 128, 0, st>>>(h->d_icp_out, d_res, nf, ng, p.icp_fitness_gate, h->d_cur, h->M, h->d_offsets,
+        k_icp_select<<<(tot + 127) / 128, 128, 0, st>>>(b_out, d_res, nf, ng, p.icp_fitness_gate, h->d_cur + oG, h->M, b_offsets,
                                                      h->KC, aligned);
         h->launches += 2;
         CK(h, cudaGetLastError());
@@ -500,6 +505,15 @@ int cuboid_create(cuboid_handle** out, const cuboid_params* p, int device, int m
         if (h->fe_slots < 1) { h->last_error = "k_frontend: no resident cluster configuration"; fprintf(stderr, "cuboid_create: %s\n", h->last_error.c_str()); return fail(CUBOID_E_CUDA); }
         h->fe_slots = std::min(h->fe_slots, std::max(1, h->B));
         CA(dalloc(h, &h->d_fe_keys, (size_t)h->fe_slots * 2 * h->P));
+        const char* ep = std::getenv("CUBOID_PIPELINE"); if (ep) h->pipeline = atoi(ep) ? 1 : 0;
+        if (h->pipeline && h->B > h->sub_batch) {
+            const int pslots = std::min(h->fe_slots, std::min(h->sub_batch, h->B));
+            for (int i = 0; i < cuboid_handle::NPIPE; ++i) {
+                if (cudaStreamCreateWithFlags(&h->pipe[i], cudaStreamNonBlocking) != cudaSuccess) return fail(CUBOID_E_CUDA);
+                if (cudaEventCreateWithFlags(&h->pipe_done[i], cudaEventDisableTiming) != cudaSuccess) return fail(CUBOID_E_CUDA);
+                CA(dalloc(h, &h->d_pipe_keys[i], (size_t)pslots * 2 * h->P));
+            }
+        }
     }
     CA(dalloc(h, &h->d_work, (size_t)2));
     if (cudaMemset(h->d_work, 0, 16) != cudaSuccess) return fail(CUBOID_E_CUDA);
@@ -525,6 +539,11 @@ int cuboid_destroy(cuboid_handle* h) {
     for (auto& t : h->d_tmpl_orig) if (t) cudaFree(t);
     for (auto& e : h->ev) if (e) cudaEventDestroy(e);
     for (auto& e : h->ev_pool) if (e) cudaEventDestroy(e);
+    for (int i = 0; i < cuboid_handle::NPIPE; ++i) {
+        if (h->pipe[i]) { cudaStreamSynchronize(h->pipe[i]); cudaStreamDestroy(h->pipe[i]); }
+        if (h->pipe_done[i]) cudaEventDestroy(h->pipe_done[i]);
+        if (h->d_pipe_keys[i]) cudaFree(h->d_pipe_keys[i]);
+    }
     if (h->copy_stream) cudaStreamDestroy(h->copy_stream);
     if (h->stream) cudaStreamDestroy(h->stream);
     delete h;
@@ -858,9 +877,38 @@ static int process_frames(cuboid_handle* h, const uint16_t* depth, bool on_devic
         CK(h, cudaEventCreate(&e));
         h->ev_pool.push_back(e);
     }
+    const bool piped = !on_device && h->pipeline && h->frontend && h->pipe[0];
+    if (stages & 8) CKS(h, ensure_icp_scratch(h, std::min(h->B, n_frames), h->have_guesses ? h->n_guess : 1));
     for (int base = 0; base < n_frames; base += h->B) {
         const int nf = std::min(h->B, n_frames - base);
         const int nsub = (nf + SUB - 1) / SUB;
+        if (piped) {
+            // Every sub-chunk runs ALL its stages on one of NPIPE streams as soon as its depth copy has landed: the copy of
+            // sub-chunk k+1, the front end of k and the ICP of k-1 overlap, and the GPU is busy from the first copy on.
+            for (int sb = 0; sb < nsub; ++sb) {
+                const int f0 = sb * SUB, n = std::min(SUB, nf - f0);
+                CK(h, cudaMemcpyAsync(h->d_depth + (size_t)f0 * per, depth + (size_t)(base + f0) * per, sizeof(uint16_t) * (size_t)n * per,
+                                      cudaMemcpyHostToDevice, h->copy_stream));
+                CK(h, cudaEventRecord(h->ev_pool[(size_t)sb * 6 + 5], h->copy_stream));
+            }
+            CK(h, cudaEventRecord(h->ev[0], h->stream));   // whatever the main stream still has queued (work counters, previous chunk)
+            for (int i = 0; i < cuboid_handle::NPIPE; ++i) CK(h, cudaStreamWaitEvent(h->pipe[i], h->ev[0], 0));
+            for (int sb = 0; sb < nsub; ++sb) {
+                const int f0 = sb * SUB, n = std::min(SUB, nf - f0), pi = sb % cuboid_handle::NPIPE;
+                ChunkIn in;
+                in.w = w; in.hgt = hgt; in.in_stride = per; in.depth = h->d_depth + (size_t)f0 * per;
+                CK(h, cudaStreamWaitEvent(h->pipe[pi], h->ev_pool[(size_t)sb * 6 + 5], 0));
+                CKS(h, run_chunk(h, in, n, h->d_res + base + f0, stages, tmpl_slot, false, false, false, false, nullptr, 0, nullptr, 0, 0,
+                                 nullptr, nullptr, 0, nullptr, false, f0, &h->ev_pool[(size_t)sb * 6], h->pipe[pi], h->d_pipe_keys[pi]));
+            }
+            for (int i = 0; i < cuboid_handle::NPIPE; ++i) {
+                CK(h, cudaEventRecord(h->pipe_done[i], h->pipe[i]));
+                CK(h, cudaStreamWaitEvent(h->stream, h->pipe_done[i], 0));
+            }
+            CK(h, cudaStreamSynchronize(h->stream));
+            h->last_chunk_base = base; h->last_chunk_frames = nf;
+            continue;   // per-stage times are not defined when stages of different sub-chunks overlap: stage_ms stays 0
+        }
         if (!on_device)
             for (int sb = 0; sb < nsub; ++sb) {
                 const int f0 = sb * SUB, n = std::min(SUB, nf - f0);

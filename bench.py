@@ -11,8 +11,9 @@ Contract (driver): python bench.py --gpus N --steps K --warmup W  [--impl refere
     every frame and device->host copy of every frame's result inside the timed region;
   * `roofline`: the dominant kernel (k_icp, FP32-pipe bound: un-fused FMUL/FADD) — algorithmic
     flops from the per-frame results (8*S*T per nearest-neighbour pass) over its CUDA-event time, against the
-    un-fused FP32 peak measured in the same run; `roofline_hbm` is the same for the HBM-bound preprocess kernel
-    against MEASURED_PEAKS.json;
+    un-fused FP32 peak measured in the same run; `roofline_hbm` is the same for the HBM-bound fused front end
+    (k_frontend: unproject + passthrough + voxel grid in one kernel, algorithmic bytes 2*P + 32*N + 16*V per frame)
+    against MEASURED_PEAKS.json; its `traffic` is the dram__bytes figure of the committed ncu capture (profiles/);
   * `cpu_baseline`: the CPU oracle (restatement of the PCL path, 1 thread like the reference node) on a bounded
     sample of the same frames;
   * --impl reference: that CPU restatement on all host cores (the real PCL/ROS reference cannot be built
@@ -314,6 +315,16 @@ def main():
         n_vox = sum(r.n_voxels for r in res)
         vox_bytes = 16.0 * n_pts + 16.0 * n_vox
         vox_s = stage["voxel"] / 1e3 / args.steps
+        fused = vox_s * 50 < pre_s          # the fused front end reports its whole time under "preprocess"
+        fe_bytes = pre_bytes + (vox_bytes if fused else 0.0)
+        fe_gbs = fe_bytes / pre_s / 1e9 if pre_s > 0 else 0.0
+        traffic = None
+        try:   # per-launch DRAM bytes of the same launch under `ncu --set full` (profiles/README.md says which capture)
+            tj = json.load(open(os.path.join(ROOT, "profiles", "frontend_traffic.json")))
+            if tj.get("frames_per_launch") == min(cc.max_batch, F) and tj.get("workload") == args.workload:
+                traffic = tj["dram_bytes_per_launch"]
+        except Exception:
+            pass
         line = {
             "metric": METRIC, "value": total_frames * args.steps / t_dev, "unit": "frames/s", "n_gpus": world, "steps": args.steps,
             "warmup": args.warmup, "ms_per_step": 1e3 * t_dev / args.steps, "higher_is_better": True, "scaling": "weak",
@@ -335,11 +346,13 @@ def main():
                          "culled_fraction": 1.0 - work_eval / max(work_brute, 1),
                          "note": "frac > 1 because exact culling (BVH + bit-exact lower bound, DESIGN.md §4) skips pairs that provably cannot "
                                  "win; results are bit-identical to the brute-force scan (CUBOID_OPT_ICP_CULL=0), see tests"},
-            "roofline_hbm": {"kernel": "k_preprocess", "bound": "hbm", "achieved": pre_gbs, "peak": peaks.get("hbm_gbs"), "unit": "GB/s",
-                             "frac": pre_gbs / peaks.get("hbm_gbs") if peaks.get("hbm_gbs") else None, "traffic": None,
-                             "peak_source": peak_src, "ms_per_launch": 1e3 * pre_s / n_chunks, "algorithmic_bytes_per_step": pre_bytes},
+            "roofline_hbm": {"kernel": "k_frontend" if fused else "k_preprocess", "bound": "hbm", "achieved": fe_gbs, "peak": peaks.get("hbm_gbs"),
+                             "unit": "GB/s", "frac": fe_gbs / peaks.get("hbm_gbs") if peaks.get("hbm_gbs") else None, "traffic": traffic,
+                             "peak_source": peak_src, "launches_per_step": n_chunks, "ms_per_launch": 1e3 * pre_s / n_chunks,
+                             "algorithmic_bytes_per_step": fe_bytes,
+                             "algorithmic_bytes_per_frame": "2*P + 16*N (unproject + passthrough) + 16*N + 16*V (voxel grid)" if fused
+                             else "2*P + 16*N (unproject + passthrough)"},
             "stages_ms_per_step": {k: v / args.steps for k, v in stage.items()},
-            "voxel_stage": {"achieved_gbs": vox_bytes / vox_s / 1e9 if vox_s > 0 else 0.0, "algorithmic_bytes_per_step": vox_bytes},
             "wall_ms_per_step": 1e3 * t_wall / args.steps,
             "frame_stats": {"mean_points": n_pts / F, "mean_voxels": n_vox / F, "mean_remain": sum(r.n_remain for r in res) / F,
                             "mean_icp_iterations": float(np.mean([r.cluster[0].iterations for r in res if r.n_clusters > 0] or [0])),

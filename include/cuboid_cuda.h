@@ -138,6 +138,38 @@ int cuboid_preprocess(cuboid_handle* h, const void* pts, int point_step, int xof
 int cuboid_segment_plane(cuboid_handle* h, const float* xyzw, int n, const int32_t* triplets, int n_triplets,
                          float coeff_out[4], int32_t* inlier_idx_out, int* n_inl, int32_t* inlier_pre_out,
                          int* n_inl_pre, float* remain_xyzw_out, int* n_remain, int* iters_run, int* plane_found);
+/* surface_normal_estimation node (cuboid_detection/src/surface_normal_estimation.cpp): the coarse cuboid pose the
+ * reference meant as ICP's initial guess (icp.cpp:165-167, 227). Three SACSegmentation runs on the shrinking cloud
+ * (:196-205): plane 0 with SACMODEL_PERPENDICULAR_PLANE, planes 1 and 2 with SACMODEL_PARALLEL_PLANE, setAxis(axis) =
+ * the table normal of ground_plane_segmentation, setEpsAngle(eps_angle = 0.1), optimize = true, 1000 iterations,
+ * distance_threshold from launch/surface_normal_estimation.launch (0.015); pcl::compute3DCentroid of each plane;
+ * then the ordering, handedness fix, projection and pose of :207-237 / :64-96. */
+typedef struct {
+    float coeff[3][4];      /* plane i in segmentation order (published as normal_z/y/x after the ordering) */
+    float midpoint[3][3];   /* pcl::compute3DCentroid of plane i's inliers */
+    int32_t n_plane[3];     /* inliers of plane i */
+    int32_t found[3];
+    int32_t n_in[3];        /* points the i-th segmentation ran on */
+    int32_t n_left;         /* points left after the third plane */
+    int32_t order[3];       /* segmentation index of normals[0], [1], [2] after the point-count ordering (:207-221) */
+    float Rt[16];           /* :228-237 row-major, columns (normals[2], normals[1], normals[0], centroid) */
+    double pose7[7];        /* geometry_msgs/Pose published on /surface_segmentation/pose: x y z qx qy qz qw */
+} cuboid_surface_result;
+int cuboid_surface_normals(cuboid_handle* h, const float* xyzw, int n, const float axis[3], double eps_angle,
+                           double distance_threshold, cuboid_surface_result* out);
+/* the host arithmetic of the same callback on already-segmented planes (coeff 3x4, midpoint 3x3) */
+void cuboid_surface_pose(const float coeff[12], const float midpoint[9], const int32_t n_plane[3], float Rt[16],
+                         int32_t order[3], double pose7[7]);
+/* bbox_filter node (cuboid_detection/src/bbox_filter.cpp:30-51 within_bbox, :89-103 ExtractIndices): keeps, in order, the
+ * points whose projection through the 3x4 CameraInfo matrix P (row-major doubles, bbox_filter.cpp:54-66) lies strictly
+ * inside the rectangle bbox = (x1, y1, x2, y2) of color_object_detection/Rectangle (bbox_filter.cpp:68-74).
+ * idx_out / xyzw_out (cap entries) may be NULL. */
+int cuboid_bbox_filter(cuboid_handle* h, const void* pts, int point_step, int xoff, int yoff, int zoff, int n,
+                       const double P[12], const int32_t bbox[4], int32_t* idx_out, float* xyzw_out, int cap, int* n_out);
+/* The same predicate fused into the extraction of cuboid_process_* / cuboid_segment_plane, i.e. the node chain
+ * ground_plane_segmentation -> bbox_filter -> iterative_closest_point (launch/iterative_closest_point.launch:15).
+ * enable = 0 (default) restores the reference's default wiring (ICP on /ground_plane_segmentation/points). */
+int cuboid_set_bbox_filter(cuboid_handle* h, const double P[12], const int32_t bbox[4], int enable);
 /* search::KdTree + EuclideanClusterExtraction (opd.cpp:346-362). idx_sorted_out: n entries;
  * offsets_out: cap_clusters+1 entries. Clusters ordered size-descending, ties by smallest member. */
 int cuboid_cluster(cuboid_handle* h, const float* xyzw, int n, int32_t* idx_sorted_out, int32_t* offsets_out,

@@ -522,14 +522,36 @@ struct SacOut {
     std::vector<int32_t> triplets;
 };
 
-void select_within(const P4* p, int n, const float c[4], double thr, std::vector<int32_t>& out) {
+/* SACMODEL_PERPENDICULAR_PLANE / SACMODEL_PARALLEL_PLANE (surface_normal_estimation.cpp:118-123): the plane model plus
+ * isModelValid(). type 0 = SACMODEL_PLANE, 1 = perpendicular plane (normal within eps of the axis, either sense),
+ * 2 = parallel plane (normal within eps of perpendicular to the axis). [PCL-recall]: coeff[3] = 0; coeff.normalize();
+ * perpendicular: min(angle, pi - angle) > eps_angle_ -> invalid; parallel: |axis . coeff| > sin_angle_ -> invalid.
+ * Canonical form of the perpendicular test (shared with the CUDA path): |cos(angle)| < cos(eps) in double, with
+ * cos(angle) = (float)(axis . coeff) / sqrtf(|axis|^2 * |coeff|^2); it differs from acos() + compare only when the angle
+ * is within an ulp of eps. */
+struct SacModel { int type = 0; float axis[3] = {0, 0, 0}; double eps = 0.0; };
+bool model_valid(const SacModel* m, const float c[4]) {
+    if (!m || m->type == 0 || !(m->eps > 0.0)) return true;
+    const float n2 = dot4(c[0], c[1], c[2], 0.0f, c[0], c[1], c[2], 0.0f);
+    const float nrm = std::sqrt(n2);
+    const float q0 = c[0] / nrm, q1 = c[1] / nrm, q2 = c[2] / nrm;
+    const float d = dot4(m->axis[0], m->axis[1], m->axis[2], 0.0f, q0, q1, q2, 0.0f);
+    if (m->type == 2) return !((double)std::fabs(d) > std::fabs(std::sin(m->eps)));
+    const float nn = dot4(m->axis[0], m->axis[1], m->axis[2], 0.0f, m->axis[0], m->axis[1], m->axis[2], 0.0f) * dot4(q0, q1, q2, 0.0f, q0, q1, q2, 0.0f);
+    double rad = (double)(d / std::sqrt(nn));
+    if (rad < -1.0) rad = -1.0; else if (rad > 1.0) rad = 1.0;
+    return !(std::fabs(rad) < std::cos(m->eps));
+}
+
+void select_within(const P4* p, int n, const float c[4], double thr, std::vector<int32_t>& out, const SacModel* m = nullptr) {
     out.clear();
+    if (!model_valid(m, c)) return;   /* SampleConsensusModel{Perpendicular,Parallel}Plane::selectWithinDistance */
     for (int i = 0; i < n; ++i) if ((double)plane_dist(c, p[i]) < thr) out.push_back(i);
 }
 
 /* pcl::RandomSampleConsensus::computeModel + SACSegmentation::segment tail (A.3) */
 void sac_plane(const P4* p, int n, double thr, int max_iter, double prob, uint32_t seed, int refine, int mode,
-               const int32_t* trip_in, int n_trip_in, SacOut& o) {
+               const int32_t* trip_in, int n_trip_in, SacOut& o, const SacModel* model = nullptr) {
     o = SacOut();
     if (n < 3) return;
     MT19937 rng(seed);
@@ -566,8 +588,9 @@ void sac_plane(const P4* p, int n, double thr, int max_iter, double prob, uint32
         o.triplets.push_back(s[0]); o.triplets.push_back(s[1]); o.triplets.push_back(s[2]);
         float c[4];
         if (!plane_from_sample(p, s, c)) { ++skipped; continue; }
-        int cnt = 0;
-        for (int i = 0; i < n; ++i) if ((double)plane_dist(c, p[i]) < thr) ++cnt;
+        int cnt = 0;   /* countWithinDistance: 0 for a model that fails isModelValid, still an iteration */
+        if (model_valid(model, c))
+            for (int i = 0; i < n; ++i) if ((double)plane_dist(c, p[i]) < thr) ++cnt;
         if (cnt > best) {
             best = cnt;
             std::memcpy(best_c, c, 16);
@@ -588,10 +611,10 @@ void sac_plane(const P4* p, int n, double thr, int max_iter, double prob, uint32
     if (!have_model) return;
     o.found = true;
     std::memcpy(o.coeff_pre, best_c, 16);
-    select_within(p, n, best_c, thr, o.inliers_pre);
+    select_within(p, n, best_c, thr, o.inliers_pre, model);
     if (refine) {
         plane_refine(p, o.inliers_pre, best_c, o.coeff, mode);
-        select_within(p, n, o.coeff, thr, o.inliers);
+        select_within(p, n, o.coeff, thr, o.inliers, model);
     } else {
         std::memcpy(o.coeff, best_c, 16);
         o.inliers = o.inliers_pre;
@@ -891,6 +914,105 @@ int orc_sac_plane(const float* xyzw, int n, double thr, int max_iter, double pro
         std::memcpy(triplets_used, o.triplets.data(), 12 * (size_t)m);
     }
     return o.found ? 1 : 0;
+}
+
+int orc_sac_plane_model(const float* xyzw, int n, int model_type, const float axis[3], double eps_angle, double thr, int max_iter,
+                        double prob, uint32_t seed, int refine, int mode, float coeff_out[4], int32_t* inliers_out, int* n_inliers,
+                        int32_t* inliers_pre, int* n_inliers_pre, int* iters_run) {
+    SacOut o;
+    SacModel m;
+    m.type = model_type; m.eps = eps_angle;
+    for (int k = 0; k < 3; ++k) m.axis[k] = axis ? axis[k] : 0.0f;
+    sac_plane(reinterpret_cast<const P4*>(xyzw), n, thr, max_iter, prob, seed, refine, mode, nullptr, 0, o, &m);
+    if (coeff_out) std::memcpy(coeff_out, o.coeff, 16);
+    if (inliers_out) std::memcpy(inliers_out, o.inliers.data(), 4 * o.inliers.size());
+    if (inliers_pre) std::memcpy(inliers_pre, o.inliers_pre.data(), 4 * o.inliers_pre.size());
+    if (n_inliers) *n_inliers = (int)o.inliers.size();
+    if (n_inliers_pre) *n_inliers_pre = (int)o.inliers_pre.size();
+    if (iters_run) *iters_run = o.iters;
+    return o.found ? 1 : 0;
+}
+
+/* surface_normal_estimation.cpp:182-233 (callback) with getNormal (:105-165): three constrained-plane RANSACs on the
+ * shrinking cloud, pcl::compute3DCentroid of each plane (sequential float sums, / (float)n), the count-descending
+ * exchange sort of :207-221, the handedness fix of :223-226 and the pose matrix of :228-237. */
+int orc_surface_normals(const float* xyzw, int n, const float axis[3], double eps_angle, double thr, int max_iter, double prob,
+                        uint32_t seed, int mode, orc_surface_result* out) {
+    std::vector<P4> cloud(reinterpret_cast<const P4*>(xyzw), reinterpret_cast<const P4*>(xyzw) + n);
+    struct Pl { float c[4]; float mid[3]; int n; int found; };
+    Pl pl[3];
+    for (int i = 0; i < 3; ++i) {
+        SacOut o;
+        SacModel m;
+        m.type = (i == 0) ? 1 : 2; m.eps = eps_angle;
+        for (int k = 0; k < 3; ++k) m.axis[k] = axis[k];
+        sac_plane(cloud.data(), (int)cloud.size(), thr, max_iter, prob, seed, 1, mode, nullptr, 0, o, &m);
+        Pl& P = pl[i];
+        P.found = o.found ? 1 : 0;
+        for (int k = 0; k < 4; ++k) P.c[k] = o.found ? o.coeff[k] : 0.0f;
+        P.n = (int)o.inliers.size();
+        float sx = 0.f, sy = 0.f, sz = 0.f;
+        for (int32_t id : o.inliers) { sx += cloud[id].x; sy += cloud[id].y; sz += cloud[id].z; }
+        const float cn = (float)P.n;
+        P.mid[0] = P.n ? sx / cn : 0.f; P.mid[1] = P.n ? sy / cn : 0.f; P.mid[2] = P.n ? sz / cn : 0.f;
+        std::vector<char> in(cloud.size(), 0);
+        for (int32_t id : o.inliers) in[id] = 1;
+        std::vector<P4> rest;
+        for (size_t k = 0; k < cloud.size(); ++k) if (!in[k]) rest.push_back(cloud[k]);
+        out->n_in[i] = (int)cloud.size();
+        cloud.swap(rest);
+    }
+    for (int i = 0; i < 3; ++i) {
+        for (int k = 0; k < 4; ++k) out->coeff[i][k] = pl[i].c[k];
+        for (int k = 0; k < 3; ++k) out->midpoint[i][k] = pl[i].mid[k];
+        out->n_plane[i] = pl[i].n; out->found[i] = pl[i].found;
+    }
+    out->n_left = (int)cloud.size();
+    orc_surface_pose(&out->coeff[0][0], &out->midpoint[0][0], out->n_plane, out->Rt, out->order);
+    return pl[0].found && pl[1].found && pl[2].found;
+}
+
+/* surface_normal_estimation.cpp:207-237: order planes by point count (largest first) with the node's own exchange loop,
+ * flip normal 2 if the triad is left-handed, project the first midpoint; Rt columns = (n2, n1, n0, centroid), row-major. */
+void orc_surface_pose(const float coeff[12], const float midpoint[9], const int32_t n_plane[3], float Rt[16], int32_t order[3]) {
+    float nr[3][3], mid[3][3];
+    int cnt[3], ord[3] = {0, 1, 2};
+    for (int i = 0; i < 3; ++i) { for (int k = 0; k < 3; ++k) { nr[i][k] = coeff[4 * i + k]; mid[i][k] = midpoint[3 * i + k]; } cnt[i] = n_plane[i]; }
+    for (int i = 0; i < 3; ++i)
+        for (int j = i; j < 3; ++j)
+            if (cnt[i] < cnt[j]) {
+                std::swap(cnt[i], cnt[j]); std::swap(ord[i], ord[j]);
+                for (int k = 0; k < 3; ++k) { std::swap(nr[i][k], nr[j][k]); std::swap(mid[i][k], mid[j][k]); }
+            }
+    /* normals[2].dot(normals[1].cross(normals[0])) < 0 : Eigen Vector3f, cross then the size-3 redux a0 + (a1 + a2) */
+    const float cr[3] = {nr[1][1] * nr[0][2] - nr[1][2] * nr[0][1], nr[1][2] * nr[0][0] - nr[1][0] * nr[0][2], nr[1][0] * nr[0][1] - nr[1][1] * nr[0][0]};
+    const float triple = nr[2][0] * cr[0] + (nr[2][1] * cr[1] + nr[2][2] * cr[2]);
+    if (triple < 0.0f) for (int k = 0; k < 3; ++k) nr[2][k] = -nr[2][k];
+    const float df[3] = {mid[0][0] - mid[1][0], mid[0][1] - mid[1][1], mid[0][2] - mid[1][2]};
+    const float proj = nr[0][0] * df[0] + (nr[0][1] * df[1] + nr[0][2] * df[2]);
+    float cen[3];
+    for (int k = 0; k < 3; ++k) cen[k] = mid[0][k] - proj * nr[0][k];
+    for (int r = 0; r < 3; ++r) { Rt[4 * r + 0] = nr[2][r]; Rt[4 * r + 1] = nr[1][r]; Rt[4 * r + 2] = nr[0][r]; Rt[4 * r + 3] = cen[r]; }
+    Rt[12] = 0.f; Rt[13] = 0.f; Rt[14] = 0.f; Rt[15] = 1.f;
+    for (int i = 0; i < 3; ++i) order[i] = ord[i];
+}
+
+// bbox_filter.cpp:30-51: u, v, w are accumulated in double (the matrix is vector<double>) and stored to float; the
+// perspective divide and the comparisons against the int rectangle run in float; a point is kept only strictly inside.
+int orc_bbox_filter(const float* xyzw, int n, const double P[12], const int32_t bbox[4], float* out_xyzw, int32_t* idx_out) {
+    const P4* p = reinterpret_cast<const P4*>(xyzw);
+    P4* o = reinterpret_cast<P4*>(out_xyzw);
+    int k = 0;
+    for (int i = 0; i < n; ++i) {
+        const double x = (double)p[i].x, y = (double)p[i].y, z = (double)p[i].z;
+        volatile float u = (float)((((P[0] * x) + (P[1] * y)) + (P[2] * z)) + P[3]);
+        volatile float v = (float)((((P[4] * x) + (P[5] * y)) + (P[6] * z)) + P[7]);
+        volatile float w = (float)((((P[8] * x) + (P[9] * y)) + (P[10] * z)) + P[11]);
+        const float un = u / w, vn = v / w;
+        const bool in = ((float)bbox[0] < un && un < (float)bbox[2]) && ((float)bbox[1] < vn && vn < (float)bbox[3]);
+        if (in) { if (o) o[k] = p[i]; if (idx_out) idx_out[k] = i; ++k; }
+    }
+    return k;
 }
 
 int orc_extract(const float* xyzw, int n, const int32_t* idx, int n_idx, int negative, float* out, int32_t* src_index) {

@@ -112,6 +112,29 @@ int orc_sac_plane(const float* xyzw, int n, double thr, int max_iter, double pro
 int orc_extract(const float* xyzw, int n, const int32_t* idx, int n_idx, int negative, float* out,
                 int32_t* src_index_out);
 
+/* f1: surface_normal_estimation (cuboid_detection/src/surface_normal_estimation.cpp:105-165 getNormal, :182-233 callback).
+ * SACSegmentation with SACMODEL_PERPENDICULAR_PLANE (model_type 1) / SACMODEL_PARALLEL_PLANE (model_type 2), setAxis,
+ * setEpsAngle(0.1), optimize = true; semantics [PCL-recall], see cuboid_oracle.cpp: model_valid. */
+int orc_sac_plane_model(const float* xyzw, int n, int model_type, const float axis[3], double eps_angle, double thr, int max_iter,
+                        double prob, uint32_t seed, int refine, int mode, float coeff_out[4], int32_t* inliers_out, int* n_inliers,
+                        int32_t* inliers_pre, int* n_inliers_pre, int* iters_run);
+typedef struct {
+    float coeff[3][4];      /* plane i of the loop at :196-205 (0: perpendicular model, 1 and 2: parallel model), segmentation order */
+    float midpoint[3][3];   /* pcl::compute3DCentroid of its inliers */
+    int32_t n_plane[3], found[3], n_in[3];
+    int32_t n_left;
+    int32_t order[3];       /* segmentation index of the plane that ends up as normals[0], [1], [2] after the sort at :207-221 */
+    float Rt[16];           /* :228-237, row-major: columns (n2, n1, n0, centroid) */
+} orc_surface_result;
+int orc_surface_normals(const float* xyzw, int n, const float axis[3], double eps_angle, double thr, int max_iter, double prob,
+                        uint32_t seed, int mode, orc_surface_result* out);
+void orc_surface_pose(const float coeff[12], const float midpoint[9], const int32_t n_plane[3], float Rt[16], int32_t order[3]);
+
+/* f3: bbox_filter's within_bbox + ExtractIndices (cuboid_detection/src/bbox_filter.cpp:30-51, 89-103): keep point i iff its
+ * projection through the 3x4 CameraInfo P lies strictly inside the rectangle (x1,y1,x2,y2). Pinned by the reference
+ * source itself (no third-party arithmetic). idx_out may be NULL. Returns count. */
+int orc_bbox_filter(const float* xyzw, int n, const double P[12], const int32_t bbox[4], float* out_xyzw, int32_t* idx_out);
+
 /* a5: KdTree + EuclideanClusterExtraction (opd.cpp:346-362). idx_sorted_out has room for n, offsets_out
  * for n_clusters+1 (cap n/min+2). Returns number of kept clusters. */
 int orc_cluster(const float* xyzw, int n, double tol, int min_size, int max_size, int32_t* idx_sorted_out,

@@ -156,6 +156,48 @@ def extract(pts, idx, negative=True):
     return out[:k].copy(), src[:k].copy()
 
 
+class SurfaceResult(C.Structure):
+    _fields_ = [("coeff", (C.c_float * 4) * 3), ("midpoint", (C.c_float * 3) * 3), ("n_plane", C.c_int32 * 3),
+                ("found", C.c_int32 * 3), ("n_in", C.c_int32 * 3), ("n_left", C.c_int32), ("order", C.c_int32 * 3),
+                ("Rt", C.c_float * 16)]
+
+
+def sac_plane_model(pts, model_type, axis, eps_angle=0.1, thr=0.015, max_iter=1000, prob=0.99, seed=12345, refine=1, mode=CANONICAL):
+    """SACSegmentation with SACMODEL_PERPENDICULAR_PLANE (1) / SACMODEL_PARALLEL_PLANE (2), setAxis + setEpsAngle."""
+    pts = _f32(pts)
+    n = len(pts)
+    ax = np.ascontiguousarray(axis, dtype=np.float32).reshape(3)
+    coeff = np.zeros(4, np.float32)
+    inl = np.empty(max(n, 1), np.int32)
+    pre = np.empty(max(n, 1), np.int32)
+    ni, npre, it = C.c_int(0), C.c_int(0), C.c_int(0)
+    found = lib().orc_sac_plane_model(_p(pts), n, int(model_type), _p(ax), C.c_double(eps_angle), C.c_double(thr), int(max_iter),
+                                      C.c_double(prob), C.c_uint32(seed), int(refine), int(mode), _p(coeff), _p(inl), C.byref(ni),
+                                      _p(pre), C.byref(npre), C.byref(it))
+    return dict(found=bool(found), coeff=coeff, inliers=inl[:ni.value].copy(), inliers_pre=pre[:npre.value].copy(), iters=it.value)
+
+
+def surface_normals(pts, axis, eps_angle=0.1, thr=0.015, max_iter=1000, prob=0.99, seed=12345, mode=CANONICAL):
+    """surface_normal_estimation callback: three constrained planes + the coarse cuboid pose."""
+    pts = _f32(pts)
+    ax = np.ascontiguousarray(axis, dtype=np.float32).reshape(3)
+    out = SurfaceResult()
+    ok = lib().orc_surface_normals(_p(pts), len(pts), _p(ax), C.c_double(eps_angle), C.c_double(thr), int(max_iter),
+                                   C.c_double(prob), C.c_uint32(seed), int(mode), C.byref(out))
+    return bool(ok), out
+
+
+def bbox_filter(pts, P, bbox):
+    """bbox_filter.cpp: points whose projection through the 3x4 matrix P lies strictly inside (x1, y1, x2, y2)."""
+    pts = _f32(pts)
+    Pd = np.ascontiguousarray(P, dtype=np.float64).reshape(12)
+    bb = np.ascontiguousarray(bbox, dtype=np.int32).reshape(4)
+    out = np.empty((max(len(pts), 1), 4), np.float32)
+    idx = np.empty(max(len(pts), 1), np.int32)
+    k = lib().orc_bbox_filter(_p(pts), len(pts), _p(Pd), _p(bb), _p(out), _p(idx))
+    return out[:k].copy(), idx[:k].copy()
+
+
 def cluster(pts, tol=0.02, min_size=200, max_size=25000):
     pts = _f32(pts)
     n = len(pts)

@@ -35,8 +35,16 @@ ABI_SYMBOLS = [
     "cuboid_pack_fitness_key", "cuboid_unpack_fitness_key", "cuboid_strerror", "cuboid_last_error",
     "cuboid_abi_version", "cuboid_params_size", "cuboid_frame_result_size", "cuboid_launch_count",
     "cuboid_stage_ms", "cuboid_measure_fp32_peak", "cuboid_set_option", "cuboid_icp_work",
+    "cuboid_bbox_filter", "cuboid_set_bbox_filter", "cuboid_surface_normals", "cuboid_surface_pose",
 ]
 OPT_ICP_CULL, OPT_TAPS, OPT_STAGES, OPT_FRONTEND = 1, 2, 3, 4
+
+
+class SurfaceResult(C.Structure):
+    """cuboid_surface_result (include/cuboid_cuda.h)."""
+    _fields_ = [("coeff", (C.c_float * 4) * 3), ("midpoint", (C.c_float * 3) * 3), ("n_plane", C.c_int32 * 3),
+                ("found", C.c_int32 * 3), ("n_in", C.c_int32 * 3), ("n_left", C.c_int32), ("order", C.c_int32 * 3),
+                ("Rt", C.c_float * 16), ("pose7", C.c_double * 7)]
 
 
 class CuboidError(RuntimeError):
@@ -93,6 +101,11 @@ def load():
     L.cuboid_measure_fp32_peak.argtypes = [vp, C.POINTER(C.c_double), C.POINTER(C.c_double)]
     L.cuboid_set_option.argtypes = [vp, i32, i32]
     L.cuboid_icp_work.argtypes = [vp, vp]
+    L.cuboid_bbox_filter.argtypes = [vp, vp, i32, i32, i32, i32, i32, vp, vp, vp, vp, i32, ip]
+    L.cuboid_set_bbox_filter.argtypes = [vp, vp, vp, i32]
+    L.cuboid_surface_normals.argtypes = [vp, vp, i32, vp, C.c_double, C.c_double, C.POINTER(SurfaceResult)]
+    L.cuboid_surface_pose.argtypes = [vp, vp, vp, vp, vp, vp]
+    L.cuboid_surface_pose.restype = None
     if L.cuboid_params_size() != C.sizeof(CuboidParams) or L.cuboid_frame_result_size() != C.sizeof(FrameResult):
         raise ImportError("struct layout mismatch between params.py and include/cuboid_cuda.h")
     _lib = L
@@ -230,6 +243,37 @@ class CuboidCuda:
                                                C.byref(found)), "cuboid_segment_plane")
         return dict(found=bool(found.value), coeff=coeff, inliers=inl[:ni.value].copy(), inliers_pre=pre[:npre.value].copy(),
                     remain=rem[:nr.value].copy(), iters=it.value)
+
+    def surface_normals(self, pts, axis, eps_angle=0.1, distance_threshold=0.015):
+        """surface_normal_estimation callback on the non-plane cloud; axis = the table normal."""
+        p = _xyzw(pts)
+        ax = np.ascontiguousarray(axis, dtype=np.float32).reshape(3)
+        out = SurfaceResult()
+        self._ck(self.lib.cuboid_surface_normals(self._h, _ptr(p), len(p), _ptr(ax), float(eps_angle), float(distance_threshold),
+                                                 C.byref(out)), "cuboid_surface_normals")
+        return out
+
+    def bbox_filter(self, pts, P, bbox):
+        """bbox_filter node: (kept points xyzw, their indices), order preserved."""
+        p = _xyzw(pts)
+        n = len(p)
+        Pd = np.ascontiguousarray(P, dtype=np.float64).reshape(12)
+        bb = np.ascontiguousarray(bbox, dtype=np.int32).reshape(4)
+        idx = np.empty(max(n, 1), np.int32)
+        out = np.empty((max(n, 1), 4), np.float32)
+        k = C.c_int(0)
+        self._ck(self.lib.cuboid_bbox_filter(self._h, _ptr(p), 16, 0, 4, 8, n, _ptr(Pd), _ptr(bb), _ptr(idx), _ptr(out), max(n, 1),
+                                             C.byref(k)), "cuboid_bbox_filter")
+        return out[:k.value].copy(), idx[:k.value].copy()
+
+    def set_bbox_filter(self, P=None, bbox=None):
+        """Fuse the bbox_filter predicate into the extraction of the pipeline entries (None, None switches it off)."""
+        if P is None:
+            self._ck(self.lib.cuboid_set_bbox_filter(self._h, None, None, 0), "cuboid_set_bbox_filter")
+            return
+        Pd = np.ascontiguousarray(P, dtype=np.float64).reshape(12)
+        bb = np.ascontiguousarray(bbox, dtype=np.int32).reshape(4)
+        self._ck(self.lib.cuboid_set_bbox_filter(self._h, _ptr(Pd), _ptr(bb), 1), "cuboid_set_bbox_filter")
 
     def cluster(self, pts, cap_clusters=1024):
         p = _xyzw(pts)

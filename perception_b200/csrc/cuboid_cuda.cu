@@ -74,6 +74,8 @@ struct cuboid_handle {
     int smem_optin = 0; int icp_smem_budget = 0;
     int last_chunk_base = 0, last_chunk_frames = 0, last_total_frames = 0;
     int taps = 1;
+    int use_bbox = 0; double bbP[12] = {}; int bb[4] = {};   // cuboid_set_bbox_filter
+    struct { int active = 0; int model_type = 0; float axis[3] = {0, 0, 0}; double eps = 0.0, thr = 0.0; } sac_override;   // cuboid_surface_normals
     // fused front end (frontend.cuh): one thread-block cluster per frame, persistent over the chunk
     int frontend = 1; int fe_cluster = 1; int fe_threads = 512; int fe_slots = 0; unsigned long long* d_fe_keys = nullptr;
     // host-buffer batches: sub-chunks run end to end on a few streams, so copies, front end and ICP of different sub-chunks overlap
@@ -303,6 +305,18 @@ int run_chunk(cuboid_handle* h, const ChunkIn& in, int nf, cuboid_frame_result* 
         s.refine = p.sac_refine; s.negative = p.extract_negative;
         s.use_z2 = p.use_pass_z2; s.z2_lo = limit_lo(p.pass_z2_min); s.z2_hi = limit_hi(p.pass_z2_max);
         s.cap_remain = h->M;
+        s.use_bbox = h->use_bbox;
+        s.model_type = 0; s.cos_eps = 1.0; s.sin_eps = 0.0;
+        if (h->sac_override.active) {   // constrained plane models of surface_normal_estimation.cpp:105-165
+            s.model_type = h->sac_override.model_type;
+            for (int k = 0; k < 3; ++k) s.axis[k] = h->sac_override.axis[k];
+            s.cos_eps = h->sac_override.eps > 0.0 ? std::cos(h->sac_override.eps) : 1.0;
+            s.sin_eps = std::fabs(std::sin(h->sac_override.eps));
+            s.thr_f = thr_up(h->sac_override.thr);
+            s.refine = 1; s.negative = 1; s.use_z2 = 0; s.use_bbox = 0;
+        }
+        for (int k = 0; k < 12; ++k) s.bbP[k] = h->bbP[k];
+        for (int k = 0; k < 4; ++k) s.bb[k] = h->bb[k];
         k_sac_plane<<<nf, SAC_THREADS, sizeof(SacShared), st>>>(s);
         ++h->launches;
         CK(h, cudaGetLastError());
@@ -751,6 +765,165 @@ int cuboid_segment_plane(cuboid_handle* h, const float* xyzw, int n, const int32
     if (inlier_idx_out && r.n_inliers) CK(h, cudaMemcpy(inlier_idx_out, h->d_inl, sizeof(int) * r.n_inliers, cudaMemcpyDeviceToHost));
     if (inlier_pre_out && r.n_inliers_pre) CK(h, cudaMemcpy(inlier_pre_out, h->d_inl_pre, sizeof(int) * r.n_inliers_pre, cudaMemcpyDeviceToHost));
     if (remain_xyzw_out && r.n_remain) CK(h, cudaMemcpy(remain_xyzw_out, h->d_remain, sizeof(float4) * r.n_remain, cudaMemcpyDeviceToHost));
+    return CUBOID_OK;
+}
+
+namespace {
+// pcl::compute3DCentroid over the inliers of a plane (surface_normal_estimation.cpp:156-157): sequential float sums in index
+// order, one lane per coordinate, then / (float)n
+__global__ void k_centroid(const float4* pts, const int* idx, int n, float* out3) {
+    const int c = threadIdx.x;
+    if (c >= 3) return;
+    float s = 0.0f;
+    for (int j = 0; j < n; ++j) {
+        const float4 p = pts[idx[j]];
+        s += c == 0 ? p.x : (c == 1 ? p.y : p.z);
+    }
+    out3[c] = n > 0 ? s / (float)n : 0.0f;
+}
+// tf::Matrix3x3::getRotation (icp.cpp:55-88, surface_normal_estimation.cpp:68-78)
+void quat_from_rot(const double R[9], double q[4]) {
+    auto M = [&](int r, int c) { return R[3 * r + c]; };
+    const double trace = M(0, 0) + M(1, 1) + M(2, 2);
+    if (trace > 0.0) {
+        double s = std::sqrt(trace + 1.0);
+        q[3] = s * 0.5; s = 0.5 / s;
+        q[0] = (M(2, 1) - M(1, 2)) * s; q[1] = (M(0, 2) - M(2, 0)) * s; q[2] = (M(1, 0) - M(0, 1)) * s;
+    } else {
+        const int i = M(0, 0) < M(1, 1) ? (M(1, 1) < M(2, 2) ? 2 : 1) : (M(0, 0) < M(2, 2) ? 2 : 0);
+        const int j = (i + 1) % 3, k = (i + 2) % 3;
+        double s = std::sqrt(M(i, i) - M(j, j) - M(k, k) + 1.0);
+        q[i] = s * 0.5; s = 0.5 / s;
+        q[3] = (M(k, j) - M(j, k)) * s; q[j] = (M(j, i) + M(i, j)) * s; q[k] = (M(k, i) + M(i, k)) * s;
+    }
+}
+}  // namespace
+
+// surface_normal_estimation.cpp:207-237 + convert_eigen_to_tf (:64-96): host arithmetic on three plane normals
+void cuboid_surface_pose(const float coeff[12], const float midpoint[9], const int32_t n_plane[3], float Rt[16], int32_t order[3],
+                         double pose7[7]) {
+    float nrm[3][3], mid[3][3];
+    int cnt[3], ord[3] = {0, 1, 2};
+    for (int i = 0; i < 3; ++i) {
+        cnt[i] = n_plane[i];
+        for (int k = 0; k < 3; ++k) { nrm[i][k] = coeff[4 * i + k]; mid[i][k] = midpoint[3 * i + k]; }
+    }
+    // the node's own exchange loop: for i, for j >= i, swap when planes[i] has fewer points than planes[j]
+    for (int i = 0; i < 3; ++i)
+        for (int j = i; j < 3; ++j) {
+            if (!(cnt[i] < cnt[j])) continue;
+            std::swap(cnt[i], cnt[j]);
+            std::swap(ord[i], ord[j]);
+            for (int k = 0; k < 3; ++k) { std::swap(nrm[i][k], nrm[j][k]); std::swap(mid[i][k], mid[j][k]); }
+        }
+    // handedness: normals[2] . (normals[1] x normals[0]) < 0 -> flip normals[2]   (Eigen size-3 redux: a0 + (a1 + a2))
+    volatile float cx = nrm[1][1] * nrm[0][2] - nrm[1][2] * nrm[0][1];
+    volatile float cy = nrm[1][2] * nrm[0][0] - nrm[1][0] * nrm[0][2];
+    volatile float cz = nrm[1][0] * nrm[0][1] - nrm[1][1] * nrm[0][0];
+    volatile float t12 = nrm[2][1] * cy + nrm[2][2] * cz;
+    volatile float triple = nrm[2][0] * cx + t12;
+    if (triple < 0.0f) for (int k = 0; k < 3; ++k) nrm[2][k] = -nrm[2][k];
+    // projection of the midpoint difference on normals[0]
+    volatile float d0 = mid[0][0] - mid[1][0], d1 = mid[0][1] - mid[1][1], d2 = mid[0][2] - mid[1][2];
+    volatile float p12 = nrm[0][1] * d1 + nrm[0][2] * d2;
+    volatile float proj = nrm[0][0] * d0 + p12;
+    for (int r = 0; r < 3; ++r) {
+        volatile float pr = proj * nrm[0][r];
+        Rt[4 * r + 0] = nrm[2][r]; Rt[4 * r + 1] = nrm[1][r]; Rt[4 * r + 2] = nrm[0][r]; Rt[4 * r + 3] = mid[0][r] - pr;
+    }
+    Rt[12] = 0.f; Rt[13] = 0.f; Rt[14] = 0.f; Rt[15] = 1.f;
+    if (order) for (int i = 0; i < 3; ++i) order[i] = ord[i];
+    if (pose7) {
+        double R9[9], q[4];
+        for (int r = 0; r < 3; ++r) for (int c = 0; c < 3; ++c) R9[3 * r + c] = (double)Rt[4 * r + c];
+        quat_from_rot(R9, q);
+        pose7[0] = (double)Rt[3]; pose7[1] = (double)Rt[7]; pose7[2] = (double)Rt[11];
+        pose7[3] = q[0]; pose7[4] = q[1]; pose7[5] = q[2]; pose7[6] = q[3];
+    }
+}
+
+int cuboid_surface_normals(cuboid_handle* h, const float* xyzw, int n, const float axis[3], double eps_angle, double distance_threshold,
+                           cuboid_surface_result* out) {
+    if (!h || (!xyzw && n > 0) || n < 0 || !axis || !out || !(distance_threshold > 0.0)) return CUBOID_E_INVALID;
+    if (n > h->P) return CUBOID_E_CAPACITY;
+    cudaSetDevice(h->device);
+    std::memset(out, 0, sizeof(*out));
+    if (n) CK(h, cudaMemcpyAsync(h->d_vox, xyzw, sizeof(float4) * n, cudaMemcpyHostToDevice, h->stream));
+    float* d_mid = reinterpret_cast<float*>(h->d_desc1);   // 3 floats of scratch
+    int cur_n = n, rc = CUBOID_OK;
+    h->sac_override.active = 1; h->sac_override.eps = eps_angle; h->sac_override.thr = distance_threshold;
+    for (int k = 0; k < 3; ++k) h->sac_override.axis[k] = axis[k];
+    for (int i = 0; i < 3 && rc == CUBOID_OK; ++i) {
+        // :196-205: plane 0 with the perpendicular model (parallel to the table top), planes 1 and 2 with the parallel model
+        h->sac_override.model_type = (i == 0) ? 1 : 2;
+        out->n_in[i] = cur_n;
+        if (cudaMemsetAsync(h->d_res, 0, sizeof(cuboid_frame_result), h->stream) != cudaSuccess) { rc = CUBOID_E_CUDA; break; }
+        k_set_counts<<<1, 32, 0, h->stream>>>(h->d_res, -1, cur_n, -1, -1, nullptr, nullptr, 0);
+        ++h->launches;
+        ChunkIn in;
+        rc = run_chunk(h, in, 1, h->d_res, 2, 0, true, true, false, true);
+        if (rc != CUBOID_OK) break;
+        cuboid_frame_result r;
+        if (cudaMemcpyAsync(&r, h->d_res, sizeof r, cudaMemcpyDeviceToHost, h->stream) != cudaSuccess ||
+            cudaStreamSynchronize(h->stream) != cudaSuccess) { rc = CUBOID_E_CUDA; break; }
+        out->found[i] = r.plane_found;
+        out->n_plane[i] = r.n_inliers;
+        for (int k = 0; k < 4; ++k) out->coeff[i][k] = r.plane_coeff[k];
+        k_centroid<<<1, 32, 0, h->stream>>>(h->d_vox, h->d_inl, r.n_inliers, d_mid);
+        ++h->launches;
+        if (cudaMemcpyAsync(out->midpoint[i], d_mid, 12, cudaMemcpyDeviceToHost, h->stream) != cudaSuccess) { rc = CUBOID_E_CUDA; break; }
+        // the leftover cloud of this plane is the input of the next one
+        if (r.n_remain && cudaMemcpyAsync(h->d_vox, h->d_remain, sizeof(float4) * r.n_remain, cudaMemcpyDeviceToDevice, h->stream) != cudaSuccess) { rc = CUBOID_E_CUDA; break; }
+        if (cudaStreamSynchronize(h->stream) != cudaSuccess) { rc = CUBOID_E_CUDA; break; }
+        cur_n = r.n_remain;
+    }
+    h->sac_override.active = 0;
+    if (rc != CUBOID_OK) return rc;
+    out->n_left = cur_n;
+    cuboid_surface_pose(&out->coeff[0][0], &out->midpoint[0][0], out->n_plane, out->Rt, out->order, out->pose7);
+    return CUBOID_OK;
+}
+
+int cuboid_set_bbox_filter(cuboid_handle* h, const double P[12], const int32_t bbox[4], int enable) {
+    if (!h || (enable && (!P || !bbox))) return CUBOID_E_INVALID;
+    h->use_bbox = enable ? 1 : 0;
+    if (enable) {
+        for (int k = 0; k < 12; ++k) h->bbP[k] = P[k];
+        for (int k = 0; k < 4; ++k) h->bb[k] = bbox[k];
+    }
+    return CUBOID_OK;
+}
+
+int cuboid_bbox_filter(cuboid_handle* h, const void* pts, int point_step, int xoff, int yoff, int zoff, int n, const double P[12],
+                       const int32_t bbox[4], int32_t* idx_out, float* xyzw_out, int cap, int* n_out) {
+    if (!h || (!pts && n > 0) || n < 0 || !P || !bbox || !n_out || point_step < 12 || (point_step & 3) || (xoff & 3) || (yoff & 3) || (zoff & 3))
+        return CUBOID_E_INVALID;
+    if (n > h->P) return CUBOID_E_CAPACITY;
+    cudaSetDevice(h->device);
+    // gather x, y, z of the PointCloud2 records into xyzw on the host side of the copy (the node does fromPCLPointCloud2 first)
+    std::vector<float> packed((size_t)std::max(n, 1) * 4);
+    const unsigned char* b = static_cast<const unsigned char*>(pts);
+    for (int i = 0; i < n; ++i) {
+        std::memcpy(&packed[(size_t)i * 4 + 0], b + (size_t)i * point_step + xoff, 4);
+        std::memcpy(&packed[(size_t)i * 4 + 1], b + (size_t)i * point_step + yoff, 4);
+        std::memcpy(&packed[(size_t)i * 4 + 2], b + (size_t)i * point_step + zoff, 4);
+        packed[(size_t)i * 4 + 3] = 1.0f;
+    }
+    if (n) CK(h, cudaMemcpyAsync(h->d_vox, packed.data(), sizeof(float4) * n, cudaMemcpyHostToDevice, h->stream));
+    BboxArgs a{};
+    a.pts = h->d_vox; a.n = n; a.idx_out = h->d_inl; a.pts_out = h->d_remain; a.n_out = reinterpret_cast<int*>(h->d_ticket);
+    for (int k = 0; k < 12; ++k) a.P[k] = P[k];
+    for (int k = 0; k < 4; ++k) a.bb[k] = bbox[k];
+    k_bbox_filter<<<1, SAC_THREADS, 0, h->stream>>>(a);
+    ++h->launches;
+    CK(h, cudaGetLastError());
+    int m = 0;
+    CK(h, cudaMemcpyAsync(&m, h->d_ticket, sizeof(int), cudaMemcpyDeviceToHost, h->stream));
+    CK(h, cudaStreamSynchronize(h->stream));
+    *n_out = m;
+    if (m > cap) return CUBOID_E_CAPACITY;
+    if (idx_out && m) CK(h, cudaMemcpy(idx_out, h->d_inl, sizeof(int) * m, cudaMemcpyDeviceToHost));
+    if (xyzw_out && m) CK(h, cudaMemcpy(xyzw_out, h->d_remain, sizeof(float4) * m, cudaMemcpyDeviceToHost));
     return CUBOID_OK;
 }
 

@@ -37,13 +37,20 @@ struct SacArgs {
     int refine, negative;
     int use_z2; float z2_lo, z2_hi;
     int cap_remain;             // frames whose remainder exceeds this are flagged and truncated
+    // SACMODEL_PERPENDICULAR_PLANE (1) / SACMODEL_PARALLEL_PLANE (2) of surface_normal_estimation.cpp:118-123; 0 = SACMODEL_PLANE
+    int model_type;
+    float axis[3];              // seg.setAxis
+    double cos_eps, sin_eps;    // cos / |sin| of seg.setEpsAngle, evaluated on the host in double; eps <= 0 switches the test off
+    int use_bbox;               // bbox_filter.cpp as a fused predicate of the extraction (after PassThrough z2)
+    double bbP[12];             // CameraInfo P, row-major 3x4
+    int bb[4];                  // x1, y1, x2, y2
 };
 
 constexpr int SAC_THREADS = 256;
 constexpr int SAC_TILE = 2048;      // points per shared-memory tile (32 KB), two buffers
 constexpr int SAC_HB = 32;          // hypotheses scored per round (first round: 8)
 
-struct SacHyp { float c[4]; int valid; int kind; };   // kind: 0 normal, 1 sampler gave up (selection.empty())
+struct SacHyp { float c[4]; int valid; int kind; int ok; };   // kind: 0 normal, 1 sampler gave up (selection.empty()); ok: isModelValid()
 
 // ---- TMA bulk copy helpers (SASS: UBLKCP / SYNCS) -------------------------------------------------
 __device__ __forceinline__ unsigned int smem_u32(const void* p) { return (unsigned int)__cvta_generic_to_shared(p); }
@@ -68,6 +75,33 @@ __device__ __forceinline__ void tma_bulk_g2s(void* dst_smem, const void* src_gme
                  : "memory");
 }
 __device__ __forceinline__ void fence_proxy_async() { asm volatile("fence.proxy.async.shared::cta;" ::: "memory"); }
+
+// bbox_filter.cpp:30-51 (within_bbox): u, v, w accumulate in double (the matrix is vector<double>) and are stored to
+// float; the divide and the strict comparisons against the int rectangle run in float.
+__device__ __forceinline__ bool bbox_within(const double* P, const int* bb, float xf, float yf, float zf) {
+    const double x = (double)xf, y = (double)yf, z = (double)zf;
+    const float u = (float)((((P[0] * x) + (P[1] * y)) + (P[2] * z)) + P[3]);
+    const float v = (float)((((P[4] * x) + (P[5] * y)) + (P[6] * z)) + P[7]);
+    const float w = (float)((((P[8] * x) + (P[9] * y)) + (P[10] * z)) + P[11]);
+    const float un = u / w, vn = v / w;
+    return ((float)bb[0] < un && un < (float)bb[2]) && ((float)bb[1] < vn && vn < (float)bb[3]);
+}
+
+// SampleConsensusModel{Perpendicular,Parallel}Plane::isModelValid, canonical form shared with oracle/cuboid_oracle.cpp
+// (model_valid): coeff[3] = 0, coeff.normalize(), then |axis . coeff| > sin(eps) -> invalid (parallel model) or
+// |cos(angle(axis, coeff))| < cos(eps) -> invalid (perpendicular model).
+__device__ __forceinline__ bool sac_model_valid(const SacArgs& a, const float c[4]) {
+    if (a.model_type == 0 || !(a.cos_eps < 1.0)) return true;
+    const float n2 = dot4_sse(c[0], c[1], c[2], 0.0f, c[0], c[1], c[2], 0.0f);
+    const float nrm = sqrtf(n2);
+    const float q0 = c[0] / nrm, q1 = c[1] / nrm, q2 = c[2] / nrm;
+    const float d = dot4_sse(a.axis[0], a.axis[1], a.axis[2], 0.0f, q0, q1, q2, 0.0f);
+    if (a.model_type == 2) return !((double)fabsf(d) > a.sin_eps);
+    const float nn = dot4_sse(a.axis[0], a.axis[1], a.axis[2], 0.0f, a.axis[0], a.axis[1], a.axis[2], 0.0f) * dot4_sse(q0, q1, q2, 0.0f, q0, q1, q2, 0.0f);
+    double rad = (double)(d / sqrtf(nn));
+    if (rad < -1.0) rad = -1.0; else if (rad > 1.0) rad = 1.0;
+    return !(fabs(rad) < a.cos_eps);
+}
 
 // SampleConsensusModelPlane::isSampleGood
 __device__ __forceinline__ bool sac_sample_good(const float4& p0, const float4& p1, const float4& p2) {
@@ -254,9 +288,10 @@ __global__ void __launch_bounds__(SAC_THREADS, 1) k_sac_plane(const SacArgs a) {
                     }
                 }
                 SacHyp& hy = S.hyp[nh];
-                if (!got) { hy.kind = 1; hy.valid = 0; ++nh; break; }
+                if (!got) { hy.kind = 1; hy.valid = 0; hy.ok = 0; ++nh; break; }
                 hy.kind = 0;
                 hy.valid = sac_plane_from_sample(vox[s0], vox[s1], vox[s2], hy.c) ? 1 : 0;
+                hy.ok = (hy.valid && sac_model_valid(a, hy.c)) ? 1 : 0;   // countWithinDistance returns 0 for an invalid model
                 ++nh;
             }
             S.rp = rp;
@@ -272,7 +307,7 @@ __global__ void __launch_bounds__(SAC_THREADS, 1) k_sac_plane(const SacArgs a) {
 #pragma unroll
         for (int s = 0; s < 4; ++s) {
             const int h = wid + 8 * s;
-            hact[s] = h < nh && S.hyp[h].valid;
+            hact[s] = h < nh && S.hyp[h].valid && S.hyp[h].ok;
 #pragma unroll
             for (int c = 0; c < 4; ++c) hc[s][c] = hact[s] ? S.hyp[h].c[c] : 0.f;
         }
@@ -355,7 +390,8 @@ __global__ void __launch_bounds__(SAC_THREADS, 1) k_sac_plane(const SacArgs a) {
 #pragma unroll
         for (int k = 0; k < 4; ++k) c[k] = S.best_c[k];
         const float thr = a.thr_f;
-        n_pre = sac_compact(V, [&](int, const float4& p) { return plane_abs_dist(c, p.x, p.y, p.z) < thr; }, inl_pre, nullptr, vox,
+        const bool ok_pre = sac_model_valid(a, c);   // selectWithinDistance clears the inliers of an invalid model
+        n_pre = sac_compact(V, [&](int, const float4& p) { return ok_pre && plane_abs_dist(c, p.x, p.y, p.z) < thr; }, inl_pre, nullptr, vox,
                             a.P, nullptr, nullptr, S.s_w);
         if (a.refine && n_pre >= 4) {
             // PCL accumulates the 9 sums sequentially in float over the inliers in index order.
@@ -390,19 +426,22 @@ __global__ void __launch_bounds__(SAC_THREADS, 1) k_sac_plane(const SacArgs a) {
         const float thr = a.thr_f;
         const bool same = !(a.refine && n_pre >= 4);
         (void)same;
-        n_inl = sac_compact(V, [&](int, const float4& p) { return plane_abs_dist(c, p.x, p.y, p.z) < thr; }, inl, nullptr, vox, a.P,
+        const bool ok_fin = sac_model_valid(a, c);
+        n_inl = sac_compact(V, [&](int, const float4& p) { return ok_fin && plane_abs_dist(c, p.x, p.y, p.z) < thr; }, inl, nullptr, vox, a.P,
                             &R.inlier_hash, nullptr, S.s_w);
     }
     // ExtractIndices (+ PassThrough z2): negative -> everything that is not an inlier, ascending
     const float thr = a.thr_f;
     const int neg = a.negative, uz2 = a.use_z2;
+    const bool ok_ext = have && sac_model_valid(a, c);
     const float z2lo = a.z2_lo, z2hi = a.z2_hi;
     const int n_rem = sac_compact(
         V,
         [&](int, const float4& p) {
-            const bool is_in = have && (plane_abs_dist(c, p.x, p.y, p.z) < thr);
+            const bool is_in = have && ok_ext && (plane_abs_dist(c, p.x, p.y, p.z) < thr);
             bool keep = neg ? !is_in : is_in;
             if (keep && uz2) keep = finite_f32(p.z) && !(p.z > z2hi || p.z < z2lo);
+            if (keep && a.use_bbox) keep = bbox_within(a.bbP, a.bb, p.x, p.y, p.z);
             return keep;
         },
         nullptr, remain, vox, a.cap_remain, nullptr, &R.remain_hash, S.s_w);
@@ -419,6 +458,15 @@ __global__ void __launch_bounds__(SAC_THREADS, 1) k_sac_plane(const SacArgs a) {
         if (st) atomicOr(&R.status, st);
         a.scr[f].best_count = S.best;
     }
+}
+
+// stand-alone bbox_filter node (cuboid_detection/src/bbox_filter.cpp:89-103): ordered compaction of one cloud
+struct BboxArgs { const float4* pts; int n; double P[12]; int bb[4]; int* idx_out; float4* pts_out; int* n_out; };
+__global__ void __launch_bounds__(SAC_THREADS) k_bbox_filter(const BboxArgs a) {
+    __shared__ int s_w[9];
+    const int n = sac_compact(a.n, [&](int, const float4& p) { return bbox_within(a.P, a.bb, p.x, p.y, p.z); }, a.idx_out, a.pts_out, a.pts,
+                              a.n, nullptr, nullptr, s_w);
+    if (threadIdx.x == 0) *a.n_out = n;
 }
 
 }  // namespace cuboid

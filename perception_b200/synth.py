@@ -83,6 +83,12 @@ def make_scene(kind="cuboid1", seed=0):
                 b.py = (iy - 1.5) * 0.2 + rng.uniform(-0.005, 0.005)
                 b.yaw = rng.uniform(-0.08, 0.08)
                 k += 1
+    elif kind == "tallbox":   # one 200 x 75 x 100 mm cuboid seen corner-on: top face and two side faces (surface_normal_estimation)
+        sc.n_boxes = 1
+        b = sc.box[0]
+        b.L, b.W, b.H = 0.2, 0.075, 0.1
+        b.px, b.py = ax + rng.uniform(-0.02, 0.02), rng.uniform(-0.03, 0.03)
+        b.yaw = math.radians(rng.uniform(25.0, 65.0))
     elif kind == "plane_only":
         sc.n_boxes = 0
     else:

@@ -400,3 +400,70 @@ def test_fused_frontend_equals_unfused_kernels(tmpl30, params, cluster, threads,
     with api.CuboidCuda(params, max_points=640 * 480, max_batch=8) as h:
         h.set_template(0, tmpl30)
         _same_frame(h.process_batch(depth)[2], ref)
+
+
+def test_bbox_filter_node_and_fused_predicate(cc, stage_data, tmpl30, params):
+    """bbox_filter.cpp as a stand-alone stage and fused into the extraction of the pipeline."""
+    rem = stage_data["remain"]
+    P = np.array([615.0, 0.0, 322.5, 0.0, 0.0, 615.5, 240.6, 0.0, 0.0, 0.0, 1.0, 0.0])
+    bbox = (200, 100, 460, 380)
+    ref_pts, ref_idx = O.bbox_filter(rem, P, bbox)
+    got_pts, got_idx = cc.bbox_filter(rem, P, bbox)
+    assert 0 < len(ref_idx) < len(rem)
+    assert np.array_equal(got_idx, ref_idx) and np.array_equal(bits(got_pts), bits(ref_pts))
+    edge = np.array([[0.0, 0.0, 1.0, 1.0], [1.0, 0.0, 1.0, 1.0], [0.5, 0.5, 0.0, 1.0], [0.0, 0.0, 0.0, 1.0]], np.float32)
+    I = np.array([1.0, 0, 0, 0, 0, 1.0, 0, 0, 0, 0, 1.0, 0])
+    for bb in ((0, -1, 1, 1), (-1, -1, 2, 1)):
+        assert np.array_equal(cc.bbox_filter(edge, I, bb)[1], O.bbox_filter(edge, I, bb)[1])
+    assert len(cc.bbox_filter(edge[:0], I, (0, 0, 1, 1))[1]) == 0
+    # fused: ground_plane_segmentation -> bbox_filter -> clustering + ICP, against the oracle's stages composed the same way
+    depth = synth.depth_batch("bench", [11, 12])
+    cc.set_bbox_filter(P, bbox)
+    try:
+        res = cc.process_batch(depth)
+        rem_gpu = [cc.fetch(i, "remain") for i in range(2)]
+    finally:
+        cc.set_bbox_filter(None)
+    for i in range(2):
+        pts = O.unproject(depth[i], params.fx, params.fy, params.cx, params.cy, params.depth_scale)
+        pz, _ = O.passthrough(pts, 2, params.pass_z_min, params.pass_z_max)
+        px, _ = O.passthrough(pz, 0, params.pass_x_min, params.pass_x_max)
+        vg = O.voxel_grid(px, params.leaf)
+        sac = O.sac_plane(vg["vox"], params.sac_threshold, params.sac_max_iter, params.sac_prob, params.sac_seed, 1)
+        rem_o, _ = O.extract(vg["vox"], sac["inliers"], True)
+        kept, _ = O.bbox_filter(rem_o, P, bbox)
+        assert 0 < len(kept) < len(rem_o)
+        assert np.array_equal(bits(rem_gpu[i]), bits(kept)) and res[i].n_remain == len(kept)
+        cidx, coff = O.cluster(kept, params.cluster_tol, params.cluster_min, params.cluster_max)
+        assert res[i].n_clusters == len(coff) - 1
+        if len(coff) > 1:
+            ref = O.icp(kept[cidx[coff[0]:coff[1]]], tmpl30, rel_mse=params.icp_rel_mse)
+            c = res[i].cluster[0]
+            assert (c.iterations, c.converged) == (ref["iters"], ref["converged"]) and c.corr_hash == ref["corr_hash"]
+            assert np.array_equal(bits(list(c.T)), bits(ref["T"].reshape(-1))) and c.fitness == ref["fitness"]
+
+
+def test_surface_normal_estimation_matches_oracle(cc, params):
+    """the three constrained-plane RANSACs, centroids and pose of surface_normal_estimation.cpp, every
+    float bit-equal to the oracle (same sampler stream, same isModelValid, same sequential sums)."""
+    for kind, seed in (("tallbox", 0), ("tallbox", 1), ("tallbox", 2), ("bench", 7), ("plane_only", 2)):
+        d = synth.depth_frame(kind, seed)
+        pts = O.unproject(d, params.fx, params.fy, params.cx, params.cy, params.depth_scale)
+        pz, _ = O.passthrough(pts, 2, params.pass_z_min, params.pass_z_max)
+        px, _ = O.passthrough(pz, 0, params.pass_x_min, params.pass_x_max)
+        vg = O.voxel_grid(px, params.leaf)
+        sac = O.sac_plane(vg["vox"], params.sac_threshold, params.sac_max_iter, params.sac_prob, params.sac_seed, 1)
+        rem, _ = O.extract(vg["vox"], sac["inliers"], True)
+        ok, ref = O.surface_normals(rem, sac["coeff"][:3], 0.1, 0.015)
+        got = cc.surface_normals(rem, sac["coeff"][:3], 0.1, 0.015)
+        assert list(got.n_plane) == list(ref.n_plane) and list(got.found) == list(ref.found) and list(got.n_in) == list(ref.n_in)
+        assert got.n_left == ref.n_left and list(got.order) == list(ref.order)
+        for i in range(3):
+            assert np.array_equal(bits(list(got.coeff[i])), bits(list(ref.coeff[i]))), (kind, seed, i)
+            assert np.array_equal(bits(list(got.midpoint[i])), bits(list(ref.midpoint[i]))), (kind, seed, i)
+        assert np.array_equal(bits(list(got.Rt)), bits(list(ref.Rt)))
+        if kind == "tallbox":
+            assert ok and min(got.n_plane) > 50
+    # constrained single segmentation through the same kernel: inlier sets equal
+    empty = cc.surface_normals(np.zeros((0, 4), np.float32), [0.0, 0.0, 1.0])
+    assert list(empty.n_plane) == [0, 0, 0] and empty.n_left == 0

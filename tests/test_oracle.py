@@ -209,3 +209,103 @@ def test_pose_and_bbox():
     assert np.allclose(Rq, H[:3, :3], atol=1e-6)
     c = O.bbox_corners(H, 0.2, 0.1, 0.03)
     assert c.shape == (8, 4) and np.allclose(c[:, :3].mean(0), H[:3, 3], atol=1e-6)
+
+
+def test_bbox_filter_restates_the_reference_arithmetic(stage_data):
+    """bbox_filter.cpp:30-51 is plain arithmetic in the reference's own source (no PCL inside): double accumulation stored to
+    float, float divide, strict comparisons against the int rectangle. Checked against an independent numpy evaluation."""
+    rem = stage_data["remain"]
+    P = np.array([615.0, 0.0, 322.5, 0.0, 0.0, 615.5, 240.6, 0.0, 0.0, 0.0, 1.0, 0.0])   # a D435-like colour CameraInfo P
+    bbox = (250, 120, 420, 330)
+    out, idx = O.bbox_filter(rem, P, bbox)
+    x, y, z = (rem[:, k].astype(np.float64) for k in range(3))
+    with np.errstate(all="ignore"):
+        u = (P[0] * x + P[1] * y + P[2] * z + P[3]).astype(np.float32)
+        v = (P[4] * x + P[5] * y + P[6] * z + P[7]).astype(np.float32)
+        w = (P[8] * x + P[9] * y + P[10] * z + P[11]).astype(np.float32)
+        un, vn = u / w, v / w
+    keep = (np.float32(bbox[0]) < un) & (un < np.float32(bbox[2])) & (np.float32(bbox[1]) < vn) & (vn < np.float32(bbox[3]))
+    assert 0 < keep.sum() < len(rem)
+    assert np.array_equal(idx, np.nonzero(keep)[0]) and np.array_equal(bits(out), bits(rem[keep]))
+    # strict inequalities, w == 0 (NaN / inf never pass), READ_INFO-style empty rectangle
+    edge = np.array([[0.0, 0.0, 1.0, 1.0], [1.0, 0.0, 1.0, 1.0], [0.5, 0.5, 0.0, 1.0], [0.0, 0.0, 0.0, 1.0]], np.float32)
+    I = np.array([1.0, 0, 0, 0, 0, 1.0, 0, 0, 0, 0, 1.0, 0])
+    _, idx = O.bbox_filter(edge, I, (0, -1, 1, 1))
+    assert list(idx) == []                      # u == x1 and u == x2 are outside, w == 0 gives inf / NaN
+    _, idx = O.bbox_filter(edge, I, (-1, -1, 2, 1))
+    assert list(idx) == [0, 1]
+    assert len(O.bbox_filter(edge[:0], I, (0, 0, 1, 1))[1]) == 0
+
+
+def _remain_of(kind, seed, params):
+    from perception_b200 import synth
+    d = synth.depth_frame(kind, seed)
+    pts = O.unproject(d, params.fx, params.fy, params.cx, params.cy, params.depth_scale)
+    pz, _ = O.passthrough(pts, 2, params.pass_z_min, params.pass_z_max)
+    px, _ = O.passthrough(pz, 0, params.pass_x_min, params.pass_x_max)
+    vg = O.voxel_grid(px, params.leaf)
+    sac = O.sac_plane(vg["vox"], params.sac_threshold, params.sac_max_iter, params.sac_prob, params.sac_seed, 1)
+    rem, _ = O.extract(vg["vox"], sac["inliers"], True)
+    return rem, sac["coeff"]
+
+
+def test_constrained_plane_models_respect_the_axis(params):
+    """SACMODEL_PERPENDICULAR_PLANE / SACMODEL_PARALLEL_PLANE (surface_normal_estimation.cpp:118-123): the accepted plane's
+    normal is within eps of the axis (resp. of perpendicular to it), and eps <= 0 degenerates to the plain plane model."""
+    rem, table = _remain_of("tallbox", 1, params)
+    axis = table[:3]
+    top = O.sac_plane_model(rem, 1, axis, 0.1)
+    rest, _ = O.extract(rem, top["inliers"], True)           # the node runs the parallel model on what the first plane left
+    side = O.sac_plane_model(rest, 2, axis, 0.1)
+    assert top["found"] and side["found"] and len(top["inliers"]) > 500 and len(side["inliers"]) > 300
+    cosang = abs(float(np.dot(top["coeff"][:3], axis)) / np.linalg.norm(top["coeff"][:3]) / np.linalg.norm(axis))
+    assert cosang > np.cos(0.1)
+    sinang = abs(float(np.dot(side["coeff"][:3], axis)) / np.linalg.norm(side["coeff"][:3]) / np.linalg.norm(axis))
+    assert sinang < np.sin(0.1) + 1e-6
+    plain = O.sac_plane(rem, 0.015)
+    for mt in (1, 2):
+        same = O.sac_plane_model(rem, mt, axis, 0.0)
+        assert np.array_equal(same["inliers"], plain["inliers"]) and np.array_equal(bits(same["coeff"]), bits(plain["coeff"]))
+    # an axis no plane of the scene is perpendicular / parallel to within a tiny eps: every model fails isModelValid
+    none = O.sac_plane_model(rem, 1, np.array([1.0, 0.0, 0.0], np.float32), 1e-4)
+    assert len(none["inliers"]) == 0
+
+
+def test_surface_normal_estimation_recovers_the_box_frame(params):
+    """surface_normal_estimation.cpp:182-237 on a corner-on 200 x 75 x 100 mm box: three faces, a right-handed near-orthonormal
+    frame whose z column is the table normal, and the point-count ordering of the node."""
+    for seed in (0, 1, 2):
+        rem, table = _remain_of("tallbox", seed, params)
+        ok, r = O.surface_normals(rem, table[:3])
+        assert ok and list(r.n_in)[0] == len(rem)
+        n = list(r.n_plane)
+        assert n[0] > 0 and n[1] > 0 and n[2] > 0 and sum(n) + r.n_left == len(rem)
+        Rt = np.array(list(r.Rt), np.float64).reshape(4, 4)
+        R = Rt[:3, :3]
+        assert abs(np.linalg.det(R) - 1.0) < 0.02 and np.abs(R.T @ R - np.eye(3)).max() < 0.12
+        cnt = [n[k] for k in r.order]
+        assert cnt[0] >= cnt[1] >= cnt[2]
+        zcol = R[:, 2]                                   # normals[0] = the plane with most points = the top face here
+        assert abs(abs(float(zcol @ table[:3])) - 1.0) < 0.02
+        assert 0.3 < Rt[2, 3] < 0.7                       # centroid in front of the camera
+
+
+def test_surface_pose_host_function_matches_oracle():
+    """cuboid_surface_pose (host arithmetic behind the C ABI, no GPU needed) against the oracle's restatement, including the
+    node's exchange-sort quirk and the handedness flip."""
+    import ctypes as C
+    from perception_b200 import api
+    L = api.load()
+    rng = np.random.default_rng(5)
+    for trial in range(40):
+        coeff = rng.normal(size=(3, 4)).astype(np.float32)
+        coeff[:, :3] /= np.linalg.norm(coeff[:, :3], axis=1, keepdims=True)
+        mid = rng.uniform(-0.5, 0.5, size=(3, 3)).astype(np.float32)
+        cnt = rng.integers(0, 6, size=3).astype(np.int32) if trial % 2 else rng.integers(0, 2000, size=3).astype(np.int32)
+        Rt_o, ord_o = np.zeros(16, np.float32), np.zeros(3, np.int32)
+        O.lib().orc_surface_pose(O._p(coeff), O._p(mid), O._p(cnt), O._p(Rt_o), O._p(ord_o))
+        Rt_g, ord_g, pose = np.zeros(16, np.float32), np.zeros(3, np.int32), np.zeros(7, np.float64)
+        L.cuboid_surface_pose(api._ptr(coeff), api._ptr(mid), api._ptr(cnt), api._ptr(Rt_g), api._ptr(ord_g), api._ptr(pose))
+        assert np.array_equal(bits(Rt_g), bits(Rt_o)) and list(ord_g) == list(ord_o)
+        assert np.allclose(pose[:3], Rt_g.reshape(4, 4)[:3, 3].astype(np.float64))
+        assert abs(np.linalg.norm(pose[3:]) - 1.0) < 0.6    # tf's quaternion of a not-quite-orthonormal matrix

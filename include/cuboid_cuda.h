@@ -205,6 +205,26 @@ int cuboid_batch_fetch(cuboid_handle* h, int frame, int what, void* out, int cap
 void cuboid_pose_from_transform(const float T[16], double H_out[16], double pose7_out[7]);
 void cuboid_bbox_corners(const double H[16], double l, double w, double hgt, float corners_xyzw_out[32]);
 
+/* ---- object_pose_detection service bookkeeping (opd.cpp:212-247, 365-441) — host logic over one frame result ------------
+ * The service runs ICP per cluster against the requested template, retries the (deterministic) ICP until it converged
+ * with fitness < icp_fitness_score or 11 attempts were made (:215-246, quirk Q4), scores every cluster by
+ * |cluster points - template points| (:411), takes the first minimum below 1000 (:415-422) and succeeds iff that
+ * difference is < 250 (:429, quirk Q5). It then reads icp_transforms[argmin], a vector with one entry per ATTEMPT
+ * (:230 vs :426, quirk Q3): `reference_cluster` is the cluster whose transform that actually is; `argmin` is the
+ * cluster the node meant. H_* = getFinalTransformation().cast<double>().inverse() of those clusters (:229). */
+typedef struct {
+    int32_t n_clusters;
+    int32_t argmin;                          /* -1: no cluster within 1000 points of the template (the node then reads out of bounds) */
+    int32_t success;                         /* res.success */
+    int32_t reference_cluster;               /* cluster owning icp_transforms[argmin] in the reference (== argmin unless an earlier cluster retried) */
+    int32_t attempts[CUBOID_MAX_CLUSTERS];   /* ICP runs the reference would have made for cluster i: 1 or 11 */
+    double diff_score[CUBOID_MAX_CLUSTERS];
+    double icp_score[CUBOID_MAX_CLUSTERS];
+    double H_argmin[16], H_reference[16];    /* row-major 4x4, identity when undefined */
+} cuboid_object_selection;
+int cuboid_select_object(const cuboid_frame_result* frame, int template_points, double icp_fitness_score,
+                         cuboid_object_selection* out);
+
 /* ---- multi-GPU (frames sharded by the caller) ------------------------------- */
 /* Packs (fitness, guess id) into one ordered 64-bit key so a single NCCL/gloo MIN all-reduce picks
  * the winner with the lowest-guess tie-break, independent of the GPU count. */

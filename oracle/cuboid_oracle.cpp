@@ -997,6 +997,29 @@ void orc_surface_pose(const float coeff[12], const float midpoint[9], const int3
     for (int i = 0; i < 3; ++i) order[i] = ord[i];
 }
 
+int orc_select_object(const int32_t* sizes, const int32_t* converged, const double* fitness, int n_clusters, int template_points,
+                      double icp_fitness_score, int32_t* argmin_out, int32_t* reference_cluster, int32_t* attempts) {
+    std::vector<int> icp_transforms;      /* which cluster each pushed transform belongs to */
+    std::vector<double> diff_scores;
+    for (int c = 0; c < n_clusters; ++c) {
+        int max_iter = 0;
+        while (true) {                     /* icp_registration: the same deterministic ICP again and again */
+            icp_transforms.push_back(c);
+            ++max_iter;
+            if ((converged[c] && fitness[c] < icp_fitness_score) || max_iter > 10) break;
+        }
+        if (attempts) attempts[c] = max_iter;
+        diff_scores.push_back((double)std::abs((int)sizes[c] - template_points));
+    }
+    double min_score = 1000;
+    int argmin = -1;
+    for (size_t i = 0; i < diff_scores.size(); ++i)
+        if (diff_scores[i] < min_score) { argmin = (int)i; min_score = diff_scores[i]; }
+    *argmin_out = argmin;
+    *reference_cluster = (argmin >= 0 && argmin < (int)icp_transforms.size()) ? icp_transforms[argmin] : -1;
+    return (argmin >= 0 && min_score < 250) ? 1 : 0;
+}
+
 // bbox_filter.cpp:30-51: u, v, w are accumulated in double (the matrix is vector<double>) and stored to float; the
 // perspective divide and the comparisons against the int rectangle run in float; a point is kept only strictly inside.
 int orc_bbox_filter(const float* xyzw, int n, const double P[12], const int32_t bbox[4], float* out_xyzw, int32_t* idx_out) {

@@ -130,6 +130,12 @@ int orc_surface_normals(const float* xyzw, int n, const float axis[3], double ep
                         uint32_t seed, int mode, orc_surface_result* out);
 void orc_surface_pose(const float coeff[12], const float midpoint[9], const int32_t n_plane[3], float Rt[16], int32_t order[3]);
 
+/* f4: object_pose_detection service bookkeeping, simulated literally with the node's own containers (opd.cpp:212-247 retry
+ * loop pushing one transform per attempt, :365-441 diff scores, argmin, success). sizes/converged/fitness per cluster in
+ * cluster order. Returns success; *argmin, *reference_cluster (owner of icp_transforms[argmin], -1 if out of range), attempts[]. */
+int orc_select_object(const int32_t* sizes, const int32_t* converged, const double* fitness, int n_clusters, int template_points,
+                      double icp_fitness_score, int32_t* argmin, int32_t* reference_cluster, int32_t* attempts);
+
 /* f3: bbox_filter's within_bbox + ExtractIndices (cuboid_detection/src/bbox_filter.cpp:30-51, 89-103): keep point i iff its
  * projection through the 3x4 CameraInfo P lies strictly inside the rectangle (x1,y1,x2,y2). Pinned by the reference
  * source itself (no third-party arithmetic). idx_out may be NULL. Returns count. */

@@ -35,7 +35,7 @@ ABI_SYMBOLS = [
     "cuboid_pack_fitness_key", "cuboid_unpack_fitness_key", "cuboid_strerror", "cuboid_last_error",
     "cuboid_abi_version", "cuboid_params_size", "cuboid_frame_result_size", "cuboid_launch_count",
     "cuboid_stage_ms", "cuboid_measure_fp32_peak", "cuboid_set_option", "cuboid_icp_work",
-    "cuboid_bbox_filter", "cuboid_set_bbox_filter", "cuboid_surface_normals", "cuboid_surface_pose",
+    "cuboid_bbox_filter", "cuboid_set_bbox_filter", "cuboid_surface_normals", "cuboid_surface_pose", "cuboid_select_object",
 ]
 OPT_ICP_CULL, OPT_TAPS, OPT_STAGES, OPT_FRONTEND = 1, 2, 3, 4
 
@@ -45,6 +45,22 @@ class SurfaceResult(C.Structure):
     _fields_ = [("coeff", (C.c_float * 4) * 3), ("midpoint", (C.c_float * 3) * 3), ("n_plane", C.c_int32 * 3),
                 ("found", C.c_int32 * 3), ("n_in", C.c_int32 * 3), ("n_left", C.c_int32), ("order", C.c_int32 * 3),
                 ("Rt", C.c_float * 16), ("pose7", C.c_double * 7)]
+
+
+class ObjectSelection(C.Structure):
+    """cuboid_object_selection (include/cuboid_cuda.h)."""
+    _fields_ = [("n_clusters", C.c_int32), ("argmin", C.c_int32), ("success", C.c_int32), ("reference_cluster", C.c_int32),
+                ("attempts", C.c_int32 * MAX_CLUSTERS), ("diff_score", C.c_double * MAX_CLUSTERS),
+                ("icp_score", C.c_double * MAX_CLUSTERS), ("H_argmin", C.c_double * 16), ("H_reference", C.c_double * 16)]
+
+
+def select_object(frame_result, template_points, icp_fitness_score):
+    """object_pose_detection service bookkeeping over one FrameResult (host logic, no GPU)."""
+    out = ObjectSelection()
+    st = load().cuboid_select_object(C.byref(frame_result), int(template_points), float(icp_fitness_score), C.byref(out))
+    if st != OK:
+        raise CuboidError(st, "cuboid_select_object")
+    return out
 
 
 class CuboidError(RuntimeError):
@@ -106,6 +122,7 @@ def load():
     L.cuboid_surface_normals.argtypes = [vp, vp, i32, vp, C.c_double, C.c_double, C.POINTER(SurfaceResult)]
     L.cuboid_surface_pose.argtypes = [vp, vp, vp, vp, vp, vp]
     L.cuboid_surface_pose.restype = None
+    L.cuboid_select_object.argtypes = [C.POINTER(FrameResult), i32, C.c_double, C.POINTER(ObjectSelection)]
     if L.cuboid_params_size() != C.sizeof(CuboidParams) or L.cuboid_frame_result_size() != C.sizeof(FrameResult):
         raise ImportError("struct layout mismatch between params.py and include/cuboid_cuda.h")
     _lib = L

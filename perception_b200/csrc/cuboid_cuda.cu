@@ -1240,6 +1240,36 @@ void cuboid_bbox_corners(const double H[16], double l, double w, double hgt, flo
     }
 }
 
+// opd.cpp:365-441 service bookkeeping, see the header
+int cuboid_select_object(const cuboid_frame_result* fr, int template_points, double icp_fitness_score, cuboid_object_selection* out) {
+    if (!fr || !out || template_points < 0) return CUBOID_E_INVALID;
+    std::memset(out, 0, sizeof(*out));
+    for (int k = 0; k < 16; ++k) out->H_argmin[k] = out->H_reference[k] = (k % 5 == 0) ? 1.0 : 0.0;
+    const int nc = std::min(std::max(fr->n_clusters, 0), (int)CUBOID_MAX_CLUSTERS);
+    out->n_clusters = nc;
+    out->argmin = -1; out->reference_cluster = -1;
+    double min_score = 1000.0;
+    for (int i = 0; i < nc; ++i) {
+        const cuboid_cluster_result& c = fr->cluster[i];
+        out->attempts[i] = (c.converged && c.fitness < icp_fitness_score) ? 1 : 11;
+        out->icp_score[i] = c.fitness;
+        out->diff_score[i] = (double)std::abs(c.size - template_points);
+        if (out->diff_score[i] < min_score) { out->argmin = i; min_score = out->diff_score[i]; }
+    }
+    if (out->argmin >= 0) {
+        double pose[7];
+        cuboid_pose_from_transform(fr->cluster[out->argmin].T, out->H_argmin, pose);
+        int first = 0;   // icp_transforms[argmin]: entry `argmin` of a list holding attempts[i] copies of cluster i's transform
+        for (int i = 0; i < nc; ++i) {
+            if (out->argmin < first + out->attempts[i]) { out->reference_cluster = i; break; }
+            first += out->attempts[i];
+        }
+        if (out->reference_cluster >= 0) cuboid_pose_from_transform(fr->cluster[out->reference_cluster].T, out->H_reference, pose);
+    }
+    out->success = (out->argmin >= 0 && min_score < 250.0) ? 1 : 0;
+    return CUBOID_OK;
+}
+
 uint64_t cuboid_pack_fitness_key(double fitness, int32_t guess_id) {
     // Non-negative doubles order like their bit patterns. The key is that pattern with its low 16 bits replaced
     // by the guess id, so one unsigned MIN all-reduce orders by fitness first and by guess id among fitness

@@ -83,3 +83,41 @@ def test_fitness_key_orders_by_fitness_then_guess():
     assert g == 17 and abs(f - 7.38e-6) / 7.38e-6 < 1e-10
     assert k(float("nan"), 0) > k(1e300, 65535)
     assert k(1e-6, 0) < 2 ** 63   # fits a signed int64 all-reduce
+
+
+def test_service_selection_matches_the_literal_simulation():
+    """cuboid_select_object (opd.cpp:365-441 bookkeeping incl. quirks Q3-Q5) against the oracle, which replays the node's own
+    containers attempt by attempt."""
+    import ctypes as C
+    from oracle import pyoracle as O
+    from perception_b200.params import FrameResult
+    rng = np.random.default_rng(11)
+    seen_mismatch = False
+    for trial in range(200):
+        fr = FrameResult()
+        nc = int(rng.integers(0, 7))
+        fr.n_clusters = nc
+        tmpl = int(rng.integers(300, 5000))
+        gate = 0.0004
+        for i in range(nc):
+            c = fr.cluster[i]
+            c.size = int(tmpl + rng.integers(-1500, 1500))
+            c.converged = int(rng.random() < 0.8)
+            c.fitness = float(rng.choice([1e-5, 3e-4, 5e-4, 2e-3]))
+            T = np.eye(4, dtype=np.float32)
+            T[:3, 3] = rng.normal(size=3)
+            for k in range(16):
+                c.T[k] = float(T.reshape(-1)[k])
+        sel = api.select_object(fr, tmpl, gate)
+        sizes = np.array([fr.cluster[i].size for i in range(nc)] + [0], np.int32)
+        conv = np.array([fr.cluster[i].converged for i in range(nc)] + [0], np.int32)
+        fit = np.array([fr.cluster[i].fitness for i in range(nc)] + [0.0], np.float64)
+        am, rc, att = C.c_int32(0), C.c_int32(0), np.zeros(8, np.int32)
+        ok = O.lib().orc_select_object(O._p(sizes), O._p(conv), O._p(fit), nc, tmpl, C.c_double(gate), C.byref(am), C.byref(rc), O._p(att))
+        assert (sel.success, sel.argmin, sel.reference_cluster) == (ok, am.value, rc.value)
+        assert list(sel.attempts)[:nc] == list(att[:nc])
+        if sel.argmin >= 0:
+            H = np.array(list(sel.H_argmin)).reshape(4, 4)
+            assert np.allclose(H[:3, 3], -np.array(list(fr.cluster[sel.argmin].T)).reshape(4, 4)[:3, 3], atol=1e-6)
+            seen_mismatch = seen_mismatch or sel.reference_cluster != sel.argmin
+    assert seen_mismatch      # quirk Q3 shows up: a retried earlier cluster shifts icp_transforms[argmin]

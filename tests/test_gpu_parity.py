@@ -467,3 +467,24 @@ def test_surface_normal_estimation_matches_oracle(cc, params):
     # constrained single segmentation through the same kernel: inlier sets equal
     empty = cc.surface_normals(np.zeros((0, 4), np.float32), [0.0, 0.0, 1.0])
     assert list(empty.n_plane) == [0, 0, 0] and empty.n_left == 0
+
+
+def test_icp_on_the_reference_real_scan_returns_the_published_pose(golden, params):
+    """The reference's real marker scan pair (tests/golden, SURVEY 8c fixture 4) through the GPU ICP: bit-equal to the oracle
+    and equal to the capture pose of transforms.txt:74-83 within the north_star tolerances."""
+    from test_oracle import scan_case
+    cap, tpl, T = scan_case(golden)
+    K = np.array([[0, 0, 0], [0, 0, -1], [0, 1, 0]], float)
+    dR = np.eye(3) + np.sin(0.002) * K + (1 - np.cos(0.002)) * K @ K
+    G = np.eye(4)
+    G[:3, :3], G[:3, 3] = dR @ T[:3, :3], T[:3, 3] + 0.0005
+    with api.CuboidCuda(params, max_points=640 * 480, max_batch=1) as h:
+        h.set_template(0, tpl)
+        g = h.icp(cap, 0, guesses=[G.astype(np.float32)])
+        far = h.icp(cap, 0)                                   # from identity: whatever minimum ICP slides into, same as the oracle
+    ref = O.icp(cap, tpl, guess=G.astype(np.float32), rel_mse=params.icp_rel_mse)
+    assert g["iters"] == ref["iters"] and g["corr_hash"] == ref["corr_hash"] and g["fitness"] == ref["fitness"]
+    assert np.array_equal(bits(g["T"]), bits(ref["T"]))
+    assert _pose_close(g["T"], T) and g["fitness"] < 1e-12
+    ref_far = O.icp(cap, tpl, rel_mse=params.icp_rel_mse)
+    assert far["iters"] == ref_far["iters"] and far["corr_hash"] == ref_far["corr_hash"] and np.array_equal(bits(far["T"]), bits(ref_far["T"]))

@@ -309,3 +309,47 @@ def test_surface_pose_host_function_matches_oracle():
         assert np.array_equal(bits(Rt_g), bits(Rt_o)) and list(ord_g) == list(ord_o)
         assert np.allclose(pose[:3], Rt_g.reshape(4, 4)[:3, 3].astype(np.float64))
         assert abs(np.linalg.norm(pose[3:]) - 1.0) < 0.6    # tf's quaternion of a not-quite-orthonormal matrix
+
+
+def _quat_R(q):
+    x, y, z, w = q
+    return np.array([[1 - 2 * (y * y + z * z), 2 * (x * y - z * w), 2 * (x * z + y * w)],
+                     [2 * (x * y + z * w), 1 - 2 * (x * x + z * z), 2 * (y * z - x * w)],
+                     [2 * (x * z - y * w), 2 * (y * z + x * w), 1 - 2 * (x * x + y * y)]])
+
+
+def scan_case(golden):
+    """The reference's real marker scan, its template-frame copy and the capture pose published for them."""
+    import os
+    from perception_b200 import pcd
+    from conftest import GOLD
+    g = golden["object_scan"]
+    cap = pcd.load_pcd(os.path.join(GOLD, g["capture"]))
+    tpl = pcd.load_pcd(os.path.join(GOLD, g["template_frame"]))
+    T = np.eye(4)
+    T[:3, :3], T[:3, 3] = _quat_R(g["rotation_xyzw"]), g["translation"]
+    return cap, tpl, T
+
+
+def test_icp_reproduces_the_published_capture_pose_of_a_real_scan(golden):
+    """Known answer from the reference's own data (SURVEY 8c fixture 4): marker_ascii_tf.pcd IS marker_ascii.pcd moved by the
+    pose in transforms.txt:74-83, so ICP of the capture onto the template-frame copy, started next to that pose, must return it (north_star tolerances: 1e-4 rad, 1e-5 m) with a vanishing fitness."""
+    cap, tpl, T = scan_case(golden)
+    assert len(cap) == len(tpl) == 597
+    moved = cap[:, :3].astype(np.float64) @ T[:3, :3].T + T[:3, 3]
+    assert np.abs(moved - tpl[:, :3]).max() < 1e-7                  # the fixture's own relation
+    # point-to-point ICP on a thin object slides into nearby local minima, so the start has to be inside the basin of the
+    # one-to-one correspondence (point spacing of the scan is ~1 mm)
+    for k, (ang, off) in enumerate(((0.002, 0.0005), (-0.001, -0.0003), (0.0015, 0.0006))):
+        ax = np.eye(3)[k]
+        K = np.array([[0, -ax[2], ax[1]], [ax[2], 0, -ax[0]], [-ax[1], ax[0], 0]])
+        dR = np.eye(3) + np.sin(ang) * K + (1 - np.cos(ang)) * K @ K
+        G = np.eye(4)
+        G[:3, :3], G[:3, 3] = dR @ T[:3, :3], T[:3, 3] + off
+        r = O.icp(cap, tpl, guess=G.astype(np.float32), rel_mse=0.0004)
+        assert r["converged"]
+        Tr = r["T"].astype(np.float64)
+        D = Tr[:3, :3] @ T[:3, :3].T
+        rot_err = np.linalg.norm([D[2, 1] - D[1, 2], D[0, 2] - D[2, 0], D[1, 0] - D[0, 1]]) / 2
+        assert rot_err < 1e-4 and np.abs(Tr[:3, 3] - T[:3, 3]).max() < 1e-5, (rot_err, Tr[:3, 3] - T[:3, 3])
+        assert r["fitness"] < 1e-12

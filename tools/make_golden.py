@@ -5,6 +5,9 @@
    .pcd the reference ships (it is: SURVEY.md probe B3).
 2. Records the image_geometry unprojection known answer (vision_opencv/image_geometry/test/utest.cpp:25-27,56-65).
 3. Stores oracle outputs for two seeded frames (a regression pin of the oracle against itself, NOT a reference pin).
+4. Copies the reference's real object scans with a published answer (SURVEY.md 8c fixture 4): object_detection/templates/
+   marker_ascii.pcd (the capture, camera frame) and marker_ascii_tf.pcd (the same 597 points in the template frame), plus the
+   capture pose listed for them in object_detection/templates/transforms.txt:74-83. These are data, not code.
 """
 import hashlib
 import json
@@ -64,6 +67,18 @@ def main():
                        "remain_hash": r.remain_hash, "cluster_hash": r.cluster_hash, "icp_iterations": c.iterations,
                        "icp_state": c.state, "icp_fitness": c.fitness, "icp_T": list(c.T), "icp_corr_hash": c.corr_hash})
     meta["oracle_frames"] = frames
+    scans = os.path.join(REF, "object_detection", "templates")
+    for name in ("marker_ascii.pcd", "marker_ascii_tf.pcd"):
+        shutil.copy(os.path.join(scans, name), os.path.join(GOLD, name))
+        os.chmod(os.path.join(GOLD, name), 0o644)
+    meta["object_scan"] = {
+        "source": "object_detection/templates/marker_ascii.pcd, marker_ascii_tf.pcd, transforms.txt:74-83",
+        "capture": "marker_ascii.pcd", "template_frame": "marker_ascii_tf.pcd",
+        "sha256": {n: sha(os.path.join(GOLD, n)) for n in ("marker_ascii.pcd", "marker_ascii_tf.pcd")},
+        "translation": [-0.0108, -0.4808, -0.3096],
+        "rotation_xyzw": [-0.342422592276, 0.0607978149491, 0.0275301284879, 0.937172602044],
+        "relation": "template_frame = R(rotation) * capture + translation (verified to 3e-8 when the fixture was made)",
+    }
     json.dump(meta, open(os.path.join(GOLD, "golden.json"), "w"), indent=1)
     print(json.dumps(meta["templates"], indent=1))
 

@@ -32,7 +32,7 @@ struct CluArgs {
     int min_size, max_size, use_cluster;
 };
 
-constexpr int CLU_THREADS = 1024;
+constexpr int CLU_THREADS = 1024;    // small per-frame problems, latency bound: several CTAs per SM beat one wide CTA
 
 __device__ __forceinline__ unsigned int cell_hash(int cx, int cy, int cz) {
     return ((unsigned int)cx * 73856093u) ^ ((unsigned int)cy * 19349663u) ^ ((unsigned int)cz * 83492791u);
@@ -59,8 +59,8 @@ __device__ __forceinline__ void uf_unite(int* parent, int a, int b) {
 // MODE 0: n <= CLU_SMEM_ALL: union-find forest, bucket table and bucketed points all in shared memory
 // MODE 1: n <= CLU_SMEM_UF : forest in shared memory, grid in global memory
 // MODE 2: everything in global memory
-constexpr int CLU_SMEM_ALL = 4096;
-constexpr int CLU_SMEM_UF = 16384;
+constexpr int CLU_SMEM_ALL = 2048;
+constexpr int CLU_SMEM_UF = 12288;
 template <int MODE>
 __device__ __forceinline__ void cluster_body(const CluArgs& a) {
     __shared__ int s_w[CLU_THREADS / 32 + 1];
@@ -251,6 +251,6 @@ __global__ void __launch_bounds__(CLU_THREADS) k_cluster(const CluArgs a) {
     else if (n <= CLU_SMEM_UF) cluster_body<1>(a);
     else cluster_body<2>(a);
 }
-constexpr size_t CLU_DYN_SMEM = (size_t)CLU_SMEM_ALL * 4 + (size_t)CLU_SMEM_ALL * 16 + (size_t)(CLU_SMEM_ALL + 4) * 4;   // 98 320 B >= 16384*4
+constexpr size_t CLU_DYN_SMEM = (size_t)CLU_SMEM_ALL * 4 + (size_t)CLU_SMEM_ALL * 16 + (size_t)(CLU_SMEM_ALL + 4) * 4;   // 49 168 B >= 12288*4
 
 }  // namespace cuboid

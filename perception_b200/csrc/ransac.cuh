@@ -47,7 +47,8 @@ struct SacArgs {
 };
 
 constexpr int SAC_THREADS = 256;
-constexpr int SAC_TILE = 2048;      // points per shared-memory tile (32 KB), two buffers
+constexpr int SAC_TILE = 1024;      // points per shared-memory tile (16 KB), two buffers
+constexpr int SAC_PROD = 512;       // inliers per refine chunk; the product rows live in the (then idle) tile buffers
 constexpr int SAC_HB = 32;          // hypotheses scored per round (first round: 8)
 
 struct SacHyp { float c[4]; int valid; int kind; int ok; };   // kind: 0 normal, 1 sampler gave up (selection.empty()); ok: isModelValid()
@@ -203,12 +204,11 @@ __device__ void sac_refine_from_sums(const float* acc_in, int count, float cout[
 }
 
 struct SacShared {
-    float4 tile[2][SAC_TILE];          // 64 KB
+    float4 tile[2][SAC_TILE];          // 32 KB; after the scoring loop the same bytes hold float prod[9][SAC_PROD + 1] (18 KB)
     unsigned long long bar[2];
     SacHyp hyp[SAC_HB];
     int counts[SAC_HB];
     int s_w[9];
-    float prod[9][1025];               // refine: per-accumulator product rows (padded: conflict-free lanes)
     float sums[9];
     float best_c[4], coeff[4];
     int n_hyp, done, have_model, rp, n_inl_pre, n_inl, n_rem;
@@ -397,18 +397,19 @@ __global__ void __launch_bounds__(SAC_THREADS, 1) k_sac_plane(const SacArgs a) {
             // PCL accumulates the 9 sums sequentially in float over the inliers in index order.
             if (threadIdx.x < 9) S.sums[threadIdx.x] = 0.0f;
             __syncthreads();
-            for (int start = 0; start < n_pre; start += 1024) {
-                const int m = min(1024, n_pre - start);
+            float (*prod)[SAC_PROD + 1] = reinterpret_cast<float (*)[SAC_PROD + 1]>(&S.tile[0][0]);   // padded rows: conflict-free lanes
+            for (int start = 0; start < n_pre; start += SAC_PROD) {
+                const int m = min(SAC_PROD, n_pre - start);
                 for (int j = threadIdx.x; j < m; j += SAC_THREADS) {
                     const float4 p = vox[inl_pre[start + j]];
-                    S.prod[0][j] = p.x * p.x; S.prod[1][j] = p.x * p.y; S.prod[2][j] = p.x * p.z;
-                    S.prod[3][j] = p.y * p.y; S.prod[4][j] = p.y * p.z; S.prod[5][j] = p.z * p.z;
-                    S.prod[6][j] = p.x; S.prod[7][j] = p.y; S.prod[8][j] = p.z;
+                    prod[0][j] = p.x * p.x; prod[1][j] = p.x * p.y; prod[2][j] = p.x * p.z;
+                    prod[3][j] = p.y * p.y; prod[4][j] = p.y * p.z; prod[5][j] = p.z * p.z;
+                    prod[6][j] = p.x; prod[7][j] = p.y; prod[8][j] = p.z;
                 }
                 __syncthreads();
                 if (threadIdx.x < 9) {
                     float acc = S.sums[threadIdx.x];
-                    const float* row = S.prod[threadIdx.x];
+                    const float* row = prod[threadIdx.x];
 #pragma unroll 8
                     for (int j = 0; j < m; ++j) acc += row[j];
                     S.sums[threadIdx.x] = acc;

@@ -57,6 +57,8 @@ struct cuboid_handle {
     float4* d_remain = nullptr;
     int *d_parent = nullptr, *d_csize = nullptr, *d_crank = nullptr, *d_idx_sorted = nullptr, *d_offsets = nullptr, *d_roots = nullptr, *d_cell_head = nullptr; float4* d_cell_pts = nullptr;
     float4* d_cur = nullptr; int* d_corr = nullptr; float* d_cd = nullptr; int* d_order = nullptr; IcpOut* d_icp_out = nullptr;
+    IcpState* d_icp_state = nullptr; IcpSlot* d_icp_ring = nullptr; IcpQueue* d_icp_queue = nullptr;   // persistent time-sliced k_icp
+    int icp_slice_iters = 8; int icp_ctas = 0;
     size_t icp_scratch_elems = 0; size_t icp_out_elems = 0;
     FrameScratch* d_scr = nullptr;
     unsigned long long *d_desc1 = nullptr, *d_desc2 = nullptr;
@@ -153,9 +155,12 @@ int ensure_icp_scratch(cuboid_handle* h, int frames, int n_guess) {
     }
     const size_t need_out = (size_t)frames * CUBOID_MAX_CLUSTERS * n_guess;
     if (need_out > h->icp_out_elems) {
-        if (h->d_icp_out) cudaFree(h->d_icp_out);
-        h->d_icp_out = nullptr; h->icp_out_elems = 0;
+        if (h->d_icp_out) { cudaFree(h->d_icp_out); cudaFree(h->d_icp_state); cudaFree(h->d_icp_ring); cudaFree(h->d_icp_queue); }
+        h->d_icp_out = nullptr; h->d_icp_state = nullptr; h->d_icp_ring = nullptr; h->d_icp_queue = nullptr; h->icp_out_elems = 0;
         CKS(h, dalloc(h, &h->d_icp_out, need_out));
+        CKS(h, dalloc(h, &h->d_icp_state, need_out));
+        CKS(h, dalloc(h, &h->d_icp_ring, need_out));
+        CKS(h, dalloc(h, &h->d_icp_queue, (size_t)frames));   // one queue header per possible first frame of a launch
         h->icp_out_elems = need_out;
     }
     return CUBOID_OK;
@@ -357,7 +362,19 @@ int run_chunk(cuboid_handle* h, const ChunkIn& in, int nf, cuboid_frame_result* 
         a.work = h->d_work;
         a.corr_trace = trace_corr; a.T_trace = trace_T; a.cap_trace = cap_trace;
         const size_t dyn = box_bytes + (a.resident ? (size_t)a.Tpad * 12 : 0);
-        k_icp<<<dim3(ng, CUBOID_MAX_CLUSTERS, nf), ICP_THREADS, dyn, st>>>(a);
+        // persistent, time-sliced: k_icp_init builds every problem's state and queue entry, then a fixed crew of CTAs (two per
+        // SM, no more than there can be problems) serves slices of icp_slice_iters iterations until all problems are finished
+        const size_t oS = (size_t)f0 * CUBOID_MAX_CLUSTERS * ng;
+        a.pstate = h->d_icp_state + oS; a.ring = h->d_icp_ring + oS; a.queue = h->d_icp_queue + f0;
+        a.n_slots = nf * CUBOID_MAX_CLUSTERS * ng;
+        a.slice_iters = std::max(1, h->icp_slice_iters);
+        a.init_smem = 65536;
+        CK(h, cudaMemsetAsync(a.queue, 0, sizeof(IcpQueue), st));
+        CK(h, cudaMemsetAsync(a.ring, 0, sizeof(IcpSlot) * (size_t)a.n_slots, st));
+        a.crew = (int)std::max<long long>(1, std::min<long long>(h->icp_ctas, (long long)nf * ng * CUBOID_MAX_CLUSTERS));
+        k_icp_init<<<dim3(ng, CUBOID_MAX_CLUSTERS, nf), ICP_THREADS, a.init_smem, st>>>(a);
+        k_icp<<<a.crew, ICP_THREADS, dyn, st>>>(a);   // workers beyond the number of real problems leave at once
+        ++h->launches;
         const int tot = nf * CUBOID_MAX_CLUSTERS;
         k_icp_select<<<(tot + 127) / 128, 128, 0, st>>>(b_out, d_res, nf, ng, p.icp_fitness_gate, h->d_cur + oG, h->M, b_offsets,
                                                      h->KC, aligned);
@@ -492,6 +509,13 @@ int cuboid_create(cuboid_handle** out, const cuboid_params* p, int device, int m
     cudaDeviceGetAttribute(&h->smem_optin, cudaDevAttrMaxSharedMemoryPerBlockOptin, device);
     h->icp_smem_budget = h->smem_optin - 4096;   // static shared memory of k_icp stays well below 4 KB
     if (cudaFuncSetAttribute(k_icp, cudaFuncAttributeMaxDynamicSharedMemorySize, h->icp_smem_budget) != cudaSuccess) return fail(CUBOID_E_CUDA);
+    if (cudaFuncSetAttribute(k_icp_init, cudaFuncAttributeMaxDynamicSharedMemorySize, 65536) != cudaSuccess) return fail(CUBOID_E_CUDA);
+    {
+        int sms = 0;
+        cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, device);
+        h->icp_ctas = 2 * sms;
+        const char* es = std::getenv("CUBOID_ICP_SLICE"); if (es) h->icp_slice_iters = std::max(1, atoi(es));
+    }
     {   // fused front end: cluster size and the number of clusters the device keeps resident
         const char* ef = std::getenv("CUBOID_FRONTEND"); if (ef) h->frontend = atoi(ef) ? 1 : 0;
         const char* ec = std::getenv("CUBOID_FE_CLUSTER"); if (ec) h->fe_cluster = std::max(1, std::min(16, atoi(ec)));
@@ -545,7 +569,7 @@ int cuboid_destroy(cuboid_handle* h) {
     if (h->stream) cudaStreamSynchronize(h->stream);
     void* ptrs[] = {h->d_depth, h->d_blob, h->d_n_in, h->d_xr, h->d_yr, h->d_pts, h->d_keysA, h->d_keysB, h->d_kpp, h->d_hist, h->d_vox, h->d_vcount, h->d_shuffled,
                     h->d_inl_pre, h->d_inl, h->d_remain, h->d_parent, h->d_csize, h->d_crank, h->d_idx_sorted, h->d_offsets, h->d_roots, h->d_cell_head, h->d_cell_pts,
-                    h->d_cur, h->d_corr, h->d_cd, h->d_order, h->d_icp_out, h->d_scr, h->d_desc1, h->d_desc2, h->d_ticket, h->d_res, h->d_rng,
+                    h->d_cur, h->d_corr, h->d_cd, h->d_order, h->d_icp_out, h->d_icp_state, h->d_icp_ring, h->d_icp_queue, h->d_scr, h->d_desc1, h->d_desc2, h->d_ticket, h->d_res, h->d_rng,
                     h->d_triplets, h->d_guesses, h->d_trace_corr, h->d_trace_T, h->d_aligned, h->d_work, h->d_fe_keys};
     for (void* q : ptrs) if (q) cudaFree(q);
     for (auto& t : h->d_tmpl) if (t) cudaFree(t);

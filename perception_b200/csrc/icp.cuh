@@ -59,6 +59,12 @@ struct IcpArgs {
     int cull;                // 1: skip subtrees whose AABB lower bound exceeds the running minimum (exact)
     unsigned long long* work;   // [2] += (source-template pairs evaluated, brute-force pairs S*T per pass) or NULL
     int* corr_trace; float* T_trace; int cap_trace;   // debug taps for problem (0,0,0)
+    // persistent, time-sliced execution (see k_icp)
+    struct IcpState* pstate;   // [problem slots of the launch]
+    struct IcpQueue* queue; struct IcpSlot* ring; int n_slots;
+    int slice_iters;           // iterations per time slice
+    int crew;                  // worker CTAs of k_icp
+    int init_smem;             // dynamic shared memory of k_icp_init (Morton sort window)
 };
 
 constexpr int ICP_THREADS = 512;   // first 256 = the canonical reduction lanes; two CTAs (two ICP problems) share an SM
@@ -291,9 +297,9 @@ __device__ __forceinline__ void icp_nn_pass(const IcpArgs& a, IcpShared& sh, con
         const int k = task * 32 + lane;
         const bool valid = k < S;
         const int i = order[valid ? k : S - 1];   // 32 lanes = 32 spatial neighbours: coherent tree walks, broadcast loads
-        const float4 p = cur[i];
+        const float4 p = __ldcg(cur + i);   // cur / corr / cd travel between SMs from one time slice to the next: read them at L2
         const float sx = p.x, sy = p.y, sz = p.z;
-        int wpos = corr[i];
+        int wpos = __ldcg(corr + i);
         int worig = a.tmpl_orig[wpos];
         float best;
         {
@@ -419,9 +425,65 @@ __device__ void icp_morton_order(const float4* src, const int* idx, int S, int* 
     __syncthreads();
 }
 
-template <bool RESIDENT>
-__device__ __forceinline__ void icp_body(const IcpArgs& a, IcpShared& sh, float* s_tmpl, uint4* s_nodes) {
+// ---- problem state that survives between time slices (global memory) --------------------------------------------------
+struct IcpState {
+    float fin[16];             // final_transformation_
+    double prev_mse;
+    int it, passes, done, converged, state, pad;
+    unsigned long long chash;  // sum of the per-iteration correspondence hashes so far
+    unsigned long long evaluated;
+};
+// Work queue of one launch: a ring with one slot per problem of the launch. A problem is in exactly one place (one slot, or
+// one CTA's hands), so at most n_slots entries are ever unread and a slot is never overwritten before it was read.
+struct IcpQueue {
+    unsigned int head, tail;   // tickets handed to poppers / pushers
+    int n_done, n_total;       // problems finished / problems of this launch (set by k_icp_init)
+    int error;
+    int alive;                 // worker CTAs that have not left yet; a worker leaves when fewer problems than workers remain
+    int pad[2];
+};
+struct IcpSlot { int prob; unsigned int seq; };   // seq == ticket + 1 once the slot holds the entry of that ticket
+
+__device__ __forceinline__ void icp_queue_push(IcpQueue* q, IcpSlot* ring, int n_slots, int prob) {
+    const unsigned int t = atomicAdd(&q->tail, 1u);
+    IcpSlot* sl = ring + (t % (unsigned int)n_slots);
+    sl->prob = prob;
+    __threadfence();
+    ((volatile IcpSlot*)sl)->seq = t + 1u;
+}
+// called by ONE thread; returns the next problem, or -1 when every problem of the launch is finished
+__device__ __forceinline__ int icp_queue_pop(IcpQueue* q, IcpSlot* ring, int n_slots) {
+    volatile IcpQueue* vq = q;
+    const int remaining = vq->n_total - vq->n_done;
+    if (remaining <= 0) return -1;
+    // more workers than unfinished problems: this one is not needed any more (checked BEFORE a ticket is claimed, a claimed
+    // ticket is always waited for). `remaining` only shrinks, so a stale value errs on the side of staying.
+    if (vq->alive > remaining) {
+        if (atomicSub(&q->alive, 1) - 1 >= remaining) return -1;
+        atomicAdd(&q->alive, 1);
+    }
+    const unsigned int t = atomicAdd(&q->head, 1u);
+    volatile IcpSlot* sl = ring + (t % (unsigned int)n_slots);
+    for (unsigned int spin = 0;; ++spin) {
+        if (sl->seq == t + 1u) { __threadfence(); return sl->prob; }
+        if (vq->n_done >= vq->n_total) return -1;
+        if (spin > (1u << 26)) { atomicExch(&q->error, 1); return -1; }   // ~10 s of sleeping: never hang the device
+        __nanosleep(128);
+    }
+}
+
+// k_icp_init: one CTA per (guess, cluster, frame) slot. Empty slots finish at once; the others get their Morton visiting
+// order, the guess-transformed working cloud, seeds, a fresh state, and are pushed on the queue.
+__global__ void __launch_bounds__(ICP_THREADS) k_icp_init(const IcpArgs a) {
+    extern __shared__ __align__(16) unsigned char smem_raw[];
+    __shared__ float s_part[16 * 8];
+    __shared__ float s_red[16];
+    __shared__ float s_guess[16];
     const int g = blockIdx.x, c = blockIdx.y, f = blockIdx.z;
+    const cuboid_frame_result& R = a.res[f];
+    if (blockIdx.x == 0 && blockIdx.y == 0 && blockIdx.z == 0 && threadIdx.x == 0) a.queue->alive = a.crew;
+    if (c >= min(R.n_clusters, CUBOID_MAX_CLUSTERS)) return;   // not a problem: n_total counts only real ones
+    const int prob = (f * CUBOID_MAX_CLUSTERS + c) * a.n_guess + g;
     const int* offsets = a.offsets + (size_t)f * (a.KC + 1);
     const int o0 = offsets[c], S = offsets[c + 1] - o0;
     const int* idx = a.idx_sorted + (size_t)f * a.M + o0;
@@ -429,40 +491,14 @@ __device__ __forceinline__ void icp_body(const IcpArgs& a, IcpShared& sh, float*
     const size_t pbase = ((size_t)f * a.n_guess + g) * a.M + o0;
     float4* cur = a.cur + pbase;
     int* corr = a.corr + pbase;
-    float* cd = a.cd + pbase;
     int* order = a.order + pbase;
-    IcpOut& out = a.out[((size_t)f * CUBOID_MAX_CLUSTERS + c) * a.n_guess + g];
-    const bool trace = a.corr_trace && f == 0 && c == 0 && g == 0;
-    const float* tp = RESIDENT ? s_tmpl : a.tmpl;
     const bool lane_thread = threadIdx.x < ICP_LANES;
-
-    // ---- Morton visiting order, sorted in the (still empty) dynamic shared memory window ----
-    {
-        const int window_bytes = a.nnodes * 16 + (RESIDENT ? a.Tpad * 12 : 0);
-        icp_morton_order(src, idx, S, order, reinterpret_cast<unsigned long long*>(s_nodes), window_bytes / 8, sh.part_f);
-    }
-    // ---- stage the template (resident case) and the BVH nodes with TMA bulk copies ----
-    if (threadIdx.x == 0) {
-        mbar_init(&sh.bar, 1);
-        asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
-        fence_proxy_async();   // generic-proxy writes of the sort happen-before the async-proxy (TMA) writes
-    }
-    __syncthreads();
-    if (threadIdx.x == 0) {
-        const unsigned int tb = RESIDENT ? (unsigned int)a.Tpad * 12u : 0u;
-        const unsigned int bb = (unsigned int)a.nnodes * 16u;
-        mbar_expect_tx(&sh.bar, tb + bb);
-        for (unsigned int off = 0; off < tb; off += 32768u)
-            tma_bulk_g2s(reinterpret_cast<unsigned char*>(s_tmpl) + off, reinterpret_cast<const unsigned char*>(a.tmpl) + off, min(32768u, tb - off), &sh.bar);
-        for (unsigned int off = 0; off < bb; off += 32768u)
-            tma_bulk_g2s(reinterpret_cast<unsigned char*>(s_nodes) + off, reinterpret_cast<const unsigned char*>(a.nodes) + off, min(32768u, bb - off), &sh.bar);
-    }
-
+    icp_morton_order(src, idx, S, order, reinterpret_cast<unsigned long long*>(smem_raw), a.init_smem / 8, s_part);
     // ---- guess: final = guess; src_t = (guess == I) ? src : guess * src ----
     if (threadIdx.x < 16) {
         float v = (threadIdx.x % 5 == 0) ? 1.f : 0.f;
         if (a.guesses && a.guess_mode == 0) v = a.guesses[(size_t)g * 16 + threadIdx.x];
-        sh.guess[threadIdx.x] = v;
+        s_guess[threadIdx.x] = v;
     }
     __syncthreads();
     if (a.guesses && a.guess_mode == 1) {
@@ -473,43 +509,74 @@ __device__ __forceinline__ void icp_body(const IcpArgs& a, IcpShared& sh, float*
                 const float4 p = src[idx[i]];
                 v3[0] = v3[0] + p.x; v3[1] = v3[1] + p.y; v3[2] = v3[2] + p.z;
             }
-        canon_block_reduce<float, 3>(v3, sh.part_f, sh.red_f);
+        canon_block_reduce<float, 3>(v3, s_part, s_red);
         if (threadIdx.x == 0) {
             const float cn = (float)S;
-            const float cx = sh.red_f[0] / cn, cy = sh.red_f[1] / cn, cz = sh.red_f[2] / cn;
+            const float cx = s_red[0] / cn, cy = s_red[1] / cn, cz = s_red[2] / cn;
             const float* Rm = a.guesses + (size_t)g * 9;
             const float cc[3] = {cx, cy, cz};
             for (int i = 0; i < 3; ++i) {
-                for (int j = 0; j < 3; ++j) sh.guess[4 * i + j] = Rm[3 * i + j];
-                sh.guess[4 * i + 3] = cc[i] - ((Rm[3 * i] * cx + Rm[3 * i + 1] * cy) + Rm[3 * i + 2] * cz);
+                for (int j = 0; j < 3; ++j) s_guess[4 * i + j] = Rm[3 * i + j];
+                s_guess[4 * i + 3] = cc[i] - ((Rm[3 * i] * cx + Rm[3 * i + 1] * cy) + Rm[3 * i + 2] * cz);
             }
         }
         __syncthreads();
     }
     bool guess_identity = true;
 #pragma unroll
-    for (int k = 0; k < 16; ++k) guess_identity = guess_identity && (sh.guess[k] == ((k % 5 == 0) ? 1.f : 0.f));
+    for (int k = 0; k < 16; ++k) guess_identity = guess_identity && (s_guess[k] == ((k % 5 == 0) ? 1.f : 0.f));
     for (int i = threadIdx.x; i < S; i += ICP_THREADS) {
         const float4 p = src[idx[i]];
-        cur[i] = guess_identity ? make_float4(p.x, p.y, p.z, 1.0f) : xform(sh.guess, p);
+        cur[i] = guess_identity ? make_float4(p.x, p.y, p.z, 1.0f) : xform(s_guess, p);
         corr[i] = 0;   // seed of the first nearest-neighbour pass: any valid template position
     }
-    if (threadIdx.x < 16) sh.fin[threadIdx.x] = sh.guess[threadIdx.x];
+    __syncthreads();
     if (threadIdx.x == 0) {
-        sh.done = 0; sh.converged = 0; sh.state = CUBOID_ICP_NOT_CONVERGED; sh.iters = 0; sh.prev_mse = 1.7976931348623157e308;
+        IcpState st;
+        for (int k = 0; k < 16; ++k) st.fin[k] = s_guess[k];
+        st.prev_mse = 1.7976931348623157e308;
+        st.it = 0; st.passes = 0; st.converged = 0; st.pad = 0;
+        st.done = S < 3 ? 1 : 0;   // "Not enough correspondences found" -> converged_ = false, no iteration
+        st.state = S < 3 ? CUBOID_ICP_NO_CORRESPONDENCES : CUBOID_ICP_NOT_CONVERGED;
+        st.chash = 0ull; st.evaluated = 0ull;
+        a.pstate[prob] = st;
+        __threadfence();
+        atomicAdd(&a.queue->n_total, 1);
+        icp_queue_push(a.queue, a.ring, a.n_slots, prob);
+    }
+}
+
+// One time slice of one problem: up to a.slice_iters iterations of the ICP loop, then either the closing fitness pass
+// (problem finished) or a state save (problem goes back on the queue).
+template <bool RESIDENT>
+__device__ __forceinline__ bool icp_slice(const IcpArgs& a, IcpShared& sh, const float* s_tmpl, const uint4* s_nodes, int prob) {
+    const int g = prob % a.n_guess, c = (prob / a.n_guess) % CUBOID_MAX_CLUSTERS, f = prob / (a.n_guess * CUBOID_MAX_CLUSTERS);
+    const int* offsets = a.offsets + (size_t)f * (a.KC + 1);
+    const int o0 = offsets[c], S = offsets[c + 1] - o0;
+    const int* idx = a.idx_sorted + (size_t)f * a.M + o0;
+    const float4* src = a.remain + (size_t)f * a.P;
+    const size_t pbase = ((size_t)f * a.n_guess + g) * a.M + o0;
+    float4* cur = a.cur + pbase;
+    int* corr = a.corr + pbase;
+    float* cd = a.cd + pbase;
+    const int* order = a.order + pbase;
+    IcpState& ps = a.pstate[prob];
+    const bool trace = a.corr_trace && f == 0 && c == 0 && g == 0;
+    const float* tp = RESIDENT ? s_tmpl : a.tmpl;
+    const bool lane_thread = threadIdx.x < ICP_LANES;
+
+    if (threadIdx.x < 16) sh.fin[threadIdx.x] = __ldcg(&ps.fin[threadIdx.x]);
+    if (threadIdx.x == 0) {
+        sh.done = __ldcg(&ps.done); sh.converged = __ldcg(&ps.converged); sh.state = __ldcg(&ps.state); sh.iters = __ldcg(&ps.it);
+        sh.prev_mse = __ldcg(&ps.prev_mse);
         sh.task = 0;
     }
-    mbar_wait(&sh.bar, 0);
     __syncthreads();
-
     unsigned long long chash = 0, evaluated = 0;
     const float one_over_n = 1.0f / (float)S;
-    int it = 0, passes = 0;
-    if (S < 3) {   // "Not enough correspondences found" -> converged_ = false, no iteration
-        if (threadIdx.x == 0) { sh.done = 1; sh.state = CUBOID_ICP_NO_CORRESPONDENCES; }
-        __syncthreads();
-    }
-    while (!sh.done) {
+    int it = sh.iters, passes = 0;
+    const int it_end = it + a.slice_iters;
+    while (!sh.done && it < it_end) {
         // 1. correspondences
         icp_nn_pass<RESIDENT>(a, sh, s_tmpl, s_nodes, cur, S, order, corr, cd, evaluated);
         ++passes;
@@ -520,12 +587,12 @@ __device__ __forceinline__ void icp_body(const IcpArgs& a, IcpShared& sh, float*
         double qd[1] = {0.0};
         if (lane_thread)
             for (int i = threadIdx.x; i < S; i += ICP_LANES) {
-                const float4 p = cur[i];
-                const int pos = corr[i];
+                const float4 p = __ldcg(cur + i);
+                const int pos = __ldcg(corr + i);
                 const float3 t = tmpl_point(tp, pos);
                 q6[0] = q6[0] + p.x; q6[1] = q6[1] + p.y; q6[2] = q6[2] + p.z;
                 q6[3] = q6[3] + t.x; q6[4] = q6[4] + t.y; q6[5] = q6[5] + t.z;
-                qd[0] = qd[0] + (double)cd[i];
+                qd[0] = qd[0] + (double)__ldcg(cd + i);
                 const int j = a.tmpl_orig[pos];      // original template index
                 chash += splitmix64((((unsigned long long)it * (unsigned long long)S + (unsigned long long)i) << 32) | (unsigned int)j);
                 if (trace && it < a.cap_trace) a.corr_trace[(size_t)it * S + i] = j;
@@ -543,8 +610,8 @@ __device__ __forceinline__ void icp_body(const IcpArgs& a, IcpShared& sh, float*
         for (int k = 0; k < 9; ++k) q9[k] = 0.f;
         if (lane_thread)
             for (int i = threadIdx.x; i < S; i += ICP_LANES) {
-                const float4 p = cur[i];
-                const float3 t = tmpl_point(tp, corr[i]);
+                const float4 p = __ldcg(cur + i);
+                const float3 t = tmpl_point(tp, __ldcg(corr + i));
                 const float sd[3] = {p.x - sm[0], p.y - sm[1], p.z - sm[2]};
                 const float dd[3] = {t.x - dm[0], t.y - dm[1], t.z - dm[2]};
 #pragma unroll
@@ -602,57 +669,98 @@ __device__ __forceinline__ void icp_body(const IcpArgs& a, IcpShared& sh, float*
         }
         __syncthreads();
         // 5. transformCloud(input_transformed, input_transformed, transformation_): incremental, in place
-        for (int i = threadIdx.x; i < S; i += ICP_THREADS) cur[i] = xform(sh.Tm, cur[i]);
+        for (int i = threadIdx.x; i < S; i += ICP_THREADS) cur[i] = xform(sh.Tm, __ldcg(cur + i));
         ++it;
         __syncthreads();
     }
-
-    // ---- output = transformCloud(src, final); getFitnessScore(): one more nearest-neighbour pass ----
-    for (int i = threadIdx.x; i < S; i += ICP_THREADS) cur[i] = xform(sh.fin, src[idx[i]]);
-    __syncthreads();
+    const bool finished = sh.done != 0;
     double fitness = 1.7976931348623157e308;
-    if (S > 0) {
-        icp_nn_pass<RESIDENT>(a, sh, s_tmpl, s_nodes, cur, S, order, corr, cd, evaluated);
-        ++passes;
+    if (finished) {
+        // ---- output = transformCloud(src, final); getFitnessScore(): one more nearest-neighbour pass ----
+        for (int i = threadIdx.x; i < S; i += ICP_THREADS) cur[i] = xform(sh.fin, src[idx[i]]);
         __syncthreads();
-        double qd[1] = {0.0};
-        if (lane_thread)
-            for (int i = threadIdx.x; i < S; i += ICP_LANES) qd[0] = qd[0] + (double)cd[i];
-        canon_block_reduce<double, 1>(qd, sh.part_d, sh.red_d);
-        fitness = sh.red_d[0] / (double)S;
+        if (S > 0) {
+            icp_nn_pass<RESIDENT>(a, sh, s_tmpl, s_nodes, cur, S, order, corr, cd, evaluated);
+            ++passes;
+            __syncthreads();
+            double qd[1] = {0.0};
+            if (lane_thread)
+                for (int i = threadIdx.x; i < S; i += ICP_LANES) qd[0] = qd[0] + (double)__ldcg(cd + i);
+            canon_block_reduce<double, 1>(qd, sh.part_d, sh.red_d);
+            fitness = sh.red_d[0] / (double)S;
+        }
     }
-    // reduce the correspondence hash and the work counters
+    // reduce this slice's share of the correspondence hash and of the work counters
     chash = warp_sum_u64(chash);
     evaluated = warp_sum_u64(evaluated);   // pairs evaluated by the 32 lanes
     __shared__ unsigned long long s_hh[ICP_THREADS / 32], s_ev[ICP_THREADS / 32];
     if ((threadIdx.x & 31) == 0) { s_hh[threadIdx.x >> 5] = chash; s_ev[threadIdx.x >> 5] = evaluated; }
     __syncthreads();
     if (threadIdx.x == 0) {
-        unsigned long long t = 0, ev = 0;
+        unsigned long long t = __ldcg(&ps.chash), ev = __ldcg(&ps.evaluated);
         for (int k = 0; k < ICP_THREADS / 32; ++k) { t += s_hh[k]; ev += s_ev[k]; }
-        for (int k = 0; k < 16; ++k) out.T[k] = sh.fin[k];
-        out.fitness = fitness;
-        out.converged = sh.converged;
-        out.iters = sh.iters;
-        out.state = sh.state;
-        out.corr_hash = t;
-        if (a.work) {
-            atomicAdd(&a.work[0], ev);
-            atomicAdd(&a.work[1], (unsigned long long)passes * (unsigned long long)S * (unsigned long long)a.T);
+        const int all_passes = __ldcg(&ps.passes) + passes;
+        if (finished) {
+            IcpOut& out = a.out[prob];
+            for (int k = 0; k < 16; ++k) out.T[k] = sh.fin[k];
+            out.fitness = fitness;
+            out.converged = sh.converged;
+            out.iters = sh.iters;
+            out.state = sh.state;
+            out.corr_hash = t;
+            if (a.work) {
+                atomicAdd(&a.work[0], ev);
+                atomicAdd(&a.work[1], (unsigned long long)all_passes * (unsigned long long)S * (unsigned long long)a.T);
+            }
+        } else {
+            for (int k = 0; k < 16; ++k) ps.fin[k] = sh.fin[k];
+            ps.prev_mse = sh.prev_mse; ps.it = sh.iters; ps.passes = all_passes; ps.done = 0; ps.converged = sh.converged; ps.state = sh.state;
+            ps.chash = t; ps.evaluated = ev;
         }
     }
+    __syncthreads();
+    return finished;
 }
 
+// Persistent worker: stages the BVH (and the template, if it fits) in shared memory ONCE, then serves time slices of
+// whatever problem is next on the queue until every problem of the launch is finished. Slicing bounds the tail: without
+// it the kernel ends when the problem with the most iterations (40 .. 150 here) ends, with most SMs idle by then.
 __global__ void __launch_bounds__(ICP_THREADS, 2) k_icp(const IcpArgs a) {
     extern __shared__ __align__(128) unsigned char smem_raw[];
     __shared__ IcpShared sh;
-    const cuboid_frame_result& R = a.res[blockIdx.z];
-    if ((int)blockIdx.y >= min(R.n_clusters, CUBOID_MAX_CLUSTERS)) return;
+    __shared__ int s_prob;
     // dynamic shared memory: [BVH nodes (nnodes x 16 B)] [template SoA leaves (Tpad*3 floats, resident case only)]
     uint4* s_nodes = reinterpret_cast<uint4*>(smem_raw);
     float* s_tmpl = reinterpret_cast<float*>(s_nodes + a.nnodes);
-    if (a.resident) icp_body<true>(a, sh, s_tmpl, s_nodes);
-    else icp_body<false>(a, sh, s_tmpl, s_nodes);
+    if (threadIdx.x == 0) {
+        mbar_init(&sh.bar, 1);
+        asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
+    }
+    __syncthreads();
+    if (threadIdx.x == 0) {
+        const unsigned int tb = a.resident ? (unsigned int)a.Tpad * 12u : 0u;
+        const unsigned int bb = (unsigned int)a.nnodes * 16u;
+        mbar_expect_tx(&sh.bar, tb + bb);
+        for (unsigned int off = 0; off < tb; off += 32768u)
+            tma_bulk_g2s(reinterpret_cast<unsigned char*>(s_tmpl) + off, reinterpret_cast<const unsigned char*>(a.tmpl) + off, min(32768u, tb - off), &sh.bar);
+        for (unsigned int off = 0; off < bb; off += 32768u)
+            tma_bulk_g2s(reinterpret_cast<unsigned char*>(s_nodes) + off, reinterpret_cast<const unsigned char*>(a.nodes) + off, min(32768u, bb - off), &sh.bar);
+    }
+    mbar_wait(&sh.bar, 0);
+    __syncthreads();
+    while (true) {
+        if (threadIdx.x == 0) s_prob = icp_queue_pop(a.queue, a.ring, a.n_slots);
+        __syncthreads();
+        const int prob = s_prob;
+        if (prob < 0) break;
+        const bool finished = a.resident ? icp_slice<true>(a, sh, s_tmpl, s_nodes, prob) : icp_slice<false>(a, sh, s_tmpl, s_nodes, prob);
+        if (threadIdx.x == 0) {
+            __threadfence();   // state / outputs before the hand-over
+            if (finished) atomicAdd(&a.queue->n_done, 1);
+            else icp_queue_push(a.queue, a.ring, a.n_slots, prob);
+        }
+        __syncthreads();
+    }
 }
 
 // best guess per (frame, cluster): lowest fitness, ties -> lowest guess id; fills cuboid_cluster_result

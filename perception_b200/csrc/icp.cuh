@@ -69,6 +69,16 @@ struct IcpArgs {
 
 constexpr int ICP_THREADS = 512;   // first 256 = the canonical reduction lanes; two CTAs (two ICP problems) share an SM
 constexpr int ICP_LANES = 256;
+// A CTA of k_icp hosts ICP_THREADS / ICP_SUB independent sub-workers of ICP_SUB threads (= the 256 canonical lanes). Each
+// serves its own problem and synchronises on its own named barrier; all share the CTA's one copy of the template and tree.
+// Four problems per SM instead of two: while one sits in its serial SVD or in a reduction, three others keep the SM busy.
+constexpr int ICP_SUB = 256;
+constexpr int ICP_NSUB = ICP_THREADS / ICP_SUB;
+__device__ __forceinline__ void sub_sync(int sub) {   // literal barrier ids: a register id would reserve all 16 barriers
+    if (sub == 0) asm volatile("bar.sync 1, %0;" ::"n"(ICP_SUB) : "memory");
+    else asm volatile("bar.sync 2, %0;" ::"n"(ICP_SUB) : "memory");
+}
+static_assert(ICP_NSUB == 2, "sub_sync names two barriers");
 constexpr int ICP_LEAF = 16;       // template points per BVH leaf
 
 
@@ -232,6 +242,28 @@ __device__ __forceinline__ void canon_block_reduce(Tq (&v)[NQ], Tq* s_part /* [N
     __syncthreads();
 }
 
+
+// the same for one sub-worker (tid = its thread index 0..255, named barrier)
+template <typename Tq, int NQ>
+__device__ __forceinline__ void canon_sub_reduce(Tq (&v)[NQ], Tq* s_part /* [NQ][8] */, Tq* s_out, int tid, int sub) {
+    const int lane = tid & 31, wid = tid >> 5;
+#pragma unroll
+    for (int q = 0; q < NQ; ++q) {
+        Tq x = v[q];
+#pragma unroll
+        for (int o = 16; o >= 1; o >>= 1) x = x + __shfl_xor_sync(FULL_MASK, x, o);
+        if (lane == 0) s_part[q * 8 + wid] = x;
+    }
+    sub_sync(sub);
+    if (tid < NQ) {
+        const Tq* p = s_part + tid * 8;
+        Tq s = p[0];
+#pragma unroll
+        for (int g = 1; g < 8; ++g) s = s + p[g];
+        s_out[tid] = s;
+    }
+    sub_sync(sub);
+}
 
 struct IcpShared {
     unsigned long long bar;
@@ -481,7 +513,7 @@ __global__ void __launch_bounds__(ICP_THREADS) k_icp_init(const IcpArgs a) {
     __shared__ float s_guess[16];
     const int g = blockIdx.x, c = blockIdx.y, f = blockIdx.z;
     const cuboid_frame_result& R = a.res[f];
-    if (blockIdx.x == 0 && blockIdx.y == 0 && blockIdx.z == 0 && threadIdx.x == 0) a.queue->alive = a.crew;
+    if (blockIdx.x == 0 && blockIdx.y == 0 && blockIdx.z == 0 && threadIdx.x == 0) a.queue->alive = a.crew * ICP_NSUB;   // poppers = sub-workers
     if (c >= min(R.n_clusters, CUBOID_MAX_CLUSTERS)) return;   // not a problem: n_total counts only real ones
     const int prob = (f * CUBOID_MAX_CLUSTERS + c) * a.n_guess + g;
     const int* offsets = a.offsets + (size_t)f * (a.KC + 1);
@@ -549,7 +581,8 @@ __global__ void __launch_bounds__(ICP_THREADS) k_icp_init(const IcpArgs a) {
 // One time slice of one problem: up to a.slice_iters iterations of the ICP loop, then either the closing fitness pass
 // (problem finished) or a state save (problem goes back on the queue).
 template <bool RESIDENT>
-__device__ __forceinline__ bool icp_slice(const IcpArgs& a, IcpShared& sh, const float* s_tmpl, const uint4* s_nodes, int prob) {
+__device__ __forceinline__ bool icp_slice(const IcpArgs& a, IcpShared& sh, const float* s_tmpl, const uint4* s_nodes, int prob, int tid, int sub,
+                                          unsigned long long* s_hh, unsigned long long* s_ev) {
     const int g = prob % a.n_guess, c = (prob / a.n_guess) % CUBOID_MAX_CLUSTERS, f = prob / (a.n_guess * CUBOID_MAX_CLUSTERS);
     const int* offsets = a.offsets + (size_t)f * (a.KC + 1);
     const int o0 = offsets[c], S = offsets[c + 1] - o0;
@@ -563,15 +596,14 @@ __device__ __forceinline__ bool icp_slice(const IcpArgs& a, IcpShared& sh, const
     IcpState& ps = a.pstate[prob];
     const bool trace = a.corr_trace && f == 0 && c == 0 && g == 0;
     const float* tp = RESIDENT ? s_tmpl : a.tmpl;
-    const bool lane_thread = threadIdx.x < ICP_LANES;
 
-    if (threadIdx.x < 16) sh.fin[threadIdx.x] = __ldcg(&ps.fin[threadIdx.x]);
-    if (threadIdx.x == 0) {
+    if (tid < 16) sh.fin[tid] = __ldcg(&ps.fin[tid]);
+    if (tid == 0) {
         sh.done = __ldcg(&ps.done); sh.converged = __ldcg(&ps.converged); sh.state = __ldcg(&ps.state); sh.iters = __ldcg(&ps.it);
         sh.prev_mse = __ldcg(&ps.prev_mse);
         sh.task = 0;
     }
-    __syncthreads();
+    sub_sync(sub);
     unsigned long long chash = 0, evaluated = 0;
     const float one_over_n = 1.0f / (float)S;
     int it = sh.iters, passes = 0;
@@ -580,13 +612,12 @@ __device__ __forceinline__ bool icp_slice(const IcpArgs& a, IcpShared& sh, const
         // 1. correspondences
         icp_nn_pass<RESIDENT>(a, sh, s_tmpl, s_nodes, cur, S, order, corr, cd, evaluated);
         ++passes;
-        __syncthreads();
-        if (threadIdx.x == 0) sh.task = 0;
+        sub_sync(sub);
+        if (tid == 0) sh.task = 0;
         // 2. means + MSE: the first 256 threads are the 256 canonical lanes
         float q6[6] = {0.f, 0.f, 0.f, 0.f, 0.f, 0.f};
         double qd[1] = {0.0};
-        if (lane_thread)
-            for (int i = threadIdx.x; i < S; i += ICP_LANES) {
+                    for (int i = tid; i < S; i += ICP_SUB) {
                 const float4 p = __ldcg(cur + i);
                 const int pos = __ldcg(corr + i);
                 const float3 t = tmpl_point(tp, pos);
@@ -597,19 +628,18 @@ __device__ __forceinline__ bool icp_slice(const IcpArgs& a, IcpShared& sh, const
                 chash += splitmix64((((unsigned long long)it * (unsigned long long)S + (unsigned long long)i) << 32) | (unsigned int)j);
                 if (trace && it < a.cap_trace) a.corr_trace[(size_t)it * S + i] = j;
             }
-        canon_block_reduce<float, 6>(q6, sh.part_f, sh.red_f);
-        canon_block_reduce<double, 1>(qd, sh.part_d, sh.red_d);
+        canon_sub_reduce<float, 6>(q6, sh.part_f, sh.red_f, tid, sub);
+        canon_sub_reduce<double, 1>(qd, sh.part_d, sh.red_d, tid, sub);
         float sm[3], dm[3];
 #pragma unroll
         for (int k = 0; k < 3; ++k) { sm[k] = sh.red_f[k] * one_over_n; dm[k] = sh.red_f[3 + k] * one_over_n; }
         const double mse_sum = sh.red_d[0];
-        __syncthreads();
+        sub_sync(sub);
         // 3. sigma = one_over_n * dst_demean * src_demean^T
         float q9[9];
 #pragma unroll
         for (int k = 0; k < 9; ++k) q9[k] = 0.f;
-        if (lane_thread)
-            for (int i = threadIdx.x; i < S; i += ICP_LANES) {
+                    for (int i = tid; i < S; i += ICP_SUB) {
                 const float4 p = __ldcg(cur + i);
                 const float3 t = tmpl_point(tp, __ldcg(corr + i));
                 const float sd[3] = {p.x - sm[0], p.y - sm[1], p.z - sm[2]};
@@ -619,9 +649,9 @@ __device__ __forceinline__ bool icp_slice(const IcpArgs& a, IcpShared& sh, const
 #pragma unroll
                     for (int cc = 0; cc < 3; ++cc) q9[3 * r + cc] = q9[3 * r + cc] + dd[r] * sd[cc];
             }
-        canon_block_reduce<float, 9>(q9, sh.part_f, sh.red_f);
+        canon_sub_reduce<float, 9>(q9, sh.part_f, sh.red_f, tid, sub);
         // 4. thread 0: SVD, R, t, final, convergence
-        if (threadIdx.x == 0) {
+        if (tid == 0) {
             M3f sigma, U, V;
 #pragma unroll
             for (int r = 0; r < 3; ++r)
@@ -667,38 +697,36 @@ __device__ __forceinline__ bool icp_slice(const IcpArgs& a, IcpShared& sh, const
             }
             sh.done = done;
         }
-        __syncthreads();
+        sub_sync(sub);
         // 5. transformCloud(input_transformed, input_transformed, transformation_): incremental, in place
-        for (int i = threadIdx.x; i < S; i += ICP_THREADS) cur[i] = xform(sh.Tm, __ldcg(cur + i));
+        for (int i = tid; i < S; i += ICP_SUB) cur[i] = xform(sh.Tm, __ldcg(cur + i));
         ++it;
-        __syncthreads();
+        sub_sync(sub);
     }
     const bool finished = sh.done != 0;
     double fitness = 1.7976931348623157e308;
     if (finished) {
         // ---- output = transformCloud(src, final); getFitnessScore(): one more nearest-neighbour pass ----
-        for (int i = threadIdx.x; i < S; i += ICP_THREADS) cur[i] = xform(sh.fin, src[idx[i]]);
-        __syncthreads();
+        for (int i = tid; i < S; i += ICP_SUB) cur[i] = xform(sh.fin, src[idx[i]]);
+        sub_sync(sub);
         if (S > 0) {
             icp_nn_pass<RESIDENT>(a, sh, s_tmpl, s_nodes, cur, S, order, corr, cd, evaluated);
             ++passes;
-            __syncthreads();
+            sub_sync(sub);
             double qd[1] = {0.0};
-            if (lane_thread)
-                for (int i = threadIdx.x; i < S; i += ICP_LANES) qd[0] = qd[0] + (double)__ldcg(cd + i);
-            canon_block_reduce<double, 1>(qd, sh.part_d, sh.red_d);
+                            for (int i = tid; i < S; i += ICP_SUB) qd[0] = qd[0] + (double)__ldcg(cd + i);
+            canon_sub_reduce<double, 1>(qd, sh.part_d, sh.red_d, tid, sub);
             fitness = sh.red_d[0] / (double)S;
         }
     }
     // reduce this slice's share of the correspondence hash and of the work counters
     chash = warp_sum_u64(chash);
     evaluated = warp_sum_u64(evaluated);   // pairs evaluated by the 32 lanes
-    __shared__ unsigned long long s_hh[ICP_THREADS / 32], s_ev[ICP_THREADS / 32];
-    if ((threadIdx.x & 31) == 0) { s_hh[threadIdx.x >> 5] = chash; s_ev[threadIdx.x >> 5] = evaluated; }
-    __syncthreads();
-    if (threadIdx.x == 0) {
+    if ((tid & 31) == 0) { s_hh[tid >> 5] = chash; s_ev[tid >> 5] = evaluated; }
+    sub_sync(sub);
+    if (tid == 0) {
         unsigned long long t = __ldcg(&ps.chash), ev = __ldcg(&ps.evaluated);
-        for (int k = 0; k < ICP_THREADS / 32; ++k) { t += s_hh[k]; ev += s_ev[k]; }
+        for (int k = 0; k < ICP_SUB / 32; ++k) { t += s_hh[k]; ev += s_ev[k]; }
         const int all_passes = __ldcg(&ps.passes) + passes;
         if (finished) {
             IcpOut& out = a.out[prob];
@@ -718,7 +746,7 @@ __device__ __forceinline__ bool icp_slice(const IcpArgs& a, IcpShared& sh, const
             ps.chash = t; ps.evaluated = ev;
         }
     }
-    __syncthreads();
+    sub_sync(sub);
     return finished;
 }
 
@@ -727,39 +755,44 @@ __device__ __forceinline__ bool icp_slice(const IcpArgs& a, IcpShared& sh, const
 // it the kernel ends when the problem with the most iterations (40 .. 150 here) ends, with most SMs idle by then.
 __global__ void __launch_bounds__(ICP_THREADS, 2) k_icp(const IcpArgs a) {
     extern __shared__ __align__(128) unsigned char smem_raw[];
-    __shared__ IcpShared sh;
-    __shared__ int s_prob;
+    __shared__ IcpShared shs[ICP_NSUB];
+    __shared__ int s_prob[ICP_NSUB];
+    __shared__ unsigned long long s_hh[ICP_NSUB][ICP_SUB / 32], s_ev[ICP_NSUB][ICP_SUB / 32];
     // dynamic shared memory: [BVH nodes (nnodes x 16 B)] [template SoA leaves (Tpad*3 floats, resident case only)]
     uint4* s_nodes = reinterpret_cast<uint4*>(smem_raw);
     float* s_tmpl = reinterpret_cast<float*>(s_nodes + a.nnodes);
     if (threadIdx.x == 0) {
-        mbar_init(&sh.bar, 1);
+        mbar_init(&shs[0].bar, 1);
         asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
     }
     __syncthreads();
     if (threadIdx.x == 0) {
         const unsigned int tb = a.resident ? (unsigned int)a.Tpad * 12u : 0u;
         const unsigned int bb = (unsigned int)a.nnodes * 16u;
-        mbar_expect_tx(&sh.bar, tb + bb);
+        mbar_expect_tx(&shs[0].bar, tb + bb);
         for (unsigned int off = 0; off < tb; off += 32768u)
-            tma_bulk_g2s(reinterpret_cast<unsigned char*>(s_tmpl) + off, reinterpret_cast<const unsigned char*>(a.tmpl) + off, min(32768u, tb - off), &sh.bar);
+            tma_bulk_g2s(reinterpret_cast<unsigned char*>(s_tmpl) + off, reinterpret_cast<const unsigned char*>(a.tmpl) + off, min(32768u, tb - off), &shs[0].bar);
         for (unsigned int off = 0; off < bb; off += 32768u)
-            tma_bulk_g2s(reinterpret_cast<unsigned char*>(s_nodes) + off, reinterpret_cast<const unsigned char*>(a.nodes) + off, min(32768u, bb - off), &sh.bar);
+            tma_bulk_g2s(reinterpret_cast<unsigned char*>(s_nodes) + off, reinterpret_cast<const unsigned char*>(a.nodes) + off, min(32768u, bb - off), &shs[0].bar);
     }
-    mbar_wait(&sh.bar, 0);
+    mbar_wait(&shs[0].bar, 0);
     __syncthreads();
+    // from here on the sub-workers go their own ways
+    const int sub = threadIdx.x / ICP_SUB, tid = threadIdx.x % ICP_SUB;
+    IcpShared& sh = shs[sub];
     while (true) {
-        if (threadIdx.x == 0) s_prob = icp_queue_pop(a.queue, a.ring, a.n_slots);
-        __syncthreads();
-        const int prob = s_prob;
+        if (tid == 0) s_prob[sub] = icp_queue_pop(a.queue, a.ring, a.n_slots);
+        sub_sync(sub);
+        const int prob = s_prob[sub];
         if (prob < 0) break;
-        const bool finished = a.resident ? icp_slice<true>(a, sh, s_tmpl, s_nodes, prob) : icp_slice<false>(a, sh, s_tmpl, s_nodes, prob);
-        if (threadIdx.x == 0) {
+        const bool finished = a.resident ? icp_slice<true>(a, sh, s_tmpl, s_nodes, prob, tid, sub, s_hh[sub], s_ev[sub])
+                                         : icp_slice<false>(a, sh, s_tmpl, s_nodes, prob, tid, sub, s_hh[sub], s_ev[sub]);
+        if (tid == 0) {
             __threadfence();   // state / outputs before the hand-over
             if (finished) atomicAdd(&a.queue->n_done, 1);
             else icp_queue_push(a.queue, a.ring, a.n_slots, prob);
         }
-        __syncthreads();
+        sub_sync(sub);
     }
 }
 

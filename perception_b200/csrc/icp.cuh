@@ -69,16 +69,22 @@ struct IcpArgs {
 
 constexpr int ICP_THREADS = 512;   // first 256 = the canonical reduction lanes; two CTAs (two ICP problems) share an SM
 constexpr int ICP_LANES = 256;
-// A CTA of k_icp hosts ICP_THREADS / ICP_SUB independent sub-workers of ICP_SUB threads (= the 256 canonical lanes). Each
-// serves its own problem and synchronises on its own named barrier; all share the CTA's one copy of the template and tree.
-// Four problems per SM instead of two: while one sits in its serial SVD or in a reduction, three others keep the SM busy.
+// A CTA of k_icp hosts ICP_NSUB independent sub-workers of ICP_SUB threads; each thread stands for ICP_LPT of the 256
+// canonical lanes. A sub-worker serves its own problem and synchronises on its own named barrier; all share the CTA's one
+// copy of the template and tree. Four problems per SM instead of two: while one sits in its serial SVD or in a reduction
+// the others keep the SM busy. Measured per 1024 frames: 1 x 512 threads 15.3 ms, 2 x 256 threads 14.5 ms, 4 x 128 threads 18.1 ms.
 constexpr int ICP_SUB = 256;
 constexpr int ICP_NSUB = ICP_THREADS / ICP_SUB;
+constexpr int ICP_LPT = ICP_LANES / ICP_SUB;
 __device__ __forceinline__ void sub_sync(int sub) {   // literal barrier ids: a register id would reserve all 16 barriers
-    if (sub == 0) asm volatile("bar.sync 1, %0;" ::"n"(ICP_SUB) : "memory");
-    else asm volatile("bar.sync 2, %0;" ::"n"(ICP_SUB) : "memory");
+    switch (sub) {
+        case 0: asm volatile("bar.sync 1, %0;" ::"n"(ICP_SUB) : "memory"); break;
+        case 1: asm volatile("bar.sync 2, %0;" ::"n"(ICP_SUB) : "memory"); break;
+        case 2: asm volatile("bar.sync 3, %0;" ::"n"(ICP_SUB) : "memory"); break;
+        default: asm volatile("bar.sync 4, %0;" ::"n"(ICP_SUB) : "memory"); break;
+    }
 }
-static_assert(ICP_NSUB == 2, "sub_sync names two barriers");
+static_assert(ICP_NSUB <= 4 && ICP_LPT * ICP_SUB == ICP_LANES, "sub_sync names four barriers; a thread stands for whole lanes");
 constexpr int ICP_LEAF = 16;       // template points per BVH leaf
 
 
@@ -243,17 +249,21 @@ __device__ __forceinline__ void canon_block_reduce(Tq (&v)[NQ], Tq* s_part /* [N
 }
 
 
-// the same for one sub-worker (tid = its thread index 0..255, named barrier)
+// the same for one sub-worker: canon_sub_partial after each of its ICP_LPT lane sets (v = the partial sums of canonical lane
+// tid + set * ICP_SUB), then canon_sub_finish
 template <typename Tq, int NQ>
-__device__ __forceinline__ void canon_sub_reduce(Tq (&v)[NQ], Tq* s_part /* [NQ][8] */, Tq* s_out, int tid, int sub) {
+__device__ __forceinline__ void canon_sub_partial(Tq (&v)[NQ], Tq* s_part /* [NQ][8] */, int tid, int set) {
     const int lane = tid & 31, wid = tid >> 5;
 #pragma unroll
     for (int q = 0; q < NQ; ++q) {
         Tq x = v[q];
 #pragma unroll
         for (int o = 16; o >= 1; o >>= 1) x = x + __shfl_xor_sync(FULL_MASK, x, o);
-        if (lane == 0) s_part[q * 8 + wid] = x;
+        if (lane == 0) s_part[q * 8 + set * (ICP_SUB / 32) + wid] = x;   // canonical warp = lanes [32w, 32w + 32)
     }
+}
+template <typename Tq, int NQ>
+__device__ __forceinline__ void canon_sub_finish(Tq* s_part /* [NQ][8] */, Tq* s_out, int tid, int sub) {
     sub_sync(sub);
     if (tid < NQ) {
         const Tq* p = s_part + tid * 8;
@@ -615,9 +625,10 @@ __device__ __forceinline__ bool icp_slice(const IcpArgs& a, IcpShared& sh, const
         sub_sync(sub);
         if (tid == 0) sh.task = 0;
         // 2. means + MSE: the first 256 threads are the 256 canonical lanes
-        float q6[6] = {0.f, 0.f, 0.f, 0.f, 0.f, 0.f};
-        double qd[1] = {0.0};
-                    for (int i = tid; i < S; i += ICP_SUB) {
+        for (int set = 0; set < ICP_LPT; ++set) {
+            float q6[6] = {0.f, 0.f, 0.f, 0.f, 0.f, 0.f};
+            double qd[1] = {0.0};
+            for (int i = tid + set * ICP_SUB; i < S; i += ICP_LANES) {
                 const float4 p = __ldcg(cur + i);
                 const int pos = __ldcg(corr + i);
                 const float3 t = tmpl_point(tp, pos);
@@ -628,18 +639,22 @@ __device__ __forceinline__ bool icp_slice(const IcpArgs& a, IcpShared& sh, const
                 chash += splitmix64((((unsigned long long)it * (unsigned long long)S + (unsigned long long)i) << 32) | (unsigned int)j);
                 if (trace && it < a.cap_trace) a.corr_trace[(size_t)it * S + i] = j;
             }
-        canon_sub_reduce<float, 6>(q6, sh.part_f, sh.red_f, tid, sub);
-        canon_sub_reduce<double, 1>(qd, sh.part_d, sh.red_d, tid, sub);
+            canon_sub_partial<float, 6>(q6, sh.part_f, tid, set);
+            canon_sub_partial<double, 1>(qd, sh.part_d, tid, set);
+        }
+        canon_sub_finish<float, 6>(sh.part_f, sh.red_f, tid, sub);
+        canon_sub_finish<double, 1>(sh.part_d, sh.red_d, tid, sub);
         float sm[3], dm[3];
 #pragma unroll
         for (int k = 0; k < 3; ++k) { sm[k] = sh.red_f[k] * one_over_n; dm[k] = sh.red_f[3 + k] * one_over_n; }
         const double mse_sum = sh.red_d[0];
         sub_sync(sub);
         // 3. sigma = one_over_n * dst_demean * src_demean^T
-        float q9[9];
+        for (int set = 0; set < ICP_LPT; ++set) {
+            float q9[9];
 #pragma unroll
-        for (int k = 0; k < 9; ++k) q9[k] = 0.f;
-                    for (int i = tid; i < S; i += ICP_SUB) {
+            for (int k = 0; k < 9; ++k) q9[k] = 0.f;
+            for (int i = tid + set * ICP_SUB; i < S; i += ICP_LANES) {
                 const float4 p = __ldcg(cur + i);
                 const float3 t = tmpl_point(tp, __ldcg(corr + i));
                 const float sd[3] = {p.x - sm[0], p.y - sm[1], p.z - sm[2]};
@@ -649,7 +664,9 @@ __device__ __forceinline__ bool icp_slice(const IcpArgs& a, IcpShared& sh, const
 #pragma unroll
                     for (int cc = 0; cc < 3; ++cc) q9[3 * r + cc] = q9[3 * r + cc] + dd[r] * sd[cc];
             }
-        canon_sub_reduce<float, 9>(q9, sh.part_f, sh.red_f, tid, sub);
+            canon_sub_partial<float, 9>(q9, sh.part_f, tid, set);
+        }
+        canon_sub_finish<float, 9>(sh.part_f, sh.red_f, tid, sub);
         // 4. thread 0: SVD, R, t, final, convergence
         if (tid == 0) {
             M3f sigma, U, V;
@@ -713,9 +730,12 @@ __device__ __forceinline__ bool icp_slice(const IcpArgs& a, IcpShared& sh, const
             icp_nn_pass<RESIDENT>(a, sh, s_tmpl, s_nodes, cur, S, order, corr, cd, evaluated);
             ++passes;
             sub_sync(sub);
-            double qd[1] = {0.0};
-                            for (int i = tid; i < S; i += ICP_SUB) qd[0] = qd[0] + (double)__ldcg(cd + i);
-            canon_sub_reduce<double, 1>(qd, sh.part_d, sh.red_d, tid, sub);
+            for (int set = 0; set < ICP_LPT; ++set) {
+                double qd[1] = {0.0};
+                for (int i = tid + set * ICP_SUB; i < S; i += ICP_LANES) qd[0] = qd[0] + (double)__ldcg(cd + i);
+                canon_sub_partial<double, 1>(qd, sh.part_d, tid, set);
+            }
+            canon_sub_finish<double, 1>(sh.part_d, sh.red_d, tid, sub);
             fitness = sh.red_d[0] / (double)S;
         }
     }

@@ -63,9 +63,11 @@ class ClockSampler:
 
     def _read(self):
         for line in self.proc.stdout:
-            self.rows.append([c.strip() for c in line.split(",")])
+            self.rows.append((time.perf_counter(), [c.strip() for c in line.split(",")]))
 
-    def stop(self):
+    def stop(self, t0=None, t1=None):
+        """Summary of the samples that arrived in [t0, t1] (the timed region); the sampler is started before the warm-up so
+        that nvidia-smi is already streaming when the region begins."""
         if not self.proc:
             return {"sm_mhz": None, "sm_max_mhz": None, "reasons": ["nvidia-smi unavailable"]}
         self.proc.terminate()
@@ -75,7 +77,8 @@ class ClockSampler:
             self.proc.kill()
         sm, mx, reasons = [], [], set()
         names = ["hw_slowdown", "hw_thermal_slowdown", "sw_thermal_slowdown", "sw_power_cap"]
-        for r in self.rows:
+        rows = [r for (ts, r) in self.rows if (t0 is None or ts >= t0) and (t1 is None or ts <= t1 + 0.25)]
+        for r in rows:
             try:
                 sm.append(float(r[1])); mx.append(float(r[2]))
                 for k, nm in enumerate(names):
@@ -195,7 +198,7 @@ def workload_config(args, frames_per_gpu):
 def main():
     ap = argparse.ArgumentParser()
     ap.add_argument("--gpus", type=int, default=1)
-    ap.add_argument("--steps", type=int, default=3)
+    ap.add_argument("--steps", type=int, default=10)
     ap.add_argument("--warmup", type=int, default=3)
     ap.add_argument("--impl", default="b200")
     ap.add_argument("--frames", type=int, default=1024, help="frames per GPU per step")
@@ -257,11 +260,11 @@ def main():
         torch.cuda.synchronize()
 
     # ---- device-resident: value + rooflines ----
+    sampler = ClockSampler(local_rank)
+    sampler.start()
     for _ in range(args.warmup):
         cc.process_batch_device(dev.data_ptr(), W, H, F, stages=stages)
     barrier()
-    sampler = ClockSampler(local_rank)
-    sampler.start()
     l0 = cc.launch_count()
     stage = {k: 0.0 for k in ("preprocess", "voxel", "plane", "cluster", "icp")}
     wall0 = time.perf_counter()
@@ -272,7 +275,7 @@ def main():
     barrier()
     wall = time.perf_counter() - wall0
     launches = cc.launch_count() - l0
-    clocks = sampler.stop()
+    clocks = sampler.stop(wall0, wall0 + wall)
     dev_ms = sum(stage.values())                               # CUDA events on the library's stream, summed over chunks
     res = cc.batch_results(F)
     work_eval, work_brute = cc.icp_work()                      # pairs evaluated / brute-force-equivalent pairs, last step

@@ -161,6 +161,7 @@ int ensure_icp_scratch(cuboid_handle* h, int frames, int n_guess) {
         CKS(h, dalloc(h, &h->d_icp_state, need_out));
         CKS(h, dalloc(h, &h->d_icp_ring, need_out));
         CKS(h, dalloc(h, &h->d_icp_queue, (size_t)frames));   // one queue header per possible first frame of a launch
+        CK(h, cudaMemset(h->d_icp_queue, 0, sizeof(IcpQueue) * (size_t)frames));
         h->icp_out_elems = need_out;
     }
     return CUBOID_OK;
@@ -435,6 +436,17 @@ __global__ void k_peak_ffma(float* out, int iters, float a, float b) {
 }
 
 }  // namespace
+
+// k_icp never spins forever: a worker that waited ~10 s for a queue slot raises IcpQueue::error and leaves. That would mean a
+// lost problem, i.e. a bug; it is reported loudly instead of returning half-finished poses.
+static int check_icp_queues(cuboid_handle* h, int nf) {
+    if (!h->d_icp_queue || nf < 1) return CUBOID_OK;
+    std::vector<IcpQueue> q((size_t)nf);
+    CK(h, cudaMemcpy(q.data(), h->d_icp_queue, sizeof(IcpQueue) * (size_t)nf, cudaMemcpyDeviceToHost));
+    for (const IcpQueue& e : q)
+        if (e.error) { h->last_error = "k_icp: a worker gave up waiting on the problem queue"; return CUBOID_E_CUDA; }
+    return CUBOID_OK;
+}
 
 extern "C" {
 
@@ -1012,6 +1024,7 @@ int cuboid_icp(cuboid_handle* h, const float* src_xyzw, int n_src, int tmpl_slot
     if (rc == CUBOID_OK) {
         if (cudaMemcpyAsync(&r, h->d_res, sizeof r, cudaMemcpyDeviceToHost, h->stream) != cudaSuccess) rc = CUBOID_E_CUDA;
         if (cudaStreamSynchronize(h->stream) != cudaSuccess) { rc = CUBOID_E_CUDA; h->last_error = cudaGetErrorString(cudaGetLastError()); }
+        if (rc == CUBOID_OK) rc = check_icp_queues(h, 1);
     }
     if (rc == CUBOID_OK) {
         const cuboid_cluster_result& c = r.cluster[0];
@@ -1049,6 +1062,7 @@ int cuboid_process_cloud(cuboid_handle* h, const void* pts, int point_step, int 
     CKS(h, run_chunk(h, in, 1, h->d_res, (have_t ? 15 : 7) & h->stage_mask, tmpl_slot));
     CK(h, cudaMemcpyAsync(result, h->d_res, sizeof(cuboid_frame_result), cudaMemcpyDeviceToHost, h->stream));
     CK(h, cudaStreamSynchronize(h->stream));
+    if (have_t) CKS(h, check_icp_queues(h, 1));
     h->last_chunk_base = 0; h->last_chunk_frames = 1; h->last_total_frames = 1;
     return CUBOID_OK;
 }
@@ -1103,6 +1117,7 @@ static int process_frames(cuboid_handle* h, const uint16_t* depth, bool on_devic
                 CK(h, cudaStreamWaitEvent(h->stream, h->pipe_done[i], 0));
             }
             CK(h, cudaStreamSynchronize(h->stream));
+            if (stages & 8) CKS(h, check_icp_queues(h, nf));
             h->last_chunk_base = base; h->last_chunk_frames = nf;
             continue;   // per-stage times are not defined when stages of different sub-chunks overlap: stage_ms stays 0
         }
@@ -1131,6 +1146,7 @@ static int process_frames(cuboid_handle* h, const uint16_t* depth, bool on_devic
             CKS(h, run_chunk(h, none, nf, h->d_res + base, stages & 14, tmpl_slot, true, true, false, false));
         }
         CK(h, cudaStreamSynchronize(h->stream));   // chunk buffers and the events are reused by the next chunk
+        if (stages & 8) CKS(h, check_icp_queues(h, 1));
         for (int sb = 0; sb < nsub; ++sb)
             for (int sg = 0; sg < 2; ++sg) {
                 float ms = 0.f;

@@ -58,7 +58,7 @@ struct cuboid_handle {
     int *d_parent = nullptr, *d_csize = nullptr, *d_crank = nullptr, *d_idx_sorted = nullptr, *d_offsets = nullptr, *d_roots = nullptr, *d_cell_head = nullptr; float4* d_cell_pts = nullptr;
     float4* d_cur = nullptr; int* d_corr = nullptr; float* d_cd = nullptr; int* d_order = nullptr; IcpOut* d_icp_out = nullptr;
     IcpState* d_icp_state = nullptr; IcpSlot* d_icp_ring = nullptr; IcpQueue* d_icp_queue = nullptr;   // persistent time-sliced k_icp
-    int icp_slice_iters = 8; int icp_ctas = 0;
+    int icp_slice_iters = 8; int icp_ctas = 0; int icp_outward = 1; int smem_sm = 0;
     size_t icp_scratch_elems = 0; size_t icp_out_elems = 0;
     FrameScratch* d_scr = nullptr;
     unsigned long long *d_desc1 = nullptr, *d_desc2 = nullptr;
@@ -67,6 +67,7 @@ struct cuboid_handle {
     int* d_rng = nullptr; int rng_len = 0;
     int* d_triplets = nullptr; int triplets_cap = 0;
     float* d_tmpl[CUBOID_MAX_TEMPLATES] = {}; int* d_tmpl_orig[CUBOID_MAX_TEMPLATES] = {}; int tmpl_n[CUBOID_MAX_TEMPLATES] = {}; int tmpl_pad[CUBOID_MAX_TEMPLATES] = {};
+    unsigned short* d_sib[CUBOID_MAX_TEMPLATES] = {}; int sib_max[CUBOID_MAX_TEMPLATES] = {}; int sib_bytes[CUBOID_MAX_TEMPLATES] = {};   // sibling chains (icp.cuh)
     uint4* d_boxes[CUBOID_MAX_TEMPLATES] = {}; int tmpl_nleaf[CUBOID_MAX_TEMPLATES] = {}; int tmpl_nnodes[CUBOID_MAX_TEMPLATES] = {};
     unsigned long long* d_work = nullptr; unsigned long long work_total[2] = {0, 0};
     int icp_cull = 1;
@@ -362,7 +363,14 @@ int run_chunk(cuboid_handle* h, const ChunkIn& in, int nf, cuboid_frame_result* 
         a.cull = h->icp_cull;
         a.work = h->d_work;
         a.corr_trace = trace_corr; a.T_trace = trace_T; a.cap_trace = cap_trace;
-        const size_t dyn = box_bytes + (a.resident ? (size_t)a.Tpad * 12 : 0);
+        size_t dyn = box_bytes + (a.resident ? (size_t)a.Tpad * 12 : 0);
+        {   // sibling chains ride along when two CTAs per SM still fit (or the template already forces one CTA per SM)
+            const size_t two_cta = (size_t)h->smem_sm / 2 - 1024 - 3072;
+            const size_t sbytes = (size_t)h->sib_bytes[tmpl_slot];
+            a.sib = h->d_sib[tmpl_slot]; a.sib_max = h->sib_max[tmpl_slot]; a.sib_bytes = (int)sbytes;
+            a.sib_on = (a.resident && h->icp_outward && sbytes > 0 && (dyn + sbytes <= two_cta || (dyn > two_cta && dyn + sbytes <= (size_t)h->icp_smem_budget))) ? 1 : 0;
+            if (a.sib_on) dyn += sbytes;
+        }
         // persistent, time-sliced: k_icp_init builds every problem's state and queue entry, then a fixed crew of CTAs (two per
         // SM, no more than there can be problems) serves slices of icp_slice_iters iterations until all problems are finished
         const size_t oS = (size_t)f0 * CUBOID_MAX_CLUSTERS * ng;
@@ -527,6 +535,8 @@ int cuboid_create(cuboid_handle** out, const cuboid_params* p, int device, int m
         cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, device);
         h->icp_ctas = 2 * sms;
         const char* es = std::getenv("CUBOID_ICP_SLICE"); if (es) h->icp_slice_iters = std::max(1, atoi(es));
+        const char* eo = std::getenv("CUBOID_ICP_OUTWARD"); if (eo) h->icp_outward = atoi(eo) ? 1 : 0;
+        cudaDeviceGetAttribute(&h->smem_sm, cudaDevAttrMaxSharedMemoryPerMultiprocessor, device);
     }
     {   // fused front end: cluster size and the number of clusters the device keeps resident
         const char* ef = std::getenv("CUBOID_FRONTEND"); if (ef) h->frontend = atoi(ef) ? 1 : 0;
@@ -586,6 +596,7 @@ int cuboid_destroy(cuboid_handle* h) {
     for (void* q : ptrs) if (q) cudaFree(q);
     for (auto& t : h->d_tmpl) if (t) cudaFree(t);
     for (auto& t : h->d_boxes) if (t) cudaFree(t);
+    for (auto& t : h->d_sib) if (t) cudaFree(t);
     for (auto& t : h->d_tmpl_orig) if (t) cudaFree(t);
     for (auto& e : h->ev) if (e) cudaEventDestroy(e);
     for (auto& e : h->ev_pool) if (e) cudaEventDestroy(e);
@@ -683,6 +694,38 @@ int cuboid_set_template(cuboid_handle* h, int slot, const float* xyz, int stride
         float* lf = host.data() + (size_t)(i / ICP_LEAF) * ICP_LEAF_FLOATS + (i % ICP_LEAF);
         lf[0] = items[i].x; lf[ICP_LEAF] = items[i].y; lf[2 * ICP_LEAF] = items[i].z;
         orig[i] = items[i].orig;   // ties resolve to the lowest ORIGINAL template index
+    }
+    // sibling chains: for every leaf the roots of the subtrees hanging off its path to the root, deepest first
+    std::vector<unsigned short> sib;
+    int sib_max = 0;
+    if (nodes.size() < 65535) {
+        std::vector<int> parent(nodes.size(), -1);
+        for (size_t i = 0; i < nodes.size(); ++i)
+            if (nodes[i].leaf < 0) { const int l = (int)i + 1, r = nodes[l].skip; parent[l] = (int)i; parent[r] = (int)i; }
+        std::vector<std::vector<unsigned short>> chain(nleaf);
+        for (size_t i = 0; i < nodes.size(); ++i) {
+            if (nodes[i].leaf < 0) continue;
+            int n_ = (int)i;
+            while (parent[n_] >= 0) {
+                const int pa = parent[n_], l = pa + 1, r = nodes[l].skip;
+                chain[nodes[i].leaf].push_back((unsigned short)(n_ == l ? r : l));
+                n_ = pa;
+            }
+            sib_max = std::max(sib_max, (int)chain[nodes[i].leaf].size());
+        }
+        if (sib_max >= 1 && sib_max <= 24) {
+            const size_t total = (((size_t)nleaf * sib_max * 2 + 15) / 16) * 16;
+            sib.assign(total / 2, (unsigned short)0xffff);
+            for (int L = 0; L < nleaf; ++L)
+                for (size_t e = 0; e < chain[L].size(); ++e) sib[(size_t)L * sib_max + e] = chain[L][e];
+        }
+    }
+    if (h->d_sib[slot]) { cudaFree(h->d_sib[slot]); h->d_sib[slot] = nullptr; }
+    h->sib_bytes[slot] = 0; h->sib_max[slot] = 0;
+    if (!sib.empty()) {
+        CKS(h, dalloc(h, &h->d_sib[slot], sib.size()));
+        CK(h, cudaMemcpy(h->d_sib[slot], sib.data(), sib.size() * 2, cudaMemcpyHostToDevice));
+        h->sib_bytes[slot] = (int)(sib.size() * 2); h->sib_max[slot] = sib_max;
     }
     if (h->d_tmpl[slot]) { cudaFree(h->d_tmpl[slot]); h->d_tmpl[slot] = nullptr; }
     if (h->d_tmpl_orig[slot]) { cudaFree(h->d_tmpl_orig[slot]); h->d_tmpl_orig[slot] = nullptr; }

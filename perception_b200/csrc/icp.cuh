@@ -44,6 +44,11 @@ struct IcpArgs {
     const uint4* nodes;      // [nnodes] depth-first BVH, 16 B each: fp16 AABB rounded OUTWARD (lo down, hi up) + link
                              //          (link >= 0: inner node, index of the first node after its subtree; link < 0: leaf ~link)
     int T, Tpad, nleaf, nnodes;
+    // Sibling chains (resident templates, staged after the template when they fit): for every leaf the roots of the subtrees
+    // hanging off its path to the root, deepest first, 0xffff-padded to sib_max entries. Leaf + these subtrees = the whole
+    // tree, so a search can start at the seed's leaf and work outwards instead of descending from the root.
+    const unsigned short* sib;     // [nleaf][sib_max]
+    int sib_on, sib_max, sib_bytes;
     const float* guesses;    // n_guess * (16 | 9) or NULL
     int n_guess, guess_mode;
     float4* cur;             // [F][G][M]
@@ -323,13 +328,56 @@ __device__ __forceinline__ float node_lb(float sx, float sy, float sz, const uin
 // Exactness: a subtree is skipped only when lb > best (strict), so no subtree holding a minimiser or a tie is
 // ever skipped; among equal distances the LOWEST ORIGINAL template index wins — the answer of a brute-force
 // scan in original order with strict '<'.
+struct IcpBest { float d; int pos; int orig; };
+// brute-force scan of one 16-point leaf; among equal distances the LOWEST ORIGINAL template index wins
+__device__ __forceinline__ void icp_scan_leaf(const IcpArgs& a, const float* tp, int leaf, float sx, float sy, float sz, IcpBest& b) {
+    const float* lf = tp + (size_t)leaf * ICP_LEAF_FLOATS;
+    const int pbase = leaf * ICP_LEAF;
+#pragma unroll
+    for (int jj = 0; jj < ICP_LEAF; jj += 4) {
+        const float4 X = *reinterpret_cast<const float4*>(lf + jj);
+        const float4 Y = *reinterpret_cast<const float4*>(lf + ICP_LEAF + jj);
+        const float4 Z = *reinterpret_cast<const float4*>(lf + 2 * ICP_LEAF + jj);
+        const float d0 = dist2(sx, sy, sz, X.x, Y.x, Z.x);
+        const float d1 = dist2(sx, sy, sz, X.y, Y.y, Z.y);
+        const float d2 = dist2(sx, sy, sz, X.z, Y.z, Z.z);
+        const float d3 = dist2(sx, sy, sz, X.w, Y.w, Z.w);
+        if (fminf(fminf(d0, d1), fminf(d2, d3)) <= b.d) {   // rare once the seed is good
+            const float dd[4] = {d0, d1, d2, d3};
+#pragma unroll
+            for (int q = 0; q < 4; ++q) {
+                if (dd[q] <= b.d) {
+                    const int pos = pbase + jj + q;
+                    const int o = a.tmpl_orig[pos];
+                    if (dd[q] < b.d || o < b.orig) { b.d = dd[q]; b.orig = o; b.pos = pos; }
+                }
+            }
+        }
+    }
+}
+
+// One nearest-neighbour pass over cur[0..S): writes corr[] (kd-ordered template position) and cd[].
+// On entry corr[] holds a valid template position per point (the previous pass's answer, or 0): its distance
+// seeds the running minimum so the culling is tight from the first node.
+//
+// Exactness: a subtree is skipped only when lb > best (strict), so no subtree holding a minimiser or a tie is
+// ever skipped; among equal distances the LOWEST ORIGINAL template index wins - the answer of a brute-force
+// scan in original order with strict '<'.
+//
+// With sibling chains the search runs OUTWARDS from the seed: the seed's own leaf is scanned first, then the subtrees
+// hanging off the leaf's path to the root are box-tested by all lanes in lockstep (a fixed, divergence-free loop of
+// <= sib_max tests, about 9) and only the survivors are walked, deepest (= nearest) first. Leaf + those subtrees = the
+// whole tree, so nothing is left out. Once ICP has roughly aligned the clouds almost every sibling test fails and a
+// query costs ~9 box tests + 1.3 leaf scans instead of a ~20-node descent from the root whose lock-step cost is ~36.
 template <bool RESIDENT>
 __device__ __forceinline__ void icp_nn_pass(const IcpArgs& a, IcpShared& sh, const float* s_tmpl, const uint4* s_nodes, const float4* cur,
                                             int S, const int* order, int* corr, float* cd, unsigned long long& evaluated) {
     const int lane = threadIdx.x & 31;
     const float* tp = RESIDENT ? s_tmpl : a.tmpl;
+    const unsigned short* s_sib = reinterpret_cast<const unsigned short*>(s_tmpl + (size_t)a.Tpad * 3);
     const int ntask = (S + 31) / 32;
     const bool cull = a.cull != 0;
+    const bool outward = RESIDENT && cull && a.sib_on;
     const int nnodes = a.nnodes;
     while (true) {
         int task = 0;
@@ -341,57 +389,57 @@ __device__ __forceinline__ void icp_nn_pass(const IcpArgs& a, IcpShared& sh, con
         const int i = order[valid ? k : S - 1];   // 32 lanes = 32 spatial neighbours: coherent tree walks, broadcast loads
         const float4 p = __ldcg(cur + i);   // cur / corr / cd travel between SMs from one time slice to the next: read them at L2
         const float sx = p.x, sy = p.y, sz = p.z;
-        int wpos = __ldcg(corr + i);
-        int worig = a.tmpl_orig[wpos];
-        float best;
+        IcpBest b;
+        b.pos = __ldcg(corr + i);
+        b.orig = a.tmpl_orig[b.pos];
         {
-            const float3 t = tmpl_point(tp, wpos);
-            best = dist2(sx, sy, sz, t.x, t.y, t.z);
+            const float3 t = tmpl_point(tp, b.pos);
+            b.d = dist2(sx, sy, sz, t.x, t.y, t.z);
         }
-        int node = 0;
         unsigned int nleaf_eval = 0;
+        int node = 0, end = nnodes;           // [node, end): the part of the depth-first node array still to walk
+        unsigned int cand = 0u;               // sibling subtrees whose box survived the lockstep test, not walked yet
+        const unsigned short* sl = s_sib;
+        if (outward) {
+            const int L = b.pos / ICP_LEAF;
+            sl = s_sib + L * a.sib_max;
+            ++nleaf_eval;
+            icp_scan_leaf(a, tp, L, sx, sy, sz, b);
+            for (int e = 0; e < a.sib_max; ++e) {
+                const unsigned int sn = sl[e];
+                if (sn != 0xffffu && !(node_lb(sx, sy, sz, s_nodes[sn]) > b.d)) cand |= 1u << e;
+            }
+            node = 0; end = 0;                // nothing to walk until a surviving sibling is opened
+        }
         while (true) {
-            // phase 1: every lane walks to its next surviving leaf
+            // every lane walks to its next surviving leaf
             int leaf = -1;
-            while (node < nnodes) {
+            while (true) {
+                if (node >= end) {
+                    if (!cand) break;
+                    const int e = __ffs(cand) - 1;
+                    cand &= cand - 1u;
+                    const int sn = sl[e];
+                    const uint4 nd = s_nodes[sn];
+                    if (node_lb(sx, sy, sz, nd) > b.d) continue;   // the minimum may have tightened since the lockstep test
+                    const int link = (int)nd.w;
+                    if (link < 0) { leaf = ~link; break; }           // the sibling is a leaf
+                    node = sn + 1; end = link;
+                    continue;
+                }
                 const uint4 nd = s_nodes[node];
                 const int link = (int)nd.w;
-                if (cull && node_lb(sx, sy, sz, nd) > best) { node = link >= 0 ? link : node + 1; continue; }
+                if (cull && node_lb(sx, sy, sz, nd) > b.d) { node = link >= 0 ? link : node + 1; continue; }
                 ++node;
                 if (link < 0) { leaf = ~link; break; }
             }
             // reconverge, so the leaf scans of all lanes issue together
             if (!__any_sync(FULL_MASK, leaf >= 0)) break;
-            if (leaf >= 0) {
-                ++nleaf_eval;
-                const float* lf = tp + (size_t)leaf * ICP_LEAF_FLOATS;
-                const int pbase = leaf * ICP_LEAF;
-#pragma unroll
-                for (int jj = 0; jj < ICP_LEAF; jj += 4) {
-                    const float4 X = *reinterpret_cast<const float4*>(lf + jj);
-                    const float4 Y = *reinterpret_cast<const float4*>(lf + ICP_LEAF + jj);
-                    const float4 Z = *reinterpret_cast<const float4*>(lf + 2 * ICP_LEAF + jj);
-                    const float d0 = dist2(sx, sy, sz, X.x, Y.x, Z.x);
-                    const float d1 = dist2(sx, sy, sz, X.y, Y.y, Z.y);
-                    const float d2 = dist2(sx, sy, sz, X.z, Y.z, Z.z);
-                    const float d3 = dist2(sx, sy, sz, X.w, Y.w, Z.w);
-                    if (fminf(fminf(d0, d1), fminf(d2, d3)) <= best) {   // rare once the seed is good
-                        const float dd[4] = {d0, d1, d2, d3};
-#pragma unroll
-                        for (int q = 0; q < 4; ++q) {
-                            if (dd[q] <= best) {
-                                const int pos = pbase + jj + q;
-                                const int o = a.tmpl_orig[pos];
-                                if (dd[q] < best || o < worig) { best = dd[q]; worig = o; wpos = pos; }
-                            }
-                        }
-                    }
-                }
-            }
+            if (leaf >= 0) { ++nleaf_eval; icp_scan_leaf(a, tp, leaf, sx, sy, sz, b); }
             __syncwarp();
         }
         evaluated += (unsigned long long)nleaf_eval * ICP_LEAF;
-        if (valid) { corr[i] = wpos; cd[i] = best; }
+        if (valid) { corr[i] = b.pos; cd[i] = b.d; }
     }
 }
 
@@ -778,7 +826,7 @@ __global__ void __launch_bounds__(ICP_THREADS, 2) k_icp(const IcpArgs a) {
     __shared__ IcpShared shs[ICP_NSUB];
     __shared__ int s_prob[ICP_NSUB];
     __shared__ unsigned long long s_hh[ICP_NSUB][ICP_SUB / 32], s_ev[ICP_NSUB][ICP_SUB / 32];
-    // dynamic shared memory: [BVH nodes (nnodes x 16 B)] [template SoA leaves (Tpad*3 floats, resident case only)]
+    // dynamic shared memory: [BVH nodes (nnodes x 16 B)] [template SoA leaves (Tpad*3 floats)] [sibling chains] (the last two: resident case)
     uint4* s_nodes = reinterpret_cast<uint4*>(smem_raw);
     float* s_tmpl = reinterpret_cast<float*>(s_nodes + a.nnodes);
     if (threadIdx.x == 0) {
@@ -789,7 +837,10 @@ __global__ void __launch_bounds__(ICP_THREADS, 2) k_icp(const IcpArgs a) {
     if (threadIdx.x == 0) {
         const unsigned int tb = a.resident ? (unsigned int)a.Tpad * 12u : 0u;
         const unsigned int bb = (unsigned int)a.nnodes * 16u;
-        mbar_expect_tx(&shs[0].bar, tb + bb);
+        const unsigned int sb = (a.resident && a.sib_on) ? (unsigned int)a.sib_bytes : 0u;
+        mbar_expect_tx(&shs[0].bar, tb + bb + sb);
+        for (unsigned int off = 0; off < sb; off += 32768u)
+            tma_bulk_g2s(reinterpret_cast<unsigned char*>(s_tmpl) + tb + off, reinterpret_cast<const unsigned char*>(a.sib) + off, min(32768u, sb - off), &shs[0].bar);
         for (unsigned int off = 0; off < tb; off += 32768u)
             tma_bulk_g2s(reinterpret_cast<unsigned char*>(s_tmpl) + off, reinterpret_cast<const unsigned char*>(a.tmpl) + off, min(32768u, tb - off), &shs[0].bar);
         for (unsigned int off = 0; off < bb; off += 32768u)

@@ -328,7 +328,7 @@ __device__ __forceinline__ float node_lb(float sx, float sy, float sz, const uin
 // Exactness: a subtree is skipped only when lb > best (strict), so no subtree holding a minimiser or a tie is
 // ever skipped; among equal distances the LOWEST ORIGINAL template index wins — the answer of a brute-force
 // scan in original order with strict '<'.
-struct IcpBest { float d; int pos; int orig; };
+struct IcpBest { float d; int pos; int orig; };   // orig < 0: original index of pos not fetched yet
 // brute-force scan of one 16-point leaf; among equal distances the LOWEST ORIGINAL template index wins
 __device__ __forceinline__ void icp_scan_leaf(const IcpArgs& a, const float* tp, int leaf, float sx, float sy, float sz, IcpBest& b) {
     const float* lf = tp + (size_t)leaf * ICP_LEAF_FLOATS;
@@ -346,10 +346,13 @@ __device__ __forceinline__ void icp_scan_leaf(const IcpArgs& a, const float* tp,
             const float dd[4] = {d0, d1, d2, d3};
 #pragma unroll
             for (int q = 0; q < 4; ++q) {
-                if (dd[q] <= b.d) {
-                    const int pos = pbase + jj + q;
+                const int pos = pbase + jj + q;
+                if (dd[q] < b.d) { b.d = dd[q]; b.pos = pos; b.orig = -1; }
+                else if (dd[q] == b.d && pos != b.pos) {
+                    // an exact tie between two different points: only now are the original indices needed (global memory)
+                    if (b.orig < 0) b.orig = a.tmpl_orig[b.pos];
                     const int o = a.tmpl_orig[pos];
-                    if (dd[q] < b.d || o < b.orig) { b.d = dd[q]; b.orig = o; b.pos = pos; }
+                    if (o < b.orig) { b.orig = o; b.pos = pos; }
                 }
             }
         }
@@ -391,7 +394,7 @@ __device__ __forceinline__ void icp_nn_pass(const IcpArgs& a, IcpShared& sh, con
         const float sx = p.x, sy = p.y, sz = p.z;
         IcpBest b;
         b.pos = __ldcg(corr + i);
-        b.orig = a.tmpl_orig[b.pos];
+        b.orig = -1;
         {
             const float3 t = tmpl_point(tp, b.pos);
             b.d = dist2(sx, sy, sz, t.x, t.y, t.z);

@@ -32,6 +32,7 @@ struct CluArgs {
     int min_size, max_size, use_cluster;
 };
 
+constexpr int CLU_RUNMAP = 256;     // candidates per query whose run is looked up in a table instead of searched
 constexpr int CLU_THREADS = 1024;   // two CTAs per SM (the shared-memory tiers below are sized for that): 1.86 ms vs 2.15 ms / 1024 frames with one
 
 __device__ __forceinline__ unsigned int cell_hash(int cx, int cy, int cz) {
@@ -61,12 +62,22 @@ __device__ __forceinline__ void uf_unite(int* parent, int a, int b) {
 // MODE 2: everything in global memory
 constexpr int CLU_SMEM_ALL = 2048;
 constexpr int CLU_SMEM_UF = 12288;
+// static shared memory of k_cluster, declared once in the kernel (not per MODE instantiation)
+struct CluShared {
+    int s_w[CLU_THREADS / 32 + 1];
+    int s_cur[1024];
+    int s_off[CLU_THREADS / 32][32], s_beg[CLU_THREADS / 32][32];
+    unsigned char s_runof[CLU_THREADS / 32][CLU_RUNMAP];   // run of every flattened candidate (queries with few enough of them)
+    unsigned long long s_h[CLU_THREADS / 32];
+};
 template <int MODE>
-__device__ __forceinline__ void cluster_body(const CluArgs& a) {
-    __shared__ int s_w[CLU_THREADS / 32 + 1];
-    __shared__ int s_cur[1024];
-    __shared__ int s_off[CLU_THREADS / 32][32], s_beg[CLU_THREADS / 32][32];
-    __shared__ unsigned long long s_h[CLU_THREADS / 32];
+__device__ __forceinline__ void cluster_body(const CluArgs& a, CluShared& cs) {
+    int* s_w = cs.s_w;
+    int* s_cur = cs.s_cur;
+    int (*s_off)[32] = cs.s_off;
+    int (*s_beg)[32] = cs.s_beg;
+    unsigned char (*s_runof)[CLU_RUNMAP] = cs.s_runof;
+    unsigned long long* s_h = cs.s_h;
     const int f = blockIdx.x;
     cuboid_frame_result& R = a.res[f];
     const int n = R.n_remain;
@@ -160,12 +171,18 @@ __device__ __forceinline__ void cluster_body(const CluArgs& a) {
         const int total = __shfl_sync(FULL_MASK, incl, 31);
         s_off[wid][lane] = incl - blen;     // exclusive offsets of the 32 (27 used) runs
         s_beg[wid][lane] = bstart;
+        const bool mapped = total <= CLU_RUNMAP;
+        if (mapped)                          // every lane stamps its run's id on the candidates it owns (runs are short)
+            for (int j = 0; j < blen; ++j) s_runof[wid][incl - blen + j] = (unsigned char)lane;
         __syncwarp();
         for (int t = lane; t < total; t += 32) {
             int e = 0;                      // last run with offset <= t (runs of length 0 share offsets: take the last)
+            if (mapped) e = s_runof[wid][t];
+            else {
 #pragma unroll
-            for (int step = 16; step >= 1; step >>= 1)
-                if (e + step < 32 && s_off[wid][e + step] <= t) e += step;
+                for (int step = 16; step >= 1; step >>= 1)
+                    if (e + step < 32 && s_off[wid][e + step] <= t) e += step;
+            }
             const float4 pj = cpts[s_beg[wid][e] + (t - s_off[wid][e])];
             const int j = __float_as_int(pj.w);
             const float ddx = pi.x - pj.x, ddy = pi.y - pj.y, ddz = pi.z - pj.z;
@@ -246,10 +263,11 @@ __device__ __forceinline__ void cluster_body(const CluArgs& a) {
 }
 
 __global__ void __launch_bounds__(CLU_THREADS) k_cluster(const CluArgs a) {
+    __shared__ CluShared cs;
     const int n = a.res[blockIdx.x].n_remain;
-    if (n <= CLU_SMEM_ALL) cluster_body<0>(a);
-    else if (n <= CLU_SMEM_UF) cluster_body<1>(a);
-    else cluster_body<2>(a);
+    if (n <= CLU_SMEM_ALL) cluster_body<0>(a, cs);
+    else if (n <= CLU_SMEM_UF) cluster_body<1>(a, cs);
+    else cluster_body<2>(a, cs);
 }
 constexpr size_t CLU_DYN_SMEM = (size_t)CLU_SMEM_ALL * 4 + (size_t)CLU_SMEM_ALL * 16 + (size_t)(CLU_SMEM_ALL + 4) * 4;   // 49 168 B >= 12288*4
 

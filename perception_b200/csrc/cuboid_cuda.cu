@@ -58,7 +58,7 @@ struct cuboid_handle {
     int *d_parent = nullptr, *d_csize = nullptr, *d_crank = nullptr, *d_idx_sorted = nullptr, *d_offsets = nullptr, *d_roots = nullptr, *d_cell_head = nullptr; float4* d_cell_pts = nullptr;
     float4* d_cur = nullptr; int* d_corr = nullptr; float* d_cd = nullptr; int* d_order = nullptr; IcpOut* d_icp_out = nullptr;
     IcpState* d_icp_state = nullptr; IcpSlot* d_icp_ring = nullptr; IcpQueue* d_icp_queue = nullptr;   // persistent time-sliced k_icp
-    int icp_slice_iters = 8; int icp_ctas = 0; int icp_outward = 1; int smem_sm = 0;
+    int icp_slice_iters = 8; int icp_ctas = 0; int icp_outward = 1; int smem_sm = 0; int icp_nsub_force = 0;
     size_t icp_scratch_elems = 0; size_t icp_out_elems = 0;
     FrameScratch* d_scr = nullptr;
     unsigned long long *d_desc1 = nullptr, *d_desc2 = nullptr;
@@ -381,8 +381,13 @@ int run_chunk(cuboid_handle* h, const ChunkIn& in, int nf, cuboid_frame_result* 
         CK(h, cudaMemsetAsync(a.queue, 0, sizeof(IcpQueue), st));
         CK(h, cudaMemsetAsync(a.ring, 0, sizeof(IcpSlot) * (size_t)a.n_slots, st));
         a.crew = (int)std::max<long long>(1, std::min<long long>(h->icp_ctas, (long long)nf * ng * CUBOID_MAX_CLUSTERS));
+        // two 256-thread sub-workers per CTA when there is at least one problem per sub-worker (one cluster per frame and guess
+        // assumed), else all 512 threads on one problem: with few problems the latency of each is what counts
+        a.nsub = ((long long)nf * ng >= 2LL * a.crew) ? 2 : 1;
+        if (h->icp_nsub_force) a.nsub = h->icp_nsub_force;
         k_icp_init<<<dim3(ng, CUBOID_MAX_CLUSTERS, nf), ICP_THREADS, a.init_smem, st>>>(a);
-        k_icp<<<a.crew, ICP_THREADS, dyn, st>>>(a);   // workers beyond the number of real problems leave at once
+        if (a.nsub == 2) k_icp<256><<<a.crew, ICP_THREADS, dyn, st>>>(a);   // workers beyond the number of real problems leave at once
+        else k_icp<512><<<a.crew, ICP_THREADS, dyn, st>>>(a);
         ++h->launches;
         const int tot = nf * CUBOID_MAX_CLUSTERS;
         k_icp_select<<<(tot + 127) / 128, 128, 0, st>>>(b_out, d_res, nf, ng, p.icp_fitness_gate, h->d_cur + oG, h->M, b_offsets,
@@ -528,7 +533,8 @@ int cuboid_create(cuboid_handle** out, const cuboid_params* p, int device, int m
     CA(ensure_icp_scratch(h, h->B, std::max(1, (int)p->n_guess)));
     cudaDeviceGetAttribute(&h->smem_optin, cudaDevAttrMaxSharedMemoryPerBlockOptin, device);
     h->icp_smem_budget = h->smem_optin - 4096;   // static shared memory of k_icp stays well below 4 KB
-    if (cudaFuncSetAttribute(k_icp, cudaFuncAttributeMaxDynamicSharedMemorySize, h->icp_smem_budget) != cudaSuccess) return fail(CUBOID_E_CUDA);
+    if (cudaFuncSetAttribute(k_icp<256>, cudaFuncAttributeMaxDynamicSharedMemorySize, h->icp_smem_budget) != cudaSuccess) return fail(CUBOID_E_CUDA);
+    if (cudaFuncSetAttribute(k_icp<512>, cudaFuncAttributeMaxDynamicSharedMemorySize, h->icp_smem_budget) != cudaSuccess) return fail(CUBOID_E_CUDA);
     if (cudaFuncSetAttribute(k_icp_init, cudaFuncAttributeMaxDynamicSharedMemorySize, 65536) != cudaSuccess) return fail(CUBOID_E_CUDA);
     {
         int sms = 0;
@@ -536,6 +542,7 @@ int cuboid_create(cuboid_handle** out, const cuboid_params* p, int device, int m
         h->icp_ctas = 2 * sms;
         const char* es = std::getenv("CUBOID_ICP_SLICE"); if (es) h->icp_slice_iters = std::max(1, atoi(es));
         const char* eo = std::getenv("CUBOID_ICP_OUTWARD"); if (eo) h->icp_outward = atoi(eo) ? 1 : 0;
+        const char* en = std::getenv("CUBOID_ICP_NSUB"); if (en) h->icp_nsub_force = (atoi(en) == 1 || atoi(en) == 2) ? atoi(en) : 0;
         cudaDeviceGetAttribute(&h->smem_sm, cudaDevAttrMaxSharedMemoryPerMultiprocessor, device);
     }
     {   // fused front end: cluster size and the number of clusters the device keeps resident

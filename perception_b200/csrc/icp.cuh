@@ -69,27 +69,22 @@ struct IcpArgs {
     struct IcpQueue* queue; struct IcpSlot* ring; int n_slots;
     int slice_iters;           // iterations per time slice
     int crew;                  // worker CTAs of k_icp
+    int nsub;                  // sub-workers per CTA (1 or 2)
     int init_smem;             // dynamic shared memory of k_icp_init (Morton sort window)
 };
 
 constexpr int ICP_THREADS = 512;   // first 256 = the canonical reduction lanes; two CTAs (two ICP problems) share an SM
 constexpr int ICP_LANES = 256;
-// A CTA of k_icp hosts ICP_NSUB independent sub-workers of ICP_SUB threads; each thread stands for ICP_LPT of the 256
-// canonical lanes. A sub-worker serves its own problem and synchronises on its own named barrier; all share the CTA's one
-// copy of the template and tree. Four problems per SM instead of two: while one sits in its serial SVD or in a reduction
-// the others keep the SM busy. Measured per 1024 frames: 1 x 512 threads 15.3 ms, 2 x 256 threads 14.5 ms, 4 x 128 threads 18.1 ms.
-constexpr int ICP_SUB = 256;
-constexpr int ICP_NSUB = ICP_THREADS / ICP_SUB;
-constexpr int ICP_LPT = ICP_LANES / ICP_SUB;
+// A CTA of k_icp hosts ICP_THREADS / SUB independent sub-workers of SUB threads (template parameter, 256 or 512). A sub-worker
+// serves its own problem and synchronises on its own named barrier; all share the CTA's one copy of the template and tree.
+// SUB = 256: four problems per SM instead of two - while one sits in its serial SVD or in a reduction the others keep the SM
+// busy (1024 VGA frames: 15.3 -> 14.5 ms). SUB = 512: all threads on one problem, for launches with fewer problems than
+// sub-workers (single frames, a few large clusters), where latency per problem is what counts. (4 x 128 threads: 18.1 ms.)
+template <int SUB>
 __device__ __forceinline__ void sub_sync(int sub) {   // literal barrier ids: a register id would reserve all 16 barriers
-    switch (sub) {
-        case 0: asm volatile("bar.sync 1, %0;" ::"n"(ICP_SUB) : "memory"); break;
-        case 1: asm volatile("bar.sync 2, %0;" ::"n"(ICP_SUB) : "memory"); break;
-        case 2: asm volatile("bar.sync 3, %0;" ::"n"(ICP_SUB) : "memory"); break;
-        default: asm volatile("bar.sync 4, %0;" ::"n"(ICP_SUB) : "memory"); break;
-    }
+    if (sub == 0) asm volatile("bar.sync 1, %0;" ::"n"(SUB) : "memory");
+    else asm volatile("bar.sync 2, %0;" ::"n"(SUB) : "memory");
 }
-static_assert(ICP_NSUB <= 4 && ICP_LPT * ICP_SUB == ICP_LANES, "sub_sync names four barriers; a thread stands for whole lanes");
 constexpr int ICP_LEAF = 16;       // template points per BVH leaf
 
 
@@ -254,9 +249,9 @@ __device__ __forceinline__ void canon_block_reduce(Tq (&v)[NQ], Tq* s_part /* [N
 }
 
 
-// the same for one sub-worker: canon_sub_partial after each of its ICP_LPT lane sets (v = the partial sums of canonical lane
-// tid + set * ICP_SUB), then canon_sub_finish
-template <typename Tq, int NQ>
+// the same for one sub-worker of SUB threads: canon_sub_partial after each of its lane sets (v = the partial sums of canonical
+// lane tid + set * SUB; threads beyond lane 255 carry zeros and are ignored), then canon_sub_finish
+template <typename Tq, int NQ, int SUB>
 __device__ __forceinline__ void canon_sub_partial(Tq (&v)[NQ], Tq* s_part /* [NQ][8] */, int tid, int set) {
     const int lane = tid & 31, wid = tid >> 5;
 #pragma unroll
@@ -264,12 +259,12 @@ __device__ __forceinline__ void canon_sub_partial(Tq (&v)[NQ], Tq* s_part /* [NQ
         Tq x = v[q];
 #pragma unroll
         for (int o = 16; o >= 1; o >>= 1) x = x + __shfl_xor_sync(FULL_MASK, x, o);
-        if (lane == 0) s_part[q * 8 + set * (ICP_SUB / 32) + wid] = x;   // canonical warp = lanes [32w, 32w + 32)
+        if (lane == 0 && set * (SUB / 32) + wid < 8) s_part[q * 8 + set * (SUB / 32) + wid] = x;   // canonical warp = lanes [32w, 32w + 32)
     }
 }
-template <typename Tq, int NQ>
+template <typename Tq, int NQ, int SUB>
 __device__ __forceinline__ void canon_sub_finish(Tq* s_part /* [NQ][8] */, Tq* s_out, int tid, int sub) {
-    sub_sync(sub);
+    sub_sync<SUB>(sub);
     if (tid < NQ) {
         const Tq* p = s_part + tid * 8;
         Tq s = p[0];
@@ -277,7 +272,7 @@ __device__ __forceinline__ void canon_sub_finish(Tq* s_part /* [NQ][8] */, Tq* s
         for (int g = 1; g < 8; ++g) s = s + p[g];
         s_out[tid] = s;
     }
-    sub_sync(sub);
+    sub_sync<SUB>(sub);
 }
 
 struct IcpShared {
@@ -574,7 +569,7 @@ __global__ void __launch_bounds__(ICP_THREADS) k_icp_init(const IcpArgs a) {
     __shared__ float s_guess[16];
     const int g = blockIdx.x, c = blockIdx.y, f = blockIdx.z;
     const cuboid_frame_result& R = a.res[f];
-    if (blockIdx.x == 0 && blockIdx.y == 0 && blockIdx.z == 0 && threadIdx.x == 0) a.queue->alive = a.crew * ICP_NSUB;   // poppers = sub-workers
+    if (blockIdx.x == 0 && blockIdx.y == 0 && blockIdx.z == 0 && threadIdx.x == 0) a.queue->alive = a.crew * a.nsub;   // poppers = sub-workers
     if (c >= min(R.n_clusters, CUBOID_MAX_CLUSTERS)) return;   // not a problem: n_total counts only real ones
     const int prob = (f * CUBOID_MAX_CLUSTERS + c) * a.n_guess + g;
     const int* offsets = a.offsets + (size_t)f * (a.KC + 1);
@@ -641,7 +636,7 @@ __global__ void __launch_bounds__(ICP_THREADS) k_icp_init(const IcpArgs a) {
 
 // One time slice of one problem: up to a.slice_iters iterations of the ICP loop, then either the closing fitness pass
 // (problem finished) or a state save (problem goes back on the queue).
-template <bool RESIDENT>
+template <bool RESIDENT, int SUB>
 __device__ __forceinline__ bool icp_slice(const IcpArgs& a, IcpShared& sh, const float* s_tmpl, const uint4* s_nodes, int prob, int tid, int sub,
                                           unsigned long long* s_hh, unsigned long long* s_ev) {
     const int g = prob % a.n_guess, c = (prob / a.n_guess) % CUBOID_MAX_CLUSTERS, f = prob / (a.n_guess * CUBOID_MAX_CLUSTERS);
@@ -657,6 +652,8 @@ __device__ __forceinline__ bool icp_slice(const IcpArgs& a, IcpShared& sh, const
     IcpState& ps = a.pstate[prob];
     const bool trace = a.corr_trace && f == 0 && c == 0 && g == 0;
     const float* tp = RESIDENT ? s_tmpl : a.tmpl;
+    constexpr int LPT = SUB >= ICP_LANES ? 1 : ICP_LANES / SUB;   // canonical lanes per thread
+    const bool canon = tid < ICP_LANES;                         // SUB = 512: the upper half only helps outside the reductions
 
     if (tid < 16) sh.fin[tid] = __ldcg(&ps.fin[tid]);
     if (tid == 0) {
@@ -664,7 +661,7 @@ __device__ __forceinline__ bool icp_slice(const IcpArgs& a, IcpShared& sh, const
         sh.prev_mse = __ldcg(&ps.prev_mse);
         sh.task = 0;
     }
-    sub_sync(sub);
+    sub_sync<SUB>(sub);
     unsigned long long chash = 0, evaluated = 0;
     const float one_over_n = 1.0f / (float)S;
     int it = sh.iters, passes = 0;
@@ -673,13 +670,13 @@ __device__ __forceinline__ bool icp_slice(const IcpArgs& a, IcpShared& sh, const
         // 1. correspondences
         icp_nn_pass<RESIDENT>(a, sh, s_tmpl, s_nodes, cur, S, order, corr, cd, evaluated);
         ++passes;
-        sub_sync(sub);
+        sub_sync<SUB>(sub);
         if (tid == 0) sh.task = 0;
         // 2. means + MSE: the first 256 threads are the 256 canonical lanes
-        for (int set = 0; set < ICP_LPT; ++set) {
+        for (int set = 0; set < LPT; ++set) {
             float q6[6] = {0.f, 0.f, 0.f, 0.f, 0.f, 0.f};
             double qd[1] = {0.0};
-            for (int i = tid + set * ICP_SUB; i < S; i += ICP_LANES) {
+            for (int i = canon ? tid + set * SUB : S; i < S; i += ICP_LANES) {
                 const float4 p = __ldcg(cur + i);
                 const int pos = __ldcg(corr + i);
                 const float3 t = tmpl_point(tp, pos);
@@ -690,22 +687,22 @@ __device__ __forceinline__ bool icp_slice(const IcpArgs& a, IcpShared& sh, const
                 chash += splitmix64((((unsigned long long)it * (unsigned long long)S + (unsigned long long)i) << 32) | (unsigned int)j);
                 if (trace && it < a.cap_trace) a.corr_trace[(size_t)it * S + i] = j;
             }
-            canon_sub_partial<float, 6>(q6, sh.part_f, tid, set);
-            canon_sub_partial<double, 1>(qd, sh.part_d, tid, set);
+            canon_sub_partial<float, 6, SUB>(q6, sh.part_f, tid, set);
+            canon_sub_partial<double, 1, SUB>(qd, sh.part_d, tid, set);
         }
-        canon_sub_finish<float, 6>(sh.part_f, sh.red_f, tid, sub);
-        canon_sub_finish<double, 1>(sh.part_d, sh.red_d, tid, sub);
+        canon_sub_finish<float, 6, SUB>(sh.part_f, sh.red_f, tid, sub);
+        canon_sub_finish<double, 1, SUB>(sh.part_d, sh.red_d, tid, sub);
         float sm[3], dm[3];
 #pragma unroll
         for (int k = 0; k < 3; ++k) { sm[k] = sh.red_f[k] * one_over_n; dm[k] = sh.red_f[3 + k] * one_over_n; }
         const double mse_sum = sh.red_d[0];
-        sub_sync(sub);
+        sub_sync<SUB>(sub);
         // 3. sigma = one_over_n * dst_demean * src_demean^T
-        for (int set = 0; set < ICP_LPT; ++set) {
+        for (int set = 0; set < LPT; ++set) {
             float q9[9];
 #pragma unroll
             for (int k = 0; k < 9; ++k) q9[k] = 0.f;
-            for (int i = tid + set * ICP_SUB; i < S; i += ICP_LANES) {
+            for (int i = canon ? tid + set * SUB : S; i < S; i += ICP_LANES) {
                 const float4 p = __ldcg(cur + i);
                 const float3 t = tmpl_point(tp, __ldcg(corr + i));
                 const float sd[3] = {p.x - sm[0], p.y - sm[1], p.z - sm[2]};
@@ -715,9 +712,9 @@ __device__ __forceinline__ bool icp_slice(const IcpArgs& a, IcpShared& sh, const
 #pragma unroll
                     for (int cc = 0; cc < 3; ++cc) q9[3 * r + cc] = q9[3 * r + cc] + dd[r] * sd[cc];
             }
-            canon_sub_partial<float, 9>(q9, sh.part_f, tid, set);
+            canon_sub_partial<float, 9, SUB>(q9, sh.part_f, tid, set);
         }
-        canon_sub_finish<float, 9>(sh.part_f, sh.red_f, tid, sub);
+        canon_sub_finish<float, 9, SUB>(sh.part_f, sh.red_f, tid, sub);
         // 4. thread 0: SVD, R, t, final, convergence
         if (tid == 0) {
             M3f sigma, U, V;
@@ -765,28 +762,28 @@ __device__ __forceinline__ bool icp_slice(const IcpArgs& a, IcpShared& sh, const
             }
             sh.done = done;
         }
-        sub_sync(sub);
+        sub_sync<SUB>(sub);
         // 5. transformCloud(input_transformed, input_transformed, transformation_): incremental, in place
-        for (int i = tid; i < S; i += ICP_SUB) cur[i] = xform(sh.Tm, __ldcg(cur + i));
+        for (int i = tid; i < S; i += SUB) cur[i] = xform(sh.Tm, __ldcg(cur + i));
         ++it;
-        sub_sync(sub);
+        sub_sync<SUB>(sub);
     }
     const bool finished = sh.done != 0;
     double fitness = 1.7976931348623157e308;
     if (finished) {
         // ---- output = transformCloud(src, final); getFitnessScore(): one more nearest-neighbour pass ----
-        for (int i = tid; i < S; i += ICP_SUB) cur[i] = xform(sh.fin, src[idx[i]]);
-        sub_sync(sub);
+        for (int i = tid; i < S; i += SUB) cur[i] = xform(sh.fin, src[idx[i]]);
+        sub_sync<SUB>(sub);
         if (S > 0) {
             icp_nn_pass<RESIDENT>(a, sh, s_tmpl, s_nodes, cur, S, order, corr, cd, evaluated);
             ++passes;
-            sub_sync(sub);
-            for (int set = 0; set < ICP_LPT; ++set) {
+            sub_sync<SUB>(sub);
+            for (int set = 0; set < LPT; ++set) {
                 double qd[1] = {0.0};
-                for (int i = tid + set * ICP_SUB; i < S; i += ICP_LANES) qd[0] = qd[0] + (double)__ldcg(cd + i);
-                canon_sub_partial<double, 1>(qd, sh.part_d, tid, set);
+                for (int i = canon ? tid + set * SUB : S; i < S; i += ICP_LANES) qd[0] = qd[0] + (double)__ldcg(cd + i);
+                canon_sub_partial<double, 1, SUB>(qd, sh.part_d, tid, set);
             }
-            canon_sub_finish<double, 1>(sh.part_d, sh.red_d, tid, sub);
+            canon_sub_finish<double, 1, SUB>(sh.part_d, sh.red_d, tid, sub);
             fitness = sh.red_d[0] / (double)S;
         }
     }
@@ -794,10 +791,10 @@ __device__ __forceinline__ bool icp_slice(const IcpArgs& a, IcpShared& sh, const
     chash = warp_sum_u64(chash);
     evaluated = warp_sum_u64(evaluated);   // pairs evaluated by the 32 lanes
     if ((tid & 31) == 0) { s_hh[tid >> 5] = chash; s_ev[tid >> 5] = evaluated; }
-    sub_sync(sub);
+    sub_sync<SUB>(sub);
     if (tid == 0) {
         unsigned long long t = __ldcg(&ps.chash), ev = __ldcg(&ps.evaluated);
-        for (int k = 0; k < ICP_SUB / 32; ++k) { t += s_hh[k]; ev += s_ev[k]; }
+        for (int k = 0; k < SUB / 32; ++k) { t += s_hh[k]; ev += s_ev[k]; }
         const int all_passes = __ldcg(&ps.passes) + passes;
         if (finished) {
             IcpOut& out = a.out[prob];
@@ -817,18 +814,20 @@ __device__ __forceinline__ bool icp_slice(const IcpArgs& a, IcpShared& sh, const
             ps.chash = t; ps.evaluated = ev;
         }
     }
-    sub_sync(sub);
+    sub_sync<SUB>(sub);
     return finished;
 }
 
 // Persistent worker: stages the BVH (and the template, if it fits) in shared memory ONCE, then serves time slices of
 // whatever problem is next on the queue until every problem of the launch is finished. Slicing bounds the tail: without
 // it the kernel ends when the problem with the most iterations (40 .. 150 here) ends, with most SMs idle by then.
+template <int SUB>
 __global__ void __launch_bounds__(ICP_THREADS, 2) k_icp(const IcpArgs a) {
+    constexpr int NSUB = ICP_THREADS / SUB;
     extern __shared__ __align__(128) unsigned char smem_raw[];
-    __shared__ IcpShared shs[ICP_NSUB];
-    __shared__ int s_prob[ICP_NSUB];
-    __shared__ unsigned long long s_hh[ICP_NSUB][ICP_SUB / 32], s_ev[ICP_NSUB][ICP_SUB / 32];
+    __shared__ IcpShared shs[NSUB];
+    __shared__ int s_prob[NSUB];
+    __shared__ unsigned long long s_hh[NSUB][SUB / 32], s_ev[NSUB][SUB / 32];
     // dynamic shared memory: [BVH nodes (nnodes x 16 B)] [template SoA leaves (Tpad*3 floats)] [sibling chains] (the last two: resident case)
     uint4* s_nodes = reinterpret_cast<uint4*>(smem_raw);
     float* s_tmpl = reinterpret_cast<float*>(s_nodes + a.nnodes);
@@ -852,21 +851,21 @@ __global__ void __launch_bounds__(ICP_THREADS, 2) k_icp(const IcpArgs a) {
     mbar_wait(&shs[0].bar, 0);
     __syncthreads();
     // from here on the sub-workers go their own ways
-    const int sub = threadIdx.x / ICP_SUB, tid = threadIdx.x % ICP_SUB;
+    const int sub = threadIdx.x / SUB, tid = threadIdx.x % SUB;
     IcpShared& sh = shs[sub];
     while (true) {
         if (tid == 0) s_prob[sub] = icp_queue_pop(a.queue, a.ring, a.n_slots);
-        sub_sync(sub);
+        sub_sync<SUB>(sub);
         const int prob = s_prob[sub];
         if (prob < 0) break;
-        const bool finished = a.resident ? icp_slice<true>(a, sh, s_tmpl, s_nodes, prob, tid, sub, s_hh[sub], s_ev[sub])
-                                         : icp_slice<false>(a, sh, s_tmpl, s_nodes, prob, tid, sub, s_hh[sub], s_ev[sub]);
+        const bool finished = a.resident ? icp_slice<true, SUB>(a, sh, s_tmpl, s_nodes, prob, tid, sub, s_hh[sub], s_ev[sub])
+                                         : icp_slice<false, SUB>(a, sh, s_tmpl, s_nodes, prob, tid, sub, s_hh[sub], s_ev[sub]);
         if (tid == 0) {
             __threadfence();   // state / outputs before the hand-over
             if (finished) atomicAdd(&a.queue->n_done, 1);
             else icp_queue_push(a.queue, a.ring, a.n_slots, prob);
         }
-        sub_sync(sub);
+        sub_sync<SUB>(sub);
     }
 }
 

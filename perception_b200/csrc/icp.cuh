@@ -82,8 +82,12 @@ constexpr int ICP_LANES = 256;
 // sub-workers (single frames, a few large clusters), where latency per problem is what counts. (4 x 128 threads: 18.1 ms.)
 template <int SUB>
 __device__ __forceinline__ void sub_sync(int sub) {   // literal barrier ids: a register id would reserve all 16 barriers
-    if (sub == 0) asm volatile("bar.sync 1, %0;" ::"n"(SUB) : "memory");
-    else asm volatile("bar.sync 2, %0;" ::"n"(SUB) : "memory");
+    switch (sub) {
+        case 0: asm volatile("bar.sync 1, %0;" ::"n"(SUB) : "memory"); break;
+        case 1: asm volatile("bar.sync 2, %0;" ::"n"(SUB) : "memory"); break;
+        case 2: asm volatile("bar.sync 3, %0;" ::"n"(SUB) : "memory"); break;
+        default: asm volatile("bar.sync 4, %0;" ::"n"(SUB) : "memory"); break;
+    }
 }
 constexpr int ICP_LEAF = 16;       // template points per BVH leaf
 
@@ -259,7 +263,7 @@ __device__ __forceinline__ void canon_sub_partial(Tq (&v)[NQ], Tq* s_part /* [NQ
         Tq x = v[q];
 #pragma unroll
         for (int o = 16; o >= 1; o >>= 1) x = x + __shfl_xor_sync(FULL_MASK, x, o);
-        if (lane == 0 && set * (SUB / 32) + wid < 8) s_part[q * 8 + set * (SUB / 32) + wid] = x;   // canonical warp = lanes [32w, 32w + 32)
+        if (lane == 0 && (SUB <= ICP_LANES || wid < 8)) s_part[q * 8 + set * (SUB / 32) + wid] = x;   // canonical warp = lanes [32w, 32w + 32)
     }
 }
 template <typename Tq, int NQ, int SUB>
@@ -653,7 +657,7 @@ __device__ __forceinline__ bool icp_slice(const IcpArgs& a, IcpShared& sh, const
     const bool trace = a.corr_trace && f == 0 && c == 0 && g == 0;
     const float* tp = RESIDENT ? s_tmpl : a.tmpl;
     constexpr int LPT = SUB >= ICP_LANES ? 1 : ICP_LANES / SUB;   // canonical lanes per thread
-    const bool canon = tid < ICP_LANES;                         // SUB = 512: the upper half only helps outside the reductions
+    const bool canon = SUB <= ICP_LANES || tid < ICP_LANES;     // SUB = 512: the upper half only helps outside the reductions
 
     if (tid < 16) sh.fin[tid] = __ldcg(&ps.fin[tid]);
     if (tid == 0) {

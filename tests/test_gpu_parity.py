@@ -488,3 +488,21 @@ def test_icp_on_the_reference_real_scan_returns_the_published_pose(golden, param
     assert _pose_close(g["T"], T) and g["fitness"] < 1e-12
     ref_far = O.icp(cap, tpl, rel_mse=params.icp_rel_mse)
     assert far["iters"] == ref_far["iters"] and far["corr_hash"] == ref_far["corr_hash"] and np.array_equal(bits(far["T"]), bits(ref_far["T"]))
+
+
+@pytest.mark.parametrize("knob,values", [("CUBOID_ICP_NSUB", ("1", "2")), ("CUBOID_ICP_SLICE", ("1", "8", "5000")),
+                                         ("CUBOID_ICP_OUTWARD", ("0", "1")), ("CUBOID_PIPELINE", ("0", "1"))])
+def test_execution_knobs_do_not_change_results(tmpl30, params, knob, values, monkeypatch):
+    """How the work is scheduled must never show in the results: sub-workers per CTA, iterations per time slice, outward search
+    vs descent from the root, pipelined sub-chunks vs one chunk - every result byte of a 40-frame batch is the same."""
+    depth = np.concatenate([synth.depth_batch("bench", list(range(60, 96))), synth.depth_batch("tallbox", [0, 1]),
+                            np.zeros((2, 480, 640), np.uint16)])
+    out = []
+    for v in values:
+        monkeypatch.setenv(knob, v)
+        monkeypatch.setenv("CUBOID_SUB_BATCH", "16")
+        with api.CuboidCuda(params, max_points=640 * 480, max_batch=40) as h:
+            h.set_template(0, tmpl30)
+            out.append([bytes(r) for r in h.process_batch(depth)])
+    for o in out[1:]:
+        assert o == out[0]

@@ -220,18 +220,28 @@ struct SacShared {
 template <typename Pred>
 __device__ int sac_compact(int V, Pred pred, int* out_idx, float4* out_pts, const float4* vox, int cap,
                            uint64_t* hash_idx, uint64_t* hash_pts, int* s_w) {
+    constexpr int PER = 4;   // consecutive elements per thread and round: a quarter of the block scans of one-per-thread
     int base = 0;
     unsigned long long hi = 0, hp = 0;
-    for (int start = 0; start < V; start += SAC_THREADS) {
-        const int i = start + threadIdx.x;
-        float4 p = make_float4(0.f, 0.f, 0.f, 0.f);
-        bool keep = false;
-        if (i < V) { p = vox[i]; keep = pred(i, p); }
+    for (int start = 0; start < V; start += SAC_THREADS * PER) {
+        const int i0 = start + threadIdx.x * PER;
+        float4 p[PER];
+        unsigned int keep = 0;
+#pragma unroll
+        for (int k = 0; k < PER; ++k) {
+            p[k] = make_float4(0.f, 0.f, 0.f, 0.f);
+            if (i0 + k < V) { p[k] = vox[i0 + k]; if (pred(i0 + k, p[k])) keep |= 1u << k; }
+        }
         int total;
-        const int pos = base + block_excl_scan256(keep ? 1 : 0, s_w, &total);
-        if (keep && pos < cap) {
-            if (out_idx) { out_idx[pos] = i; hi += hash_index((unsigned int)pos, i); }
-            if (out_pts) { out_pts[pos] = p; hp += hash_point((unsigned int)pos, p.x, p.y, p.z); }
+        int pos = base + block_excl_scan256(__popc(keep), s_w, &total);
+#pragma unroll
+        for (int k = 0; k < PER; ++k) {
+            if (!(keep & (1u << k))) continue;
+            if (pos < cap) {
+                if (out_idx) { out_idx[pos] = i0 + k; hi += hash_index((unsigned int)pos, i0 + k); }
+                if (out_pts) { out_pts[pos] = p[k]; hp += hash_point((unsigned int)pos, p[k].x, p[k].y, p[k].z); }
+            }
+            ++pos;
         }
         base += total;
         __syncthreads();

@@ -237,7 +237,7 @@ int run_chunk(cuboid_handle* h, const ChunkIn& in, int nf, cuboid_frame_result* 
         a.pts = b_pts; a.res = d_res; a.scr = b_scr; a.n_frames = nf; a.Pout = h->P;
         if (in.in_stride > h->P) return CUBOID_E_CAPACITY;
         fa.keys = fe_keys_override ? fe_keys_override : h->d_fe_keys; fa.kpp = h->taps ? b_kpp : nullptr; fa.vox = b_vox; fa.vcount = h->taps ? b_vcount : nullptr;
-        fa.inv_leaf = 1.0f / p.leaf; fa.P = h->P; fa.n_frames = nf;
+        fa.inv_leaf = 1.0f / p.leaf; fa.P = h->P; fa.n_frames = nf; fa.hashes = h->taps ? 1 : 0;
         cudaLaunchConfig_t cfg{};
         cudaLaunchAttribute at[1];
         at[0].id = cudaLaunchAttributeClusterDimension;

@@ -31,6 +31,7 @@ struct FrontArgs {
     float4* vox;                 // [F][P]
     int* vcount;                 // [F][P] points per voxel (parity tap) or NULL
     float inv_leaf;
+    int hashes;                  // 1: accumulate points_hash / voxel_key_hash / voxel_hash (parity taps); 0: leave them 0
     int P;                       // per-frame stride of pts / vox / kpp / vcount / keys
     int n_frames;
 };
@@ -323,8 +324,10 @@ __global__ void __launch_bounds__(NT, 2048 / NT >= 2 ? (NT <= 512 ? 2 : 1) : 1) 
                         sk = g.overflow_mode ? ((unsigned int)idx ^ 0x80000000u) : (unsigned int)idx;
                         __stcg(bufA + pos, ((unsigned long long)sk << 32) | (unsigned int)pos);
                         if (kpp) kpp[pos] = idx;
-                        hh[0] += hash_point((unsigned int)pos, pt.x, pt.y, pt.z);
-                        hh[1] += hash_index((unsigned int)pos, idx);
+                        if (a.hashes) {
+                            hh[0] += hash_point((unsigned int)pos, pt.x, pt.y, pt.z);
+                            hh[1] += hash_index((unsigned int)pos, idx);
+                        }
                     }
                     if (C == 1 && valid) {   // one CTA owns the frame: every pass's digit histogram is order-independent, count it here
 #pragma unroll
@@ -525,7 +528,7 @@ __global__ void __launch_bounds__(NT, 2048 / NT >= 2 ? (NT <= 512 ? 2 : 1) : 1) 
                     const float cx = sx / cnt, cy = sy / cnt, cz = sz / cnt;
                     vox[pos] = make_float4(cx, cy, cz, 1.0f);
                     if (vcount) vcount[pos] = end - lp;
-                    hv[0] += hash_point((unsigned int)pos, cx, cy, cz);
+                    if (a.hashes) hv[0] += hash_point((unsigned int)pos, cx, cy, cz);
                 }
                 vrun += total;
                 __syncthreads();
@@ -562,7 +565,7 @@ __global__ void __launch_bounds__(NT, 2048 / NT >= 2 ? (NT <= 512 ? 2 : 1) : 1) 
                         const int vp = s_def_pos[d];
                         vox[vp] = make_float4(cx, cy, cz, 1.0f);
                         if (vcount) vcount[vp] = acc.cnt;
-                        hv[0] += hash_point((unsigned int)vp, cx, cy, cz);
+                        if (a.hashes) hv[0] += hash_point((unsigned int)vp, cx, cy, cz);
                     }
                 }
                 __syncthreads();

@@ -57,14 +57,21 @@ struct FeFrame {         // cluster-wide facts of the current frame, replicated 
 //   A1/A2   u16 tile-local input index of every survivor of the tile            NT*8*2  bytes
 //           + the tile's depth values (u16), + the keep masks A1 found, so A2       NT*8*2 + FE_MASK_BYTES
 //             does not unproject and filter again
-//   B       per-warp digit counters [NT/32][256] u32                            NT*32   bytes
+//   B       per-warp digit counters [NT/32][256] u32 + two prefetched key tiles   NT*32 + 2*NT*8*8 bytes
 //   C2      key,x,y,z of the staged sorted records (+ look-ahead) + u16 heads   (NT*4+128)*16 + NT*4*2 bytes
 constexpr int FE_MASK_BYTES = 40960;   // keep masks of one input slice (1 byte per 8 inputs): a VGA frame on one CTA needs 38 400
+constexpr int fe_max(int a, int b) { return a > b ? a : b; }
 template <int NT>
-constexpr int fe_dyn_smem() {
-    return (NT * 32 + FE_MASK_BYTES) > ((NT * FE_RITEMS + FE_LOOK) * 16 + NT * FE_RITEMS * 2) ? (NT * 32 + FE_MASK_BYTES)
-                                                                                             : ((NT * FE_RITEMS + FE_LOOK) * 16 + NT * FE_RITEMS * 2);
+constexpr int fe_dyn_smem() {   // A: selection + depth tile + masks; B: digit counters + two prefetched key tiles; C2: staging + heads
+    return fe_max(fe_max(NT * 32 + FE_MASK_BYTES, NT * 32 + 2 * NT * FE_ITEMS * 8), (NT * FE_RITEMS + FE_LOOK) * 16 + NT * FE_RITEMS * 2);
 }
+// asynchronous global -> shared copies (LDGSTS): the next tile of sort records is on its way while this one is ranked
+__device__ __forceinline__ void fe_cp_async16(void* smem, const void* gmem) {
+    asm volatile("cp.async.cg.shared.global [%0], [%1], 16;" ::"r"((unsigned int)__cvta_generic_to_shared(smem)), "l"(gmem) : "memory");
+}
+__device__ __forceinline__ void fe_cp_async_commit() { asm volatile("cp.async.commit_group;" ::: "memory"); }
+template <int N>
+__device__ __forceinline__ void fe_cp_async_wait() { asm volatile("cp.async.wait_group %0;" ::"n"(N) : "memory"); }
 
 template <int NT, int NQ>
 __device__ __forceinline__ void fe_block_sum_u64(unsigned long long (&v)[NQ], unsigned long long* s_part /*[NQ][NT/32]*/) {
@@ -386,16 +393,34 @@ __global__ void __launch_bounds__(NT, 2048 / NT >= 2 ? (NT <= 512 ? 2 : 1) : 1) 
                 if (tid < 256) s_base[tid] = (unsigned int)ex + before;
                 __syncthreads();
             }
-            for (int t0 = q0; t0 < q1; t0 += TILE) {
+            // Full tiles are prefetched one tile ahead with 16-byte asynchronous copies (L2 only, like __ldcg): every warp fetches
+            // its own 256 records (2 KB), lane l the 16-byte chunks l, l + 32, l + 64, l + 96, so a __syncwarp publishes them.
+            unsigned long long* s_pre = reinterpret_cast<unsigned long long*>(fe_dyn + NT * 32);
+            auto prefetch = [&](int t0, int buf) {
+                if (t0 < q1 && t0 + TILE <= q1) {
+                    const unsigned long long* g = src + t0 + wid * (32 * FE_ITEMS);
+                    unsigned long long* sdst = s_pre + buf * TILE + wid * (32 * FE_ITEMS);
+#pragma unroll
+                    for (int j = 0; j < FE_ITEMS / 2; ++j) fe_cp_async16(sdst + 2 * (j * 32 + lane), g + 2 * (j * 32 + lane));
+                }
+                fe_cp_async_commit();
+            };
+            prefetch(q0, 0);
+            int buf = 0;
+            for (int t0 = q0; t0 < q1; t0 += TILE, buf ^= 1) {
                 for (int d = lane; d < 256; d += 32) s_cnt[wid][d] = 0;
+                prefetch(t0 + TILE, buf ^ 1);
+                fe_cp_async_wait<1>();
                 __syncwarp();
                 // warp w owns the contiguous run [t0 + w*256, +256): (warp, item, lane) order == ascending input order
                 unsigned long long key[FE_ITEMS];
                 unsigned int rank[FE_ITEMS];
+                const bool full = t0 + TILE <= q1;
 #pragma unroll
                 for (int k = 0; k < FE_ITEMS; ++k) {
                     const int i = t0 + wid * (32 * FE_ITEMS) + k * 32 + lane;
-                    key[k] = i < q1 ? __ldcg(src + i) : ~0ull;
+                    if (full) key[k] = s_pre[buf * TILE + wid * (32 * FE_ITEMS) + k * 32 + lane];
+                    else key[k] = i < q1 ? __ldcg(src + i) : ~0ull;
                 }
 #pragma unroll
                 for (int k = 0; k < FE_ITEMS; ++k) {
@@ -428,6 +453,7 @@ __global__ void __launch_bounds__(NT, 2048 / NT >= 2 ? (NT <= 512 ? 2 : 1) : 1) 
                 }
                 __syncthreads();
             }
+            fe_cp_async_wait<0>();
             __threadfence();
             cluster.sync();
         }

@@ -670,6 +670,18 @@ __device__ __forceinline__ bool icp_slice(const IcpArgs& a, IcpShared& sh, const
     const float one_over_n = 1.0f / (float)S;
     int it = sh.iters, passes = 0;
     const int it_end = it + a.slice_iters;
+    if (it == 0 && !sh.done && S > 64 && a.cull) {
+        // First pass of a problem: every seed is template position 0, i.e. no bound at all, and the cloud is typically far from
+        // the template, so each query would walk most of the tree. Search the first warp's worth of queries properly, then hand
+        // the answer of one of them to everybody as the seed: any valid template position is a valid seed, results are unchanged.
+        icp_nn_pass<RESIDENT>(a, sh, s_tmpl, s_nodes, cur, 32, order, corr, cd, evaluated);
+        sub_sync<SUB>(sub);
+        if (tid == 0) sh.task = 0;
+        const int seed = __ldcg(corr + order[0]);
+        sub_sync<SUB>(sub);
+        for (int i = tid; i < S; i += SUB) corr[i] = seed;
+        sub_sync<SUB>(sub);
+    }
     while (!sh.done && it < it_end) {
         // 1. correspondences
         icp_nn_pass<RESIDENT>(a, sh, s_tmpl, s_nodes, cur, S, order, corr, cd, evaluated);

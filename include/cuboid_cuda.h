@@ -70,7 +70,7 @@ typedef struct {
     double sac_prob;                     /* 0.99 (PCL default) */
     int32_t sac_refine;                  /* setOptimizeCoefficients(true)  gps.cpp:85 */
     int32_t extract_negative;            /* invert        gps.cpp:100 */
-    double cluster_tol;                  /* 0.02          opd.cpp:356 */
+    double cluster_tol;                  /* 0.02          opd.cpp:356; accepted range [1e-4, 1e3] m */
     int32_t cluster_min, cluster_max;    /* 200, 25000    opd.cpp:357-358 */
     int32_t use_cluster;                 /* 1: opd.cpp:346-413 per-cluster ICP; 0: icp.cpp:156-178 whole cloud */
     int32_t icp_max_iter;                /* 5000          icp.cpp:173 */

@@ -2,14 +2,18 @@
 //
 // A Euclidean cluster is a connected component of the graph {(i,j) : d2(i,j) < (float)(tol*tol)} with
 // d2 = ((dx*dx)+dy*dy)+dz*dz in float (FLANN L2_Simple, strict '<'), so the BFS order of the reference
-// does not matter. One CTA per frame: points are binned into a hashed uniform grid (cell = 1.001 * tol, so
-// two points closer than tol are always in the same or in adjacent cells), every point tests the candidates
-// of its 27 neighbour cells with the exact float distance, and edges feed a lock-free union-find (larger
+// does not matter, and neither does which edges are used as long as the components come out the same.
+// One CTA per frame: points are binned into a hashed uniform grid of FINE cells (side 0.52 * tol). Two points
+// of one cell are always within tol (3 * 0.52^2 = 0.81 < 1), so a cell is united without distance tests;
+// two points within tol are at most 2 cells apart per axis (1 / 0.52 = 1.92 < 2), so cell pairs of the
+// 5x5x5 neighbourhood are examined, each only until ONE pair of points within tol is found (exact float test)
+// or not at all when both cells already hang under the same root. Both margins (19 % and 4 %) dwarf the float
+// rounding of the cell coordinate for |coordinate / cell| < 1e6. Edges feed a lock-free union-find (larger
 // root hooks under smaller root, so a component's root is its smallest member). Then the size filter, the
 // canonical ordering (size descending, ties by smallest member) and a stable scatter of the member indices
 // (ascending inside each cluster).
 //
-// Roofline: latency bound; ops = 8 * M * d-bar with d-bar = candidates examined per point (27 cells); bytes = 20*M.
+// Roofline: latency bound; work = cells * 62 probes + (cell pairs examined) * (points per cell)^2 tests; bytes = 20*M.
 #pragma once
 #include "common.cuh"
 
@@ -28,11 +32,10 @@ struct CluArgs {
     cuboid_frame_result* res;
     int P, M, KC;
     float r2;
-    float inv_cell;         // 1 / (1.001 * tol)
+    float inv_cell;         // 1 / (0.52 * tol)
     int min_size, max_size, use_cluster;
 };
 
-constexpr int CLU_RUNMAP = 256;     // candidates per query whose run is looked up in a table instead of searched
 constexpr int CLU_THREADS = 1024;   // two CTAs per SM (the shared-memory tiers below are sized for that): 1.86 ms vs 2.15 ms / 1024 frames with one
 
 __device__ __forceinline__ unsigned int cell_hash(int cx, int cy, int cz) {
@@ -66,17 +69,13 @@ constexpr int CLU_SMEM_UF = 12288;
 struct CluShared {
     int s_w[CLU_THREADS / 32 + 1];
     int s_cur[1024];
-    int s_off[CLU_THREADS / 32][32], s_beg[CLU_THREADS / 32][32];
-    unsigned char s_runof[CLU_THREADS / 32][CLU_RUNMAP];   // run of every flattened candidate (queries with few enough of them)
     unsigned long long s_h[CLU_THREADS / 32];
+    int s_nrep;
 };
 template <int MODE>
 __device__ __forceinline__ void cluster_body(const CluArgs& a, CluShared& cs) {
     int* s_w = cs.s_w;
     int* s_cur = cs.s_cur;
-    int (*s_off)[32] = cs.s_off;
-    int (*s_beg)[32] = cs.s_beg;
-    unsigned char (*s_runof)[CLU_RUNMAP] = cs.s_runof;
     unsigned long long* s_h = cs.s_h;
     const int f = blockIdx.x;
     cuboid_frame_result& R = a.res[f];
@@ -114,8 +113,8 @@ __device__ __forceinline__ void cluster_body(const CluArgs& a, CluShared& cs) {
     for (int i = threadIdx.x; i < n; i += CLU_THREADS) { parent[i] = i; csize[i] = 0; crank[i] = -1; }
     __syncthreads();
 
-    // hashed uniform grid: table size = power of two >= 2n; points are counting-sorted by bucket so that the
-    // candidates of a cell are one contiguous run (independent, pipelined loads instead of a pointer chase)
+    // hashed uniform grid of fine cells: table size = power of two >= 2n; points are counting-sorted by bucket so
+    // that the points of a cell are (part of) one contiguous run
     // MODE 0 shared layout: parent[4096] | cpts float4[4096] | cend[hs+1 <= 4097]
     float4* cpts = MODE == 0 ? reinterpret_cast<float4*>(s_dyn + CLU_SMEM_ALL) : a.cell_pts + (size_t)f * a.M;
     int* cend = MODE == 0 ? s_dyn + CLU_SMEM_ALL + 4 * CLU_SMEM_ALL : a.cell_start + (size_t)f * (2 * a.M + 2);
@@ -152,44 +151,89 @@ __device__ __forceinline__ void cluster_body(const CluArgs& a, CluShared& cs) {
         cpts[pos] = make_float4(p.x, p.y, p.z, __int_as_float(i));
     }
     __syncthreads();
-    // Pair test, one warp per query point: the (deduplicated) runs of its 27 neighbour buckets are flattened into
-    // one candidate sequence and the 32 lanes take consecutive candidates, so loads are contiguous and all lanes
-    // execute the same distance code. Edges feed the union-find; a pair already under one parent is skipped.
-    for (int i = wid; i < n; i += CLU_THREADS / 32) {
-        const float4 pi = pts[i];
-        const int cx = (int)floorf(pi.x * inv_cell), cy = (int)floorf(pi.y * inv_cell), cz = (int)floorf(pi.z * inv_cell);
-        int bstart = 0, blen = 0;
-        if (lane < 27) {
-            const unsigned int b = cell_hash(cx + (lane % 3) - 1, cy + ((lane / 3) % 3) - 1, cz + (lane / 9) - 1) & hmask;
-            const unsigned int same = __match_any_sync(0x07ffffffu, b);   // distinct neighbour cells can share a bucket
-            if (lane == __ffs(same) - 1) {
-                bstart = b ? cend[b - 1] : 0;
-                blen = cend[b] - bstart;
+    // (S) Points of one fine cell are within tol of each other (cell diagonal^2 = 3 * 0.52^2 tol^2 < r2), so every
+    // point is united with the first point of its cell in bucket order without a distance test; that first point
+    // is the cell's representative. One thread per bucketed position.
+    int* reps = idx_sorted;     // scratch until the final scatter writes the member lists
+    if (threadIdx.x == 0) cs.s_nrep = 0;
+    __syncthreads();
+    const bool edges = a.r2 > 0.f;
+    for (int pos = threadIdx.x; edges && pos < n; pos += CLU_THREADS) {
+        const float4 p = cpts[pos];
+        const int cx = (int)floorf(p.x * inv_cell), cy = (int)floorf(p.y * inv_cell), cz = (int)floorf(p.z * inv_cell);
+        const unsigned int b = cell_hash(cx, cy, cz) & hmask;
+        int q = b ? cend[b - 1] : 0;
+        float4 pq = p;
+        for (; q < pos; ++q) {
+            pq = cpts[q];
+            if ((int)floorf(pq.x * inv_cell) == cx && (int)floorf(pq.y * inv_cell) == cy && (int)floorf(pq.z * inv_cell) == cz) break;
+        }
+        if (q == pos) reps[atomicAdd(&cs.s_nrep, 1)] = pos;
+        else uf_unite(parent, __float_as_int(p.w), __float_as_int(pq.w));
+    }
+    __syncthreads();
+    // (P) Cell pairs, one warp per representative: two points closer than tol sit in cells at most 2 apart per axis
+    // (tol / cell = 1.92), and each unordered pair of cells is visited once, from the cell whose offset to the other
+    // is in the upper half of the 5x5x5 neighbourhood (62 offsets, probed by the lanes in two rounds). For every
+    // non-empty neighbour not already under the same root the lanes test point pairs with the exact float distance
+    // until the first one within tol; that single edge joins the two cells.
+    const int nrep = cs.s_nrep;
+    for (int r = wid; r < nrep; r += CLU_THREADS / 32) {
+        const float4 pa0 = cpts[reps[r]];
+        const int cx = (int)floorf(pa0.x * inv_cell), cy = (int)floorf(pa0.y * inv_cell), cz = (int)floorf(pa0.z * inv_cell);
+        const unsigned int bA = cell_hash(cx, cy, cz) & hmask;
+        const int sA = bA ? cend[bA - 1] : 0, lenA = cend[bA] - sA;
+        const int ia0 = __float_as_int(pa0.w);
+        for (int round = 0; round < 2; ++round) {
+            const int k = round * 32 + lane;
+            int sB = 0, lenB = 0;
+            if (k < 62) {
+                const int code = k + 63;
+                const int tx = cx + code % 5 - 2, ty = cy + (code / 5) % 5 - 2, tz = cz + code / 25 - 2;
+                const unsigned int b = cell_hash(tx, ty, tz) & hmask;
+                sB = b ? cend[b - 1] : 0;
+                lenB = cend[b] - sB;
+                if (lenB > 0) {     // cheap skip when the run starts with a point of the target cell that already shares A's root
+                    const float4 pb0 = cpts[sB];
+                    if ((int)floorf(pb0.x * inv_cell) == tx && (int)floorf(pb0.y * inv_cell) == ty && (int)floorf(pb0.z * inv_cell) == tz &&
+                        uf_find(parent, __float_as_int(pb0.w)) == uf_find(parent, ia0))
+                        lenB = 0;
+                }
+            }
+            unsigned int todo = __ballot_sync(FULL_MASK, lenB > 0);
+            while (todo) {
+                const int src = __ffs(todo) - 1;
+                todo &= todo - 1;
+                const int s2 = __shfl_sync(FULL_MASK, sB, src), l2 = __shfl_sync(FULL_MASK, lenB, src);
+                const int code = round * 32 + src + 63;
+                const int tx = cx + code % 5 - 2, ty = cy + (code / 5) % 5 - 2, tz = cz + code / 25 - 2;
+                const long long total = (long long)lenA * l2;
+                for (long long t0 = 0; t0 < total; t0 += 32) {
+                    const long long t = t0 + lane;
+                    bool hit = false;
+                    int ia = 0, ib = 0;
+                    if (t < total) {
+                        int qa, qb;
+                        if (total < (1ll << 31)) { qa = (int)t / l2; qb = (int)t - qa * l2; }
+                        else { qa = (int)(t / l2); qb = (int)(t - (long long)qa * l2); }
+                        const float4 pa = cpts[sA + qa], pb = cpts[s2 + qb];
+                        const float ddx = pa.x - pb.x, ddy = pa.y - pb.y, ddz = pa.z - pb.z;
+                        const float d2 = ((ddx * ddx) + ddy * ddy) + ddz * ddz;
+                        if (d2 < a.r2 &&        // buckets can hold foreign cells: both points must be in the cells of this pair
+                            (int)floorf(pa.x * inv_cell) == cx && (int)floorf(pa.y * inv_cell) == cy && (int)floorf(pa.z * inv_cell) == cz &&
+                            (int)floorf(pb.x * inv_cell) == tx && (int)floorf(pb.y * inv_cell) == ty && (int)floorf(pb.z * inv_cell) == tz) {
+                            hit = true; ia = __float_as_int(pa.w); ib = __float_as_int(pb.w);
+                        }
+                    }
+                    const unsigned int hm = __ballot_sync(FULL_MASK, hit);
+                    if (hm) {
+                        if (lane == __ffs(hm) - 1) uf_unite(parent, ia, ib);
+                        break;
+                    }
+                }
+                __syncwarp();
             }
         }
-        const int incl = warp_incl_scan(blen, lane);
-        const int total = __shfl_sync(FULL_MASK, incl, 31);
-        s_off[wid][lane] = incl - blen;     // exclusive offsets of the 32 (27 used) runs
-        s_beg[wid][lane] = bstart;
-        const bool mapped = total <= CLU_RUNMAP;
-        if (mapped)                          // every lane stamps its run's id on the candidates it owns (runs are short)
-            for (int j = 0; j < blen; ++j) s_runof[wid][incl - blen + j] = (unsigned char)lane;
-        __syncwarp();
-        for (int t = lane; t < total; t += 32) {
-            int e = 0;                      // last run with offset <= t (runs of length 0 share offsets: take the last)
-            if (mapped) e = s_runof[wid][t];
-            else {
-#pragma unroll
-                for (int step = 16; step >= 1; step >>= 1)
-                    if (e + step < 32 && s_off[wid][e + step] <= t) e += step;
-            }
-            const float4 pj = cpts[s_beg[wid][e] + (t - s_off[wid][e])];
-            const int j = __float_as_int(pj.w);
-            const float ddx = pi.x - pj.x, ddy = pi.y - pj.y, ddz = pi.z - pj.z;
-            const float d2 = ((ddx * ddx) + ddy * ddy) + ddz * ddz;
-            if (j < i && d2 < a.r2 && ((volatile int*)parent)[j] != ((volatile int*)parent)[i]) uf_unite(parent, i, j);
-        }
-        __syncwarp();
     }
     __syncthreads();
     for (int i = threadIdx.x; i < n; i += CLU_THREADS) {

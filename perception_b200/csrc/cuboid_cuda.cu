@@ -125,6 +125,8 @@ int dalloc(cuboid_handle* h, T** p, size_t n) {
 int validate_params(const cuboid_params* p) {
     if (!(p->leaf > 0.f) || p->sac_max_iter < 0 || p->n_guess < 1 || p->icp_max_iter < 1) return CUBOID_E_INVALID;
     if (!(p->sac_prob > 0.0 && p->sac_prob < 1.0)) return CUBOID_E_INVALID;
+    // cluster.cuh: the fine-cell argument needs |coordinate / (0.52 tol)| < 1e6
+    if (p->use_cluster && !(p->cluster_tol >= 1e-4 && p->cluster_tol <= 1e3)) return CUBOID_E_INVALID;
     // icp.cpp:175 leaves setMaxCorrespondenceDistance commented out; a distance gate that can actually reject is not built
     if (!(p->icp_max_corr_dist * p->icp_max_corr_dist >= 3.0e38)) return CUBOID_E_UNSUPPORTED;
     return CUBOID_OK;
@@ -334,7 +336,7 @@ int run_chunk(cuboid_handle* h, const ChunkIn& in, int nf, cuboid_frame_result* 
         c.remain = b_remain; c.parent = b_parent; c.csize = b_csize; c.crank = b_crank; c.idx_sorted = b_idx_sorted;
         c.offsets = b_offsets; c.roots = b_roots; c.cell_start = h->d_cell_head + (size_t)f0 * (2 * h->M + 2); c.cell_pts = h->d_cell_pts + oM; c.res = d_res; c.P = h->P; c.M = h->M; c.KC = h->KC;
         c.r2 = (float)(p.cluster_tol * p.cluster_tol);
-        c.inv_cell = (float)(1.0 / (1.001 * (p.cluster_tol > 0 ? p.cluster_tol : 1.0))); c.min_size = p.cluster_min; c.max_size = p.cluster_max;
+        c.inv_cell = (float)(1.0 / (0.52 * (p.cluster_tol > 0 ? p.cluster_tol : 1.0))); c.min_size = p.cluster_min; c.max_size = p.cluster_max;
         c.use_cluster = force_cluster ? 1 : p.use_cluster;
         k_cluster<<<nf, CLU_THREADS, CLU_DYN_SMEM, st>>>(c);
         ++h->launches;

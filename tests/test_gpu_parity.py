@@ -139,6 +139,41 @@ def test_cluster_sets_equal(cc, stage_data):
     assert list(go) == [0]
 
 
+@pytest.mark.parametrize("n,box,cmin", [(1800, 0.28, 4), (10000, 0.5, 4), (30000, 0.72, 8)])   # the three memory tiers of k_cluster
+def test_cluster_components_at_the_percolation_threshold(n, box, cmin):
+    """Uniform random clouds with ~2.7 neighbours per point: components hinge on single borderline edges, cells
+    are sparsely filled and hash buckets mix cells -- the fine-cell shortcut must still give the oracle's components."""
+    from perception_b200.params import default_params
+    p = default_params("cuboid")
+    p.cluster_min, p.cluster_max = cmin, 25000
+    h = api.CuboidCuda(p, device=0, max_points=32768, max_batch=1)
+    try:
+        for seed in range(3):
+            rng = np.random.default_rng(100 + seed)
+            pts = np.ones((n, 4), np.float32)
+            pts[:, :3] = rng.uniform(-box / 2, box / 2, (n, 3))
+            oi, oo = O.cluster(pts, p.cluster_tol, cmin, 25000)
+            gi, go = h.cluster(pts)
+            assert 20 < len(oo) <= 1024 and np.array_equal(go, oo) and np.array_equal(gi, oi)
+        # lattices whose spacing is exactly / just under / just over the tolerance (strict '<' on the float distance)
+        p.cluster_min = 1
+        h.set_params(p)
+        for spacing, n_expected in ((np.float32(0.02), None), (np.float32(0.019999), 1), (np.float32(0.020001), 1000)):
+            g = np.arange(10, dtype=np.float32) * spacing
+            pts = np.ones((1000, 4), np.float32)
+            pts[:, :3] = np.stack(np.meshgrid(g, g, g, indexing="ij"), -1).reshape(-1, 3) - np.float32(0.11)
+            oi, oo = O.cluster(pts, p.cluster_tol, 1, 25000)
+            gi, go = h.cluster(pts)
+            assert np.array_equal(go, oo) and np.array_equal(gi, oi)
+            assert n_expected is None or len(oo) - 1 == n_expected
+    finally:
+        h.close()
+    bad = default_params("cuboid")
+    bad.cluster_tol = 1e-6
+    with pytest.raises(api.CuboidError):
+        api.CuboidCuda(bad, device=0, max_points=1024, max_batch=1)
+
+
 def test_icp_per_iteration_correspondences_bit_exact(cc, stage_data, tmpl30):
     src = stage_data["remain"][stage_data["cidx"]]
     o = O.icp(src, tmpl30, trace_iters=128)

@@ -70,7 +70,7 @@ struct CluShared {
     int s_w[CLU_THREADS / 32 + 1];
     int s_cur[1024];
     unsigned long long s_h[CLU_THREADS / 32];
-    int s_nrep;
+    int s_nrep, s_next;
 };
 template <int MODE>
 __device__ __forceinline__ void cluster_body(const CluArgs& a, CluShared& cs) {
@@ -155,7 +155,7 @@ __device__ __forceinline__ void cluster_body(const CluArgs& a, CluShared& cs) {
     // point is united with the first point of its cell in bucket order without a distance test; that first point
     // is the cell's representative. One thread per bucketed position.
     int* reps = idx_sorted;     // scratch until the final scatter writes the member lists
-    if (threadIdx.x == 0) cs.s_nrep = 0;
+    if (threadIdx.x == 0) { cs.s_nrep = 0; cs.s_next = 0; }
     __syncthreads();
     const bool edges = a.r2 > 0.f;
     for (int pos = threadIdx.x; edges && pos < n; pos += CLU_THREADS) {
@@ -177,8 +177,14 @@ __device__ __forceinline__ void cluster_body(const CluArgs& a, CluShared& cs) {
     // is in the upper half of the 5x5x5 neighbourhood (62 offsets, probed by the lanes in two rounds). For every
     // non-empty neighbour not already under the same root the lanes test point pairs with the exact float distance
     // until the first one within tol; that single edge joins the two cells.
+    // Representatives are claimed dynamically (cells differ a lot in cost); the edges found in a round are applied
+    // together afterwards, one per lane, instead of one at a time while the other lanes wait.
     const int nrep = cs.s_nrep;
-    for (int r = wid; r < nrep; r += CLU_THREADS / 32) {
+    while (true) {
+        int r = 0;
+        if (lane == 0) r = atomicAdd(&cs.s_next, 1);
+        r = __shfl_sync(FULL_MASK, r, 0);
+        if (r >= nrep) break;
         const float4 pa0 = cpts[reps[r]];
         const int cx = (int)floorf(pa0.x * inv_cell), cy = (int)floorf(pa0.y * inv_cell), cz = (int)floorf(pa0.z * inv_cell);
         const unsigned int bA = cell_hash(cx, cy, cz) & hmask;
@@ -186,6 +192,7 @@ __device__ __forceinline__ void cluster_body(const CluArgs& a, CluShared& cs) {
         const int ia0 = __float_as_int(pa0.w);
         for (int round = 0; round < 2; ++round) {
             const int k = round * 32 + lane;
+            const int rootA = uf_find(parent, ia0);
             int sB = 0, lenB = 0;
             if (k < 62) {
                 const int code = k + 63;
@@ -196,43 +203,55 @@ __device__ __forceinline__ void cluster_body(const CluArgs& a, CluShared& cs) {
                 if (lenB > 0) {     // cheap skip when the run starts with a point of the target cell that already shares A's root
                     const float4 pb0 = cpts[sB];
                     if ((int)floorf(pb0.x * inv_cell) == tx && (int)floorf(pb0.y * inv_cell) == ty && (int)floorf(pb0.z * inv_cell) == tz &&
-                        uf_find(parent, __float_as_int(pb0.w)) == uf_find(parent, ia0))
+                        uf_find(parent, __float_as_int(pb0.w)) == rootA)
                         lenB = 0;
                 }
             }
             unsigned int todo = __ballot_sync(FULL_MASK, lenB > 0);
+            int ua = -1, ub = -1;       // the edge found for this lane's neighbour
             while (todo) {
                 const int src = __ffs(todo) - 1;
                 todo &= todo - 1;
                 const int s2 = __shfl_sync(FULL_MASK, sB, src), l2 = __shfl_sync(FULL_MASK, lenB, src);
                 const int code = round * 32 + src + 63;
                 const int tx = cx + code % 5 - 2, ty = cy + (code / 5) % 5 - 2, tz = cz + code / 25 - 2;
-                const long long total = (long long)lenA * l2;
-                for (long long t0 = 0; t0 < total; t0 += 32) {
-                    const long long t = t0 + lane;
-                    bool hit = false;
-                    int ia = 0, ib = 0;
-                    if (t < total) {
-                        int qa, qb;
-                        if (total < (1ll << 31)) { qa = (int)t / l2; qb = (int)t - qa * l2; }
-                        else { qa = (int)(t / l2); qb = (int)(t - (long long)qa * l2); }
-                        const float4 pa = cpts[sA + qa], pb = cpts[s2 + qb];
-                        const float ddx = pa.x - pb.x, ddy = pa.y - pb.y, ddz = pa.z - pb.z;
-                        const float d2 = ((ddx * ddx) + ddy * ddy) + ddz * ddz;
-                        if (d2 < a.r2 &&        // buckets can hold foreign cells: both points must be in the cells of this pair
-                            (int)floorf(pa.x * inv_cell) == cx && (int)floorf(pa.y * inv_cell) == cy && (int)floorf(pa.z * inv_cell) == cz &&
-                            (int)floorf(pb.x * inv_cell) == tx && (int)floorf(pb.y * inv_cell) == ty && (int)floorf(pb.z * inv_cell) == tz) {
-                            hit = true; ia = __float_as_int(pa.w); ib = __float_as_int(pb.w);
+                // pairs (qa, qb) of run A x run B: the lanes form rows of width 2^sh >= l2 (no division); a run of
+                // more than 32 points is swept 32 at a time for every point of A
+                const int sh = l2 <= 1 ? 0 : 32 - __clz(l2 - 1);
+                const bool wide = sh > 5;
+                const int rows = wide ? 1 : 32 >> sh;
+                const int row = wide ? 0 : lane >> sh, col = wide ? lane : lane & ((1 << sh) - 1);
+                bool found = false;
+                for (int qa0 = 0; qa0 < lenA && !found; qa0 += rows) {
+                    const int qa = qa0 + row;
+                    for (int qb0 = 0; qb0 < l2; qb0 += 32) {
+                        const int qb = qb0 + col;
+                        bool hit = false;
+                        int ia = 0, ib = 0;
+                        if (qa < lenA && qb < l2) {
+                            const float4 pa = cpts[sA + qa], pb = cpts[s2 + qb];
+                            const float ddx = pa.x - pb.x, ddy = pa.y - pb.y, ddz = pa.z - pb.z;
+                            const float d2 = ((ddx * ddx) + ddy * ddy) + ddz * ddz;
+                            if (d2 < a.r2 &&        // buckets can hold foreign cells: both points must be in the cells of this pair
+                                (int)floorf(pa.x * inv_cell) == cx && (int)floorf(pa.y * inv_cell) == cy && (int)floorf(pa.z * inv_cell) == cz &&
+                                (int)floorf(pb.x * inv_cell) == tx && (int)floorf(pb.y * inv_cell) == ty && (int)floorf(pb.z * inv_cell) == tz) {
+                                hit = true; ia = __float_as_int(pa.w); ib = __float_as_int(pb.w);
+                            }
                         }
-                    }
-                    const unsigned int hm = __ballot_sync(FULL_MASK, hit);
-                    if (hm) {
-                        if (lane == __ffs(hm) - 1) uf_unite(parent, ia, ib);
-                        break;
+                        const unsigned int hm = __ballot_sync(FULL_MASK, hit);
+                        if (hm) {
+                            const int hl = __ffs(hm) - 1;
+                            const int ja = __shfl_sync(FULL_MASK, ia, hl), jb = __shfl_sync(FULL_MASK, ib, hl);
+                            if (lane == src) { ua = ja; ub = jb; }
+                            found = true;
+                            break;
+                        }
+                        if (!wide) break;   // one sweep covers the whole run
                     }
                 }
-                __syncwarp();
             }
+            if (ua >= 0) uf_unite(parent, ua, ub);
+            __syncwarp();
         }
     }
     __syncthreads();

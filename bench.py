@@ -51,15 +51,41 @@ class ClockSampler:
 
     def __init__(self, gpu_index):
         self.gpu, self.rows, self.proc = gpu_index, [], None
+        self.nvml, self.samples, self.stop_flag, self.max_mhz = None, [], False, None
 
     def start(self):
+        """NVML polled every 5 ms from a thread (a 0.2 s timed region still gets dozens of samples); nvidia-smi -lms as fallback."""
+        try:
+            import pynvml
+            pynvml.nvmlInit()
+            vis = os.environ.get("CUDA_VISIBLE_DEVICES")
+            phys = int(vis.split(",")[self.gpu]) if vis and all(x.strip().isdigit() for x in vis.split(",")) else self.gpu
+            self.dev = pynvml.nvmlDeviceGetHandleByIndex(phys)
+            self.max_mhz = float(pynvml.nvmlDeviceGetMaxClockInfo(self.dev, pynvml.NVML_CLOCK_SM))
+            self.nvml = pynvml
+            self.thr = threading.Thread(target=self._poll, daemon=True)
+            self.thr.start()
+            return
+        except Exception:
+            self.nvml = None
         try:
             self.proc = subprocess.Popen(["nvidia-smi", "-i", str(self.gpu), "--query-gpu=" + self.Q, "--format=csv,noheader,nounits",
-                                          "-lms", "200"], stdout=subprocess.PIPE, stderr=subprocess.DEVNULL, text=True)
+                                          "-lms", "50"], stdout=subprocess.PIPE, stderr=subprocess.DEVNULL, text=True)
             self.thr = threading.Thread(target=self._read, daemon=True)
             self.thr.start()
         except Exception:
             self.proc = None
+
+    def _poll(self):
+        nv = self.nvml
+        get_reasons = getattr(nv, "nvmlDeviceGetCurrentClocksEventReasons", None) or nv.nvmlDeviceGetCurrentClocksThrottleReasons
+        while not self.stop_flag:
+            try:
+                self.samples.append((time.perf_counter(), float(nv.nvmlDeviceGetClockInfo(self.dev, nv.NVML_CLOCK_SM)),
+                                     int(get_reasons(self.dev))))
+            except Exception:
+                pass
+            time.sleep(0.005)
 
     def _read(self):
         for line in self.proc.stdout:
@@ -68,6 +94,14 @@ class ClockSampler:
     def stop(self, t0=None, t1=None):
         """Summary of the samples that arrived in [t0, t1] (the timed region); the sampler is started before the warm-up so
         that nvidia-smi is already streaming when the region begins."""
+        if self.nvml:
+            self.stop_flag = True
+            self.thr.join(timeout=1)
+            bits = {"hw_slowdown": 0x8, "hw_thermal_slowdown": 0x40, "sw_thermal_slowdown": 0x20, "sw_power_cap": 0x4}
+            sel = [(mhz, rs) for (ts, mhz, rs) in self.samples if (t0 is None or ts >= t0) and (t1 is None or ts <= t1)]
+            reasons = sorted(nm for nm, bit in bits.items() if any(rs & bit for _, rs in sel))
+            return {"sm_mhz": float(np.median([m for m, _ in sel])) if sel else None, "sm_max_mhz": self.max_mhz,
+                    "reasons": reasons, "samples": len(sel), "source": "nvml, 5 ms poll"}
         if not self.proc:
             return {"sm_mhz": None, "sm_max_mhz": None, "reasons": ["nvidia-smi unavailable"]}
         self.proc.terminate()
@@ -205,7 +239,7 @@ def main():
     ap.add_argument("--chunk", type=int, default=1024, help="frames resident per chunk (max_batch)")
     ap.add_argument("--cpu-sample", type=int, default=64, help="frames of the CPU baseline sample")
     ap.add_argument("--no-cpu", action="store_true")
-    ap.add_argument("--e2e-handles", type=int, default=2,
+    ap.add_argument("--e2e-handles", type=int, default=3,
                     help="library handles (one host thread each) the end-to-end loop spreads its steps over; 1 = strictly serial calls")
     ap.add_argument("--workload", default="full", choices=sorted(WORKLOADS))
     args = ap.parse_args()
@@ -304,8 +338,12 @@ def main():
                 hx.set_guesses(rots, mode=1)
             hx.set_option(api.OPT_STAGES, stages)
             hx.set_option(api.OPT_TAPS, 0)
-            hx.process_batch(host)                      # warm-up of the extra handle
             handles.append(hx)
+        pipe = int(os.environ.get("CUBOID_E2E_PIPELINE", "0"))
+        for hx in handles:                              # handles overlap each other: chunk-wide launches inside each
+            hx.set_option(api.OPT_PIPELINE, pipe)
+        for hx in handles[1:]:
+            hx.process_batch(host)                      # warm-up of the extra handles
         out = [None] * args.steps
 
         def drive(k):
@@ -324,6 +362,7 @@ def main():
         same_all = all(bytes(a) == bytes(b) for o in out for a, b in zip(o, res_e2e))
         for hx in handles[1:]:
             hx.close()
+        cc.set_option(api.OPT_PIPELINE, 1)
         if not same_all:
             raise SystemExit("bench.py: concurrent handles returned different results")
 
@@ -376,7 +415,11 @@ def main():
                     "d2h_bytes_per_step": F * C.sizeof(FrameResult), "handles_per_gpu": n_handles,
                     "serial_calls_value": total_frames * args.steps / e2e_serial_s,
                     "note": "cuboid_process_batch on pinned host depth, results to host; value = steps dealt round-robin over "
-                            "%d handle(s), one host thread each; serial_calls_value = one handle, one call after the other" % n_handles},
+                            "%d handle(s), one host thread each (CUBOID_OPT_PIPELINE=0: chunk-wide launches inside a handle, the "
+                            "handles overlap each other's copies); serial_calls_value = one handle with its internal sub-chunk "
+                            "pipeline, one call after the other. `value` times ONE handle with its stages back to back on one "
+                            "stream, so the overlapped multi-handle figure can come out slightly above it (ICP tails of one "
+                            "batch are filled by the next batch's front end)" % n_handles},
             "gpu_launches": int(launches),
             # achieved = ALGORITHMIC flops (8*S*T per nearest-neighbour pass, the brute-force figure) / CUDA-event time.
             # The kernel returns brute force's exact answer but proves most pairs irrelevant with an exact AABB bound, so this

@@ -247,8 +247,13 @@ int cuboid_stage_ms(cuboid_handle* h, float ms_out[5]);
  *          CUBOID_OPT_STAGES (default 15; stage bits cuboid_process_batch / cuboid_process_cloud run, as in
  *          cuboid_process_batch_device: e.g. 3 = ground-plane segmentation only),
  *          CUBOID_OPT_FRONTEND (default 1: stages 1a+1b run as ONE kernel, one thread-block cluster per frame;
- *          0 = the unfused kernels, kept as the byte-for-byte cross-check of the fused one) */
-enum { CUBOID_OPT_ICP_CULL = 1, CUBOID_OPT_TAPS = 2, CUBOID_OPT_STAGES = 3, CUBOID_OPT_FRONTEND = 4 };
+ *          0 = the unfused kernels, kept as the byte-for-byte cross-check of the fused one),
+ *          CUBOID_OPT_PIPELINE (default 1: inside one cuboid_process_batch call every sub-chunk of 256 frames runs all
+ *          its stages on its own stream as soon as its depth copy lands -- best for ONE handle called in a loop;
+ *          0 = only the front end follows the copies sub-chunk by sub-chunk and plane / clusters / ICP are launched
+ *          once over the whole chunk -- best when several handles, one host thread each, share the GPU and overlap
+ *          each other's copies; same results either way) */
+enum { CUBOID_OPT_ICP_CULL = 1, CUBOID_OPT_TAPS = 2, CUBOID_OPT_STAGES = 3, CUBOID_OPT_FRONTEND = 4, CUBOID_OPT_PIPELINE = 5 };
 int cuboid_set_option(cuboid_handle* h, int option, int value);
 /* last batch: out[0] = source-template pairs the ICP kernel actually evaluated, out[1] = pairs of the
  * brute-force equivalent (S*T per nearest-neighbour pass). Roofline accounting for the culled kernel. */

@@ -37,7 +37,7 @@ ABI_SYMBOLS = [
     "cuboid_stage_ms", "cuboid_measure_fp32_peak", "cuboid_set_option", "cuboid_icp_work",
     "cuboid_bbox_filter", "cuboid_set_bbox_filter", "cuboid_surface_normals", "cuboid_surface_pose", "cuboid_select_object",
 ]
-OPT_ICP_CULL, OPT_TAPS, OPT_STAGES, OPT_FRONTEND = 1, 2, 3, 4
+OPT_ICP_CULL, OPT_TAPS, OPT_STAGES, OPT_FRONTEND, OPT_PIPELINE = 1, 2, 3, 4, 5
 
 
 class SurfaceResult(C.Structure):

@@ -40,7 +40,7 @@ struct cuboid_handle {
     cudaStream_t stream = nullptr;
     cudaStream_t copy_stream = nullptr;   // host->device depth copies of chunk k+1 overlap the kernels of chunk k
     std::vector<cudaEvent_t> ev_pool;     // stage-boundary events of every sub-chunk (timing) + copy events
-    int sub_batch = 128;                  // frames per host->device copy / pre-ICP launch group inside a resident chunk
+    int sub_batch = 256;                  // frames per host->device copy / pre-ICP launch group inside a resident chunk
     cudaEvent_t ev[6] = {};
     // chunk buffers
     uint16_t* d_depth = nullptr;
@@ -1406,6 +1406,7 @@ int cuboid_set_option(cuboid_handle* h, int option, int value) {
         case CUBOID_OPT_ICP_CULL: h->icp_cull = value ? 1 : 0; return CUBOID_OK;
         case CUBOID_OPT_TAPS: h->taps = value ? 1 : 0; return CUBOID_OK;
         case CUBOID_OPT_FRONTEND: h->frontend = value ? 1 : 0; return CUBOID_OK;
+        case CUBOID_OPT_PIPELINE: h->pipeline = value ? 1 : 0; return CUBOID_OK;
         case CUBOID_OPT_STAGES:
             if (value < 1 || value > 15) return CUBOID_E_INVALID;
             h->stage_mask = (value & 8) ? 15 : (value & 4) ? 7 : (value & 2) ? 3 : 1;

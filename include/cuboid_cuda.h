@@ -42,7 +42,9 @@ enum {
 enum {
     CUBOID_W_VOXEL_OVERFLOW = 1, /* dx*dy*dz > INT32_MAX: PCL warns and carries on; so do we */
     CUBOID_W_RNG_EXHAUSTED = 2,  /* RANSAC sampler ran past the precomputed mt19937 table */
-    CUBOID_W_CLUSTERS_TRUNCATED = 4
+    CUBOID_W_CLUSTERS_TRUNCATED = 4,
+    CUBOID_W_CLUSTER_RANGE = 8   /* a non-plane point lies more than 5e5 clustering cells (2.6e5 * cluster_tol) from the origin:
+                                    k_cluster's cell argument is not guaranteed for this frame */
 };
 
 /* ICP convergence states = pcl::registration::DefaultConvergenceCriteria */

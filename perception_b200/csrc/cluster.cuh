@@ -8,7 +8,7 @@
 // two points within tol are at most 2 cells apart per axis (1 / 0.52 = 1.92 < 2), so cell pairs of the
 // 5x5x5 neighbourhood are examined, each only until ONE pair of points within tol is found (exact float test)
 // or not at all when both cells already hang under the same root. Both margins (19 % and 4 %) dwarf the float
-// rounding of the cell coordinate for |coordinate / cell| < 1e6. Edges feed a lock-free union-find (larger
+// rounding of the cell coordinate for |coordinate / cell| < 5e5, where it is below 0.03 cells (beyond that the frame is flagged CUBOID_W_CLUSTER_RANGE). Edges feed a lock-free union-find (larger
 // root hooks under smaller root, so a component's root is its smallest member). Then the size filter, the
 // canonical ordering (size descending, ties by smallest member) and a stable scatter of the member indices
 // (ascending inside each cluster).
@@ -124,11 +124,14 @@ __device__ __forceinline__ void cluster_body(const CluArgs& a, CluShared& cs) {
     for (int i = threadIdx.x; i <= hs; i += CLU_THREADS) cend[i] = 0;
     __syncthreads();
     const float inv_cell = a.inv_cell;
+    bool far = false;
     for (int i = threadIdx.x; i < n; i += CLU_THREADS) {
         const float4 p = pts[i];
         const int cx = (int)floorf(p.x * inv_cell), cy = (int)floorf(p.y * inv_cell), cz = (int)floorf(p.z * inv_cell);
         atomicAdd(&cend[cell_hash(cx, cy, cz) & hmask], 1);
+        far |= !(fmaxf(fmaxf(fabsf(p.x), fabsf(p.y)), fabsf(p.z)) * inv_cell <= 5.0e5f);   // also catches NaN / inf
     }
+    if (far) atomicOr(&R.status, CUBOID_W_CLUSTER_RANGE);   // the cell coordinate's rounding is no longer small against the margins
     __syncthreads();
     {   // exclusive scan of the hs bucket counts (running carry over 1024-wide slices): cend[b] = start of bucket b
         int carry = 0;

@@ -125,7 +125,7 @@ int dalloc(cuboid_handle* h, T** p, size_t n) {
 int validate_params(const cuboid_params* p) {
     if (!(p->leaf > 0.f) || p->sac_max_iter < 0 || p->n_guess < 1 || p->icp_max_iter < 1) return CUBOID_E_INVALID;
     if (!(p->sac_prob > 0.0 && p->sac_prob < 1.0)) return CUBOID_E_INVALID;
-    // cluster.cuh: the fine-cell argument needs |coordinate / (0.52 tol)| < 1e6
+    // cluster.cuh: the fine-cell argument needs |coordinate / (0.52 tol)| < 5e5 (26 m at the smallest tolerance)
     if (p->use_cluster && !(p->cluster_tol >= 1e-4 && p->cluster_tol <= 1e3)) return CUBOID_E_INVALID;
     // icp.cpp:175 leaves setMaxCorrespondenceDistance commented out; a distance gate that can actually reject is not built
     if (!(p->icp_max_corr_dist * p->icp_max_corr_dist >= 3.0e38)) return CUBOID_E_UNSUPPORTED;

@@ -17,7 +17,15 @@ __global__ void k(int mode, unsigned int* out, long long* cyc, int iters, int sp
 #pragma unroll
             for (int b = 0; b < 8; ++b) { const unsigned int bal = __ballot_sync(0xffffffffu, (d >> b) & 1u); peers &= ((d >> b) & 1u) ? bal : ~bal; }
         } else if (mode == 2) { atomicAdd(&cnt[w & 15][d & 255], 1u); peers = d; }
-        else { atomicAdd(&cnt[0][d & 255], 1u); peers = d; }
+        else if (mode == 3) { atomicAdd(&cnt[0][d & 255], 1u); peers = d; }
+        else {      // match through a warp-private mask table: OR the lane bit in, read the mask back, leader clears it
+            atomicOr(&cnt[w & 15][d & 255], 1u << lane);
+            __syncwarp();
+            peers = ((volatile unsigned int*)cnt[w & 15])[d & 255];
+            __syncwarp();
+            if (lane == __ffs(peers) - 1) cnt[w & 15][d & 255] = 0u;
+            __syncwarp();
+        }
         acc += __popc(peers);
         d = (d + (acc & 1) + 1) % spread;
     }
@@ -28,9 +36,9 @@ __global__ void k(int mode, unsigned int* out, long long* cyc, int iters, int sp
 int main() {
     unsigned int* out; long long* cyc;
     cudaMalloc(&out, 4 * 148 * 2 * 512); cudaMalloc(&cyc, 8 * 148 * 2 * 16);
-    const char* names[] = {"match_any", "8 ballots", "atoms warp-private", "atoms shared row"};
-    for (int spread : {4, 32, 256})
-        for (int mode = 0; mode < 4; ++mode) {
+    const char* names[] = {"match_any", "8 ballots", "atoms warp-private", "atoms shared row", "atomicOr match"};
+    for (int spread : {1, 4, 32, 256})
+        for (int mode = 0; mode < 5; ++mode) {
             const int iters = 2000;
             k<<<296, 512>>>(mode, out, cyc, iters, spread);
             cudaDeviceSynchronize();

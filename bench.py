@@ -124,6 +124,15 @@ class ClockSampler:
                 "reasons": sorted(reasons), "samples": len(sm)}
 
 
+def _without_taps(r):
+    """Bytes of a frame result with the parity-tap hashes that CUBOID_OPT_TAPS = 0 leaves at zero blanked."""
+    c = type(r).from_buffer_copy(bytes(r))
+    c.points_hash = c.voxel_key_hash = c.voxel_hash = 0
+    for k in range(len(c.cluster)):
+        c.cluster[k].corr_hash = 0
+    return bytes(c)
+
+
 def make_frames(n, seed0, kind="bench"):
     from perception_b200 import synth
     return synth.depth_batch(kind, range(seed0, seed0 + n))
@@ -285,7 +294,7 @@ def main():
     if rots is not None:
         cc.set_guesses(rots, mode=1)
     stages = wl["stages"]
-    cc.set_option(api.OPT_TAPS, 0)   # the per-point key / per-voxel count arrays are parity taps (tests fetch them); hashes stay on
+    cc.set_option(api.OPT_TAPS, 0)   # no parity taps in the timed runs (key / count arrays, point / voxel / correspondence hashes); see cpu_baseline
     peak_unfused, peak_ffma = cc.measure_fp32_peak()
 
     def barrier():
@@ -465,8 +474,15 @@ def main():
             c0 = time.perf_counter()
             cpu_res = [O.process_frame(op, frames[i], otm, guesses=rots) for i in range(ns)]
             cdt = time.perf_counter() - c0
-            same = all(cpu_res[i].cluster[0].corr_hash == res[i].cluster[0].corr_hash and cpu_res[i].inlier_hash == res[i].inlier_hash
-                       for i in range(ns))
+            # The timed runs carry no parity taps (CUBOID_OPT_TAPS = 0 leaves the point / voxel / correspondence hashes at 0). The
+            # sample is run once more with the taps on: its hashes must equal the oracle's (every point, voxel, inlier and every
+            # ICP iteration's correspondences) and everything else must equal the timed run's results byte for byte.
+            cc.set_option(api.OPT_TAPS, 1)
+            chk = cc.process_batch(np.ascontiguousarray(frames[:ns]))
+            cc.set_option(api.OPT_TAPS, 0)
+            same = all(cpu_res[i].cluster[0].corr_hash == chk[i].cluster[0].corr_hash and cpu_res[i].inlier_hash == chk[i].inlier_hash
+                       and cpu_res[i].points_hash == chk[i].points_hash and cpu_res[i].voxel_hash == chk[i].voxel_hash
+                       and _without_taps(chk[i]) == _without_taps(res[i]) for i in range(ns))
             line["cpu_baseline"] = {"value": ns / cdt, "unit": "frames/s", "cores": 1, "kind": "port",
                                     "sample": "first %d frames of the same batch, single thread (the reference node is one ros::spin thread)" % ns,
                                     "gpu_matches_oracle_on_sample": bool(same)}

@@ -245,7 +245,7 @@ int64_t cuboid_launch_count(cuboid_handle* h);
 int cuboid_stage_ms(cuboid_handle* h, float ms_out[5]);
 /* options: CUBOID_OPT_ICP_CULL (default 1; 0 = plain brute force over every template chunk, same results),
  *          CUBOID_OPT_TAPS (default 1; 0 = do not keep the per-point voxel key / per-voxel count arrays and leave the
- *          front-end parity hashes points_hash / voxel_key_hash / voxel_hash at 0; every other output is unchanged),
+ *          parity hashes points_hash / voxel_key_hash / voxel_hash / corr_hash at 0; every other output is unchanged),
  *          CUBOID_OPT_STAGES (default 15; stage bits cuboid_process_batch / cuboid_process_cloud run, as in
  *          cuboid_process_batch_device: e.g. 3 = ground-plane segmentation only),
  *          CUBOID_OPT_FRONTEND (default 1: stages 1a+1b run as ONE kernel, one thread-block cluster per frame;

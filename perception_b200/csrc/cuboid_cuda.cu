@@ -363,6 +363,7 @@ int run_chunk(cuboid_handle* h, const ChunkIn& in, int nf, cuboid_frame_result* 
         if (box_bytes > (size_t)h->icp_smem_budget) return CUBOID_E_CAPACITY;
         a.resident = (box_bytes + (size_t)a.Tpad * 12 <= (size_t)h->icp_smem_budget) ? 1 : 0;
         a.cull = h->icp_cull;
+        a.hashes = h->taps ? 1 : 0;
         a.work = h->d_work;
         a.corr_trace = trace_corr; a.T_trace = trace_T; a.cap_trace = cap_trace;
         size_t dyn = box_bytes + (a.resident ? (size_t)a.Tpad * 12 : 0);

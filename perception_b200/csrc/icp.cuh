@@ -71,6 +71,7 @@ struct IcpArgs {
     int crew;                  // worker CTAs of k_icp
     int nsub;                  // sub-workers per CTA (1 or 2)
     int init_smem;             // dynamic shared memory of k_icp_init (Morton sort window)
+    int hashes;                // 1: accumulate corr_hash (parity tap); 0: leave it 0
 };
 
 constexpr int ICP_THREADS = 512;   // first 256 = the canonical reduction lanes; two CTAs (two ICP problems) share an SM
@@ -699,9 +700,11 @@ __device__ __forceinline__ bool icp_slice(const IcpArgs& a, IcpShared& sh, const
                 q6[0] = q6[0] + p.x; q6[1] = q6[1] + p.y; q6[2] = q6[2] + p.z;
                 q6[3] = q6[3] + t.x; q6[4] = q6[4] + t.y; q6[5] = q6[5] + t.z;
                 qd[0] = qd[0] + (double)__ldcg(cd + i);
-                const int j = a.tmpl_orig[pos];      // original template index
-                chash += splitmix64((((unsigned long long)it * (unsigned long long)S + (unsigned long long)i) << 32) | (unsigned int)j);
-                if (trace && it < a.cap_trace) a.corr_trace[(size_t)it * S + i] = j;
+                if (a.hashes || trace) {             // parity taps: the correspondence hash and the per-iteration trace
+                    const int j = a.tmpl_orig[pos];  // original template index
+                    chash += splitmix64((((unsigned long long)it * (unsigned long long)S + (unsigned long long)i) << 32) | (unsigned int)j);
+                    if (trace && it < a.cap_trace) a.corr_trace[(size_t)it * S + i] = j;
+                }
             }
             canon_sub_partial<float, 6, SUB>(q6, sh.part_f, tid, set);
             canon_sub_partial<double, 1, SUB>(qd, sh.part_d, tid, set);

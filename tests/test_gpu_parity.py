@@ -541,3 +541,23 @@ def test_execution_knobs_do_not_change_results(tmpl30, params, knob, values, mon
             out.append([bytes(r) for r in h.process_batch(depth)])
     for o in out[1:]:
         assert o == out[0]
+
+
+def test_taps_off_only_blanks_the_parity_hashes(tmpl30, params):
+    """CUBOID_OPT_TAPS = 0 (what bench.py times) drops the parity instrumentation - the point / voxel / correspondence
+    hashes read 0 - and changes no other result byte."""
+    depth = np.concatenate([synth.depth_batch("bench", list(range(300, 312))), np.zeros((1, 480, 640), np.uint16)])
+    with api.CuboidCuda(params, max_points=640 * 480, max_batch=13) as h:
+        h.set_template(0, tmpl30)
+        on = h.process_batch(depth)
+        h.set_option(api.OPT_TAPS, 0)
+        off = h.process_batch(depth)
+    for a, b in zip(on, off):
+        assert b.points_hash == 0 and b.voxel_key_hash == 0 and b.voxel_hash == 0 and b.cluster[0].corr_hash == 0
+        assert b.inlier_hash == a.inlier_hash and b.remain_hash == a.remain_hash and b.cluster_hash == a.cluster_hash
+        c = type(a).from_buffer_copy(bytes(a))
+        c.points_hash = c.voxel_key_hash = c.voxel_hash = 0
+        for k in range(len(c.cluster)):
+            c.cluster[k].corr_hash = 0
+        assert bytes(c) == bytes(b)
+    assert on[0].points_hash != 0 and on[0].cluster[0].corr_hash != 0

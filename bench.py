@@ -133,6 +133,28 @@ def _without_taps(r):
     return bytes(c)
 
 
+def _bind_to_gpu_cpus(gpu_index):
+    """Pin this process (and the host threads it starts later) to the CPUs NVML names as local to its GPU, before the pinned
+    depth buffer is allocated, so that the buffer's pages and the threads feeding the copies sit on the GPU's NUMA node.
+    A no-op on this pool's boxes (one NUMA node: 16 CPUs with 1 GPU, 32 CPUs with 8), where the 8-GPU end-to-end figure is
+    bounded by the host side regardless (~170 GB/s of depth frames out of host memory); it matters on two-socket hosts."""
+    try:
+        import pynvml
+        pynvml.nvmlInit()
+        vis = os.environ.get("CUDA_VISIBLE_DEVICES")
+        phys = int(vis.split(",")[gpu_index]) if vis and all(x.strip().isdigit() for x in vis.split(",")) else gpu_index
+        dev = pynvml.nvmlDeviceGetHandleByIndex(phys)
+        words = pynvml.nvmlDeviceGetCpuAffinity(dev, (os.cpu_count() + 63) // 64)
+        cpus = {64 * w + b for w, m in enumerate(words) for b in range(64) if (int(m) >> b) & 1}
+        cpus &= os.sched_getaffinity(0)
+        if len(cpus) >= 4:
+            os.sched_setaffinity(0, cpus)
+            return "%d cpus local to gpu %d" % (len(cpus), phys)
+        return "unchanged (NVML names %d usable cpus)" % len(cpus)
+    except Exception as e:      # no NVML, a restricted cpuset, ...: run unbound
+        return "unchanged (%s)" % type(e).__name__
+
+
 def make_frames(n, seed0, kind="bench"):
     from perception_b200 import synth
     return synth.depth_batch(kind, range(seed0, seed0 + n))
@@ -273,6 +295,7 @@ def main():
     if not torch.cuda.is_available():
         raise SystemExit("bench.py needs a CUDA device: libcuboid_cuda has no CPU fallback")
     torch.cuda.set_device(local_rank)
+    numa = _bind_to_gpu_cpus(local_rank) if os.environ.get("CUBOID_BENCH_BIND", "1") != "0" else "off"
     if world > 1:
         os.environ.setdefault("MASTER_ADDR", "127.0.0.1")
         dist.init_process_group("nccl", device_id=torch.device("cuda", local_rank))
@@ -430,7 +453,7 @@ def main():
             "config": workload_config(args, F),
             "clocks": clocks,
             "e2e": {"value": total_frames * args.steps / t_e2e, "unit": "frames/s", "h2d_bytes_per_step": F * W * H * 2,
-                    "d2h_bytes_per_step": F * C.sizeof(FrameResult), "handles_per_gpu": n_handles,
+                    "d2h_bytes_per_step": F * C.sizeof(FrameResult), "handles_per_gpu": n_handles, "cpu_binding": numa,
                     "serial_calls_value": total_frames * args.steps / e2e_serial_s,
                     "note": "cuboid_process_batch on pinned host depth, results to host; value = steps dealt round-robin over "
                             "%d handle(s), one host thread each (CUBOID_OPT_PIPELINE=0: chunk-wide launches inside a handle, the "

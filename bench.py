@@ -8,14 +8,16 @@ Contract (driver): python bench.py --gpus N --steps K --warmup W  [--impl refere
   * `value`  : whole-job frames/s with the depth frames already resident in HBM, device time from CUDA events
     recorded on the library's own stream (max over ranks);
   * `e2e`    : the same metric through cuboid_process_batch with PINNED HOST depth buffers: host->device copy of
-    every frame and device->host copy of every frame's result inside the timed region;
+    every frame and device->host copy of every frame's result inside the timed region; steps are dealt round-robin over
+    --e2e-handles library handles (default 3), one host thread each, so that one batch's copies run under another's ICP;
   * `roofline`: the dominant kernel (k_icp, FP32-pipe bound: un-fused FMUL/FADD) — algorithmic
     flops from the per-frame results (8*S*T per nearest-neighbour pass) over its CUDA-event time, against the
     un-fused FP32 peak measured in the same run; `roofline_hbm` is the same for the HBM-bound fused front end
     (k_frontend: unproject + passthrough + voxel grid in one kernel, algorithmic bytes 2*P + 32*N + 16*V per frame)
     against MEASURED_PEAKS.json; its `traffic` is the dram__bytes figure of the committed ncu capture (profiles/);
   * `cpu_baseline`: the CPU oracle (restatement of the PCL path, 1 thread like the reference node) on a bounded
-    sample of the same frames;
+    sample of the same frames; the same sample is re-run on the GPU with the parity taps on (the timed runs carry
+    none) and must match the oracle's hashes, and the timed run's results in every other byte;
   * --impl reference: that CPU restatement on all host cores (the real PCL/ROS reference cannot be built
     offline: DESIGN.md), same metric/config, rank 0 only.
 """

@@ -561,3 +561,33 @@ def test_taps_off_only_blanks_the_parity_hashes(tmpl30, params):
             c.cluster[k].corr_hash = 0
         assert bytes(c) == bytes(b)
     assert on[0].points_hash != 0 and on[0].cluster[0].corr_hash != 0
+
+
+def test_pipeline_option_and_concurrent_handles_return_the_same_bytes(tmpl30, params, monkeypatch):
+    """CUBOID_OPT_PIPELINE only moves launches between streams: a handle gives the same bytes with the sub-chunk pipeline
+    (one handle called in a loop) and with chunk-wide launches (several handles sharing the GPU), also when two handles
+    run at the same time from two host threads, as bench.py's end-to-end arm drives them."""
+    import threading
+    monkeypatch.setenv("CUBOID_SUB_BATCH", "8")
+    depth = np.concatenate([synth.depth_batch("bench", list(range(400, 420))), np.zeros((1, 480, 640), np.uint16)])
+    hs = [api.CuboidCuda(params, max_points=640 * 480, max_batch=21) for _ in range(2)]
+    try:
+        for h in hs:
+            h.set_template(0, tmpl30)
+        ref = [bytes(r) for r in hs[0].process_batch(depth)]                 # pipelined sub-chunks of 8 frames
+        out = [None, None]
+        for h in hs:
+            h.set_option(api.OPT_PIPELINE, 0)
+
+        def drive(k):
+            out[k] = [[bytes(r) for r in hs[k].process_batch(depth)] for _ in range(3)]
+
+        thr = [threading.Thread(target=drive, args=(k,)) for k in range(2)]
+        for t in thr:
+            t.start()
+        for t in thr:
+            t.join()
+        assert all(o == ref for k in range(2) for o in out[k])
+    finally:
+        for h in hs:
+            h.close()

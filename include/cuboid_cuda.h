@@ -260,6 +260,8 @@ int cuboid_set_option(cuboid_handle* h, int option, int value);
 /* last batch: out[0] = source-template pairs the ICP kernel actually evaluated, out[1] = pairs of the
  * brute-force equivalent (S*T per nearest-neighbour pass). Roofline accounting for the culled kernel. */
 int cuboid_icp_work(cuboid_handle* h, uint64_t out[2]);
+/* developer counters of the ICP kernel (all zero unless the library was built with -DCUBOID_ICP_STATS); reset != 0 clears them */
+int cuboid_debug_counters(cuboid_handle* h, uint64_t out[32], int reset);
 /* un-fused FP32 (FMUL+FADD) and FFMA throughput micro-benchmark, lane-ops/s -> TFLOP/s */
 int cuboid_measure_fp32_peak(cuboid_handle* h, double* unfused_tflops, double* ffma_tflops);
 

@@ -35,7 +35,7 @@ ABI_SYMBOLS = [
     "cuboid_pack_fitness_key", "cuboid_unpack_fitness_key", "cuboid_strerror", "cuboid_last_error",
     "cuboid_abi_version", "cuboid_params_size", "cuboid_frame_result_size", "cuboid_launch_count",
     "cuboid_stage_ms", "cuboid_measure_fp32_peak", "cuboid_set_option", "cuboid_icp_work",
-    "cuboid_bbox_filter", "cuboid_set_bbox_filter", "cuboid_surface_normals", "cuboid_surface_pose", "cuboid_select_object",
+    "cuboid_debug_counters", "cuboid_bbox_filter", "cuboid_set_bbox_filter", "cuboid_surface_normals", "cuboid_surface_pose", "cuboid_select_object",
 ]
 OPT_ICP_CULL, OPT_TAPS, OPT_STAGES, OPT_FRONTEND, OPT_PIPELINE = 1, 2, 3, 4, 5
 
@@ -117,6 +117,7 @@ def load():
     L.cuboid_measure_fp32_peak.argtypes = [vp, C.POINTER(C.c_double), C.POINTER(C.c_double)]
     L.cuboid_set_option.argtypes = [vp, i32, i32]
     L.cuboid_icp_work.argtypes = [vp, vp]
+    L.cuboid_debug_counters.argtypes = [vp, vp, i32]
     L.cuboid_bbox_filter.argtypes = [vp, vp, i32, i32, i32, i32, i32, vp, vp, vp, vp, i32, ip]
     L.cuboid_set_bbox_filter.argtypes = [vp, vp, vp, i32]
     L.cuboid_surface_normals.argtypes = [vp, vp, i32, vp, C.c_double, C.c_double, C.POINTER(SurfaceResult)]
@@ -376,6 +377,12 @@ class CuboidCuda:
         w = np.zeros(2, np.uint64)
         self._ck(self.lib.cuboid_icp_work(self._h, _ptr(w)), "cuboid_icp_work")
         return int(w[0]), int(w[1])
+
+    def debug_counters(self, reset=True):
+        """Developer counters of k_icp (zeros unless the library was built with -DCUBOID_ICP_STATS)."""
+        w = np.zeros(32, np.uint64)
+        self._ck(self.lib.cuboid_debug_counters(self._h, _ptr(w), 1 if reset else 0), "cuboid_debug_counters")
+        return [int(x) for x in w]
 
     def measure_fp32_peak(self):
         a, b = C.c_double(0), C.c_double(0)

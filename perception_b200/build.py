@@ -6,7 +6,7 @@ import subprocess
 HERE = os.path.dirname(os.path.abspath(__file__))
 ROOT = os.path.dirname(HERE)
 CSRC = os.path.join(HERE, "csrc")
-CUDA_LIB = os.path.join(HERE, "libcuboid_cuda.so")
+CUDA_LIB = os.environ.get("CUBOID_CUDA_LIB") or os.path.join(HERE, "libcuboid_cuda.so")   # the override is for developer builds (tools/)
 SYNTH_LIB = os.path.join(HERE, "libcuboid_synth.so")
 
 NVCC_FLAGS = [
@@ -40,6 +40,8 @@ def build_cuda(force=False, verbose=False):
                                     "-o", CUDA_LIB, os.path.join(CSRC, "cuboid_cuda.cu")]
     if verbose:
         cmd.insert(1, "-Xptxas=-v")
+    for d in os.environ.get("CUBOID_NVCC_DEFINES", "").split():   # developer builds, e.g. CUBOID_NVCC_DEFINES=-DCUBOID_ICP_STATS
+        cmd.insert(1, d)
     r = subprocess.run(cmd, capture_output=True, text=True)
     if r.returncode != 0:
         raise RuntimeError("nvcc failed:\n" + r.stdout + r.stderr)

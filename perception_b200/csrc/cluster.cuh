@@ -27,10 +27,11 @@ struct CluArgs {
     int* idx_sorted;        // [F][M]
     int* offsets;           // [F][KC+1]
     int* roots;             // [F][KC]
-    int* cell_start;        // [F][2*M+2] hashed grid: end of every bucket in cell_pts
+    int* cell_start;        // [F][cell_stride] hashed grid: end of every bucket in cell_pts (cell_stride = pow2 >= 2*M, + 1)
     float4* cell_pts;       // [F][M]     points grouped by bucket, .w = point index (bits)
     cuboid_frame_result* res;
     int P, M, KC;
+    int cell_stride;
     float r2;
     float inv_cell;         // 1 / (0.52 * tol)
     int min_size, max_size, use_cluster;
@@ -117,7 +118,7 @@ __device__ __forceinline__ void cluster_body(const CluArgs& a, CluShared& cs) {
     // that the points of a cell are (part of) one contiguous run
     // MODE 0 shared layout: parent[4096] | cpts float4[4096] | cend[hs+1 <= 4097]
     float4* cpts = MODE == 0 ? reinterpret_cast<float4*>(s_dyn + CLU_SMEM_ALL) : a.cell_pts + (size_t)f * a.M;
-    int* cend = MODE == 0 ? s_dyn + CLU_SMEM_ALL + 4 * CLU_SMEM_ALL : a.cell_start + (size_t)f * (2 * a.M + 2);
+    int* cend = MODE == 0 ? s_dyn + CLU_SMEM_ALL + 4 * CLU_SMEM_ALL : a.cell_start + (size_t)f * a.cell_stride;
     int hs = 64;
     while (hs < (MODE == 0 ? n : 2 * n)) hs <<= 1;
     const unsigned int hmask = (unsigned int)hs - 1u;

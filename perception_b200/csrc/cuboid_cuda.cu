@@ -36,6 +36,7 @@ struct cuboid_handle {
     cuboid_params p;
     int device = 0;
     int P = 0, B = 0, M = 0, KC = 1024;
+    int cell_stride = 0;                  // ints per frame of d_cell_head: k_cluster's bucket table is a power of two >= 2 * n_remain, plus one
     int tilesP = 0, tilesV = 0;
     cudaStream_t stream = nullptr;
     cudaStream_t copy_stream = nullptr;   // host->device depth copies of chunk k+1 overlap the kernels of chunk k
@@ -56,10 +57,10 @@ struct cuboid_handle {
     int *d_shuffled = nullptr, *d_inl_pre = nullptr, *d_inl = nullptr;
     float4* d_remain = nullptr;
     int *d_parent = nullptr, *d_csize = nullptr, *d_crank = nullptr, *d_idx_sorted = nullptr, *d_offsets = nullptr, *d_roots = nullptr, *d_cell_head = nullptr; float4* d_cell_pts = nullptr;
-    float4* d_cur = nullptr; int* d_corr = nullptr; float* d_cd = nullptr; int* d_order = nullptr; IcpOut* d_icp_out = nullptr;
+    float4* d_cur = nullptr; int* d_corr = nullptr; float* d_cd = nullptr; int* d_order = nullptr; int* d_miss = nullptr; IcpOut* d_icp_out = nullptr;
     IcpState* d_icp_state = nullptr; IcpSlot* d_icp_ring = nullptr; IcpQueue* d_icp_queue = nullptr;   // persistent time-sliced k_icp
-    int icp_slice_iters = 8; int icp_ctas = 0; int icp_outward = 1; int smem_sm = 0; int icp_nsub_force = 0;
-    size_t icp_scratch_elems = 0; size_t icp_out_elems = 0;
+    int icp_slice_iters = 8; int icp_ctas = 0; int icp_outward = 1; int icp_queued = 1; int smem_sm = 0; int icp_nsub_force = 0;
+    size_t icp_scratch_elems = 0; size_t icp_out_elems = 0; size_t icp_queue_frames = 0;
     FrameScratch* d_scr = nullptr;
     unsigned long long *d_desc1 = nullptr, *d_desc2 = nullptr;
     unsigned int* d_ticket = nullptr;
@@ -68,12 +69,18 @@ struct cuboid_handle {
     int* d_triplets = nullptr; int triplets_cap = 0;
     float* d_tmpl[CUBOID_MAX_TEMPLATES] = {}; int* d_tmpl_orig[CUBOID_MAX_TEMPLATES] = {}; int tmpl_n[CUBOID_MAX_TEMPLATES] = {}; int tmpl_pad[CUBOID_MAX_TEMPLATES] = {};
     unsigned short* d_sib[CUBOID_MAX_TEMPLATES] = {}; int sib_max[CUBOID_MAX_TEMPLATES] = {}; int sib_bytes[CUBOID_MAX_TEMPLATES] = {};   // sibling chains (icp.cuh)
+    uint4* d_nnt[CUBOID_MAX_TEMPLATES] = {}; NnTableView nnt[CUBOID_MAX_TEMPLATES] = {};   // nearest-neighbour candidate tables (nn_table.cuh)
+    int icp_table = 1; double nnt_h = 0.001;
+    unsigned short* d_orig16[CUBOID_MAX_TEMPLATES] = {};   // original index of every kd-ordered position as u16 (queued search), NULL when the template has more than 65536 points
     uint4* d_boxes[CUBOID_MAX_TEMPLATES] = {}; int tmpl_nleaf[CUBOID_MAX_TEMPLATES] = {}; int tmpl_nnodes[CUBOID_MAX_TEMPLATES] = {};
     unsigned long long* d_work = nullptr; unsigned long long work_total[2] = {0, 0};
+    unsigned long long* d_stats = nullptr;   // developer counters of k_icp (32 x u64), all zero unless built with -DCUBOID_ICP_STATS
     int icp_cull = 1;
     int stage_mask = 15;
     float* d_guesses = nullptr; int n_guess = 1; int guess_mode = 0; bool have_guesses = false;
-    int* d_trace_corr = nullptr; float* d_trace_T = nullptr; float4* d_aligned = nullptr;
+    // cuboid_icp's per-call device buffers live in the handle and only ever grow: no cudaMalloc / cudaFree on the single-frame path
+    int* d_trace_corr = nullptr; size_t trace_corr_cap = 0; float* d_trace_T = nullptr; size_t trace_T_cap = 0;
+    float4* d_aligned = nullptr; size_t aligned_cap = 0; float* d_call_guesses = nullptr; size_t call_guesses_cap = 0;
     int smem_optin = 0; int icp_smem_budget = 0;
     int last_chunk_base = 0, last_chunk_frames = 0, last_total_frames = 0;
     int taps = 1;
@@ -89,6 +96,8 @@ struct cuboid_handle {
 };
 
 namespace {
+
+constexpr int CUBOID_MAX_SAC_ITER = 1000000;
 
 #define CK(h, call)                                                                                         \
     do {                                                                                                    \
@@ -122,8 +131,25 @@ int dalloc(cuboid_handle* h, T** p, size_t n) {
     return CUBOID_OK;
 }
 
+// grow-only device buffer owned by the handle
+template <typename T>
+int ensure_buf(cuboid_handle* h, T** p, size_t* cap, size_t n) {
+    if (n <= *cap && *p) return CUBOID_OK;
+    if (*p) cudaFree(*p);
+    *p = nullptr; *cap = 0;
+    CKS(h, dalloc(h, p, std::max<size_t>(n, 1)));
+    *cap = std::max<size_t>(n, 1);
+    return CUBOID_OK;
+}
+
 int validate_params(const cuboid_params* p) {
     if (!(p->leaf > 0.f) || p->sac_max_iter < 0 || p->n_guess < 1 || p->icp_max_iter < 1) return CUBOID_E_INVALID;
+    // the unprojection divides by fx, fy: zero / non-finite intrinsics would turn every point into inf / NaN, which the
+    // PassThrough test (written for finite input, like PCL's after its own isfinite check) would let through
+    if (!std::isfinite(p->fx) || !std::isfinite(p->fy) || p->fx == 0.f || p->fy == 0.f || !std::isfinite(p->cx) || !std::isfinite(p->cy) ||
+        !std::isfinite(p->depth_scale) || p->depth_scale == 0.f || !std::isfinite(p->leaf))
+        return CUBOID_E_INVALID;
+    if (p->sac_max_iter > CUBOID_MAX_SAC_ITER || p->n_guess > 65535) return CUBOID_E_INVALID;   // the mt19937 table is 33 ints per iteration
     if (!(p->sac_prob > 0.0 && p->sac_prob < 1.0)) return CUBOID_E_INVALID;
     // cluster.cuh: the fine-cell argument needs |coordinate / (0.52 tol)| < 5e5 (26 m at the smallest tolerance)
     if (p->use_cluster && !(p->cluster_tol >= 1e-4 && p->cluster_tol <= 1e3)) return CUBOID_E_INVALID;
@@ -148,24 +174,33 @@ int upload_rng(cuboid_handle* h) {
 int ensure_icp_scratch(cuboid_handle* h, int frames, int n_guess) {
     const size_t need = (size_t)frames * n_guess * h->M;
     if (need > h->icp_scratch_elems) {
-        if (h->d_cur) { cudaFree(h->d_cur); cudaFree(h->d_corr); cudaFree(h->d_cd); cudaFree(h->d_order); }
-        h->d_cur = nullptr; h->d_corr = nullptr; h->d_cd = nullptr; h->d_order = nullptr; h->icp_scratch_elems = 0;
+        if (h->d_cur) { cudaFree(h->d_cur); cudaFree(h->d_corr); cudaFree(h->d_cd); cudaFree(h->d_order); cudaFree(h->d_miss); }
+        h->d_cur = nullptr; h->d_corr = nullptr; h->d_cd = nullptr; h->d_order = nullptr; h->d_miss = nullptr; h->icp_scratch_elems = 0;
         CKS(h, dalloc(h, &h->d_cur, need));
         CKS(h, dalloc(h, &h->d_corr, need));
         CKS(h, dalloc(h, &h->d_cd, need));
         CKS(h, dalloc(h, &h->d_order, need));
+        CKS(h, dalloc(h, &h->d_miss, need));
         h->icp_scratch_elems = need;
     }
     const size_t need_out = (size_t)frames * CUBOID_MAX_CLUSTERS * n_guess;
     if (need_out > h->icp_out_elems) {
-        if (h->d_icp_out) { cudaFree(h->d_icp_out); cudaFree(h->d_icp_state); cudaFree(h->d_icp_ring); cudaFree(h->d_icp_queue); }
-        h->d_icp_out = nullptr; h->d_icp_state = nullptr; h->d_icp_ring = nullptr; h->d_icp_queue = nullptr; h->icp_out_elems = 0;
+        if (h->d_icp_out) { cudaFree(h->d_icp_out); cudaFree(h->d_icp_state); cudaFree(h->d_icp_ring); }
+        h->d_icp_out = nullptr; h->d_icp_state = nullptr; h->d_icp_ring = nullptr; h->icp_out_elems = 0;
         CKS(h, dalloc(h, &h->d_icp_out, need_out));
         CKS(h, dalloc(h, &h->d_icp_state, need_out));
         CKS(h, dalloc(h, &h->d_icp_ring, need_out));
-        CKS(h, dalloc(h, &h->d_icp_queue, (size_t)frames));   // one queue header per possible first frame of a launch
-        CK(h, cudaMemset(h->d_icp_queue, 0, sizeof(IcpQueue) * (size_t)frames));
         h->icp_out_elems = need_out;
+    }
+    // one queue header per possible first frame of a launch: sized by the frame count alone (a call with few frames and many
+    // guesses must not shrink it under a later full batch), never below the resident chunk
+    const size_t need_q = std::max((size_t)frames, (size_t)h->B);
+    if (need_q > h->icp_queue_frames) {
+        if (h->d_icp_queue) cudaFree(h->d_icp_queue);
+        h->d_icp_queue = nullptr; h->icp_queue_frames = 0;
+        CKS(h, dalloc(h, &h->d_icp_queue, need_q));
+        CK(h, cudaMemset(h->d_icp_queue, 0, sizeof(IcpQueue) * need_q));
+        h->icp_queue_frames = need_q;
     }
     return CUBOID_OK;
 }
@@ -195,6 +230,15 @@ int ensure_ray_tables(cuboid_handle* h, int w, int hgt) {
     CK(h, cudaStreamSynchronize(h->stream));
     h->ray_w = w; h->ray_h = hgt; h->ray_k[0] = p.fx; h->ray_k[1] = p.fy; h->ray_k[2] = p.cx; h->ray_k[3] = p.cy;
     return CUBOID_OK;
+}
+
+typedef void (*IcpKernel)(const IcpArgs);
+// k_icp<SUB, MODE>: nsub sub-workers per CTA (4, 2, 1 -> SUB 256, 512, 1024); mode 0 nodes only / 1 resident / 2 resident + queued search / 3 = 2 + candidate table
+IcpKernel icp_kernel(int nsub, int mode) {
+    static const IcpKernel tab[3][4] = {{k_icp<256, 0>, k_icp<256, 1>, k_icp<256, 2>, k_icp<256, 3>},
+                                        {k_icp<512, 0>, k_icp<512, 1>, k_icp<512, 2>, k_icp<512, 3>},
+                                        {k_icp<1024, 0>, k_icp<1024, 1>, k_icp<1024, 2>, k_icp<1024, 3>}};
+    return tab[nsub >= 4 ? 0 : (nsub == 2 ? 1 : 2)][mode];
 }
 
 struct ChunkIn {
@@ -334,7 +378,7 @@ int run_chunk(cuboid_handle* h, const ChunkIn& in, int nf, cuboid_frame_result* 
     if ((stages & 4) && !skip_cluster) {
         CluArgs c{};
         c.remain = b_remain; c.parent = b_parent; c.csize = b_csize; c.crank = b_crank; c.idx_sorted = b_idx_sorted;
-        c.offsets = b_offsets; c.roots = b_roots; c.cell_start = h->d_cell_head + (size_t)f0 * (2 * h->M + 2); c.cell_pts = h->d_cell_pts + oM; c.res = d_res; c.P = h->P; c.M = h->M; c.KC = h->KC;
+        c.offsets = b_offsets; c.roots = b_roots; c.cell_start = h->d_cell_head + (size_t)f0 * h->cell_stride; c.cell_pts = h->d_cell_pts + oM; c.res = d_res; c.P = h->P; c.M = h->M; c.KC = h->KC; c.cell_stride = h->cell_stride;
         c.r2 = (float)(p.cluster_tol * p.cluster_tol);
         c.inv_cell = (float)(1.0 / (0.52 * (p.cluster_tol > 0 ? p.cluster_tol : 1.0))); c.min_size = p.cluster_min; c.max_size = p.cluster_max;
         c.use_cluster = force_cluster ? 1 : p.use_cluster;
@@ -356,25 +400,33 @@ int run_chunk(cuboid_handle* h, const ChunkIn& in, int nf, cuboid_frame_result* 
         a.guesses = gs; a.n_guess = ng; a.guess_mode = gm;
         const size_t oG = (size_t)f0 * ng * h->M;
         IcpOut* b_out = h->d_icp_out + (size_t)f0 * CUBOID_MAX_CLUSTERS * ng;
-        a.cur = h->d_cur + oG; a.corr = h->d_corr + oG; a.cd = h->d_cd + oG; a.order = h->d_order + oG; a.out = b_out; a.res = d_res;
+        a.cur = h->d_cur + oG; a.corr = h->d_corr + oG; a.cd = h->d_cd + oG; a.order = h->d_order + oG; a.miss = h->d_miss + oG; a.out = b_out; a.res = d_res;
         a.P = h->P; a.M = h->M; a.KC = h->KC; a.max_iter = p.icp_max_iter;
         a.rot_thr = 1.0 - p.icp_tf_eps; a.trans_thr = p.icp_tf_eps; a.rel_mse = p.icp_rel_mse; a.abs_thr = 1e-12;
+        // shared memory of one k_icp CTA (one per SM): BVH nodes, then - as far as they fit - the template leaves, the sibling
+        // chains, the original-index table and the per-warp work lists of the queued search
         const size_t box_bytes = (size_t)a.nnodes * 16;
         if (box_bytes > (size_t)h->icp_smem_budget) return CUBOID_E_CAPACITY;
-        a.resident = (box_bytes + (size_t)a.Tpad * 12 <= (size_t)h->icp_smem_budget) ? 1 : 0;
+        size_t dyn = box_bytes;
+        a.resident = (dyn + (size_t)a.Tpad * 12 <= (size_t)h->icp_smem_budget) ? 1 : 0;
+        if (a.resident) dyn += (size_t)a.Tpad * 12;
         a.cull = h->icp_cull;
         a.hashes = h->taps ? 1 : 0;
-        a.work = h->d_work;
+        a.work = h->d_work; a.stats = h->d_stats;
         a.corr_trace = trace_corr; a.T_trace = trace_T; a.cap_trace = cap_trace;
-        size_t dyn = box_bytes + (a.resident ? (size_t)a.Tpad * 12 : 0);
-        {   // sibling chains ride along when two CTAs per SM still fit (or the template already forces one CTA per SM)
-            const size_t two_cta = (size_t)h->smem_sm / 2 - 1024 - 3072;
+        {
             const size_t sbytes = (size_t)h->sib_bytes[tmpl_slot];
             a.sib = h->d_sib[tmpl_slot]; a.sib_max = h->sib_max[tmpl_slot]; a.sib_bytes = (int)sbytes;
-            a.sib_on = (a.resident && h->icp_outward && sbytes > 0 && (dyn + sbytes <= two_cta || (dyn > two_cta && dyn + sbytes <= (size_t)h->icp_smem_budget))) ? 1 : 0;
+            a.sib_on = (a.resident && h->icp_outward && sbytes > 0 && dyn + sbytes <= (size_t)h->icp_smem_budget) ? 1 : 0;
             if (a.sib_on) dyn += sbytes;
+            const size_t qbytes = (size_t)a.Tpad * 2 + (size_t)(ICP_NT / 32) * sizeof(IcpWarpScr);
+            a.orig16 = h->d_orig16[tmpl_slot];
+            a.qmode = (a.sib_on && a.cull && h->icp_queued && a.orig16 && dyn + qbytes <= (size_t)h->icp_smem_budget) ? 1 : 0;
+            if (a.qmode) dyn += qbytes;
+            a.tmode = (a.qmode && h->icp_table && h->d_nnt[tmpl_slot]) ? 1 : 0;
+            a.tab = h->nnt[tmpl_slot];
         }
-        // persistent, time-sliced: k_icp_init builds every problem's state and queue entry, then a fixed crew of CTAs (two per
+        // persistent, time-sliced: k_icp_init builds every problem's state and queue entry, then a fixed crew of CTAs (one per
         // SM, no more than there can be problems) serves slices of icp_slice_iters iterations until all problems are finished
         const size_t oS = (size_t)f0 * CUBOID_MAX_CLUSTERS * ng;
         a.pstate = h->d_icp_state + oS; a.ring = h->d_icp_ring + oS; a.queue = h->d_icp_queue + f0;
@@ -384,18 +436,22 @@ int run_chunk(cuboid_handle* h, const ChunkIn& in, int nf, cuboid_frame_result* 
         CK(h, cudaMemsetAsync(a.queue, 0, sizeof(IcpQueue), st));
         CK(h, cudaMemsetAsync(a.ring, 0, sizeof(IcpSlot) * (size_t)a.n_slots, st));
         a.crew = (int)std::max<long long>(1, std::min<long long>(h->icp_ctas, (long long)nf * ng * CUBOID_MAX_CLUSTERS));
-        // two 256-thread sub-workers per CTA when there is at least one problem per sub-worker (one cluster per frame and guess
-        // assumed), else all 512 threads on one problem: with few problems the latency of each is what counts
-        a.nsub = ((long long)nf * ng >= 2LL * a.crew) ? 2 : 1;
+        // sub-workers per CTA: four of 256 threads when there is at least one problem per sub-worker (one cluster per frame and
+        // guess assumed), else two of 512, else all 1024 threads on one problem: with few problems the latency of each counts
+        const long long nprob = (long long)nf * ng;
+        a.nsub = nprob >= 4LL * a.crew ? 4 : (nprob >= 2LL * a.crew ? 2 : 1);
         if (h->icp_nsub_force) a.nsub = h->icp_nsub_force;
         k_icp_init<<<dim3(ng, CUBOID_MAX_CLUSTERS, nf), ICP_THREADS, a.init_smem, st>>>(a);
-        if (a.nsub == 2) k_icp<256><<<a.crew, ICP_THREADS, dyn, st>>>(a);   // workers beyond the number of real problems leave at once
-        else k_icp<512><<<a.crew, ICP_THREADS, dyn, st>>>(a);
-        ++h->launches;
+        const int mode = a.tmode ? 3 : (a.qmode ? 2 : (a.resident ? 1 : 0));
+        auto kfn = icp_kernel(a.nsub, mode);
+        kfn<<<a.crew, ICP_NT, dyn, st>>>(a);   // workers beyond the number of real problems leave at once
         const int tot = nf * CUBOID_MAX_CLUSTERS;
-        k_icp_select<<<(tot + 127) / 128, 128, 0, st>>>(b_out, d_res, nf, ng, p.icp_fitness_gate, h->d_cur + oG, h->M, b_offsets,
-                                                     h->KC, aligned);
-        h->launches += 2;
+        k_icp_select<<<(tot + 127) / 128, 128, 0, st>>>(b_out, d_res, nf, ng, p.icp_fitness_gate);
+        h->launches += 3;
+        if (aligned) {
+            k_icp_aligned<<<32, 256, 0, st>>>(d_res, h->d_cur + oG, h->M, b_offsets, aligned);
+            ++h->launches;
+        }
         CK(h, cudaGetLastError());
     }
     CK(h, cudaEventRecord(evs[5], st));
@@ -481,7 +537,7 @@ void cuboid_default_params(cuboid_params* p) {
     p->n_guess = 1; p->guess_mode = 0;
 }
 
-int cuboid_create(cuboid_handle** out, const cuboid_params* p, int device, int max_points, int max_batch) {
+static int create_impl(cuboid_handle** out, const cuboid_params* p, int device, int max_points, int max_batch) {
     if (!out || !p || max_points < 1 || max_batch < 1) return CUBOID_E_INVALID;
     *out = nullptr;
     const int vs = validate_params(p);
@@ -525,7 +581,12 @@ int cuboid_create(cuboid_handle** out, const cuboid_params* p, int device, int m
     CA(dalloc(h, &h->d_idx_sorted, BM));
     CA(dalloc(h, &h->d_offsets, (size_t)h->B * (h->KC + 1)));
     CA(dalloc(h, &h->d_roots, (size_t)h->B * h->KC));
-    CA(dalloc(h, &h->d_cell_head, (size_t)h->B * (2 * h->M + 2)));
+    {   // cluster.cuh: hs = smallest power of two >= max(64, 2 n), n <= M, and cend[0 .. hs] is used
+        int hs = 64;
+        while (hs < 2 * h->M) hs <<= 1;
+        h->cell_stride = hs + 1;
+    }
+    CA(dalloc(h, &h->d_cell_head, (size_t)h->B * h->cell_stride));
     CA(dalloc(h, &h->d_cell_pts, BM));
     CA(dalloc(h, &h->d_scr, (size_t)h->B));
     CA(dalloc(h, &h->d_desc1, (size_t)h->B * h->tilesP));
@@ -535,17 +596,21 @@ int cuboid_create(cuboid_handle** out, const cuboid_params* p, int device, int m
     CA(upload_rng(h));
     CA(ensure_icp_scratch(h, h->B, std::max(1, (int)p->n_guess)));
     cudaDeviceGetAttribute(&h->smem_optin, cudaDevAttrMaxSharedMemoryPerBlockOptin, device);
-    h->icp_smem_budget = h->smem_optin - 4096;   // static shared memory of k_icp stays well below 4 KB
-    if (cudaFuncSetAttribute(k_icp<256>, cudaFuncAttributeMaxDynamicSharedMemorySize, h->icp_smem_budget) != cudaSuccess) return fail(CUBOID_E_CUDA);
-    if (cudaFuncSetAttribute(k_icp<512>, cudaFuncAttributeMaxDynamicSharedMemorySize, h->icp_smem_budget) != cudaSuccess) return fail(CUBOID_E_CUDA);
+    h->icp_smem_budget = h->smem_optin - 6144;   // static shared memory of k_icp (4 x IcpShared + hash / work partials) stays below 6 KB
+    for (int ns : {4, 2, 1})
+        for (int mode = 0; mode < 4; ++mode)
+            if (cudaFuncSetAttribute(icp_kernel(ns, mode), cudaFuncAttributeMaxDynamicSharedMemorySize, h->icp_smem_budget) != cudaSuccess) return fail(CUBOID_E_CUDA);
     if (cudaFuncSetAttribute(k_icp_init, cudaFuncAttributeMaxDynamicSharedMemorySize, 65536) != cudaSuccess) return fail(CUBOID_E_CUDA);
     {
         int sms = 0;
         cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, device);
-        h->icp_ctas = 2 * sms;
+        h->icp_ctas = sms;   // one 1024-thread CTA per SM
         const char* es = std::getenv("CUBOID_ICP_SLICE"); if (es) h->icp_slice_iters = std::max(1, atoi(es));
         const char* eo = std::getenv("CUBOID_ICP_OUTWARD"); if (eo) h->icp_outward = atoi(eo) ? 1 : 0;
-        const char* en = std::getenv("CUBOID_ICP_NSUB"); if (en) h->icp_nsub_force = (atoi(en) == 1 || atoi(en) == 2) ? atoi(en) : 0;
+        const char* en = std::getenv("CUBOID_ICP_NSUB"); if (en) h->icp_nsub_force = (atoi(en) == 1 || atoi(en) == 2 || atoi(en) == 4) ? atoi(en) : 0;
+        const char* eq = std::getenv("CUBOID_ICP_QUEUED"); if (eq) h->icp_queued = atoi(eq) ? 1 : 0;
+        const char* etb = std::getenv("CUBOID_ICP_TABLE"); if (etb) h->icp_table = atoi(etb) ? 1 : 0;
+        const char* eh = std::getenv("CUBOID_NNT_H_MM"); if (eh && atof(eh) > 0.0) h->nnt_h = atof(eh) * 1e-3;
         cudaDeviceGetAttribute(&h->smem_sm, cudaDevAttrMaxSharedMemoryPerMultiprocessor, device);
     }
     {   // fused front end: cluster size and the number of clusters the device keeps resident
@@ -587,6 +652,8 @@ int cuboid_create(cuboid_handle** out, const cuboid_params* p, int device, int m
     }
     CA(dalloc(h, &h->d_work, (size_t)2));
     if (cudaMemset(h->d_work, 0, 16) != cudaSuccess) return fail(CUBOID_E_CUDA);
+    CA(dalloc(h, &h->d_stats, (size_t)32));
+    if (cudaMemset(h->d_stats, 0, 256) != cudaSuccess) return fail(CUBOID_E_CUDA);
     { const char* ec = std::getenv("CUBOID_ICP_CULL"); if (ec) h->icp_cull = atoi(ec) ? 1 : 0; }
     if (cudaFuncSetAttribute(k_sac_plane, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)sizeof(SacShared)) != cudaSuccess) return fail(CUBOID_E_CUDA);
     if (cudaFuncSetAttribute(k_cluster, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)CLU_DYN_SMEM) != cudaSuccess) return fail(CUBOID_E_CUDA);
@@ -601,12 +668,14 @@ int cuboid_destroy(cuboid_handle* h) {
     if (h->stream) cudaStreamSynchronize(h->stream);
     void* ptrs[] = {h->d_depth, h->d_blob, h->d_n_in, h->d_xr, h->d_yr, h->d_pts, h->d_keysA, h->d_keysB, h->d_kpp, h->d_hist, h->d_vox, h->d_vcount, h->d_shuffled,
                     h->d_inl_pre, h->d_inl, h->d_remain, h->d_parent, h->d_csize, h->d_crank, h->d_idx_sorted, h->d_offsets, h->d_roots, h->d_cell_head, h->d_cell_pts,
-                    h->d_cur, h->d_corr, h->d_cd, h->d_order, h->d_icp_out, h->d_icp_state, h->d_icp_ring, h->d_icp_queue, h->d_scr, h->d_desc1, h->d_desc2, h->d_ticket, h->d_res, h->d_rng,
-                    h->d_triplets, h->d_guesses, h->d_trace_corr, h->d_trace_T, h->d_aligned, h->d_work, h->d_fe_keys};
+                    h->d_cur, h->d_corr, h->d_cd, h->d_order, h->d_miss, h->d_icp_out, h->d_icp_state, h->d_icp_ring, h->d_icp_queue, h->d_scr, h->d_desc1, h->d_desc2, h->d_ticket, h->d_res, h->d_rng,
+                    h->d_triplets, h->d_guesses, h->d_trace_corr, h->d_trace_T, h->d_aligned, h->d_call_guesses, h->d_work, h->d_stats, h->d_fe_keys};
     for (void* q : ptrs) if (q) cudaFree(q);
     for (auto& t : h->d_tmpl) if (t) cudaFree(t);
     for (auto& t : h->d_boxes) if (t) cudaFree(t);
     for (auto& t : h->d_sib) if (t) cudaFree(t);
+    for (auto& t : h->d_orig16) if (t) cudaFree(t);
+    for (auto& t : h->d_nnt) if (t) cudaFree(t);
     for (auto& t : h->d_tmpl_orig) if (t) cudaFree(t);
     for (auto& e : h->ev) if (e) cudaEventDestroy(e);
     for (auto& e : h->ev_pool) if (e) cudaEventDestroy(e);
@@ -621,7 +690,7 @@ int cuboid_destroy(cuboid_handle* h) {
     return CUBOID_OK;
 }
 
-int cuboid_set_params(cuboid_handle* h, const cuboid_params* p) {
+static int set_params_impl(cuboid_handle* h, const cuboid_params* p) {
     if (!h || !p) return CUBOID_E_INVALID;
     const int vs = validate_params(p);
     if (vs != CUBOID_OK) return vs;
@@ -668,7 +737,7 @@ void bvh_build(KdItem* a, int first, int n, std::vector<BvhNode>& nodes) {
 }
 }  // namespace
 
-int cuboid_set_template(cuboid_handle* h, int slot, const float* xyz, int stride_bytes, int n) {
+static int set_template_impl(cuboid_handle* h, int slot, const float* xyz, int stride_bytes, int n) {
     if (!h || slot < 0 || slot >= CUBOID_MAX_TEMPLATES || !xyz || n < 1 || stride_bytes < 12) return CUBOID_E_INVALID;
     cudaSetDevice(h->device);
     const int nleaf = (n + ICP_LEAF - 1) / ICP_LEAF;
@@ -700,6 +769,11 @@ int cuboid_set_template(cuboid_handle* h, int slot, const float* xyz, int stride
     // SoA per leaf: x[32] y[32] z[32]; far sentinels (huge but finite distance: never win, never NaN) pad the tail
     std::vector<float> host((size_t)pad * 3, 1.0e18f);
     std::vector<int> orig(pad, 0x7fffffff);
+    for (int i = n; i < pad; ++i) {   // sentinels at distinct distances, so they never look like an exact tie among themselves
+        float* lf = host.data() + (size_t)(i / ICP_LEAF) * ICP_LEAF_FLOATS + (i % ICP_LEAF);
+        const float v = 1.0e18f * (1.0f + 0.01f * (float)(i - n + 1));
+        lf[0] = v; lf[ICP_LEAF] = v; lf[2 * ICP_LEAF] = v;
+    }
     for (int i = 0; i < n; ++i) {
         float* lf = host.data() + (size_t)(i / ICP_LEAF) * ICP_LEAF_FLOATS + (i % ICP_LEAF);
         lf[0] = items[i].x; lf[ICP_LEAF] = items[i].y; lf[2 * ICP_LEAF] = items[i].z;
@@ -737,6 +811,13 @@ int cuboid_set_template(cuboid_handle* h, int slot, const float* xyz, int stride
         CK(h, cudaMemcpy(h->d_sib[slot], sib.data(), sib.size() * 2, cudaMemcpyHostToDevice));
         h->sib_bytes[slot] = (int)(sib.size() * 2); h->sib_max[slot] = sib_max;
     }
+    if (h->d_orig16[slot]) { cudaFree(h->d_orig16[slot]); h->d_orig16[slot] = nullptr; }
+    if (pad <= 65536 && nodes.size() < 65535) {
+        std::vector<unsigned short> o16(pad, (unsigned short)0xffff);
+        for (int i = 0; i < n; ++i) o16[i] = (unsigned short)items[i].orig;
+        CKS(h, dalloc(h, &h->d_orig16[slot], o16.size()));
+        CK(h, cudaMemcpy(h->d_orig16[slot], o16.data(), o16.size() * 2, cudaMemcpyHostToDevice));
+    }
     if (h->d_tmpl[slot]) { cudaFree(h->d_tmpl[slot]); h->d_tmpl[slot] = nullptr; }
     if (h->d_tmpl_orig[slot]) { cudaFree(h->d_tmpl_orig[slot]); h->d_tmpl_orig[slot] = nullptr; }
     if (h->d_boxes[slot]) { cudaFree(h->d_boxes[slot]); h->d_boxes[slot] = nullptr; }
@@ -747,7 +828,60 @@ int cuboid_set_template(cuboid_handle* h, int slot, const float* xyz, int stride
     CK(h, cudaMemcpy(h->d_tmpl_orig[slot], orig.data(), sizeof(int) * orig.size(), cudaMemcpyHostToDevice));
     CK(h, cudaMemcpy(h->d_boxes[slot], packed.data(), sizeof(uint4) * packed.size(), cudaMemcpyHostToDevice));
     h->tmpl_n[slot] = n; h->tmpl_pad[slot] = pad; h->tmpl_nleaf[slot] = nleaf; h->tmpl_nnodes[slot] = (int)nodes.size();
+    // nearest-neighbour candidate table (nn_table.cuh): a dense grid of cells of side hcell around the template, 10 cells of margin
+    if (h->d_nnt[slot]) { cudaFree(h->d_nnt[slot]); h->d_nnt[slot] = nullptr; }
+    h->nnt[slot] = NnTableView{};
+    if (h->icp_table && h->d_orig16[slot]) {
+        double mn[3] = {1e300, 1e300, 1e300}, mx[3] = {-1e300, -1e300, -1e300}, maxabs = 0.0;
+        bool finite = true;
+        for (int i = 0; i < n; ++i) {
+            const double c[3] = {(double)items[i].x, (double)items[i].y, (double)items[i].z};
+            for (int d = 0; d < 3; ++d) { finite = finite && std::isfinite(c[d]); mn[d] = std::min(mn[d], c[d]); mx[d] = std::max(mx[d], c[d]); maxabs = std::max(maxabs, std::fabs(c[d])); }
+        }
+        double hcell = h->nnt_h;
+        long long dims[3] = {0, 0, 0};
+        for (int tries = 0; finite && tries < 64; ++tries) {   // widen the cells until the dense grid has at most 3M of them (96 MB)
+            const double band = 10.0 * hcell;
+            long long nv = 1;
+            for (int d = 0; d < 3; ++d) { dims[d] = (long long)std::ceil((mx[d] - mn[d] + 2.0 * band) / hcell) + 1; nv *= dims[d]; }
+            if (nv <= 3000000LL) break;
+            hcell *= 1.15;
+        }
+        long long nvox = dims[0] * dims[1] * dims[2];
+        if (finite && nvox > 0 && nvox <= 3000000LL) {
+            NnTableGeom g{};
+            NnTableView view{};
+            view.inv_h = (float)(1.0 / hcell);
+            g.h = 1.0 / (double)view.inv_h;                 // the cell side the run-time index computation actually uses
+            for (int d = 0; d < 3; ++d) { view.org[d] = (float)(mn[d] - 10.0 * hcell); g.org[d] = (double)view.org[d]; }
+            view.nx = g.nx = (int)dims[0]; view.ny = g.ny = (int)dims[1]; view.nz = g.nz = (int)dims[2];
+            g.delta = std::max(1.0e-3 * g.h, 2.0e-6 * (maxabs + 12.0 * hcell));   // >> the rounding of (q - org) * inv_h in float
+            g.band2 = (10.0 * g.h) * (10.0 * g.h);
+            CKS(h, dalloc(h, &h->d_nnt[slot], (size_t)(2 * nvox)));
+            k_nn_table_build<ICP_LEAF><<<(unsigned int)((nvox + NNT_THREADS - 1) / NNT_THREADS), NNT_THREADS, 0, h->stream>>>(
+                h->d_tmpl[slot], h->d_tmpl_orig[slot], n, g, h->d_nnt[slot]);
+            ++h->launches;
+            CK(h, cudaGetLastError());
+            CK(h, cudaStreamSynchronize(h->stream));
+            view.rec = h->d_nnt[slot];
+            h->nnt[slot] = view;
+        }
+    }
     return CUBOID_OK;
+}
+
+
+// Nothing throws across the C boundary: the entry points that allocate host memory (std::vector, std::string) catch here.
+#define CUBOID_NOTHROW(h_, expr)                                             \
+    try { return (expr); }                                                   \
+    catch (const std::bad_alloc&) { if (h_) (h_)->last_error = "out of host memory"; return CUBOID_E_CAPACITY; } \
+    catch (...) { return CUBOID_E_INVALID; }
+int cuboid_create(cuboid_handle** out, const cuboid_params* p, int device, int max_points, int max_batch) {
+    CUBOID_NOTHROW((cuboid_handle*)nullptr, create_impl(out, p, device, max_points, max_batch))
+}
+int cuboid_set_params(cuboid_handle* h, const cuboid_params* p) { CUBOID_NOTHROW(h, set_params_impl(h, p)) }
+int cuboid_set_template(cuboid_handle* h, int slot, const float* xyz, int stride_bytes, int n) {
+    CUBOID_NOTHROW(h, set_template_impl(h, slot, xyz, stride_bytes, n))
 }
 
 int cuboid_set_guesses(cuboid_handle* h, const float* guesses, int n_guess, int guess_mode) {
@@ -777,6 +911,15 @@ int cuboid_unproject(cuboid_handle* h, const uint16_t* depth, int w, int hgt, fl
     return CUBOID_OK;
 }
 
+// x, y, z are 4-byte fields inside one point_step-sized record (sensor_msgs/PointField offsets), 4-byte aligned
+static bool blob_layout_ok(int point_step, int xoff, int yoff, int zoff) {
+    if (point_step < 12 || (point_step & 3)) return false;
+    const int off[3] = {xoff, yoff, zoff};
+    for (int o : off)
+        if (o < 0 || (o & 3) || o + 4 > point_step) return false;
+    return true;
+}
+
 static int upload_blob(cuboid_handle* h, const void* pts, int point_step, int n) {
     const size_t bytes = (size_t)n * point_step;
     if (bytes > h->blob_cap) {
@@ -793,12 +936,12 @@ static int upload_blob(cuboid_handle* h, const void* pts, int point_step, int n)
 
 int cuboid_preprocess(cuboid_handle* h, const void* pts, int point_step, int xoff, int yoff, int zoff, int n, float* vox_xyzw_out,
                       int cap, int* n_vox, int32_t* key_per_point_out, int* n_pass) {
-    if (!h || (!pts && n > 0) || n < 0 || point_step < 12 || (point_step & 3) || (xoff & 3) || (yoff & 3) || (zoff & 3)) return CUBOID_E_INVALID;
+    if (!h || (!pts && n > 0) || n < 0 || !blob_layout_ok(point_step, xoff, yoff, zoff)) return CUBOID_E_INVALID;
     if (n > h->P) return CUBOID_E_CAPACITY;
     cudaSetDevice(h->device);
+    CKS(h, upload_blob(h, pts, point_step, n));
     const int saved_taps = h->taps;
     h->taps = 1;
-    CKS(h, upload_blob(h, pts, point_step, n));
     ChunkIn in;
     in.blob = h->d_blob; in.point_step = point_step; in.xoff = xoff; in.yoff = yoff; in.zoff = zoff; in.in_stride = h->P;
     const int st = run_chunk(h, in, 1, h->d_res, 1, 0);
@@ -830,6 +973,8 @@ int cuboid_segment_plane(cuboid_handle* h, const float* xyzw, int n, const int32
     ++h->launches;
     const int* dtrip = nullptr;
     if (triplets && n_triplets > 0) {
+        for (long long k = 0; k < 3LL * n_triplets; ++k)
+            if (triplets[k] < 0 || triplets[k] >= n) return CUBOID_E_INVALID;
         if (n_triplets > h->triplets_cap) {
             if (h->d_triplets) cudaFree(h->d_triplets);
             h->d_triplets = nullptr; h->triplets_cap = 0;
@@ -983,10 +1128,9 @@ int cuboid_set_bbox_filter(cuboid_handle* h, const double P[12], const int32_t b
     return CUBOID_OK;
 }
 
-int cuboid_bbox_filter(cuboid_handle* h, const void* pts, int point_step, int xoff, int yoff, int zoff, int n, const double P[12],
+static int bbox_filter_impl(cuboid_handle* h, const void* pts, int point_step, int xoff, int yoff, int zoff, int n, const double P[12],
                        const int32_t bbox[4], int32_t* idx_out, float* xyzw_out, int cap, int* n_out) {
-    if (!h || (!pts && n > 0) || n < 0 || !P || !bbox || !n_out || point_step < 12 || (point_step & 3) || (xoff & 3) || (yoff & 3) || (zoff & 3))
-        return CUBOID_E_INVALID;
+    if (!h || (!pts && n > 0) || n < 0 || !P || !bbox || !n_out || !blob_layout_ok(point_step, xoff, yoff, zoff)) return CUBOID_E_INVALID;
     if (n > h->P) return CUBOID_E_CAPACITY;
     cudaSetDevice(h->device);
     // gather x, y, z of the PointCloud2 records into xyzw on the host side of the copy (the node does fromPCLPointCloud2 first)
@@ -1014,6 +1158,11 @@ int cuboid_bbox_filter(cuboid_handle* h, const void* pts, int point_step, int xo
     if (idx_out && m) CK(h, cudaMemcpy(idx_out, h->d_inl, sizeof(int) * m, cudaMemcpyDeviceToHost));
     if (xyzw_out && m) CK(h, cudaMemcpy(xyzw_out, h->d_remain, sizeof(float4) * m, cudaMemcpyDeviceToHost));
     return CUBOID_OK;
+}
+
+int cuboid_bbox_filter(cuboid_handle* h, const void* pts, int point_step, int xoff, int yoff, int zoff, int n, const double P[12],
+                       const int32_t bbox[4], int32_t* idx_out, float* xyzw_out, int cap, int* n_out) {
+    CUBOID_NOTHROW(h, bbox_filter_impl(h, pts, point_step, xoff, yoff, zoff, n, P, bbox, idx_out, xyzw_out, cap, n_out))
 }
 
 int cuboid_cluster(cuboid_handle* h, const float* xyzw, int n, int32_t* idx_sorted_out, int32_t* offsets_out, int cap_clusters,
@@ -1055,30 +1204,36 @@ int cuboid_icp(cuboid_handle* h, const float* src_xyzw, int n_src, int tmpl_slot
     ++h->launches;
     float* dg = nullptr;
     if (guesses_4x4) {
-        CK(h, cudaMalloc(reinterpret_cast<void**>(&dg), sizeof(float) * 16 * n_guess));
+        CKS(h, ensure_buf(h, &h->d_call_guesses, &h->call_guesses_cap, (size_t)16 * n_guess));
+        dg = h->d_call_guesses;
         CK(h, cudaMemcpyAsync(dg, guesses_4x4, sizeof(float) * 16 * n_guess, cudaMemcpyHostToDevice, h->stream));
     } else {
         n_guess = 1;
     }
     int* dct = nullptr; float* dtt = nullptr; float4* dal = nullptr;
     if (corr_trace && cap_trace_iters > 0 && n_src > 0) {
-        CK(h, cudaMalloc(reinterpret_cast<void**>(&dct), sizeof(int) * (size_t)cap_trace_iters * n_src));
+        CKS(h, ensure_buf(h, &h->d_trace_corr, &h->trace_corr_cap, (size_t)cap_trace_iters * n_src));
+        CKS(h, ensure_buf(h, &h->d_trace_T, &h->trace_T_cap, (size_t)16 * cap_trace_iters));
+        dct = h->d_trace_corr; dtt = h->d_trace_T;
         CK(h, cudaMemsetAsync(dct, 0xff, sizeof(int) * (size_t)cap_trace_iters * n_src, h->stream));
-        CK(h, cudaMalloc(reinterpret_cast<void**>(&dtt), sizeof(float) * 16 * cap_trace_iters));
         CK(h, cudaMemsetAsync(dtt, 0, sizeof(float) * 16 * cap_trace_iters, h->stream));
     }
-    if (aligned_xyzw_out && n_src > 0) CK(h, cudaMalloc(reinterpret_cast<void**>(&dal), sizeof(float4) * n_src));
+    if (aligned_xyzw_out && n_src > 0) {
+        CKS(h, ensure_buf(h, &h->d_aligned, &h->aligned_cap, (size_t)n_src));
+        dal = h->d_aligned;
+    }
     ChunkIn in;
     // with no guesses the kernel must still see "no guess table": pass override only when present
-    const int st = run_chunk(h, in, 1, h->d_res, 8, tmpl_slot, true, true, true, true, nullptr, 0, dg, n_guess, 0, dct, dtt, cap_trace_iters, dal);
-    int rc = st;
+    CKS(h, run_chunk(h, in, 1, h->d_res, 8, tmpl_slot, true, true, true, true, nullptr, 0, dg, n_guess, 0, dct, dtt, cap_trace_iters, dal));
     cuboid_frame_result r;
-    std::memset(&r, 0, sizeof r);
-    if (rc == CUBOID_OK) {
-        if (cudaMemcpyAsync(&r, h->d_res, sizeof r, cudaMemcpyDeviceToHost, h->stream) != cudaSuccess) rc = CUBOID_E_CUDA;
-        if (cudaStreamSynchronize(h->stream) != cudaSuccess) { rc = CUBOID_E_CUDA; h->last_error = cudaGetErrorString(cudaGetLastError()); }
-        if (rc == CUBOID_OK) rc = check_icp_queues(h, 1);
+    CK(h, cudaMemcpyAsync(&r, h->d_res, sizeof r, cudaMemcpyDeviceToHost, h->stream));
+    if (dct) {
+        CK(h, cudaMemcpyAsync(corr_trace, dct, sizeof(int) * (size_t)cap_trace_iters * n_src, cudaMemcpyDeviceToHost, h->stream));
+        if (T_trace) CK(h, cudaMemcpyAsync(T_trace, dtt, sizeof(float) * 16 * cap_trace_iters, cudaMemcpyDeviceToHost, h->stream));
     }
+    if (dal) CK(h, cudaMemcpyAsync(aligned_xyzw_out, dal, sizeof(float4) * n_src, cudaMemcpyDeviceToHost, h->stream));
+    CK(h, cudaStreamSynchronize(h->stream));
+    const int rc = check_icp_queues(h, 1);
     if (rc == CUBOID_OK) {
         const cuboid_cluster_result& c = r.cluster[0];
         if (best_T_out) std::memcpy(best_T_out, c.T, 64);
@@ -1089,23 +1244,14 @@ int cuboid_icp(cuboid_handle* h, const float* src_xyzw, int n_src, int tmpl_slot
         if (state) *state = c.state;
         if (best_guess) *best_guess = c.best_guess;
         if (corr_hash) *corr_hash = c.corr_hash;
-        if (dct) {
-            cudaMemcpy(corr_trace, dct, sizeof(int) * (size_t)cap_trace_iters * n_src, cudaMemcpyDeviceToHost);
-            if (T_trace) cudaMemcpy(T_trace, dtt, sizeof(float) * 16 * cap_trace_iters, cudaMemcpyDeviceToHost);
-        }
-        if (dal) cudaMemcpy(aligned_xyzw_out, dal, sizeof(float4) * n_src, cudaMemcpyDeviceToHost);
     }
-    if (dg) cudaFree(dg);
-    if (dct) cudaFree(dct);
-    if (dtt) cudaFree(dtt);
-    if (dal) cudaFree(dal);
     h->last_chunk_base = 0; h->last_chunk_frames = 1; h->last_total_frames = 1;
     return rc;
 }
 
 int cuboid_process_cloud(cuboid_handle* h, const void* pts, int point_step, int xoff, int yoff, int zoff, int n, int tmpl_slot,
                          cuboid_frame_result* result) {
-    if (!h || (!pts && n > 0) || n < 0 || !result || point_step < 12 || (point_step & 3) || (xoff & 3) || (yoff & 3) || (zoff & 3)) return CUBOID_E_INVALID;
+    if (!h || (!pts && n > 0) || n < 0 || !result || !blob_layout_ok(point_step, xoff, yoff, zoff)) return CUBOID_E_INVALID;
     if (n > h->P) return CUBOID_E_CAPACITY;
     cudaSetDevice(h->device);
     CKS(h, upload_blob(h, pts, point_step, n));
@@ -1220,8 +1366,8 @@ static int process_frames(cuboid_handle* h, const uint16_t* depth, bool on_devic
 }
 
 int cuboid_process_batch(cuboid_handle* h, const uint16_t* depth, int w, int hgt, int n_frames, int tmpl_slot, cuboid_frame_result* results) {
-    if (!results) return CUBOID_E_INVALID;
-    const bool have_t = h && tmpl_slot >= 0 && tmpl_slot < CUBOID_MAX_TEMPLATES && h->d_tmpl[tmpl_slot];
+    if (!h || !results) return CUBOID_E_INVALID;
+    const bool have_t = tmpl_slot >= 0 && tmpl_slot < CUBOID_MAX_TEMPLATES && h->d_tmpl[tmpl_slot];
     CKS(h, process_frames(h, depth, false, w, hgt, n_frames, tmpl_slot, (have_t ? 15 : 7) & h->stage_mask));
     CK(h, cudaMemcpyAsync(results, h->d_res, sizeof(cuboid_frame_result) * n_frames, cudaMemcpyDeviceToHost, h->stream));
     CK(h, cudaStreamSynchronize(h->stream));
@@ -1414,6 +1560,13 @@ int cuboid_set_option(cuboid_handle* h, int option, int value) {
             return CUBOID_OK;
         default: return CUBOID_E_INVALID;
     }
+}
+int cuboid_debug_counters(cuboid_handle* h, uint64_t out[32], int reset) {
+    if (!h || !out) return CUBOID_E_INVALID;
+    cudaSetDevice(h->device);
+    CK(h, cudaMemcpy(out, h->d_stats, 256, cudaMemcpyDeviceToHost));
+    if (reset) CK(h, cudaMemset(h->d_stats, 0, 256));
+    return CUBOID_OK;
 }
 int cuboid_icp_work(cuboid_handle* h, uint64_t out[2]) {
     if (!h || !out) return CUBOID_E_INVALID;

@@ -1,19 +1,25 @@
 // icp.cuh — stage 4: pcl::IterativeClosestPoint<PointXYZ,PointXYZ>::align + getFitnessScore
-// (icp.cpp:170-182, opd.cpp:220-235). One persistent CTA per (frame, cluster, guess):
-// the whole ICP loop — nearest neighbours, Umeyama, 3x3 Jacobi SVD, incremental transform,
-// DefaultConvergenceCriteria — runs on the device, no host round trip.
+// (icp.cpp:170-182, opd.cpp:220-235). The whole ICP loop — nearest neighbours, Umeyama, 3x3 Jacobi SVD,
+// incremental transform, DefaultConvergenceCriteria — runs on the device, no host round trip.
 //
-//   nearest neighbour   exact search over a bounding-volume hierarchy of the template. The template is re-ordered
-//                       once on the host (kd split) into spatially compact 32-point leaves stored SoA, with the
-//                       tree nodes (AABB + skip link, depth-first order) beside them; both are staged ONCE in
-//                       shared memory by TMA bulk copies. Each lane owns one source point and walks the tree
-//                       stacklessly: a node is skipped only if the AABB lower bound — evaluated with the same
-//                       un-fused rounding sequence as the distance itself, hence a true bit-level bound — is
-//                       strictly above the lane's running minimum, which is seeded with the distance to the
-//                       previous iteration's correspondent. Leaves are scanned brute force,
-//                       d2 = ((dx*dx)+dy*dy)+dz*dz; ties resolve to the LOWEST ORIGINAL template index, i.e.
-//                       exactly what a brute-force scan in template order with strict '<' returns (the canonical
-//                       tie rule). With culling off the same code visits every leaf (plain brute force).
+//   execution           k_icp_init builds every (frame, cluster, guess) problem; k_icp is a PERSISTENT kernel, one
+//                       1024-thread CTA per SM hosting 1024 / SUB sub-workers (SUB = 256, 512 or 1024 threads, named
+//                       barriers) around ONE shared-memory copy of the template, its BVH, the sibling chains and the
+//                       original-index table. A sub-worker pops a problem from a ring queue, runs a time slice of
+//                       iterations and either finishes it or pushes it back.
+//   nearest neighbour   exact search over a bounding-volume hierarchy of the template (kd split on the host into 16-point
+//                       leaves stored SoA, nodes in depth-first order, fp16 boxes rounded OUTWARD). A subtree is skipped
+//                       only if its box's lower bound — evaluated with the same un-fused rounding sequence as the distance
+//                       itself, hence a true bit-level bound — is strictly above the running minimum. The search runs
+//                       OUTWARD from the previous iteration's correspondent: its leaf first, then the sibling subtrees of
+//                       that leaf's path to the root are box-tested by all lanes in lockstep. What survives is NOT walked
+//                       lane by lane: (query, subtree) items go on a per-warp work list in shared memory that the warp
+//                       drains 32 items at a time — node tests and leaf scans always run with full warps, whichever
+//                       queries they belong to (icp_nn_pass, QUEUED). Leaves are scanned brute force,
+//                       d2 = ((dx*dx)+dy*dy)+dz*dz; ties resolve to the LOWEST ORIGINAL template index, i.e. exactly what a
+//                       brute-force scan in template order with strict '<' returns (the canonical tie rule).
+//                       A work list that would overflow (queries far from the template) falls back to the per-lane
+//                       stackless walk, which is also the path for templates too large for shared memory.
 //   Umeyama             canonical 256-lane strided partial sums + xor-butterfly + 8 warp partials left to right
 //                       (identical in oracle/cuboid_oracle.cpp: canon_reduce), Eigen JacobiSVD restated
 //   convergence         max iterations | transform epsilon | |dMSE| < 1e-12 | rel dMSE < icp_fitness_score
@@ -24,6 +30,7 @@
 #include <cuda_fp16.h>
 
 #include "common.cuh"
+#include "nn_table.cuh"
 #include "ransac.cuh"   // TMA bulk-copy helpers
 
 namespace cuboid {
@@ -39,7 +46,7 @@ struct IcpArgs {
     const float4* remain;    // [F][P]
     const int* idx_sorted;   // [F][M]
     const int* offsets;      // [F][KC+1]
-    const float* tmpl;       // [nleaf][3][32] kd-ordered 32-point leaves, SoA per leaf (x[32] y[32] z[32]); far sentinels pad the tail
+    const float* tmpl;       // [nleaf][3][16] kd-ordered 16-point leaves, SoA per leaf (x[16] y[16] z[16]); far sentinels pad the tail
     const int* tmpl_orig;    // [Tpad] original template index of every kd-ordered position (sentinels: INT_MAX)
     const uint4* nodes;      // [nnodes] depth-first BVH, 16 B each: fp16 AABB rounded OUTWARD (lo down, hi up) + link
                              //          (link >= 0: inner node, index of the first node after its subtree; link < 0: leaf ~link)
@@ -49,6 +56,12 @@ struct IcpArgs {
     // tree, so a search can start at the seed's leaf and work outwards instead of descending from the root.
     const unsigned short* sib;     // [nleaf][sib_max]
     int sib_on, sib_max, sib_bytes;
+    const unsigned short* orig16;  // [Tpad] original template index of every kd-ordered position as u16 (queued search; Tpad <= 65536)
+    NnTableView tab;               // nearest-neighbour candidate table of the template (nn_table.cuh); used when tmode = 1
+    int tmode;
+    int* miss;                     // [F][G][M] queries the table could not answer, per problem (visited by the BVH search afterwards)
+    unsigned long long* stats;     // developer counters (only written when compiled with -DCUBOID_ICP_STATS), else ignored
+    int qmode;                     // 1: queued outward search (needs resident template, sibling chains, orig16 and the per-warp scratch)
     const float* guesses;    // n_guess * (16 | 9) or NULL
     int n_guess, guess_mode;
     float4* cur;             // [F][G][M]
@@ -74,13 +87,14 @@ struct IcpArgs {
     int hashes;                // 1: accumulate corr_hash (parity tap); 0: leave it 0
 };
 
-constexpr int ICP_THREADS = 512;   // first 256 = the canonical reduction lanes; two CTAs (two ICP problems) share an SM
+constexpr int ICP_THREADS = 512;   // k_icp_init's CTA size
+constexpr int ICP_NT = 1024;       // k_icp's CTA size: one CTA per SM, 1024 / SUB sub-workers
 constexpr int ICP_LANES = 256;
-// A CTA of k_icp hosts ICP_THREADS / SUB independent sub-workers of SUB threads (template parameter, 256 or 512). A sub-worker
+// A CTA of k_icp hosts ICP_NT / SUB independent sub-workers of SUB threads (template parameter: 256, 512 or 1024). A sub-worker
 // serves its own problem and synchronises on its own named barrier; all share the CTA's one copy of the template and tree.
-// SUB = 256: four problems per SM instead of two - while one sits in its serial SVD or in a reduction the others keep the SM
-// busy (1024 VGA frames: 15.3 -> 14.5 ms). SUB = 512: all threads on one problem, for launches with fewer problems than
-// sub-workers (single frames, a few large clusters), where latency per problem is what counts. (4 x 128 threads: 18.1 ms.)
+// SUB = 256: four problems per SM - while one sits in its serial SVD or in a reduction the others keep the SM busy.
+// SUB = 512 / 1024: more threads per problem, for launches with fewer problems than sub-workers (sub-chunks, single frames),
+// where latency per problem is what counts. (128-thread sub-workers were measured slower: the reductions take twice the rounds.)
 template <int SUB>
 __device__ __forceinline__ void sub_sync(int sub) {   // literal barrier ids: a register id would reserve all 16 barriers
     switch (sub) {
@@ -291,6 +305,7 @@ struct IcpShared {
     float guess[16];
     int done, converged, state, iters;
     int task;           // dynamic task counter of the nearest-neighbour pass
+    int nmiss;          // queries of the current pass the candidate table could not answer
     double prev_mse;
 };
 
@@ -359,9 +374,102 @@ __device__ __forceinline__ void icp_scan_leaf(const IcpArgs& a, const float* tp,
     }
 }
 
+// ---- queued outward search: per-warp scratch in shared memory -----------------------------------------------------------
+constexpr int ICP_QCAP = 224;      // node work list entries per warp
+constexpr int ICP_QLEAF = 64;      // leaf work list entries per warp (a leaf round runs as soon as 32 are waiting)
+struct IcpWarpScr {
+    unsigned long long key[32];    // per query of the task: (bits of the best d2) << 32 | original index << 16 | kd position
+    float px[32], py[32], pz[32];  // the queries
+    unsigned int nodes[ICP_QCAP];  // (owner lane << 16) | node index: subtrees whose box may still hold a closer point
+    unsigned int leaves[ICP_QLEAF];// (owner lane << 16) | leaf index: leaves whose box survived, waiting for a full-warp scan
+};
+static_assert(sizeof(IcpWarpScr) % 16 == 0, "per-warp scratch keeps 16-byte alignment");
+
+// Brute-force scan of one 16-point leaf, branch-free: a tournament over the 16 distances carries the arg-min along.
+// Returns (bits of min d2) << 32 | original index << 16 | kd position. d2 >= +0, so its bit pattern orders like its value and
+// one 64-bit unsigned minimum over such keys is "lowest distance, then lowest ORIGINAL template index" - the canonical tie rule.
+// Two equal distances inside the leaf are rare (exact float ties); any equal pair met by the tournament sends the lane through
+// the exact loop below (false positives only cost time).
+__device__ __forceinline__ unsigned long long icp_leaf_key(const float* tp, const unsigned short* s_orig, int leaf, float sx, float sy, float sz) {
+    const float* lf = tp + (size_t)leaf * ICP_LEAF_FLOATS;
+    float d[ICP_LEAF];
+#pragma unroll
+    for (int jj = 0; jj < ICP_LEAF; jj += 4) {
+        const float4 X = *reinterpret_cast<const float4*>(lf + jj);
+        const float4 Y = *reinterpret_cast<const float4*>(lf + ICP_LEAF + jj);
+        const float4 Z = *reinterpret_cast<const float4*>(lf + 2 * ICP_LEAF + jj);
+        d[jj + 0] = dist2(sx, sy, sz, X.x, Y.x, Z.x);
+        d[jj + 1] = dist2(sx, sy, sz, X.y, Y.y, Z.y);
+        d[jj + 2] = dist2(sx, sy, sz, X.z, Y.z, Z.z);
+        d[jj + 3] = dist2(sx, sy, sz, X.w, Y.w, Z.w);
+    }
+    float m[ICP_LEAF];
+    int ix[ICP_LEAF];
+    bool tie = false;
+#pragma unroll
+    for (int k = 0; k < ICP_LEAF; ++k) { m[k] = d[k]; ix[k] = k; }
+#pragma unroll
+    for (int w = ICP_LEAF / 2; w >= 1; w >>= 1)
+#pragma unroll
+        for (int k = 0; k < w; ++k) {      // merge (2k, 2k+1): strict '<' keeps the lower kd position on equality
+            const float x = m[2 * k], y = m[2 * k + 1];
+            const bool lt = y < x;
+            tie = tie || (y == x);
+            m[k] = lt ? y : x;
+            ix[k] = lt ? ix[2 * k + 1] : ix[2 * k];
+        }
+    const float best = m[0];
+    int j = ix[0];
+    const int pbase = leaf * ICP_LEAF;
+    unsigned int o = s_orig[pbase + j];
+    if (tie) {   // exact: lowest original index among the points of this leaf at the minimal distance
+#pragma unroll
+        for (int q = 0; q < ICP_LEAF; ++q)
+            if (d[q] == best) {
+                const unsigned int oq = s_orig[pbase + q];
+                if (oq < o) { o = oq; j = q; }
+            }
+    }
+    return ((unsigned long long)__float_as_uint(best) << 32) | (unsigned long long)((o << 16) | (unsigned int)(pbase + j));
+}
+
+// Per-lane stackless walk of the depth-first node array [node, end) plus the sibling subtrees in `cand` (bit e = entry e of the
+// sibling chain sl), deepest first. Lanes reconverge before every leaf scan so the scans issue together.
+template <bool RESIDENT>
+__device__ __forceinline__ void icp_walk(const IcpArgs& a, const float* tp, const uint4* s_nodes, const unsigned short* sl, unsigned int cand,
+                                         int node, int end, bool cull, float sx, float sy, float sz, IcpBest& b, unsigned int& nleaf_eval) {
+    while (true) {
+        // every lane walks to its next surviving leaf
+        int leaf = -1;
+        while (true) {
+            if (node >= end) {
+                if (!cand) break;
+                const int e = __ffs(cand) - 1;
+                cand &= cand - 1u;
+                const int sn = sl[e];
+                const uint4 nd = s_nodes[sn];
+                if (node_lb(sx, sy, sz, nd) > b.d) continue;   // the minimum may have tightened since the lockstep test
+                const int link = (int)nd.w;
+                if (link < 0) { leaf = ~link; break; }           // the sibling is a leaf
+                node = sn + 1; end = link;
+                continue;
+            }
+            const uint4 nd = s_nodes[node];
+            const int link = (int)nd.w;
+            if (cull && node_lb(sx, sy, sz, nd) > b.d) { node = link >= 0 ? link : node + 1; continue; }
+            ++node;
+            if (link < 0) { leaf = ~link; break; }
+        }
+        // reconverge, so the leaf scans of all lanes issue together
+        if (!__any_sync(FULL_MASK, leaf >= 0)) break;
+        if (leaf >= 0) { ++nleaf_eval; icp_scan_leaf(a, tp, leaf, sx, sy, sz, b); }
+        __syncwarp();
+    }
+}
+
 // One nearest-neighbour pass over cur[0..S): writes corr[] (kd-ordered template position) and cd[].
-// On entry corr[] holds a valid template position per point (the previous pass's answer, or 0): its distance
-// seeds the running minimum so the culling is tight from the first node.
+// On entry corr[] holds a valid template position per point (the previous pass's answer, or any position): the search
+// starts there, so the running minimum is tight from the first box test.
 //
 // Exactness: a subtree is skipped only when lb > best (strict), so no subtree holding a minimiser or a tie is
 // ever skipped; among equal distances the LOWEST ORIGINAL template index wins - the answer of a brute-force
@@ -369,15 +477,22 @@ __device__ __forceinline__ void icp_scan_leaf(const IcpArgs& a, const float* tp,
 //
 // With sibling chains the search runs OUTWARDS from the seed: the seed's own leaf is scanned first, then the subtrees
 // hanging off the leaf's path to the root are box-tested by all lanes in lockstep (a fixed, divergence-free loop of
-// <= sib_max tests, about 9) and only the survivors are walked, deepest (= nearest) first. Leaf + those subtrees = the
-// whole tree, so nothing is left out. Once ICP has roughly aligned the clouds almost every sibling test fails and a
-// query costs ~9 box tests + 1.3 leaf scans instead of a ~20-node descent from the root whose lock-step cost is ~36.
-template <bool RESIDENT>
-__device__ __forceinline__ void icp_nn_pass(const IcpArgs& a, IcpShared& sh, const float* s_tmpl, const uint4* s_nodes, const float4* cur,
-                                            int S, const int* order, int* corr, float* cd, unsigned long long& evaluated) {
+// <= sib_max tests, about 9). Leaf + those subtrees = the whole tree, so nothing is left out. Once ICP has roughly aligned
+// the clouds almost every sibling test fails.
+//   QUEUED  the survivors of all 32 queries go on the warp's work list (IcpWarpScr) as (owner lane, node) items. The warp
+//           pops up to 32 items at a time: each lane box-tests ONE node against its owner's current minimum; surviving inner
+//           nodes push their two children, surviving leaves go on the leaf list, which is scanned 32 leaves at a time, each
+//           result merged into the owner's key by a 64-bit shared-memory atomicMin. Every instruction of the drain runs with
+//           (nearly) all lanes, however unevenly the survivors are spread over the queries - the per-lane walk below ran at
+//           4 of 32 lanes. A list that would overflow (queries still far from the template: many boxes survive) abandons the
+//           lists and finishes the task with the per-lane walk from the root, seeded with the best found so far.
+//   else    every lane walks its own survivors (icp_walk).
+template <bool RESIDENT, bool QUEUED>
+__device__ __forceinline__ void icp_nn_pass(const IcpArgs& a, IcpShared& sh, const float* s_tmpl, const uint4* s_nodes, const unsigned short* s_sib,
+                                            const unsigned short* s_orig, IcpWarpScr* wscr, const float4* cur, int S, const int* order, int* corr,
+                                            float* cd, unsigned long long& evaluated) {
     const int lane = threadIdx.x & 31;
     const float* tp = RESIDENT ? s_tmpl : a.tmpl;
-    const unsigned short* s_sib = reinterpret_cast<const unsigned short*>(s_tmpl + (size_t)a.Tpad * 3);
     const int ntask = (S + 31) / 32;
     const bool cull = a.cull != 0;
     const bool outward = RESIDENT && cull && a.sib_on;
@@ -392,14 +507,132 @@ __device__ __forceinline__ void icp_nn_pass(const IcpArgs& a, IcpShared& sh, con
         const int i = order[valid ? k : S - 1];   // 32 lanes = 32 spatial neighbours: coherent tree walks, broadcast loads
         const float4 p = __ldcg(cur + i);   // cur / corr / cd travel between SMs from one time slice to the next: read them at L2
         const float sx = p.x, sy = p.y, sz = p.z;
+        const int pos0 = __ldcg(corr + i);
+        unsigned int nleaf_eval = 0;
+        if (QUEUED) {
+            IcpWarpScr& ws = *wscr;
+            const int L = pos0 / ICP_LEAF;
+            const unsigned short* sl = s_sib + L * a.sib_max;
+            ++nleaf_eval;
+            unsigned long long key = icp_leaf_key(tp, s_orig, L, sx, sy, sz);
+            unsigned int cand = 0u;
+            {
+                const float bd = __uint_as_float((unsigned int)(key >> 32));
+                for (int e = 0; e < a.sib_max; ++e) {
+                    const unsigned int sn = sl[e];
+                    if (sn != 0xffffu && !(node_lb(sx, sy, sz, s_nodes[sn]) > bd)) cand |= 1u << e;
+                }
+            }
+            if (!valid) cand = 0u;   // padding lanes repeat the last query: no work-list items for them
+#ifdef CUBOID_ICP_STATS
+            unsigned int st_nr = 0, st_ni = 0, st_lr = 0, st_li = 0, st_q = 0, st_fb = 0, st_init = 0;
+#endif
+            if (__any_sync(FULL_MASK, cand != 0u)) {
+                const unsigned int lt_mask = (1u << lane) - 1u;
+                ws.key[lane] = key; ws.px[lane] = sx; ws.py[lane] = sy; ws.pz[lane] = sz;
+                const int cnt = __popc(cand);
+                const int incl = warp_incl_scan(cnt, lane);
+                const int total = __shfl_sync(FULL_MASK, incl, 31);
+                bool fallback = total > ICP_QCAP;
+#ifdef CUBOID_ICP_STATS
+                st_q = 1; st_init = (unsigned int)total;
+#endif
+                if (!fallback) {
+                    int off = incl - cnt;
+                    for (unsigned int c2 = cand; c2; c2 &= c2 - 1u) ws.nodes[off++] = ((unsigned int)lane << 16) | (unsigned int)sl[__ffs(c2) - 1];
+                    __syncwarp();
+                    int n = total, nl = 0;
+                    while (true) {
+                        if (nl >= 32 || (n == 0 && nl > 0)) {
+                            // leaf round: up to 32 waiting leaves, one per lane, whoever owns them
+                            const int take = min(nl, 32);
+                            const bool has = lane < take;
+#ifdef CUBOID_ICP_STATS
+                            ++st_lr; st_li += take;
+#endif
+                            const unsigned int item = ws.leaves[nl - take + (has ? lane : 0)];
+                            nl -= take;
+                            const int owner = (int)(item >> 16), leaf = (int)(item & 0xffffu);
+                            const unsigned long long k2 = icp_leaf_key(tp, s_orig, leaf, ws.px[owner], ws.py[owner], ws.pz[owner]);
+                            if (has) {
+                                ++nleaf_eval;
+                                if (k2 < ws.key[owner]) atomicMin(&ws.key[owner], k2);
+                            }
+                            __syncwarp();
+                            continue;
+                        }
+                        if (n == 0) break;
+                        // node round: up to 32 waiting subtrees, one box test per lane against the owner's current minimum
+                        const int take = min(n, 32);
+                        const bool has = lane < take;
+#ifdef CUBOID_ICP_STATS
+                        ++st_nr; st_ni += take;
+#endif
+                        const unsigned int item = ws.nodes[n - take + (has ? lane : 0)];
+                        n -= take;
+                        __syncwarp();   // every lane holds its item before the pushes below reuse the popped entries
+                        const int owner = (int)(item >> 16), node = (int)(item & 0xffffu);
+                        const uint4 nd = s_nodes[node];
+                        const float bd = __uint_as_float((unsigned int)(ws.key[owner] >> 32));
+                        const bool alive = has && !(node_lb(ws.px[owner], ws.py[owner], ws.pz[owner], nd) > bd);
+                        const int link = (int)nd.w;
+                        const bool isleaf = alive && link < 0, inner = alive && link >= 0;
+                        const unsigned int lm = __ballot_sync(FULL_MASK, isleaf), im = __ballot_sync(FULL_MASK, inner);
+                        if (isleaf) ws.leaves[nl + __popc(lm & lt_mask)] = ((unsigned int)owner << 16) | (unsigned int)(~link);
+                        nl += __popc(lm);
+                        const int ni = __popc(im);
+                        if (n + 2 * ni > ICP_QCAP) { fallback = true; break; }   // warp-uniform
+                        if (inner) {
+                            // depth-first layout: left child = node + 1, right child = the first node after the left subtree
+                            const int lw = (int)s_nodes[node + 1].w;
+                            const int right = lw >= 0 ? lw : node + 2;
+                            const int r = n + 2 * __popc(im & lt_mask);
+                            ws.nodes[r] = ((unsigned int)owner << 16) | (unsigned int)right;
+                            ws.nodes[r + 1] = ((unsigned int)owner << 16) | (unsigned int)(node + 1);
+                        }
+                        n += 2 * ni;
+                        __syncwarp();
+                    }
+                }
+                __syncwarp();
+                key = ws.key[lane];
+                __syncwarp();   // the scratch is rewritten by the next task
+#ifdef CUBOID_ICP_STATS
+                st_fb = fallback ? 1 : 0;
+#endif
+                if (fallback) {
+#ifdef CUBOID_ICP_STATS
+                    if (lane == 0 && a.stats) { atomicAdd(&a.stats[0], 1ull); atomicAdd(&a.stats[1], 1ull); atomicAdd(&a.stats[2], 1ull); atomicAdd(&a.stats[3], st_nr);
+                        atomicAdd(&a.stats[4], st_ni); atomicAdd(&a.stats[5], st_lr); atomicAdd(&a.stats[6], st_li); atomicAdd(&a.stats[7], st_init); }
+#endif
+                    // queries still far from the template: finish with the per-lane walk over the whole tree, seeded with the best so far
+                    IcpBest b;
+                    b.d = __uint_as_float((unsigned int)(key >> 32));
+                    b.pos = (int)((unsigned int)key & 0xffffu);
+                    b.orig = (int)(((unsigned int)key >> 16) & 0xffffu);
+                    icp_walk<RESIDENT>(a, tp, s_nodes, s_sib, 0u, 0, nnodes, true, sx, sy, sz, b, nleaf_eval);
+                    if (valid) { corr[i] = b.pos; cd[i] = b.d; }
+                    evaluated += (unsigned long long)nleaf_eval * ICP_LEAF;
+                    continue;
+                }
+            }
+#ifdef CUBOID_ICP_STATS
+            if (lane == 0 && a.stats) { atomicAdd(&a.stats[0], 1ull); atomicAdd(&a.stats[1], st_q); atomicAdd(&a.stats[3], st_nr);
+                atomicAdd(&a.stats[4], st_ni); atomicAdd(&a.stats[5], st_lr); atomicAdd(&a.stats[6], st_li); atomicAdd(&a.stats[7], st_init);
+                atomicAdd(&a.stats[8 + min(st_nr, 21u)], 1ull); }
+            (void)st_fb;
+#endif
+            evaluated += (unsigned long long)nleaf_eval * ICP_LEAF;
+            if (valid) { corr[i] = (int)((unsigned int)key & 0xffffu); cd[i] = __uint_as_float((unsigned int)(key >> 32)); }
+            continue;
+        }
         IcpBest b;
-        b.pos = __ldcg(corr + i);
+        b.pos = pos0;
         b.orig = -1;
         {
             const float3 t = tmpl_point(tp, b.pos);
             b.d = dist2(sx, sy, sz, t.x, t.y, t.z);
         }
-        unsigned int nleaf_eval = 0;
         int node = 0, end = nnodes;           // [node, end): the part of the depth-first node array still to walk
         unsigned int cand = 0u;               // sibling subtrees whose box survived the lockstep test, not walked yet
         const unsigned short* sl = s_sib;
@@ -414,35 +647,70 @@ __device__ __forceinline__ void icp_nn_pass(const IcpArgs& a, IcpShared& sh, con
             }
             node = 0; end = 0;                // nothing to walk until a surviving sibling is opened
         }
-        while (true) {
-            // every lane walks to its next surviving leaf
-            int leaf = -1;
-            while (true) {
-                if (node >= end) {
-                    if (!cand) break;
-                    const int e = __ffs(cand) - 1;
-                    cand &= cand - 1u;
-                    const int sn = sl[e];
-                    const uint4 nd = s_nodes[sn];
-                    if (node_lb(sx, sy, sz, nd) > b.d) continue;   // the minimum may have tightened since the lockstep test
-                    const int link = (int)nd.w;
-                    if (link < 0) { leaf = ~link; break; }           // the sibling is a leaf
-                    node = sn + 1; end = link;
-                    continue;
-                }
-                const uint4 nd = s_nodes[node];
-                const int link = (int)nd.w;
-                if (cull && node_lb(sx, sy, sz, nd) > b.d) { node = link >= 0 ? link : node + 1; continue; }
-                ++node;
-                if (link < 0) { leaf = ~link; break; }
-            }
-            // reconverge, so the leaf scans of all lanes issue together
-            if (!__any_sync(FULL_MASK, leaf >= 0)) break;
-            if (leaf >= 0) { ++nleaf_eval; icp_scan_leaf(a, tp, leaf, sx, sy, sz, b); }
-            __syncwarp();
-        }
+        icp_walk<RESIDENT>(a, tp, s_nodes, sl, cand, node, end, cull, sx, sy, sz, b, nleaf_eval);
         evaluated += (unsigned long long)nleaf_eval * ICP_LEAF;
         if (valid) { corr[i] = b.pos; cd[i] = b.d; }
+    }
+}
+
+// Table pass of the nearest-neighbour search (nn_table.cuh): every query whose grid cell has a valid record scans the record's
+// <= 15 candidates (sorted by original index, strict '<': the canonical tie rule) and is done; the others are appended to the
+// problem's miss list, which the BVH search (icp_nn_pass) then visits instead of `order`.
+__device__ __forceinline__ void icp_nn_table_pass(const IcpArgs& a, IcpShared& sh, const float* tp, const float4* cur, int S, const int* order,
+                                                  int* corr, float* cd, int* miss, unsigned long long& evaluated) {
+    const int lane = threadIdx.x & 31;
+    const int ntask = (S + 31) / 32;
+    const NnTableView& T = a.tab;
+    const unsigned int lt_mask = (1u << lane) - 1u;
+    while (true) {
+        int task = 0;
+        if (lane == 0) task = atomicAdd(&sh.task, 1);
+        task = __shfl_sync(FULL_MASK, task, 0);
+        if (task >= ntask) break;
+        const int k = task * 32 + lane;
+        const bool valid = k < S;
+        const int i = order[valid ? k : S - 1];
+        const float4 p = __ldcg(cur + i);
+        const float sx = p.x, sy = p.y, sz = p.z;
+        const float fx = (sx - T.org[0]) * T.inv_h, fy = (sy - T.org[1]) * T.inv_h, fz = (sz - T.org[2]) * T.inv_h;
+        const bool inside = valid && fx >= 0.f && fx < (float)T.nx && fy >= 0.f && fy < (float)T.ny && fz >= 0.f && fz < (float)T.nz;
+        unsigned int R[8] = {0xffffu, 0u, 0u, 0u, 0u, 0u, 0u, 0u};
+        if (inside) {
+            const size_t cell = ((size_t)(int)fz * T.ny + (size_t)(int)fy) * T.nx + (size_t)(int)fx;   // fx >= 0: truncation = floor
+            const uint4 r0 = __ldg(T.rec + 2 * cell), r1 = __ldg(T.rec + 2 * cell + 1);
+            R[0] = r0.x; R[1] = r0.y; R[2] = r0.z; R[3] = r0.w; R[4] = r1.x; R[5] = r1.y; R[6] = r1.z; R[7] = r1.w;
+        }
+        const unsigned int nrec = R[0] & 0xffffu;
+        const bool hit = nrec != 0xffffu;
+        const int n = hit ? (int)nrec : 0;
+        float bd = __uint_as_float(0x7f800000u);
+        int bpos = 0;
+#pragma unroll
+        for (int c = 0; c < NNT_K; ++c) {
+            if (c > 0 && (c & 3) == 0 && !__any_sync(FULL_MASK, c < n)) break;
+            const unsigned int word = R[(c + 1) >> 1];
+            const int pos = (int)(((c + 1) & 1) ? (word >> 16) : (word & 0xffffu));
+            if (c < n) {
+                const float3 t = tmpl_point(tp, pos);
+                const float d = dist2(sx, sy, sz, t.x, t.y, t.z);
+                if (d < bd) { bd = d; bpos = pos; }
+            }
+        }
+        evaluated += (unsigned long long)n;
+#ifdef CUBOID_ICP_STATS
+        {
+            const unsigned int hm = __ballot_sync(FULL_MASK, hit), vm = __ballot_sync(FULL_MASK, valid);
+            if (lane == 0 && a.stats) { atomicAdd(&a.stats[30], (unsigned long long)__popc(hm)); atomicAdd(&a.stats[31], (unsigned long long)__popc(vm)); }
+        }
+#endif
+        if (hit) { corr[i] = bpos; cd[i] = bd; }
+        const unsigned int mm = __ballot_sync(FULL_MASK, valid && !hit);
+        if (mm) {
+            int base = 0;
+            if (lane == 0) base = atomicAdd(&sh.nmiss, __popc(mm));
+            base = __shfl_sync(FULL_MASK, base, 0);
+            if (valid && !hit) miss[base + __popc(mm & lt_mask)] = i;
+        }
     }
 }
 
@@ -641,8 +909,9 @@ __global__ void __launch_bounds__(ICP_THREADS) k_icp_init(const IcpArgs a) {
 
 // One time slice of one problem: up to a.slice_iters iterations of the ICP loop, then either the closing fitness pass
 // (problem finished) or a state save (problem goes back on the queue).
-template <bool RESIDENT, int SUB>
-__device__ __forceinline__ bool icp_slice(const IcpArgs& a, IcpShared& sh, const float* s_tmpl, const uint4* s_nodes, int prob, int tid, int sub,
+template <bool RESIDENT, bool QUEUED, bool TABLE, int SUB>
+__device__ __forceinline__ bool icp_slice(const IcpArgs& a, IcpShared& sh, const float* s_tmpl, const uint4* s_nodes, const unsigned short* s_sib,
+                                          const unsigned short* s_orig, IcpWarpScr* wscr, int prob, int tid, int sub,
                                           unsigned long long* s_hh, unsigned long long* s_ev) {
     const int g = prob % a.n_guess, c = (prob / a.n_guess) % CUBOID_MAX_CLUSTERS, f = prob / (a.n_guess * CUBOID_MAX_CLUSTERS);
     const int* offsets = a.offsets + (size_t)f * (a.KC + 1);
@@ -654,6 +923,7 @@ __device__ __forceinline__ bool icp_slice(const IcpArgs& a, IcpShared& sh, const
     int* corr = a.corr + pbase;
     float* cd = a.cd + pbase;
     const int* order = a.order + pbase;
+    int* miss = TABLE ? a.miss + pbase : nullptr;
     IcpState& ps = a.pstate[prob];
     const bool trace = a.corr_trace && f == 0 && c == 0 && g == 0;
     const float* tp = RESIDENT ? s_tmpl : a.tmpl;
@@ -664,7 +934,7 @@ __device__ __forceinline__ bool icp_slice(const IcpArgs& a, IcpShared& sh, const
     if (tid == 0) {
         sh.done = __ldcg(&ps.done); sh.converged = __ldcg(&ps.converged); sh.state = __ldcg(&ps.state); sh.iters = __ldcg(&ps.it);
         sh.prev_mse = __ldcg(&ps.prev_mse);
-        sh.task = 0;
+        sh.task = 0; sh.nmiss = 0;
     }
     sub_sync<SUB>(sub);
     unsigned long long chash = 0, evaluated = 0;
@@ -675,7 +945,7 @@ __device__ __forceinline__ bool icp_slice(const IcpArgs& a, IcpShared& sh, const
         // First pass of a problem: every seed is template position 0, i.e. no bound at all, and the cloud is typically far from
         // the template, so each query would walk most of the tree. Search the first warp's worth of queries properly, then hand
         // the answer of one of them to everybody as the seed: any valid template position is a valid seed, results are unchanged.
-        icp_nn_pass<RESIDENT>(a, sh, s_tmpl, s_nodes, cur, 32, order, corr, cd, evaluated);
+        icp_nn_pass<RESIDENT, QUEUED>(a, sh, s_tmpl, s_nodes, s_sib, s_orig, wscr, cur, 32, order, corr, cd, evaluated);
         sub_sync<SUB>(sub);
         if (tid == 0) sh.task = 0;
         const int seed = __ldcg(corr + order[0]);
@@ -684,8 +954,18 @@ __device__ __forceinline__ bool icp_slice(const IcpArgs& a, IcpShared& sh, const
         sub_sync<SUB>(sub);
     }
     while (!sh.done && it < it_end) {
-        // 1. correspondences
-        icp_nn_pass<RESIDENT>(a, sh, s_tmpl, s_nodes, cur, S, order, corr, cd, evaluated);
+        // 1. correspondences: the candidate table answers the queries close to the template, the BVH search the rest
+        if (TABLE) {
+            icp_nn_table_pass(a, sh, tp, cur, S, order, corr, cd, miss, evaluated);
+            sub_sync<SUB>(sub);
+            const int nm = sh.nmiss;
+            if (tid == 0) sh.task = 0;
+            sub_sync<SUB>(sub);
+            if (tid == 0) sh.nmiss = 0;
+            if (nm > 0) icp_nn_pass<RESIDENT, QUEUED>(a, sh, s_tmpl, s_nodes, s_sib, s_orig, wscr, cur, nm, miss, corr, cd, evaluated);
+        } else {
+            icp_nn_pass<RESIDENT, QUEUED>(a, sh, s_tmpl, s_nodes, s_sib, s_orig, wscr, cur, S, order, corr, cd, evaluated);
+        }
         ++passes;
         sub_sync<SUB>(sub);
         if (tid == 0) sh.task = 0;
@@ -794,7 +1074,17 @@ __device__ __forceinline__ bool icp_slice(const IcpArgs& a, IcpShared& sh, const
         for (int i = tid; i < S; i += SUB) cur[i] = xform(sh.fin, src[idx[i]]);
         sub_sync<SUB>(sub);
         if (S > 0) {
-            icp_nn_pass<RESIDENT>(a, sh, s_tmpl, s_nodes, cur, S, order, corr, cd, evaluated);
+            if (TABLE) {
+                icp_nn_table_pass(a, sh, tp, cur, S, order, corr, cd, miss, evaluated);
+                sub_sync<SUB>(sub);
+                const int nm = sh.nmiss;
+                if (tid == 0) sh.task = 0;
+                sub_sync<SUB>(sub);
+                if (tid == 0) sh.nmiss = 0;
+                if (nm > 0) icp_nn_pass<RESIDENT, QUEUED>(a, sh, s_tmpl, s_nodes, s_sib, s_orig, wscr, cur, nm, miss, corr, cd, evaluated);
+            } else {
+                icp_nn_pass<RESIDENT, QUEUED>(a, sh, s_tmpl, s_nodes, s_sib, s_orig, wscr, cur, S, order, corr, cd, evaluated);
+            }
             ++passes;
             sub_sync<SUB>(sub);
             for (int set = 0; set < LPT; ++set) {
@@ -837,33 +1127,43 @@ __device__ __forceinline__ bool icp_slice(const IcpArgs& a, IcpShared& sh, const
     return finished;
 }
 
-// Persistent worker: stages the BVH (and the template, if it fits) in shared memory ONCE, then serves time slices of
-// whatever problem is next on the queue until every problem of the launch is finished. Slicing bounds the tail: without
-// it the kernel ends when the problem with the most iterations (40 .. 150 here) ends, with most SMs idle by then.
-template <int SUB>
-__global__ void __launch_bounds__(ICP_THREADS, 2) k_icp(const IcpArgs a) {
-    constexpr int NSUB = ICP_THREADS / SUB;
+// Persistent worker: stages the BVH (and, if they fit, the template, the sibling chains and the original-index table) in shared
+// memory ONCE, then serves time slices of whatever problem is next on the queue until every problem of the launch is finished.
+// Slicing bounds the tail: without it the kernel ends when the problem with the most iterations (40 .. 150 here) ends, with
+// most SMs idle by then. MODE 0: nodes only in shared memory (template through L1/L2); 1: resident template, per-lane walk;
+// 2: resident template + queued outward search (icp_nn_pass); 3: 2 + the nearest-neighbour candidate table in front of it.
+template <int SUB, int MODE>
+__global__ void __launch_bounds__(ICP_NT, 1) k_icp(const IcpArgs a) {
+    constexpr int NSUB = ICP_NT / SUB;
     extern __shared__ __align__(128) unsigned char smem_raw[];
     __shared__ IcpShared shs[NSUB];
     __shared__ int s_prob[NSUB];
     __shared__ unsigned long long s_hh[NSUB][SUB / 32], s_ev[NSUB][SUB / 32];
-    // dynamic shared memory: [BVH nodes (nnodes x 16 B)] [template SoA leaves (Tpad*3 floats)] [sibling chains] (the last two: resident case)
+    // dynamic shared memory: [BVH nodes (nnodes x 16 B)] [template SoA leaves (Tpad*3 floats)] [sibling chains] [orig16 (Tpad u16)]
+    // [per-warp scratch x 32]   (everything after the nodes: resident modes; the last two: MODE 2)
     uint4* s_nodes = reinterpret_cast<uint4*>(smem_raw);
     float* s_tmpl = reinterpret_cast<float*>(s_nodes + a.nnodes);
+    const unsigned int tb = MODE >= 1 ? (unsigned int)a.Tpad * 12u : 0u;
+    const unsigned int bb = (unsigned int)a.nnodes * 16u;
+    const unsigned int sb = (MODE >= 1 && a.sib_on) ? (unsigned int)a.sib_bytes : 0u;
+    const unsigned int ob = MODE >= 2 ? (unsigned int)a.Tpad * 2u : 0u;
+    const unsigned short* s_sib = reinterpret_cast<const unsigned short*>(reinterpret_cast<unsigned char*>(s_tmpl) + tb);
+    const unsigned short* s_orig = reinterpret_cast<const unsigned short*>(reinterpret_cast<unsigned char*>(s_tmpl) + tb + sb);
+    IcpWarpScr* s_wscr = reinterpret_cast<IcpWarpScr*>(reinterpret_cast<unsigned char*>(s_tmpl) + tb + sb + ob);
     if (threadIdx.x == 0) {
         mbar_init(&shs[0].bar, 1);
         asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
     }
     __syncthreads();
     if (threadIdx.x == 0) {
-        const unsigned int tb = a.resident ? (unsigned int)a.Tpad * 12u : 0u;
-        const unsigned int bb = (unsigned int)a.nnodes * 16u;
-        const unsigned int sb = (a.resident && a.sib_on) ? (unsigned int)a.sib_bytes : 0u;
-        mbar_expect_tx(&shs[0].bar, tb + bb + sb);
+        mbar_expect_tx(&shs[0].bar, tb + bb + sb + ob);
+        unsigned char* t8 = reinterpret_cast<unsigned char*>(s_tmpl);
+        for (unsigned int off = 0; off < ob; off += 32768u)
+            tma_bulk_g2s(t8 + tb + sb + off, reinterpret_cast<const unsigned char*>(a.orig16) + off, min(32768u, ob - off), &shs[0].bar);
         for (unsigned int off = 0; off < sb; off += 32768u)
-            tma_bulk_g2s(reinterpret_cast<unsigned char*>(s_tmpl) + tb + off, reinterpret_cast<const unsigned char*>(a.sib) + off, min(32768u, sb - off), &shs[0].bar);
+            tma_bulk_g2s(t8 + tb + off, reinterpret_cast<const unsigned char*>(a.sib) + off, min(32768u, sb - off), &shs[0].bar);
         for (unsigned int off = 0; off < tb; off += 32768u)
-            tma_bulk_g2s(reinterpret_cast<unsigned char*>(s_tmpl) + off, reinterpret_cast<const unsigned char*>(a.tmpl) + off, min(32768u, tb - off), &shs[0].bar);
+            tma_bulk_g2s(t8 + off, reinterpret_cast<const unsigned char*>(a.tmpl) + off, min(32768u, tb - off), &shs[0].bar);
         for (unsigned int off = 0; off < bb; off += 32768u)
             tma_bulk_g2s(reinterpret_cast<unsigned char*>(s_nodes) + off, reinterpret_cast<const unsigned char*>(a.nodes) + off, min(32768u, bb - off), &shs[0].bar);
     }
@@ -872,13 +1172,13 @@ __global__ void __launch_bounds__(ICP_THREADS, 2) k_icp(const IcpArgs a) {
     // from here on the sub-workers go their own ways
     const int sub = threadIdx.x / SUB, tid = threadIdx.x % SUB;
     IcpShared& sh = shs[sub];
+    IcpWarpScr* wscr = s_wscr + (threadIdx.x >> 5);
     while (true) {
         if (tid == 0) s_prob[sub] = icp_queue_pop(a.queue, a.ring, a.n_slots);
         sub_sync<SUB>(sub);
         const int prob = s_prob[sub];
         if (prob < 0) break;
-        const bool finished = a.resident ? icp_slice<true, SUB>(a, sh, s_tmpl, s_nodes, prob, tid, sub, s_hh[sub], s_ev[sub])
-                                         : icp_slice<false, SUB>(a, sh, s_tmpl, s_nodes, prob, tid, sub, s_hh[sub], s_ev[sub]);
+        const bool finished = icp_slice<(MODE >= 1), (MODE >= 2), (MODE == 3), SUB>(a, sh, s_tmpl, s_nodes, s_sib, s_orig, wscr, prob, tid, sub, s_hh[sub], s_ev[sub]);
         if (tid == 0) {
             __threadfence();   // state / outputs before the hand-over
             if (finished) atomicAdd(&a.queue->n_done, 1);
@@ -889,8 +1189,7 @@ __global__ void __launch_bounds__(ICP_THREADS, 2) k_icp(const IcpArgs a) {
 }
 
 // best guess per (frame, cluster): lowest fitness, ties -> lowest guess id; fills cuboid_cluster_result
-__global__ void k_icp_select(const IcpOut* out, cuboid_frame_result* res, int n_frames, int n_guess, double gate,
-                             const float4* cur, int M, const int* offsets, int KC, float4* aligned_out) {
+__global__ void k_icp_select(const IcpOut* out, cuboid_frame_result* res, int n_frames, int n_guess, double gate) {
     const int t = blockIdx.x * blockDim.x + threadIdx.x;
     const int f = t / CUBOID_MAX_CLUSTERS, c = t % CUBOID_MAX_CLUSTERS;
     if (f >= n_frames) return;
@@ -908,11 +1207,14 @@ __global__ void k_icp_select(const IcpOut* out, cuboid_frame_result* res, int n_
     C.accepted = (o[bg].converged && o[bg].fitness < gate) ? 1 : 0;
     for (int k = 0; k < 16; ++k) C.T[k] = o[bg].T[k];
     C.corr_hash = o[bg].corr_hash;
-    if (aligned_out && f == 0 && c == 0) {   // single-problem API: hand back the aligned cloud of the winner
-        const int o0 = offsets[0], S = offsets[1] - o0;
-        const float4* src = cur + ((size_t)f * n_guess + bg) * M + o0;
-        for (int i = 0; i < S; ++i) aligned_out[i] = src[i];
-    }
+}
+// single-problem API (cuboid_icp): hand back the aligned cloud of the winning guess of (frame 0, cluster 0)
+__global__ void k_icp_aligned(const cuboid_frame_result* res, const float4* cur, int M, const int* offsets, float4* aligned_out) {
+    if (res[0].n_clusters < 1) return;
+    const int bg = res[0].cluster[0].best_guess;
+    const int o0 = offsets[0], S = offsets[1] - o0;
+    const float4* src = cur + (size_t)bg * M + o0;
+    for (int i = blockIdx.x * blockDim.x + threadIdx.x; i < S; i += gridDim.x * blockDim.x) aligned_out[i] = src[i];
 }
 
 }  // namespace cuboid

@@ -525,11 +525,12 @@ def test_icp_on_the_reference_real_scan_returns_the_published_pose(golden, param
     assert far["iters"] == ref_far["iters"] and far["corr_hash"] == ref_far["corr_hash"] and np.array_equal(bits(far["T"]), bits(ref_far["T"]))
 
 
-@pytest.mark.parametrize("knob,values", [("CUBOID_ICP_NSUB", ("1", "2")), ("CUBOID_ICP_SLICE", ("1", "8", "5000")),
-                                         ("CUBOID_ICP_OUTWARD", ("0", "1")), ("CUBOID_PIPELINE", ("0", "1"))])
+@pytest.mark.parametrize("knob,values", [("CUBOID_ICP_NSUB", ("1", "2", "4")), ("CUBOID_ICP_SLICE", ("1", "8", "5000")),
+                                         ("CUBOID_ICP_OUTWARD", ("0", "1")), ("CUBOID_ICP_QUEUED", ("0", "1")), ("CUBOID_ICP_TABLE", ("0", "1")), ("CUBOID_NNT_H_MM", ("0.7", "2.5")),
+                                         ("CUBOID_PIPELINE", ("0", "1"))])
 def test_execution_knobs_do_not_change_results(tmpl30, params, knob, values, monkeypatch):
     """How the work is scheduled must never show in the results: sub-workers per CTA, iterations per time slice, outward search
-    vs descent from the root, pipelined sub-chunks vs one chunk - every result byte of a 40-frame batch is the same."""
+    vs descent from the root, queued (work-list) vs per-lane walk of the surviving subtrees, pipelined sub-chunks vs one chunk - every result byte of a 40-frame batch is the same."""
     depth = np.concatenate([synth.depth_batch("bench", list(range(60, 96))), synth.depth_batch("tallbox", [0, 1]),
                             np.zeros((2, 480, 640), np.uint16)])
     out = []

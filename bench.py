@@ -510,6 +510,79 @@ def summarize(m, world):
     }
 
 
+def run_hypothesis_sharded(args, local_rank, rank, world, torch, dist):
+    """SURVEY.md 8e, second axis: the hypotheses of every cluster are split over the GPUs. A step = cuboid_process_batch on the
+    (same) host frames with this rank's slice of the hypotheses + one all_gather of cuboid_guess_record + the exact arg-min.
+    Timed with a barrier on both sides, max over ranks; with --frames 1 the step time is the single-frame latency."""
+    from perception_b200 import api
+    from perception_b200 import dist as pd
+    from perception_b200.params import default_params
+    wl = WORKLOADS[args.workload]
+    if wl["n_guess"] < 2:
+        raise SystemExit("--shard hypotheses needs a workload with several hypotheses (--workload guess64)")
+    Wd, Ht, F = wl["w"], wl["h"], args.frames
+    p = default_params(wl["variant"])
+    rots = guess_rotations()
+    p.n_guess, p.guess_mode = len(rots), 1
+    tm = template()
+    frames = make_frames(F, 0, wl["kind"])                       # the same frames on every rank
+    host = torch.empty((F, Ht, Wd), dtype=torch.uint16, pin_memory=True)
+    host.numpy()[...] = frames
+    g0, cnt = pd.shard_range(len(rots), rank, world)
+    cc = api.CuboidCuda(p, device=local_rank, max_points=Wd * Ht, max_batch=min(args.chunk, F))
+    cc.set_template(0, tm)
+    cc.set_guesses(rots[g0:g0 + cnt], mode=1)
+    cc.set_guess_offset(g0)
+    cc.set_option(api.OPT_TAPS, 0)
+    cc.set_option(api.OPT_STAGES, wl["stages"])
+
+    def barrier():
+        torch.cuda.synchronize()
+        if world > 1:
+            dist.barrier()
+        torch.cuda.synchronize()
+
+    sampler = ClockSampler(local_rank)
+    sampler.start()
+    for _ in range(args.warmup):
+        res = pd.reduce_hypotheses(cc.process_batch(host), p.icp_fitness_gate)
+    barrier()
+    l0 = cc.launch_count()
+    times = []
+    w0 = time.perf_counter()
+    for _ in range(args.steps):
+        t0 = time.perf_counter()
+        res = pd.reduce_hypotheses(cc.process_batch(host), p.icp_fitness_gate)
+        times.append(time.perf_counter() - t0)
+    barrier()
+    wall = time.perf_counter() - w0
+    launches = cc.launch_count() - l0
+    clocks = sampler.stop(w0, w0 + wall)
+    t = wall
+    if world > 1:
+        tt = torch.tensor([wall], dtype=torch.float64, device="cuda")
+        dist.all_reduce(tt, op=dist.ReduceOp.MAX)
+        t = float(tt.item())
+    import hashlib
+    digest = hashlib.sha256(b"".join(bytes(r) for r in res)).hexdigest()[:16]
+    if rank == 0:
+        import ctypes as C
+        from perception_b200.params import FrameResult
+        line = {"metric": METRIC, "value": F * args.steps / t, "unit": "frames/s", "n_gpus": world, "steps": args.steps, "warmup": args.warmup,
+                "ms_per_step": 1e3 * t / args.steps, "higher_is_better": True, "scaling": "strong", "vs_baseline": None, "dtype": "f32",
+                "data": "synthetic", "config": dict(workload_config(args, F), parallelism="every GPU runs the same %d frame(s) with %d of the %d "
+                "initial-pose hypotheses per cluster; one all_gather of 80-byte records per step, exact (fitness, guess id) arg-min" % (F, cnt, len(rots))),
+                "clocks": clocks, "gpu_launches": int(launches),
+                "e2e": {"value": F * args.steps / t, "unit": "frames/s", "h2d_bytes_per_step": F * Wd * Ht * 2, "d2h_bytes_per_step": F * C.sizeof(FrameResult),
+                        "note": "the timed step IS the end-to-end call: pinned host depth in, results to host, records all-gathered over %s" % ("NCCL" if world > 1 else "nothing (1 GPU)")},
+                "latency_ms": {"p50": 1e3 * float(np.percentile(times, 50)), "max": 1e3 * float(np.max(times)), "frames_per_step": F},
+                "results_digest": digest,
+                "frame_stats": {"best_guess_frame0": int(res[0].cluster[0].best_guess) if res[0].n_clusters else None,
+                                "fitness_frame0": float(res[0].cluster[0].fitness) if res[0].n_clusters else None}}
+        print(json.dumps(line), flush=True)
+    cc.close()
+
+
 def _profile_json(name):
     try:
         return json.load(open(os.path.join(ROOT, "profiles", name)))
@@ -536,6 +609,10 @@ def main():
     ap.add_argument("--e2e-handles", type=int, default=3,
                     help="library handles (one host thread each) the end-to-end loop spreads its steps over; 1 = strictly serial calls")
     ap.add_argument("--workload", default="full", choices=sorted(WORKLOADS))
+    ap.add_argument("--shard", default="frames", choices=["frames", "hypotheses"],
+                    help="frames: every rank takes its own block of frames (weak scaling, the default); hypotheses: every rank runs the "
+                         "SAME frames with its slice of the initial-pose hypotheses and one all-gather of 80-byte records picks the winner "
+                         "(strong scaling / single-frame latency; use with --workload guess64)")
     args = ap.parse_args()
     global W, H
     wl = WORKLOADS[args.workload]
@@ -564,6 +641,12 @@ def main():
         dist.init_process_group("nccl", device_id=torch.device("cuda", local_rank))
 
     F = args.frames
+    if args.shard == "hypotheses":
+        run_hypothesis_sharded(args, local_rank, rank, world, torch, dist)
+        if world > 1:
+            dist.barrier()
+            dist.destroy_process_group()
+        return
     m = measure(args, args.workload, F, args.chunk, args.steps, args.warmup, args.e2e_handles, local_rank, rank, world, torch, dist,
                 with_ceiling=True)
     cc, res, tm, p, frames, rots, stage = m.cc, m.res, m.tm, m.p, m.frames, m.rots, m.stage

@@ -227,9 +227,27 @@ typedef struct {
 int cuboid_select_object(const cuboid_frame_result* frame, int template_points, double icp_fitness_score,
                          cuboid_object_selection* out);
 
-/* ---- multi-GPU (frames sharded by the caller) ------------------------------- */
-/* Packs (fitness, guess id) into one ordered 64-bit key so a single NCCL/gloo MIN all-reduce picks
- * the winner with the lowest-guess tie-break, independent of the GPU count. */
+/* ---- multi-GPU -------------------------------------------------------------------
+ * Frames are independent: the caller shards them over GPUs (one handle per GPU), no exchange step exists.
+ * Second axis, for single-frame latency: the n_guess initial-pose hypotheses of every cluster (icp.cpp:165-178 runs ONE; the
+ * hypotheses are north_star's extension) are split over the GPUs. Rank r uploads its slice [g0, g1) with cuboid_set_guesses,
+ * declares g0 with cuboid_set_guess_offset (best_guess in every result then carries GLOBAL ids), runs the same frame, turns
+ * every (frame, cluster) result into an 80-byte record, all-gathers the records (ncclAllGather / MPI / torch.distributed —
+ * the library does not link a communication library) and calls cuboid_reduce_guess_records on the gathered array.
+ * The winner is the lexicographic minimum of (fitness, guess id) on the exact double: identical for 1, 2, 4, 8 GPUs. */
+typedef struct {
+    double fitness;          /* icp.getFitnessScore() of this rank's best hypothesis for the cluster */
+    int32_t guess_id;        /* global hypothesis id */
+    int32_t iter_state;      /* iterations | state << 24 | converged << 28 */
+    float T[16];
+} cuboid_guess_record;       /* 80 bytes */
+int cuboid_set_guess_offset(cuboid_handle* h, int id_offset);
+void cuboid_guess_record_from_result(const cuboid_cluster_result* c, cuboid_guess_record* out);
+/* recs: n_ranks records of ONE (frame, cluster); out keeps its size field, gets the winner's pose, fitness, iterations, state,
+ * converged, best_guess and accepted = converged && fitness < gate; corr_hash (a per-rank parity tap) is cleared. */
+int cuboid_reduce_guess_records(const cuboid_guess_record* recs, int n_ranks, double gate, cuboid_cluster_result* out);
+/* Legacy 64-bit key (fitness bits with the low 16 mantissa bits replaced by the guess id) for a single MIN all-reduce. It
+ * orders fitness values that agree to 2^-36 relative by guess id, i.e. it is NOT the exact rule above: use the records. */
 uint64_t cuboid_pack_fitness_key(double fitness, int32_t guess_id);
 void cuboid_unpack_fitness_key(uint64_t key, double* fitness, int32_t* guess_id);
 

@@ -20,7 +20,7 @@ import os
 import numpy as np
 
 from . import build as _build
-from .params import MAX_CLUSTERS, CuboidParams, FrameResult, default_params  # noqa: F401
+from .params import MAX_CLUSTERS, ClusterResult, CuboidParams, FrameResult, default_params  # noqa: F401
 
 OK = 0
 E_INVALID, E_NO_DEVICE, E_CUDA, E_CAPACITY, E_NO_TEMPLATE, E_UNSUPPORTED = -1, -2, -3, -4, -5, -6
@@ -35,7 +35,8 @@ ABI_SYMBOLS = [
     "cuboid_pack_fitness_key", "cuboid_unpack_fitness_key", "cuboid_strerror", "cuboid_last_error",
     "cuboid_abi_version", "cuboid_params_size", "cuboid_frame_result_size", "cuboid_launch_count",
     "cuboid_stage_ms", "cuboid_measure_fp32_peak", "cuboid_set_option", "cuboid_icp_work",
-    "cuboid_debug_counters", "cuboid_bbox_filter", "cuboid_set_bbox_filter", "cuboid_surface_normals", "cuboid_surface_pose", "cuboid_select_object",
+    "cuboid_debug_counters", "cuboid_set_guess_offset", "cuboid_guess_record_from_result", "cuboid_reduce_guess_records",
+    "cuboid_bbox_filter", "cuboid_set_bbox_filter", "cuboid_surface_normals", "cuboid_surface_pose", "cuboid_select_object",
 ]
 OPT_ICP_CULL, OPT_TAPS, OPT_STAGES, OPT_FRONTEND, OPT_PIPELINE = 1, 2, 3, 4, 5
 
@@ -61,6 +62,26 @@ def select_object(frame_result, template_points, icp_fitness_score):
     if st != OK:
         raise CuboidError(st, "cuboid_select_object")
     return out
+
+
+class GuessRecord(C.Structure):
+    """cuboid_guess_record (include/cuboid_cuda.h): what one rank contributes per (frame, cluster) to the hypothesis-sharded mode."""
+    _fields_ = [("fitness", C.c_double), ("guess_id", C.c_int32), ("iter_state", C.c_int32), ("T", C.c_float * 16)]
+
+
+def guess_record(cluster_result):
+    out = GuessRecord()
+    load().cuboid_guess_record_from_result(C.byref(cluster_result), C.byref(out))
+    return out
+
+
+def reduce_guess_records(records, gate, into):
+    """records: sequence / ctypes array of GuessRecord of ONE (frame, cluster), one per rank; `into` (a ClusterResult) receives the winner."""
+    arr = (GuessRecord * len(records))(*records)
+    st = load().cuboid_reduce_guess_records(arr, len(records), float(gate), C.byref(into))
+    if st != OK:
+        raise CuboidError(st, "cuboid_reduce_guess_records")
+    return into
 
 
 class CuboidError(RuntimeError):
@@ -107,6 +128,10 @@ def load():
     L.cuboid_pack_fitness_key.restype = C.c_uint64
     L.cuboid_unpack_fitness_key.argtypes = [C.c_uint64, C.POINTER(C.c_double), C.POINTER(C.c_int32)]
     L.cuboid_unpack_fitness_key.restype = None
+    L.cuboid_set_guess_offset.argtypes = [vp, i32]
+    L.cuboid_guess_record_from_result.argtypes = [vp, vp]
+    L.cuboid_guess_record_from_result.restype = None
+    L.cuboid_reduce_guess_records.argtypes = [vp, i32, C.c_double, vp]
     L.cuboid_strerror.argtypes = [i32]
     L.cuboid_strerror.restype = C.c_char_p
     L.cuboid_last_error.argtypes = [vp]
@@ -223,6 +248,10 @@ class CuboidCuda:
             return
         g = _f32(guesses).reshape(-1, 16 if mode == 0 else 9)
         self._ck(self.lib.cuboid_set_guesses(self._h, _ptr(g), len(g), int(mode)), "cuboid_set_guesses")
+
+    def set_guess_offset(self, id_offset):
+        """Hypothesis-sharded mode: this handle holds guesses [id_offset, id_offset + n) of the global list."""
+        self._ck(self.lib.cuboid_set_guess_offset(self._h, int(id_offset)), "cuboid_set_guess_offset")
 
     # -- stages -------------------------------------------------------------------------------
     def unproject(self, depth):

@@ -101,7 +101,11 @@ __device__ __forceinline__ void sub_sync(int sub) {   // literal barrier ids: a 
         case 0: asm volatile("bar.sync 1, %0;" ::"n"(SUB) : "memory"); break;
         case 1: asm volatile("bar.sync 2, %0;" ::"n"(SUB) : "memory"); break;
         case 2: asm volatile("bar.sync 3, %0;" ::"n"(SUB) : "memory"); break;
-        default: asm volatile("bar.sync 4, %0;" ::"n"(SUB) : "memory"); break;
+        case 3: asm volatile("bar.sync 4, %0;" ::"n"(SUB) : "memory"); break;
+        case 4: asm volatile("bar.sync 5, %0;" ::"n"(SUB) : "memory"); break;
+        case 5: asm volatile("bar.sync 6, %0;" ::"n"(SUB) : "memory"); break;
+        case 6: asm volatile("bar.sync 7, %0;" ::"n"(SUB) : "memory"); break;
+        default: asm volatile("bar.sync 8, %0;" ::"n"(SUB) : "memory"); break;
     }
 }
 constexpr int ICP_LEAF = 16;       // template points per BVH leaf
@@ -1189,7 +1193,7 @@ __global__ void __launch_bounds__(ICP_NT, 1) k_icp(const IcpArgs a) {
 }
 
 // best guess per (frame, cluster): lowest fitness, ties -> lowest guess id; fills cuboid_cluster_result
-__global__ void k_icp_select(const IcpOut* out, cuboid_frame_result* res, int n_frames, int n_guess, double gate) {
+__global__ void k_icp_select(const IcpOut* out, cuboid_frame_result* res, int n_frames, int n_guess, double gate, int guess_offset) {
     const int t = blockIdx.x * blockDim.x + threadIdx.x;
     const int f = t / CUBOID_MAX_CLUSTERS, c = t % CUBOID_MAX_CLUSTERS;
     if (f >= n_frames) return;
@@ -1201,7 +1205,7 @@ __global__ void k_icp_select(const IcpOut* out, cuboid_frame_result* res, int n_
     cuboid_cluster_result& C = R.cluster[c];
     C.converged = o[bg].converged;
     C.iterations = o[bg].iters;
-    C.best_guess = bg;
+    C.best_guess = bg + guess_offset;   // global hypothesis id when the hypotheses are split over GPUs
     C.state = o[bg].state;
     C.fitness = o[bg].fitness;
     C.accepted = (o[bg].converged && o[bg].fitness < gate) ? 1 : 0;

@@ -346,6 +346,22 @@ def test_multi_guess_rotations_about_centroid(tmpl30, params):
         _same_frame(res[i], O.process_frame(p, depth[i], tmpl30, guesses=rots))
 
 
+def test_bench_64_rotation_guess_set_matches_oracle(tmpl30):
+    """BASELINE config 3 as bench.py runs it: identity + 63 rotations about the cluster centroid, full iteration budget, two frames."""
+    import bench
+    rots = bench.guess_rotations()
+    assert rots.shape == (64, 3, 3)
+    depth = synth.depth_batch("bench", [11, 12])
+    p = default_params("cuboid")
+    p.n_guess, p.guess_mode = 64, 1
+    with api.CuboidCuda(p, max_points=640 * 480, max_batch=2) as h:
+        h.set_template(0, tmpl30)
+        h.set_guesses(rots, mode=1)
+        res = h.process_batch(depth)
+    for i in range(2):
+        _same_frame(res[i], O.process_frame(p, depth[i], tmpl30, guesses=rots))
+
+
 def test_multi_object_frame_and_second_template(tmpl100):
     p = default_params("multi8")
     depth = synth.depth_batch("multi8", [0])

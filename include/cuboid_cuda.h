@@ -135,6 +135,14 @@ int cuboid_unproject(cuboid_handle* h, const uint16_t* depth, int w, int hgt, fl
  * key_per_point_out (n int32, voxel idx of each SURVIVING point in input order, compacted) may be NULL. */
 int cuboid_preprocess(cuboid_handle* h, const void* pts, int point_step, int xoff, int yoff, int zoff, int n,
                       float* vox_xyzw_out, int cap, int* n_vox, int32_t* key_per_point_out, int* n_pass);
+/* PointCloud2 inputs that carry a packed "rgb" / "rgba" field (realsense2_camera's cloud: x, y, z, rgb): tell the library where it
+ * sits inside a record (sensor_msgs/PointField offset, 4-byte aligned; -1 = none, the default). PassThrough and ExtractIndices
+ * copy whole PCLPointCloud2 records and VoxelGrid<PCLPointCloud2> (gps.cpp:69-73, downsample_all_data_ = true) averages r, g, b
+ * per voxel, so the cloud the node republishes (gps.cpp:110-112) keeps its colour. With a field declared, the w component of every
+ * xyzw point the library returns for a PointCloud2 input (cuboid_preprocess, cuboid_batch_fetch what = 0 / 2 / 4) holds that packed
+ * word - per voxel (int(mean r) << 16) | (int(mean g) << 8) | int(mean b) - instead of pcl::PointXYZ's 1.0f padding. Other extra
+ * fields are not carried. */
+int cuboid_set_cloud_fields(cuboid_handle* h, int rgb_offset);
 /* SACSegmentation::segment + ExtractIndices (gps.cpp:76-101). triplets NULL -> internal seeded sampler
  * (boost::mt19937(12345) stream shared with the oracle). Any output pointer may be NULL. */
 int cuboid_segment_plane(cuboid_handle* h, const float* xyzw, int n, const int32_t* triplets, int n_triplets,

@@ -35,7 +35,7 @@ ABI_SYMBOLS = [
     "cuboid_pack_fitness_key", "cuboid_unpack_fitness_key", "cuboid_strerror", "cuboid_last_error",
     "cuboid_abi_version", "cuboid_params_size", "cuboid_frame_result_size", "cuboid_launch_count",
     "cuboid_stage_ms", "cuboid_measure_fp32_peak", "cuboid_set_option", "cuboid_icp_work",
-    "cuboid_debug_counters", "cuboid_set_guess_offset", "cuboid_guess_record_from_result", "cuboid_reduce_guess_records",
+    "cuboid_debug_counters", "cuboid_set_cloud_fields", "cuboid_set_guess_offset", "cuboid_guess_record_from_result", "cuboid_reduce_guess_records",
     "cuboid_bbox_filter", "cuboid_set_bbox_filter", "cuboid_surface_normals", "cuboid_surface_pose", "cuboid_select_object",
 ]
 OPT_ICP_CULL, OPT_TAPS, OPT_STAGES, OPT_FRONTEND, OPT_PIPELINE = 1, 2, 3, 4, 5
@@ -129,6 +129,7 @@ def load():
     L.cuboid_unpack_fitness_key.argtypes = [C.c_uint64, C.POINTER(C.c_double), C.POINTER(C.c_int32)]
     L.cuboid_unpack_fitness_key.restype = None
     L.cuboid_set_guess_offset.argtypes = [vp, i32]
+    L.cuboid_set_cloud_fields.argtypes = [vp, i32]
     L.cuboid_guess_record_from_result.argtypes = [vp, vp]
     L.cuboid_guess_record_from_result.restype = None
     L.cuboid_reduce_guess_records.argtypes = [vp, i32, C.c_double, vp]
@@ -248,6 +249,10 @@ class CuboidCuda:
             return
         g = _f32(guesses).reshape(-1, 16 if mode == 0 else 9)
         self._ck(self.lib.cuboid_set_guesses(self._h, _ptr(g), len(g), int(mode)), "cuboid_set_guesses")
+
+    def set_cloud_fields(self, rgb_offset=-1):
+        """Offset of the packed rgb / rgba field of PointCloud2 inputs (-1: none): carried through PassThrough, VoxelGrid, ExtractIndices."""
+        self._ck(self.lib.cuboid_set_cloud_fields(self._h, int(rgb_offset)), "cuboid_set_cloud_fields")
 
     def set_guess_offset(self, id_offset):
         """Hypothesis-sharded mode: this handle holds guesses [id_offset, id_offset + n) of the global list."""

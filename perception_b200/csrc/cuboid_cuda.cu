@@ -85,6 +85,7 @@ struct cuboid_handle {
     int last_chunk_base = 0, last_chunk_frames = 0, last_total_frames = 0;
     int taps = 1;
     int use_bbox = 0; double bbP[12] = {}; int bb[4] = {};   // cuboid_set_bbox_filter
+    int rgb_off = -1;                                        // cuboid_set_cloud_fields: offset of the packed rgb(a) field of PointCloud2 inputs, -1 = none
     struct { int active = 0; int model_type = 0; float axis[3] = {0, 0, 0}; double eps = 0.0, thr = 0.0; } sac_override;   // cuboid_surface_normals
     // fused front end (frontend.cuh): one thread-block cluster per frame, persistent over the chunk
     int frontend = 1; int fe_cluster = 1; int fe_threads = 512; int fe_slots = 0; unsigned long long* d_fe_keys = nullptr;
@@ -274,6 +275,9 @@ int run_chunk(cuboid_handle* h, const ChunkIn& in, int nf, cuboid_frame_result* 
         FrontArgs fa{};
         PreArgs& a = fa.pre;
         a.depth = in.depth; a.blob = in.blob; a.point_step = in.point_step; a.xoff = in.xoff; a.yoff = in.yoff; a.zoff = in.zoff;
+        a.rgboff = (in.blob && h->rgb_off >= 0) ? h->rgb_off : -1;
+        if (a.rgboff >= 0 && a.rgboff + 4 > in.point_step) return CUBOID_E_INVALID;
+        fa.rgb = a.rgboff >= 0 ? 1 : 0;
         a.n_in = in.blob ? h->d_n_in + f0 : nullptr;
         a.w = in.w; a.h = in.hgt; a.P = in.in_stride; a.w_magic = row_magic(in.w, in.in_stride);
         a.fx = p.fx; a.fy = p.fy; a.cx = p.cx; a.cy = p.cy; a.depth_scale = p.depth_scale;
@@ -304,6 +308,7 @@ int run_chunk(cuboid_handle* h, const ChunkIn& in, int nf, cuboid_frame_result* 
         CK(h, cudaGetLastError());
     }
     if (!fused && (stages & 1) && !skip_pre) {
+        if (in.blob && h->rgb_off >= 0) return CUBOID_E_UNSUPPORTED;   // the rgb field is carried by the fused front end only
         CK(h, cudaMemsetAsync(d_res, 0, sizeof(cuboid_frame_result) * nf, st));
         k_init_scratch<<<(nf + 127) / 128, 128, 0, st>>>(b_scr, nf);
         ++h->launches;
@@ -311,6 +316,7 @@ int run_chunk(cuboid_handle* h, const ChunkIn& in, int nf, cuboid_frame_result* 
         const int tiles = (per + PRE_TILE - 1) / PRE_TILE;
         PreArgs a{};
         a.depth = in.depth; a.blob = in.blob; a.point_step = in.point_step; a.xoff = in.xoff; a.yoff = in.yoff; a.zoff = in.zoff;
+        a.rgboff = -1;
         a.n_in = in.blob ? h->d_n_in + f0 : nullptr;
         a.w = in.w; a.h = in.hgt; a.P = per; a.w_magic = row_magic(in.w, per);
         a.fx = p.fx; a.fy = p.fy; a.cx = p.cx; a.cy = p.cy; a.depth_scale = p.depth_scale;
@@ -1115,6 +1121,12 @@ int cuboid_surface_normals(cuboid_handle* h, const float* xyzw, int n, const flo
     if (rc != CUBOID_OK) return rc;
     out->n_left = cur_n;
     cuboid_surface_pose(&out->coeff[0][0], &out->midpoint[0][0], out->n_plane, out->Rt, out->order, out->pose7);
+    return CUBOID_OK;
+}
+
+int cuboid_set_cloud_fields(cuboid_handle* h, int rgb_offset) {
+    if (!h || rgb_offset < -1 || (rgb_offset >= 0 && (rgb_offset & 3))) return CUBOID_E_INVALID;
+    h->rgb_off = rgb_offset;
     return CUBOID_OK;
 }
 

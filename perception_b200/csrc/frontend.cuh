@@ -31,6 +31,7 @@ struct FrontArgs {
     float4* vox;                 // [F][P]
     int* vcount;                 // [F][P] points per voxel (parity tap) or NULL
     float inv_leaf;
+    int rgb;                     // 1: .w of every point is a packed rgb(a) word: VoxelGrid<PCLPointCloud2> averages r, g, b per voxel (gps.cpp:69-73)
     int hashes;                  // 1: accumulate points_hash / voxel_key_hash / voxel_hash (parity taps); 0: leave them 0
     int P;                       // per-frame stride of pts / vox / kpp / vcount / keys
     int n_frames;
@@ -58,12 +59,12 @@ struct FeFrame {         // cluster-wide facts of the current frame, replicated 
 //           + the tile's depth values (u16), + the keep masks A1 found, so A2       NT*8*2 + FE_MASK_BYTES
 //             does not unproject and filter again
 //   B       per-warp digit counters [NT/32][256] u32 + two prefetched key tiles   NT*32 + 2*NT*8*8 bytes
-//   C2      key,x,y,z of the staged sorted records (+ look-ahead) + u16 heads   (NT*4+128)*16 + NT*4*2 bytes
+//   C2      key,x,y,z,w of the staged sorted records (+ look-ahead) + u16 heads (NT*4+128)*20 + NT*4*2 bytes
 constexpr int FE_MASK_BYTES = 40960;   // keep masks of one input slice (1 byte per 8 inputs): a VGA frame on one CTA needs 38 400
 constexpr int fe_max(int a, int b) { return a > b ? a : b; }
 template <int NT>
 constexpr int fe_dyn_smem() {   // A: selection + depth tile + masks; B: digit counters + two prefetched key tiles; C2: staging + heads
-    return fe_max(fe_max(NT * 32 + FE_MASK_BYTES, NT * 32 + 2 * NT * FE_ITEMS * 8), (NT * FE_RITEMS + FE_LOOK) * 16 + NT * FE_RITEMS * 2);
+    return fe_max(fe_max(NT * 32 + FE_MASK_BYTES, NT * 32 + 2 * NT * FE_ITEMS * 8), (NT * FE_RITEMS + FE_LOOK) * 20 + NT * FE_RITEMS * 2);
 }
 // asynchronous global -> shared copies (LDGSTS): the next tile of sort records is on its way while this one is ranked
 __device__ __forceinline__ void fe_cp_async16(void* smem, const void* gmem) {
@@ -103,8 +104,10 @@ __device__ __forceinline__ float4 fe_point_at(const PreArgs& a, int f, int i) {
         return make_float4(z * a.xr[u], z * a.yr[v], z, 1.0f);
     } else {
         const unsigned char* rec = a.blob + ((size_t)f * a.P + i) * a.point_step;
+        // .w = pcl::PointXYZ's padding (1.0f), or the record's packed rgb(a) word when the cloud carries one: it then travels with
+        // the point through every float4 copy of the pipeline (nothing downstream reads .w as a coordinate)
         return make_float4(*reinterpret_cast<const float*>(rec + a.xoff), *reinterpret_cast<const float*>(rec + a.yoff),
-                           *reinterpret_cast<const float*>(rec + a.zoff), 1.0f);
+                           *reinterpret_cast<const float*>(rec + a.zoff), a.rgboff >= 0 ? *reinterpret_cast<const float*>(rec + a.rgboff) : 1.0f);
     }
 }
 
@@ -138,8 +141,16 @@ __device__ __forceinline__ unsigned int fe_digit_peers(unsigned int d) {
 // One 32-record step of a voxel's run, called by a whole warp: lane j holds record j (match = it belongs to the voxel,
 // a = its point). Adds the leading matching records to the running sums IN ORDER and returns how many there were
 // (32 = the run may continue). An axis whose values are all +-0 folds without the 32-deep dependent chain.
-struct FeRun { float sx, sy, sz; int cnt; };
-__device__ __forceinline__ int fe_run_step(FeRun& r, bool match, float ax, float ay, float az) {
+struct FeRun { float sx, sy, sz; int cnt; unsigned int sr, sg, sb; };
+// VoxelGrid<PCLPointCloud2>'s rgb special case (PCL voxel_grid.cpp, [PCL-recall]): r, g, b of pcl::RGB {b, g, r, a} are summed as
+// floats (exact integers below 2^24, so the order does not matter), divided by the float count like every centroid field, truncated to
+// int and repacked as (r << 16) | (g << 8) | b.
+__device__ __forceinline__ float fe_rgb_avg(unsigned int sr, unsigned int sg, unsigned int sb, int cnt) {
+    const float c = (float)cnt;
+    const int r = (int)((float)sr / c), g = (int)((float)sg / c), b = (int)((float)sb / c);
+    return __int_as_float((r << 16) | (g << 8) | b);
+}
+__device__ __forceinline__ int fe_run_step(FeRun& r, bool match, float ax, float ay, float az, unsigned int aw = 0u) {
     const unsigned int miss = __ballot_sync(FULL_MASK, !match);
     const int nmatch = miss ? (__ffs(miss) - 1) : 32;
     const unsigned int in = nmatch == 32 ? FULL_MASK : ((1u << nmatch) - 1u);
@@ -150,6 +161,12 @@ __device__ __forceinline__ int fe_run_step(FeRun& r, bool match, float ax, float
     if (nzx) { for (int j = 0; j < nmatch; ++j) r.sx += __shfl_sync(FULL_MASK, ax, j); } else r.sx = fe_add_zeros(r.sx, pzx != 0u);
     if (nzy) { for (int j = 0; j < nmatch; ++j) r.sy += __shfl_sync(FULL_MASK, ay, j); } else r.sy = fe_add_zeros(r.sy, pzy != 0u);
     if (nzz) { for (int j = 0; j < nmatch; ++j) r.sz += __shfl_sync(FULL_MASK, az, j); } else r.sz = fe_add_zeros(r.sz, pzz != 0u);
+    {
+        const bool mine = (int)(threadIdx.x & 31) < nmatch;
+        r.sr += __reduce_add_sync(FULL_MASK, mine ? ((aw >> 16) & 255u) : 0u);
+        r.sg += __reduce_add_sync(FULL_MASK, mine ? ((aw >> 8) & 255u) : 0u);
+        r.sb += __reduce_add_sync(FULL_MASK, mine ? (aw & 255u) : 0u);
+    }
     r.cnt += nmatch;
     return nmatch;
 }
@@ -495,6 +512,7 @@ __global__ void __launch_bounds__(NT, 2048 / NT >= 2 ? (NT <= 512 ? 2 : 1) : 1) 
             float* s_py = s_px + RSTAGE;
             float* s_pz = s_py + RSTAGE;
             unsigned short* s_head = reinterpret_cast<unsigned short*>(s_pz + RSTAGE);
+            unsigned int* s_pw = reinterpret_cast<unsigned int*>(s_head + RTILE);   // packed rgb(a) of the staged points (a.rgb only)
             const float4* pts = p.pts + (size_t)f * p.Pout;
             float4* vox = a.vox + (size_t)f * a.P;
             int* vcount = a.vcount ? a.vcount + (size_t)f * a.P : nullptr;
@@ -517,6 +535,7 @@ __global__ void __launch_bounds__(NT, 2048 / NT >= 2 ? (NT <= 512 ? 2 : 1) : 1) 
                             const float4 pt = __ldcg(pts + (unsigned int)rec[k]);
                             s_key[l] = (unsigned int)(rec[k] >> 32);
                             s_px[l] = pt.x; s_py[l] = pt.y; s_pz[l] = pt.z;
+                            if (a.rgb) s_pw[l] = __float_as_uint(pt.w);
                         }
                     }
                 }
@@ -552,7 +571,13 @@ __global__ void __launch_bounds__(NT, 2048 / NT >= 2 ? (NT <= 512 ? 2 : 1) : 1) 
                     for (int q = lp + 1; q < end; ++q) { sx += s_px[q]; sy += s_py[q]; sz += s_pz[q]; }
                     const float cnt = (float)(end - lp);
                     const float cx = sx / cnt, cy = sy / cnt, cz = sz / cnt;
-                    vox[pos] = make_float4(cx, cy, cz, 1.0f);
+                    float cw = 1.0f;
+                    if (a.rgb) {
+                        unsigned int sr = 0, sg = 0, sb = 0;
+                        for (int q = lp; q < end; ++q) { const unsigned int w = s_pw[q]; sr += (w >> 16) & 255u; sg += (w >> 8) & 255u; sb += w & 255u; }
+                        cw = fe_rgb_avg(sr, sg, sb, end - lp);
+                    }
+                    vox[pos] = make_float4(cx, cy, cz, cw);
                     if (vcount) vcount[pos] = end - lp;
                     if (a.hashes) hv[0] += hash_point((unsigned int)pos, cx, cy, cz);
                 }
@@ -563,11 +588,15 @@ __global__ void __launch_bounds__(NT, 2048 / NT >= 2 ? (NT <= 512 ? 2 : 1) : 1) 
                     const unsigned int mykey = s_key[lp];
                     FeRun acc;
                     acc.sx = s_px[lp]; acc.sy = s_py[lp]; acc.sz = s_pz[lp]; acc.cnt = 1;
+                    {
+                        const unsigned int w0 = a.rgb ? s_pw[lp] : 0u;
+                        acc.sr = (w0 >> 16) & 255u; acc.sg = (w0 >> 8) & 255u; acc.sb = w0 & 255u;
+                    }
                     bool open = true;
                     for (int l = lp + 1; open && l < n_stage; l += 32) {   // the part of the run that is staged in shared memory
                         const int i = l + lane;
                         const bool m = i < n_stage && s_key[i] == mykey;
-                        open = fe_run_step(acc, m, m ? s_px[i] : 0.f, m ? s_py[i] : 0.f, m ? s_pz[i] : 0.f) == min(32, n_stage - l);
+                        open = fe_run_step(acc, m, m ? s_px[i] : 0.f, m ? s_py[i] : 0.f, m ? s_pz[i] : 0.f, (m && a.rgb) ? s_pw[i] : 0u) == min(32, n_stage - l);
                     }
                     for (int q = t0 + n_stage; open && q < N; q += 128) {    // the rest from the sorted records, 128 per round trip
                         unsigned long long rec[4];
@@ -583,13 +612,13 @@ __global__ void __launch_bounds__(NT, 2048 / NT >= 2 ? (NT <= 512 ? 2 : 1) : 1) 
                         for (int j = 0; j < 4; ++j) pt[j] = m[j] ? __ldcg(pts + (unsigned int)rec[j]) : make_float4(0.f, 0.f, 0.f, 0.f);
 #pragma unroll
                         for (int j = 0; j < 4; ++j)
-                            if (open) open = fe_run_step(acc, m[j], pt[j].x, pt[j].y, pt[j].z) == 32;
+                            if (open) open = fe_run_step(acc, m[j], pt[j].x, pt[j].y, pt[j].z, a.rgb ? __float_as_uint(pt[j].w) : 0u) == 32;
                     }
                     if (lane == 0) {
                         const float c = (float)acc.cnt;
                         const float cx = acc.sx / c, cy = acc.sy / c, cz = acc.sz / c;
                         const int vp = s_def_pos[d];
-                        vox[vp] = make_float4(cx, cy, cz, 1.0f);
+                        vox[vp] = make_float4(cx, cy, cz, a.rgb ? fe_rgb_avg(acc.sr, acc.sg, acc.sb, acc.cnt) : 1.0f);
                         if (vcount) vcount[vp] = acc.cnt;
                         if (a.hashes) hv[0] += hash_point((unsigned int)vp, cx, cy, cz);
                     }

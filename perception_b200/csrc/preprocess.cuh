@@ -16,6 +16,7 @@ struct PreArgs {
     const uint16_t* depth;       // [F][P] (SRC 0)
     const unsigned char* blob;   // [F][P*point_step] (SRC 1)
     int point_step, xoff, yoff, zoff;
+    int rgboff;                  // offset of the packed rgb / rgba field inside a record, or -1: carried in .w of every point (fused front end)
     const int* n_in;             // per-frame input count (SRC 1) or NULL -> P
     int w, h;                    // image size (SRC 0)
     unsigned int w_magic;        // ceil(2^32 / w) when i / w == __umulhi(i, w_magic) for every input index (P*w <= 2^32), else 0

@@ -608,3 +608,48 @@ def test_pipeline_option_and_concurrent_handles_return_the_same_bytes(tmpl30, pa
     finally:
         for h in hs:
             h.close()
+
+
+def test_rgb_field_is_carried_through_voxelgrid_and_extraction(frame0, tmpl30, params):
+    """gps.cpp:49-112 on a PointCloud2 with x, y, z, rgb (point_step 20, rgb at 16): PassThrough / ExtractIndices copy whole
+    records and VoxelGrid<PCLPointCloud2> (downsample_all_data_) averages r, g, b per voxel: float sums of the channel values
+    (exact integers), float division by the count, truncation, repacked as r << 16 | g << 8 | b  [PCL-recall: voxel_grid.cpp
+    'RGB special case']. xyz results must not change by a bit; the published remainder keeps the colour of its voxels."""
+    with api.CuboidCuda(params, max_points=640 * 480, max_batch=1) as h:
+        h.set_template(0, tmpl30)
+        cloud = h.unproject(frame0)
+        n = len(cloud)
+        rng = np.random.default_rng(5)
+        rgb = rng.integers(0, 1 << 24, n, dtype=np.uint32) | (rng.integers(0, 256, n, dtype=np.uint32) << 24)   # alpha byte must be dropped
+        blob = np.zeros((n, 5), np.float32)
+        blob[:, :3] = cloud[:, :3]
+        blob[:, 3] = 7.0                                   # a foreign field between z and rgb
+        blob[:, 4] = rgb.view(np.float32)
+        plain = h.process_cloud(blob, point_step=20, n=n)
+        vox_plain, rem_plain = h.fetch(0, "voxels"), h.fetch(0, "remain")
+        assert (vox_plain[:, 3] == 1.0).all() and (rem_plain[:, 3] == 1.0).all()
+        h.set_cloud_fields(16)
+        col = h.process_cloud(blob, point_step=20, n=n)
+        pts, keys = h.fetch(0, "points"), h.fetch(0, "voxel_keys")
+        vox, rem, inl = h.fetch(0, "voxels"), h.fetch(0, "remain"), h.fetch(0, "inliers")
+        h.set_cloud_fields(-1)
+    a, b = type(plain).from_buffer_copy(bytes(plain)), type(col).from_buffer_copy(bytes(col))
+    assert bytes(a) == bytes(b)                            # counts, hashes, plane, clusters, poses: unchanged
+    assert np.array_equal(bits(vox[:, :3]), bits(vox_plain[:, :3])) and np.array_equal(bits(rem[:, :3]), bits(rem_plain[:, :3]))
+    # survivors keep their own colour (PassThrough copies records), in order
+    keep = np.isfinite(cloud[:, :3]).all(axis=1) & ~((cloud[:, 2] > 0.9) | (cloud[:, 2] < 0.0)) & ~((cloud[:, 0] > 0.2) | (cloud[:, 0] < -0.2))
+    assert np.array_equal(pts[:, 3].view(np.uint32), rgb[keep])
+    # per-voxel colour
+    w = pts[:, 3].view(np.uint32)
+    uk, inv, cnt = np.unique(keys, return_inverse=True, return_counts=True)
+    assert len(uk) == len(vox)
+    want = np.zeros(len(uk), np.uint32)
+    for shift in (16, 8, 0):
+        s = np.zeros(len(uk), np.float32)
+        np.add.at(s, inv, ((w >> shift) & 255).astype(np.float32))
+        want |= (s / cnt.astype(np.float32)).astype(np.int32).astype(np.uint32) << shift
+    assert np.array_equal(vox[:, 3].view(np.uint32), want)
+    # ExtractIndices(negative) republishes the voxel records that are not plane inliers, colour included
+    mask = np.ones(len(vox), bool)
+    mask[inl] = False
+    assert np.array_equal(bits(rem), bits(vox[mask]))

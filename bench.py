@@ -182,9 +182,12 @@ def run_reference(args, rank, world):
     if rank != 0:
         return
     from concurrent.futures import ThreadPoolExecutor
+    from oracle import pcl_probe
     from oracle import pyoracle as O
     from perception_b200.params import default_params
     cores = os.cpu_count() or 1
+    pcl = pcl_probe.find_pcl()                     # a real PCL, if this box has one, pins the oracle and is timed beside it
+    pcl_report = {"found": pcl["found"], "detail": pcl["detail"]}
     wl = WORKLOADS[args.workload]
     dp = default_params(wl["variant"])
     dp.n_guess, dp.guess_mode = wl["n_guess"], (1 if wl["n_guess"] > 1 else 0)
@@ -218,7 +221,23 @@ def run_reference(args, rank, world):
                                    "rate), frames parallel over %d host threads" % (per_step, args.frames, cores)},
         "e2e": {"value": fps, "unit": "frames/s", "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
         "note": "CPU restatement of the PCL path (oracle/), not a PCL binary: PCL/ROS cannot be built offline",
+        "pcl_probe": pcl_report,
     }
+    if pcl["found"] and args.workload == "full":
+        try:   # the literal PCL call sequence on frame 0: its own timing and the restatement-vs-PCL difference
+            import tempfile
+            binary = pcl_probe.build_harness(pcl)
+            if binary:
+                pts = O.unproject(frames[0], dp.fx, dp.fy, dp.cx, dp.cy, dp.depth_scale)
+                tpl = os.path.join(ROOT, "tests", "golden", "template_cuboid_L200_W100_H30_3faces.pcd")
+                dump = pcl_probe.run_harness(binary, pts, tpl, tempfile.mkdtemp(prefix="pcl_harness_"))
+                if dump:
+                    ms = dump["ms_segmentation"] + dump["ms_icp"]
+                    pcl_report.update({"frames_per_s_one_thread": 1e3 / ms if ms > 0 else None, "ms_segmentation": dump["ms_segmentation"],
+                                       "ms_icp": dump["ms_icp"], "vs_restatement": pcl_probe.compare_with_oracle(dump, O.process_frame(p, frames[0], tm, mode=O.LITERAL))})
+                    line["cpu_baseline"]["kind"] = "port (+ reference PCL timed on one frame: pcl_probe)"
+        except Exception as e:
+            pcl_report["error"] = repr(e)
     print(json.dumps(line), flush=True)
 
 

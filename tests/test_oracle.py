@@ -353,3 +353,60 @@ def test_icp_reproduces_the_published_capture_pose_of_a_real_scan(golden):
         rot_err = np.linalg.norm([D[2, 1] - D[1, 2], D[0, 2] - D[2, 0], D[1, 0] - D[0, 1]]) / 2
         assert rot_err < 1e-4 and np.abs(Tr[:3, 3] - T[:3, 3]).max() < 1e-5, (rot_err, Tr[:3, 3] - T[:3, 3])
         assert r["fitness"] < 1e-12
+
+
+def test_literal_vs_canonical_oracle_divergence_is_what_design_md_states(tmpl30):
+    """north_star's tolerance (1e-4 rad, 1e-5 m, 1e-6 fitness) is established against the CANONICAL oracle only (the GPU is bit-exact
+    against it). The oracle's own LITERAL mode (std::sort voxel order, sequential Eigen-style sums, host libm) is the closest thing to
+    a second reading of PCL available offline; this test pins how far the two readings are apart on 256 bench frames, so that the
+    claim in DESIGN.md section 5 stays a measured one. Integer outputs almost always agree; poses agree within tolerance when both
+    modes stop ICP at the same iteration and differ by what the extra iterations move when last-bit differences shift the
+    relative-MSE stop."""
+    from concurrent.futures import ThreadPoolExecutor
+    from perception_b200 import synth
+    p = O.params_from(default_params("cuboid"))
+    n = 256
+    frames = synth.depth_batch("bench", range(n))
+
+    def run(i):
+        return O.process_frame(p, frames[i], tmpl30, mode=O.CANONICAL), O.process_frame(p, frames[i], tmpl30, mode=O.LITERAL)
+
+    with ThreadPoolExecutor(os.cpu_count() or 1) as ex:
+        res = list(ex.map(run, range(n)))
+    same_int = same_it = within = within_same = 0
+    dt_same = []
+    for a, b in res:
+        si = all(getattr(a, k) == getattr(b, k) for k in ("n_points", "n_voxels", "voxel_key_hash", "n_inliers", "inlier_hash", "n_remain", "cluster_hash"))
+        ca, cb = a.cluster[0], b.cluster[0]
+        Ta, Tb = np.array(list(ca.T), np.float64).reshape(4, 4), np.array(list(cb.T), np.float64).reshape(4, 4)
+        ang = np.linalg.norm(Ta[:3, :3] @ Tb[:3, :3].T - np.eye(3)) / np.sqrt(2.0)      # = the rotation angle for small angles
+        tr = np.abs(Ta[:3, 3] - Tb[:3, 3]).max()
+        ok = ang <= 1e-4 and tr <= 1e-5 and abs(ca.fitness - cb.fitness) <= 1e-6
+        same_int += si
+        same_it += ca.iterations == cb.iterations
+        within += ok
+        if ca.iterations == cb.iterations:
+            within_same += ok
+            dt_same.append(tr)
+    # measured 2026-10 (this container, gcc 13, glibc 2.39): 255/256 integer-identical, 195/256 same stop iteration, 162/256 within
+    # tolerance overall, 161/195 within tolerance when the stop iteration agrees; the bounds leave room for another libm
+    assert same_int >= 0.98 * n
+    assert same_it >= 0.65 * n
+    assert within >= 0.5 * n
+    assert within_same >= 0.75 * same_it
+    assert np.median(dt_same) < 1e-5
+
+
+def test_pcl_probe_and_harness_source():
+    """no PCL here, so the probe must say so (and bench.py falls back to the restatement); the harness that would pin
+    the oracle is committed source that follows the reference's call sequence."""
+    from oracle import pcl_probe
+    info = pcl_probe.find_pcl()
+    assert set(info) == {"found", "how", "detail"}
+    if not info["found"]:
+        assert pcl_probe.build_harness(info) is None
+    src = open(pcl_probe.HARNESS_SRC).read()
+    for call in ("PassThrough<pcl::PCLPointCloud2>", "VoxelGrid<pcl::PCLPointCloud2>", "SACSegmentation<pcl::PointXYZ>", "ExtractIndices<pcl::PCLPointCloud2>",
+                 "IterativeClosestPoint<pcl::PointXYZ, pcl::PointXYZ>", "setEuclideanFitnessEpsilon", "setTransformationEpsilon(1e-9)", "setMaximumIterations(5000)",
+                 "ground_plane_segmentation.cpp:53-101", "iterative_closest_point.cpp:170-182"):
+        assert call in src, call

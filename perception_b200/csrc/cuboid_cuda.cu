@@ -89,6 +89,7 @@ struct cuboid_handle {
     struct { int active = 0; int model_type = 0; float axis[3] = {0, 0, 0}; double eps = 0.0, thr = 0.0; } sac_override;   // cuboid_surface_normals
     // fused front end (frontend.cuh): one thread-block cluster per frame, persistent over the chunk
     int frontend = 1; int fe_cluster = 1; int fe_threads = 512; int fe_slots = 0; unsigned long long* d_fe_keys = nullptr;
+    int fe_hash = 0; size_t fe_stride = 0;   // voxel-hash path of k_frontend (opt-in: CUBOID_FE_HASH=1; 1024 threads, one CTA per SM) and the per-slot scratch size in u64
     // host-buffer batches: sub-chunks run end to end on a few streams, so copies, front end and ICP of different sub-chunks overlap
     static constexpr int NPIPE = 4; cudaStream_t pipe[NPIPE] = {}; cudaEvent_t pipe_done[NPIPE] = {}; unsigned long long* d_pipe_keys[NPIPE] = {}; int pipeline = 1;
     int64_t launches = 0;
@@ -288,6 +289,7 @@ int run_chunk(cuboid_handle* h, const ChunkIn& in, int nf, cuboid_frame_result* 
         if (in.in_stride > h->P) return CUBOID_E_CAPACITY;
         fa.keys = fe_keys_override ? fe_keys_override : h->d_fe_keys; fa.kpp = h->taps ? b_kpp : nullptr; fa.vox = b_vox; fa.vcount = h->taps ? b_vcount : nullptr;
         fa.inv_leaf = 1.0f / p.leaf; fa.P = h->P; fa.n_frames = nf; fa.hashes = h->taps ? 1 : 0;
+        fa.keys_stride = h->fe_stride; fa.hash = (h->fe_hash && h->fe_threads == 1024 && h->fe_cluster == 1) ? h->fe_hash : 0;
         cudaLaunchConfig_t cfg{};
         cudaLaunchAttribute at[1];
         at[0].id = cudaLaunchAttributeClusterDimension;
@@ -622,7 +624,12 @@ static int create_impl(cuboid_handle** out, const cuboid_params* p, int device, 
     {   // fused front end: cluster size and the number of clusters the device keeps resident
         const char* ef = std::getenv("CUBOID_FRONTEND"); if (ef) h->frontend = atoi(ef) ? 1 : 0;
         const char* ec = std::getenv("CUBOID_FE_CLUSTER"); if (ec) h->fe_cluster = std::max(1, std::min(16, atoi(ec)));
-        const char* et = std::getenv("CUBOID_FE_THREADS"); if (et) h->fe_threads = atoi(et) == 1024 ? 1024 : 512;
+        const char* eh = std::getenv("CUBOID_FE_HASH"); if (eh) h->fe_hash = std::max(0, std::min(2, atoi(eh)));   // 2: developer, mark the path taken in status
+        // Opt-in (measured slower than the radix path on B200: 7.1 ms against 4.75 ms per 1024 VGA frames): the
+        // voxel-hash path (one 1024-thread CTA per SM); frames with more voxels than its table holds fall back per frame to the radix
+        // path inside the same kernel. Bigger clouds (720p: ~600k voxels) always keep two 512-thread CTAs per SM.
+        if (h->fe_hash && h->P <= 400000 && h->fe_cluster == 1) h->fe_threads = 1024; else h->fe_hash = 0;
+        const char* et = std::getenv("CUBOID_FE_THREADS"); if (et) { h->fe_threads = atoi(et) == 1024 ? 1024 : 512; if (h->fe_threads != 1024) h->fe_hash = 0; }
         const void* fns[4] = {(const void*)k_frontend<0, 512>, (const void*)k_frontend<1, 512>, (const void*)k_frontend<0, 1024>, (const void*)k_frontend<1, 1024>};
         for (int k = 0; k < 4; ++k) {
             if (cudaFuncSetAttribute(fns[k], cudaFuncAttributeMaxDynamicSharedMemorySize, fe_smem(k < 2 ? 512 : 1024)) != cudaSuccess) return fail(CUBOID_E_CUDA);
@@ -645,14 +652,15 @@ static int create_impl(cuboid_handle** out, const cuboid_params* p, int device, 
         }
         if (h->fe_slots < 1) { h->last_error = "k_frontend: no resident cluster configuration"; fprintf(stderr, "cuboid_create: %s\n", h->last_error.c_str()); return fail(CUBOID_E_CUDA); }
         h->fe_slots = std::min(h->fe_slots, std::max(1, h->B));
-        CA(dalloc(h, &h->d_fe_keys, (size_t)h->fe_slots * 2 * h->P));
+        h->fe_stride = std::max((size_t)2 * h->P, h->fe_hash ? feh_scratch_u64(h->P) : (size_t)0);
+        CA(dalloc(h, &h->d_fe_keys, (size_t)h->fe_slots * h->fe_stride));
         const char* ep = std::getenv("CUBOID_PIPELINE"); if (ep) h->pipeline = atoi(ep) ? 1 : 0;
         if (h->pipeline && h->B > h->sub_batch) {
             const int pslots = std::min(h->fe_slots, std::min(h->sub_batch, h->B));
             for (int i = 0; i < cuboid_handle::NPIPE; ++i) {
                 if (cudaStreamCreateWithFlags(&h->pipe[i], cudaStreamNonBlocking) != cudaSuccess) return fail(CUBOID_E_CUDA);
                 if (cudaEventCreateWithFlags(&h->pipe_done[i], cudaEventDisableTiming) != cudaSuccess) return fail(CUBOID_E_CUDA);
-                CA(dalloc(h, &h->d_pipe_keys[i], (size_t)pslots * 2 * h->P));
+                CA(dalloc(h, &h->d_pipe_keys[i], (size_t)pslots * h->fe_stride));
             }
         }
     }

@@ -26,7 +26,10 @@ namespace cg = cooperative_groups;
 
 struct FrontArgs {
     PreArgs pre;                 // input description, limits, pts, res, scr (tile_count / tiles are unused here)
-    unsigned long long* keys;    // [n_slots][2][P] radix ping-pong of the frame a cluster slot is working on
+    unsigned long long* keys;    // [n_slots][keys_stride] scratch of the frame a cluster slot is working on: the radix ping-pong [2][P], or the
+                                 // voxel-hash path's records / offsets / slot ids / grouped point indices (FehScratch)
+    size_t keys_stride;          // u64 per slot
+    int hash;                    // 1: try the voxel-hash path first (needs NT = 1024, cluster size 1), fall back to the radix path per frame
     int* kpp;                    // [F][P] voxel idx per point (parity tap) or NULL
     float4* vox;                 // [F][P]
     int* vcount;                 // [F][P] points per voxel (parity tap) or NULL
@@ -62,9 +65,38 @@ struct FeFrame {         // cluster-wide facts of the current frame, replicated 
 //   C2      key,x,y,z,w of the staged sorted records (+ look-ahead) + u16 heads (NT*4+128)*20 + NT*4*2 bytes
 constexpr int FE_MASK_BYTES = 40960;   // keep masks of one input slice (1 byte per 8 inputs): a VGA frame on one CTA needs 38 400
 constexpr int fe_max(int a, int b) { return a > b ? a : b; }
+// ---- voxel-hash path (fe_hash_frame, opt-in with CUBOID_FE_HASH=1): the distinct voxels of a frame are found with a hash table in
+// shared memory, only THEY are sorted, and the points are grouped by one counting scatter. Same outputs as the radix path, byte for
+// byte (tests), and 1.6x instead of 2.8x the algorithmic DRAM traffic - but on B200 it executes as many instructions as the radix
+// path (hashing and the unproject / filter work done twice replace the saved radix passes) with more barrier stalls: 7.1 ms against
+// 4.75 ms per 1024 VGA frames (profiles/README.md). Kept as the measured alternative, not the default.
+constexpr int FEH_CAP = 32768;        // table slots (keys u32 + packed u16 counts = 192 KB)
+constexpr int FEH_PROBES = 64;        // an insert that does not find its slot within this many probes sends the frame to the radix path
+constexpr int FEH_RCAP = 4096;        // points staged per reduce chunk
+constexpr int FEH_LONG = 64;          // runs longer than this are sorted and summed by a whole warp
+constexpr int FEH_MAXRUN = 2048;      // longest run (points of one voxel) the path handles; longer: radix path
+constexpr int FEH_SMEM = FEH_CAP * 4 + FEH_CAP * 2 + 1024 * FE_ITEMS * 2;   // table + counts + selection tile = 212 992 B
 template <int NT>
 constexpr int fe_dyn_smem() {   // A: selection + depth tile + masks; B: digit counters + two prefetched key tiles; C2: staging + heads
-    return fe_max(fe_max(NT * 32 + FE_MASK_BYTES, NT * 32 + 2 * NT * FE_ITEMS * 8), (NT * FE_RITEMS + FE_LOOK) * 20 + NT * FE_RITEMS * 2);
+    return fe_max(fe_max(fe_max(NT * 32 + FE_MASK_BYTES, NT * 32 + 2 * NT * FE_ITEMS * 8), (NT * FE_RITEMS + FE_LOOK) * 20 + NT * FE_RITEMS * 2),
+                  NT == 1024 ? FEH_SMEM : 0);
+}
+// global scratch of one slot on the hash path (inside FrontArgs::keys): two record buffers, voxel start offsets, slot id per
+// point, point indices grouped by voxel
+struct FehScratch {
+    unsigned long long* recA; unsigned long long* recB; unsigned int* vstart; unsigned short* slotid; unsigned int* sidx;
+};
+__host__ __device__ inline size_t feh_scratch_u64(int P) {   // u64 needed per slot
+    return (size_t)2 * FEH_CAP + (size_t)(FEH_CAP + 8) / 2 + ((size_t)P * 2 + 7) / 8 + ((size_t)P * 4 + 7) / 8 + 8;
+}
+__device__ __forceinline__ FehScratch feh_scratch(unsigned long long* base, int P) {
+    FehScratch s;
+    s.recA = base; s.recB = base + FEH_CAP;
+    s.vstart = reinterpret_cast<unsigned int*>(base + 2 * FEH_CAP);
+    unsigned long long* q = base + 2 * FEH_CAP + (FEH_CAP + 8) / 2;
+    s.slotid = reinterpret_cast<unsigned short*>(q);
+    s.sidx = reinterpret_cast<unsigned int*>(q + ((size_t)P * 2 + 7) / 8);
+    return s;
 }
 // asynchronous global -> shared copies (LDGSTS): the next tile of sort records is on its way while this one is ranked
 __device__ __forceinline__ void fe_cp_async16(void* smem, const void* gmem) {
@@ -171,6 +203,396 @@ __device__ __forceinline__ int fe_run_step(FeRun& r, bool match, float ax, float
     return nmatch;
 }
 
+// static shared memory of k_frontend the hash path borrows
+struct FehStatic {
+    int* s_w;                       // [NT/32 + 1] block scan scratch
+    unsigned int (*s_histA)[256];   // [4][256] digit histograms of the record sort
+    unsigned int* s_base;           // [256]
+    unsigned long long* s_h64;      // [2 * NT/32]
+    int* s_ndef; int* s_def_lp; int* s_def_pos;   // deferred (long) runs of a reduce chunk
+    int* s_misc;                    // [8]: distinct voxels, abort flag, max count, chunk end
+};
+
+__device__ __forceinline__ int fe_bitlen(int v) { return v <= 0 ? 0 : 32 - __clz(v); }
+
+// Voxel-hash path for ONE frame (NT = 1024 threads, cluster size 1). On entry A1 has run: s_f.N survivors, geometry g.
+// Returns false (nothing usable written except pts / kpp, which the radix path rewrites identically) when the frame does not fit
+// the path: too many distinct voxels, a voxel with more than FEH_MAXRUN points, or more than 30 key bits.
+//   A2h  one pass over the inputs: unproject / filter (recomputed: no room for A1's keep masks), ordered compaction, point store,
+//        then per survivor the voxel's (i, j, k) packed into a key whose order is the order of PCL's idx = i + j*dx + k*dx*dy
+//        (k in the top bits), find-or-insert in the table, count += 1, slot id -> global
+//   Bh   occupied slots -> (key, slot, count) records; stable LSD radix sort of the V records (not of the N points)
+//   Ch   prefix sum of the counts in key order: vstart[r]; cursor[slot] = vstart[r]
+//   Dh   every point index to cursor[slot]++: the points of a voxel become one contiguous run (in no particular order)
+//   Eh   chunks of whole runs staged in shared memory: each run is sorted ascending (= the stable order of the radix path), the
+//        points are gathered, ONE THREAD PER VOXEL sums its run sequentially (long runs: a whole warp), centroids out
+template <int SRC, int NT>
+__device__ __forceinline__ bool fe_hash_frame(const FrontArgs& a, int f, int n_in, int N, const VoxelGeom& g, unsigned long long* slot_scratch,
+                                              unsigned char* fe_dyn, const FehStatic& st) {
+    static_assert(NT == 1024, "the hash path is laid out for one 1024-thread CTA per SM");
+    constexpr int NW = NT / 32;
+    const PreArgs& p = a.pre;
+    const int tid = threadIdx.x, lane = tid & 31, wid = tid >> 5;
+    const int b0 = fe_bitlen(g.div_b[0] - 1), b1 = fe_bitlen(g.div_b[1] - 1), b2 = fe_bitlen(g.div_b[2] - 1);
+    const int kbits = b0 + b1 + b2;
+    auto why = [&](int code) { if (a.hash == 2 && threadIdx.x == 0) atomicOr(&a.pre.res[f].status, code << 8); };   // developer: CUBOID_FE_HASH=2
+    if (kbits > 30 || g.overflow_mode) { why(1); return false; }
+    unsigned int* s_tab = reinterpret_cast<unsigned int*>(fe_dyn);
+    unsigned int* s_cnt = s_tab + FEH_CAP;                       // two u16 counts per word
+    unsigned short* s_sel = reinterpret_cast<unsigned short*>(s_cnt + FEH_CAP / 2);
+    const FehScratch gs = feh_scratch(slot_scratch, a.P);
+    int* s_misc = st.s_misc;
+    for (int i = tid; i < FEH_CAP; i += NT) s_tab[i] = 0xffffffffu;
+    for (int i = tid; i < FEH_CAP / 2; i += NT) s_cnt[i] = 0u;
+    if (tid < 8) s_misc[tid] = 0;
+    __syncthreads();
+
+    // ---- A2h ----
+    {
+        constexpr int HT = NT * FE_ITEMS;   // inputs per tile
+        float4* out = p.pts + (size_t)f * p.Pout;
+        int* kpp = a.kpp ? a.kpp + (size_t)f * a.P : nullptr;
+        int run = 0;
+        unsigned long long hh[2] = {0ull, 0ull};
+        for (int t0 = 0; t0 < n_in; t0 += HT) {
+            const int first = t0 + tid * FE_ITEMS;
+            unsigned int keep = 0;
+            if (first < n_in) {
+                float px[FE_ITEMS], py[FE_ITEMS], pz[FE_ITEMS];
+                keep = pre_points<SRC>(p, f, first, n_in, px, py, pz);
+            }
+            int total;
+            int lp = block_excl_scan<NT>(__popc(keep), st.s_w, &total);
+#pragma unroll
+            for (int k = 0; k < FE_ITEMS; ++k)
+                if (keep & (1u << k)) s_sel[lp++] = (unsigned short)(tid * FE_ITEMS + k);
+            __syncthreads();
+            for (int q = tid; q < total; q += NT) {
+                const int sel = (int)s_sel[q];
+                // the depth value was read a moment ago by pre_points: it comes from L1 / L2
+                const float4 pt = SRC == 0 ? fe_point_from_depth(p, t0 + sel, __ldg(p.depth + (size_t)f * p.P + t0 + sel)) : fe_point_at<SRC>(p, f, t0 + sel);
+                const int pos = run + q;
+                out[pos] = pt;
+                // the three terms of voxel_index (common.cuh), kept apart
+                const int i0 = (int)(floorf(pt.x * g.inv) - (float)g.min_b[0]);
+                const int i1 = (int)(floorf(pt.y * g.inv) - (float)g.min_b[1]);
+                const int i2 = (int)(floorf(pt.z * g.inv) - (float)g.min_b[2]);
+                const unsigned int key = (unsigned int)i0 | ((unsigned int)i1 << b0) | ((unsigned int)i2 << (b0 + b1));
+                unsigned int h = (key * 2654435761u) >> 17;     // 15 bits
+                bool placed = false;
+                const bool aborted = *reinterpret_cast<volatile int*>(&s_misc[1]) != 0;   // the frame is going to the radix path anyway: skip the probing
+                for (int probe = 0; probe < FEH_PROBES && !aborted; ++probe) {
+                    const unsigned int cur = s_tab[h];
+                    if (cur == key) { placed = true; break; }
+                    if (cur == 0xffffffffu) {
+                        const unsigned int old = atomicCAS(&s_tab[h], 0xffffffffu, key);
+                        if (old == 0xffffffffu || old == key) { placed = true; break; }
+                    }
+                    h = (h + 1) & (FEH_CAP - 1);
+                }
+                if (!placed) { s_misc[1] = 1; h = 0; }       // table (nearly) full: more distinct voxels than the path is built for
+                const unsigned int sh16 = (h & 1u) * 16u;
+                const unsigned int oldc = atomicAdd(&s_cnt[h >> 1], 1u << sh16);
+                if (((oldc >> sh16) & 0xffffu) == 0xffffu) s_misc[1] = 1;   // the packed count overflowed into its neighbour
+                gs.slotid[pos] = (unsigned short)h;
+                if (kpp || a.hashes) {
+                    const int idx = (int)((unsigned int)i0 + (unsigned int)i1 * g.mul1 + (unsigned int)i2 * g.mul2);
+                    if (kpp) kpp[pos] = idx;
+                    if (a.hashes) {
+                        hh[0] += hash_point((unsigned int)pos, pt.x, pt.y, pt.z);
+                        hh[1] += hash_index((unsigned int)pos, idx);
+                    }
+                }
+            }
+            run += total;
+            __syncthreads();
+        }
+        if (s_misc[1]) { why(2); return false; }    // block-uniform: nobody writes the flag after the last barrier of the loop
+        // the parity hashes are committed only when the path completes (the radix path would add them again otherwise)
+        fe_block_sum_u64<NT, 2>(hh, st.s_h64);
+        __syncthreads();
+        if (tid == 0) { st.s_h64[0] = hh[0]; st.s_h64[1] = hh[1]; }
+        __syncthreads();
+    }
+    const int npass = (kbits + 7) / 8;
+
+    // ---- Bh: records of the occupied slots, digit histograms of every pass, longest run ----
+    {
+        for (int k = tid; k < 4 * 256; k += NT) (&st.s_histA[0][0])[k] = 0u;
+        __syncthreads();
+        constexpr int PER = FEH_CAP / NT;   // 32 consecutive slots per thread
+        int occ = 0, mx = 0;
+#pragma unroll 4
+        for (int j = 0; j < PER; ++j) occ += (s_tab[tid * PER + j] != 0xffffffffu) ? 1 : 0;
+        int total;
+        int wp = block_excl_scan<NT>(occ, st.s_w, &total);
+        for (int j = 0; j < PER; ++j) {
+            const int sl = tid * PER + j;
+            const unsigned int key = s_tab[sl];
+            if (key == 0xffffffffu) continue;
+            const unsigned int c = (s_cnt[sl >> 1] >> ((sl & 1) * 16)) & 0xffffu;
+            mx = max(mx, (int)c);
+            __stcg(gs.recA + wp, ((unsigned long long)key << 32) | ((unsigned long long)sl << 16) | (unsigned long long)c);
+            ++wp;
+            for (int ps = 0; ps < npass; ++ps) atomicAdd(&st.s_histA[ps][(key >> (8 * ps)) & 255u], 1u);
+        }
+        atomicMax(&s_misc[2], mx);
+        if (tid == 0) s_misc[0] = total;
+        __syncthreads();
+        if (s_misc[2] > FEH_MAXRUN) { why(4); return false; }
+    }
+    const int V = s_misc[0];
+    // stable LSD radix sort of the V records by key (the radix path's tile code, one CTA, global ping-pong recA <-> recB)
+    {
+        constexpr int TILE = NT * FE_ITEMS;
+        unsigned int (*s_cntw)[256] = reinterpret_cast<unsigned int (*)[256]>(fe_dyn);   // the table is dead from here on
+        for (int pass = 0; pass < npass; ++pass) {
+            const unsigned long long* src = (pass & 1) ? gs.recB : gs.recA;
+            unsigned long long* dst = (pass & 1) ? gs.recA : gs.recB;
+            const int shift = 32 + pass * 8;
+            {
+                const unsigned int tot = tid < 256 ? st.s_histA[pass][tid] : 0u;
+                int total;
+                const int ex = block_excl_scan<NT>((int)tot, st.s_w, &total);
+                if (tid < 256) st.s_base[tid] = (unsigned int)ex;
+                __syncthreads();
+            }
+            for (int t0 = 0; t0 < V; t0 += TILE) {
+                for (int d = lane; d < 256; d += 32) s_cntw[wid][d] = 0;
+                __syncwarp();
+                unsigned long long key[FE_ITEMS];
+                unsigned int rank[FE_ITEMS];
+#pragma unroll
+                for (int k = 0; k < FE_ITEMS; ++k) {
+                    const int i = t0 + wid * (32 * FE_ITEMS) + k * 32 + lane;
+                    key[k] = i < V ? __ldcg(src + i) : ~0ull;
+                }
+#pragma unroll
+                for (int k = 0; k < FE_ITEMS; ++k) {
+                    const int i = t0 + wid * (32 * FE_ITEMS) + k * 32 + lane;
+                    const bool valid = i < V;
+                    const unsigned int d = valid ? ((unsigned int)(key[k] >> shift) & 255u) : 256u;
+                    const unsigned int peers = fe_digit_peers(d);
+                    const int leader = __ffs(peers) - 1;
+                    unsigned int before = 0;
+                    if (valid && lane == leader) { before = s_cntw[wid][d]; s_cntw[wid][d] = before + __popc(peers); }
+                    before = __shfl_sync(FULL_MASK, before, leader);
+                    rank[k] = before + __popc(peers & ((1u << lane) - 1u));
+                    __syncwarp();
+                }
+                __syncthreads();
+                if (tid < 256) {
+                    unsigned int runb = st.s_base[tid];
+#pragma unroll 8
+                    for (int ww = 0; ww < NW; ++ww) { const unsigned int c = s_cntw[ww][tid]; s_cntw[ww][tid] = runb; runb += c; }
+                    st.s_base[tid] = runb;
+                }
+                __syncthreads();
+#pragma unroll
+                for (int k = 0; k < FE_ITEMS; ++k) {
+                    const int i = t0 + wid * (32 * FE_ITEMS) + k * 32 + lane;
+                    if (i < V) {
+                        const unsigned int d = (unsigned int)(key[k] >> shift) & 255u;
+                        __stcg(dst + s_cntw[wid][d] + rank[k], key[k]);
+                    }
+                }
+                __syncthreads();
+            }
+        }
+    }
+    const unsigned long long* recs = (npass & 1) ? gs.recB : gs.recA;
+
+    // ---- Ch: vstart[r] = first grouped position of voxel r (key order); cursor[slot] = the same ----
+    unsigned int* s_cursor = reinterpret_cast<unsigned int*>(fe_dyn);
+    {
+        int carry = 0;
+        for (int r0 = 0; r0 < V; r0 += NT) {
+            const int r = r0 + tid;
+            const unsigned long long rec = r < V ? __ldcg(recs + r) : 0ull;
+            const int c = (int)(rec & 0xffffull);
+            int total;
+            const int ex = carry + block_excl_scan<NT>(c, st.s_w, &total);
+            if (r < V) {
+                __stcg(gs.vstart + r, (unsigned int)ex);
+                s_cursor[(unsigned int)(rec >> 16) & 0x7fffu] = (unsigned int)ex;
+            }
+            carry += total;
+            __syncthreads();
+        }
+        if (tid == 0) __stcg(gs.vstart + V, (unsigned int)carry);
+        if (carry != N) { why(16); return false; }   // cannot happen; never publish a frame whose counts do not add up
+    }
+    __syncthreads();
+    // ---- Dh: group the point indices by voxel. Every warp takes a contiguous range of the points and walks it in order; inside a
+    //      warp a run of consecutive points of one voxel (the usual case in raster order) claims its places with ONE atomic, so the
+    //      points of a voxel arrive in ascending order except where two warps' ranges meet: Eh's sort has next to nothing to do ----
+    {
+        const int per = (((N + NW - 1) / NW) + 31) & ~31;
+        const int w0 = min(N, wid * per), w1 = min(N, wid * per + per);
+        for (int b = w0; b < w1; b += 32) {
+            const int pos = b + lane;
+            const bool v = pos < w1;
+            const unsigned int sl = v ? (unsigned int)__ldcg(gs.slotid + pos) : 0xffffffffu;
+            const unsigned int prev = __shfl_up_sync(FULL_MASK, sl, 1);
+            const bool head = v && (lane == 0 || sl != prev);
+            const unsigned int hm = __ballot_sync(FULL_MASK, head), vm = __ballot_sync(FULL_MASK, v);
+            const int hl = max(0, 31 - __clz(hm & (0xffffffffu >> (31 - lane))));   // the head of this lane's run
+            unsigned int dest = 0;
+            if (head) {
+                const unsigned int above = hm & ~((2u << lane) - 1u);
+                const int nxt = above ? (__ffs(above) - 1) : __popc(vm);            // valid lanes are a prefix of the warp
+                dest = atomicAdd(&s_cursor[sl], (unsigned int)(nxt - lane));
+            }
+            dest = __shfl_sync(FULL_MASK, dest, hl);
+            if (v) __stcg(gs.sidx + dest + (unsigned int)(lane - hl), (unsigned int)pos);
+        }
+    }
+    __syncthreads();
+
+    // ---- Eh: sorted runs -> sequential float centroids ----
+    {
+        unsigned int* s_idx = reinterpret_cast<unsigned int*>(fe_dyn);            // the cursors are dead from here on
+        float* s_px = reinterpret_cast<float*>(s_idx + FEH_RCAP);
+        float* s_py = s_px + FEH_RCAP;
+        float* s_pz = s_py + FEH_RCAP;
+        unsigned int* s_pw = reinterpret_cast<unsigned int*>(s_pz + FEH_RCAP);
+        unsigned int* s_big = s_pw + FEH_RCAP;                                    // [FEH_MAXRUN] bitonic scratch of one long run per warp round
+        const float4* pts = p.pts + (size_t)f * p.Pout;
+        float4* vox = a.vox + (size_t)f * a.P;
+        int* vcount = a.vcount ? a.vcount + (size_t)f * a.P : nullptr;
+        unsigned long long hv[1] = {0ull};
+        int r0 = 0;
+        while (r0 < V) {
+            const unsigned int base = __ldcg(gs.vstart + r0);
+            const int r = r0 + tid;
+            unsigned int s = 0, e = 0;
+            bool fits = false;
+            if (r < V) { s = __ldcg(gs.vstart + r); e = __ldcg(gs.vstart + r + 1); fits = (e - base) <= (unsigned int)FEH_RCAP; }
+            const int nv = __syncthreads_count(fits ? 1 : 0);     // runs are contiguous: the fitting voxels are a prefix
+            if (tid == nv - 1) s_misc[3] = (int)(e - base);
+            if (tid == 0) *st.s_ndef = 0;
+            __syncthreads();
+            const int npts = s_misc[3];
+            for (int l = tid; l < npts; l += NT) s_idx[l] = __ldcg(gs.sidx + base + l);
+            __syncthreads();
+            const int lp = (int)(s - base), c = (int)(e - s);
+            bool deferred = false;
+            if (tid < nv) {
+                if (c <= FEH_LONG) {
+                    for (int i = lp + 1; i < lp + c; ++i) {      // insertion sort: ascending point index
+                        const unsigned int v = s_idx[i];
+                        int j = i - 1;
+                        while (j >= lp && s_idx[j] > v) { s_idx[j + 1] = s_idx[j]; --j; }
+                        s_idx[j + 1] = v;
+                    }
+                } else {
+                    deferred = true;
+                    const int d = atomicAdd(st.s_ndef, 1);
+                    if (d < FE_MAXDEF) { st.s_def_lp[d] = lp; st.s_def_pos[d] = tid; }
+                }
+            }
+            __syncthreads();
+            const int ndef = min(*st.s_ndef, FE_MAXDEF);          // <= RCAP / LONG = 64 = FE_MAXDEF long runs fit a chunk
+            // long runs arrive sorted unless several warps contributed to them (Dh): a warp checks each, and only the unsorted ones
+            // (the origin voxel that collects the zero-depth pixels of the whole frame, voxels where two ranges meet) are sorted,
+            // one after the other, by a block-wide bitonic network in the scratch (padded with ~0 to a power of two)
+            for (int d = wid; d < ndef; d += NW) {
+                const int dl = st.s_def_lp[d];
+                const int vt = st.s_def_pos[d] & 0xffff;
+                const int dc = (int)(__ldcg(gs.vstart + r0 + vt + 1) - __ldcg(gs.vstart + r0 + vt));
+                bool bad = false;
+                for (int i = lane; i + 1 < dc; i += 32) bad = bad || (s_idx[dl + i] > s_idx[dl + i + 1]);
+                bad = __any_sync(FULL_MASK, bad);
+                if (lane == 0) st.s_def_pos[d] = vt | (bad ? 0x10000 : 0);
+            }
+            __syncthreads();
+            for (int d = 0; d < ndef; ++d) {
+                if (!(st.s_def_pos[d] & 0x10000)) continue;        // block-uniform
+                const int dl = st.s_def_lp[d];
+                const int vt = st.s_def_pos[d] & 0xffff;
+                const int dc = (int)(__ldcg(gs.vstart + r0 + vt + 1) - __ldcg(gs.vstart + r0 + vt));
+                int n2 = 64;
+                while (n2 < dc) n2 <<= 1;
+                for (int i = tid; i < n2; i += NT) s_big[i] = i < dc ? s_idx[dl + i] : 0xffffffffu;
+                __syncthreads();
+                for (int k = 2; k <= n2; k <<= 1)
+                    for (int j = k >> 1; j > 0; j >>= 1) {
+                        for (int t = tid; t < n2; t += NT) {
+                            const int u = t ^ j;
+                            if (u > t) {
+                                const unsigned int x = s_big[t], y = s_big[u];
+                                const bool up = (t & k) == 0;
+                                if ((x > y) == up) { s_big[t] = y; s_big[u] = x; }
+                            }
+                        }
+                        __syncthreads();
+                    }
+                for (int i = tid; i < dc; i += NT) s_idx[dl + i] = s_big[i];
+                __syncthreads();
+            }
+            for (int l = tid; l < npts; l += NT) {
+                const float4 pt = __ldcg(pts + s_idx[l]);
+                s_px[l] = pt.x; s_py[l] = pt.y; s_pz[l] = pt.z;
+                if (a.rgb) s_pw[l] = __float_as_uint(pt.w);
+            }
+            __syncthreads();
+            if (tid < nv && !deferred) {
+                float sx = s_px[lp], sy = s_py[lp], sz = s_pz[lp];   // centroid starts as the first point, then += in ascending point order
+                for (int q = lp + 1; q < lp + c; ++q) { sx += s_px[q]; sy += s_py[q]; sz += s_pz[q]; }
+                const float cnt = (float)c;
+                const float cx = sx / cnt, cy = sy / cnt, cz = sz / cnt;
+                float cw = 1.0f;
+                if (a.rgb) {
+                    unsigned int sr = 0, sg = 0, sb = 0;
+                    for (int q = lp; q < lp + c; ++q) { const unsigned int w = s_pw[q]; sr += (w >> 16) & 255u; sg += (w >> 8) & 255u; sb += w & 255u; }
+                    cw = fe_rgb_avg(sr, sg, sb, c);
+                }
+                vox[r] = make_float4(cx, cy, cz, cw);
+                if (vcount) vcount[r] = c;
+                if (a.hashes) hv[0] += hash_point((unsigned int)r, cx, cy, cz);
+            }
+            for (int d = wid; d < ndef; d += NW) {   // long runs: a whole warp, lane-parallel loads, in-order sums (fe_run_step)
+                const int dl = st.s_def_lp[d];
+                const int vt = st.s_def_pos[d] & 0xffff;
+                const int dc = (int)(__ldcg(gs.vstart + r0 + vt + 1) - __ldcg(gs.vstart + r0 + vt));
+                FeRun acc;
+                acc.sx = s_px[dl]; acc.sy = s_py[dl]; acc.sz = s_pz[dl]; acc.cnt = 1;
+                {
+                    const unsigned int w0 = a.rgb ? s_pw[dl] : 0u;
+                    acc.sr = (w0 >> 16) & 255u; acc.sg = (w0 >> 8) & 255u; acc.sb = w0 & 255u;
+                }
+                for (int l = dl + 1; l < dl + dc; l += 32) {
+                    const int i = l + lane;
+                    const bool m = i < dl + dc;
+                    fe_run_step(acc, m, m ? s_px[i] : 0.f, m ? s_py[i] : 0.f, m ? s_pz[i] : 0.f, (m && a.rgb) ? s_pw[i] : 0u);
+                }
+                if (lane == 0) {
+                    const float cf = (float)acc.cnt;
+                    const float cx = acc.sx / cf, cy = acc.sy / cf, cz = acc.sz / cf;
+                    const int vp = r0 + vt;
+                    vox[vp] = make_float4(cx, cy, cz, a.rgb ? fe_rgb_avg(acc.sr, acc.sg, acc.sb, acc.cnt) : 1.0f);
+                    if (vcount) vcount[vp] = acc.cnt;
+                    if (a.hashes) hv[0] += hash_point((unsigned int)vp, cx, cy, cz);
+                }
+            }
+            __syncthreads();
+            r0 += nv;
+        }
+        // commit: voxel count and parity hashes
+        const unsigned long long h0 = st.s_h64[0], h1 = st.s_h64[1];
+        __syncthreads();
+        fe_block_sum_u64<NT, 1>(hv, st.s_h64);
+        if (tid == 0) {
+            p.res[f].n_voxels = V;
+            if (a.hash == 2) atomicOr(&p.res[f].status, 32 << 8);
+            if (h0) atomic_add_u64(&p.res[f].points_hash, h0);
+            if (h1) atomic_add_u64(&p.res[f].voxel_key_hash, h1);
+            if (hv[0]) atomic_add_u64(&p.res[f].voxel_hash, hv[0]);
+        }
+    }
+    return true;
+}
+
 template <int SRC, int NT>
 __global__ void __launch_bounds__(NT, 2048 / NT >= 2 ? (NT <= 512 ? 2 : 1) : 1) k_frontend(const FrontArgs a) {
     constexpr int NW = NT / 32;
@@ -186,6 +608,7 @@ __global__ void __launch_bounds__(NT, 2048 / NT >= 2 ? (NT <= 512 ? 2 : 1) : 1) 
     __shared__ float s_mm[NW][6];
     __shared__ int s_wc[NW];
     __shared__ unsigned long long s_h64[2 * NW];
+    __shared__ int s_misc[8];              // hash path: distinct voxels, abort flag, longest run, chunk size
     __shared__ int s_ndef;                 // voxels of the current reduce tile deferred to the warp-cooperative routine
     __shared__ int s_def_lp[FE_MAXDEF], s_def_pos[FE_MAXDEF];
 
@@ -194,7 +617,7 @@ __global__ void __launch_bounds__(NT, 2048 / NT >= 2 ? (NT <= 512 ? 2 : 1) : 1) 
     const int slot = blockIdx.x / C, nslots = gridDim.x / C;
     const int tid = threadIdx.x, lane = tid & 31, wid = tid >> 5;
     const PreArgs& p = a.pre;
-    unsigned long long* bufA = a.keys + (size_t)slot * 2 * a.P;
+    unsigned long long* bufA = a.keys + (size_t)slot * a.keys_stride;
     unsigned long long* bufB = bufA + a.P;
 
     for (int f = slot; f < a.n_frames; f += nslots) {
@@ -203,7 +626,8 @@ __global__ void __launch_bounds__(NT, 2048 / NT >= 2 ? (NT <= 512 ? 2 : 1) : 1) 
         slice = (slice + 7) & ~7;
         const int s0 = min(n_in, r * slice), s1 = min(n_in, r * slice + slice);
         unsigned char* s_mask = fe_dyn + NT * 32;
-        const bool use_mask = ((slice + TILE - 1) / TILE) * NT <= FE_MASK_BYTES;
+        const bool hash_try = NT == 1024 && C == 1 && a.hash != 0;    // the hash path recomputes the masks (its table takes their room)
+        const bool use_mask = !hash_try && ((slice + TILE - 1) / TILE) * NT <= FE_MASK_BYTES;
 
         // ---- A1: survivors and min/max of this CTA's input slice ----
         {
@@ -297,6 +721,16 @@ __global__ void __launch_bounds__(NT, 2048 / NT >= 2 ? (NT <= 512 ? 2 : 1) : 1) 
         }
         const VoxelGeom g = s_f.g;
         const int npass = (g.sort_bits + 7) / 8;
+        if constexpr (NT == 1024) {
+            if (hash_try) {
+                FehStatic st;
+                st.s_w = s_w; st.s_histA = s_histA; st.s_base = s_base; st.s_h64 = s_h64; st.s_ndef = &s_ndef; st.s_def_lp = s_def_lp;
+                st.s_def_pos = s_def_pos; st.s_misc = s_misc;
+                const bool done = fe_hash_frame<SRC, NT>(a, f, n_in, N, g, bufA, fe_dyn, st);
+                __syncthreads();
+                if (done) { cluster.sync(); continue; }
+            }
+        }
         if (C == 1) {
             for (int k = tid; k < 4 * 256; k += NT) (&s_histA[0][0])[k] = 0u;
             __syncthreads();

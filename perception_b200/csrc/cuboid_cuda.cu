@@ -59,7 +59,7 @@ struct cuboid_handle {
     int *d_parent = nullptr, *d_csize = nullptr, *d_crank = nullptr, *d_idx_sorted = nullptr, *d_offsets = nullptr, *d_roots = nullptr, *d_cell_head = nullptr; float4* d_cell_pts = nullptr;
     float4* d_cur = nullptr; int* d_corr = nullptr; float* d_cd = nullptr; int* d_order = nullptr; int* d_miss = nullptr; IcpOut* d_icp_out = nullptr;
     IcpState* d_icp_state = nullptr; IcpSlot* d_icp_ring = nullptr; IcpQueue* d_icp_queue = nullptr;   // persistent time-sliced k_icp
-    int icp_slice_iters = 8; int icp_ctas = 0; int icp_outward = 1; int icp_queued = 1; int smem_sm = 0; int icp_nsub_force = 0;
+    int icp_slice_iters = 8; int icp_ctas = 0; int icp_outward = 1; int icp_queued = 1; int icp_local = 1; int smem_sm = 0; int icp_nsub_force = 0;
     size_t icp_scratch_elems = 0; size_t icp_out_elems = 0; size_t icp_queue_frames = 0;
     FrameScratch* d_scr = nullptr;
     unsigned long long *d_desc1 = nullptr, *d_desc2 = nullptr;
@@ -89,6 +89,7 @@ struct cuboid_handle {
     struct { int active = 0; int model_type = 0; float axis[3] = {0, 0, 0}; double eps = 0.0, thr = 0.0; } sac_override;   // cuboid_surface_normals
     // fused front end (frontend.cuh): one thread-block cluster per frame, persistent over the chunk
     int frontend = 1; int fe_cluster = 1; int fe_threads = 512; int fe_slots = 0; unsigned long long* d_fe_keys = nullptr;
+    int fe_cluster_small = 0; int sms = 0;   // cluster size used when a launch has so few frames that one CTA per frame would leave most SMs idle (single-frame latency)
     int fe_hash = 0; size_t fe_stride = 0;   // voxel-hash path of k_frontend (opt-in: CUBOID_FE_HASH=1; 1024 threads, one CTA per SM) and the per-slot scratch size in u64
     // host-buffer batches: sub-chunks run end to end on a few streams, so copies, front end and ICP of different sub-chunks overlap
     static constexpr int NPIPE = 4; cudaStream_t pipe[NPIPE] = {}; cudaEvent_t pipe_done[NPIPE] = {}; unsigned long long* d_pipe_keys[NPIPE] = {}; int pipeline = 1;
@@ -289,12 +290,15 @@ int run_chunk(cuboid_handle* h, const ChunkIn& in, int nf, cuboid_frame_result* 
         if (in.in_stride > h->P) return CUBOID_E_CAPACITY;
         fa.keys = fe_keys_override ? fe_keys_override : h->d_fe_keys; fa.kpp = h->taps ? b_kpp : nullptr; fa.vox = b_vox; fa.vcount = h->taps ? b_vcount : nullptr;
         fa.inv_leaf = 1.0f / p.leaf; fa.P = h->P; fa.n_frames = nf; fa.hashes = h->taps ? 1 : 0;
-        fa.keys_stride = h->fe_stride; fa.hash = (h->fe_hash && h->fe_threads == 1024 && h->fe_cluster == 1) ? h->fe_hash : 0;
+        // few frames (a ROS callback passes ONE): a thread-block cluster per frame spreads it over 8 SMs (DSMEM exchange inside k_frontend)
+        int fe_c = h->fe_cluster;
+        if (fe_c == 1 && h->fe_cluster_small > 1 && (long long)nf * h->fe_cluster_small <= h->sms) fe_c = h->fe_cluster_small;
+        fa.keys_stride = h->fe_stride; fa.hash = (h->fe_hash && h->fe_threads == 1024 && fe_c == 1) ? h->fe_hash : 0;
         cudaLaunchConfig_t cfg{};
         cudaLaunchAttribute at[1];
         at[0].id = cudaLaunchAttributeClusterDimension;
-        at[0].val.clusterDim.x = h->fe_cluster; at[0].val.clusterDim.y = 1; at[0].val.clusterDim.z = 1;
-        cfg.gridDim = dim3((unsigned int)(std::min(h->fe_slots, nf) * h->fe_cluster));
+        at[0].val.clusterDim.x = fe_c; at[0].val.clusterDim.y = 1; at[0].val.clusterDim.z = 1;
+        cfg.gridDim = dim3((unsigned int)(std::min(h->fe_slots, nf) * fe_c));
         cfg.blockDim = dim3((unsigned int)h->fe_threads);
         cfg.dynamicSmemBytes = (size_t)fe_smem(h->fe_threads);
         cfg.stream = st;
@@ -449,8 +453,13 @@ int run_chunk(cuboid_handle* h, const ChunkIn& in, int nf, cuboid_frame_result* 
         const long long nprob = (long long)nf * ng;
         a.nsub = nprob >= 4LL * a.crew ? 4 : (nprob >= 2LL * a.crew ? 2 : 1);
         if (h->icp_nsub_force) a.nsub = h->icp_nsub_force;
-        k_icp_init<<<dim3(ng, CUBOID_MAX_CLUSTERS, nf), ICP_THREADS, a.init_smem, st>>>(a);
         const int mode = a.tmode ? 3 : (a.qmode ? 2 : (a.resident ? 1 : 0));
+        a.local_cap = 0;
+        if (mode == 3 && a.nsub == 1 && h->icp_local) {   // the rest of the shared memory holds the working set (24 B per point) of the CTA's problem
+            a.local_cap = (int)std::min<size_t>(((size_t)h->icp_smem_budget - dyn) / 24, (size_t)h->M);
+            dyn += (size_t)a.local_cap * 24;
+        }
+        k_icp_init<<<dim3(ng, CUBOID_MAX_CLUSTERS, nf), ICP_THREADS, a.init_smem, st>>>(a);
         auto kfn = icp_kernel(a.nsub, mode);
         kfn<<<a.crew, ICP_NT, dyn, st>>>(a);   // workers beyond the number of real problems leave at once
         const int tot = nf * CUBOID_MAX_CLUSTERS;
@@ -617,6 +626,7 @@ static int create_impl(cuboid_handle** out, const cuboid_params* p, int device, 
         const char* eo = std::getenv("CUBOID_ICP_OUTWARD"); if (eo) h->icp_outward = atoi(eo) ? 1 : 0;
         const char* en = std::getenv("CUBOID_ICP_NSUB"); if (en) h->icp_nsub_force = (atoi(en) == 1 || atoi(en) == 2 || atoi(en) == 4) ? atoi(en) : 0;
         const char* eq = std::getenv("CUBOID_ICP_QUEUED"); if (eq) h->icp_queued = atoi(eq) ? 1 : 0;
+        const char* el = std::getenv("CUBOID_ICP_LOCAL"); if (el) h->icp_local = atoi(el) ? 1 : 0;
         const char* etb = std::getenv("CUBOID_ICP_TABLE"); if (etb) h->icp_table = atoi(etb) ? 1 : 0;
         const char* eh = std::getenv("CUBOID_NNT_H_MM"); if (eh && atof(eh) > 0.0) h->nnt_h = atof(eh) * 1e-3;
         cudaDeviceGetAttribute(&h->smem_sm, cudaDevAttrMaxSharedMemoryPerMultiprocessor, device);
@@ -649,6 +659,23 @@ static int create_impl(cuboid_handle** out, const cuboid_params* p, int device, 
             if (cudaOccupancyMaxActiveClusters(&ncl, fns[h->fe_threads == 512 ? 0 : 2], &cfg) == cudaSuccess && ncl > 0) { h->fe_slots = ncl; break; }
             cudaGetLastError();
             if (h->fe_cluster == 1) break;
+        }
+        h->sms = sms;
+        if (h->fe_cluster == 1) {   // can 8-CTA clusters of this configuration be resident? then small launches use them
+            const char* es = std::getenv("CUBOID_FE_CLUSTER_SMALL");
+            const int want = es ? std::max(1, std::min(8, atoi(es))) : 8;
+            for (int c = want; c > 1; c >>= 1) {
+                cudaLaunchConfig_t cfg{};
+                cudaLaunchAttribute at[1];
+                at[0].id = cudaLaunchAttributeClusterDimension;
+                at[0].val.clusterDim.x = c; at[0].val.clusterDim.y = 1; at[0].val.clusterDim.z = 1;
+                cfg.gridDim = dim3((unsigned int)((sms / c) * c)); cfg.blockDim = dim3((unsigned int)h->fe_threads);
+                cfg.dynamicSmemBytes = (size_t)fe_smem(h->fe_threads);
+                cfg.attrs = at; cfg.numAttrs = 1;
+                int ncl = 0;
+                if (cudaOccupancyMaxActiveClusters(&ncl, fns[h->fe_threads == 512 ? 0 : 2], &cfg) == cudaSuccess && ncl > 0) { h->fe_cluster_small = c; break; }
+                cudaGetLastError();
+            }
         }
         if (h->fe_slots < 1) { h->last_error = "k_frontend: no resident cluster configuration"; fprintf(stderr, "cuboid_create: %s\n", h->last_error.c_str()); return fail(CUBOID_E_CUDA); }
         h->fe_slots = std::min(h->fe_slots, std::max(1, h->B));
@@ -842,7 +869,7 @@ static int set_template_impl(cuboid_handle* h, int slot, const float* xyz, int s
     CK(h, cudaMemcpy(h->d_tmpl_orig[slot], orig.data(), sizeof(int) * orig.size(), cudaMemcpyHostToDevice));
     CK(h, cudaMemcpy(h->d_boxes[slot], packed.data(), sizeof(uint4) * packed.size(), cudaMemcpyHostToDevice));
     h->tmpl_n[slot] = n; h->tmpl_pad[slot] = pad; h->tmpl_nleaf[slot] = nleaf; h->tmpl_nnodes[slot] = (int)nodes.size();
-    // nearest-neighbour candidate table (nn_table.cuh): a dense grid of cells of side hcell around the template, 10 cells of margin
+    // nearest-neighbour candidate table (nn_table.cuh): a dense grid of cells of side hcell around the template, NNT_BAND cells of margin
     if (h->d_nnt[slot]) { cudaFree(h->d_nnt[slot]); h->d_nnt[slot] = nullptr; }
     h->nnt[slot] = NnTableView{};
     if (h->icp_table && h->d_orig16[slot]) {
@@ -854,8 +881,8 @@ static int set_template_impl(cuboid_handle* h, int slot, const float* xyz, int s
         }
         double hcell = h->nnt_h;
         long long dims[3] = {0, 0, 0};
-        for (int tries = 0; finite && tries < 64; ++tries) {   // widen the cells until the dense grid has at most 3M of them (96 MB)
-            const double band = 10.0 * hcell;
+        for (int tries = 0; finite && tries < 64; ++tries) {   // widen the cells until the dense grid has at most 3M of them (192 MB)
+            const double band = NNT_BAND * hcell;
             long long nv = 1;
             for (int d = 0; d < 3; ++d) { dims[d] = (long long)std::ceil((mx[d] - mn[d] + 2.0 * band) / hcell) + 1; nv *= dims[d]; }
             if (nv <= 3000000LL) break;
@@ -867,11 +894,11 @@ static int set_template_impl(cuboid_handle* h, int slot, const float* xyz, int s
             NnTableView view{};
             view.inv_h = (float)(1.0 / hcell);
             g.h = 1.0 / (double)view.inv_h;                 // the cell side the run-time index computation actually uses
-            for (int d = 0; d < 3; ++d) { view.org[d] = (float)(mn[d] - 10.0 * hcell); g.org[d] = (double)view.org[d]; }
+            for (int d = 0; d < 3; ++d) { view.org[d] = (float)(mn[d] - NNT_BAND * hcell); g.org[d] = (double)view.org[d]; }
             view.nx = g.nx = (int)dims[0]; view.ny = g.ny = (int)dims[1]; view.nz = g.nz = (int)dims[2];
-            g.delta = std::max(1.0e-3 * g.h, 2.0e-6 * (maxabs + 12.0 * hcell));   // >> the rounding of (q - org) * inv_h in float
-            g.band2 = (10.0 * g.h) * (10.0 * g.h);
-            CKS(h, dalloc(h, &h->d_nnt[slot], (size_t)(2 * nvox)));
+            g.delta = std::max(1.0e-3 * g.h, 2.0e-6 * (maxabs + (NNT_BAND + 2.0) * hcell));   // >> the rounding of (q - org) * inv_h in float
+            g.band2 = (NNT_BAND * g.h) * (NNT_BAND * g.h);
+            CKS(h, dalloc(h, &h->d_nnt[slot], (size_t)(4 * nvox)));
             k_nn_table_build<ICP_LEAF><<<(unsigned int)((nvox + NNT_THREADS - 1) / NNT_THREADS), NNT_THREADS, 0, h->stream>>>(
                 h->d_tmpl[slot], h->d_tmpl_orig[slot], n, g, h->d_nnt[slot]);
             ++h->launches;

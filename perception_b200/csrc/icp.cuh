@@ -61,6 +61,7 @@ struct IcpArgs {
     int tmode;
     int* miss;                     // [F][G][M] queries the table could not answer, per problem (visited by the BVH search afterwards)
     unsigned long long* stats;     // developer counters (only written when compiled with -DCUBOID_ICP_STATS), else ignored
+    int local_cap;                 // > 0: a sub-worker keeps the working set of a problem with at most this many points in shared memory (one sub-worker per CTA)
     int qmode;                     // 1: queued outward search (needs resident template, sibling chains, orig16 and the per-warp scratch)
     const float* guesses;    // n_guess * (16 | 9) or NULL
     int n_guess, guess_mode;
@@ -310,6 +311,7 @@ struct IcpShared {
     int done, converged, state, iters;
     int task;           // dynamic task counter of the nearest-neighbour pass
     int nmiss;          // queries of the current pass the candidate table could not answer
+    int pend;           // 1: Tm has not been applied to the working cloud yet (the next table pass does it while it reads the points)
     double prev_mse;
 };
 
@@ -377,6 +379,12 @@ __device__ __forceinline__ void icp_scan_leaf(const IcpArgs& a, const float* tp,
         }
     }
 }
+
+// Working-set loads of the ICP loop. In global memory cur / corr / cd travel between SMs from one time slice to the next, so they are
+// read at L2 (__ldcg: this SM's L1 may hold lines from an earlier slice). LOCAL = the slice keeps them in shared memory (launches
+// with one sub-worker per CTA and a cluster small enough: single-frame latency), where a plain load is right.
+template <bool LOCAL, typename T>
+__device__ __forceinline__ T icp_ld(const T* p) { if (LOCAL) return *p; else return __ldcg(p); }
 
 // ---- queued outward search: per-warp scratch in shared memory -----------------------------------------------------------
 constexpr int ICP_QCAP = 224;      // node work list entries per warp
@@ -491,7 +499,7 @@ __device__ __forceinline__ void icp_walk(const IcpArgs& a, const float* tp, cons
 //           4 of 32 lanes. A list that would overflow (queries still far from the template: many boxes survive) abandons the
 //           lists and finishes the task with the per-lane walk from the root, seeded with the best found so far.
 //   else    every lane walks its own survivors (icp_walk).
-template <bool RESIDENT, bool QUEUED>
+template <bool RESIDENT, bool QUEUED, bool LOCAL>
 __device__ __forceinline__ void icp_nn_pass(const IcpArgs& a, IcpShared& sh, const float* s_tmpl, const uint4* s_nodes, const unsigned short* s_sib,
                                             const unsigned short* s_orig, IcpWarpScr* wscr, const float4* cur, int S, const int* order, int* corr,
                                             float* cd, unsigned long long& evaluated) {
@@ -509,9 +517,9 @@ __device__ __forceinline__ void icp_nn_pass(const IcpArgs& a, IcpShared& sh, con
         const int k = task * 32 + lane;
         const bool valid = k < S;
         const int i = order[valid ? k : S - 1];   // 32 lanes = 32 spatial neighbours: coherent tree walks, broadcast loads
-        const float4 p = __ldcg(cur + i);   // cur / corr / cd travel between SMs from one time slice to the next: read them at L2
+        const float4 p = icp_ld<LOCAL>(cur + i);
         const float sx = p.x, sy = p.y, sz = p.z;
-        const int pos0 = __ldcg(corr + i);
+        const int pos0 = icp_ld<LOCAL>(corr + i);
         unsigned int nleaf_eval = 0;
         if (QUEUED) {
             IcpWarpScr& ws = *wscr;
@@ -660,8 +668,9 @@ __device__ __forceinline__ void icp_nn_pass(const IcpArgs& a, IcpShared& sh, con
 // Table pass of the nearest-neighbour search (nn_table.cuh): every query whose grid cell has a valid record scans the record's
 // <= 15 candidates (sorted by original index, strict '<': the canonical tie rule) and is done; the others are appended to the
 // problem's miss list, which the BVH search (icp_nn_pass) then visits instead of `order`.
-__device__ __forceinline__ void icp_nn_table_pass(const IcpArgs& a, IcpShared& sh, const float* tp, const float4* cur, int S, const int* order,
-                                                  int* corr, float* cd, int* miss, unsigned long long& evaluated) {
+template <bool LOCAL>
+__device__ __forceinline__ void icp_nn_table_pass(const IcpArgs& a, IcpShared& sh, const float* tp, float4* cur, int S, const int* order,
+                                                  int* corr, float* cd, int* miss, unsigned long long& evaluated, bool pend) {
     const int lane = threadIdx.x & 31;
     const int ntask = (S + 31) / 32;
     const NnTableView& T = a.tab;
@@ -674,14 +683,19 @@ __device__ __forceinline__ void icp_nn_table_pass(const IcpArgs& a, IcpShared& s
         const int k = task * 32 + lane;
         const bool valid = k < S;
         const int i = order[valid ? k : S - 1];
-        const float4 p = __ldcg(cur + i);
+        float4 p = icp_ld<LOCAL>(cur + i);
+        if (pend && valid) {   // transformCloud(input_transformed, transformation_) of the previous iteration, folded into this read
+            p = xform(sh.Tm, p);
+            cur[i] = p;
+        }
         const float sx = p.x, sy = p.y, sz = p.z;
         const float fx = (sx - T.org[0]) * T.inv_h, fy = (sy - T.org[1]) * T.inv_h, fz = (sz - T.org[2]) * T.inv_h;
         const bool inside = valid && fx >= 0.f && fx < (float)T.nx && fy >= 0.f && fy < (float)T.ny && fz >= 0.f && fz < (float)T.nz;
         unsigned int R[8] = {0xffffu, 0u, 0u, 0u, 0u, 0u, 0u, 0u};
+        size_t cell = 0;
         if (inside) {
-            const size_t cell = ((size_t)(int)fz * T.ny + (size_t)(int)fy) * T.nx + (size_t)(int)fx;   // fx >= 0: truncation = floor
-            const uint4 r0 = __ldg(T.rec + 2 * cell), r1 = __ldg(T.rec + 2 * cell + 1);
+            cell = ((size_t)(int)fz * T.ny + (size_t)(int)fy) * T.nx + (size_t)(int)fx;   // fx >= 0: truncation = floor
+            const uint4 r0 = __ldg(T.rec + 4 * cell), r1 = __ldg(T.rec + 4 * cell + 1);
             R[0] = r0.x; R[1] = r0.y; R[2] = r0.z; R[3] = r0.w; R[4] = r1.x; R[5] = r1.y; R[6] = r1.z; R[7] = r1.w;
         }
         const unsigned int nrec = R[0] & 0xffffu;
@@ -690,7 +704,7 @@ __device__ __forceinline__ void icp_nn_table_pass(const IcpArgs& a, IcpShared& s
         float bd = __uint_as_float(0x7f800000u);
         int bpos = 0;
 #pragma unroll
-        for (int c = 0; c < NNT_K; ++c) {
+        for (int c = 0; c < 15; ++c) {
             if (c > 0 && (c & 3) == 0 && !__any_sync(FULL_MASK, c < n)) break;
             const unsigned int word = R[(c + 1) >> 1];
             const int pos = (int)(((c + 1) & 1) ? (word >> 16) : (word & 0xffffu));
@@ -698,6 +712,23 @@ __device__ __forceinline__ void icp_nn_table_pass(const IcpArgs& a, IcpShared& s
                 const float3 t = tmpl_point(tp, pos);
                 const float d = dist2(sx, sy, sz, t.x, t.y, t.z);
                 if (d < bd) { bd = d; bpos = pos; }
+            }
+        }
+        if (__any_sync(FULL_MASK, n > 15)) {   // cells further from the template: the second half of the record (candidates 15..30)
+            if (n > 15) {
+                const uint4 r2 = __ldg(T.rec + 4 * cell + 2), r3 = __ldg(T.rec + 4 * cell + 3);
+                R[0] = r2.x; R[1] = r2.y; R[2] = r2.z; R[3] = r2.w; R[4] = r3.x; R[5] = r3.y; R[6] = r3.z; R[7] = r3.w;
+            }
+#pragma unroll
+            for (int c = 15; c < NNT_K; ++c) {
+                if (c > 15 && ((c - 15) & 3) == 0 && !__any_sync(FULL_MASK, c < n)) break;
+                const unsigned int word = R[(c - 15) >> 1];
+                const int pos = (int)(((c - 15) & 1) ? (word >> 16) : (word & 0xffffu));
+                if (c < n) {
+                    const float3 t = tmpl_point(tp, pos);
+                    const float d = dist2(sx, sy, sz, t.x, t.y, t.z);
+                    if (d < bd) { bd = d; bpos = pos; }
+                }
             }
         }
         evaluated += (unsigned long long)n;
@@ -913,9 +944,9 @@ __global__ void __launch_bounds__(ICP_THREADS) k_icp_init(const IcpArgs a) {
 
 // One time slice of one problem: up to a.slice_iters iterations of the ICP loop, then either the closing fitness pass
 // (problem finished) or a state save (problem goes back on the queue).
-template <bool RESIDENT, bool QUEUED, bool TABLE, int SUB>
+template <bool RESIDENT, bool QUEUED, bool TABLE, bool LOCAL, int SUB>
 __device__ __forceinline__ bool icp_slice(const IcpArgs& a, IcpShared& sh, const float* s_tmpl, const uint4* s_nodes, const unsigned short* s_sib,
-                                          const unsigned short* s_orig, IcpWarpScr* wscr, int prob, int tid, int sub,
+                                          const unsigned short* s_orig, IcpWarpScr* wscr, unsigned char* s_local, int prob, int tid, int sub,
                                           unsigned long long* s_hh, unsigned long long* s_ev) {
     const int g = prob % a.n_guess, c = (prob / a.n_guess) % CUBOID_MAX_CLUSTERS, f = prob / (a.n_guess * CUBOID_MAX_CLUSTERS);
     const int* offsets = a.offsets + (size_t)f * (a.KC + 1);
@@ -923,12 +954,18 @@ __device__ __forceinline__ bool icp_slice(const IcpArgs& a, IcpShared& sh, const
     const int* idx = a.idx_sorted + (size_t)f * a.M + o0;
     const float4* src = a.remain + (size_t)f * a.P;
     const size_t pbase = ((size_t)f * a.n_guess + g) * a.M + o0;
-    float4* cur = a.cur + pbase;
-    int* corr = a.corr + pbase;
-    float* cd = a.cd + pbase;
+    float4* const g_cur = a.cur + pbase;
+    int* const g_corr = a.corr + pbase;
+    // LOCAL: the working cloud, its correspondences and distances live in shared memory for the whole slice
+    float4* cur = LOCAL ? reinterpret_cast<float4*>(s_local) : g_cur;
+    int* corr = LOCAL ? reinterpret_cast<int*>(s_local + (size_t)S * 16) : g_corr;
+    float* cd = LOCAL ? reinterpret_cast<float*>(s_local + (size_t)S * 20) : a.cd + pbase;
     const int* order = a.order + pbase;
     int* miss = TABLE ? a.miss + pbase : nullptr;
     IcpState& ps = a.pstate[prob];
+    if (LOCAL) {
+        for (int i = tid; i < S; i += SUB) { cur[i] = __ldcg(g_cur + i); corr[i] = __ldcg(g_corr + i); }
+    }
     const bool trace = a.corr_trace && f == 0 && c == 0 && g == 0;
     const float* tp = RESIDENT ? s_tmpl : a.tmpl;
     constexpr int LPT = SUB >= ICP_LANES ? 1 : ICP_LANES / SUB;   // canonical lanes per thread
@@ -949,26 +986,28 @@ __device__ __forceinline__ bool icp_slice(const IcpArgs& a, IcpShared& sh, const
         // First pass of a problem: every seed is template position 0, i.e. no bound at all, and the cloud is typically far from
         // the template, so each query would walk most of the tree. Search the first warp's worth of queries properly, then hand
         // the answer of one of them to everybody as the seed: any valid template position is a valid seed, results are unchanged.
-        icp_nn_pass<RESIDENT, QUEUED>(a, sh, s_tmpl, s_nodes, s_sib, s_orig, wscr, cur, 32, order, corr, cd, evaluated);
+        icp_nn_pass<RESIDENT, QUEUED, LOCAL>(a, sh, s_tmpl, s_nodes, s_sib, s_orig, wscr, cur, 32, order, corr, cd, evaluated);
         sub_sync<SUB>(sub);
         if (tid == 0) sh.task = 0;
-        const int seed = __ldcg(corr + order[0]);
+        const int seed = icp_ld<LOCAL>(corr + order[0]);
         sub_sync<SUB>(sub);
         for (int i = tid; i < S; i += SUB) corr[i] = seed;
         sub_sync<SUB>(sub);
     }
+    bool pend = false;   // TABLE: this iteration's transformation_ is applied by the next table pass (or below, when the slice ends)
     while (!sh.done && it < it_end) {
         // 1. correspondences: the candidate table answers the queries close to the template, the BVH search the rest
         if (TABLE) {
-            icp_nn_table_pass(a, sh, tp, cur, S, order, corr, cd, miss, evaluated);
+            icp_nn_table_pass<LOCAL>(a, sh, tp, cur, S, order, corr, cd, miss, evaluated, pend);
+            pend = false;
             sub_sync<SUB>(sub);
             const int nm = sh.nmiss;
             if (tid == 0) sh.task = 0;
             sub_sync<SUB>(sub);
             if (tid == 0) sh.nmiss = 0;
-            if (nm > 0) icp_nn_pass<RESIDENT, QUEUED>(a, sh, s_tmpl, s_nodes, s_sib, s_orig, wscr, cur, nm, miss, corr, cd, evaluated);
+            if (nm > 0) icp_nn_pass<RESIDENT, QUEUED, LOCAL>(a, sh, s_tmpl, s_nodes, s_sib, s_orig, wscr, cur, nm, miss, corr, cd, evaluated);
         } else {
-            icp_nn_pass<RESIDENT, QUEUED>(a, sh, s_tmpl, s_nodes, s_sib, s_orig, wscr, cur, S, order, corr, cd, evaluated);
+            icp_nn_pass<RESIDENT, QUEUED, LOCAL>(a, sh, s_tmpl, s_nodes, s_sib, s_orig, wscr, cur, S, order, corr, cd, evaluated);
         }
         ++passes;
         sub_sync<SUB>(sub);
@@ -978,12 +1017,12 @@ __device__ __forceinline__ bool icp_slice(const IcpArgs& a, IcpShared& sh, const
             float q6[6] = {0.f, 0.f, 0.f, 0.f, 0.f, 0.f};
             double qd[1] = {0.0};
             for (int i = canon ? tid + set * SUB : S; i < S; i += ICP_LANES) {
-                const float4 p = __ldcg(cur + i);
-                const int pos = __ldcg(corr + i);
+                const float4 p = icp_ld<LOCAL>(cur + i);
+                const int pos = icp_ld<LOCAL>(corr + i);
                 const float3 t = tmpl_point(tp, pos);
                 q6[0] = q6[0] + p.x; q6[1] = q6[1] + p.y; q6[2] = q6[2] + p.z;
                 q6[3] = q6[3] + t.x; q6[4] = q6[4] + t.y; q6[5] = q6[5] + t.z;
-                qd[0] = qd[0] + (double)__ldcg(cd + i);
+                qd[0] = qd[0] + (double)icp_ld<LOCAL>(cd + i);
                 if (a.hashes || trace) {             // parity taps: the correspondence hash and the per-iteration trace
                     const int j = a.tmpl_orig[pos];  // original template index
                     chash += splitmix64((((unsigned long long)it * (unsigned long long)S + (unsigned long long)i) << 32) | (unsigned int)j);
@@ -1006,8 +1045,8 @@ __device__ __forceinline__ bool icp_slice(const IcpArgs& a, IcpShared& sh, const
 #pragma unroll
             for (int k = 0; k < 9; ++k) q9[k] = 0.f;
             for (int i = canon ? tid + set * SUB : S; i < S; i += ICP_LANES) {
-                const float4 p = __ldcg(cur + i);
-                const float3 t = tmpl_point(tp, __ldcg(corr + i));
+                const float4 p = icp_ld<LOCAL>(cur + i);
+                const float3 t = tmpl_point(tp, icp_ld<LOCAL>(corr + i));
                 const float sd[3] = {p.x - sm[0], p.y - sm[1], p.z - sm[2]};
                 const float dd[3] = {t.x - dm[0], t.y - dm[1], t.z - dm[2]};
 #pragma unroll
@@ -1066,9 +1105,19 @@ __device__ __forceinline__ bool icp_slice(const IcpArgs& a, IcpShared& sh, const
             sh.done = done;
         }
         sub_sync<SUB>(sub);
-        // 5. transformCloud(input_transformed, input_transformed, transformation_): incremental, in place
-        for (int i = tid; i < S; i += SUB) cur[i] = xform(sh.Tm, __ldcg(cur + i));
+        // 5. transformCloud(input_transformed, input_transformed, transformation_): incremental, in place. With the candidate table
+        //    the next pass over the cloud is the table pass of the next iteration, which applies it as it reads (one pass and one
+        //    barrier less); when ICP has converged the cloud is rebuilt from the source with the final transformation anyway.
         ++it;
+        if (TABLE) {
+            pend = true;
+        } else {
+            for (int i = tid; i < S; i += SUB) cur[i] = xform(sh.Tm, icp_ld<LOCAL>(cur + i));
+            sub_sync<SUB>(sub);
+        }
+    }
+    if (TABLE && pend && !sh.done) {   // the slice ends between two iterations: the saved cloud must be the transformed one
+        for (int i = tid; i < S; i += SUB) cur[i] = xform(sh.Tm, icp_ld<LOCAL>(cur + i));
         sub_sync<SUB>(sub);
     }
     const bool finished = sh.done != 0;
@@ -1079,26 +1128,29 @@ __device__ __forceinline__ bool icp_slice(const IcpArgs& a, IcpShared& sh, const
         sub_sync<SUB>(sub);
         if (S > 0) {
             if (TABLE) {
-                icp_nn_table_pass(a, sh, tp, cur, S, order, corr, cd, miss, evaluated);
+                icp_nn_table_pass<LOCAL>(a, sh, tp, cur, S, order, corr, cd, miss, evaluated, false);
                 sub_sync<SUB>(sub);
                 const int nm = sh.nmiss;
                 if (tid == 0) sh.task = 0;
                 sub_sync<SUB>(sub);
                 if (tid == 0) sh.nmiss = 0;
-                if (nm > 0) icp_nn_pass<RESIDENT, QUEUED>(a, sh, s_tmpl, s_nodes, s_sib, s_orig, wscr, cur, nm, miss, corr, cd, evaluated);
+                if (nm > 0) icp_nn_pass<RESIDENT, QUEUED, LOCAL>(a, sh, s_tmpl, s_nodes, s_sib, s_orig, wscr, cur, nm, miss, corr, cd, evaluated);
             } else {
-                icp_nn_pass<RESIDENT, QUEUED>(a, sh, s_tmpl, s_nodes, s_sib, s_orig, wscr, cur, S, order, corr, cd, evaluated);
+                icp_nn_pass<RESIDENT, QUEUED, LOCAL>(a, sh, s_tmpl, s_nodes, s_sib, s_orig, wscr, cur, S, order, corr, cd, evaluated);
             }
             ++passes;
             sub_sync<SUB>(sub);
             for (int set = 0; set < LPT; ++set) {
                 double qd[1] = {0.0};
-                for (int i = canon ? tid + set * SUB : S; i < S; i += ICP_LANES) qd[0] = qd[0] + (double)__ldcg(cd + i);
+                for (int i = canon ? tid + set * SUB : S; i < S; i += ICP_LANES) qd[0] = qd[0] + (double)icp_ld<LOCAL>(cd + i);
                 canon_sub_partial<double, 1, SUB>(qd, sh.part_d, tid, set);
             }
             canon_sub_finish<double, 1, SUB>(sh.part_d, sh.red_d, tid, sub);
             fitness = sh.red_d[0] / (double)S;
         }
+    }
+    if (LOCAL) {   // hand the working cloud back: the next slice (or k_icp_aligned) reads it from global memory
+        for (int i = tid; i < S; i += SUB) { g_cur[i] = cur[i]; g_corr[i] = corr[i]; }
     }
     // reduce this slice's share of the correspondence hash and of the work counters
     chash = warp_sum_u64(chash);
@@ -1182,7 +1234,17 @@ __global__ void __launch_bounds__(ICP_NT, 1) k_icp(const IcpArgs a) {
         sub_sync<SUB>(sub);
         const int prob = s_prob[sub];
         if (prob < 0) break;
-        const bool finished = icp_slice<(MODE >= 1), (MODE >= 2), (MODE == 3), SUB>(a, sh, s_tmpl, s_nodes, s_sib, s_orig, wscr, prob, tid, sub, s_hh[sub], s_ev[sub]);
+        bool finished;
+        if (MODE == 3 && SUB == ICP_NT) {   // one sub-worker per CTA: room for the problem's working set next to the template
+            const int pc = (prob / a.n_guess) % CUBOID_MAX_CLUSTERS, pf = prob / (a.n_guess * CUBOID_MAX_CLUSTERS);
+            const int* po = a.offsets + (size_t)pf * (a.KC + 1);
+            const int pS = po[pc + 1] - po[pc];
+            unsigned char* s_local = reinterpret_cast<unsigned char*>(s_wscr + ICP_NT / 32);
+            if (pS <= a.local_cap) finished = icp_slice<true, true, true, true, SUB>(a, sh, s_tmpl, s_nodes, s_sib, s_orig, wscr, s_local, prob, tid, sub, s_hh[sub], s_ev[sub]);
+            else finished = icp_slice<true, true, true, false, SUB>(a, sh, s_tmpl, s_nodes, s_sib, s_orig, wscr, nullptr, prob, tid, sub, s_hh[sub], s_ev[sub]);
+        } else {
+            finished = icp_slice<(MODE >= 1), (MODE >= 2), (MODE == 3), false, SUB>(a, sh, s_tmpl, s_nodes, s_sib, s_orig, wscr, nullptr, prob, tid, sub, s_hh[sub], s_ev[sub]);
+        }
         if (tid == 0) {
             __threadfence();   // state / outputs before the hand-over
             if (finished) atomicAdd(&a.queue->n_done, 1);

@@ -3,11 +3,12 @@
 //
 // Once ICP has roughly aligned the clouds almost every query lies within a few millimetres of the template, where the set of
 // template points that can be ITS nearest neighbour is tiny: the points whose Voronoi cells reach the query's neighbourhood.
-// The table stores that set for every cell of a dense grid around the template (cell side h, default 1 mm): a 32-byte record
-// (one L2 sector) with up to 15 kd-ordered template positions, sorted by ORIGINAL template index. A query whose record is
+// The table stores that set for every cell of a dense grid around the template (cell side h, default 1 mm): a 64-byte record
+// (two L2 sectors; cells with at most 15 candidates are answered from the first) with up to 31 kd-ordered template positions,
+// sorted by ORIGINAL template index. A query whose record is
 // valid scans those few points with the un-fused float distance and strict '<' in that order — exactly what a brute-force scan
 // of the whole template in original order with strict '<' returns (the canonical tie rule). Queries outside the grid, or in
-// cells that would need more than 15 candidates (far from the template), are misses and go to the BVH search (icp.cuh).
+// cells that would need more than 31 candidates (far from the template), are misses and go to the BVH search (icp.cuh).
 //
 // Why the candidate set is complete (no float-minimiser can be missing). Let V be the cell, widened by delta on every side so
 // that it contains every query the run-time index computation can map to it (that computation's rounding error is below
@@ -24,13 +25,14 @@
 
 namespace cuboid {
 
-constexpr int NNT_K = 15;         // candidates per record
-constexpr int NNT_C1MAX = 96;     // first-level candidates per cell; more = the cell is too far from the template
+constexpr int NNT_K = 31;         // candidates per record (64 bytes: two L2 sectors; the second one is only read for cells with more than 15)
+constexpr int NNT_C1MAX = 160;    // first-level candidates per cell; more = the cell is too far from the template
 constexpr int NNT_SUB = 4;        // sub-boxes per axis of the second level
 constexpr int NNT_THREADS = 128;
+constexpr double NNT_BAND = 25.0;   // cells of margin around the template's bounding box = how far from the template a query can still be answered
 
 struct NnTableView {              // what k_icp needs at run time
-    const uint4* rec;             // [nz][ny][nx][2]: halfword 0 = n (0xffff: miss), halfwords 1..15 = kd-ordered positions
+    const uint4* rec;             // [nz][ny][nx][4]: halfword 0 = n (0xffff: miss), halfwords 1..31 = kd-ordered positions
     float org[3];
     float inv_h;
     int nx, ny, nz;
@@ -117,10 +119,10 @@ __global__ void __launch_bounds__(NNT_THREADS) k_nn_table_build(const float* __r
     }
     if (n1 > NNT_C1MAX) far_cell = true;
     if (!live) return;
-    uint4* out = rec + 2 * v;
+    uint4* out = rec + 4 * v;
     if (far_cell) {
         out[0] = make_uint4(0xffffu, 0u, 0u, 0u);
-        out[1] = make_uint4(0u, 0u, 0u, 0u);
+        out[1] = out[2] = out[3] = make_uint4(0u, 0u, 0u, 0u);
         return;
     }
     // ---- level 2: union over the sub-boxes of the points that can be a nearest neighbour inside the sub-box ----
@@ -166,12 +168,12 @@ __global__ void __launch_bounds__(NNT_THREADS) k_nn_table_build(const float* __r
     }
     if (over) {
         out[0] = make_uint4(0xffffu, 0u, 0u, 0u);
-        out[1] = make_uint4(0u, 0u, 0u, 0u);
+        out[1] = out[2] = out[3] = make_uint4(0u, 0u, 0u, 0u);
         return;
     }
-    unsigned int w[8];
+    unsigned int w[16];
 #pragma unroll
-    for (int q = 0; q < 8; ++q) w[q] = 0u;
+    for (int q = 0; q < 16; ++q) w[q] = 0u;
     w[0] = (unsigned int)k;
     for (int c = 0; c < k; ++c) {
         const int hw = c + 1;
@@ -179,6 +181,8 @@ __global__ void __launch_bounds__(NNT_THREADS) k_nn_table_build(const float* __r
     }
     out[0] = make_uint4(w[0], w[1], w[2], w[3]);
     out[1] = make_uint4(w[4], w[5], w[6], w[7]);
+    out[2] = make_uint4(w[8], w[9], w[10], w[11]);
+    out[3] = make_uint4(w[12], w[13], w[14], w[15]);
 }
 
 }  // namespace cuboid

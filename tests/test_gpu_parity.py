@@ -426,7 +426,7 @@ def test_full_size_batch_properties(cc, tmpl30, params):
     assert all(r.n_clusters == 1 and r.cluster[0].converged for r in res)
 
 
-@pytest.mark.parametrize("cluster,threads", [(1, 512), (2, 512), (4, 512), (1, 1024), (4, 1024), (8, 1024)])
+@pytest.mark.parametrize("cluster,threads", [(1, 512), (2, 512), (4, 512), (8, 512), (1, 1024), (4, 1024), (8, 1024)])
 def test_fused_frontend_equals_unfused_kernels(tmpl30, params, cluster, threads, monkeypatch):
     """Stages 1a+1b as one cluster-per-frame kernel (frontend.cuh) against the unfused kernels: every result byte and
     every fetched intermediate array equal, for each cluster size, on normal, empty and degenerate frames."""
@@ -542,7 +542,7 @@ def test_icp_on_the_reference_real_scan_returns_the_published_pose(golden, param
 
 
 @pytest.mark.parametrize("knob,values", [("CUBOID_ICP_NSUB", ("1", "2", "4")), ("CUBOID_ICP_SLICE", ("1", "8", "5000")),
-                                         ("CUBOID_ICP_OUTWARD", ("0", "1")), ("CUBOID_ICP_QUEUED", ("0", "1")), ("CUBOID_ICP_TABLE", ("0", "1")), ("CUBOID_FE_HASH", ("0", "1")), ("CUBOID_NNT_H_MM", ("0.7", "2.5")),
+                                         ("CUBOID_ICP_OUTWARD", ("0", "1")), ("CUBOID_ICP_QUEUED", ("0", "1")), ("CUBOID_ICP_TABLE", ("0", "1")), ("CUBOID_FE_HASH", ("0", "1")), ("CUBOID_ICP_LOCAL", ("0", "1")), ("CUBOID_FE_CLUSTER_SMALL", ("1", "8")), ("CUBOID_NNT_H_MM", ("0.7", "2.5")),
                                          ("CUBOID_PIPELINE", ("0", "1"))])
 def test_execution_knobs_do_not_change_results(tmpl30, params, knob, values, monkeypatch):
     """How the work is scheduled must never show in the results: sub-workers per CTA, iterations per time slice, outward search

@@ -9,8 +9,9 @@ p = default_params("cuboid")
 tm = pcd.template_points(0.2, 0.1, 0.03, 0.002)
 n = int(sys.argv[1]) if len(sys.argv) > 1 else 256
 depth = synth.depth_batch("bench", range(n))
+import time
 with api.CuboidCuda(p, max_points=640 * 480, max_batch=n) as cc:
-    cc.set_template(0, tm)
+    t0 = time.time(); cc.set_template(0, tm); print('set_template %.3f s' % (time.time() - t0))
     cc.set_option(api.OPT_TAPS, 0)
     cc.debug_counters()
     cc.process_batch(depth)

@@ -682,7 +682,10 @@ __device__ __forceinline__ void icp_nn_table_pass(const IcpArgs& a, IcpShared& s
         if (task >= ntask) break;
         const int k = task * 32 + lane;
         const bool valid = k < S;
-        const int i = order[valid ? k : S - 1];
+        // points in their own order (no visiting-order indirection: coalesced reads; a table lookup gains nothing from spatially
+        // coherent lanes). The BVH pass over the misses keeps the Morton order when everything missed (early iterations).
+        // (Requesting the next task's points before this task's record arrives was measured: no gain, 5.78 vs 5.76 ms.)
+        const int i = valid ? k : S - 1;
         float4 p = icp_ld<LOCAL>(cur + i);
         if (pend && valid) {   // transformCloud(input_transformed, transformation_) of the previous iteration, folded into this read
             p = xform(sh.Tm, p);
@@ -1005,7 +1008,7 @@ __device__ __forceinline__ bool icp_slice(const IcpArgs& a, IcpShared& sh, const
             if (tid == 0) sh.task = 0;
             sub_sync<SUB>(sub);
             if (tid == 0) sh.nmiss = 0;
-            if (nm > 0) icp_nn_pass<RESIDENT, QUEUED, LOCAL>(a, sh, s_tmpl, s_nodes, s_sib, s_orig, wscr, cur, nm, miss, corr, cd, evaluated);
+            if (nm > 0) icp_nn_pass<RESIDENT, QUEUED, LOCAL>(a, sh, s_tmpl, s_nodes, s_sib, s_orig, wscr, cur, nm, nm == S ? order : miss, corr, cd, evaluated);
         } else {
             icp_nn_pass<RESIDENT, QUEUED, LOCAL>(a, sh, s_tmpl, s_nodes, s_sib, s_orig, wscr, cur, S, order, corr, cd, evaluated);
         }
@@ -1134,7 +1137,7 @@ __device__ __forceinline__ bool icp_slice(const IcpArgs& a, IcpShared& sh, const
                 if (tid == 0) sh.task = 0;
                 sub_sync<SUB>(sub);
                 if (tid == 0) sh.nmiss = 0;
-                if (nm > 0) icp_nn_pass<RESIDENT, QUEUED, LOCAL>(a, sh, s_tmpl, s_nodes, s_sib, s_orig, wscr, cur, nm, miss, corr, cd, evaluated);
+                if (nm > 0) icp_nn_pass<RESIDENT, QUEUED, LOCAL>(a, sh, s_tmpl, s_nodes, s_sib, s_orig, wscr, cur, nm, nm == S ? order : miss, corr, cd, evaluated);
             } else {
                 icp_nn_pass<RESIDENT, QUEUED, LOCAL>(a, sh, s_tmpl, s_nodes, s_sib, s_orig, wscr, cur, S, order, corr, cd, evaluated);
             }

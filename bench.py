@@ -609,8 +609,10 @@ def _profile_json(name):
         return None
 
 
-# frames per step / steps of the secondary BASELINE configs inside the default run (the headline config runs at --frames / --steps)
-CONFIG_RUNS = {"seg": (1024, 5), "guess64": (64, 3), "multi8": (256, 3), "hd720": (64, 3)}
+# frames per step / steps of the secondary BASELINE configs inside the default run (the headline config runs at --frames / --steps).
+# The per-frame kernels (one CTA per frame in the front end, plane and cluster stages) are latency bound per frame, so throughput
+# needs enough frames in flight to fill 148 SMs with several CTAs each: 256 frames of 720p, 1024 of VGA.
+CONFIG_RUNS = {"seg": (1024, 5), "guess64": (256, 3), "multi8": (1024, 3), "hd720": (256, 3)}
 CONFIG_CPU = {"full": (3, 10), "seg": (3, 10), "guess64": (1, 3), "multi8": (3, 10), "hd720": (1, 3)}   # (warm-ups, timed frames)
 
 

@@ -304,11 +304,13 @@ int run_chunk(cuboid_handle* h, const ChunkIn& in, int nf, cuboid_frame_result* 
         cfg.stream = st;
         cfg.attrs = at; cfg.numAttrs = 1;
         if (h->fe_threads == 512) {
-            if (in.blob) CK(h, cudaLaunchKernelEx(&cfg, k_frontend<1, 512>, fa));
-            else CK(h, cudaLaunchKernelEx(&cfg, k_frontend<0, 512>, fa));
+            if (in.blob && fa.rgb) CK(h, cudaLaunchKernelEx(&cfg, k_frontend<1, 512, true>, fa));
+            else if (in.blob) CK(h, cudaLaunchKernelEx(&cfg, k_frontend<1, 512, false>, fa));
+            else CK(h, cudaLaunchKernelEx(&cfg, k_frontend<0, 512, false>, fa));
         } else {
-            if (in.blob) CK(h, cudaLaunchKernelEx(&cfg, k_frontend<1, 1024>, fa));
-            else CK(h, cudaLaunchKernelEx(&cfg, k_frontend<0, 1024>, fa));
+            if (in.blob && fa.rgb) CK(h, cudaLaunchKernelEx(&cfg, k_frontend<1, 1024, true>, fa));
+            else if (in.blob) CK(h, cudaLaunchKernelEx(&cfg, k_frontend<1, 1024, false>, fa));
+            else CK(h, cudaLaunchKernelEx(&cfg, k_frontend<0, 1024, false>, fa));
         }
         ++h->launches;
         CK(h, cudaGetLastError());
@@ -640,9 +642,10 @@ static int create_impl(cuboid_handle** out, const cuboid_params* p, int device, 
         // path inside the same kernel. Bigger clouds (720p: ~600k voxels) always keep two 512-thread CTAs per SM.
         if (h->fe_hash && h->P <= 400000 && h->fe_cluster == 1) h->fe_threads = 1024; else h->fe_hash = 0;
         const char* et = std::getenv("CUBOID_FE_THREADS"); if (et) { h->fe_threads = atoi(et) == 1024 ? 1024 : 512; if (h->fe_threads != 1024) h->fe_hash = 0; }
-        const void* fns[4] = {(const void*)k_frontend<0, 512>, (const void*)k_frontend<1, 512>, (const void*)k_frontend<0, 1024>, (const void*)k_frontend<1, 1024>};
-        for (int k = 0; k < 4; ++k) {
-            if (cudaFuncSetAttribute(fns[k], cudaFuncAttributeMaxDynamicSharedMemorySize, fe_smem(k < 2 ? 512 : 1024)) != cudaSuccess) return fail(CUBOID_E_CUDA);
+        const void* fns[6] = {(const void*)k_frontend<0, 512, false>, (const void*)k_frontend<1, 512, false>, (const void*)k_frontend<0, 1024, false>,
+                              (const void*)k_frontend<1, 1024, false>, (const void*)k_frontend<1, 512, true>, (const void*)k_frontend<1, 1024, true>};
+        for (int k = 0; k < 6; ++k) {
+            if (cudaFuncSetAttribute(fns[k], cudaFuncAttributeMaxDynamicSharedMemorySize, fe_smem((k < 2 || k == 4) ? 512 : 1024)) != cudaSuccess) return fail(CUBOID_E_CUDA);
             if (h->fe_cluster > 8) cudaFuncSetAttribute(fns[k], cudaFuncAttributeNonPortableClusterSizeAllowed, 1);
         }
         int sms = 0;

@@ -182,6 +182,7 @@ __device__ __forceinline__ float fe_rgb_avg(unsigned int sr, unsigned int sg, un
     const int r = (int)((float)sr / c), g = (int)((float)sg / c), b = (int)((float)sb / c);
     return __int_as_float((r << 16) | (g << 8) | b);
 }
+template <bool RGB>
 __device__ __forceinline__ int fe_run_step(FeRun& r, bool match, float ax, float ay, float az, unsigned int aw = 0u) {
     const unsigned int miss = __ballot_sync(FULL_MASK, !match);
     const int nmatch = miss ? (__ffs(miss) - 1) : 32;
@@ -193,7 +194,7 @@ __device__ __forceinline__ int fe_run_step(FeRun& r, bool match, float ax, float
     if (nzx) { for (int j = 0; j < nmatch; ++j) r.sx += __shfl_sync(FULL_MASK, ax, j); } else r.sx = fe_add_zeros(r.sx, pzx != 0u);
     if (nzy) { for (int j = 0; j < nmatch; ++j) r.sy += __shfl_sync(FULL_MASK, ay, j); } else r.sy = fe_add_zeros(r.sy, pzy != 0u);
     if (nzz) { for (int j = 0; j < nmatch; ++j) r.sz += __shfl_sync(FULL_MASK, az, j); } else r.sz = fe_add_zeros(r.sz, pzz != 0u);
-    {
+    if (RGB) {
         const bool mine = (int)(threadIdx.x & 31) < nmatch;
         r.sr += __reduce_add_sync(FULL_MASK, mine ? ((aw >> 16) & 255u) : 0u);
         r.sg += __reduce_add_sync(FULL_MASK, mine ? ((aw >> 8) & 255u) : 0u);
@@ -226,7 +227,7 @@ __device__ __forceinline__ int fe_bitlen(int v) { return v <= 0 ? 0 : 32 - __clz
 //   Dh   every point index to cursor[slot]++: the points of a voxel become one contiguous run (in no particular order)
 //   Eh   chunks of whole runs staged in shared memory: each run is sorted ascending (= the stable order of the radix path), the
 //        points are gathered, ONE THREAD PER VOXEL sums its run sequentially (long runs: a whole warp), centroids out
-template <int SRC, int NT>
+template <int SRC, int NT, bool RGB>
 __device__ __forceinline__ bool fe_hash_frame(const FrontArgs& a, int f, int n_in, int N, const VoxelGeom& g, unsigned long long* slot_scratch,
                                               unsigned char* fe_dyn, const FehStatic& st) {
     static_assert(NT == 1024, "the hash path is laid out for one 1024-thread CTA per SM");
@@ -533,7 +534,7 @@ __device__ __forceinline__ bool fe_hash_frame(const FrontArgs& a, int f, int n_i
             for (int l = tid; l < npts; l += NT) {
                 const float4 pt = __ldcg(pts + s_idx[l]);
                 s_px[l] = pt.x; s_py[l] = pt.y; s_pz[l] = pt.z;
-                if (a.rgb) s_pw[l] = __float_as_uint(pt.w);
+                if (RGB) s_pw[l] = __float_as_uint(pt.w);
             }
             __syncthreads();
             if (tid < nv && !deferred) {
@@ -542,7 +543,7 @@ __device__ __forceinline__ bool fe_hash_frame(const FrontArgs& a, int f, int n_i
                 const float cnt = (float)c;
                 const float cx = sx / cnt, cy = sy / cnt, cz = sz / cnt;
                 float cw = 1.0f;
-                if (a.rgb) {
+                if (RGB) {
                     unsigned int sr = 0, sg = 0, sb = 0;
                     for (int q = lp; q < lp + c; ++q) { const unsigned int w = s_pw[q]; sr += (w >> 16) & 255u; sg += (w >> 8) & 255u; sb += w & 255u; }
                     cw = fe_rgb_avg(sr, sg, sb, c);
@@ -558,19 +559,19 @@ __device__ __forceinline__ bool fe_hash_frame(const FrontArgs& a, int f, int n_i
                 FeRun acc;
                 acc.sx = s_px[dl]; acc.sy = s_py[dl]; acc.sz = s_pz[dl]; acc.cnt = 1;
                 {
-                    const unsigned int w0 = a.rgb ? s_pw[dl] : 0u;
+                    const unsigned int w0 = RGB ? s_pw[dl] : 0u;
                     acc.sr = (w0 >> 16) & 255u; acc.sg = (w0 >> 8) & 255u; acc.sb = w0 & 255u;
                 }
                 for (int l = dl + 1; l < dl + dc; l += 32) {
                     const int i = l + lane;
                     const bool m = i < dl + dc;
-                    fe_run_step(acc, m, m ? s_px[i] : 0.f, m ? s_py[i] : 0.f, m ? s_pz[i] : 0.f, (m && a.rgb) ? s_pw[i] : 0u);
+                    fe_run_step<RGB>(acc, m, m ? s_px[i] : 0.f, m ? s_py[i] : 0.f, m ? s_pz[i] : 0.f, (m && RGB) ? s_pw[i] : 0u);
                 }
                 if (lane == 0) {
                     const float cf = (float)acc.cnt;
                     const float cx = acc.sx / cf, cy = acc.sy / cf, cz = acc.sz / cf;
                     const int vp = r0 + vt;
-                    vox[vp] = make_float4(cx, cy, cz, a.rgb ? fe_rgb_avg(acc.sr, acc.sg, acc.sb, acc.cnt) : 1.0f);
+                    vox[vp] = make_float4(cx, cy, cz, RGB ? fe_rgb_avg(acc.sr, acc.sg, acc.sb, acc.cnt) : 1.0f);
                     if (vcount) vcount[vp] = acc.cnt;
                     if (a.hashes) hv[0] += hash_point((unsigned int)vp, cx, cy, cz);
                 }
@@ -593,7 +594,9 @@ __device__ __forceinline__ bool fe_hash_frame(const FrontArgs& a, int f, int n_i
     return true;
 }
 
-template <int SRC, int NT>
+// RGB (PointCloud2 inputs with a packed rgb field, FrontArgs::rgb) is a compile-time variant: the colour bookkeeping costs the
+// depth-frame path 4 % when it is a run-time test.
+template <int SRC, int NT, bool RGB>
 __global__ void __launch_bounds__(NT, 2048 / NT >= 2 ? (NT <= 512 ? 2 : 1) : 1) k_frontend(const FrontArgs a) {
     constexpr int NW = NT / 32;
     constexpr int TILE = NT * FE_ITEMS;
@@ -726,7 +729,7 @@ __global__ void __launch_bounds__(NT, 2048 / NT >= 2 ? (NT <= 512 ? 2 : 1) : 1) 
                 FehStatic st;
                 st.s_w = s_w; st.s_histA = s_histA; st.s_base = s_base; st.s_h64 = s_h64; st.s_ndef = &s_ndef; st.s_def_lp = s_def_lp;
                 st.s_def_pos = s_def_pos; st.s_misc = s_misc;
-                const bool done = fe_hash_frame<SRC, NT>(a, f, n_in, N, g, bufA, fe_dyn, st);
+                const bool done = fe_hash_frame<SRC, NT, RGB>(a, f, n_in, N, g, bufA, fe_dyn, st);
                 __syncthreads();
                 if (done) { cluster.sync(); continue; }
             }
@@ -946,7 +949,7 @@ __global__ void __launch_bounds__(NT, 2048 / NT >= 2 ? (NT <= 512 ? 2 : 1) : 1) 
             float* s_py = s_px + RSTAGE;
             float* s_pz = s_py + RSTAGE;
             unsigned short* s_head = reinterpret_cast<unsigned short*>(s_pz + RSTAGE);
-            unsigned int* s_pw = reinterpret_cast<unsigned int*>(s_head + RTILE);   // packed rgb(a) of the staged points (a.rgb only)
+            unsigned int* s_pw = reinterpret_cast<unsigned int*>(s_head + RTILE);   // packed rgb(a) of the staged points (RGB only)
             const float4* pts = p.pts + (size_t)f * p.Pout;
             float4* vox = a.vox + (size_t)f * a.P;
             int* vcount = a.vcount ? a.vcount + (size_t)f * a.P : nullptr;
@@ -969,7 +972,7 @@ __global__ void __launch_bounds__(NT, 2048 / NT >= 2 ? (NT <= 512 ? 2 : 1) : 1) 
                             const float4 pt = __ldcg(pts + (unsigned int)rec[k]);
                             s_key[l] = (unsigned int)(rec[k] >> 32);
                             s_px[l] = pt.x; s_py[l] = pt.y; s_pz[l] = pt.z;
-                            if (a.rgb) s_pw[l] = __float_as_uint(pt.w);
+                            if (RGB) s_pw[l] = __float_as_uint(pt.w);
                         }
                     }
                 }
@@ -1006,7 +1009,7 @@ __global__ void __launch_bounds__(NT, 2048 / NT >= 2 ? (NT <= 512 ? 2 : 1) : 1) 
                     const float cnt = (float)(end - lp);
                     const float cx = sx / cnt, cy = sy / cnt, cz = sz / cnt;
                     float cw = 1.0f;
-                    if (a.rgb) {
+                    if (RGB) {
                         unsigned int sr = 0, sg = 0, sb = 0;
                         for (int q = lp; q < end; ++q) { const unsigned int w = s_pw[q]; sr += (w >> 16) & 255u; sg += (w >> 8) & 255u; sb += w & 255u; }
                         cw = fe_rgb_avg(sr, sg, sb, end - lp);
@@ -1023,14 +1026,14 @@ __global__ void __launch_bounds__(NT, 2048 / NT >= 2 ? (NT <= 512 ? 2 : 1) : 1) 
                     FeRun acc;
                     acc.sx = s_px[lp]; acc.sy = s_py[lp]; acc.sz = s_pz[lp]; acc.cnt = 1;
                     {
-                        const unsigned int w0 = a.rgb ? s_pw[lp] : 0u;
+                        const unsigned int w0 = RGB ? s_pw[lp] : 0u;
                         acc.sr = (w0 >> 16) & 255u; acc.sg = (w0 >> 8) & 255u; acc.sb = w0 & 255u;
                     }
                     bool open = true;
                     for (int l = lp + 1; open && l < n_stage; l += 32) {   // the part of the run that is staged in shared memory
                         const int i = l + lane;
                         const bool m = i < n_stage && s_key[i] == mykey;
-                        open = fe_run_step(acc, m, m ? s_px[i] : 0.f, m ? s_py[i] : 0.f, m ? s_pz[i] : 0.f, (m && a.rgb) ? s_pw[i] : 0u) == min(32, n_stage - l);
+                        open = fe_run_step<RGB>(acc, m, m ? s_px[i] : 0.f, m ? s_py[i] : 0.f, m ? s_pz[i] : 0.f, (m && RGB) ? s_pw[i] : 0u) == min(32, n_stage - l);
                     }
                     for (int q = t0 + n_stage; open && q < N; q += 128) {    // the rest from the sorted records, 128 per round trip
                         unsigned long long rec[4];
@@ -1046,13 +1049,13 @@ __global__ void __launch_bounds__(NT, 2048 / NT >= 2 ? (NT <= 512 ? 2 : 1) : 1) 
                         for (int j = 0; j < 4; ++j) pt[j] = m[j] ? __ldcg(pts + (unsigned int)rec[j]) : make_float4(0.f, 0.f, 0.f, 0.f);
 #pragma unroll
                         for (int j = 0; j < 4; ++j)
-                            if (open) open = fe_run_step(acc, m[j], pt[j].x, pt[j].y, pt[j].z, a.rgb ? __float_as_uint(pt[j].w) : 0u) == 32;
+                            if (open) open = fe_run_step<RGB>(acc, m[j], pt[j].x, pt[j].y, pt[j].z, RGB ? __float_as_uint(pt[j].w) : 0u) == 32;
                     }
                     if (lane == 0) {
                         const float c = (float)acc.cnt;
                         const float cx = acc.sx / c, cy = acc.sy / c, cz = acc.sz / c;
                         const int vp = s_def_pos[d];
-                        vox[vp] = make_float4(cx, cy, cz, a.rgb ? fe_rgb_avg(acc.sr, acc.sg, acc.sb, acc.cnt) : 1.0f);
+                        vox[vp] = make_float4(cx, cy, cz, RGB ? fe_rgb_avg(acc.sr, acc.sg, acc.sb, acc.cnt) : 1.0f);
                         if (vcount) vcount[vp] = acc.cnt;
                         if (a.hashes) hv[0] += hash_point((unsigned int)vp, cx, cy, cz);
                     }

@@ -373,6 +373,22 @@ def test_multi_object_frame_and_second_template(tmpl100):
     _same_frame(res[0], ref)
 
 
+def test_multi8_bench_config_four_frames_full_iterations(tmpl30):
+    """BASELINE configs[3] as bench.py runs it (8 cuboids per frame, the 200x100x30 template, default iteration budget):
+    four frames, every cluster's ICP trajectory against the oracle."""
+    from concurrent.futures import ThreadPoolExecutor
+    p = default_params("multi8")
+    depth = synth.depth_batch("multi8", [1, 2, 3, 4])
+    with api.CuboidCuda(p, max_points=640 * 480, max_batch=4) as h:
+        h.set_template(0, tmpl30)
+        res = h.process_batch(depth)
+    with ThreadPoolExecutor(4) as ex:
+        refs = list(ex.map(lambda i: O.process_frame(p, depth[i], tmpl30), range(4)))
+    for i in range(4):
+        assert refs[i].n_clusters == 8
+        _same_frame(res[i], refs[i])
+
+
 def test_object_detection_variant_small_leaf(tmpl30):
     """object_detection.launch: leaf 0.001 (inv_leaf = 999.99994f), threshold 0.01, extra PassThrough z [0, 0.75]."""
     p = default_params("object")
@@ -395,6 +411,20 @@ def test_hd720_small_leaf_stress_frame(tmpl30):
     ref = O.process_frame(p, depth[0], tmpl30)
     assert ref.n_points > 800000 and ref.n_voxels > 500000
     _same_frame(res[0], ref)
+
+
+def test_hd720_bench_config_four_frames_full_iterations(tmpl30):
+    """BASELINE configs[4] as bench.py runs it: four 1280x720 frames, 2 mm leaf, default (5000) ICP iteration budget."""
+    from concurrent.futures import ThreadPoolExecutor
+    p = default_params("hd720")
+    depth = synth.depth_batch("hd720", [1, 2, 3, 4])
+    with api.CuboidCuda(p, max_points=1280 * 720, max_batch=4) as h:
+        h.set_template(0, tmpl30)
+        res = h.process_batch(depth)
+    with ThreadPoolExecutor(4) as ex:
+        refs = list(ex.map(lambda i: O.process_frame(p, depth[i], tmpl30), range(4)))
+    for i in range(4):
+        _same_frame(res[i], refs[i])
 
 
 def test_stage_mask_segmentation_only(cc, params, tmpl30):

@@ -62,10 +62,13 @@ __device__ __forceinline__ void uf_unite(int* parent, int a, int b) {
 }
 
 // MODE 0: n <= CLU_SMEM_ALL: union-find forest, bucket table and bucketed points all in shared memory
-// MODE 1: n <= CLU_SMEM_UF : forest in shared memory, grid in global memory
+// MODE 1: n <= CLU_SMEM_UF : forest in shared memory, grid in global memory (k_cluster, two CTAs per SM);
+//         n <= CLU_SMEM_UF_BIG: the same in k_cluster_big (one CTA per SM, 128 KB forest), launched next to k_cluster: every CTA
+//         of either kernel looks at its frame's n_remain and leaves at once when the frame belongs to the other kernel
 // MODE 2: everything in global memory
 constexpr int CLU_SMEM_ALL = 2048;
 constexpr int CLU_SMEM_UF = 12288;
+constexpr int CLU_SMEM_UF_BIG = 32768;
 // static shared memory of k_cluster, declared once in the kernel (not per MODE instantiation)
 struct CluShared {
     int s_w[CLU_THREADS / 32 + 1];
@@ -334,8 +337,17 @@ __global__ void __launch_bounds__(CLU_THREADS) k_cluster(const CluArgs a) {
     const int n = a.res[blockIdx.x].n_remain;
     if (n <= CLU_SMEM_ALL) cluster_body<0>(a, cs);
     else if (n <= CLU_SMEM_UF) cluster_body<1>(a, cs);
+    else if (n <= CLU_SMEM_UF_BIG && a.use_cluster) return;   // k_cluster_big's frame
     else cluster_body<2>(a, cs);
 }
+// frames with CLU_SMEM_UF < n_remain <= CLU_SMEM_UF_BIG (multi-object scenes): the union-find forest still fits shared memory when a
+// CTA has an SM to itself
+__global__ void __launch_bounds__(CLU_THREADS, 1) k_cluster_big(const CluArgs a) {
+    __shared__ CluShared cs;
+    const int n = a.res[blockIdx.x].n_remain;
+    if (n > CLU_SMEM_UF && n <= CLU_SMEM_UF_BIG && a.use_cluster) cluster_body<1>(a, cs);
+}
+constexpr size_t CLU_DYN_SMEM_BIG = (size_t)CLU_SMEM_UF_BIG * 4;
 constexpr size_t CLU_DYN_SMEM = (size_t)CLU_SMEM_ALL * 4 + (size_t)CLU_SMEM_ALL * 16 + (size_t)(CLU_SMEM_ALL + 4) * 4;   // 49 168 B >= 12288*4
 
 }  // namespace cuboid

@@ -398,6 +398,10 @@ int run_chunk(cuboid_handle* h, const ChunkIn& in, int nf, cuboid_frame_result* 
         c.use_cluster = force_cluster ? 1 : p.use_cluster;
         k_cluster<<<nf, CLU_THREADS, CLU_DYN_SMEM, st>>>(c);
         ++h->launches;
+        if (c.use_cluster && h->M > CLU_SMEM_UF) {   // frames with a large remainder (multi-object scenes): forest in 128 KB of shared memory
+            k_cluster_big<<<nf, CLU_THREADS, CLU_DYN_SMEM_BIG, st>>>(c);
+            ++h->launches;
+        }
         CK(h, cudaGetLastError());
     }
     CK(h, cudaEventRecord(evs[4], st));
@@ -701,6 +705,7 @@ static int create_impl(cuboid_handle** out, const cuboid_params* p, int device, 
     { const char* ec = std::getenv("CUBOID_ICP_CULL"); if (ec) h->icp_cull = atoi(ec) ? 1 : 0; }
     if (cudaFuncSetAttribute(k_sac_plane, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)sizeof(SacShared)) != cudaSuccess) return fail(CUBOID_E_CUDA);
     if (cudaFuncSetAttribute(k_cluster, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)CLU_DYN_SMEM) != cudaSuccess) return fail(CUBOID_E_CUDA);
+    if (cudaFuncSetAttribute(k_cluster_big, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)CLU_DYN_SMEM_BIG) != cudaSuccess) return fail(CUBOID_E_CUDA);
 #undef CA
     *out = h;
     return CUBOID_OK;

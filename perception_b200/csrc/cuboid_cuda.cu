@@ -69,8 +69,8 @@ struct cuboid_handle {
     int* d_triplets = nullptr; int triplets_cap = 0;
     float* d_tmpl[CUBOID_MAX_TEMPLATES] = {}; int* d_tmpl_orig[CUBOID_MAX_TEMPLATES] = {}; int tmpl_n[CUBOID_MAX_TEMPLATES] = {}; int tmpl_pad[CUBOID_MAX_TEMPLATES] = {};
     unsigned short* d_sib[CUBOID_MAX_TEMPLATES] = {}; int sib_max[CUBOID_MAX_TEMPLATES] = {}; int sib_bytes[CUBOID_MAX_TEMPLATES] = {};   // sibling chains (icp.cuh)
-    uint4* d_nnt[CUBOID_MAX_TEMPLATES] = {}; NnTableView nnt[CUBOID_MAX_TEMPLATES] = {};   // nearest-neighbour candidate tables (nn_table.cuh)
-    int icp_table = 1; double nnt_h = 0.001;
+    uint4* d_nnt[CUBOID_MAX_TEMPLATES] = {}; unsigned short* d_nnseed[CUBOID_MAX_TEMPLATES] = {}; NnTableView nnt[CUBOID_MAX_TEMPLATES] = {};   // nearest-neighbour candidate tables (nn_table.cuh)
+    int icp_table = 1; double nnt_h = 0.001; int icp_seed_grid = 1; double nns_mult = 8.0;
     unsigned short* d_orig16[CUBOID_MAX_TEMPLATES] = {};   // original index of every kd-ordered position as u16 (queued search), NULL when the template has more than 65536 points
     uint4* d_boxes[CUBOID_MAX_TEMPLATES] = {}; int tmpl_nleaf[CUBOID_MAX_TEMPLATES] = {}; int tmpl_nnodes[CUBOID_MAX_TEMPLATES] = {};
     unsigned long long* d_work = nullptr; unsigned long long work_total[2] = {0, 0};
@@ -633,6 +633,8 @@ static int create_impl(cuboid_handle** out, const cuboid_params* p, int device, 
         const char* en = std::getenv("CUBOID_ICP_NSUB"); if (en) h->icp_nsub_force = (atoi(en) == 1 || atoi(en) == 2 || atoi(en) == 4) ? atoi(en) : 0;
         const char* eq = std::getenv("CUBOID_ICP_QUEUED"); if (eq) h->icp_queued = atoi(eq) ? 1 : 0;
         const char* el = std::getenv("CUBOID_ICP_LOCAL"); if (el) h->icp_local = atoi(el) ? 1 : 0;
+        const char* esg = std::getenv("CUBOID_ICP_SEEDGRID"); if (esg) h->icp_seed_grid = atoi(esg) ? 1 : 0;
+        const char* esm = std::getenv("CUBOID_NNS_MULT"); if (esm && atof(esm) >= 1.0) h->nns_mult = atof(esm);
         const char* etb = std::getenv("CUBOID_ICP_TABLE"); if (etb) h->icp_table = atoi(etb) ? 1 : 0;
         const char* eh = std::getenv("CUBOID_NNT_H_MM"); if (eh && atof(eh) > 0.0) h->nnt_h = atof(eh) * 1e-3;
         cudaDeviceGetAttribute(&h->smem_sm, cudaDevAttrMaxSharedMemoryPerMultiprocessor, device);
@@ -725,6 +727,7 @@ int cuboid_destroy(cuboid_handle* h) {
     for (auto& t : h->d_sib) if (t) cudaFree(t);
     for (auto& t : h->d_orig16) if (t) cudaFree(t);
     for (auto& t : h->d_nnt) if (t) cudaFree(t);
+    for (auto& t : h->d_nnseed) if (t) cudaFree(t);
     for (auto& t : h->d_tmpl_orig) if (t) cudaFree(t);
     for (auto& e : h->ev) if (e) cudaEventDestroy(e);
     for (auto& e : h->ev_pool) if (e) cudaEventDestroy(e);
@@ -879,6 +882,7 @@ static int set_template_impl(cuboid_handle* h, int slot, const float* xyz, int s
     h->tmpl_n[slot] = n; h->tmpl_pad[slot] = pad; h->tmpl_nleaf[slot] = nleaf; h->tmpl_nnodes[slot] = (int)nodes.size();
     // nearest-neighbour candidate table (nn_table.cuh): a dense grid of cells of side hcell around the template, NNT_BAND cells of margin
     if (h->d_nnt[slot]) { cudaFree(h->d_nnt[slot]); h->d_nnt[slot] = nullptr; }
+    if (h->d_nnseed[slot]) { cudaFree(h->d_nnseed[slot]); h->d_nnseed[slot] = nullptr; }
     h->nnt[slot] = NnTableView{};
     if (h->icp_table && h->d_orig16[slot]) {
         double mn[3] = {1e300, 1e300, 1e300}, mx[3] = {-1e300, -1e300, -1e300}, maxabs = 0.0;
@@ -911,6 +915,23 @@ static int set_template_impl(cuboid_handle* h, int slot, const float* xyz, int s
                 h->d_tmpl[slot], h->d_tmpl_orig[slot], n, g, h->d_nnt[slot]);
             ++h->launches;
             CK(h, cudaGetLastError());
+            if (h->icp_seed_grid) {   // seed grid: cells nns_mult x the table's, 200 table cells (20 cm at the default) around the bounding box
+                const double hs = h->nns_mult * hcell, ms = 200.0 * hcell;   // margin: 20 cm at the default cell size
+                long long sd[3];
+                for (int d = 0; d < 3; ++d) sd[d] = (long long)std::ceil((mx[d] - mn[d] + 2.0 * ms) / hs) + 1;
+                const long long nc = sd[0] * sd[1] * sd[2];
+                if (nc > 0 && nc <= 4000000LL) {
+                    CKS(h, dalloc(h, &h->d_nnseed[slot], (size_t)nc));
+                    for (int d = 0; d < 3; ++d) view.sorg[d] = (float)(mn[d] - ms);
+                    view.sinv_h = (float)(1.0 / hs);
+                    view.snx = (int)sd[0]; view.sny = (int)sd[1]; view.snz = (int)sd[2];
+                    k_nn_seed_build<ICP_LEAF><<<(unsigned int)((nc + NNT_THREADS - 1) / NNT_THREADS), NNT_THREADS, 0, h->stream>>>(
+                        h->d_tmpl[slot], n, view.sorg[0], view.sorg[1], view.sorg[2], 1.0f / view.sinv_h, view.snx, view.sny, view.snz, h->d_nnseed[slot]);
+                    ++h->launches;
+                    CK(h, cudaGetLastError());
+                    view.seed = h->d_nnseed[slot];
+                }
+            }
             CK(h, cudaStreamSynchronize(h->stream));
             view.rec = h->d_nnt[slot];
             h->nnt[slot] = view;

@@ -519,10 +519,22 @@ __device__ __forceinline__ void icp_nn_pass(const IcpArgs& a, IcpShared& sh, con
         const int i = order[valid ? k : S - 1];   // 32 lanes = 32 spatial neighbours: coherent tree walks, broadcast loads
         const float4 p = icp_ld<LOCAL>(cur + i);
         const float sx = p.x, sy = p.y, sz = p.z;
-        const int pos0 = icp_ld<LOCAL>(corr + i);
+        int pos0 = icp_ld<LOCAL>(corr + i);
         unsigned int nleaf_eval = 0;
         if (QUEUED) {
             IcpWarpScr& ws = *wscr;
+            if (a.tmode && a.tab.seed) {
+                // these are the queries the candidate table could not answer: far from the template, typically because the cloud has
+                // just moved a lot and the previous correspondent is a poor seed. The seed grid names a template point near the
+                // query's coarse cell (clamped to the grid); start from whichever of the two is closer. Any position is a valid seed.
+                const NnTableView& T = a.tab;
+                const int gx = min(max((int)floorf((sx - T.sorg[0]) * T.sinv_h), 0), T.snx - 1);
+                const int gy = min(max((int)floorf((sy - T.sorg[1]) * T.sinv_h), 0), T.sny - 1);
+                const int gz = min(max((int)floorf((sz - T.sorg[2]) * T.sinv_h), 0), T.snz - 1);
+                const int pos1 = (int)__ldg(T.seed + ((size_t)gz * T.sny + gy) * T.snx + gx);
+                const float3 t0 = tmpl_point(tp, pos0), t1 = tmpl_point(tp, pos1);
+                if (dist2(sx, sy, sz, t1.x, t1.y, t1.z) < dist2(sx, sy, sz, t0.x, t0.y, t0.z)) pos0 = pos1;
+            }
             const int L = pos0 / ICP_LEAF;
             const unsigned short* sl = s_sib + L * a.sib_max;
             ++nleaf_eval;

@@ -36,6 +36,12 @@ struct NnTableView {              // what k_icp needs at run time
     float org[3];
     float inv_h;
     int nx, ny, nz;
+    // seed grid for the queries the table cannot answer (far from the template): per coarse cell the kd position of the template point
+    // nearest to the cell's centre. ANY template position is a valid seed of the exact BVH search; a near one makes its bound tight.
+    const unsigned short* seed;   // [snz][sny][snx], NULL = none
+    float sorg[3];
+    float sinv_h;
+    int snx, sny, snz;
 };
 
 struct NnTableGeom {              // build-time geometry, all in double of the exact float values the run time uses
@@ -183,6 +189,40 @@ __global__ void __launch_bounds__(NNT_THREADS) k_nn_table_build(const float* __r
     out[1] = make_uint4(w[4], w[5], w[6], w[7]);
     out[2] = make_uint4(w[8], w[9], w[10], w[11]);
     out[3] = make_uint4(w[12], w[13], w[14], w[15]);
+}
+
+
+// seed grid: one thread per coarse cell, brute-force nearest template point of the cell centre (float: it is only a seed)
+template <int LEAF>
+__global__ void __launch_bounds__(NNT_THREADS) k_nn_seed_build(const float* __restrict__ tmpl, int n, float ox, float oy, float oz, float h, int nx, int ny, int nz,
+                                                               unsigned short* __restrict__ seed) {
+    constexpr int TILE = 512;
+    __shared__ float s_x[TILE], s_y[TILE], s_z[TILE];
+    const long long nc = (long long)nx * ny * nz;
+    const long long v = (long long)blockIdx.x * NNT_THREADS + threadIdx.x;
+    const bool live = v < nc;
+    const int ix = live ? (int)(v % nx) : 0, iy = live ? (int)((v / nx) % ny) : 0, iz = live ? (int)(v / ((long long)nx * ny)) : 0;
+    const float cx = ox + ((float)ix + 0.5f) * h, cy = oy + ((float)iy + 0.5f) * h, cz = oz + ((float)iz + 0.5f) * h;
+    float best = 3.0e38f;
+    int bpos = 0;
+    for (int t0 = 0; t0 < n; t0 += TILE) {
+        __syncthreads();
+        for (int j = threadIdx.x; j < TILE; j += NNT_THREADS) {
+            const int p = t0 + j;
+            if (p < n) {
+                const float* lf = tmpl + (size_t)(p / LEAF) * (3 * LEAF) + (p % LEAF);
+                s_x[j] = lf[0]; s_y[j] = lf[LEAF]; s_z[j] = lf[2 * LEAF];
+            }
+        }
+        __syncthreads();
+        const int cnt = min(TILE, n - t0);
+        for (int j = 0; j < cnt; ++j) {
+            const float dx = cx - s_x[j], dy = cy - s_y[j], dz = cz - s_z[j];
+            const float d = dx * dx + dy * dy + dz * dz;
+            if (d < best) { best = d; bpos = t0 + j; }
+        }
+    }
+    if (live) seed[v] = (unsigned short)bpos;
 }
 
 }  // namespace cuboid

@@ -90,6 +90,7 @@ struct cuboid_handle {
     // fused front end (frontend.cuh): one thread-block cluster per frame, persistent over the chunk
     int frontend = 1; int fe_cluster = 1; int fe_threads = 512; int fe_slots = 0; unsigned long long* d_fe_keys = nullptr;
     int fe_cluster_small = 0; int sms = 0;   // cluster size used when a launch has so few frames that one CTA per frame would leave most SMs idle (single-frame latency)
+    int fe_onepass = 1;                        // one-pass front end for depth input (static key bounds): CUBOID_FE_ONEPASS
     int fe_hash = 0; size_t fe_stride = 0;   // voxel-hash path of k_frontend (opt-in: CUBOID_FE_HASH=1; 1024 threads, one CTA per SM) and the per-slot scratch size in u64
     // host-buffer batches: sub-chunks run end to end on a few streams, so copies, front end and ICP of different sub-chunks overlap
     static constexpr int NPIPE = 4; cudaStream_t pipe[NPIPE] = {}; cudaEvent_t pipe_done[NPIPE] = {}; unsigned long long* d_pipe_keys[NPIPE] = {}; int pipeline = 1;
@@ -294,6 +295,32 @@ int run_chunk(cuboid_handle* h, const ChunkIn& in, int nf, cuboid_frame_result* 
         int fe_c = h->fe_cluster;
         if (fe_c == 1 && h->fe_cluster_small > 1 && (long long)nf * h->fe_cluster_small <= h->sms) fe_c = h->fe_cluster_small;
         fa.keys_stride = h->fe_stride; fa.hash = (h->fe_hash && h->fe_threads == 1024 && fe_c == 1) ? h->fe_hash : 0;
+        fa.st_on = 0;
+        if (!in.blob && fe_c == 1 && h->fe_onepass && in.w > 0 && in.hgt > 0) {
+            // static bounds of floor(coordinate / leaf) over everything the pass-through filters can let through (float products and
+            // floors are monotone, so the device's values stay inside): x and z from the limits, y = z * yr[v] from the corners
+            std::vector<float> yr2(2);
+            { volatile float t0 = 0.0f - p.cy; yr2[0] = t0 / p.fy; volatile float t1 = (float)(in.hgt - 1) - p.cy; yr2[1] = t1 / p.fy; }
+            const float inv = fa.inv_leaf;
+            const float zl = std::max(a.z_lo, 0.0f), zh = a.z_hi;
+            float ylo = 3.0e38f, yhi = -3.0e38f;
+            for (float z : {zl, zh}) for (float y : yr2) { volatile float v = z * y; ylo = std::min(ylo, (float)v); yhi = std::max(yhi, (float)v); }
+            const float lo[3] = {a.x_lo, ylo, zl}, hi[3] = {a.x_hi, yhi, zh};
+            long long dims = 1; int bits[3]; bool ok = zh >= zl;
+            for (int k = 0; k < 3 && ok; ++k) {
+                volatile float fl = lo[k] * inv, fh = hi[k] * inv;
+                const double l = std::floor((double)(float)fl), u = std::floor((double)(float)fh);
+                ok = std::isfinite(l) && std::isfinite(u) && u >= l && std::fabs(l) < 4.0e6 && std::fabs(u) < 4.0e6;
+                if (!ok) break;
+                fa.st_min[k] = (int)l;
+                const long long d = (long long)(u - l) + 1;
+                bits[k] = 0; while ((1LL << bits[k]) < d) ++bits[k];
+                dims *= d;
+            }
+            if (ok && bits[0] + bits[1] + bits[2] <= 32 && dims <= 2147483647LL) {
+                fa.st_on = 1; fa.st_b0 = bits[0]; fa.st_b1 = bits[0] + bits[1]; fa.st_bits = bits[0] + bits[1] + bits[2];
+            }
+        }
         cudaLaunchConfig_t cfg{};
         cudaLaunchAttribute at[1];
         at[0].id = cudaLaunchAttributeClusterDimension;
@@ -642,6 +669,7 @@ static int create_impl(cuboid_handle** out, const cuboid_params* p, int device, 
     {   // fused front end: cluster size and the number of clusters the device keeps resident
         const char* ef = std::getenv("CUBOID_FRONTEND"); if (ef) h->frontend = atoi(ef) ? 1 : 0;
         const char* ec = std::getenv("CUBOID_FE_CLUSTER"); if (ec) h->fe_cluster = std::max(1, std::min(16, atoi(ec)));
+        const char* eo1 = std::getenv("CUBOID_FE_ONEPASS"); if (eo1) h->fe_onepass = atoi(eo1) ? 1 : 0;
         const char* eh = std::getenv("CUBOID_FE_HASH"); if (eh) h->fe_hash = std::max(0, std::min(2, atoi(eh)));   // 2: developer, mark the path taken in status
         // Opt-in (measured slower than the radix path on B200: 7.1 ms against 4.75 ms per 1024 VGA frames): the
         // voxel-hash path (one 1024-thread CTA per SM); frames with more voxels than its table holds fall back per frame to the radix

@@ -29,6 +29,11 @@ struct FrontArgs {
     unsigned long long* keys;    // [n_slots][keys_stride] scratch of the frame a cluster slot is working on: the radix ping-pong [2][P], or the
                                  // voxel-hash path's records / offsets / slot ids / grouped point indices (FehScratch)
     size_t keys_stride;          // u64 per slot
+    // One-pass mode (depth input, one CTA per frame, no parity taps): the sort key of a point is its (k, j, i) voxel coordinates relative to
+    // STATIC lower bounds the host derives from the pass-through limits and the intrinsics, k in the top bits. Its order is the order
+    // of PCL's idx = i + j*dx + k*dx*dy for any actual min / max, so the first pass over the inputs (survivor count, min / max: A1)
+    // is not needed before the keys can be written: min / max are reduced during the one pass and the geometry is published after it.
+    int st_on, st_min[3], st_b0, st_b1, st_bits;
     int hash;                    // 1: try the voxel-hash path first (needs NT = 1024, cluster size 1), fall back to the radix path per frame
     int* kpp;                    // [F][P] voxel idx per point (parity tap) or NULL
     float4* vox;                 // [F][P]
@@ -630,10 +635,11 @@ __global__ void __launch_bounds__(NT, 2048 / NT >= 2 ? (NT <= 512 ? 2 : 1) : 1) 
         const int s0 = min(n_in, r * slice), s1 = min(n_in, r * slice + slice);
         unsigned char* s_mask = fe_dyn + NT * 32;
         const bool hash_try = NT == 1024 && C == 1 && a.hash != 0;    // the hash path recomputes the masks (its table takes their room)
-        const bool use_mask = !hash_try && ((slice + TILE - 1) / TILE) * NT <= FE_MASK_BYTES;
+        const bool onepass = SRC == 0 && C == 1 && a.st_on != 0 && !a.kpp && !a.hashes && !hash_try;   // kernel-uniform
+        const bool use_mask = !hash_try && !onepass && ((slice + TILE - 1) / TILE) * NT <= FE_MASK_BYTES;
 
         // ---- A1: survivors and min/max of this CTA's input slice ----
-        {
+        if (!onepass) {
             int cnt = 0;
             float mn[3] = {3.402823466e38f, 3.402823466e38f, 3.402823466e38f};
             float mx[3] = {-3.402823466e38f, -3.402823466e38f, -3.402823466e38f};
@@ -678,8 +684,8 @@ __global__ void __launch_bounds__(NT, 2048 / NT >= 2 ? (NT <= 512 ? 2 : 1) : 1) 
                 for (int c = 0; c < 3; ++c) { s_x.mn[c] = xmn[c]; s_x.mx[c] = xmx[c]; }
             }
         }
-        cluster.sync();
-        if (tid == 0) {
+        if (!onepass) cluster.sync();
+        if (tid == 0 && !onepass) {
             int base = 0, N = 0;
             float mn[3] = {3.402823466e38f, 3.402823466e38f, 3.402823466e38f};
             float mx[3] = {-3.402823466e38f, -3.402823466e38f, -3.402823466e38f};
@@ -717,13 +723,14 @@ __global__ void __launch_bounds__(NT, 2048 / NT >= 2 ? (NT <= 512 ? 2 : 1) : 1) 
             }
         }
         __syncthreads();
-        const int N = s_f.N;
+        int N = onepass ? 1 : s_f.N;     // one-pass mode learns N at the end of A2
         if (N == 0) {          // cluster-uniform; the barrier keeps a fast CTA from overwriting s_x while a peer still reads it
             cluster.sync();
             continue;
         }
-        const VoxelGeom g = s_f.g;
-        const int npass = (g.sort_bits + 7) / 8;
+        VoxelGeom g = s_f.g;             // one-pass mode: stale, not used before it is recomputed after A2
+        if (onepass) { g.inv = a.inv_leaf; g.overflow_mode = 0; }
+        const int npass = onepass ? (a.st_bits + 7) / 8 : (g.sort_bits + 7) / 8;
         if constexpr (NT == 1024) {
             if (hash_try) {
                 FehStatic st;
@@ -746,8 +753,10 @@ __global__ void __launch_bounds__(NT, 2048 / NT >= 2 ? (NT <= 512 ? 2 : 1) : 1) 
             unsigned short* s_dep = reinterpret_cast<unsigned short*>(fe_dyn + NT * 16);
             float4* out = p.pts + (size_t)f * p.Pout;
             int* kpp = a.kpp ? a.kpp + (size_t)f * a.P : nullptr;
-            int run = s_f.base;
+            int run = onepass ? 0 : s_f.base;
             unsigned long long hh[2] = {0ull, 0ull};
+            float omn[3] = {3.402823466e38f, 3.402823466e38f, 3.402823466e38f};      // one-pass mode: min / max of the survivors
+            float omx[3] = {-3.402823466e38f, -3.402823466e38f, -3.402823466e38f};
             int it = 0;
             for (int t0 = s0; t0 < s1; t0 += TILE, ++it) {
                 const int first = t0 + tid * FE_ITEMS;
@@ -764,6 +773,15 @@ __global__ void __launch_bounds__(NT, 2048 / NT >= 2 ? (NT <= 512 ? 2 : 1) : 1) 
                     else {
                         float px[FE_ITEMS], py[FE_ITEMS], pz[FE_ITEMS];
                         keep = pre_points<SRC>(p, f, first, s1, px, py, pz);
+                        if (onepass) {
+#pragma unroll
+                            for (int k = 0; k < FE_ITEMS; ++k)
+                                if (keep & (1u << k)) {
+                                    omn[0] = fminf(omn[0], px[k]); omx[0] = fmaxf(omx[0], px[k]);
+                                    omn[1] = fminf(omn[1], py[k]); omx[1] = fmaxf(omx[1], py[k]);
+                                    omn[2] = fminf(omn[2], pz[k]); omx[2] = fmaxf(omx[2], pz[k]);
+                                }
+                        }
                     }
                 }
                 int total;
@@ -781,8 +799,15 @@ __global__ void __launch_bounds__(NT, 2048 / NT >= 2 ? (NT <= 512 ? 2 : 1) : 1) 
                         const float4 pt = SRC == 0 ? fe_point_from_depth(p, t0 + sel, s_dep[sel]) : fe_point_at<SRC>(p, f, t0 + sel);
                         const int pos = run + q;
                         out[pos] = pt;
-                        const int idx = voxel_index(g, pt.x, pt.y, pt.z);
-                        sk = g.overflow_mode ? ((unsigned int)idx ^ 0x80000000u) : (unsigned int)idx;
+                        int idx = 0;
+                        if (onepass) {   // (k, j, i) relative to the static bounds: orders like PCL's idx whatever the frame's own min / max turn out to be
+                            const int i0 = (int)floorf(pt.x * g.inv) - a.st_min[0], i1 = (int)floorf(pt.y * g.inv) - a.st_min[1],
+                                      i2 = (int)floorf(pt.z * g.inv) - a.st_min[2];
+                            sk = (unsigned int)i0 | ((unsigned int)i1 << a.st_b0) | ((unsigned int)i2 << a.st_b1);
+                        } else {
+                            idx = voxel_index(g, pt.x, pt.y, pt.z);
+                            sk = g.overflow_mode ? ((unsigned int)idx ^ 0x80000000u) : (unsigned int)idx;
+                        }
                         __stcg(bufA + pos, ((unsigned long long)sk << 32) | (unsigned int)pos);
                         if (kpp) kpp[pos] = idx;
                         if (a.hashes) {
@@ -803,6 +828,45 @@ __global__ void __launch_bounds__(NT, 2048 / NT >= 2 ? (NT <= 512 ? 2 : 1) : 1) 
             if (tid == 0) {
                 if (hh[0]) atomic_add_u64(&p.res[f].points_hash, hh[0]);
                 if (hh[1]) atomic_add_u64(&p.res[f].voxel_key_hash, hh[1]);
+            }
+            if (onepass) {   // what A1 and the frame set-up would have published: survivor count, min / max -> min_b / div_b
+                N = run;
+#pragma unroll
+                for (int o = 16; o >= 1; o >>= 1)
+#pragma unroll
+                    for (int c = 0; c < 3; ++c) {
+                        omn[c] = fminf(omn[c], __shfl_xor_sync(FULL_MASK, omn[c], o));
+                        omx[c] = fmaxf(omx[c], __shfl_xor_sync(FULL_MASK, omx[c], o));
+                    }
+                if (lane == 0)
+#pragma unroll
+                    for (int c = 0; c < 3; ++c) { s_mm[wid][c] = omn[c]; s_mm[wid][3 + c] = omx[c]; }
+                __syncthreads();
+                if (tid == 0) {
+                    float xmn[3] = {3.402823466e38f, 3.402823466e38f, 3.402823466e38f};
+                    float xmx[3] = {-3.402823466e38f, -3.402823466e38f, -3.402823466e38f};
+                    for (int w = 0; w < NW; ++w)
+                        for (int c = 0; c < 3; ++c) { xmn[c] = fminf(xmn[c], s_mm[w][c]); xmx[c] = fmaxf(xmx[c], s_mm[w][3 + c]); }
+                    FrameScratch sc;
+                    sc.mm[0] = sc.mm[1] = sc.mm[2] = 0xffffffffu;
+                    sc.mm[3] = sc.mm[4] = sc.mm[5] = 0u;
+                    sc.sort_bits = 0; sc.overflow_mode = 0; sc.best_count = 0; sc.pad = 0;
+                    cuboid_frame_result& R = p.res[f];
+                    R.n_points = N;
+                    if (N > 0) {
+                        for (int k = 0; k < 3; ++k) { sc.mm[k] = enc_f32(xmn[k]); sc.mm[3 + k] = enc_f32(xmx[k]); }
+                        const VoxelGeom gg = voxel_geom(sc, a.inv_leaf);
+                        sc.sort_bits = gg.sort_bits; sc.overflow_mode = gg.overflow_mode;
+                        for (int k = 0; k < 3; ++k) { R.min_b[k] = gg.min_b[k]; R.div_b[k] = gg.div_b[k]; }
+                        if (gg.pcl_overflow) atomicOr(&R.status, CUBOID_W_VOXEL_OVERFLOW);
+                    } else {
+                        R.n_voxels = 0;
+                    }
+                    p.scr[f] = sc;
+                    s_ndef = 0;
+                }
+                __syncthreads();
+                if (N == 0) continue;   // block-uniform (C == 1: no cluster peers to keep in step)
             }
         }
         __threadfence();

@@ -9,17 +9,28 @@ Contract (driver): python bench.py --gpus N --steps K --warmup W  [--impl refere
     recorded on the library's own stream (max over ranks);
   * `e2e`    : the same metric through cuboid_process_batch with PINNED HOST depth buffers: host->device copy of
     every frame and device->host copy of every frame's result inside the timed region; steps are dealt round-robin over
-    --e2e-handles library handles (default 3), one host thread each, so that one batch's copies run under another's ICP;
-  * `roofline`: the dominant kernel (k_icp, FP32-pipe bound: un-fused FMUL/FADD) — algorithmic
-    flops from the per-frame results (8*S*T per nearest-neighbour pass) over its CUDA-event time, against the
-    un-fused FP32 peak measured in the same run; `roofline_hbm` is the same for the HBM-bound fused front end
+    --e2e-handles library handles (default 3), one host thread each, so that one batch's copies run under another's ICP.
+    `h2d_ceiling_gbs_per_gpu` is the bare pinned copy of the same bytes on every rank at once (nothing else running):
+    what the box's PCIe / host memory allows, and `frac_of_h2d_ceiling` is the end-to-end figure against it;
+  * `roofline`: the dominant kernel, k_icp. Its nominal roofline is the FP32 pipe with un-fused FMUL / FADD (bit-exactness
+    forbids FFMA): `achieved` = the flops the kernel EXECUTED (8 per source-template pair it evaluated, counted by the kernel)
+    over its CUDA-event time, `frac` = that over the un-fused peak measured in the same run. The brute-force-equivalent rate
+     is kept under `algorithmic` as context only; `issue` (profiles/icp_issue.json, from the committed ncu
+    capture) says what actually bounds the kernel: issue slots and latency. `roofline_hbm` is the HBM-bound fused front end
     (k_frontend: unproject + passthrough + voxel grid in one kernel, algorithmic bytes 2*P + 32*N + 16*V per frame)
     against MEASURED_PEAKS.json; its `traffic` is the dram__bytes figure of the committed ncu capture (profiles/);
-  * `cpu_baseline`: the CPU oracle (restatement of the PCL path, 1 thread like the reference node) on a bounded
-    sample of the same frames; the same sample is re-run on the GPU with the parity taps on (the timed runs carry
-    none) and must match the oracle's hashes, and the timed run's results in every other byte;
-  * --impl reference: that CPU restatement on all host cores (the real PCL/ROS reference cannot be built
-    offline: DESIGN.md), same metric/config, rank 0 only.
+  * `configs`: every other BASELINE.json config in the same line (1 GPU, default run): single-frame latency through
+    cuboid_process_cloud with host buffers (p50 / p99 of 200 calls), ground-plane segmentation only, 64 hypotheses per
+    cluster, 8 objects per frame, 1280x720 - each with value / e2e / stage ms and its own CPU baseline;
+  * `cpu_baseline`: the CPU oracle (restatement of the PCL path) in LITERAL mode, 1 thread like the reference node, 3 warm-up
+    frames + the median of 10 per-frame times; a sample of the same batch is also run through the
+    oracle in canonical mode and re-run on the GPU with the parity taps on (the timed runs carry none): it must match the
+    oracle's hashes, and the timed run's results in every other byte;
+  * --impl reference: that CPU restatement (literal mode) on all host cores; each step = a bounded sample (2 x cores frames) of
+    the same workload. The real PCL/ROS reference cannot be built offline; oracle/pcl_probe.py looks for a PCL at
+    run time and, if it finds one, builds and times the literal PCL harness beside it. Rank 0 only;
+  * --shard hypotheses (with --workload guess64): the low-latency multi-GPU mode - every rank runs the same frames with its
+    slice of the initial-pose hypotheses, one all_gather of 80-byte records, exact arg-min (strong scaling).
 """
 import argparse
 import json

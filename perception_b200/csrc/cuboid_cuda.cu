@@ -481,10 +481,11 @@ int run_chunk(cuboid_handle* h, const ChunkIn& in, int nf, cuboid_frame_result* 
         CK(h, cudaMemsetAsync(a.queue, 0, sizeof(IcpQueue), st));
         CK(h, cudaMemsetAsync(a.ring, 0, sizeof(IcpSlot) * (size_t)a.n_slots, st));
         a.crew = (int)std::max<long long>(1, std::min<long long>(h->icp_ctas, (long long)nf * ng * CUBOID_MAX_CLUSTERS));
-        // sub-workers per CTA: four of 256 threads when there is at least one problem per sub-worker (one cluster per frame and
-        // guess assumed), else two of 512, else all 1024 threads on one problem: with few problems the latency of each counts
+        // sub-workers per CTA: as few (= as wide) as still keep every problem of the launch resident at once (one cluster per frame
+        // and guess assumed): all 1024 threads on one problem while there are no more problems than CTAs, two sub-workers of 512
+        // up to two problems per CTA, four of 256 beyond - with few problems the latency of each is what counts
         const long long nprob = (long long)nf * ng;
-        a.nsub = nprob >= 4LL * a.crew ? 4 : (nprob >= 2LL * a.crew ? 2 : 1);
+        a.nsub = nprob > 2LL * a.crew ? 4 : (nprob > (long long)a.crew ? 2 : 1);
         if (h->icp_nsub_force) a.nsub = h->icp_nsub_force;
         const int mode = a.tmode ? 3 : (a.qmode ? 2 : (a.resident ? 1 : 0));
         a.local_cap = 0;
@@ -1097,6 +1098,8 @@ int cuboid_segment_plane(cuboid_handle* h, const float* xyzw, int n, const int32
     if (inlier_idx_out && r.n_inliers) CK(h, cudaMemcpy(inlier_idx_out, h->d_inl, sizeof(int) * r.n_inliers, cudaMemcpyDeviceToHost));
     if (inlier_pre_out && r.n_inliers_pre) CK(h, cudaMemcpy(inlier_pre_out, h->d_inl_pre, sizeof(int) * r.n_inliers_pre, cudaMemcpyDeviceToHost));
     if (remain_xyzw_out && r.n_remain) CK(h, cudaMemcpy(remain_xyzw_out, h->d_remain, sizeof(float4) * r.n_remain, cudaMemcpyDeviceToHost));
+    // the remainder is capped at the handle's M (min(max_points, 65536)) points: say so instead of handing back a silently shorter cloud
+    if (r.status & CUBOID_W_CLUSTERS_TRUNCATED) { h->last_error = "cuboid_segment_plane: more non-plane points than the handle's remainder capacity"; return CUBOID_E_CAPACITY; }
     return CUBOID_OK;
 }
 
@@ -1198,6 +1201,7 @@ int cuboid_surface_normals(cuboid_handle* h, const float* xyzw, int n, const flo
         cuboid_frame_result r;
         if (cudaMemcpyAsync(&r, h->d_res, sizeof r, cudaMemcpyDeviceToHost, h->stream) != cudaSuccess ||
             cudaStreamSynchronize(h->stream) != cudaSuccess) { rc = CUBOID_E_CUDA; break; }
+        if (r.status & CUBOID_W_CLUSTERS_TRUNCATED) { h->last_error = "cuboid_surface_normals: more leftover points than the handle's remainder capacity"; rc = CUBOID_E_CAPACITY; break; }
         out->found[i] = r.plane_found;
         out->n_plane[i] = r.n_inliers;
         for (int k = 0; k < 4; ++k) out->coeff[i][k] = r.plane_coeff[k];

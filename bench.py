@@ -504,7 +504,15 @@ def single_frame_latency(local_rank, calls=200, warm=20):
         cc.set_template(0, tm)
         cc.set_option(api.OPT_TAPS, 0)
         cloud = np.ascontiguousarray(cc.unproject(depth))      # what realsense2_camera would publish: all 307 200 points, xyz + pad
-        for name, fn in (("process_cloud", lambda: cc.process_cloud(cloud)), ("process_batch_1", lambda: cc.process_batch(depth[None]))):
+        try:                                                   # the same message in page-locked memory (a node that cares pins its buffer)
+            import torch
+            pinned = torch.from_numpy(cloud).pin_memory().numpy()
+        except Exception:
+            pinned = None
+        cases = [("process_cloud", lambda: cc.process_cloud(cloud)), ("process_batch_1", lambda: cc.process_batch(depth[None]))]
+        if pinned is not None:
+            cases.append(("process_cloud_pinned", lambda: cc.process_cloud(pinned)))
+        for name, fn in cases:
             for _ in range(warm):
                 r = fn()
             ts = []
@@ -513,10 +521,11 @@ def single_frame_latency(local_rank, calls=200, warm=20):
                 r = fn()
                 ts.append(time.perf_counter() - t0)
             ts = np.asarray(ts) * 1e3
-            r0 = r if name == "process_cloud" else r[0]
+            r0 = r[0] if name == "process_batch_1" else r
             out[name] = {"p50_ms": float(np.percentile(ts, 50)), "p99_ms": float(np.percentile(ts, 99)), "mean_ms": float(ts.mean()),
                          "calls": calls, "frames_per_s_at_p50": 1e3 / float(np.percentile(ts, 50)),
-                         "h2d_bytes_per_call": int(cloud.nbytes if name == "process_cloud" else depth.nbytes),
+                         "h2d_bytes_per_call": int(depth.nbytes if name == "process_batch_1" else cloud.nbytes),
+                         "host_buffer": "pinned" if name == "process_cloud_pinned" else "pageable (numpy)",
                          "icp_iterations": int(r0.cluster[0].iterations), "accepted": int(r0.cluster[0].accepted)}
     out["workload"] = ("BASELINE configs[0]: single synthetic 640x480 frame (cuboid1, seed 0), voxel + RANSAC plane + cluster + ICP vs the "
                        "7250-point template, one call per frame with host buffers")

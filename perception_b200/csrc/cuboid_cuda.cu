@@ -89,6 +89,7 @@ struct cuboid_handle {
     struct { int active = 0; int model_type = 0; float axis[3] = {0, 0, 0}; double eps = 0.0, thr = 0.0; } sac_override;   // cuboid_surface_normals
     // fused front end (frontend.cuh): one thread-block cluster per frame, persistent over the chunk
     int frontend = 1; int fe_cluster = 1; int fe_threads = 512; int fe_slots = 0; unsigned long long* d_fe_keys = nullptr;
+    int sac_wide = 1;                        // 1024-thread k_sac_plane for launches with few frames
     int fe_cluster_small = 0; int sms = 0;   // cluster size used when a launch has so few frames that one CTA per frame would leave most SMs idle (single-frame latency)
     int fe_onepass = 1;                        // one-pass front end for depth input (static key bounds): CUBOID_FE_ONEPASS
     int fe_hash = 0; size_t fe_stride = 0;   // voxel-hash path of k_frontend (opt-in: CUBOID_FE_HASH=1; 1024 threads, one CTA per SM) and the per-slot scratch size in u64
@@ -411,7 +412,9 @@ int run_chunk(cuboid_handle* h, const ChunkIn& in, int nf, cuboid_frame_result* 
         }
         for (int k = 0; k < 12; ++k) s.bbP[k] = h->bbP[k];
         for (int k = 0; k < 4; ++k) s.bb[k] = h->bb[k];
-        k_sac_plane<<<nf, SAC_THREADS, sizeof(SacShared), st>>>(s);
+        // few frames (one ROS callback, a small 720p batch): a 1024-thread CTA per frame instead of leaving most SMs idle
+        if (h->sac_wide && 2LL * nf <= h->sms) k_sac_plane<1024><<<nf, 1024, sizeof(SacShared), st>>>(s);
+        else k_sac_plane<SAC_THREADS><<<nf, SAC_THREADS, sizeof(SacShared), st>>>(s);
         ++h->launches;
         CK(h, cudaGetLastError());
     }
@@ -487,6 +490,9 @@ int run_chunk(cuboid_handle* h, const ChunkIn& in, int nf, cuboid_frame_result* 
         const long long nprob = (long long)nf * ng;
         a.nsub = nprob > 2LL * a.crew ? 4 : (nprob > (long long)a.crew ? 2 : 1);
         if (h->icp_nsub_force) a.nsub = h->icp_nsub_force;
+        // time slicing evens out the tail when problems outnumber the sub-workers; with a sub-worker per problem nothing waits in the
+        // queue, so a problem runs to the end in one slice (no state round trips through global memory)
+        if (nprob * CUBOID_MAX_CLUSTERS <= (long long)a.crew * a.nsub || (p.use_cluster == 0 && nprob <= (long long)a.crew * a.nsub)) a.slice_iters = 1 << 28;
         const int mode = a.tmode ? 3 : (a.qmode ? 2 : (a.resident ? 1 : 0));
         a.local_cap = 0;
         if (mode == 3 && a.nsub == 1 && h->icp_local) {   // the rest of the shared memory holds the working set (24 B per point) of the CTA's problem
@@ -734,7 +740,9 @@ static int create_impl(cuboid_handle** out, const cuboid_params* p, int device, 
     CA(dalloc(h, &h->d_stats, (size_t)32));
     if (cudaMemset(h->d_stats, 0, 256) != cudaSuccess) return fail(CUBOID_E_CUDA);
     { const char* ec = std::getenv("CUBOID_ICP_CULL"); if (ec) h->icp_cull = atoi(ec) ? 1 : 0; }
-    if (cudaFuncSetAttribute(k_sac_plane, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)sizeof(SacShared)) != cudaSuccess) return fail(CUBOID_E_CUDA);
+    if (cudaFuncSetAttribute(k_sac_plane<SAC_THREADS>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)sizeof(SacShared)) != cudaSuccess) return fail(CUBOID_E_CUDA);
+    if (cudaFuncSetAttribute(k_sac_plane<1024>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)sizeof(SacShared)) != cudaSuccess) return fail(CUBOID_E_CUDA);
+    { const char* ew = std::getenv("CUBOID_SAC_WIDE"); if (ew) h->sac_wide = atoi(ew) ? 1 : 0; }
     if (cudaFuncSetAttribute(k_cluster, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)CLU_DYN_SMEM) != cudaSuccess) return fail(CUBOID_E_CUDA);
     if (cudaFuncSetAttribute(k_cluster_big, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)CLU_DYN_SMEM_BIG) != cudaSuccess) return fail(CUBOID_E_CUDA);
 #undef CA

@@ -208,7 +208,7 @@ struct SacShared {
     unsigned long long bar[2];
     SacHyp hyp[SAC_HB];
     int counts[SAC_HB];
-    int s_w[9];
+    int s_w[33];
     float sums[9];
     float best_c[4], coeff[4];
     int n_hyp, done, have_model, rp, n_inl_pre, n_inl, n_rem;
@@ -217,13 +217,13 @@ struct SacShared {
 };
 
 // ordered compaction of {i : pred(i)} over [0,V) into out_idx / out_pts (either may be NULL); returns count.
-template <typename Pred>
+template <int NT = SAC_THREADS, typename Pred>
 __device__ int sac_compact(int V, Pred pred, int* out_idx, float4* out_pts, const float4* vox, int cap,
                            uint64_t* hash_idx, uint64_t* hash_pts, int* s_w) {
     constexpr int PER = 4;   // consecutive elements per thread and round: a quarter of the block scans of one-per-thread
     int base = 0;
     unsigned long long hi = 0, hp = 0;
-    for (int start = 0; start < V; start += SAC_THREADS * PER) {
+    for (int start = 0; start < V; start += NT * PER) {
         const int i0 = start + threadIdx.x * PER;
         float4 p[PER];
         unsigned int keep = 0;
@@ -233,7 +233,7 @@ __device__ int sac_compact(int V, Pred pred, int* out_idx, float4* out_pts, cons
             if (i0 + k < V) { p[k] = vox[i0 + k]; if (pred(i0 + k, p[k])) keep |= 1u << k; }
         }
         int total;
-        int pos = base + block_excl_scan256(__popc(keep), s_w, &total);
+        int pos = base + (NT == 256 ? block_excl_scan256(__popc(keep), s_w, &total) : block_excl_scan<NT>(__popc(keep), s_w, &total));
 #pragma unroll
         for (int k = 0; k < PER; ++k) {
             if (!(keep & (1u << k))) continue;
@@ -251,7 +251,13 @@ __device__ int sac_compact(int V, Pred pred, int* out_idx, float4* out_pts, cons
     return base;
 }
 
-__global__ void __launch_bounds__(SAC_THREADS, 1) k_sac_plane(const SacArgs a) {
+// NT = 256: one CTA per frame, four per SM (throughput). NT = 1024: launches with so few frames that most SMs would idle (the
+// single-frame ROS callback, small 720p batches): the 32 warps split every point tile four ways per hypothesis group, compactions
+// and the product staging of the refinement run four times as wide; the sequential parts (draw, accept, the 9 refine chains) are
+// the same. Results do not depend on NT.
+template <int NT>
+__global__ void __launch_bounds__(NT, 1) k_sac_plane(const SacArgs a) {
+    constexpr int NSLICE = NT / 256;    // warps per hypothesis group
     extern __shared__ __align__(128) unsigned char smem_raw[];
     SacShared& S = *reinterpret_cast<SacShared*>(smem_raw);
     const int f = blockIdx.x;
@@ -266,7 +272,7 @@ __global__ void __launch_bounds__(SAC_THREADS, 1) k_sac_plane(const SacArgs a) {
         mbar_init(&S.bar[0], 1); mbar_init(&S.bar[1], 1);
         asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
     }
-    if (!a.triplets) for (int i = threadIdx.x; i < V; i += SAC_THREADS) shuffled[i] = i;
+    if (!a.triplets) for (int i = threadIdx.x; i < V; i += NT) shuffled[i] = i;
     __syncthreads();
 
     unsigned int phase0 = 0, phase1 = 0;
@@ -310,13 +316,15 @@ __global__ void __launch_bounds__(SAC_THREADS, 1) k_sac_plane(const SacArgs a) {
         __syncthreads();
         const int nh = S.n_hyp;
 
-        // ---- score: warp w owns hypotheses w, w+8, ... ; tiles arrive by TMA bulk copy ----
+        // ---- score: warp w owns hypotheses (w % 8), (w % 8) + 8, ... on slice w / 8 of every tile; tiles arrive by TMA bulk copy ----
         float hc[4][4];
         int hcnt[4] = {0, 0, 0, 0};
         bool hact[4];
+        const int hgrp = wid & 7, slice = wid >> 3;
+        if (NSLICE > 1) { if (threadIdx.x < SAC_HB) S.counts[threadIdx.x] = 0; }
 #pragma unroll
         for (int s = 0; s < 4; ++s) {
-            const int h = wid + 8 * s;
+            const int h = hgrp + 8 * s;
             hact[s] = h < nh && S.hyp[h].valid && S.hyp[h].ok;
 #pragma unroll
             for (int c = 0; c < 4; ++c) hc[s][c] = hact[s] ? S.hyp[h].c[c] : 0.f;
@@ -337,7 +345,7 @@ __global__ void __launch_bounds__(SAC_THREADS, 1) k_sac_plane(const SacArgs a) {
             }
             if (buf == 0) { mbar_wait(&S.bar[0], phase0); phase0 ^= 1; } else { mbar_wait(&S.bar[1], phase1); phase1 ^= 1; }
             const int cntp = min(SAC_TILE, V - tl * SAC_TILE);
-            for (int j0 = 0; j0 < cntp; j0 += 32) {
+            for (int j0 = slice * (SAC_TILE / NSLICE); j0 < min(cntp, (slice + 1) * (SAC_TILE / NSLICE)); j0 += 32) {
                 const int j = j0 + lane;
                 const bool in = j < cntp;
                 const float4 p = in ? S.tile[buf][j] : make_float4(0.f, 0.f, 0.f, 0.f);
@@ -352,7 +360,10 @@ __global__ void __launch_bounds__(SAC_THREADS, 1) k_sac_plane(const SacArgs a) {
         }
         if (lane == 0) {
 #pragma unroll
-            for (int s = 0; s < 4; ++s) { const int h = wid + 8 * s; if (h < SAC_HB) S.counts[h] = hcnt[s]; }
+            for (int s = 0; s < 4; ++s) {
+                const int h = hgrp + 8 * s;
+                if (h < SAC_HB) { if (NSLICE > 1) atomicAdd(&S.counts[h], hcnt[s]); else S.counts[h] = hcnt[s]; }
+            }
         }
         __syncthreads();
 
@@ -401,7 +412,7 @@ __global__ void __launch_bounds__(SAC_THREADS, 1) k_sac_plane(const SacArgs a) {
         for (int k = 0; k < 4; ++k) c[k] = S.best_c[k];
         const float thr = a.thr_f;
         const bool ok_pre = sac_model_valid(a, c);   // selectWithinDistance clears the inliers of an invalid model
-        n_pre = sac_compact(V, [&](int, const float4& p) { return ok_pre && plane_abs_dist(c, p.x, p.y, p.z) < thr; }, inl_pre, nullptr, vox,
+        n_pre = sac_compact<NT>(V, [&](int, const float4& p) { return ok_pre && plane_abs_dist(c, p.x, p.y, p.z) < thr; }, inl_pre, nullptr, vox,
                             a.P, nullptr, nullptr, S.s_w);
         if (a.refine && n_pre >= 4) {
             // PCL accumulates the 9 sums sequentially in float over the inliers in index order.
@@ -410,7 +421,7 @@ __global__ void __launch_bounds__(SAC_THREADS, 1) k_sac_plane(const SacArgs a) {
             float (*prod)[SAC_PROD + 1] = reinterpret_cast<float (*)[SAC_PROD + 1]>(&S.tile[0][0]);   // padded rows: conflict-free lanes
             for (int start = 0; start < n_pre; start += SAC_PROD) {
                 const int m = min(SAC_PROD, n_pre - start);
-                for (int j = threadIdx.x; j < m; j += SAC_THREADS) {
+                for (int j = threadIdx.x; j < m; j += NT) {
                     const float4 p = vox[inl_pre[start + j]];
                     prod[0][j] = p.x * p.x; prod[1][j] = p.x * p.y; prod[2][j] = p.x * p.z;
                     prod[3][j] = p.y * p.y; prod[4][j] = p.y * p.z; prod[5][j] = p.z * p.z;
@@ -438,7 +449,7 @@ __global__ void __launch_bounds__(SAC_THREADS, 1) k_sac_plane(const SacArgs a) {
         const bool same = !(a.refine && n_pre >= 4);
         (void)same;
         const bool ok_fin = sac_model_valid(a, c);
-        n_inl = sac_compact(V, [&](int, const float4& p) { return ok_fin && plane_abs_dist(c, p.x, p.y, p.z) < thr; }, inl, nullptr, vox, a.P,
+        n_inl = sac_compact<NT>(V, [&](int, const float4& p) { return ok_fin && plane_abs_dist(c, p.x, p.y, p.z) < thr; }, inl, nullptr, vox, a.P,
                             &R.inlier_hash, nullptr, S.s_w);
     }
     // ExtractIndices (+ PassThrough z2): negative -> everything that is not an inlier, ascending
@@ -446,7 +457,7 @@ __global__ void __launch_bounds__(SAC_THREADS, 1) k_sac_plane(const SacArgs a) {
     const int neg = a.negative, uz2 = a.use_z2;
     const bool ok_ext = have && sac_model_valid(a, c);
     const float z2lo = a.z2_lo, z2hi = a.z2_hi;
-    const int n_rem = sac_compact(
+    const int n_rem = sac_compact<NT>(
         V,
         [&](int, const float4& p) {
             const bool is_in = have && ok_ext && (plane_abs_dist(c, p.x, p.y, p.z) < thr);

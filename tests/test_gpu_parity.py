@@ -712,3 +712,75 @@ def test_one_pass_front_end_equals_two_pass(tmpl30, params, monkeypatch):
         for k in ("status", "n_points", "n_voxels", "n_inliers", "n_remain", "n_clusters", "inlier_hash", "remain_hash", "cluster_hash"):
             assert getattr(a, k) == getattr(tapped[i], k), (i, k)
         assert list(a.min_b) == list(tapped[i].min_b) and list(a.div_b) == list(tapped[i].div_b)
+
+
+def test_candidate_table_at_cell_boundaries_and_beyond_the_band(cc, tmpl30):
+    """The nearest-neighbour candidate table (nn_table.cuh) maps a query to a 1 mm cell with float arithmetic; its records are built
+    for the cell widened by a margin. Adversarial queries: exactly on cell faces / edges / corners of the grid and one ulp either
+    side of them, at every distance from the template surface up to and beyond the 25 mm band, plus points far outside the grid.
+    Iteration-0 correspondences must equal a float32 brute-force scan in template order (first minimum = lowest index)."""
+    tm = np.ascontiguousarray(tmpl30[:, :3], dtype=np.float32)
+    rng = np.random.default_rng(11)
+    h = np.float32(1e-3)
+    org = (tm.min(axis=0).astype(np.float64) - 25.0 * 1e-3).astype(np.float32)        # the grid origin cuboid_set_template derives
+    n = 6000
+    base = tm[rng.integers(0, len(tm), n)] + rng.normal(0, 1, (n, 3)).astype(np.float32) * rng.choice([0.001, 0.004, 0.012, 0.03, 0.08], (n, 1)).astype(np.float32)
+    cell = np.floor((base - org) / h).astype(np.float32)
+    snapped = (org + cell * h).astype(np.float32)                                     # on a grid face in every axis (a cell corner)
+    q = base.copy()
+    kind = rng.integers(0, 4, n)
+    for ax in range(3):
+        on = (kind == ax) | (kind == 3)                                               # faces (one axis) and corners (all three)
+        q[on, ax] = snapped[on, ax]
+    nudge = rng.integers(-1, 2, (n, 3))
+    q = np.where(nudge < 0, np.nextafter(q, np.float32(-np.inf)), np.where(nudge > 0, np.nextafter(q, np.float32(np.inf)), q)).astype(np.float32)
+    q[:50] += np.float32(0.7)                                                         # far outside the grid: BVH path
+    src = np.ones((n, 4), np.float32)
+    src[:, :3] = q
+    d = q[:, None, :] - tm[None, :, :]
+    d2 = ((d[..., 0] * d[..., 0]) + d[..., 1] * d[..., 1]).astype(np.float32) + d[..., 2] * d[..., 2]
+    want = d2.argmin(axis=1)
+    p = default_params("cuboid")
+    p.icp_max_iter = 1
+    cc.set_params(p)
+    try:
+        cc.set_template(5, tmpl30)
+        g = cc.icp(src, 5, trace_iters=1)
+    finally:
+        cc.set_params(default_params("cuboid"))
+    assert np.array_equal(g["corr_trace"][0], want)
+
+
+@pytest.mark.parametrize("seed", range(10))
+def test_random_parameter_sets_match_oracle(seed, tmpl30, tmpl100):
+    """Seeded parameter fuzz: leaf size, pass-through limits, RANSAC threshold, cluster tolerance / sizes, ICP epsilon, template, scene
+    kind - one frame each through cuboid_process_batch (taps on: the two-pass front end) and once more without taps (the one-pass
+    front end with its static key bounds), against the oracle."""
+    rng = np.random.default_rng(1000 + seed)
+    p = default_params("cuboid")
+    p.leaf = float(rng.choice([0.003, 0.004, 0.005, 0.0065, 0.008, 0.011]))
+    p.pass_z_max = float(rng.uniform(0.6, 1.2))
+    p.pass_z_min = float(rng.choice([0.0, 0.05, 0.2]))
+    xw = float(rng.uniform(0.12, 0.45))
+    p.pass_x_min, p.pass_x_max = -xw, float(xw * rng.uniform(0.7, 1.0))
+    p.sac_threshold = float(rng.choice([0.006, 0.01, 0.015, 0.02]))
+    p.cluster_tol = float(rng.choice([0.012, 0.02, 0.03]))
+    p.cluster_min = int(rng.choice([50, 200, 400]))
+    p.icp_rel_mse = p.icp_fitness_gate = float(rng.choice([1e-4, 4e-4, 2e-3]))
+    p.icp_max_iter = int(rng.choice([40, 5000]))
+    p.use_cluster = int(rng.integers(0, 2))
+    tm = tmpl30 if rng.integers(0, 2) else tmpl100
+    kind = str(rng.choice(["bench", "plane_var", "tallbox", "multi8"]))
+    depth = synth.depth_batch(kind, [int(rng.integers(0, 500))])
+    ref = O.process_frame(p, depth[0], tm)
+    with api.CuboidCuda(p, max_points=640 * 480, max_batch=1) as h:
+        h.set_template(0, tm)
+        res = h.process_batch(depth)
+        _same_frame(res[0], ref)
+        h.set_option(api.OPT_TAPS, 0)
+        fast = h.process_batch(depth)
+    a, b = type(ref).from_buffer_copy(bytes(fast[0])), type(ref).from_buffer_copy(bytes(res[0]))
+    b.points_hash = b.voxel_key_hash = b.voxel_hash = 0
+    for k in range(len(b.cluster)):
+        b.cluster[k].corr_hash = 0
+    assert bytes(a) == bytes(b)

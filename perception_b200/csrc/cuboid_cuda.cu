@@ -90,7 +90,7 @@ struct cuboid_handle {
     // fused front end (frontend.cuh): one thread-block cluster per frame, persistent over the chunk
     int frontend = 1; int fe_cluster = 1; int fe_threads = 512; int fe_slots = 0; unsigned long long* d_fe_keys = nullptr;
     int sac_wide = 1;                        // 1024-thread k_sac_plane for launches with few frames
-    int fe_cluster_small = 0; int sms = 0;   // cluster size used when a launch has so few frames that one CTA per frame would leave most SMs idle (single-frame latency)
+    int fe_cluster_small = 0; int sms = 0; int fe_runs = 0;   // cluster size used when a launch has so few frames that one CTA per frame would leave most SMs idle (single-frame latency)
     int fe_onepass = 1;                        // one-pass front end for depth input (static key bounds): CUBOID_FE_ONEPASS
     int fe_hash = 0; size_t fe_stride = 0;   // voxel-hash path of k_frontend (opt-in: CUBOID_FE_HASH=1; 1024 threads, one CTA per SM) and the per-slot scratch size in u64
     // host-buffer batches: sub-chunks run end to end on a few streams, so copies, front end and ICP of different sub-chunks overlap
@@ -122,7 +122,22 @@ constexpr int CUBOID_MAX_SAC_ITER = 1000000;
 
 float limit_hi(double mx) { float f = (float)mx; if ((double)f > mx) f = nextafterf(f, -INFINITY); return f; }
 float limit_lo(double mn) { float f = (float)mn; if ((double)f < mn) f = nextafterf(f, INFINITY); return f; }
-int fe_smem(int nt) { return nt == 512 ? fe_dyn_smem<512>() : fe_dyn_smem<1024>(); }
+int fe_smem_mode(int nt, bool masks, bool hash, bool runs);
+int fe_smem(int nt) {   // the most any mode of a launch needs
+    int m = 0;
+    for (int k = 0; k < 8; ++k) m = std::max(m, fe_smem_mode(nt, (k & 1) != 0, (k & 2) != 0, (k & 4) != 0));
+    return m;
+}
+int fe_smem_mode(int nt, bool masks, bool hash, bool runs) {
+    return nt == 256 ? fe_dyn_smem<256>(masks, hash, runs) : (nt == 512 ? fe_dyn_smem<512>(masks, hash, runs) : fe_dyn_smem<1024>(masks, hash, runs));
+}
+// k_frontend instance for (input kind, CTA size, rgb carried)
+const void* fe_fn(int src, int nt, bool rgb, bool runs = false) {
+    if (src == 0 && runs) return nt == 256 ? (const void*)k_frontend<0, 256, false, true> : (nt == 512 ? (const void*)k_frontend<0, 512, false, true> : (const void*)k_frontend<0, 1024, false, true>);
+    if (nt == 256) return src == 0 ? (const void*)k_frontend<0, 256, false> : (rgb ? (const void*)k_frontend<1, 256, true> : (const void*)k_frontend<1, 256, false>);
+    if (nt == 512) return src == 0 ? (const void*)k_frontend<0, 512, false> : (rgb ? (const void*)k_frontend<1, 512, true> : (const void*)k_frontend<1, 512, false>);
+    return src == 0 ? (const void*)k_frontend<0, 1024, false> : (rgb ? (const void*)k_frontend<1, 1024, true> : (const void*)k_frontend<1, 1024, false>);
+}
 // ceil(2^32 / w) if __umulhi(i, magic) == i / w for every i < n (true when n * w <= 2^32), else 0 (plain division)
 unsigned int row_magic(int w, int n) {
     if (w < 2 || (unsigned long long)n * (unsigned long long)w > (1ull << 32)) return 0u;
@@ -296,7 +311,7 @@ int run_chunk(cuboid_handle* h, const ChunkIn& in, int nf, cuboid_frame_result* 
         int fe_c = h->fe_cluster;
         if (fe_c == 1 && h->fe_cluster_small > 1 && (long long)nf * h->fe_cluster_small <= h->sms) fe_c = h->fe_cluster_small;
         fa.keys_stride = h->fe_stride; fa.hash = (h->fe_hash && h->fe_threads == 1024 && fe_c == 1) ? h->fe_hash : 0;
-        fa.st_on = 0;
+        fa.st_on = 0; fa.runs = 0;
         if (!in.blob && fe_c == 1 && h->fe_onepass && in.w > 0 && in.hgt > 0) {
             // static bounds of floor(coordinate / leaf) over everything the pass-through filters can let through (float products and
             // floors are monotone, so the device's values stay inside): x and z from the limits, y = z * yr[v] from the corners
@@ -320,6 +335,7 @@ int run_chunk(cuboid_handle* h, const ChunkIn& in, int nf, cuboid_frame_result* 
             }
             if (ok && bits[0] + bits[1] + bits[2] <= 32 && dims <= 2147483647LL) {
                 fa.st_on = 1; fa.st_b0 = bits[0]; fa.st_b1 = bits[0] + bits[1]; fa.st_bits = bits[0] + bits[1] + bits[2];
+                fa.runs = (h->fe_runs && h->P < (1 << 27)) ? 1 : 0;   // a run record keeps its first point in 27 bits
             }
         }
         cudaLaunchConfig_t cfg{};
@@ -328,17 +344,18 @@ int run_chunk(cuboid_handle* h, const ChunkIn& in, int nf, cuboid_frame_result* 
         at[0].val.clusterDim.x = fe_c; at[0].val.clusterDim.y = 1; at[0].val.clusterDim.z = 1;
         cfg.gridDim = dim3((unsigned int)(std::min(h->fe_slots, nf) * fe_c));
         cfg.blockDim = dim3((unsigned int)h->fe_threads);
-        cfg.dynamicSmemBytes = (size_t)fe_smem(h->fe_threads);
+        {   // the kernel's own test for its one-pass mode: then A1 and its masks do not run
+            const bool onepass = fa.st_on && !fa.kpp && !fa.hashes && !fa.hash;
+            fa.arena = fe_smem_mode(h->fe_threads, !onepass, fa.hash != 0, onepass && fa.runs);
+            const char* ea = std::getenv("CUBOID_FE_ARENA_KB");   // developer: force a bigger arena (what the L1 carve-out costs)
+            if (ea) fa.arena = std::min(std::max(fa.arena, atoi(ea) * 1024), fe_smem(h->fe_threads));
+        }
+        cfg.dynamicSmemBytes = (size_t)fa.arena;
         cfg.stream = st;
         cfg.attrs = at; cfg.numAttrs = 1;
-        if (h->fe_threads == 512) {
-            if (in.blob && fa.rgb) CK(h, cudaLaunchKernelEx(&cfg, k_frontend<1, 512, true>, fa));
-            else if (in.blob) CK(h, cudaLaunchKernelEx(&cfg, k_frontend<1, 512, false>, fa));
-            else CK(h, cudaLaunchKernelEx(&cfg, k_frontend<0, 512, false>, fa));
-        } else {
-            if (in.blob && fa.rgb) CK(h, cudaLaunchKernelEx(&cfg, k_frontend<1, 1024, true>, fa));
-            else if (in.blob) CK(h, cudaLaunchKernelEx(&cfg, k_frontend<1, 1024, false>, fa));
-            else CK(h, cudaLaunchKernelEx(&cfg, k_frontend<0, 1024, false>, fa));
+        {
+            void* kargs[1] = {(void*)&fa};
+            CK(h, cudaLaunchKernelExC(&cfg, fe_fn(in.blob ? 1 : 0, h->fe_threads, in.blob && fa.rgb, fa.runs != 0), kargs));
         }
         ++h->launches;
         CK(h, cudaGetLastError());
@@ -677,18 +694,19 @@ static int create_impl(cuboid_handle** out, const cuboid_params* p, int device, 
         const char* ef = std::getenv("CUBOID_FRONTEND"); if (ef) h->frontend = atoi(ef) ? 1 : 0;
         const char* ec = std::getenv("CUBOID_FE_CLUSTER"); if (ec) h->fe_cluster = std::max(1, std::min(16, atoi(ec)));
         const char* eo1 = std::getenv("CUBOID_FE_ONEPASS"); if (eo1) h->fe_onepass = atoi(eo1) ? 1 : 0;
+        const char* eru = std::getenv("CUBOID_FE_RUNS"); if (eru) h->fe_runs = atoi(eru) ? 1 : 0;
         const char* eh = std::getenv("CUBOID_FE_HASH"); if (eh) h->fe_hash = std::max(0, std::min(2, atoi(eh)));   // 2: developer, mark the path taken in status
         // Opt-in (measured slower than the radix path on B200: 7.1 ms against 4.75 ms per 1024 VGA frames): the
         // voxel-hash path (one 1024-thread CTA per SM); frames with more voxels than its table holds fall back per frame to the radix
         // path inside the same kernel. Bigger clouds (720p: ~600k voxels) always keep two 512-thread CTAs per SM.
         if (h->fe_hash && h->P <= 400000 && h->fe_cluster == 1) h->fe_threads = 1024; else h->fe_hash = 0;
-        const char* et = std::getenv("CUBOID_FE_THREADS"); if (et) { h->fe_threads = atoi(et) == 1024 ? 1024 : 512; if (h->fe_threads != 1024) h->fe_hash = 0; }
-        const void* fns[6] = {(const void*)k_frontend<0, 512, false>, (const void*)k_frontend<1, 512, false>, (const void*)k_frontend<0, 1024, false>,
-                              (const void*)k_frontend<1, 1024, false>, (const void*)k_frontend<1, 512, true>, (const void*)k_frontend<1, 1024, true>};
-        for (int k = 0; k < 6; ++k) {
-            if (cudaFuncSetAttribute(fns[k], cudaFuncAttributeMaxDynamicSharedMemorySize, fe_smem((k < 2 || k == 4) ? 512 : 1024)) != cudaSuccess) return fail(CUBOID_E_CUDA);
-            if (h->fe_cluster > 8) cudaFuncSetAttribute(fns[k], cudaFuncAttributeNonPortableClusterSizeAllowed, 1);
-        }
+        const char* et = std::getenv("CUBOID_FE_THREADS"); if (et) { h->fe_threads = atoi(et) == 1024 ? 1024 : (atoi(et) == 256 ? 256 : 512); if (h->fe_threads != 1024) h->fe_hash = 0; }
+        for (int nt : {256, 512, 1024})
+            for (int v = 0; v < 4; ++v) {
+                const void* fn = fe_fn((v == 1 || v == 2) ? 1 : 0, nt, v == 2, v == 3);
+                if (cudaFuncSetAttribute(fn, cudaFuncAttributeMaxDynamicSharedMemorySize, fe_smem(nt)) != cudaSuccess) return fail(CUBOID_E_CUDA);
+                if (h->fe_cluster > 8) cudaFuncSetAttribute(fn, cudaFuncAttributeNonPortableClusterSizeAllowed, 1);
+            }
         int sms = 0;
         cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, device);
         for (; h->fe_cluster >= 1; h->fe_cluster >>= 1) {
@@ -700,7 +718,7 @@ static int create_impl(cuboid_handle** out, const cuboid_params* p, int device, 
             cfg.dynamicSmemBytes = (size_t)fe_smem(h->fe_threads);
             cfg.attrs = at; cfg.numAttrs = 1;
             int ncl = 0;
-            if (cudaOccupancyMaxActiveClusters(&ncl, fns[h->fe_threads == 512 ? 0 : 2], &cfg) == cudaSuccess && ncl > 0) { h->fe_slots = ncl; break; }
+            if (cudaOccupancyMaxActiveClusters(&ncl, fe_fn(0, h->fe_threads, false), &cfg) == cudaSuccess && ncl > 0) { h->fe_slots = ncl; break; }
             cudaGetLastError();
             if (h->fe_cluster == 1) break;
         }
@@ -717,7 +735,7 @@ static int create_impl(cuboid_handle** out, const cuboid_params* p, int device, 
                 cfg.dynamicSmemBytes = (size_t)fe_smem(h->fe_threads);
                 cfg.attrs = at; cfg.numAttrs = 1;
                 int ncl = 0;
-                if (cudaOccupancyMaxActiveClusters(&ncl, fns[h->fe_threads == 512 ? 0 : 2], &cfg) == cudaSuccess && ncl > 0) { h->fe_cluster_small = c; break; }
+                if (cudaOccupancyMaxActiveClusters(&ncl, fe_fn(0, h->fe_threads, false), &cfg) == cudaSuccess && ncl > 0) { h->fe_cluster_small = c; break; }
                 cudaGetLastError();
             }
         }

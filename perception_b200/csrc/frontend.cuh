@@ -34,6 +34,10 @@ struct FrontArgs {
     // of PCL's idx = i + j*dx + k*dx*dy for any actual min / max, so the first pass over the inputs (survivor count, min / max: A1)
     // is not needed before the keys can be written: min / max are reduced during the one pass and the geometry is published after it.
     int st_on, st_min[3], st_b0, st_b1, st_bits;
+    // Run records (one-pass mode only): consecutive survivors of one warp step that fall into the same voxel become ONE sort record
+    // (key << 32 | first point << 5 | length - 1). A raster run stays contiguous in the stable order, so the radix passes move ~2x fewer
+    // records and the centroid pass expands them again in order: same sums, bit for bit.
+    int runs;
     int hash;                    // 1: try the voxel-hash path first (needs NT = 1024, cluster size 1), fall back to the radix path per frame
     int* kpp;                    // [F][P] voxel idx per point (parity tap) or NULL
     float4* vox;                 // [F][P]
@@ -43,12 +47,21 @@ struct FrontArgs {
     int hashes;                  // 1: accumulate points_hash / voxel_key_hash / voxel_hash (parity taps); 0: leave them 0
     int P;                       // per-frame stride of pts / vox / kpp / vcount / keys
     int n_frames;
+    int arena;                   // dynamic shared memory of this launch (bytes)
 };
 
 constexpr int FE_ITEMS = 8;      // inputs / sort records per thread and tile
 constexpr int FE_RITEMS = 4;     // sorted records per thread and reduce tile
 constexpr int FE_LONGRUN = 96;   // voxels with more points than this are summed by a whole warp (lane-parallel loads)
 constexpr int FE_MAXDEF = 64;    // >= 512*4/96 + 1 and >= 1024*4/96 + 1
+#ifndef CUBOID_FE_RREC
+#define CUBOID_FE_RREC 4
+#endif
+#ifndef CUBOID_FE_RCAPT
+#define CUBOID_FE_RCAPT 8
+#endif
+constexpr int FE_RREC = CUBOID_FE_RREC;     // run-record path: sorted records staged per thread and reduce tile
+constexpr int FE_RCAPT = CUBOID_FE_RCAPT;   // ... and the points they may expand to, per thread
 constexpr int FE_LOOK = 128;     // sorted records staged past a reduce tile so that the tile's last voxel can finish in shared memory
 
 struct FeXchg {          // what a CTA publishes to its cluster peers
@@ -66,7 +79,7 @@ struct FeFrame {         // cluster-wide facts of the current frame, replicated 
 //   A1/A2   u16 tile-local input index of every survivor of the tile            NT*8*2  bytes
 //           + the tile's depth values (u16), + the keep masks A1 found, so A2       NT*8*2 + FE_MASK_BYTES
 //             does not unproject and filter again
-//   B       per-warp digit counters [NT/32][256] u32 + two prefetched key tiles   NT*32 + 2*NT*8*8 bytes
+//   B       per-warp digit counters [NT/32][256] u32 + one prefetched key tile    NT*32 + NT*8*8 bytes
 //   C2      key,x,y,z,w of the staged sorted records (+ look-ahead) + u16 heads (NT*4+128)*20 + NT*4*2 bytes
 constexpr int FE_MASK_BYTES = 40960;   // keep masks of one input slice (1 byte per 8 inputs): a VGA frame on one CTA needs 38 400
 constexpr int fe_max(int a, int b) { return a > b ? a : b; }
@@ -81,10 +94,14 @@ constexpr int FEH_RCAP = 4096;        // points staged per reduce chunk
 constexpr int FEH_LONG = 64;          // runs longer than this are sorted and summed by a whole warp
 constexpr int FEH_MAXRUN = 2048;      // longest run (points of one voxel) the path handles; longer: radix path
 constexpr int FEH_SMEM = FEH_CAP * 4 + FEH_CAP * 2 + 1024 * FE_ITEMS * 2;   // table + counts + selection tile = 212 992 B
+// What a launch needs depends on its mode (the carve-out left to L1 matters: 4.7 -> 5.2 ms per 1024 VGA frames when two 97 KB CTAs
+// pushed it from 196 to 228 KB): keep masks only when A1 runs, the hash table only on the hash path, run staging only with run records.
 template <int NT>
-constexpr int fe_dyn_smem() {   // A: selection + depth tile + masks; B: digit counters + two prefetched key tiles; C2: staging + heads
-    return fe_max(fe_max(fe_max(NT * 32 + FE_MASK_BYTES, NT * 32 + 2 * NT * FE_ITEMS * 8), (NT * FE_RITEMS + FE_LOOK) * 20 + NT * FE_RITEMS * 2),
-                  NT == 1024 ? FEH_SMEM : 0);
+constexpr int fe_dyn_smem(bool masks = true, bool hash = true, bool runs = true) {
+    // A: selection + depth tile (+ masks | + run staging); B: digit counters + one prefetched key tile; C2: staging + heads
+    return fe_max(fe_max(fe_max(NT * 32 + (masks ? FE_MASK_BYTES : (runs ? NT * FE_ITEMS * 8 + 2 * NT : 0)), NT * 32 + NT * FE_ITEMS * 8),
+                         runs && !masks ? NT * FE_RREC * 14 + 4 + NT * FE_RCAPT * 12 : (NT * FE_RITEMS + FE_LOOK) * 20 + NT * FE_RITEMS * 2),
+                  (hash && NT == 1024) ? FEH_SMEM : 0);
 }
 // global scratch of one slot on the hash path (inside FrontArgs::keys): two record buffers, voxel start offsets, slot id per
 // point, point indices grouped by voxel
@@ -601,8 +618,9 @@ __device__ __forceinline__ bool fe_hash_frame(const FrontArgs& a, int f, int n_i
 
 // RGB (PointCloud2 inputs with a packed rgb field, FrontArgs::rgb) is a compile-time variant: the colour bookkeeping costs the
 // depth-frame path 4 % when it is a run-time test.
-template <int SRC, int NT, bool RGB>
-__global__ void __launch_bounds__(NT, 2048 / NT >= 2 ? (NT <= 512 ? 2 : 1) : 1) k_frontend(const FrontArgs a) {
+// RUNS (run records, depth input only) likewise: compiled into the common kernel it costs the default path registers (spills).
+template <int SRC, int NT, bool RGB, bool RUNS = false>
+__global__ void __launch_bounds__(NT, NT <= 256 ? 4 : (NT <= 512 ? 2 : 1)) k_frontend(const FrontArgs a) {
     constexpr int NW = NT / 32;
     constexpr int TILE = NT * FE_ITEMS;
     constexpr int RTILE = NT * FE_RITEMS;
@@ -636,7 +654,9 @@ __global__ void __launch_bounds__(NT, 2048 / NT >= 2 ? (NT <= 512 ? 2 : 1) : 1) 
         unsigned char* s_mask = fe_dyn + NT * 32;
         const bool hash_try = NT == 1024 && C == 1 && a.hash != 0;    // the hash path recomputes the masks (its table takes their room)
         const bool onepass = SRC == 0 && C == 1 && a.st_on != 0 && !a.kpp && !a.hashes && !hash_try;   // kernel-uniform
-        const bool use_mask = !hash_try && !onepass && ((slice + TILE - 1) / TILE) * NT <= FE_MASK_BYTES;
+        const bool use_mask = !hash_try && !onepass && ((slice + TILE - 1) / TILE) * NT <= FE_MASK_BYTES && NT * 32 + FE_MASK_BYTES <= a.arena;
+        const bool runs = RUNS && onepass && a.runs != 0;
+        int NR = 0;                      // sort records of the frame: its points, or its runs
 
         // ---- A1: survivors and min/max of this CTA's input slice ----
         if (!onepass) {
@@ -754,6 +774,9 @@ __global__ void __launch_bounds__(NT, 2048 / NT >= 2 ? (NT <= 512 ? 2 : 1) : 1) 
             float4* out = p.pts + (size_t)f * p.Pout;
             int* kpp = a.kpp ? a.kpp + (size_t)f * a.P : nullptr;
             int run = onepass ? 0 : s_f.base;
+            int rrun = 0;                                                                                     // run records written so far
+            unsigned long long* s_run = reinterpret_cast<unsigned long long*>(fe_dyn + NT * 32);            // [TILE / 32][32] records of a tile, per warp step
+            int* s_rc = reinterpret_cast<int*>(fe_dyn + NT * 32 + TILE * 8);                                  // [2][TILE / 32] their counts, then offsets
             unsigned long long hh[2] = {0ull, 0ull};
             float omn[3] = {3.402823466e38f, 3.402823466e38f, 3.402823466e38f};      // one-pass mode: min / max of the survivors
             float omx[3] = {-3.402823466e38f, -3.402823466e38f, -3.402823466e38f};
@@ -808,18 +831,51 @@ __global__ void __launch_bounds__(NT, 2048 / NT >= 2 ? (NT <= 512 ? 2 : 1) : 1) 
                             idx = voxel_index(g, pt.x, pt.y, pt.z);
                             sk = g.overflow_mode ? ((unsigned int)idx ^ 0x80000000u) : (unsigned int)idx;
                         }
-                        __stcg(bufA + pos, ((unsigned long long)sk << 32) | (unsigned int)pos);
+                        if (!runs) __stcg(bufA + pos, ((unsigned long long)sk << 32) | (unsigned int)pos);
                         if (kpp) kpp[pos] = idx;
                         if (a.hashes) {
                             hh[0] += hash_point((unsigned int)pos, pt.x, pt.y, pt.z);
                             hh[1] += hash_index((unsigned int)pos, idx);
                         }
                     }
-                    if (C == 1 && valid) {   // one CTA owns the frame: every pass's digit histogram is order-independent, count it here
+                    bool count = C == 1 && valid;   // one CTA owns the frame: every pass's digit histogram is order-independent, count it here
+                    if (runs) {   // heads of the runs of equal keys among this warp step's 32 consecutive survivors -> the step's slots of s_run, in order
+                        const unsigned int prev = __shfl_up_sync(FULL_MASK, sk, 1);
+                        const bool head = valid && (lane == 0 || sk != prev);
+                        const unsigned int hb = __ballot_sync(FULL_MASK, head), vb = __ballot_sync(FULL_MASK, valid);
+                        const int wb = (qb / NT) * NW + wid;
+                        if (head) {
+                            const unsigned int above = hb & ~((2u << lane) - 1u);
+                            const int len = (above ? (__ffs(above) - 1) : __popc(vb)) - lane;   // the valid lanes are a prefix
+                            s_run[wb * 32 + __popc(hb & ((1u << lane) - 1u))] =
+                                ((unsigned long long)sk << 32) | ((unsigned long long)(unsigned int)(run + q) << 5) | (unsigned int)(len - 1);
+                        }
+                        if (lane == 0) s_rc[wb] = __popc(hb);
+                        count = false;   // digit histograms: per record, in the dense copy below
+                    }
+                    if (count) {
 #pragma unroll
                         for (int ps = 0; ps < 4; ++ps)
                             if (ps < npass) atomicAdd(&s_histA[ps][(sk >> (8 * ps)) & 255u], 1u);
                     }
+                }
+                if (runs) {   // the tile's run records, dense and in order, to the sort buffer
+                    __syncthreads();
+                    const int nwb = ((total + NT - 1) / NT) * NW;
+                    int tot_r;
+                    const int ex = block_excl_scan<NT>(tid < nwb ? s_rc[tid] : 0, s_w, &tot_r);
+                    if (tid < nwb) s_rc[TILE / 32 + tid] = ex;
+                    __syncthreads();
+                    for (int wb = wid; wb < nwb; wb += NW)
+                        if (lane < s_rc[wb]) {
+                            const unsigned long long rec = s_run[wb * 32 + lane];
+                            __stcg(bufA + rrun + s_rc[TILE / 32 + wb] + lane, rec);
+                            const unsigned int rk = (unsigned int)(rec >> 32);
+#pragma unroll
+                            for (int ps = 0; ps < 4; ++ps)
+                                if (ps < npass) atomicAdd(&s_histA[ps][(rk >> (8 * ps)) & 255u], 1u);
+                        }
+                    rrun += tot_r;
                 }
                 run += total;
                 __syncthreads();
@@ -829,6 +885,7 @@ __global__ void __launch_bounds__(NT, 2048 / NT >= 2 ? (NT <= 512 ? 2 : 1) : 1) 
                 if (hh[0]) atomic_add_u64(&p.res[f].points_hash, hh[0]);
                 if (hh[1]) atomic_add_u64(&p.res[f].voxel_key_hash, hh[1]);
             }
+            NR = runs ? rrun : 0;
             if (onepass) {   // what A1 and the frame set-up would have published: survivor count, min / max -> min_b / div_b
                 N = run;
 #pragma unroll
@@ -873,9 +930,10 @@ __global__ void __launch_bounds__(NT, 2048 / NT >= 2 ? (NT <= 512 ? 2 : 1) : 1) 
         cluster.sync();
 
         // ---- B: stable LSD radix sort of the frame's N records, 8-bit digits, significant key bits only ----
-        int per = (N + C - 1) / C;
+        if (!runs) NR = N;
+        int per = (NR + C - 1) / C;
         per = (per + 255) & ~255;       // whole warp runs (8 items x 32 lanes): tiles of a range stay warp-aligned
-        const int q0 = min(N, r * per), q1 = min(N, r * per + per);
+        const int q0 = min(NR, r * per), q1 = min(NR, r * per + per);
         unsigned int (*s_cnt)[256] = reinterpret_cast<unsigned int (*)[256]>(fe_dyn);
         for (int pass = 0; pass < npass; ++pass) {
             const unsigned long long* src = (pass & 1) ? bufB : bufA;
@@ -924,11 +982,10 @@ __global__ void __launch_bounds__(NT, 2048 / NT >= 2 ? (NT <= 512 ? 2 : 1) : 1) 
                 fe_cp_async_commit();
             };
             prefetch(q0, 0);
-            int buf = 0;
-            for (int t0 = q0; t0 < q1; t0 += TILE, buf ^= 1) {
+            constexpr int buf = 0;   // ONE staging buffer: a warp has its tile in registers before it requests the next one
+            for (int t0 = q0; t0 < q1; t0 += TILE) {
                 for (int d = lane; d < 256; d += 32) s_cnt[wid][d] = 0;
-                prefetch(t0 + TILE, buf ^ 1);
-                fe_cp_async_wait<1>();
+                fe_cp_async_wait<0>();
                 __syncwarp();
                 // warp w owns the contiguous run [t0 + w*256, +256): (warp, item, lane) order == ascending input order
                 unsigned long long key[FE_ITEMS];
@@ -940,6 +997,8 @@ __global__ void __launch_bounds__(NT, 2048 / NT >= 2 ? (NT <= 512 ? 2 : 1) : 1) 
                     if (full) key[k] = s_pre[buf * TILE + wid * (32 * FE_ITEMS) + k * 32 + lane];
                     else key[k] = i < q1 ? __ldcg(src + i) : ~0ull;
                 }
+                __syncwarp();
+                prefetch(t0 + TILE, 0);   // in flight while this tile is ranked and scattered
 #pragma unroll
                 for (int k = 0; k < FE_ITEMS; ++k) {
                     const int i = t0 + wid * (32 * FE_ITEMS) + k * 32 + lane;
@@ -1006,7 +1065,156 @@ __global__ void __launch_bounds__(NT, 2048 / NT >= 2 ? (NT <= 512 ? 2 : 1) : 1) 
         // ---- C2: sequential float centroid of every voxel that starts in this range. A tile of sorted records (key and
         //      gathered point) is staged with parallel loads; heads are compacted; then ONE THREAD PER VOXEL sums its run
         //      out of shared memory in sorted (= ascending point index) order and the centroid stores are coalesced ----
-        {
+        if (runs) {
+            // Run records: a tile stages up to RS sorted records (key, first point, length), expands them IN ORDER into at most FE_RCAP
+            // points in shared memory (the points of a voxel are then contiguous, as in the point-record path below), and one thread per
+            // voxel sums its points. Tiles advance by whole voxels; the records past n_here are look-ahead for the tile's last voxels.
+            constexpr int RS = NT * FE_RREC;
+            constexpr int FE_RCAP = NT * FE_RCAPT;
+            unsigned int* s_key = reinterpret_cast<unsigned int*>(fe_dyn);
+            unsigned int* s_meta = s_key + RS;                          // first point << 5 | length - 1
+            unsigned int* s_off = s_meta + RS;                          // [RS + 1] first staged point of a record
+            float* s_px = reinterpret_cast<float*>(s_off + RS + 1);
+            float* s_py = s_px + FE_RCAP;
+            float* s_pz = s_py + FE_RCAP;
+            unsigned short* s_head = reinterpret_cast<unsigned short*>(s_pz + FE_RCAP);   // [RS]
+            const float4* pts = p.pts + (size_t)f * p.Pout;
+            float4* vox = a.vox + (size_t)f * a.P;
+            int vrun = 0;
+            for (int t0 = 0; t0 < NR;) {
+                const int n_avail = min(RS, NR - t0);
+                for (int l = tid; l < n_avail; l += NT) {
+                    const unsigned long long rec = __ldcg(keys + t0 + l);
+                    s_key[l] = (unsigned int)(rec >> 32);
+                    s_meta[l] = (unsigned int)rec;
+                }
+                const unsigned int prev_key = t0 > 0 ? (unsigned int)(__ldcg(keys + t0 - 1) >> 32) : 0u;
+                if (tid == 0) { s_misc[0] = n_avail; s_misc[1] = 0; }
+                __syncthreads();
+                // thread t owns the records [t * FE_RREC, + FE_RREC): point offsets and voxel heads in one packed scan
+                const int first = tid * FE_RREC;
+                unsigned int meta[FE_RREC];
+                unsigned int heads = 0;
+                int npt = 0;
+#pragma unroll
+                for (int k = 0; k < FE_RREC; ++k) {
+                    const int l = first + k;
+                    meta[k] = 0u;
+                    if (l < n_avail) {
+                        meta[k] = s_meta[l];
+                        npt += (int)(meta[k] & 31u) + 1;
+                        if (t0 + l == 0 || s_key[l] != (l > 0 ? s_key[l - 1] : prev_key)) heads |= 1u << k;
+                    }
+                }
+                int total;
+                const int ex = block_excl_scan<NT>(npt | (__popc(heads) << 18), s_w, &total);
+                int off = ex & 0x3ffff, hp = ex >> 18;
+                const int nheads = total >> 18;
+#pragma unroll
+                for (int k = 0; k < FE_RREC; ++k) {
+                    const int l = first + k;
+                    if (l < n_avail) {
+                        const int len = (int)(meta[k] & 31u) + 1;
+                        s_off[l] = (unsigned int)off;
+                        if (heads & (1u << k)) s_head[hp++] = (unsigned short)l;
+                        if (off <= FE_RCAP && off + len > FE_RCAP) s_misc[0] = l;   // the first record that does not fit: staging stops here
+                        off += len;
+                        if (l == n_avail - 1) s_off[n_avail] = (unsigned int)off;
+                    }
+                }
+                __syncthreads();
+                const int n_stage = s_misc[0];                                      // records whose points are staged
+                const bool last = t0 + n_stage == NR;
+                const int n_here = last ? n_stage : max(n_stage - FE_LOOK, min(n_stage, 32));
+                // expansion, in record order: the points of a voxel become contiguous in shared memory
+#pragma unroll
+                for (int k = 0; k < FE_RREC; ++k)
+                    if (first + k < n_stage) {
+                        const int len = (int)(meta[k] & 31u) + 1, o = (int)s_off[first + k];
+                        const float4* src = pts + (meta[k] >> 5);
+                        for (int q = 0; q < len; ++q) {
+                            const float4 pt = src[q];
+                            s_px[o + q] = pt.x; s_py[o + q] = pt.y; s_pz[o + q] = pt.z;
+                        }
+                    }
+                __syncthreads();
+                for (int v = tid; v < nheads; v += NT) {
+                    const int lp = s_head[v];
+                    if (lp >= n_here) continue;                                     // look-ahead: belongs to the next tile
+                    const int end = (v + 1 < nheads) ? min((int)s_head[v + 1], n_stage) : n_stage;
+                    const bool open = !last && (v + 1 == nheads || (int)s_head[v + 1] > n_stage);   // may continue past the staged records
+                    const int pa = (int)s_off[lp], pb = (int)s_off[end];
+                    const int pos = vrun + v;
+                    if (open || pb - pa > FE_LONGRUN) {
+                        const int d = atomicAdd(&s_ndef, 1);
+                        s_def_lp[d] = lp | (open ? 0x10000 : 0) | (end << 17); s_def_pos[d] = pos;
+                        continue;
+                    }
+                    float sx = s_px[pa], sy = s_py[pa], sz = s_pz[pa];
+                    for (int q = pa + 1; q < pb; ++q) { sx += s_px[q]; sy += s_py[q]; sz += s_pz[q]; }
+                    const float cnt = (float)(pb - pa);
+                    vox[pos] = make_float4(sx / cnt, sy / cnt, sz / cnt, 1.0f);
+                }
+                // voxels of this tile = heads in front of n_here
+                for (int v = tid; v < nheads; v += NT)
+                    if ((int)s_head[v] < n_here && (v + 1 == nheads || (int)s_head[v + 1] >= n_here)) s_misc[1] = v + 1;
+                __syncthreads();
+                for (int d = wid; d < s_ndef; d += NW) {   // long or open voxels: a whole warp, lane-parallel loads, in-order sums
+                    const int lp = s_def_lp[d] & 0xffff, end = s_def_lp[d] >> 17;
+                    const bool open = (s_def_lp[d] & 0x10000) != 0;
+                    const unsigned int mykey = s_key[lp];
+                    const int pa = (int)s_off[lp], pb = (int)s_off[end];
+                    FeRun acc;
+                    acc.sx = s_px[pa]; acc.sy = s_py[pa]; acc.sz = s_pz[pa]; acc.cnt = 1; acc.sr = acc.sg = acc.sb = 0u;
+                    for (int l = pa + 1; l < pb; l += 32) {
+                        const int i = l + lane;
+                        const bool m = i < pb;
+                        fe_run_step<false>(acc, m, m ? s_px[i] : 0.f, m ? s_py[i] : 0.f, m ? s_pz[i] : 0.f);
+                    }
+                    bool more = open;
+                    for (int q = t0 + n_stage; more && q < NR; q += 32) {   // the rest of the voxel from the sorted records, 32 records per round
+                        const int i = q + lane;
+                        const unsigned long long rec = i < NR ? __ldcg(keys + i) : 0ull;
+                        const bool mine = i < NR && (unsigned int)(rec >> 32) == mykey;
+                        const unsigned int mb = __ballot_sync(FULL_MASK, !mine);
+                        const int nrec = mb ? (__ffs(mb) - 1) : 32;                 // leading records of this voxel
+                        more = nrec == 32;
+                        const int len = lane < nrec ? (int)((unsigned int)rec & 31u) + 1 : 0;
+                        const int inc = warp_incl_scan(len, lane);
+                        const int tot = __shfl_sync(FULL_MASK, inc, 31);
+                        const int exl = inc - len;
+                        const unsigned int pfirst = ((unsigned int)rec >> 5);
+                        for (int c0 = 0; c0 < tot; c0 += 32) {                      // 32 points per step: point c0 + lane belongs to the record whose range holds it
+                            const int want = c0 + lane;
+                            int lo = 0;                                             // last record with exl <= want (binary search over the lanes)
+#pragma unroll
+                            for (int sft = 16; sft >= 1; sft >>= 1) {
+                                const int cand = lo + sft;
+                                const int ce = __shfl_sync(FULL_MASK, exl, cand & 31);
+                                const int cl = __shfl_sync(FULL_MASK, len, cand & 31);
+                                if (cand < 32 && cl > 0 && ce <= want) lo = cand;
+                            }
+                            const int re = __shfl_sync(FULL_MASK, exl, lo);
+                            const unsigned int rp = __shfl_sync(FULL_MASK, pfirst, lo);
+                            const bool m = want < tot;
+                            float4 pt = make_float4(0.f, 0.f, 0.f, 0.f);
+                            if (m) pt = pts[rp + (unsigned int)(want - re)];
+                            fe_run_step<false>(acc, m, pt.x, pt.y, pt.z);
+                        }
+                    }
+                    if (lane == 0) {
+                        const float c = (float)acc.cnt;
+                        vox[s_def_pos[d]] = make_float4(acc.sx / c, acc.sy / c, acc.sz / c, 1.0f);
+                    }
+                }
+                __syncthreads();
+                vrun += s_misc[1];
+                t0 += n_here;
+                __syncthreads();
+                if (tid == 0) s_ndef = 0;
+            }
+            if (tid == 0) p.res[f].n_voxels = vrun;
+        } else {
             unsigned int* s_key = reinterpret_cast<unsigned int*>(fe_dyn);
             constexpr int RSTAGE = RTILE + FE_LOOK;
             float* s_px = reinterpret_cast<float*>(fe_dyn) + RSTAGE;

@@ -456,7 +456,7 @@ def test_full_size_batch_properties(cc, tmpl30, params):
     assert all(r.n_clusters == 1 and r.cluster[0].converged for r in res)
 
 
-@pytest.mark.parametrize("cluster,threads", [(1, 512), (2, 512), (4, 512), (8, 512), (1, 1024), (4, 1024), (8, 1024)])
+@pytest.mark.parametrize("cluster,threads", [(1, 512), (2, 512), (4, 512), (8, 512), (1, 1024), (4, 1024), (8, 1024), (1, 256), (8, 256)])
 def test_fused_frontend_equals_unfused_kernels(tmpl30, params, cluster, threads, monkeypatch):
     """Stages 1a+1b as one cluster-per-frame kernel (frontend.cuh) against the unfused kernels: every result byte and
     every fetched intermediate array equal, for each cluster size, on normal, empty and degenerate frames."""
@@ -572,7 +572,7 @@ def test_icp_on_the_reference_real_scan_returns_the_published_pose(golden, param
 
 
 @pytest.mark.parametrize("knob,values", [("CUBOID_ICP_NSUB", ("1", "2", "4")), ("CUBOID_ICP_SLICE", ("1", "8", "5000")),
-                                         ("CUBOID_ICP_OUTWARD", ("0", "1")), ("CUBOID_ICP_QUEUED", ("0", "1")), ("CUBOID_ICP_TABLE", ("0", "1")), ("CUBOID_FE_HASH", ("0", "1")), ("CUBOID_FE_ONEPASS", ("0", "1")), ("CUBOID_ICP_LOCAL", ("0", "1")), ("CUBOID_ICP_SEEDGRID", ("0", "1")), ("CUBOID_FE_CLUSTER_SMALL", ("1", "8")), ("CUBOID_SAC_WIDE", ("0", "1")), ("CUBOID_NNT_H_MM", ("0.7", "2.5")),
+                                         ("CUBOID_ICP_OUTWARD", ("0", "1")), ("CUBOID_ICP_QUEUED", ("0", "1")), ("CUBOID_ICP_TABLE", ("0", "1")), ("CUBOID_FE_HASH", ("0", "1")), ("CUBOID_FE_ONEPASS", ("0", "1")), ("CUBOID_FE_RUNS", ("0", "1")), ("CUBOID_ICP_LOCAL", ("0", "1")), ("CUBOID_ICP_SEEDGRID", ("0", "1")), ("CUBOID_FE_CLUSTER_SMALL", ("1", "8")), ("CUBOID_SAC_WIDE", ("0", "1")), ("CUBOID_NNT_H_MM", ("0.7", "2.5")),
                                          ("CUBOID_PIPELINE", ("0", "1"))])
 def test_execution_knobs_do_not_change_results(tmpl30, params, knob, values, monkeypatch):
     """How the work is scheduled must never show in the results: sub-workers per CTA, iterations per time slice, outward search
@@ -687,27 +687,41 @@ def test_rgb_field_is_carried_through_voxelgrid_and_extraction(frame0, tmpl30, p
 
 def test_one_pass_front_end_equals_two_pass(tmpl30, params, monkeypatch):
     """Depth input without parity taps (what bench.py times): the front end writes its sort keys relative to STATIC bounds (pass-through
-    limits, intrinsics) in ONE pass over the pixels instead of reducing min / max first. Every result byte and every fetched array must
-    equal the two-pass path's, on normal, empty, constant and plane-only frames, and the tapped run must agree on all it shares."""
-    depth = np.concatenate([synth.depth_batch("bench", [50, 51, 52, 53]), synth.depth_batch("plane_var", [7, 8]), np.zeros((3, 480, 640), np.uint16)])
+    limits, intrinsics) in ONE pass over the pixels instead of reducing min / max first, and sorts one record per RUN of consecutive
+    survivors of a voxel instead of one per point (CUBOID_FE_RUNS). Every result byte and every fetched array must equal the two-pass
+    path's, on normal, empty, constant and plane-only frames, on frames whose origin voxel (all zero-depth pixels) is made of tens of
+    thousands of runs of every length, and on a near wall whose voxels hold more than a hundred points each; the tapped run must agree
+    on all it shares."""
+    depth = np.concatenate([synth.depth_batch("bench", [50, 51, 52, 53]), synth.depth_batch("plane_var", [7, 8]), np.zeros((3, 480, 640), np.uint16),
+                            synth.depth_batch("bench", [54, 55, 56, 57])])
     depth[7] = 2000
     depth[8, 100:110, 300:320] = 450            # a handful of survivors in an otherwise empty frame
+    rng = np.random.default_rng(5)
+    depth[9][rng.random((480, 640)) < 0.5] = 0  # origin voxel: ~150k points in runs of 1, 2, 3 ... between surviving pixels
+    depth[10][:, ::2] = 0                       # ... in runs of exactly one
+    depth[11] = 300                             # a wall at 0.3 m: ~10 x 10 pixels per 5 mm voxel
+    depth[11, ::7, ::5] = 0
+    depth[12][200:, :] = 0                      # whole zero rows: runs of 32
+    n = len(depth)
     out = {}
-    for onepass in ("0", "1"):
+    for onepass, runs in (("0", "0"), ("1", "0"), ("1", "1")):
         monkeypatch.setenv("CUBOID_FE_ONEPASS", onepass)
-        with api.CuboidCuda(params, max_points=640 * 480, max_batch=9) as h:
+        monkeypatch.setenv("CUBOID_FE_RUNS", runs)
+        with api.CuboidCuda(params, max_points=640 * 480, max_batch=n) as h:
             h.set_template(0, tmpl30)
             h.set_option(api.OPT_TAPS, 0)
             res = h.process_batch(depth)
-            out[onepass] = ([bytes(r) for r in res], {w: [h.fetch(f, w) for f in range(9)] for w in ("points", "voxels", "remain", "inliers")})
-    assert out["0"][0] == out["1"][0]
-    for w, arrs in out["0"][1].items():
-        for f, arr in enumerate(arrs):
-            assert np.array_equal(bits(arr) if arr.dtype == np.float32 else arr, bits(out["1"][1][w][f]) if arr.dtype == np.float32 else out["1"][1][w][f]), (w, f)
-    with api.CuboidCuda(params, max_points=640 * 480, max_batch=9) as h:    # taps on: two-pass by construction, checked against the oracle elsewhere
+            out[onepass + runs] = ([bytes(r) for r in res], {w: [h.fetch(f, w) for f in range(n)] for w in ("points", "voxels", "remain", "inliers")})
+    for other in ("10", "11"):
+        assert out["00"][0] == out[other][0]
+        for w, arrs in out["00"][1].items():
+            for f, arr in enumerate(arrs):
+                assert np.array_equal(bits(arr) if arr.dtype == np.float32 else arr, bits(out[other][1][w][f]) if arr.dtype == np.float32 else out[other][1][w][f]), (other, w, f)
+    out["1"] = out["11"]
+    with api.CuboidCuda(params, max_points=640 * 480, max_batch=n) as h:    # taps on: two-pass by construction, checked against the oracle elsewhere
         h.set_template(0, tmpl30)
         tapped = h.process_batch(depth)
-    for i in range(9):
+    for i in range(n):
         a = type(tapped[i]).from_buffer_copy(out["1"][0][i])
         for k in ("status", "n_points", "n_voxels", "n_inliers", "n_remain", "n_clusters", "inlier_hash", "remain_hash", "cluster_hash"):
             assert getattr(a, k) == getattr(tapped[i], k), (i, k)

@@ -90,7 +90,7 @@ struct cuboid_handle {
     // fused front end (frontend.cuh): one thread-block cluster per frame, persistent over the chunk
     int frontend = 1; int fe_cluster = 1; int fe_threads = 512; int fe_slots = 0; unsigned long long* d_fe_keys = nullptr;
     int sac_wide = 1;                        // 1024-thread k_sac_plane for launches with few frames
-    int fe_cluster_small = 0; int sms = 0; int fe_runs = 0;   // cluster size used when a launch has so few frames that one CTA per frame would leave most SMs idle (single-frame latency)
+    int fe_cluster_small = 0; int sms = 0; int fe_runs = 0; int fe_solo = 1;   // cluster size used when a launch has so few frames that one CTA per frame would leave most SMs idle (single-frame latency)
     int fe_onepass = 1;                        // one-pass front end for depth input (static key bounds): CUBOID_FE_ONEPASS
     int fe_hash = 0; size_t fe_stride = 0;   // voxel-hash path of k_frontend (opt-in: CUBOID_FE_HASH=1; 1024 threads, one CTA per SM) and the per-slot scratch size in u64
     // host-buffer batches: sub-chunks run end to end on a few streams, so copies, front end and ICP of different sub-chunks overlap
@@ -132,8 +132,9 @@ int fe_smem_mode(int nt, bool masks, bool hash, bool runs) {
     return nt == 256 ? fe_dyn_smem<256>(masks, hash, runs) : (nt == 512 ? fe_dyn_smem<512>(masks, hash, runs) : fe_dyn_smem<1024>(masks, hash, runs));
 }
 // k_frontend instance for (input kind, CTA size, rgb carried)
-const void* fe_fn(int src, int nt, bool rgb, bool runs = false) {
-    if (src == 0 && runs) return nt == 256 ? (const void*)k_frontend<0, 256, false, true> : (nt == 512 ? (const void*)k_frontend<0, 512, false, true> : (const void*)k_frontend<0, 1024, false, true>);
+const void* fe_fn(int src, int nt, bool rgb, bool runs = false, bool solo = false) {
+    if (src == 0 && runs) return nt == 256 ? (const void*)k_frontend<0, 256, false, true, true> : (nt == 512 ? (const void*)k_frontend<0, 512, false, true, true> : (const void*)k_frontend<0, 1024, false, true, true>);
+    if (src == 0 && solo) return nt == 256 ? (const void*)k_frontend<0, 256, false, false, true> : (nt == 512 ? (const void*)k_frontend<0, 512, false, false, true> : (const void*)k_frontend<0, 1024, false, false, true>);
     if (nt == 256) return src == 0 ? (const void*)k_frontend<0, 256, false> : (rgb ? (const void*)k_frontend<1, 256, true> : (const void*)k_frontend<1, 256, false>);
     if (nt == 512) return src == 0 ? (const void*)k_frontend<0, 512, false> : (rgb ? (const void*)k_frontend<1, 512, true> : (const void*)k_frontend<1, 512, false>);
     return src == 0 ? (const void*)k_frontend<0, 1024, false> : (rgb ? (const void*)k_frontend<1, 1024, true> : (const void*)k_frontend<1, 1024, false>);
@@ -354,8 +355,10 @@ int run_chunk(cuboid_handle* h, const ChunkIn& in, int nf, cuboid_frame_result* 
         cfg.stream = st;
         cfg.attrs = at; cfg.numAttrs = 1;
         {
+            const bool solo = fe_c == 1 && fa.st_on && !fa.kpp && !fa.hashes && !fa.hash && h->fe_solo;   // the kernel's one-pass mode as its own instance
+            if (!solo) fa.runs = 0;
             void* kargs[1] = {(void*)&fa};
-            CK(h, cudaLaunchKernelExC(&cfg, fe_fn(in.blob ? 1 : 0, h->fe_threads, in.blob && fa.rgb, fa.runs != 0), kargs));
+            CK(h, cudaLaunchKernelExC(&cfg, fe_fn(in.blob ? 1 : 0, h->fe_threads, in.blob && fa.rgb, fa.runs != 0, solo), kargs));
         }
         ++h->launches;
         CK(h, cudaGetLastError());
@@ -695,6 +698,7 @@ static int create_impl(cuboid_handle** out, const cuboid_params* p, int device, 
         const char* ec = std::getenv("CUBOID_FE_CLUSTER"); if (ec) h->fe_cluster = std::max(1, std::min(16, atoi(ec)));
         const char* eo1 = std::getenv("CUBOID_FE_ONEPASS"); if (eo1) h->fe_onepass = atoi(eo1) ? 1 : 0;
         const char* eru = std::getenv("CUBOID_FE_RUNS"); if (eru) h->fe_runs = atoi(eru) ? 1 : 0;
+        const char* eso = std::getenv("CUBOID_FE_SOLO"); if (eso) h->fe_solo = atoi(eso) ? 1 : 0;
         const char* eh = std::getenv("CUBOID_FE_HASH"); if (eh) h->fe_hash = std::max(0, std::min(2, atoi(eh)));   // 2: developer, mark the path taken in status
         // Opt-in (measured slower than the radix path on B200: 7.1 ms against 4.75 ms per 1024 VGA frames): the
         // voxel-hash path (one 1024-thread CTA per SM); frames with more voxels than its table holds fall back per frame to the radix
@@ -702,8 +706,8 @@ static int create_impl(cuboid_handle** out, const cuboid_params* p, int device, 
         if (h->fe_hash && h->P <= 400000 && h->fe_cluster == 1) h->fe_threads = 1024; else h->fe_hash = 0;
         const char* et = std::getenv("CUBOID_FE_THREADS"); if (et) { h->fe_threads = atoi(et) == 1024 ? 1024 : (atoi(et) == 256 ? 256 : 512); if (h->fe_threads != 1024) h->fe_hash = 0; }
         for (int nt : {256, 512, 1024})
-            for (int v = 0; v < 4; ++v) {
-                const void* fn = fe_fn((v == 1 || v == 2) ? 1 : 0, nt, v == 2, v == 3);
+            for (int v = 0; v < 5; ++v) {
+                const void* fn = fe_fn((v == 1 || v == 2) ? 1 : 0, nt, v == 2, v == 3, v == 4);
                 if (cudaFuncSetAttribute(fn, cudaFuncAttributeMaxDynamicSharedMemorySize, fe_smem(nt)) != cudaSuccess) return fail(CUBOID_E_CUDA);
                 if (h->fe_cluster > 8) cudaFuncSetAttribute(fn, cudaFuncAttributeNonPortableClusterSizeAllowed, 1);
             }

@@ -619,7 +619,9 @@ __device__ __forceinline__ bool fe_hash_frame(const FrontArgs& a, int f, int n_i
 // RGB (PointCloud2 inputs with a packed rgb field, FrontArgs::rgb) is a compile-time variant: the colour bookkeeping costs the
 // depth-frame path 4 % when it is a run-time test.
 // RUNS (run records, depth input only) likewise: compiled into the common kernel it costs the default path registers (spills).
-template <int SRC, int NT, bool RGB, bool RUNS = false>
+// SOLO: depth input, one CTA per frame, one-pass mode, no parity taps - what a throughput launch runs. As its own instance the cluster
+// exchange, the A1 pass and the taps are compiled out (registers, and a CTA barrier where the general kernel has a cluster barrier).
+template <int SRC, int NT, bool RGB, bool RUNS = false, bool SOLO = false>
 __global__ void __launch_bounds__(NT, NT <= 256 ? 4 : (NT <= 512 ? 2 : 1)) k_frontend(const FrontArgs a) {
     constexpr int NW = NT / 32;
     constexpr int TILE = NT * FE_ITEMS;
@@ -639,7 +641,11 @@ __global__ void __launch_bounds__(NT, NT <= 256 ? 4 : (NT <= 512 ? 2 : 1)) k_fro
     __shared__ int s_def_lp[FE_MAXDEF], s_def_pos[FE_MAXDEF];
 
     cg::cluster_group cluster = cg::this_cluster();
-    const int C = (int)cluster.num_blocks(), r = (int)cluster.block_rank();
+    static_assert(!SOLO || (SRC == 0 && !RGB), "SOLO is the depth-frame instance");
+    static_assert(!RUNS || SOLO, "run records need the one-pass mode");
+    const int C = SOLO ? 1 : (int)cluster.num_blocks(), r = SOLO ? 0 : (int)cluster.block_rank();
+    auto csync = [&]() { if (SOLO) __syncthreads(); else cluster.sync(); };
+    const bool tap_hashes = !SOLO && a.hashes != 0;
     const int slot = blockIdx.x / C, nslots = gridDim.x / C;
     const int tid = threadIdx.x, lane = tid & 31, wid = tid >> 5;
     const PreArgs& p = a.pre;
@@ -652,10 +658,10 @@ __global__ void __launch_bounds__(NT, NT <= 256 ? 4 : (NT <= 512 ? 2 : 1)) k_fro
         slice = (slice + 7) & ~7;
         const int s0 = min(n_in, r * slice), s1 = min(n_in, r * slice + slice);
         unsigned char* s_mask = fe_dyn + NT * 32;
-        const bool hash_try = NT == 1024 && C == 1 && a.hash != 0;    // the hash path recomputes the masks (its table takes their room)
-        const bool onepass = SRC == 0 && C == 1 && a.st_on != 0 && !a.kpp && !a.hashes && !hash_try;   // kernel-uniform
+        const bool hash_try = !SOLO && NT == 1024 && C == 1 && a.hash != 0;    // the hash path recomputes the masks (its table takes their room)
+        const bool onepass = SOLO || (SRC == 0 && C == 1 && a.st_on != 0 && !a.kpp && !a.hashes && !hash_try);   // kernel-uniform
         const bool use_mask = !hash_try && !onepass && ((slice + TILE - 1) / TILE) * NT <= FE_MASK_BYTES && NT * 32 + FE_MASK_BYTES <= a.arena;
-        const bool runs = RUNS && onepass && a.runs != 0;
+        const bool runs = RUNS && a.runs != 0;
         int NR = 0;                      // sort records of the frame: its points, or its runs
 
         // ---- A1: survivors and min/max of this CTA's input slice ----
@@ -704,7 +710,7 @@ __global__ void __launch_bounds__(NT, NT <= 256 ? 4 : (NT <= 512 ? 2 : 1)) k_fro
                 for (int c = 0; c < 3; ++c) { s_x.mn[c] = xmn[c]; s_x.mx[c] = xmx[c]; }
             }
         }
-        if (!onepass) cluster.sync();
+        if (!onepass) csync();
         if (tid == 0 && !onepass) {
             int base = 0, N = 0;
             float mn[3] = {3.402823466e38f, 3.402823466e38f, 3.402823466e38f};
@@ -745,7 +751,7 @@ __global__ void __launch_bounds__(NT, NT <= 256 ? 4 : (NT <= 512 ? 2 : 1)) k_fro
         __syncthreads();
         int N = onepass ? 1 : s_f.N;     // one-pass mode learns N at the end of A2
         if (N == 0) {          // cluster-uniform; the barrier keeps a fast CTA from overwriting s_x while a peer still reads it
-            cluster.sync();
+            csync();
             continue;
         }
         VoxelGeom g = s_f.g;             // one-pass mode: stale, not used before it is recomputed after A2
@@ -758,7 +764,7 @@ __global__ void __launch_bounds__(NT, NT <= 256 ? 4 : (NT <= 512 ? 2 : 1)) k_fro
                 st.s_def_pos = s_def_pos; st.s_misc = s_misc;
                 const bool done = fe_hash_frame<SRC, NT, RGB>(a, f, n_in, N, g, bufA, fe_dyn, st);
                 __syncthreads();
-                if (done) { cluster.sync(); continue; }
+                if (done) { csync(); continue; }
             }
         }
         if (C == 1) {
@@ -772,7 +778,7 @@ __global__ void __launch_bounds__(NT, NT <= 256 ? 4 : (NT <= 512 ? 2 : 1)) k_fro
             unsigned short* s_sel = reinterpret_cast<unsigned short*>(fe_dyn);
             unsigned short* s_dep = reinterpret_cast<unsigned short*>(fe_dyn + NT * 16);
             float4* out = p.pts + (size_t)f * p.Pout;
-            int* kpp = a.kpp ? a.kpp + (size_t)f * a.P : nullptr;
+            int* kpp = (!SOLO && a.kpp) ? a.kpp + (size_t)f * a.P : nullptr;
             int run = onepass ? 0 : s_f.base;
             int rrun = 0;                                                                                     // run records written so far
             unsigned long long* s_run = reinterpret_cast<unsigned long long*>(fe_dyn + NT * 32);            // [TILE / 32][32] records of a tile, per warp step
@@ -833,7 +839,7 @@ __global__ void __launch_bounds__(NT, NT <= 256 ? 4 : (NT <= 512 ? 2 : 1)) k_fro
                         }
                         if (!runs) __stcg(bufA + pos, ((unsigned long long)sk << 32) | (unsigned int)pos);
                         if (kpp) kpp[pos] = idx;
-                        if (a.hashes) {
+                        if (tap_hashes) {
                             hh[0] += hash_point((unsigned int)pos, pt.x, pt.y, pt.z);
                             hh[1] += hash_index((unsigned int)pos, idx);
                         }
@@ -927,7 +933,7 @@ __global__ void __launch_bounds__(NT, NT <= 256 ? 4 : (NT <= 512 ? 2 : 1)) k_fro
             }
         }
         __threadfence();
-        cluster.sync();
+        csync();
 
         // ---- B: stable LSD radix sort of the frame's N records, 8-bit digits, significant key bits only ----
         if (!runs) NR = N;
@@ -951,7 +957,7 @@ __global__ void __launch_bounds__(NT, NT <= 256 ? 4 : (NT <= 512 ? 2 : 1)) k_fro
                         if (i0 + j * NT < q1) atomicAdd(&s_hist[(unsigned int)(k4[j] >> shift) & 255u], 1u);
                 }
                 __syncthreads();
-                cluster.sync();
+                csync();
             }
             {   // digit d = tid: records of digit d in front of this CTA's = all smaller digits + digit d of lower ranks
                 unsigned int tot = 0, before = 0;
@@ -1032,7 +1038,7 @@ __global__ void __launch_bounds__(NT, NT <= 256 ? 4 : (NT <= 512 ? 2 : 1)) k_fro
             }
             fe_cp_async_wait<0>();
             __threadfence();
-            cluster.sync();
+            csync();
         }
         const unsigned long long* keys = (npass & 1) ? bufB : bufA;
 
@@ -1052,7 +1058,7 @@ __global__ void __launch_bounds__(NT, NT <= 256 ? 4 : (NT <= 512 ? 2 : 1)) k_fro
                 for (int w = 0; w < NW; ++w) t += s_wc[w];
                 s_x.heads = t;
             }
-            cluster.sync();
+            csync();
         }
         if (tid == 0) {
             int vbase = 0;
@@ -1224,7 +1230,7 @@ __global__ void __launch_bounds__(NT, NT <= 256 ? 4 : (NT <= 512 ? 2 : 1)) k_fro
             unsigned int* s_pw = reinterpret_cast<unsigned int*>(s_head + RTILE);   // packed rgb(a) of the staged points (RGB only)
             const float4* pts = p.pts + (size_t)f * p.Pout;
             float4* vox = a.vox + (size_t)f * a.P;
-            int* vcount = a.vcount ? a.vcount + (size_t)f * a.P : nullptr;
+            int* vcount = (!SOLO && a.vcount) ? a.vcount + (size_t)f * a.P : nullptr;
             int vrun = s_f.vbase;
             unsigned long long hv[1] = {0ull};
             for (int t0 = q0; t0 < q1; t0 += RTILE) {
@@ -1288,7 +1294,7 @@ __global__ void __launch_bounds__(NT, NT <= 256 ? 4 : (NT <= 512 ? 2 : 1)) k_fro
                     }
                     vox[pos] = make_float4(cx, cy, cz, cw);
                     if (vcount) vcount[pos] = end - lp;
-                    if (a.hashes) hv[0] += hash_point((unsigned int)pos, cx, cy, cz);
+                    if (tap_hashes) hv[0] += hash_point((unsigned int)pos, cx, cy, cz);
                 }
                 vrun += total;
                 __syncthreads();
@@ -1329,7 +1335,7 @@ __global__ void __launch_bounds__(NT, NT <= 256 ? 4 : (NT <= 512 ? 2 : 1)) k_fro
                         const int vp = s_def_pos[d];
                         vox[vp] = make_float4(cx, cy, cz, RGB ? fe_rgb_avg(acc.sr, acc.sg, acc.sb, acc.cnt) : 1.0f);
                         if (vcount) vcount[vp] = acc.cnt;
-                        if (a.hashes) hv[0] += hash_point((unsigned int)vp, cx, cy, cz);
+                        if (tap_hashes) hv[0] += hash_point((unsigned int)vp, cx, cy, cz);
                     }
                 }
                 __syncthreads();
@@ -1340,7 +1346,7 @@ __global__ void __launch_bounds__(NT, NT <= 256 ? 4 : (NT <= 512 ? 2 : 1)) k_fro
             if (tid == 0 && hv[0]) atomic_add_u64(&p.res[f].voxel_hash, hv[0]);
         }
     }
-    cluster.sync();   // no CTA may exit while a peer can still read its shared memory
+    if (!SOLO) cluster.sync();   // no CTA may exit while a peer can still read its shared memory
 }
 
 }  // namespace cuboid

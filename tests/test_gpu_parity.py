@@ -572,7 +572,7 @@ def test_icp_on_the_reference_real_scan_returns_the_published_pose(golden, param
 
 
 @pytest.mark.parametrize("knob,values", [("CUBOID_ICP_NSUB", ("1", "2", "4")), ("CUBOID_ICP_SLICE", ("1", "8", "5000")),
-                                         ("CUBOID_ICP_OUTWARD", ("0", "1")), ("CUBOID_ICP_QUEUED", ("0", "1")), ("CUBOID_ICP_TABLE", ("0", "1")), ("CUBOID_FE_HASH", ("0", "1")), ("CUBOID_FE_ONEPASS", ("0", "1")), ("CUBOID_FE_RUNS", ("0", "1")), ("CUBOID_ICP_LOCAL", ("0", "1")), ("CUBOID_ICP_SEEDGRID", ("0", "1")), ("CUBOID_FE_CLUSTER_SMALL", ("1", "8")), ("CUBOID_SAC_WIDE", ("0", "1")), ("CUBOID_NNT_H_MM", ("0.7", "2.5")),
+                                         ("CUBOID_ICP_OUTWARD", ("0", "1")), ("CUBOID_ICP_QUEUED", ("0", "1")), ("CUBOID_ICP_TABLE", ("0", "1")), ("CUBOID_FE_HASH", ("0", "1")), ("CUBOID_FE_ONEPASS", ("0", "1")), ("CUBOID_FE_RUNS", ("0", "1")), ("CUBOID_FE_SOLO", ("0", "1")), ("CUBOID_ICP_LOCAL", ("0", "1")), ("CUBOID_ICP_SEEDGRID", ("0", "1")), ("CUBOID_FE_CLUSTER_SMALL", ("1", "8")), ("CUBOID_SAC_WIDE", ("0", "1")), ("CUBOID_NNT_H_MM", ("0.7", "2.5")),
                                          ("CUBOID_PIPELINE", ("0", "1"))])
 def test_execution_knobs_do_not_change_results(tmpl30, params, knob, values, monkeypatch):
     """How the work is scheduled must never show in the results: sub-workers per CTA, iterations per time slice, outward search
@@ -704,15 +704,16 @@ def test_one_pass_front_end_equals_two_pass(tmpl30, params, monkeypatch):
     depth[12][200:, :] = 0                      # whole zero rows: runs of 32
     n = len(depth)
     out = {}
-    for onepass, runs in (("0", "0"), ("1", "0"), ("1", "1")):
+    for onepass, runs in (("0", "0"), ("1", "0"), ("1", "1"), ("1", "s")):
         monkeypatch.setenv("CUBOID_FE_ONEPASS", onepass)
-        monkeypatch.setenv("CUBOID_FE_RUNS", runs)
+        monkeypatch.setenv("CUBOID_FE_RUNS", "0" if runs == "s" else runs)
+        monkeypatch.setenv("CUBOID_FE_SOLO", "0" if runs == "s" else "1")     # "1s": one-pass mode inside the general kernel instance
         with api.CuboidCuda(params, max_points=640 * 480, max_batch=n) as h:
             h.set_template(0, tmpl30)
             h.set_option(api.OPT_TAPS, 0)
             res = h.process_batch(depth)
             out[onepass + runs] = ([bytes(r) for r in res], {w: [h.fetch(f, w) for f in range(n)] for w in ("points", "voxels", "remain", "inliers")})
-    for other in ("10", "11"):
+    for other in ("10", "11", "1s"):
         assert out["00"][0] == out[other][0]
         for w, arrs in out["00"][1].items():
             for f, arr in enumerate(arrs):

@@ -13,8 +13,9 @@ except Exception as e:
     print('FAILED', t[:200]); print(open('gpurun_out/fe_try.err').read()[-1500:])
 "
 }
-run CUBOID_FE_RUNS=0
-run CUBOID_FE_RUNS=1
-run CUBOID_FE_RUNS=0
-run CUBOID_FE_RUNS=1
-timeout 1500 python -m pytest tests -m gpu -x -q 2>&1 | tail -5
+run CUBOID_FE_SOLO=0
+run CUBOID_FE_SOLO=1
+run CUBOID_FE_SOLO=0
+run CUBOID_FE_SOLO=1
+run CUBOID_FE_SOLO=1 CUBOID_FE_RUNS=1
+timeout 900 python -m pytest tests/test_gpu_parity.py -m gpu -x -q -k "one_pass_front_end or fused_frontend_equals or (knobs and FE_) or full_size or taps_off" 2>&1 | tail -5

@@ -27,6 +27,7 @@
 // Roofline: FP32 pipe (un-fused). Brute force is 8*S*T ops per pass; the culled kernel reports both the
 // pairs it actually evaluated and the brute-force equivalent (IcpArgs::work).
 #pragma once
+#include <type_traits>
 #include <cuda_fp16.h>
 
 #include "common.cuh"
@@ -177,7 +178,7 @@ __device__ __forceinline__ float det3(const M3f& m) {
     return h0 - h1 + h2;
 }
 // Eigen::JacobiSVD<Matrix3f>(sigma, ComputeFullU | ComputeFullV)
-__device__ void jacobi_svd3(const M3f& in, M3f& U, M3f& V) {
+__device__ __forceinline__ void jacobi_svd3(const M3f& in, M3f& U, M3f& V) {
     const float precision = 2.0f * 1.1920928955078125e-07f;
     const float consider_zero = 1.17549435e-38f;
     float scale = 0.f;
@@ -224,18 +225,30 @@ __device__ void jacobi_svd3(const M3f& in, M3f& U, M3f& V) {
     }
 #pragma unroll
     for (int i = 0; i < 3; ++i) sv[i] = sv[i] * scale;
+    // Selection sort of the singular values, largest first (first maximum on ties; stops at a zero maximum), columns of U and V
+    // swapped along. Written with static indices only: a run-time column index would put U, V and W in local memory for the whole
+    // routine, and every rotation above would go through it (the SVD is the serial part of an ICP iteration).
+    auto swap_cols = [&](auto I, auto J) {
+        constexpr int i = decltype(I)::value, j = decltype(J)::value;
+        float t = sv[i]; sv[i] = sv[j]; sv[j] = t;
 #pragma unroll
-    for (int i = 0; i < 3; ++i) {
-        int pos = i;
-        for (int k = i + 1; k < 3; ++k) if (sv[k] > sv[pos]) pos = k;
-        if (sv[pos] == 0.f) break;
-        if (pos != i) {
-            float t = sv[i]; sv[i] = sv[pos]; sv[pos] = t;
-            for (int r = 0; r < 3; ++r) {
-                t = U.a[r][i]; U.a[r][i] = U.a[r][pos]; U.a[r][pos] = t;
-                t = V.a[r][i]; V.a[r][i] = V.a[r][pos]; V.a[r][pos] = t;
-            }
+        for (int r = 0; r < 3; ++r) {
+            t = U.a[r][i]; U.a[r][i] = U.a[r][j]; U.a[r][j] = t;
+            t = V.a[r][i]; V.a[r][i] = V.a[r][j]; V.a[r][j] = t;
         }
+    };
+    using I0 = std::integral_constant<int, 0>; using I1 = std::integral_constant<int, 1>; using I2 = std::integral_constant<int, 2>;
+    {
+        const bool p1 = sv[1] > sv[0];
+        const float m01 = p1 ? sv[1] : sv[0];
+        const bool p2 = sv[2] > m01;
+        if ((p2 ? sv[2] : m01) == 0.f) return;
+        if (p2) swap_cols(I0{}, I2{}); else if (p1) swap_cols(I0{}, I1{});
+    }
+    {
+        const bool p2 = sv[2] > sv[1];
+        if ((p2 ? sv[2] : sv[1]) == 0.f) return;
+        if (p2) swap_cols(I1{}, I2{});
     }
 }
 

@@ -312,6 +312,25 @@ __device__ __forceinline__ void canon_sub_finish(Tq* s_part /* [NQ][8] */, Tq* s
     sub_sync<SUB>(sub);
 }
 
+// both at once (the means / MSE step): one barrier pair instead of two
+template <int NQ, int SUB>
+__device__ __forceinline__ void canon_sub_finish_fd(float* s_part_f, float* s_out_f, double* s_part_d, double* s_out_d, int tid, int sub) {
+    sub_sync<SUB>(sub);
+    if (tid < NQ) {
+        const float* p = s_part_f + tid * 8;
+        float s = p[0];
+#pragma unroll
+        for (int g = 1; g < 8; ++g) s = s + p[g];
+        s_out_f[tid] = s;
+    } else if (tid == 32) {
+        double s = s_part_d[0];
+#pragma unroll
+        for (int g = 1; g < 8; ++g) s = s + s_part_d[g];
+        s_out_d[0] = s;
+    }
+    sub_sync<SUB>(sub);
+}
+
 struct IcpShared {
     unsigned long long bar;
     float part_f[16 * 8];
@@ -1030,15 +1049,18 @@ __device__ __forceinline__ bool icp_slice(const IcpArgs& a, IcpShared& sh, const
             pend = false;
             sub_sync<SUB>(sub);
             const int nm = sh.nmiss;
-            if (tid == 0) sh.task = 0;
-            sub_sync<SUB>(sub);
-            if (tid == 0) sh.nmiss = 0;
-            if (nm > 0) icp_nn_pass<RESIDENT, QUEUED, LOCAL>(a, sh, s_tmpl, s_nodes, s_sib, s_orig, wscr, cur, nm, nm == S ? order : miss, corr, cd, evaluated);
+            if (nm > 0) {   // (uniform) the usual late iteration has no misses and goes on behind the one barrier above
+                if (tid == 0) sh.task = 0;
+                sub_sync<SUB>(sub);
+                if (tid == 0) sh.nmiss = 0;
+                icp_nn_pass<RESIDENT, QUEUED, LOCAL>(a, sh, s_tmpl, s_nodes, s_sib, s_orig, wscr, cur, nm, nm == S ? order : miss, corr, cd, evaluated);
+                sub_sync<SUB>(sub);
+            }
         } else {
             icp_nn_pass<RESIDENT, QUEUED, LOCAL>(a, sh, s_tmpl, s_nodes, s_sib, s_orig, wscr, cur, S, order, corr, cd, evaluated);
+            sub_sync<SUB>(sub);
         }
         ++passes;
-        sub_sync<SUB>(sub);
         if (tid == 0) sh.task = 0;
         // 2. means + MSE: the first 256 threads are the 256 canonical lanes
         for (int set = 0; set < LPT; ++set) {
@@ -1060,13 +1082,13 @@ __device__ __forceinline__ bool icp_slice(const IcpArgs& a, IcpShared& sh, const
             canon_sub_partial<float, 6, SUB>(q6, sh.part_f, tid, set);
             canon_sub_partial<double, 1, SUB>(qd, sh.part_d, tid, set);
         }
-        canon_sub_finish<float, 6, SUB>(sh.part_f, sh.red_f, tid, sub);
-        canon_sub_finish<double, 1, SUB>(sh.part_d, sh.red_d, tid, sub);
+        canon_sub_finish_fd<6, SUB>(sh.part_f, sh.red_f, sh.part_d, sh.red_d, tid, sub);
         float sm[3], dm[3];
 #pragma unroll
         for (int k = 0; k < 3; ++k) { sm[k] = sh.red_f[k] * one_over_n; dm[k] = sh.red_f[3 + k] * one_over_n; }
         const double mse_sum = sh.red_d[0];
-        sub_sync<SUB>(sub);
+        // (no barrier here: red_f / red_d are next written behind the first barrier of the covariance step's finish, part_f was read
+        // in front of the second barrier of the finish above)
         // 3. sigma = one_over_n * dst_demean * src_demean^T
         for (int set = 0; set < LPT; ++set) {
             float q9[9];

@@ -83,7 +83,7 @@ per-source-line table: a `gpurun` call brings back at most 64 MiB), copied here 
 | `{tag}_launches.csv` | ncu launch list (`--metrics gpu__time_duration.sum --clock-control none`) of `python bench.py --steps 1 --warmup 1 --no-cpu --no-configs` |
 | `{tag}_k_icp_*`, `{tag}_k_frontend_*`, `{tag}_k_sac_plane_*`, `{tag}_k_cluster_*` | `ncu --set full --import-source on --clock-control none` of the 1024-frame launch of each of the four big kernels: `_summary.md` / `_summary.json` (key metrics), `_raw.csv` (every metric of the capture), `_lines.txt` (source lines by stall samples and by executed instructions, with lanes per instruction) |
 | `icp_issue.json`, `frontend_traffic.json` | what `bench.py` reads for `roofline.issue` and `roofline_hbm.traffic` (derived from the two captures above) |
-| `{tag}_sass_histogram.md` | `cuobjdump -sass` opcode histogram of every kernel of the built `.so` (`tools/sass_hist.py`): `UBLKCP` / `SYNCS` (TMA bulk copies + mbarriers) in `k_icp` and `k_sac_plane`, `LDGSTS` and the cluster barriers `UCGABAR_*` in `k_frontend`, no `UTMALDG`, no tensor-core opcodes (nothing on this path is a contraction) |
+| `{tag}_sass_histogram.md` | `cuobjdump -sass` opcode histogram of every kernel of the built `.so` (`tools/sass_hist.py`): `UBLKCP` / `SYNCS` (TMA bulk copies + mbarriers) in `k_icp` and `k_sac_plane`, `LDGSTS` in `k_frontend` (and the cluster barriers `UCGABAR_*` in its general instance; none in the `SOLO` instance a throughput launch runs), no `UTMALDG`, no tensor-core opcodes (nothing on this path is a contraction) |
 | `{tag}_hyp_n1_f1.json`, `{tag}_hyp_n1_f64.json`, `r2_c_hyp_n2_*`, `r2_g_hyp_n8_*` | `bench.py --workload guess64 --shard hypotheses` at 1 / 2 / 8 GPUs, one frame and 64 frames per step (identical `results_digest`) |
 | `r2_g_bench_n8.json`, `r2_g_bench_n8_multi8.json`, `r2_f_bench_n8_hd720.json` | the bench on 8 GPUs of one box (torchrun; frames sharded, NCCL only for the timing all-reduce): headline workload, BASELINE config 4 (multi8), config 5 (hd720) |
 
@@ -125,20 +125,20 @@ per call; under ncu they run one after the other):
 ```
 
 Reading: a quarter of the round-1 instruction count, 26 of 32 lanes per instruction; half the issue slots are used and neither the
-FP32 pipe (17 %) nor memory (DRAM 2 %, L2 hit rate 94 %) is near a limit: the kernel waits on dependent L2 loads (the point, then
+FP32 pipe (18 %) nor memory (DRAM 2 %, L2 hit rate 94 %) is near a limit: the kernel waits on dependent L2 loads (the point, then
 its 64-byte table record) and on the barriers between the passes of an iteration. DESIGN.md section 9.
 
-## ncu `--set full` of `k_frontend<0, 512, false>` (1024 frames in one persistent launch, 296 CTAs, one-pass mode)
+## ncu `--set full` of `k_frontend<0, 512, false, false, true>` (the `SOLO` instance: 1024 depth frames in one persistent launch, 296 CTAs, one-pass mode)
 
 {md('k_frontend')}
 ```
 {lines('k_frontend')}
 ```
 
-Reading: as in round 1 - half the issue slots, DRAM at 37 % of peak with 14 GB of traffic against 5.2 GB algorithmic (the radix
-ping-pong of 296 frames in flight does not stay in L2). Half the instructions are the three radix passes (a quarter of all
-instructions rank equal digits with eight votes per record and pass). The voxel-hash path (`CUBOID_FE_HASH=1`) moves 8.4 GB but is
-slower (7.1 ms): DESIGN.md section 8.
+Reading: half the issue slots, DRAM at 39 % of peak with 14 GB of traffic against 5.2 GB algorithmic (the radix ping-pong of 296
+frames in flight does not stay in L2). Half the instructions are the three radix passes (a quarter of all instructions rank equal
+digits with eight votes per record and pass). Two variants that move fewer bytes are in the library as opt-in knobs and are slower:
+the voxel-hash path (`CUBOID_FE_HASH=1`: 8.4 GB, 7.1 ms) and run records (`CUBOID_FE_RUNS=1`: 9.2 GB, 4.74 ms); DESIGN.md section 8.
 
 ## ncu `--set full` of `k_sac_plane<256>` (1024 frames, one 256-thread CTA per frame)
 

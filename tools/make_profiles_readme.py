@@ -85,7 +85,7 @@ per-source-line table: a `gpurun` call brings back at most 64 MiB), copied here 
 | `icp_issue.json`, `frontend_traffic.json` | what `bench.py` reads for `roofline.issue` and `roofline_hbm.traffic` (derived from the two captures above) |
 | `{tag}_sass_histogram.md` | `cuobjdump -sass` opcode histogram of every kernel of the built `.so` (`tools/sass_hist.py`): `UBLKCP` / `SYNCS` (TMA bulk copies + mbarriers) in `k_icp` and `k_sac_plane`, `LDGSTS` in `k_frontend` (and the cluster barriers `UCGABAR_*` in its general instance; none in the `SOLO` instance a throughput launch runs), no `UTMALDG`, no tensor-core opcodes (nothing on this path is a contraction) |
 | `{tag}_hyp_n1_f1.json`, `{tag}_hyp_n1_f64.json`, `r2_c_hyp_n2_*`, `r2_g_hyp_n8_*` | `bench.py --workload guess64 --shard hypotheses` at 1 / 2 / 8 GPUs, one frame and 64 frames per step (identical `results_digest`) |
-| `r2_g_bench_n8.json`, `r2_g_bench_n8_multi8.json`, `r2_f_bench_n8_hd720.json` | the bench on 8 GPUs of one box (torchrun; frames sharded, NCCL only for the timing all-reduce): headline workload, BASELINE config 4 (multi8), config 5 (hd720) |
+| `r2_i_bench_n8.json`, `r2_g_bench_n8_multi8.json`, `r2_f_bench_n8_hd720.json` | the bench on 8 GPUs of one box (torchrun; frames sharded, NCCL only for the timing all-reduce): headline workload, BASELINE config 4 (multi8), config 5 (hd720) |
 
 ## End-of-round bench line (`{tag}_bench.json`)
 

@@ -89,7 +89,7 @@ struct cuboid_handle {
     struct { int active = 0; int model_type = 0; float axis[3] = {0, 0, 0}; double eps = 0.0, thr = 0.0; } sac_override;   // cuboid_surface_normals
     // fused front end (frontend.cuh): one thread-block cluster per frame, persistent over the chunk
     int frontend = 1; int fe_cluster = 1; int fe_threads = 512; int fe_slots = 0; unsigned long long* d_fe_keys = nullptr;
-    int sac_wide = 1;                        // 1024-thread k_sac_plane for launches with few frames
+    int sac_wide = 1;                        // 1024-thread k_sac_plane: 0 never, 1 for launches with few frames, 2 always (developer)
     int fe_cluster_small = 0; int sms = 0; int fe_runs = 0; int fe_solo = 1;   // cluster size used when a launch has so few frames that one CTA per frame would leave most SMs idle (single-frame latency)
     int fe_onepass = 1;                        // one-pass front end for depth input (static key bounds): CUBOID_FE_ONEPASS
     int fe_hash = 0; size_t fe_stride = 0;   // voxel-hash path of k_frontend (opt-in: CUBOID_FE_HASH=1; 1024 threads, one CTA per SM) and the per-slot scratch size in u64
@@ -433,7 +433,10 @@ int run_chunk(cuboid_handle* h, const ChunkIn& in, int nf, cuboid_frame_result* 
         for (int k = 0; k < 12; ++k) s.bbP[k] = h->bbP[k];
         for (int k = 0; k < 4; ++k) s.bb[k] = h->bb[k];
         // few frames (one ROS callback, a small 720p batch): a 1024-thread CTA per frame instead of leaving most SMs idle
-        if (h->sac_wide && 2LL * nf <= h->sms) k_sac_plane<1024><<<nf, 1024, sizeof(SacShared), st>>>(s);
+        // 1024 threads per frame when one 256-thread CTA per frame would leave most SMs idle (few frames). Not for big frames in full
+        // launches: 256 frames of 720p take 12.2 ms narrow (one wave, a frame's own latency) and 16.0 ms wide (measured)
+        const bool wide = h->sac_wide == 2 || (h->sac_wide == 1 && 2LL * nf <= h->sms);
+        if (wide) k_sac_plane<1024><<<nf, 1024, sizeof(SacShared), st>>>(s);
         else k_sac_plane<SAC_THREADS><<<nf, SAC_THREADS, sizeof(SacShared), st>>>(s);
         ++h->launches;
         CK(h, cudaGetLastError());
@@ -764,7 +767,7 @@ static int create_impl(cuboid_handle** out, const cuboid_params* p, int device, 
     { const char* ec = std::getenv("CUBOID_ICP_CULL"); if (ec) h->icp_cull = atoi(ec) ? 1 : 0; }
     if (cudaFuncSetAttribute(k_sac_plane<SAC_THREADS>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)sizeof(SacShared)) != cudaSuccess) return fail(CUBOID_E_CUDA);
     if (cudaFuncSetAttribute(k_sac_plane<1024>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)sizeof(SacShared)) != cudaSuccess) return fail(CUBOID_E_CUDA);
-    { const char* ew = std::getenv("CUBOID_SAC_WIDE"); if (ew) h->sac_wide = atoi(ew) ? 1 : 0; }
+    { const char* ew = std::getenv("CUBOID_SAC_WIDE"); if (ew) h->sac_wide = std::max(0, std::min(2, atoi(ew))); }
     if (cudaFuncSetAttribute(k_cluster, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)CLU_DYN_SMEM) != cudaSuccess) return fail(CUBOID_E_CUDA);
     if (cudaFuncSetAttribute(k_cluster_big, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)CLU_DYN_SMEM_BIG) != cudaSuccess) return fail(CUBOID_E_CUDA);
 #undef CA

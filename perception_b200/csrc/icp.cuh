@@ -714,23 +714,24 @@ __device__ __forceinline__ void icp_nn_pass(const IcpArgs& a, IcpShared& sh, con
 // problem's miss list, which the BVH search (icp_nn_pass) then visits instead of `order`.
 template <bool LOCAL>
 __device__ __forceinline__ void icp_nn_table_pass(const IcpArgs& a, IcpShared& sh, const float* tp, float4* cur, int S, const int* order,
-                                                  int* corr, float* cd, int* miss, unsigned long long& evaluated, bool pend) {
+                                                  int* corr, float* cd, int* miss, unsigned long long& evaluated, bool pend, int wid, int nw) {
     const int lane = threadIdx.x & 31;
     const int ntask = (S + 31) / 32;
     const NnTableView& T = a.tab;
     const unsigned int lt_mask = (1u << lane) - 1u;
-    while (true) {
-        int task = 0;
-        if (lane == 0) task = atomicAdd(&sh.task, 1);
-        task = __shfl_sync(FULL_MASK, task, 0);
-        if (task >= ntask) break;
+    // Tasks (32 consecutive points) are dealt to the sub-worker's warps round-robin: a table lookup costs every task about the same,
+    // so nothing is gained by claiming them from a counter (a shared-memory atomic round trip in front of every task), and with the
+    // next task known its points are requested while this task's record is on its way.
+    float4 p_next = make_float4(0.f, 0.f, 0.f, 0.f);
+    if (wid < ntask) p_next = icp_ld<LOCAL>(cur + min(wid * 32 + lane, S - 1));
+    for (int task = wid; task < ntask; task += nw) {
         const int k = task * 32 + lane;
         const bool valid = k < S;
         // points in their own order (no visiting-order indirection: coalesced reads; a table lookup gains nothing from spatially
         // coherent lanes). The BVH pass over the misses keeps the Morton order when everything missed (early iterations).
-        // (Requesting the next task's points before this task's record arrives was measured: no gain, 5.78 vs 5.76 ms.)
         const int i = valid ? k : S - 1;
-        float4 p = icp_ld<LOCAL>(cur + i);
+        float4 p = p_next;
+        if (task + nw < ntask) p_next = icp_ld<LOCAL>(cur + min((task + nw) * 32 + lane, S - 1));
         if (pend && valid) {   // transformCloud(input_transformed, transformation_) of the previous iteration, folded into this read
             p = xform(sh.Tm, p);
             cur[i] = p;
@@ -1045,7 +1046,7 @@ __device__ __forceinline__ bool icp_slice(const IcpArgs& a, IcpShared& sh, const
     while (!sh.done && it < it_end) {
         // 1. correspondences: the candidate table answers the queries close to the template, the BVH search the rest
         if (TABLE) {
-            icp_nn_table_pass<LOCAL>(a, sh, tp, cur, S, order, corr, cd, miss, evaluated, pend);
+            icp_nn_table_pass<LOCAL>(a, sh, tp, cur, S, order, corr, cd, miss, evaluated, pend, tid >> 5, SUB / 32);
             pend = false;
             sub_sync<SUB>(sub);
             const int nm = sh.nmiss;
@@ -1178,7 +1179,7 @@ __device__ __forceinline__ bool icp_slice(const IcpArgs& a, IcpShared& sh, const
         sub_sync<SUB>(sub);
         if (S > 0) {
             if (TABLE) {
-                icp_nn_table_pass<LOCAL>(a, sh, tp, cur, S, order, corr, cd, miss, evaluated, false);
+                icp_nn_table_pass<LOCAL>(a, sh, tp, cur, S, order, corr, cd, miss, evaluated, false, tid >> 5, SUB / 32);
                 sub_sync<SUB>(sub);
                 const int nm = sh.nmiss;
                 if (tid == 0) sh.task = 0;

@@ -721,7 +721,8 @@ __device__ __forceinline__ void icp_nn_table_pass(const IcpArgs& a, IcpShared& s
     const unsigned int lt_mask = (1u << lane) - 1u;
     // Tasks (32 consecutive points) are dealt to the sub-worker's warps round-robin: a table lookup costs every task about the same,
     // so nothing is gained by claiming them from a counter (a shared-memory atomic round trip in front of every task), and with the
-    // next task known its points are requested while this task's record is on its way.
+    // next task known its points are requested while this task's record is on its way. (Also requesting the next task's RECORD one
+    // task ahead was measured: 4.71 against 4.36 ms - sixteen more live registers in a loop that already spills at 64.)
     float4 p_next = make_float4(0.f, 0.f, 0.f, 0.f);
     if (wid < ntask) p_next = icp_ld<LOCAL>(cur + min(wid * 32 + lane, S - 1));
     for (int task = wid; task < ntask; task += nw) {

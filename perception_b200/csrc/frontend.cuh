@@ -2,12 +2,14 @@
 // both PassThrough filters, ordered compaction, getMinMax3D, the VoxelGrid key, the stable radix sort and the
 // sequential float centroids (gps.cpp:53-73, opd.cpp:275-298).
 //
-// One thread-block CLUSTER owns one frame at a time (persistent grid, clusters stride over the frames of the chunk).
-// The CTAs of the cluster split the frame's pixels, then its sort records, then its sorted records into contiguous
-// ranges; what they must agree on (survivor counts, min/max, digit histograms, voxel counts) is exchanged through
-// distributed shared memory between cluster barriers. The radix ping-pong buffers belong to the cluster SLOT, not to
-// the frame, so the same few megabytes are rewritten frame after frame and stay resident in the 126 MB L2: the only
-// HBM traffic left is the algorithmic one (depth in, points out, centroids out).
+// One thread-block CLUSTER owns one frame at a time (persistent grid, clusters stride over the frames of the chunk); a throughput
+// launch uses clusters of ONE CTA, two CTAs per SM (the SOLO instance below), a launch with a handful of frames spreads each frame
+// over an 8-CTA cluster. The CTAs of a cluster split the frame's pixels, then its sort records, then its sorted records into
+// contiguous ranges; what they must agree on (survivor counts, min/max, digit histograms, voxel counts) is exchanged through
+// distributed shared memory between cluster barriers. The radix ping-pong buffers belong to the cluster SLOT, not to the frame, so
+// the same few megabytes are rewritten frame after frame. With 296 frames in flight they do not stay in the 126 MB L2: measured
+// DRAM traffic is 2.7x the algorithmic bytes (profiles/README.md), and the kernel is bound by instruction issue, not by that traffic
+// (two variants that move fewer bytes - the voxel-hash path and run records, both below, both opt-in - are slower).
 //
 // Results are bit-identical to the unfused kernels in preprocess.cuh / voxel.cuh (kept as the CUBOID_OPT_FRONTEND=0
 // path and compared byte for byte in tests/test_gpu_parity.py): same point order, same keys, same stable order inside

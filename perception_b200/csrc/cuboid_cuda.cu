@@ -259,6 +259,7 @@ IcpKernel icp_kernel(int nsub, int mode) {
     static const IcpKernel tab[3][4] = {{k_icp<256, 0>, k_icp<256, 1>, k_icp<256, 2>, k_icp<256, 3>},
                                         {k_icp<512, 0>, k_icp<512, 1>, k_icp<512, 2>, k_icp<512, 3>},
                                         {k_icp<1024, 0>, k_icp<1024, 1>, k_icp<1024, 2>, k_icp<1024, 3>}};
+    if (nsub == 3) return k_icp<256, 3, 768>;   // developer (CUBOID_ICP_NSUB=3): three 256-thread sub-workers with 85 registers per thread
     return tab[nsub >= 4 ? 0 : (nsub == 2 ? 1 : 2)][mode];   // (eight 128-thread sub-workers were measured: 9.1 ms against 7.4 ms)
 }
 
@@ -513,6 +514,7 @@ int run_chunk(cuboid_handle* h, const ChunkIn& in, int nf, cuboid_frame_result* 
         const long long nprob = (long long)nf * ng;
         a.nsub = nprob > 2LL * a.crew ? 4 : (nprob > (long long)a.crew ? 2 : 1);
         if (h->icp_nsub_force) a.nsub = h->icp_nsub_force;
+        if (a.nsub == 3 && !a.tmode) a.nsub = 4;
         // time slicing evens out the tail when problems outnumber the sub-workers; with a sub-worker per problem nothing waits in the
         // queue, so a problem runs to the end in one slice (no state round trips through global memory)
         if (nprob * CUBOID_MAX_CLUSTERS <= (long long)a.crew * a.nsub || (p.use_cluster == 0 && nprob <= (long long)a.crew * a.nsub)) a.slice_iters = 1 << 28;
@@ -524,7 +526,7 @@ int run_chunk(cuboid_handle* h, const ChunkIn& in, int nf, cuboid_frame_result* 
         }
         k_icp_init<<<dim3(ng, CUBOID_MAX_CLUSTERS, nf), ICP_THREADS, a.init_smem, st>>>(a);
         auto kfn = icp_kernel(a.nsub, mode);
-        kfn<<<a.crew, ICP_NT, dyn, st>>>(a);   // workers beyond the number of real problems leave at once
+        kfn<<<a.crew, a.nsub == 3 ? 768 : ICP_NT, dyn, st>>>(a);   // workers beyond the number of real problems leave at once
         const int tot = nf * CUBOID_MAX_CLUSTERS;
         k_icp_select<<<(tot + 127) / 128, 128, 0, st>>>(b_out, d_res, nf, ng, p.icp_fitness_gate, guesses_override ? 0 : h->guess_offset);
         h->launches += 3;
@@ -677,7 +679,7 @@ static int create_impl(cuboid_handle** out, const cuboid_params* p, int device, 
     CA(ensure_icp_scratch(h, h->B, std::max(1, (int)p->n_guess)));
     cudaDeviceGetAttribute(&h->smem_optin, cudaDevAttrMaxSharedMemoryPerBlockOptin, device);
     h->icp_smem_budget = h->smem_optin - 9216;   // static shared memory of k_icp (up to 8 x IcpShared + hash / work partials) stays below 9 KB
-    for (int ns : {4, 2, 1})
+    for (int ns : {4, 3, 2, 1})
         for (int mode = 0; mode < 4; ++mode)
             if (cudaFuncSetAttribute(icp_kernel(ns, mode), cudaFuncAttributeMaxDynamicSharedMemorySize, h->icp_smem_budget) != cudaSuccess) return fail(CUBOID_E_CUDA);
     if (cudaFuncSetAttribute(k_icp_init, cudaFuncAttributeMaxDynamicSharedMemorySize, 65536) != cudaSuccess) return fail(CUBOID_E_CUDA);
@@ -687,7 +689,7 @@ static int create_impl(cuboid_handle** out, const cuboid_params* p, int device, 
         h->icp_ctas = sms;   // one 1024-thread CTA per SM
         const char* es = std::getenv("CUBOID_ICP_SLICE"); if (es) h->icp_slice_iters = std::max(1, atoi(es));
         const char* eo = std::getenv("CUBOID_ICP_OUTWARD"); if (eo) h->icp_outward = atoi(eo) ? 1 : 0;
-        const char* en = std::getenv("CUBOID_ICP_NSUB"); if (en) h->icp_nsub_force = (atoi(en) == 1 || atoi(en) == 2 || atoi(en) == 4) ? atoi(en) : 0;
+        const char* en = std::getenv("CUBOID_ICP_NSUB"); if (en) h->icp_nsub_force = (atoi(en) >= 1 && atoi(en) <= 4) ? atoi(en) : 0;
         const char* eq = std::getenv("CUBOID_ICP_QUEUED"); if (eq) h->icp_queued = atoi(eq) ? 1 : 0;
         const char* el = std::getenv("CUBOID_ICP_LOCAL"); if (el) h->icp_local = atoi(el) ? 1 : 0;
         const char* esg = std::getenv("CUBOID_ICP_SEEDGRID"); if (esg) h->icp_seed_grid = atoi(esg) ? 1 : 0;

@@ -1240,9 +1240,9 @@ __device__ __forceinline__ bool icp_slice(const IcpArgs& a, IcpShared& sh, const
 // Slicing bounds the tail: without it the kernel ends when the problem with the most iterations (40 .. 150 here) ends, with
 // most SMs idle by then. MODE 0: nodes only in shared memory (template through L1/L2); 1: resident template, per-lane walk;
 // 2: resident template + queued outward search (icp_nn_pass); 3: 2 + the nearest-neighbour candidate table in front of it.
-template <int SUB, int MODE>
-__global__ void __launch_bounds__(ICP_NT, 1) k_icp(const IcpArgs a) {
-    constexpr int NSUB = ICP_NT / SUB;
+template <int SUB, int MODE, int NT = ICP_NT>
+__global__ void __launch_bounds__(NT, 1) k_icp(const IcpArgs a) {
+    constexpr int NSUB = NT / SUB;
     extern __shared__ __align__(128) unsigned char smem_raw[];
     __shared__ IcpShared shs[NSUB];
     __shared__ int s_prob[NSUB];
@@ -1287,11 +1287,11 @@ __global__ void __launch_bounds__(ICP_NT, 1) k_icp(const IcpArgs a) {
         const int prob = s_prob[sub];
         if (prob < 0) break;
         bool finished;
-        if (MODE == 3 && SUB == ICP_NT) {   // one sub-worker per CTA: room for the problem's working set next to the template
+        if (MODE == 3 && SUB == NT) {   // one sub-worker per CTA: room for the problem's working set next to the template
             const int pc = (prob / a.n_guess) % CUBOID_MAX_CLUSTERS, pf = prob / (a.n_guess * CUBOID_MAX_CLUSTERS);
             const int* po = a.offsets + (size_t)pf * (a.KC + 1);
             const int pS = po[pc + 1] - po[pc];
-            unsigned char* s_local = reinterpret_cast<unsigned char*>(s_wscr + ICP_NT / 32);
+            unsigned char* s_local = reinterpret_cast<unsigned char*>(s_wscr + NT / 32);
             if (pS <= a.local_cap) finished = icp_slice<true, true, true, true, SUB>(a, sh, s_tmpl, s_nodes, s_sib, s_orig, wscr, s_local, prob, tid, sub, s_hh[sub], s_ev[sub]);
             else finished = icp_slice<true, true, true, false, SUB>(a, sh, s_tmpl, s_nodes, s_sib, s_orig, wscr, nullptr, prob, tid, sub, s_hh[sub], s_ev[sub]);
         } else {

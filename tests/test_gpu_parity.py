@@ -571,7 +571,7 @@ def test_icp_on_the_reference_real_scan_returns_the_published_pose(golden, param
     assert far["iters"] == ref_far["iters"] and far["corr_hash"] == ref_far["corr_hash"] and np.array_equal(bits(far["T"]), bits(ref_far["T"]))
 
 
-@pytest.mark.parametrize("knob,values", [("CUBOID_ICP_NSUB", ("1", "2", "4")), ("CUBOID_ICP_SLICE", ("1", "8", "5000")),
+@pytest.mark.parametrize("knob,values", [("CUBOID_ICP_NSUB", ("1", "2", "3", "4")), ("CUBOID_ICP_SLICE", ("1", "8", "5000")),
                                          ("CUBOID_ICP_OUTWARD", ("0", "1")), ("CUBOID_ICP_QUEUED", ("0", "1")), ("CUBOID_ICP_TABLE", ("0", "1")), ("CUBOID_FE_HASH", ("0", "1")), ("CUBOID_FE_ONEPASS", ("0", "1")), ("CUBOID_FE_RUNS", ("0", "1")), ("CUBOID_FE_SOLO", ("0", "1")), ("CUBOID_ICP_LOCAL", ("0", "1")), ("CUBOID_ICP_SEEDGRID", ("0", "1")), ("CUBOID_FE_CLUSTER_SMALL", ("1", "8")), ("CUBOID_SAC_WIDE", ("0", "1", "2")), ("CUBOID_NNT_H_MM", ("0.7", "2.5")),
                                          ("CUBOID_PIPELINE", ("0", "1"))])
 def test_execution_knobs_do_not_change_results(tmpl30, params, knob, values, monkeypatch):

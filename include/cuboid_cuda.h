@@ -78,7 +78,7 @@ typedef struct {
     int32_t icp_max_iter;                /* 5000          icp.cpp:173 */
     double icp_tf_eps;                   /* 1e-9          icp.cpp:174 */
     double icp_rel_mse;                  /* icp_fitness_score as setEuclideanFitnessEpsilon  icp.cpp:176 */
-    double icp_max_corr_dist;            /* sqrt(DBL_MAX): icp.cpp:175 is commented out; finite values are UNSUPPORTED */
+    double icp_max_corr_dist;            /* sqrt(DBL_MAX): icp.cpp:175 is commented out; a finite value drops the pairs beyond it */
     double icp_fitness_gate;             /* icp_fitness_score as the acceptance gate         icp.cpp:182 */
     int32_t n_guess;                     /* initial-pose hypotheses per cluster (>=1) in cuboid_process_* */
     int32_t guess_mode;                  /* 0: absolute 4x4 guesses; 1: 3x3 rotations about the cluster centroid */

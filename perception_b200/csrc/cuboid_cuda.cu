@@ -174,8 +174,8 @@ int validate_params(const cuboid_params* p) {
     if (!(p->sac_prob > 0.0 && p->sac_prob < 1.0)) return CUBOID_E_INVALID;
     // cluster.cuh: the fine-cell argument needs |coordinate / (0.52 tol)| < 5e5 (26 m at the smallest tolerance)
     if (p->use_cluster && !(p->cluster_tol >= 1e-4 && p->cluster_tol <= 1e3)) return CUBOID_E_INVALID;
-    // icp.cpp:175 leaves setMaxCorrespondenceDistance commented out; a distance gate that can actually reject is not built
-    if (!(p->icp_max_corr_dist * p->icp_max_corr_dist >= 3.0e38)) return CUBOID_E_UNSUPPORTED;
+    // icp.cpp:175 leaves setMaxCorrespondenceDistance commented out (default sqrt(DBL_MAX)); a finite distance runs k_icp's mode 4
+    if (!(p->icp_max_corr_dist > 0.0)) return CUBOID_E_INVALID;
     return CUBOID_OK;
 }
 
@@ -256,10 +256,10 @@ int ensure_ray_tables(cuboid_handle* h, int w, int hgt) {
 typedef void (*IcpKernel)(const IcpArgs);
 // k_icp<SUB, MODE>: nsub sub-workers per CTA (4, 2, 1 -> SUB 256, 512, 1024); mode 0 nodes only / 1 resident / 2 resident + queued search / 3 = 2 + candidate table
 IcpKernel icp_kernel(int nsub, int mode) {
-    static const IcpKernel tab[3][4] = {{k_icp<256, 0>, k_icp<256, 1>, k_icp<256, 2>, k_icp<256, 3>},
-                                        {k_icp<512, 0>, k_icp<512, 1>, k_icp<512, 2>, k_icp<512, 3>},
-                                        {k_icp<1024, 0>, k_icp<1024, 1>, k_icp<1024, 2>, k_icp<1024, 3>}};
-    if (nsub == 3) return k_icp<256, 3, 768>;   // developer (CUBOID_ICP_NSUB=3): three 256-thread sub-workers with 85 registers per thread
+    static const IcpKernel tab[3][5] = {{k_icp<256, 0>, k_icp<256, 1>, k_icp<256, 2>, k_icp<256, 3>, k_icp<256, 4>},
+                                        {k_icp<512, 0>, k_icp<512, 1>, k_icp<512, 2>, k_icp<512, 3>, k_icp<512, 4>},
+                                        {k_icp<1024, 0>, k_icp<1024, 1>, k_icp<1024, 2>, k_icp<1024, 3>, k_icp<1024, 4>}};
+    if (nsub == 3 && mode == 3) return k_icp<256, 3, 768>;   // developer (CUBOID_ICP_NSUB=3): three 256-thread sub-workers with 85 registers per thread
     return tab[nsub >= 4 ? 0 : (nsub == 2 ? 1 : 2)][mode];   // (eight 128-thread sub-workers were measured: 9.1 ms against 7.4 ms)
 }
 
@@ -486,6 +486,7 @@ int run_chunk(cuboid_handle* h, const ChunkIn& in, int nf, cuboid_frame_result* 
         a.hashes = h->taps ? 1 : 0;
         a.work = h->d_work; a.stats = h->d_stats;
         a.corr_trace = trace_corr; a.T_trace = trace_T; a.cap_trace = cap_trace;
+        const bool reject = !(p.icp_max_corr_dist * p.icp_max_corr_dist >= 3.0e38);   // a maximum correspondence distance that can reject
         {
             const size_t sbytes = (size_t)h->sib_bytes[tmpl_slot];
             a.sib = h->d_sib[tmpl_slot]; a.sib_max = h->sib_max[tmpl_slot]; a.sib_bytes = (int)sbytes;
@@ -493,7 +494,7 @@ int run_chunk(cuboid_handle* h, const ChunkIn& in, int nf, cuboid_frame_result* 
             if (a.sib_on) dyn += sbytes;
             const size_t qbytes = (size_t)a.Tpad * 2 + (size_t)(ICP_NT / 32) * sizeof(IcpWarpScr);
             a.orig16 = h->d_orig16[tmpl_slot];
-            a.qmode = (a.sib_on && a.cull && h->icp_queued && a.orig16 && dyn + qbytes <= (size_t)h->icp_smem_budget) ? 1 : 0;
+            a.qmode = (!reject && a.sib_on && a.cull && h->icp_queued && a.orig16 && dyn + qbytes <= (size_t)h->icp_smem_budget) ? 1 : 0;
             if (a.qmode) dyn += qbytes;
             a.tmode = (a.qmode && h->icp_table && h->d_nnt[tmpl_slot]) ? 1 : 0;
             a.tab = h->nnt[tmpl_slot];
@@ -514,11 +515,15 @@ int run_chunk(cuboid_handle* h, const ChunkIn& in, int nf, cuboid_frame_result* 
         const long long nprob = (long long)nf * ng;
         a.nsub = nprob > 2LL * a.crew ? 4 : (nprob > (long long)a.crew ? 2 : 1);
         if (h->icp_nsub_force) a.nsub = h->icp_nsub_force;
-        if (a.nsub == 3 && !a.tmode) a.nsub = 4;
         // time slicing evens out the tail when problems outnumber the sub-workers; with a sub-worker per problem nothing waits in the
         // queue, so a problem runs to the end in one slice (no state round trips through global memory)
         if (nprob * CUBOID_MAX_CLUSTERS <= (long long)a.crew * a.nsub || (p.use_cluster == 0 && nprob <= (long long)a.crew * a.nsub)) a.slice_iters = 1 << 28;
-        const int mode = a.tmode ? 3 : (a.qmode ? 2 : (a.resident ? 1 : 0));
+        // a finite setMaxCorrespondenceDistance (icp.cpp:175, commented out upstream): mode 4 = resident template, per-lane search, pairs
+        // beyond the distance dropped before the transformation estimate (templates too large for shared memory: unsupported)
+        a.max_d2 = p.icp_max_corr_dist * p.icp_max_corr_dist;
+        if (reject && !a.resident) return CUBOID_E_UNSUPPORTED;
+        const int mode = reject ? 4 : (a.tmode ? 3 : (a.qmode ? 2 : (a.resident ? 1 : 0)));
+        if (a.nsub == 3 && mode != 3) a.nsub = 4;
         a.local_cap = 0;
         if (mode == 3 && a.nsub == 1 && h->icp_local) {   // the rest of the shared memory holds the working set (24 B per point) of the CTA's problem
             a.local_cap = (int)std::min<size_t>(((size_t)h->icp_smem_budget - dyn) / 24, (size_t)h->M);
@@ -680,7 +685,7 @@ static int create_impl(cuboid_handle** out, const cuboid_params* p, int device, 
     cudaDeviceGetAttribute(&h->smem_optin, cudaDevAttrMaxSharedMemoryPerBlockOptin, device);
     h->icp_smem_budget = h->smem_optin - 9216;   // static shared memory of k_icp (up to 8 x IcpShared + hash / work partials) stays below 9 KB
     for (int ns : {4, 3, 2, 1})
-        for (int mode = 0; mode < 4; ++mode)
+        for (int mode = 0; mode < 5; ++mode)
             if (cudaFuncSetAttribute(icp_kernel(ns, mode), cudaFuncAttributeMaxDynamicSharedMemorySize, h->icp_smem_budget) != cudaSuccess) return fail(CUBOID_E_CUDA);
     if (cudaFuncSetAttribute(k_icp_init, cudaFuncAttributeMaxDynamicSharedMemorySize, 65536) != cudaSuccess) return fail(CUBOID_E_CUDA);
     {

@@ -87,6 +87,7 @@ struct IcpArgs {
     int nsub;                  // sub-workers per CTA (1 or 2)
     int init_smem;             // dynamic shared memory of k_icp_init (Morton sort window)
     int hashes;                // 1: accumulate corr_hash (parity tap); 0: leave it 0
+    double max_d2;             // setMaxCorrespondenceDistance squared (k_icp MODE 4 only: pairs beyond it are dropped, icp.cpp:175)
 };
 
 constexpr int ICP_THREADS = 512;   // k_icp_init's CTA size
@@ -993,7 +994,7 @@ __global__ void __launch_bounds__(ICP_THREADS) k_icp_init(const IcpArgs a) {
 
 // One time slice of one problem: up to a.slice_iters iterations of the ICP loop, then either the closing fitness pass
 // (problem finished) or a state save (problem goes back on the queue).
-template <bool RESIDENT, bool QUEUED, bool TABLE, bool LOCAL, int SUB>
+template <bool RESIDENT, bool QUEUED, bool TABLE, bool LOCAL, int SUB, bool REJECT = false>
 __device__ __forceinline__ bool icp_slice(const IcpArgs& a, IcpShared& sh, const float* s_tmpl, const uint4* s_nodes, const unsigned short* s_sib,
                                           const unsigned short* s_orig, IcpWarpScr* wscr, unsigned char* s_local, int prob, int tid, int sub,
                                           unsigned long long* s_hh, unsigned long long* s_ev) {
@@ -1064,18 +1065,56 @@ __device__ __forceinline__ bool icp_slice(const IcpArgs& a, IcpShared& sh, const
         }
         ++passes;
         if (tid == 0) sh.task = 0;
+        // REJECT (a finite setMaxCorrespondenceDistance): CorrespondenceEstimation drops the pairs beyond the distance and keeps the
+        // order of the rest; everything below then runs over that compacted list (its canonical lanes are positions IN the list).
+        int NC = S;
+        const int* list = nullptr;
+        if constexpr (REJECT) {
+            int* wl = a.miss + pbase;                                  // the table's miss list is free in this mode
+            int* s_cnt = reinterpret_cast<int*>(sh.part_f);            // [SUB / 32]
+            const int lane = tid & 31, wid = tid >> 5;
+            int base = 0;
+            for (int c0 = 0; c0 < S; c0 += SUB) {
+                const int i = c0 + tid;
+                const bool acc = i < S && !((double)icp_ld<LOCAL>(cd + i) > a.max_d2);
+                const unsigned int bal = __ballot_sync(FULL_MASK, acc);
+                if (lane == 0) s_cnt[wid] = __popc(bal);
+                sub_sync<SUB>(sub);
+                int before = 0, tot = 0;
+                for (int w = 0; w < SUB / 32; ++w) { const int c = s_cnt[w]; before += w < wid ? c : 0; tot += c; }
+                if (acc) wl[base + before + __popc(bal & ((1u << lane) - 1u))] = i;
+                base += tot;
+                sub_sync<SUB>(sub);
+            }
+            NC = base;
+            list = wl;
+            if (NC < 3) {              // "Not enough correspondences found": not converged, iteration not counted
+                if (tid == 0) { sh.done = 1; sh.converged = 0; sh.state = CUBOID_ICP_NO_CORRESPONDENCES; }
+                sub_sync<SUB>(sub);
+                break;
+            }
+            if (a.hashes || trace) {   // the parity taps see every source point; a dropped pair reads -1
+                for (int i = tid; i < S; i += SUB) {
+                    const int j = ((double)icp_ld<LOCAL>(cd + i) > a.max_d2) ? -1 : a.tmpl_orig[icp_ld<LOCAL>(corr + i)];
+                    chash += splitmix64((((unsigned long long)it * (unsigned long long)S + (unsigned long long)i) << 32) | (unsigned int)j);
+                    if (trace && it < a.cap_trace) a.corr_trace[(size_t)it * S + i] = j;
+                }
+            }
+        }
+        const float oon = REJECT ? 1.0f / (float)NC : one_over_n;
         // 2. means + MSE: the first 256 threads are the 256 canonical lanes
         for (int set = 0; set < LPT; ++set) {
             float q6[6] = {0.f, 0.f, 0.f, 0.f, 0.f, 0.f};
             double qd[1] = {0.0};
-            for (int i = canon ? tid + set * SUB : S; i < S; i += ICP_LANES) {
+            for (int ci = canon ? tid + set * SUB : NC; ci < NC; ci += ICP_LANES) {
+                const int i = REJECT ? __ldcg(list + ci) : ci;
                 const float4 p = icp_ld<LOCAL>(cur + i);
                 const int pos = icp_ld<LOCAL>(corr + i);
                 const float3 t = tmpl_point(tp, pos);
                 q6[0] = q6[0] + p.x; q6[1] = q6[1] + p.y; q6[2] = q6[2] + p.z;
                 q6[3] = q6[3] + t.x; q6[4] = q6[4] + t.y; q6[5] = q6[5] + t.z;
                 qd[0] = qd[0] + (double)icp_ld<LOCAL>(cd + i);
-                if (a.hashes || trace) {             // parity taps: the correspondence hash and the per-iteration trace
+                if (!REJECT && (a.hashes || trace)) {   // parity taps: the correspondence hash and the per-iteration trace
                     const int j = a.tmpl_orig[pos];  // original template index
                     chash += splitmix64((((unsigned long long)it * (unsigned long long)S + (unsigned long long)i) << 32) | (unsigned int)j);
                     if (trace && it < a.cap_trace) a.corr_trace[(size_t)it * S + i] = j;
@@ -1087,7 +1126,7 @@ __device__ __forceinline__ bool icp_slice(const IcpArgs& a, IcpShared& sh, const
         canon_sub_finish_fd<6, SUB>(sh.part_f, sh.red_f, sh.part_d, sh.red_d, tid, sub);
         float sm[3], dm[3];
 #pragma unroll
-        for (int k = 0; k < 3; ++k) { sm[k] = sh.red_f[k] * one_over_n; dm[k] = sh.red_f[3 + k] * one_over_n; }
+        for (int k = 0; k < 3; ++k) { sm[k] = sh.red_f[k] * oon; dm[k] = sh.red_f[3 + k] * oon; }
         const double mse_sum = sh.red_d[0];
         // (no barrier here: red_f / red_d are next written behind the first barrier of the covariance step's finish, part_f was read
         // in front of the second barrier of the finish above)
@@ -1096,7 +1135,8 @@ __device__ __forceinline__ bool icp_slice(const IcpArgs& a, IcpShared& sh, const
             float q9[9];
 #pragma unroll
             for (int k = 0; k < 9; ++k) q9[k] = 0.f;
-            for (int i = canon ? tid + set * SUB : S; i < S; i += ICP_LANES) {
+            for (int ci = canon ? tid + set * SUB : NC; ci < NC; ci += ICP_LANES) {
+                const int i = REJECT ? __ldcg(list + ci) : ci;
                 const float4 p = icp_ld<LOCAL>(cur + i);
                 const float3 t = tmpl_point(tp, icp_ld<LOCAL>(corr + i));
                 const float sd[3] = {p.x - sm[0], p.y - sm[1], p.z - sm[2]};
@@ -1115,7 +1155,7 @@ __device__ __forceinline__ bool icp_slice(const IcpArgs& a, IcpShared& sh, const
 #pragma unroll
             for (int r = 0; r < 3; ++r)
 #pragma unroll
-                for (int cc = 0; cc < 3; ++cc) sigma.a[r][cc] = one_over_n * sh.red_f[3 * r + cc];
+                for (int cc = 0; cc < 3; ++cc) sigma.a[r][cc] = oon * sh.red_f[3 * r + cc];
             jacobi_svd3(sigma, U, V);
             float Sg[3] = {1.f, 1.f, 1.f};
             if (det3(U) * det3(V) < 0.f) Sg[2] = -1.f;
@@ -1149,7 +1189,7 @@ __device__ __forceinline__ bool icp_slice(const IcpArgs& a, IcpShared& sh, const
                 if (cos_angle >= a.rot_thr && tsq <= a.trans_thr) { done = 1; sh.converged = 1; sh.state = CUBOID_ICP_TRANSFORM; }
             }
             if (!done) {
-                const double mse = mse_sum / (double)S;
+                const double mse = mse_sum / (double)NC;
                 if (fabs(mse - sh.prev_mse) < a.abs_thr) { done = 1; sh.converged = 1; sh.state = CUBOID_ICP_ABS_MSE; }
                 else if (fabs(mse - sh.prev_mse) / sh.prev_mse < a.rel_mse) { done = 1; sh.converged = 1; sh.state = CUBOID_ICP_REL_MSE; }
                 else sh.prev_mse = mse;
@@ -1239,7 +1279,8 @@ __device__ __forceinline__ bool icp_slice(const IcpArgs& a, IcpShared& sh, const
 // memory ONCE, then serves time slices of whatever problem is next on the queue until every problem of the launch is finished.
 // Slicing bounds the tail: without it the kernel ends when the problem with the most iterations (40 .. 150 here) ends, with
 // most SMs idle by then. MODE 0: nodes only in shared memory (template through L1/L2); 1: resident template, per-lane walk;
-// 2: resident template + queued outward search (icp_nn_pass); 3: 2 + the nearest-neighbour candidate table in front of it.
+// 2: resident template + queued outward search (icp_nn_pass); 3: 2 + the nearest-neighbour candidate table in front of it;
+// 4: 1 + a finite maximum correspondence distance (pairs beyond it dropped: the compacted-list path of icp_slice).
 template <int SUB, int MODE, int NT = ICP_NT>
 __global__ void __launch_bounds__(NT, 1) k_icp(const IcpArgs a) {
     constexpr int NSUB = NT / SUB;
@@ -1254,7 +1295,7 @@ __global__ void __launch_bounds__(NT, 1) k_icp(const IcpArgs a) {
     const unsigned int tb = MODE >= 1 ? (unsigned int)a.Tpad * 12u : 0u;
     const unsigned int bb = (unsigned int)a.nnodes * 16u;
     const unsigned int sb = (MODE >= 1 && a.sib_on) ? (unsigned int)a.sib_bytes : 0u;
-    const unsigned int ob = MODE >= 2 ? (unsigned int)a.Tpad * 2u : 0u;
+    const unsigned int ob = (MODE == 2 || MODE == 3) ? (unsigned int)a.Tpad * 2u : 0u;
     const unsigned short* s_sib = reinterpret_cast<const unsigned short*>(reinterpret_cast<unsigned char*>(s_tmpl) + tb);
     const unsigned short* s_orig = reinterpret_cast<const unsigned short*>(reinterpret_cast<unsigned char*>(s_tmpl) + tb + sb);
     IcpWarpScr* s_wscr = reinterpret_cast<IcpWarpScr*>(reinterpret_cast<unsigned char*>(s_tmpl) + tb + sb + ob);
@@ -1295,7 +1336,7 @@ __global__ void __launch_bounds__(NT, 1) k_icp(const IcpArgs a) {
             if (pS <= a.local_cap) finished = icp_slice<true, true, true, true, SUB>(a, sh, s_tmpl, s_nodes, s_sib, s_orig, wscr, s_local, prob, tid, sub, s_hh[sub], s_ev[sub]);
             else finished = icp_slice<true, true, true, false, SUB>(a, sh, s_tmpl, s_nodes, s_sib, s_orig, wscr, nullptr, prob, tid, sub, s_hh[sub], s_ev[sub]);
         } else {
-            finished = icp_slice<(MODE >= 1), (MODE >= 2), (MODE == 3), false, SUB>(a, sh, s_tmpl, s_nodes, s_sib, s_orig, wscr, nullptr, prob, tid, sub, s_hh[sub], s_ev[sub]);
+            finished = icp_slice<(MODE >= 1), (MODE == 2 || MODE == 3), (MODE == 3), false, SUB, (MODE == 4)>(a, sh, s_tmpl, s_nodes, s_sib, s_orig, wscr, nullptr, prob, tid, sub, s_hh[sub], s_ev[sub]);
         }
         if (tid == 0) {
             __threadfence();   // state / outputs before the hand-over

@@ -287,6 +287,56 @@ def test_icp_edge_cases(cc, tmpl30):
     assert e.value.status == api.E_NO_TEMPLATE
 
 
+@pytest.mark.parametrize("maxd,near", [(10.0, False), (0.49, False), (0.45, False), (0.43, False), (0.008, True), (0.005, True), (0.003, True), (1e-6, True)])
+def test_icp_finite_max_correspondence_distance(cc, stage_data, tmpl30, maxd, near):
+    """icp.setMaxCorrespondenceDistance (iterative_closest_point.cpp:175, commented out upstream: the default is sqrt(DBL_MAX)).
+    With a finite distance CorrespondenceEstimation drops the pairs beyond it, the transformation estimate and the MSE run over the
+    rest in their original order, and fewer than 3 pairs end ICP unconverged. Every iteration's correspondences (-1 = dropped) and
+    transformation, the final transformation, the aligned cloud and the fitness must equal the oracle's: from the identity (the cloud
+    is half a metre from the template: distances that drop nothing, 227, 1356 and all of the 1410 pairs of the first iteration) and
+    from a guess 6 mm off the aligned pose (distances that keep dropping tens to hundreds of pairs in every iteration)."""
+    src = stage_data["remain"][stage_data["cidx"]]
+    G = None
+    if near:
+        G = O.icp(src, tmpl30)["T"].copy()
+        G[:3, 3] += np.float32(0.006)
+    o = O.icp(src, tmpl30, guess=G, max_corr_dist=maxd, trace_iters=160)
+    p = default_params("cuboid")
+    p.icp_max_corr_dist = maxd
+    cc.set_params(p)
+    try:
+        g = cc.icp(src, 0, guesses=None if G is None else [G], trace_iters=160)
+    finally:
+        cc.set_params(default_params("cuboid"))
+    assert (g["iters"], g["state"], g["converged"]) == (o["iters"], o["state"], o["converged"])
+    n = min(o["iters"], 160)
+    assert np.array_equal(g["corr_trace"][:n], o["corr_trace"][:n])
+    assert np.array_equal(bits(g["T_trace"][:n]), bits(o["T_trace"][:n]))
+    assert g["corr_hash"] == o["corr_hash"]
+    assert np.array_equal(bits(g["T"]), bits(o["T"])) and np.array_equal(bits(g["aligned"]), bits(o["aligned"]))
+    assert g["fitness"] == o["fitness"]
+    if maxd in (0.43, 1e-6):
+        assert (g["iters"], g["state"], g["converged"]) == (0, 5, 0)
+    elif maxd < 10.0:
+        assert (o["corr_trace"][0] < 0).any()                 # the distance really rejects on this cloud
+
+
+def test_process_batch_with_a_finite_max_correspondence_distance(tmpl30):
+    """The whole-frame entry with the same parameter: results equal the oracle's frame by frame (one distance under which ICP still
+    converges with part of the first iteration's pairs dropped, one under which it finds no correspondences at all)."""
+    depth = synth.depth_batch("bench", [20, 21, 22])
+    for maxd in (0.47, 0.2):
+        p = default_params("cuboid")
+        p.icp_max_corr_dist = maxd
+        with api.CuboidCuda(p, max_points=640 * 480, max_batch=3) as h:
+            h.set_template(0, tmpl30)
+            res = h.process_batch(depth)
+        for i in range(3):
+            _same_frame(res[i], O.process_frame(p, depth[i], tmpl30))
+        if maxd == 0.2:
+            assert all(r.cluster[0].state == 5 and not r.cluster[0].converged for r in res)
+
+
 def test_process_batch_matches_oracle_frame_by_frame(cc, tmpl30, params):
     seeds = [0, 1, 2, 3, 4]
     depth = synth.depth_batch("bench", seeds)

@@ -292,6 +292,7 @@ __device__ __forceinline__ void canon_block_reduce(Tq (&v)[NQ], Tq* s_part /* [N
 template <typename Tq, int NQ, int SUB>
 __device__ __forceinline__ void canon_sub_partial(Tq (&v)[NQ], Tq* s_part /* [NQ][8] */, int tid, int set) {
     const int lane = tid & 31, wid = tid >> 5;
+    if (SUB > ICP_LANES && wid >= ICP_LANES / 32) return;   // (warp-uniform) only the canonical warps hold anything: the others would shuffle zeros
 #pragma unroll
     for (int q = 0; q < NQ; ++q) {
         Tq x = v[q];

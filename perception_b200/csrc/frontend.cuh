@@ -18,6 +18,7 @@
 // Roofline: HBM. Algorithmic bytes per frame = 2*P + 16*N (a0+a1) + 16*N + 16*V (a2).
 #pragma once
 #include <cooperative_groups.h>
+#include <type_traits>
 
 #include "common.cuh"
 #include "preprocess.cuh"
@@ -182,9 +183,13 @@ __device__ __forceinline__ float fe_add_zeros(float s, bool any_plus_zero) {
 // lanes of the warp holding the same 8-bit digit (256 = "no record": never equal to a real digit's peers that matter).
 // Eight votes: MATCH.ANY costs ~2 cycles per DISTINCT value per SM (measured, tools/microbench/match_bench.cu), which
 // is several times more than this for the scattered digits of the later radix passes.
+template <bool ALL_VALID = false>   // ALL_VALID: every lane holds a record (a full tile): no vote on that
 __device__ __forceinline__ unsigned int fe_digit_peers(unsigned int d) {
-    unsigned int peers = __ballot_sync(FULL_MASK, d < 256u);
-    if (d >= 256u) peers = ~peers;
+    unsigned int peers = FULL_MASK;
+    if (!ALL_VALID) {
+        peers = __ballot_sync(FULL_MASK, d < 256u);
+        if (d >= 256u) peers = ~peers;
+    }
 #pragma unroll
     for (int b = 0; b < 8; ++b) {
         const unsigned int bit = (d >> b) & 1u;
@@ -1007,19 +1012,23 @@ __global__ void __launch_bounds__(NT, NT <= 256 ? 4 : (NT <= 512 ? 2 : 1)) k_fro
                 }
                 __syncwarp();
                 prefetch(t0 + TILE, 0);   // in flight while this tile is ranked and scattered
+                auto rank_tile = [&](auto all_valid) {   // all but the last tile of a range are full: their lanes need no validity vote
+                    constexpr bool ALL = decltype(all_valid)::value;
 #pragma unroll
-                for (int k = 0; k < FE_ITEMS; ++k) {
-                    const int i = t0 + wid * (32 * FE_ITEMS) + k * 32 + lane;
-                    const bool valid = i < q1;
-                    const unsigned int d = valid ? ((unsigned int)(key[k] >> shift) & 255u) : 256u;
-                    const unsigned int peers = fe_digit_peers(d);
-                    const int leader = __ffs(peers) - 1;
-                    unsigned int before = 0;
-                    if (valid && lane == leader) { before = s_cnt[wid][d]; s_cnt[wid][d] = before + __popc(peers); }
-                    before = __shfl_sync(FULL_MASK, before, leader);
-                    rank[k] = before + __popc(peers & ((1u << lane) - 1u));
-                    __syncwarp();
-                }
+                    for (int k = 0; k < FE_ITEMS; ++k) {
+                        const int i = t0 + wid * (32 * FE_ITEMS) + k * 32 + lane;
+                        const bool valid = ALL || i < q1;
+                        const unsigned int d = valid ? ((unsigned int)(key[k] >> shift) & 255u) : 256u;
+                        const unsigned int peers = fe_digit_peers<ALL>(d);
+                        const int leader = __ffs(peers) - 1;
+                        unsigned int before = 0;
+                        if (valid && lane == leader) { before = s_cnt[wid][d]; s_cnt[wid][d] = before + __popc(peers); }
+                        before = __shfl_sync(FULL_MASK, before, leader);
+                        rank[k] = before + __popc(peers & ((1u << lane) - 1u));
+                        __syncwarp();
+                    }
+                };
+                if (full) rank_tile(std::true_type{}); else rank_tile(std::false_type{});
                 __syncthreads();
                 if (tid < 256) {
                     unsigned int run = s_base[tid];

@@ -337,7 +337,7 @@ int run_chunk(cuboid_handle* h, const ChunkIn& in, int nf, cuboid_frame_result* 
             }
             if (ok && bits[0] + bits[1] + bits[2] <= 32 && dims <= 2147483647LL) {
                 fa.st_on = 1; fa.st_b0 = bits[0]; fa.st_b1 = bits[0] + bits[1]; fa.st_bits = bits[0] + bits[1] + bits[2];
-                fa.runs = (h->fe_runs && h->P < (1 << 27)) ? 1 : 0;   // a run record keeps its first point in 27 bits
+                fa.runs = (h->fe_runs && h->fe_threads == 512 && h->P < (1 << 27)) ? 1 : 0;   // a run record keeps its first point in 27 bits; tested with 512-thread CTAs
             }
         }
         cudaLaunchConfig_t cfg{};

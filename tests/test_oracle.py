@@ -162,6 +162,35 @@ def test_icp_nn_equals_bruteforce_lowest_index(tmpl30):
     assert np.array_equal(r["corr_trace"][0], d2.argmin(axis=1))   # argmin returns the first (lowest) index on ties
 
 
+def test_icp_max_correspondence_distance_drops_pairs_like_correspondence_estimation(tmpl30):
+    """setMaxCorrespondenceDistance (icp.cpp:175, commented out upstream). PCL's CorrespondenceEstimation::determineCorrespondences
+    skips a source point whose nearest squared distance is greater than max_dist^2 ([PCL-recall]); the transformation is estimated
+    from the remaining pairs in their order, and fewer than 3 pairs (min_number_correspondences_) end ICP unconverged. Checked
+    against a brute-force float32 scan and a float64 Kabsch fit of the kept pairs."""
+    rng = np.random.default_rng(21)
+    src = np.ones((400, 4), np.float32)
+    src[:, :3] = tmpl30[rng.integers(0, len(tmpl30), 400), :3] + rng.normal(0, 0.004, (400, 3)).astype(np.float32)
+    maxd = 0.005
+    r = O.icp(src, tmpl30, max_iter=1, max_corr_dist=maxd, trace_iters=1)
+    d = src[:, None, :3] - tmpl30[None, :, :3]
+    d2 = (d[..., 0] * d[..., 0] + d[..., 1] * d[..., 1]).astype(np.float32) + d[..., 2] * d[..., 2]
+    nn, dmin = d2.argmin(axis=1), d2.min(axis=1)
+    keep = ~(dmin.astype(np.float64) > maxd * maxd)
+    assert 20 < keep.sum() < 380                                           # the distance rejects, and not everything
+    assert np.array_equal(r["corr_trace"][0], np.where(keep, nn, -1))
+    a, b = src[keep, :3].astype(np.float64), tmpl30[nn[keep], :3].astype(np.float64)   # Kabsch on the kept pairs only
+    ca, cb = a.mean(0), b.mean(0)
+    U, _, Vt = np.linalg.svd((b - cb).T @ (a - ca))
+    S = np.diag([1.0, 1.0, np.sign(np.linalg.det(U) * np.linalg.det(Vt))])
+    R = U @ S @ Vt
+    assert np.allclose(r["T"][:3, :3], R, atol=2e-5) and np.allclose(r["T"][:3, 3], cb - R @ ca, atol=2e-6)
+    far = O.icp(src, tmpl30, max_corr_dist=1e-7)
+    assert (far["iters"], far["state"], far["converged"]) == (0, 5, 0) and np.array_equal(far["T"], np.eye(4, dtype=np.float32))
+    same = O.icp(src, tmpl30, max_corr_dist=10.0)
+    dflt = O.icp(src, tmpl30)
+    assert same["corr_hash"] == dflt["corr_hash"] and np.array_equal(bits(same["T"]), bits(dflt["T"]))
+
+
 def test_icp_edge_cases(tmpl30):
     r = O.icp(tmpl30[:2], tmpl30)
     assert not r["converged"] and r["iters"] == 0 and r["state"] == 5 and np.array_equal(r["T"], np.eye(4, dtype=np.float32))
